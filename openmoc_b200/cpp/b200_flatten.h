@@ -1,0 +1,78 @@
+/**
+ * @file b200_flatten.h
+ * @brief Flattens an OpenMOC TrackGenerator(3D) into the SoA arrays that the
+ *        B200 sweep kernels consume (the arguments of b200_upload_* in
+ *        include/b200moc.h) and reads/writes them as a "B2TRK" track file.
+ *
+ * This file is PLUG-IN code: it is compiled against the reference's headers
+ * (src/TraverseSegments.h, src/TrackGenerator3D.h ...) and lives on the
+ * OpenMOC side of the C-ABI.  It replaces the per-track clone_track() /
+ * cudaMalloc loop of the reference GPUSolver (src/accel/cuda/clone.cu:86-126)
+ * by a single pass over TraverseSegments::loopOverTracks (the same traversal
+ * TransportSweep uses, src/TrackTraversingAlgorithms.cpp:866-879), so all four
+ * segmentation modes (EXPLICIT_2D/3D, OTF_TRACKS, OTF_STACKS) flatten the same
+ * way.
+ */
+#ifndef B200_FLATTEN_H_
+#define B200_FLATTEN_H_
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+class TrackGenerator;
+class Geometry;
+
+/** Host-side SoA image of everything the sweep path reads. */
+struct B200FlatTracks {
+  /* problem shape */
+  int num_groups = 0;
+  int num_azim = 0;        /* full number of azimuthal angles (A) */
+  int num_polar = 0;       /* full number of polar angles (P) */
+  int solve_3d = 0;
+  int fluxes_per_track = 0; /* F: G*P/2 in 2D, G in 3D (Solver.cpp:432-449) */
+  int64_t n_tracks = 0, n_segments = 0, n_fsrs = 0;
+  int n_materials = 0;
+
+  /* segment stream, contiguous per track, forward order */
+  std::vector<double> seg_length;
+  std::vector<int32_t> seg_fsr;
+  std::vector<int32_t> seg_mat;
+  std::vector<int32_t> seg_cmfd_fwd, seg_cmfd_bwd;
+  std::vector<double> seg_start;  /* xyz relative to FSR centroid (LS) */
+
+  /* per track, indexed by Track uid */
+  std::vector<int64_t> trk_seg_offset;  /* n_tracks + 1 */
+  std::vector<int32_t> trk_azim, trk_polar, trk_xy;
+  std::vector<int64_t> trk_next_fwd, trk_next_bwd;
+  std::vector<uint8_t> trk_flags;   /* bit0 next_fwd_is_fwd, bit1 next_bwd_is_fwd */
+  std::vector<uint8_t> trk_bc_fwd, trk_bc_bwd;  /* boundaryType enum values */
+  std::vector<double> trk_phi, trk_theta;
+
+  /* quadrature: [A/2][P] total weights, [A/2][P] sin(theta) */
+  std::vector<double> quad_weight, quad_sin_theta;
+
+  /* FSR data */
+  std::vector<double> fsr_volume;
+  std::vector<int32_t> fsr_mat;
+  std::vector<double> fsr_centroid; /* xyz */
+
+  /* material tables [n_materials][...] in the reference's storage order */
+  std::vector<double> mat_sigma_t, mat_sigma_a, mat_sigma_f, mat_nu_sigma_f, mat_chi;
+  std::vector<double> mat_sigma_s;      /* [dest*G+orig]  (Material.cpp:728-731) */
+  std::vector<double> mat_fiss_matrix;  /* [G_dest*G+g_orig] (Material.cpp:975-978) */
+  std::vector<uint8_t> mat_fissionable;
+};
+
+/**
+ * Flatten the tracks of a TrackGenerator whose segments are final, i.e. after
+ * Solver::initializeFSRs() and Solver::initializeExpEvaluators() have run
+ * (centroid re-centring and tau>max splitting mutate segments).
+ */
+void b200_flatten(TrackGenerator* track_generator, B200FlatTracks* out,
+                  bool with_ls_data = true);
+
+/** Write / read the chunked binary track file (see openmoc_b200/trackfile.py). */
+void b200_write_trackfile(const B200FlatTracks& ft, const std::string& path);
+
+#endif /* B200_FLATTEN_H_ */

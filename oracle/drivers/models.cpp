@@ -1,0 +1,321 @@
+/**
+ * @file models.cpp
+ * @brief See models.h.  Our own C++ restatement of the reference's Python
+ *        input decks (the Python module cannot be built here: no swig).
+ */
+#include "models.h"
+
+#include <vector>
+
+#include "Geometry.h"
+#include "Universe.h"
+#include "Cell.h"
+#include "Surface.h"
+#include "Material.h"
+#include "c5g7_xs.h"
+
+namespace {
+
+std::map<std::string, Material*> make_c5g7_materials() {
+  std::map<std::string, Material*> out;
+  for (int i = 0; i < c5g7::num_materials; i++) {
+    const c5g7::XS& x = c5g7::materials[i];
+    Material* m = new Material(i + 1, x.name);
+    m->setNumEnergyGroups(c5g7::G);
+    m->setSigmaT(const_cast<double*>(x.sigma_t), c5g7::G);
+    m->setSigmaS(const_cast<double*>(x.sigma_s), c5g7::G * c5g7::G);
+    m->setSigmaF(const_cast<double*>(x.sigma_f), c5g7::G);
+    m->setNuSigmaF(const_cast<double*>(x.nu_sigma_f), c5g7::G);
+    m->setChi(const_cast<double*>(x.chi), c5g7::G);
+    out[x.name] = m;
+  }
+  return out;
+}
+
+void fill_lattice(Lattice* lat, int ny, int nx, const std::vector<Universe*>& rows_top_down) {
+  /* rows_top_down is row-major starting at the upper-left corner, exactly the
+   * nested-list convention of Lattice::setUniverses (Universe.cpp:1604-1616) */
+  std::vector<Universe*> tmp(rows_top_down);
+  lat->setUniverses(1, ny, nx, tmp.data());
+}
+
+/* ---------------- tests/input_set.py:95-137 ---------------- */
+Model pin_cell(int dims) {
+  Model md;
+  md.materials = make_c5g7_materials();
+  ZCylinder* zcyl = new ZCylinder(0.0, 0.0, 1.0);
+  XPlane* xmin = new XPlane(-2.0); XPlane* xmax = new XPlane(2.0);
+  YPlane* ymin = new YPlane(-2.0); YPlane* ymax = new YPlane(2.0);
+  xmin->setBoundaryType(REFLECTIVE); xmax->setBoundaryType(REFLECTIVE);
+  ymin->setBoundaryType(REFLECTIVE); ymax->setBoundaryType(REFLECTIVE);
+
+  Cell* fuel = new Cell();
+  fuel->setFill(md.materials["UO2"]);
+  fuel->addSurface(-1, zcyl);
+  Cell* moderator = new Cell();
+  moderator->setFill(md.materials["Water"]);
+  moderator->addSurface(+1, zcyl);
+  moderator->addSurface(+1, xmin); moderator->addSurface(-1, xmax);
+  moderator->addSurface(+1, ymin); moderator->addSurface(-1, ymax);
+  if (dims == 3) {
+    ZPlane* zmin = new ZPlane(-2.0); ZPlane* zmax = new ZPlane(2.0);
+    zmin->setBoundaryType(REFLECTIVE); zmax->setBoundaryType(REFLECTIVE);
+    fuel->addSurface(+1, zmin); fuel->addSurface(-1, zmax);
+    moderator->addSurface(+1, zmin); moderator->addSurface(-1, zmax);
+  }
+  Universe* root = new Universe();
+  root->addCell(fuel);
+  root->addCell(moderator);
+  md.geometry = new Geometry();
+  md.geometry->setRootUniverse(root);
+  return md;
+}
+
+/* ---------------- tests/input_set.py:310-417 ---------------- */
+Model simple_lattice(int dims) {
+  Model md;
+  md.materials = make_c5g7_materials();
+  XPlane* xmin = new XPlane(-2.0); XPlane* xmax = new XPlane(2.0);
+  YPlane* ymin = new YPlane(-2.0); YPlane* ymax = new YPlane(2.0);
+  xmin->setBoundaryType(REFLECTIVE); xmax->setBoundaryType(REFLECTIVE);
+  ymin->setBoundaryType(REFLECTIVE); ymax->setBoundaryType(REFLECTIVE);
+
+  const double radii[3] = {0.4, 0.3, 0.2};
+  Universe* pins[3];
+  for (int i = 0; i < 3; i++) {
+    ZCylinder* cyl = new ZCylinder(0.0, 0.0, radii[i]);
+    Cell* fuel = new Cell();
+    fuel->setNumRings(3);
+    fuel->setNumSectors(8);
+    fuel->setFill(md.materials["UO2"]);
+    fuel->addSurface(-1, cyl);
+    Cell* mod = new Cell();
+    mod->setNumSectors(8);
+    mod->setFill(md.materials["Water"]);
+    mod->addSurface(+1, cyl);
+    pins[i] = new Universe();
+    pins[i]->addCell(fuel);
+    pins[i]->addCell(mod);
+  }
+
+  Cell* lattice_cell = new Cell();
+  Cell* root_cell = new Cell();
+  root_cell->addSurface(+1, xmin); root_cell->addSurface(-1, xmax);
+  root_cell->addSurface(+1, ymin); root_cell->addSurface(-1, ymax);
+  if (dims == 3) {
+    ZPlane* zmin = new ZPlane(-5.0); ZPlane* zmax = new ZPlane(5.0);
+    zmin->setBoundaryType(REFLECTIVE);
+    zmax->setBoundaryType(VACUUM);
+    root_cell->addSurface(+1, zmin); root_cell->addSurface(-1, zmax);
+  }
+  Universe* assembly = new Universe();
+  Universe* root = new Universe();
+  assembly->addCell(lattice_cell);
+  root->addCell(root_cell);
+
+  Lattice* lattice = new Lattice();
+  lattice->setWidth(1.0, 1.0);
+  fill_lattice(lattice, 2, 2, {pins[0], pins[1], pins[0], pins[2]});
+  lattice_cell->setFill(lattice);
+
+  Lattice* core = new Lattice();
+  core->setWidth(2.0, 2.0);
+  fill_lattice(core, 2, 2, {assembly, assembly, assembly, assembly});
+  root_cell->setFill(core);
+
+  md.geometry = new Geometry();
+  md.geometry->setRootUniverse(root);
+  return md;
+}
+
+/* ---------------- tests/input_set.py:32-92 ---------------- */
+Model hom_inf(int) {
+  Model md;
+  double sigma_f[2] = {0.000625, 0.135416667};
+  double nu_sigma_f[2] = {0.0015, 0.325};
+  double sigma_s[4] = {0.1, 0.117, 0., 1.42};
+  double chi[2] = {1.0, 0.0};
+  double sigma_t[2] = {0.2208, 1.604};
+  Material* m = new Material(1, "2-group infinite medium");
+  m->setNumEnergyGroups(2);
+  m->setSigmaF(sigma_f, 2); m->setNuSigmaF(nu_sigma_f, 2);
+  m->setSigmaS(sigma_s, 4); m->setChi(chi, 2); m->setSigmaT(sigma_t, 2);
+  md.materials["infinite medium"] = m;
+
+  const double length = 2.5; const int n = 10;
+  XPlane* xmin = new XPlane(-length / 2.); XPlane* xmax = new XPlane(length / 2.);
+  YPlane* ymin = new YPlane(-length / 2.); YPlane* ymax = new YPlane(length / 2.);
+  xmin->setBoundaryType(REFLECTIVE); xmax->setBoundaryType(REFLECTIVE);
+  ymin->setBoundaryType(REFLECTIVE); ymax->setBoundaryType(REFLECTIVE);
+  Cell* fill = new Cell();
+  fill->setFill(m);
+  Cell* root_cell = new Cell();
+  root_cell->addSurface(+1, xmin); root_cell->addSurface(-1, xmax);
+  root_cell->addSurface(+1, ymin); root_cell->addSurface(-1, ymax);
+  Universe* fill_u = new Universe();
+  fill_u->addCell(fill);
+  Universe* root = new Universe();
+  root->addCell(root_cell);
+  Lattice* lat = new Lattice();
+  lat->setWidth(length / n, length / n);
+  fill_lattice(lat, n, n, std::vector<Universe*>(n * n, fill_u));
+  root_cell->setFill(lat);
+  md.geometry = new Geometry();
+  md.geometry->setRootUniverse(root);
+  return md;
+}
+
+/* ------- sample-input/benchmarks/c5g7/{surfaces,cells,universes,lattices,c5g7-2d}.py ------- */
+Model c5g7_2d(int) {
+  Model md;
+  md.materials = make_c5g7_materials();
+  std::map<std::string, Material*>& M = md.materials;
+
+  XPlane* xmin = new XPlane(-32.13); XPlane* xmax = new XPlane(32.13);
+  YPlane* ymin = new YPlane(-32.13); YPlane* ymax = new YPlane(32.13);
+  xmin->setBoundaryType(REFLECTIVE); xmax->setBoundaryType(VACUUM);   /* surfaces.py:24-27 */
+  ymin->setBoundaryType(VACUUM);     ymax->setBoundaryType(REFLECTIVE);
+  ZCylinder* fuel_cyl = new ZCylinder(0.0, 0.0, 0.54);
+
+  const int fuel_rings = 5, num_sectors = 4;   /* cells.py:6-8 */
+
+  /* one shared moderator cell (8 sectors), cells.py:91,105 */
+  Cell* moderator = new Cell();
+  moderator->setFill(M["Water"]);
+  moderator->setNumSectors(8);
+  moderator->addSurface(+1, fuel_cyl);
+
+  struct PinSpec { const char* mat; bool rings; };
+  /* u, m, o, x: fuel pins without rings; g, f, p: 5 rings (cells.py:73-91) */
+  const PinSpec specs[7] = {{"UO2", false}, {"MOX-4.3%", false}, {"MOX-7%", false},
+                            {"MOX-8.7%", false}, {"Guide Tube", true},
+                            {"Fission Chamber", true}, {"Water", true}};
+  Universe* pin[7];
+  for (int i = 0; i < 7; i++) {
+    Cell* c = new Cell();
+    c->setFill(M[specs[i].mat]);
+    if (specs[i].rings) c->setNumRings(fuel_rings);
+    c->setNumSectors(num_sectors);
+    c->addSurface(-1, fuel_cyl);
+    pin[i] = new Universe();
+    pin[i]->addCell(c);
+    pin[i]->addCell(moderator);
+  }
+  Universe *u = pin[0], *m = pin[1], *o = pin[2], *x = pin[3], *g = pin[4], *f = pin[5];
+
+  /* plain reflector cell and its 3x3 refined mesh (lattices.py:52-58) */
+  Cell* reflector = new Cell();
+  reflector->setFill(M["Water"]);
+  Universe* r = new Universe();
+  r->addCell(reflector);
+  Lattice* refined = new Lattice();
+  refined->setWidth(1.26 / 3, 1.26 / 3, 100.);
+  fill_lattice(refined, 3, 3, std::vector<Universe*>(9, r));
+  Cell* refined_cell = new Cell();
+  refined_cell->setFill(refined);
+  Universe* a = new Universe();
+  a->addCell(refined_cell);
+
+  /* 17x17 assemblies (lattices.py:60-82 and 108-130) */
+  Universe* uo2_t[17 * 17];
+  Universe* mox_t[17 * 17];
+  const char* guide_rows[17] = {
+      ".................", ".................", ".....g..g..g.....", "...g.........g...",
+      ".................", "..g..g..g..g..g..", ".................", ".................",
+      "..g..g..f..g..g..", ".................", ".................", "..g..g..g..g..g..",
+      ".................", "...g.........g...", ".....g..g..g.....", ".................",
+      "................."};
+  const char* mox_rows[17] = {
+      "mmmmmmmmmmmmmmmmm", "mooooooooooooooom", "mooooooooooooooom", "mooooxxxxxxxoooom",
+      "moooxxxxxxxxxooom", "mooxxxxxxxxxxxoom", "mooxxxxxxxxxxxoom", "mooxxxxxxxxxxxoom",
+      "mooxxxxxxxxxxxoom", "mooxxxxxxxxxxxoom", "mooxxxxxxxxxxxoom", "mooxxxxxxxxxxxoom",
+      "moooxxxxxxxxxooom", "mooooxxxxxxxoooom", "mooooooooooooooom", "mooooooooooooooom",
+      "mmmmmmmmmmmmmmmmm"};
+  for (int j = 0; j < 17; j++)
+    for (int i = 0; i < 17; i++) {
+      char gt = guide_rows[j][i];
+      Universe* tube = (gt == 'g') ? g : (gt == 'f') ? f : NULL;
+      uo2_t[j * 17 + i] = tube ? tube : u;
+      char mc = mox_rows[j][i];
+      mox_t[j * 17 + i] = tube ? tube : (mc == 'm') ? m : (mc == 'o') ? o : x;
+    }
+
+  auto make_assembly = [&](const std::vector<Universe*>& t) {
+    Lattice* lat = new Lattice();
+    lat->setWidth(1.26, 1.26, 100.);
+    fill_lattice(lat, 17, 17, t);
+    Cell* c = new Cell();
+    c->setFill(lat);
+    Universe* uni = new Universe();
+    uni->addCell(c);
+    return uni;
+  };
+  Universe* uu = make_assembly(std::vector<Universe*>(uo2_t, uo2_t + 289));
+  Universe* mu = make_assembly(std::vector<Universe*>(mox_t, mox_t + 289));
+
+  /* reflector assemblies (lattices.py:180-199) */
+  std::vector<Universe*> right(289), bottom(289), corner(289);
+  for (int j = 0; j < 17; j++)
+    for (int i = 0; i < 17; i++) {
+      right[j * 17 + i] = (i < 11) ? a : r;
+      bottom[j * 17 + i] = (j < 11) ? a : r;
+      corner[j * 17 + i] = (j < 11 && i < 11) ? a : r;
+    }
+  Universe* ri = make_assembly(right);
+  Universe* rb = make_assembly(bottom);
+  Universe* rc = make_assembly(corner);
+
+  /* c5g7-2d.py:34-37 */
+  Lattice* root_lat = new Lattice();
+  root_lat->setWidth(21.42, 21.42);
+  fill_lattice(root_lat, 3, 3, {uu, mu, ri, mu, uu, ri, rb, rb, rc});
+  Cell* root_cell = new Cell();
+  root_cell->addSurface(+1, xmin); root_cell->addSurface(-1, xmax);
+  root_cell->addSurface(+1, ymin); root_cell->addSurface(-1, ymax);
+  root_cell->setFill(root_lat);
+  Universe* root = new Universe();
+  root->addCell(root_cell);
+
+  md.geometry = new Geometry();
+  md.geometry->setRootUniverse(root);
+  return md;
+}
+
+std::vector<double> linspace(double a, double b, int n) {
+  std::vector<double> v(n);
+  double step = (b - a) / (n - 1);
+  for (int i = 0; i < n; i++) v[i] = a + i * step;   /* numpy: start + i*step */
+  v[n - 1] = b;
+  return v;
+}
+
+}  // namespace
+
+
+Model build_model(const std::string& name, int dims) {
+  if (name == "pin-cell") return pin_cell(dims);
+  if (name == "simple-lattice") return simple_lattice(dims);
+  if (name == "hom-inf") return hom_inf(dims);
+  if (name == "c5g7-2d") return c5g7_2d(dims);
+  log_printf(ERROR, "unknown model %s", name.c_str());
+  return Model();
+}
+
+
+void set_70_group_xs(Model& model) {
+  const int G = 70;
+  std::vector<double> v;
+  Material* uo2 = model.materials["UO2"];
+  uo2->setNumEnergyGroups(G);
+  v = linspace(0, 1, G); for (double& e : v) e *= 7; uo2->setNuSigmaF(v.data(), G);
+  v = linspace(0, 1, G * G); for (double& e : v) e /= 1000; uo2->setSigmaS(v.data(), G * G);
+  v.assign(G, 1 / 70.); uo2->setChi(v.data(), G);
+  v = linspace(2, 3, G); uo2->setSigmaT(v.data(), G);
+
+  Material* water = model.materials["Water"];
+  water->setNumEnergyGroups(G);
+  v.assign(G, 0.); water->setNuSigmaF(v.data(), G);
+  v = linspace(1, 2, G * G); for (double& e : v) e /= 1000; water->setSigmaS(v.data(), G * G);
+  v.assign(G, 0.); water->setChi(v.data(), G);
+  v = linspace(3, 4, G); water->setSigmaT(v.data(), G);
+}

@@ -1,0 +1,34 @@
+/**
+ * @file models.h
+ * @brief C++ restatements of the reference's test/sample input decks, built
+ *        with the reference's own Geometry/Cell/Lattice classes.
+ *        TEST INFRASTRUCTURE (oracle side) - never linked into the product.
+ *
+ *  pin-cell        tests/input_set.py:95-137   (PinCellInput)
+ *  simple-lattice  tests/input_set.py:310-417  (SimpleLatticeInput, 2D or 3D)
+ *  c5g7-2d         sample-input/benchmarks/c5g7/{surfaces,cells,universes,
+ *                  lattices,c5g7-2d}.py
+ *  hom-inf         tests/input_set.py:32-92    (HomInfMedInput)
+ */
+#ifndef ORACLE_MODELS_H_
+#define ORACLE_MODELS_H_
+
+#include <map>
+#include <string>
+
+class Geometry;
+class Material;
+
+struct Model {
+  Geometry* geometry;
+  std::map<std::string, Material*> materials;
+};
+
+/** dims = 2 or 3 (only simple-lattice and pin-cell honour 3). */
+Model build_model(const std::string& name, int dims);
+
+/** Replace the UO2/Water data by the synthetic 70-group set of
+ *  tests/test_forward_3D_lattice_70g/test_forward_3D_lattice_70g.py:43-61. */
+void set_70_group_xs(Model& model);
+
+#endif

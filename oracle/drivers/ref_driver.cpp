@@ -1,0 +1,167 @@
+/**
+ * @file ref_driver.cpp
+ * @brief Runs the UNMODIFIED reference CPUSolver / CPULSSolver on one of the
+ *        restated input decks (models.cpp), prints its results in the format of
+ *        the reference's regression harness (tests/testing_harness.py:158-207)
+ *        and optionally dumps the flattened tracks as a B2TRK file.
+ *        TEST INFRASTRUCTURE + CPU baseline; never part of the product path.
+ *
+ * Usage: ref_driver --model NAME [--dims 2|3] [--azim N] [--spacing S]
+ *                   [--polar N] [--zspacing S] [--formation explicit|otf-tracks|otf-stacks]
+ *                   [--quad ty|equal-angle|gl|equal-weight|leonard] [--groups70]
+ *                   [--solver cpu|cpuls] [--mode eigen|none] [--tol T]
+ *                   [--max-iters N] [--threads N] [--res fission|flux|total]
+ *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet]
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "CPUSolver.h"
+#include "CPULSSolver.h"
+#include "TrackGenerator3D.h"
+#include "log.h"
+
+#include "models.h"
+#include "../../openmoc_b200/cpp/b200_flatten.h"
+
+static const char* arg(int argc, char** argv, const char* key, const char* dflt) {
+  for (int i = 1; i < argc - 1; i++)
+    if (!strcmp(argv[i], key)) return argv[i + 1];
+  return dflt;
+}
+static bool flag(int argc, char** argv, const char* key) {
+  for (int i = 1; i < argc; i++)
+    if (!strcmp(argv[i], key)) return true;
+  return false;
+}
+
+int main(int argc, char** argv) {
+  std::string model_name = arg(argc, argv, "--model", "pin-cell");
+  int dims = atoi(arg(argc, argv, "--dims", "2"));
+  int num_azim = atoi(arg(argc, argv, "--azim", "4"));
+  double spacing = atof(arg(argc, argv, "--spacing", "0.1"));
+  int num_polar = atoi(arg(argc, argv, "--polar", dims == 3 ? "2" : "6"));
+  double z_spacing = atof(arg(argc, argv, "--zspacing", "0.1"));
+  std::string formation = arg(argc, argv, "--formation", "otf-tracks");
+  std::string quad_name = arg(argc, argv, "--quad", "default");
+  std::string solver_name = arg(argc, argv, "--solver", "cpu");
+  std::string mode = arg(argc, argv, "--mode", "eigen");
+  double tol = atof(arg(argc, argv, "--tol", "1e-5"));
+  int max_iters = atoi(arg(argc, argv, "--max-iters", "500"));
+  int threads = atoi(arg(argc, argv, "--threads", "1"));
+  std::string res = arg(argc, argv, "--res", "fission");
+  std::string dump_tracks = arg(argc, argv, "--dump-tracks", "");
+  std::string results = arg(argc, argv, "--results", "");
+  std::string json = arg(argc, argv, "--json", "");
+  bool fluxes_in_results = !flag(argc, argv, "--no-fluxes");
+
+  if (flag(argc, argv, "--quiet")) set_log_level("WARNING");
+  else set_log_level("NORMAL");
+
+  Model md = build_model(model_name, dims);
+  if (flag(argc, argv, "--groups70")) set_70_group_xs(md);
+  Geometry* geometry = md.geometry;
+  geometry->initializeFlatSourceRegions();
+
+  Quadrature* quad = NULL;
+  if (quad_name == "equal-angle") quad = new EqualAnglePolarQuad();
+  else if (quad_name == "ty") quad = new TYPolarQuad();
+  else if (quad_name == "gl") quad = new GLPolarQuad();
+  else if (quad_name == "equal-weight") quad = new EqualWeightPolarQuad();
+  else if (quad_name == "leonard") quad = new LeonardPolarQuad();
+  if (quad != NULL) quad->setNumPolarAngles(num_polar);
+
+  TrackGenerator* tg;
+  if (dims == 3) {
+    TrackGenerator3D* tg3 = new TrackGenerator3D(geometry, num_azim, num_polar, spacing, z_spacing);
+    if (formation == "explicit") tg3->setSegmentFormation(EXPLICIT_3D);
+    else if (formation == "otf-stacks") tg3->setSegmentFormation(OTF_STACKS);
+    else tg3->setSegmentFormation(OTF_TRACKS);
+    tg = tg3;
+  } else {
+    tg = new TrackGenerator(geometry, num_azim, spacing);
+  }
+  if (quad != NULL) tg->setQuadrature(quad);
+  /* the harness ray-traces single-threaded in 2D "for FSR reproducibility"
+   * (tests/testing_harness.py:83-85); OTF 3D needs tg threads == solver threads */
+  tg->setNumThreads(dims == 3 ? threads : 1);
+  tg->generateTracks();
+
+  CPUSolver* solver = (solver_name == "cpuls") ? new CPULSSolver(tg) : new CPUSolver(tg);
+  solver->setNumThreads(threads);
+  solver->setConvergenceThreshold(tol);
+
+  residualType rt = FISSION_SOURCE;
+  if (res == "flux") rt = SCALAR_FLUX;
+  else if (res == "total") rt = TOTAL_SOURCE;
+
+  if (mode == "eigen")
+    solver->computeEigenvalue(max_iters, rt);
+  else
+    solver->initializeSolver(FORWARD);
+
+  long n_fsr = geometry->getNumFSRs();
+  int G = geometry->getNumEnergyGroups();
+  long n_trk = tg->getNumTracks();
+  long n_seg = tg->getNumSegments();
+  int F = (dims == 3) ? G : G * tg->getQuadrature()->getNumPolarAngles() / 2;
+
+  if (mode == "eigen" && !flag(argc, argv, "--quiet")) solver->printTimerReport();
+
+  /* ---- results in the harness format ---- */
+  if (mode == "eigen" && !results.empty()) {
+    FILE* f = fopen(results.c_str(), "w");
+    fprintf(f, "# Iterations: %d\n", solver->getNumIterations());
+    fprintf(f, "keff: %12.5E\n", solver->getKeff());
+    if (fluxes_in_results) {
+      fprintf(f, "fluxes:\n");
+      std::vector<FP_PRECISION> phi(n_fsr * G);
+      solver->getFluxes(phi.data(), n_fsr * G);
+      for (long i = 0; i < n_fsr * G; i++) fprintf(f, "%12.6E\n", phi[i]);
+    }
+    fclose(f);
+  }
+
+  /* ---- machine-readable summary (full precision) ---- */
+  if (!json.empty()) {
+    FILE* f = fopen(json.c_str(), "w");
+    double sweep_time = 0., total_time = 0.;
+    if (mode == "eigen") {
+      Timer timer;  /* splits are static/shared in the reference's Timer */
+      sweep_time = timer.getSplit("Transport Sweep");
+      total_time = timer.getSplit("Total time");
+    }
+    fprintf(f, "{\"model\": \"%s\", \"dims\": %d, \"num_azim\": %d, \"spacing\": %.17g, "
+               "\"num_polar\": %d, \"solver\": \"%s\", \"threads\": %d, \"tol\": %.17g,\n",
+            model_name.c_str(), dims, num_azim, spacing,
+            (int)tg->getQuadrature()->getNumPolarAngles(), solver_name.c_str(), threads, tol);
+    fprintf(f, " \"n_tracks\": %ld, \"n_segments\": %ld, \"n_fsrs\": %ld, \"num_groups\": %d, "
+               "\"fluxes_per_track\": %d,\n", n_trk, n_seg, n_fsr, G, F);
+    if (mode == "eigen") {
+      int it = solver->getNumIterations();
+      fprintf(f, " \"iterations\": %d, \"keff\": %.17g, \"sweep_time_s\": %.9g, "
+                 "\"total_time_s\": %.9g, \"integrations\": %.17g,\n",
+              it, solver->getKeff(), sweep_time, total_time, 2.0 * F * (double)n_seg * it);
+      std::vector<FP_PRECISION> phi(n_fsr * G);
+      solver->getFluxes(phi.data(), n_fsr * G);
+      fprintf(f, " \"fluxes\": [");
+      for (long i = 0; i < n_fsr * G; i++) fprintf(f, "%s%.17g", i ? ", " : "", phi[i]);
+      fprintf(f, "],\n");
+    }
+    fprintf(f, " \"ok\": true}\n");
+    fclose(f);
+  }
+
+  /* ---- flattened tracks (segments are final after the solve/initialize) ---- */
+  if (!dump_tracks.empty()) {
+    B200FlatTracks ft;
+    b200_flatten(tg, &ft);
+    b200_write_trackfile(ft, dump_tracks);
+    printf("[ref_driver] wrote %s: %ld tracks, %ld segments, %ld FSRs, G=%d F=%d\n",
+           dump_tracks.c_str(), (long)ft.n_tracks, (long)ft.n_segments, (long)ft.n_fsrs,
+           ft.num_groups, ft.fluxes_per_track);
+  }
+  return 0;
+}
