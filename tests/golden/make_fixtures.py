@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Regenerate tests/golden/ from the UNMODIFIED reference.
+
+Runs oracle/_ref/ref_driver (the reference's CPUSolver built by oracle/Makefile
+from /root/reference/src) on the reference's own regression decks and stores
+
+  <case>.b2trk   flattened tracks (input of the hot path)
+  <case>.json    reference results at full precision (k_eff, iterations, phi)
+  ref_goldens.json  the reference's own committed golden files, verbatim
+                    (tests/test_forward_*/results_true.dat), used to pin the
+                    C oracle without needing /root/reference at test time.
+
+Needs /root/reference; run in the CPU container:  python tests/golden/make_fixtures.py
+"""
+import json, os, subprocess, sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+REF = "/root/reference"
+
+CASES = {
+    # name: ref_driver args                                            (reference test it mirrors)
+    "pin_cell": ["--model", "pin-cell", "--azim", "4", "--spacing", "0.1"],          # test_forward_pin_cell
+    "simple_lattice": ["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12"],  # test_forward_simple_lattice
+    "lattice3d_70g": ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2",
+                      "--spacing", "2.1", "--zspacing", "2.8", "--groups70", "--tol", "5e-3"],  # test_forward_3D_lattice_70g
+    "lattice3d_7g": ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2",
+                     "--spacing", "0.24", "--zspacing", "0.9"],                       # test_forward_3D_lattice
+    "hom_inf": ["--model", "hom-inf", "--azim", "4", "--spacing", "0.1"],            # test_forward_hom_inf_medium
+    "c5g7_2d_coarse": ["--model", "c5g7-2d", "--azim", "4", "--spacing", "0.5", "--polar", "6",
+                       "--quad", "equal-angle", "--max-iters", "40", "--no-fluxes"],  # C3 deck, coarse tracks
+}
+
+def main():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    for name, args in CASES.items():
+        trk = os.path.join(HERE, name + ".b2trk")
+        js = os.path.join(HERE, name + ".json")
+        subprocess.check_call([DRIVER] + args + ["--quiet", "--dump-tracks", trk, "--json", js])
+        d = json.load(open(js))
+        if name.startswith("c5g7") or name.startswith("lattice3d_70g"):
+            d.pop("fluxes", None)    # keep the fixture small; phi is compared through the oracle
+        d.pop("sweep_time_s", None); d.pop("total_time_s", None)
+        json.dump(d, open(js, "w"))
+        print(name, d.get("iterations"), d.get("keff"), d["n_tracks"], d["n_segments"], d["n_fsrs"])
+    gold = {}
+    for t in ("test_forward_pin_cell", "test_forward_simple_lattice", "test_forward_3D_lattice_70g",
+              "test_forward_3D_lattice", "test_forward_hom_inf_medium"):
+        gold[t] = open(os.path.join(REF, "tests", t, "results_true.dat")).read()
+    json.dump(gold, open(os.path.join(HERE, "ref_goldens.json"), "w"), indent=1)
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,99 @@
+"""Pins the plain-C oracle (oracle/moc_oracle.c) to the reference.
+
+Two anchors, neither needs /root/reference at test time:
+  * the reference's own committed goldens (tests/golden/ref_goldens.json holds
+    tests/test_forward_*/results_true.dat verbatim), compared byte-for-byte in
+    the format of tests/testing_harness.py:158-207;
+  * full-precision results of the unmodified reference CPUSolver run on the same
+    decks (tests/golden/<case>.json, written by tests/golden/make_fixtures.py).
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_case
+from oracle.oracle_py import (OracleSolver, format_harness_results, lib,
+                              FISSION_SOURCE, SCALAR_FLUX, TOTAL_SOURCE)
+
+GOLDENS = json.load(open(os.path.join(GOLDEN, "ref_goldens.json")))
+
+
+def solve(name, tol=1e-5, max_iters=500):
+    ft, ref = load_case(name)
+    ft.validate()
+    s = OracleSolver(ft)
+    n = s.computeEigenvalue(max_iters, tol, FISSION_SOURCE)
+    return s, n, ref
+
+
+def test_pin_cell_golden_bytes():
+    s, n, ref = solve("pin_cell")
+    out = format_harness_results(n, s.getKeff(), s.getFluxes())
+    assert out == GOLDENS["test_forward_pin_cell"]
+    assert n == ref["iterations"] == 261
+    assert abs(s.getKeff() - ref["keff"]) < 1e-12
+    np.testing.assert_allclose(s.getFluxes(), ref["fluxes"], rtol=1e-11)
+
+
+def test_simple_lattice_golden_sha512():
+    s, n, ref = solve("simple_lattice")
+    out = format_harness_results(n, s.getKeff(), s.getFluxes())
+    assert hashlib.sha512(out.encode()).hexdigest() == GOLDENS["test_forward_simple_lattice"].strip()
+    assert n == ref["iterations"] == 187
+    np.testing.assert_allclose(s.getFluxes(), ref["fluxes"], rtol=1e-10)
+
+
+def test_hom_inf_medium_golden_bytes():
+    s, n, ref = solve("hom_inf")
+    out = format_harness_results(n, s.getKeff(), s.getFluxes())
+    assert out == GOLDENS["test_forward_hom_inf_medium"]
+
+
+def test_lattice3d_70g_golden_bytes():
+    s, n, ref = solve("lattice3d_70g", tol=5e-3)
+    assert format_harness_results(n, s.getKeff()) == GOLDENS["test_forward_3D_lattice_70g"]
+    assert abs(s.getKeff() - ref["keff"]) < 1e-11
+
+
+def test_lattice3d_7g_golden_bytes():
+    s, n, ref = solve("lattice3d_7g")
+    assert format_harness_results(n, s.getKeff()) == GOLDENS["test_forward_3D_lattice"]
+    np.testing.assert_allclose(s.getFluxes(), ref["fluxes"], rtol=1e-9)
+
+
+def test_c5g7_coarse_matches_reference_run():
+    s, n, ref = solve("c5g7_2d_coarse", max_iters=40)
+    assert n == ref["iterations"] == 40
+    assert abs(s.getKeff() - ref["keff"]) < 1e-10
+
+
+def test_expF1_known_answers():
+    # tests/unit_tests/test_exponentials.py:13,74-77 (expF1_fractional)
+    taus = [1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1, 10, 100]
+    expect = [0.9999999950003422, 0.9999999500034228, 0.9999995000343784,
+              0.9999950003587617, 0.9999500050851808, 0.9995002005718668,
+              0.9950169413610763, 0.9516272442309586, 0.6321211831479621,
+              0.09999547551656497, 0.010000005017389789]
+    got = [lib().moc_oracle_expF1(t) for t in taus]
+    assert np.all(np.abs(np.array(got) - np.array(expect)) < 1e-8)
+
+
+def test_threads_do_not_change_answer():
+    ft, ref = load_case("simple_lattice")
+    a = OracleSolver(ft); a.computeEigenvalue(30, 1e-5)
+    b = OracleSolver(ft); b.setNumThreads(4); b.computeEigenvalue(30, 1e-5)
+    np.testing.assert_allclose(a.getFluxes(), b.getFluxes(), rtol=1e-11)
+
+
+def test_fixed_source_flux_positive_and_converges():
+    ft, _ = load_case("pin_cell")
+    s = OracleSolver(ft)
+    s.setFixedSourceByFSR(1, 1, 1.0)
+    n = s.computeFlux(400, 1e-6)
+    assert n < 400
+    phi = s.getFluxes().reshape(-1, ft.num_groups)
+    # computeFlux evaluates the source once (Solver.cpp:1390): only the fixed-source group is lit
+    assert np.all(phi[:, 0] > 0) and np.all(phi[:, 1:] == 0)
