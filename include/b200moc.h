@@ -1,0 +1,152 @@
+/*
+ * b200moc.h - C ABI of the B200-native MOC transport-sweep engine.
+ *
+ * This is the drop-in boundary: a `B200Solver : public Solver` on the OpenMOC
+ * side (openmoc_b200/cpp/B200Solver.cpp) implements every pure virtual of
+ * src/Solver.h:334-431 as a one-line call into this library, exactly like the
+ * reference's GPUSolver (src/accel/cuda/GPUSolver.h:78-179) does with its own
+ * kernels.  Only POD pointers and sizes cross the boundary; no OpenMOC, torch
+ * or CUDA types.  Paths below are relative to the reference repository.
+ *
+ * Conventions (all "CPU convention"):
+ *   scalar flux / reduced source  double  [r*G + e]          src/Solver.h:34-46
+ *   track angular flux            float   [(t*2+dir)*F + p*G + e]  src/Solver.h:49-54
+ *        dir 0 = forward, 1 = reverse;  F = G*P/2 (2D) or G (3D)   src/Solver.cpp:432-449
+ *   sigma_s[dest*G + orig], fiss_matrix[dest*G + orig]       src/Material.cpp:728,977
+ *   q = Q / 4pi (not divided by sigma_t)                     src/CPUSolver.cpp:1974
+ *   fission source normalised to N_FSR                       src/CPUSolver.cpp:1910,2327
+ *
+ * Every function returns 0 on success, non-zero on failure with the message
+ * available from b200_last_error() (the plug-in turns it into
+ * log_printf(ERROR, ...) => std::logic_error => Python RuntimeError, the
+ * reference's own convention, src/log.cpp:535-599).
+ */
+#ifndef B200MOC_H_
+#define B200MOC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_solver b200_solver;
+
+/* residualType, src/Solver.h:75-85 */
+enum { B200_RES_SCALAR_FLUX = 0, B200_RES_FISSION_SOURCE = 1, B200_RES_TOTAL_SOURCE = 2 };
+/* stabilizationType, src/Solver.h:103-113 */
+enum { B200_STAB_DIAGONAL = 0, B200_STAB_YAMAMOTO = 1, B200_STAB_GLOBAL = 2 };
+/* boundaryType, src/boundary_type.h:14-29 */
+enum { B200_BC_VACUUM = 0, B200_BC_REFLECTIVE = 1, B200_BC_PERIODIC = 2, B200_BC_INTERFACE = 3 };
+/* arithmetic of the per-segment attenuation */
+enum { B200_PRECISION_DOUBLE = 0,   /* FP_PRECISION=double build of the reference: default */
+       B200_PRECISION_MIXED = 1 };  /* fp32 exponential + fp32 delta-psi, fp64 tally */
+
+typedef struct b200_config {
+  int32_t num_groups;      /* G */
+  int32_t num_azim;        /* A: azimuthal angles in (0, 2pi) */
+  int32_t num_polar;       /* P: polar angles in (0, pi) */
+  int32_t solve_3d;        /* 0: 2D tracks carry P/2 polar angles; 1: one per track */
+  int64_t n_tracks, n_segments, n_fsrs;
+  int32_t n_materials;
+  int32_t device;          /* CUDA device ordinal */
+  int32_t precision;       /* B200_PRECISION_* */
+  int32_t deterministic;   /* 1: order-independent (fixed-point) FSR tally */
+  int64_t n_fsrs_global;   /* normalisation count when FSRs are sharded; 0 => n_fsrs */
+} b200_config;
+
+const char* b200_last_error(void);
+int b200_version(void);
+/* number of visible CUDA devices, or -1 with an error message */
+int b200_device_count(void);
+
+/* replaces GPUSolver::GPUSolver / ~GPUSolver (GPUSolver.cu:771-850) */
+int b200_create(const b200_config* cfg, b200_solver** out);
+int b200_destroy(b200_solver* s);
+
+/* replaces GPUSolver::initializeTracks + clone_track (GPUSolver.cu:1312-1353,
+ * clone.cu:86-126): one SoA upload instead of one cudaMalloc per track. */
+int b200_upload_tracks(b200_solver* s,
+                       const double* seg_length, const int32_t* seg_fsr,
+                       const int64_t* trk_seg_offset,           /* n_tracks+1 */
+                       const int32_t* trk_azim, const int32_t* trk_polar,
+                       const int64_t* trk_next_fwd, const int64_t* trk_next_bwd,
+                       const uint8_t* trk_flags,  /* bit0 next_fwd_is_fwd, bit1 next_bwd_is_fwd */
+                       const uint8_t* trk_bc_fwd, const uint8_t* trk_bc_bwd);
+/* replaces GPUSolver::copyQuadrature (GPUSolver.cu:1102-1143); [A/2][P] tables of
+ * Quadrature::getWeightInline / getSinThetaInline (src/Quadrature.h:301-336) */
+int b200_upload_quadrature(b200_solver* s, const double* weight, const double* sin_theta);
+/* replaces GPUSolver::initializeFSRs (GPUSolver.cu:1165-1215) */
+int b200_upload_fsrs(b200_solver* s, const double* volume, const int32_t* fsr_material);
+/* replaces GPUSolver::initializeMaterials + clone_material (GPUSolver.cu:1224-1303) */
+int b200_upload_materials(b200_solver* s, const double* sigma_t, const double* sigma_s,
+                          const double* fiss_matrix, const double* nu_sigma_f,
+                          const double* sigma_f, const double* chi,
+                          const uint8_t* fissionable);
+/* builds device-side derived tables; call after the four uploads (re-callable) */
+int b200_finalize(b200_solver* s);
+
+/* ---- one entry per Solver pure virtual (src/Solver.h:334-431) ---- */
+int b200_zero_track_fluxes(b200_solver* s);
+int b200_flatten_fsr_fluxes(b200_solver* s, double value);
+int b200_flatten_fsr_fluxes_chi_spectrum(b200_solver* s, int32_t material);
+int b200_store_fsr_fluxes(b200_solver* s);
+int b200_normalize_fluxes(b200_solver* s, double* norm_factor);
+int b200_compute_stabilizing_flux(b200_solver* s);
+int b200_stabilize_flux(b200_solver* s);
+int b200_compute_fsr_sources(b200_solver* s, int32_t iteration);
+int b200_compute_fsr_fission_sources(b200_solver* s);
+int b200_compute_fsr_scatter_sources(b200_solver* s);
+int b200_compute_residual(b200_solver* s, int32_t res_type, double* residual);
+int b200_compute_keff(b200_solver* s, double* k_eff);
+int b200_add_source_to_scalar_flux(b200_solver* s);
+/* zero phi, sweep every track both ways, hand boundary fluxes over.  On return
+ * scalar_flux holds the raw tally sum(w*delta_psi); a multi-GPU host sums it
+ * across ranks (b200_device_pointer) before b200_add_source_to_scalar_flux. */
+int b200_transport_sweep(b200_solver* s);
+
+/* ---- public Solver API (src/Solver.h:440-585) ---- */
+int b200_get_fluxes(b200_solver* s, double* out_fluxes, int64_t num_fluxes);
+int b200_set_fluxes(b200_solver* s, const double* in_fluxes, int64_t num_fluxes);
+int b200_set_fixed_source_by_fsr(b200_solver* s, int64_t fsr_id, int32_t group /*1-based*/, double source);
+int b200_reset_fixed_sources(b200_solver* s);
+int b200_compute_fsr_fission_rates(b200_solver* s, double* fission_rates, int64_t num_fsrs, int32_t nu);
+int b200_stabilize_transport(b200_solver* s, double factor, int32_t stabilization_type);
+int b200_allow_negative_fluxes(b200_solver* s, int32_t allowed);
+int b200_get_keff(b200_solver* s, double* k_eff);
+int b200_set_keff(b200_solver* s, double k_eff);
+int b200_get_fsr_sources(b200_solver* s, double* out, int64_t n);       /* reduced sources q */
+int b200_set_fsr_sources(b200_solver* s, const double* in, int64_t n);
+int b200_get_start_fluxes(b200_solver* s, float* out, int64_t n);       /* n = n_tracks*2*F */
+int b200_set_start_fluxes(b200_solver* s, const float* in, int64_t n);
+
+/* ---- fused drivers: the loops of Solver::computeEigenvalue / computeFlux /
+ *      computeSource (src/Solver.cpp:1542-1689, 1352-1420, 1459-1516) run
+ *      device-side, convergence flag evaluated on the GPU ---- */
+int b200_compute_eigenvalue(b200_solver* s, int32_t max_iters, double tolerance,
+                            int32_t res_type, int32_t* num_iterations);
+int b200_compute_flux(b200_solver* s, int32_t max_iters, double tolerance,
+                      int32_t only_fixed_source, int32_t* num_iterations);
+int b200_compute_source(b200_solver* s, int32_t max_iters, double k_eff, double tolerance,
+                        int32_t res_type, int32_t* num_iterations);
+/* run exactly n source iterations (sources..store) without convergence test;
+ * benchmark hook.  residual/k of the last iteration are returned if non-NULL */
+int b200_iterate(b200_solver* s, int32_t n, int32_t res_type, double* k_eff, double* residual);
+
+/* ---- instrumentation (the "Transport Sweep" timer split, src/CPUSolver.cpp:2365-2378) ---- */
+int b200_get_sweep_stats(b200_solver* s, double* sweep_ms_total, int64_t* num_sweeps,
+                         int64_t* kernel_launches);
+int b200_reset_sweep_stats(b200_solver* s);
+int b200_synchronize(b200_solver* s);
+
+/* ---- plumbing for multi-GPU hosts: raw device pointers of solver arrays so a
+ *      host framework (torch.distributed / NCCL) can reduce them in place.
+ *      name in {"scalar_flux","old_scalar_flux","reduced_sources","start_flux"} */
+int b200_device_pointer(b200_solver* s, const char* name, void** ptr, int64_t* num_elements);
+/* use an externally owned cudaStream_t (passed as void*) for all launches */
+int b200_set_stream(b200_solver* s, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MOC_H_ */

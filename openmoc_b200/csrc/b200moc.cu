@@ -1,0 +1,1060 @@
+/*
+ * b200moc.cu - implementation of the C ABI declared in include/b200moc.h.
+ *
+ * Host side is deliberately thin: device buffers, launch geometry, the fused
+ * source-iteration loop, and error translation.  All arithmetic on the hot path
+ * lives in sweep.cuh / fsr_kernels.cuh.  There is NO CPU fallback: every entry
+ * point fails with an error message if CUDA is unavailable.
+ */
+#include "../../include/b200moc.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "fsr_kernels.cuh"
+#include "sweep.cuh"
+
+using namespace b200;
+
+/* ------------------------------------------------------------------------- */
+/* errors                                                                     */
+/* ------------------------------------------------------------------------- */
+static thread_local std::string g_last_error;
+
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return 1;
+}
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__,     \
+                  __LINE__, #call);                                                    \
+  } while (0)
+
+#define NEED(s)                                                   \
+  do {                                                            \
+    if ((s) == nullptr) return fail("%s: null solver handle", __func__); \
+    CU(cudaSetDevice((s)->cfg.device));                           \
+  } while (0)
+
+#define NEED_FINAL(s)                                                         \
+  do {                                                                        \
+    NEED(s);                                                                  \
+    if (!(s)->finalized) return fail("%s: b200_finalize has not been called", __func__); \
+  } while (0)
+
+extern "C" const char* b200_last_error(void) { return g_last_error.c_str(); }
+extern "C" int b200_version(void) { return 100; }
+extern "C" int b200_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    fail("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return n;
+}
+
+/* ------------------------------------------------------------------------- */
+/* solver object                                                              */
+/* ------------------------------------------------------------------------- */
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    if (p != nullptr && n == count) return cudaSuccess;
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc((void**)&p, count * sizeof(T));
+  }
+  cudaError_t upload(const T* host, size_t count, cudaStream_t st) {
+    cudaError_t e = alloc(count);
+    if (e != cudaSuccess || count == 0) return e;
+    return cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, st);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct b200_solver {
+  b200_config cfg;
+  int G = 0, NP = 0, F = 0, A2 = 0;
+  int64_t n_trk = 0, n_seg = 0, n_fsr = 0, n_fsr_global = 0, n_fissionable = 0;
+  int n_mat = 0;
+  bool have_tracks = false, have_quad = false, have_fsrs = false, have_mats = false;
+  bool finalized = false;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+
+  /* host copies needed to derive tables */
+  std::vector<int64_t> h_off, h_next_fwd, h_next_bwd;
+  std::vector<int32_t> h_azim, h_polar, h_fsr_mat;
+  std::vector<uint8_t> h_flags, h_bc_fwd, h_bc_bwd, h_fissionable;
+  std::vector<double> h_weight, h_sin, h_sigma_t, h_sigma_s;
+
+  /* device: tracks */
+  DevBuf<double> seg_len;
+  DevBuf<int32_t> seg_fsr;
+  DevBuf<int64_t> trk_off, out_slot;
+  DevBuf<int32_t> trk_class, order;
+  DevBuf<uint8_t> carry;
+  DevBuf<double> cls_w, cls_inv_sin;
+  /* device: FSR + materials */
+  DevBuf<int32_t> fsr_mat;
+  DevBuf<double> vol, sigma_t, sigma_s, fiss, nu_sigma_f, sigma_f, chi, max_ratio;
+  DevBuf<uint8_t> fissionable;
+  /* device: state */
+  DevBuf<double> phi, phi_old, fixed, stab, scratch;
+  DevBuf<double2> qst;
+  DevBuf<float> psi_a, psi_b;
+  float* psi_start = nullptr;  /* what the next sweep reads (= reference _start_flux) */
+  float* psi_other = nullptr;
+  DevBuf<double> scal, partials, hist_k, hist_res;
+  DevBuf<int> iscal;
+  double* h_scal = nullptr;   /* pinned mirrors */
+  int* h_iscal = nullptr;
+
+  /* sweep launch geometry */
+  int gpl = 1, lpi = 1, ipw = 1;
+  int64_t sweep_blocks = 0;
+
+  /* options */
+  bool fixed_on = false, stabilize = false, neg_allowed = false;
+  double stab_factor = 1.0;
+  int stab_type = 0;
+
+  /* stats */
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+  double sweep_ms = 0.;
+  int64_t n_sweeps = 0, n_launches = 0;
+};
+
+static FsrArgs fsr_args(b200_solver* s) {
+  FsrArgs a;
+  a.G = s->G;
+  a.n_fsr = s->n_fsr;
+  a.n_fsr_global = s->n_fsr_global;
+  a.n_fissionable = s->n_fissionable;
+  a.fsr_mat = s->fsr_mat.p;
+  a.vol = s->vol.p;
+  a.sigma_t = s->sigma_t.p;
+  a.sigma_s = s->sigma_s.p;
+  a.fiss = s->fiss.p;
+  a.nu_sigma_f = s->nu_sigma_f.p;
+  a.sigma_f = s->sigma_f.p;
+  a.chi = s->chi.p;
+  a.fissionable = s->fissionable.p;
+  a.phi = s->phi.p;
+  a.phi_old = s->phi_old.p;
+  a.qst = s->qst.p;
+  a.fixed = s->fixed_on ? s->fixed.p : nullptr;
+  a.stab = s->stab.p;
+  a.scal = s->scal.p;
+  a.iscal = s->iscal.p;
+  a.partials = s->partials.p;
+  return a;
+}
+
+static inline int grid_for(int64_t n, int threads, int cap = 148 * 8) {
+  int64_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return (int)b;
+}
+
+/* ------------------------------------------------------------------------- */
+/* create / destroy / uploads                                                 */
+/* ------------------------------------------------------------------------- */
+extern "C" int b200_create(const b200_config* cfg, b200_solver** out) {
+  if (cfg == nullptr || out == nullptr) return fail("b200_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("b200_create: no CUDA device available (%s); the B200 solver has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail("b200_create: device %d out of range [0,%d)", cfg->device, ndev);
+  if (cfg->num_groups < 1) return fail("b200_create: num_groups=%d", cfg->num_groups);
+  if (cfg->num_azim < 4 || cfg->num_azim % 4) return fail("b200_create: num_azim=%d must be a positive multiple of 4", cfg->num_azim);
+  if (cfg->num_polar < 2 || cfg->num_polar % 2) return fail("b200_create: num_polar=%d must be even", cfg->num_polar);
+  if (cfg->n_tracks < 0 || cfg->n_segments < 0 || cfg->n_fsrs < 1 || cfg->n_materials < 1)
+    return fail("b200_create: negative or empty problem size");
+  if (cfg->precision != B200_PRECISION_DOUBLE && cfg->precision != B200_PRECISION_MIXED)
+    return fail("b200_create: unknown precision %d", cfg->precision);
+  if (cfg->deterministic) return fail("b200_create: deterministic tally mode is not available in this build");
+  if (!cfg->solve_3d && cfg->num_polar / 2 > 6)
+    return fail("b200_create: %d polar angles per 2D track not supported (max 6)", cfg->num_polar / 2);
+  if (cfg->num_groups > 256) return fail("b200_create: %d energy groups not supported (max 256)", cfg->num_groups);
+  CU(cudaSetDevice(cfg->device));
+  b200_solver* s = new b200_solver();
+  s->cfg = *cfg;
+  s->G = cfg->num_groups;
+  s->NP = cfg->solve_3d ? 1 : cfg->num_polar / 2;
+  s->F = s->G * s->NP;
+  s->A2 = cfg->num_azim / 2;
+  s->n_trk = cfg->n_tracks;
+  s->n_seg = cfg->n_segments;
+  s->n_fsr = cfg->n_fsrs;
+  s->n_fsr_global = cfg->n_fsrs_global > 0 ? cfg->n_fsrs_global : cfg->n_fsrs;
+  s->n_mat = cfg->n_materials;
+  e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete s; return fail("cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  s->own_stream = true;
+  CU(s->scal.alloc(SC_COUNT_D));
+  CU(s->iscal.alloc(SI_COUNT_I));
+  CU(s->partials.alloc(MAX_PARTIALS));
+  CU(cudaMemsetAsync(s->scal.p, 0, SC_COUNT_D * sizeof(double), s->stream));
+  CU(cudaMemsetAsync(s->iscal.p, 0, SI_COUNT_I * sizeof(int), s->stream));
+  CU(cudaMallocHost((void**)&s->h_scal, SC_COUNT_D * sizeof(double)));
+  CU(cudaMallocHost((void**)&s->h_iscal, SI_COUNT_I * sizeof(int)));
+  double one = 1.0;
+  CU(cudaMemcpyAsync(s->scal.p + SC_KEFF, &one, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  *out = s;
+  return 0;
+}
+
+extern "C" int b200_destroy(b200_solver* s) {
+  if (s == nullptr) return 0;
+  cudaSetDevice(s->cfg.device);
+  cudaStreamSynchronize(s->stream);
+  for (auto& p : s->ev_pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto& p : s->ev_free) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  s->seg_len.release(); s->seg_fsr.release(); s->trk_off.release(); s->out_slot.release();
+  s->trk_class.release(); s->order.release(); s->carry.release(); s->cls_w.release();
+  s->cls_inv_sin.release(); s->fsr_mat.release(); s->vol.release(); s->sigma_t.release();
+  s->sigma_s.release(); s->fiss.release(); s->nu_sigma_f.release(); s->sigma_f.release();
+  s->chi.release(); s->max_ratio.release(); s->fissionable.release(); s->phi.release();
+  s->phi_old.release(); s->fixed.release(); s->stab.release(); s->scratch.release();
+  s->qst.release(); s->psi_a.release(); s->psi_b.release(); s->scal.release();
+  s->partials.release(); s->hist_k.release(); s->hist_res.release(); s->iscal.release();
+  if (s->h_scal) cudaFreeHost(s->h_scal);
+  if (s->h_iscal) cudaFreeHost(s->h_iscal);
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return 0;
+}
+
+extern "C" int b200_upload_tracks(b200_solver* s, const double* seg_length, const int32_t* seg_fsr,
+                                  const int64_t* trk_seg_offset, const int32_t* trk_azim,
+                                  const int32_t* trk_polar, const int64_t* trk_next_fwd,
+                                  const int64_t* trk_next_bwd, const uint8_t* trk_flags,
+                                  const uint8_t* trk_bc_fwd, const uint8_t* trk_bc_bwd) {
+  NEED(s);
+  if (!trk_seg_offset || !trk_azim || !trk_polar || !trk_next_fwd || !trk_next_bwd || !trk_flags ||
+      !trk_bc_fwd || !trk_bc_bwd || (s->n_seg > 0 && (!seg_length || !seg_fsr)))
+    return fail("b200_upload_tracks: null array");
+  const int64_t nt = s->n_trk, ns = s->n_seg;
+  if (trk_seg_offset[0] != 0 || trk_seg_offset[nt] != ns)
+    return fail("b200_upload_tracks: trk_seg_offset must run from 0 to n_segments=%lld (got %lld..%lld)",
+                (long long)ns, (long long)trk_seg_offset[0], (long long)trk_seg_offset[nt]);
+  for (int64_t t = 0; t < nt; t++) {
+    if (trk_seg_offset[t + 1] < trk_seg_offset[t])
+      return fail("b200_upload_tracks: trk_seg_offset not monotone at track %lld", (long long)t);
+    if (trk_azim[t] < 0 || trk_azim[t] >= s->A2)
+      return fail("b200_upload_tracks: track %lld azim index %d outside [0,%d)", (long long)t, trk_azim[t], s->A2);
+    if (s->cfg.solve_3d && (trk_polar[t] < 0 || trk_polar[t] >= s->cfg.num_polar))
+      return fail("b200_upload_tracks: track %lld polar index %d outside [0,%d)", (long long)t, trk_polar[t], s->cfg.num_polar);
+    const uint8_t bcs[2] = {trk_bc_fwd[t], trk_bc_bwd[t]};
+    const int64_t nx[2] = {trk_next_fwd[t], trk_next_bwd[t]};
+    for (int d = 0; d < 2; d++) {
+      if (bcs[d] == B200_BC_INTERFACE)
+        return fail("b200_upload_tracks: track %lld ends on a domain INTERFACE; spatial domain "
+                    "decomposition is not supported by this build", (long long)t);
+      if ((bcs[d] == B200_BC_REFLECTIVE || bcs[d] == B200_BC_PERIODIC) && (nx[d] < 0 || nx[d] >= nt))
+        return fail("b200_upload_tracks: track %lld links to track %lld outside [0,%lld)",
+                    (long long)t, (long long)nx[d], (long long)nt);
+    }
+  }
+  for (int64_t i = 0; i < ns; i++)
+    if (seg_fsr[i] < 0 || seg_fsr[i] >= s->n_fsr)
+      return fail("b200_upload_tracks: segment %lld FSR id %d outside [0,%lld)", (long long)i, seg_fsr[i], (long long)s->n_fsr);
+  CU(s->seg_len.upload(seg_length, ns, s->stream));
+  CU(s->seg_fsr.upload(seg_fsr, ns, s->stream));
+  CU(s->trk_off.upload(trk_seg_offset, nt + 1, s->stream));
+  s->h_off.assign(trk_seg_offset, trk_seg_offset + nt + 1);
+  s->h_azim.assign(trk_azim, trk_azim + nt);
+  s->h_polar.assign(trk_polar, trk_polar + nt);
+  s->h_next_fwd.assign(trk_next_fwd, trk_next_fwd + nt);
+  s->h_next_bwd.assign(trk_next_bwd, trk_next_bwd + nt);
+  s->h_flags.assign(trk_flags, trk_flags + nt);
+  s->h_bc_fwd.assign(trk_bc_fwd, trk_bc_fwd + nt);
+  s->h_bc_bwd.assign(trk_bc_bwd, trk_bc_bwd + nt);
+  CU(cudaStreamSynchronize(s->stream));
+  s->have_tracks = true;
+  s->finalized = false;
+  return 0;
+}
+
+extern "C" int b200_upload_quadrature(b200_solver* s, const double* weight, const double* sin_theta) {
+  NEED(s);
+  if (!weight || !sin_theta) return fail("b200_upload_quadrature: null array");
+  const size_t n = (size_t)s->A2 * s->cfg.num_polar;
+  for (size_t i = 0; i < n; i++)
+    if (!(sin_theta[i] > 0.0) || !(sin_theta[i] <= 1.0 + 1e-12))
+      return fail("b200_upload_quadrature: sin_theta[%zu]=%g outside (0,1]", i, sin_theta[i]);
+  s->h_weight.assign(weight, weight + n);
+  s->h_sin.assign(sin_theta, sin_theta + n);
+  s->have_quad = true;
+  s->finalized = false;
+  return 0;
+}
+
+extern "C" int b200_upload_fsrs(b200_solver* s, const double* volume, const int32_t* fsr_material) {
+  NEED(s);
+  if (!volume || !fsr_material) return fail("b200_upload_fsrs: null array");
+  for (int64_t r = 0; r < s->n_fsr; r++)
+    if (fsr_material[r] < 0 || fsr_material[r] >= s->n_mat)
+      return fail("b200_upload_fsrs: FSR %lld material %d outside [0,%d)", (long long)r, fsr_material[r], s->n_mat);
+  CU(s->vol.upload(volume, s->n_fsr, s->stream));
+  CU(s->fsr_mat.upload(fsr_material, s->n_fsr, s->stream));
+  s->h_fsr_mat.assign(fsr_material, fsr_material + s->n_fsr);
+  CU(cudaStreamSynchronize(s->stream));
+  s->have_fsrs = true;
+  s->finalized = false;
+  return 0;
+}
+
+extern "C" int b200_upload_materials(b200_solver* s, const double* sigma_t, const double* sigma_s,
+                                     const double* fiss_matrix, const double* nu_sigma_f,
+                                     const double* sigma_f, const double* chi,
+                                     const uint8_t* fissionable) {
+  NEED(s);
+  if (!sigma_t || !sigma_s || !fiss_matrix || !nu_sigma_f || !chi || !fissionable)
+    return fail("b200_upload_materials: null array");
+  const size_t nG = (size_t)s->n_mat * s->G, nGG = nG * s->G;
+  for (size_t i = 0; i < nG; i++)
+    if (!(sigma_t[i] > 0.0))
+      return fail("b200_upload_materials: sigma_t[%zu]=%g must be positive", i, sigma_t[i]);
+  std::vector<double> zeros;
+  if (sigma_f == nullptr) { zeros.assign(nG, 0.); sigma_f = zeros.data(); }
+  CU(s->sigma_t.upload(sigma_t, nG, s->stream));
+  CU(s->sigma_s.upload(sigma_s, nGG, s->stream));
+  CU(s->fiss.upload(fiss_matrix, nGG, s->stream));
+  CU(s->nu_sigma_f.upload(nu_sigma_f, nG, s->stream));
+  CU(s->sigma_f.upload(sigma_f, nG, s->stream));
+  CU(s->chi.upload(chi, nG, s->stream));
+  CU(s->fissionable.upload(fissionable, s->n_mat, s->stream));
+  s->h_fissionable.assign(fissionable, fissionable + s->n_mat);
+  s->h_sigma_t.assign(sigma_t, sigma_t + nG);
+  s->h_sigma_s.assign(sigma_s, sigma_s + nGG);
+  CU(cudaStreamSynchronize(s->stream));
+  s->have_mats = true;
+  s->finalized = false;
+  return 0;
+}
+
+/* choose groups-per-lane so that lanes-per-item * items-per-warp fills the warp */
+static void choose_lane_map(int G, int* gpl, int* lpi, int* ipw) {
+  static const int cand[] = {1, 2, 3, 4, 7, 8};
+  double best = -1.;
+  for (int c : cand) {
+    int l = (G + c - 1) / c;
+    if (l > 32) continue;
+    int i = 32 / l;
+    double util = (double)i * G / (32.0 * c);
+    if (util > best + 1e-9) { best = util; *gpl = c; *lpi = l; *ipw = i; }
+  }
+}
+
+extern "C" int b200_finalize(b200_solver* s) {
+  NEED(s);
+  if (!s->have_tracks || !s->have_quad || !s->have_fsrs || !s->have_mats)
+    return fail("b200_finalize: tracks, quadrature, FSRs and materials must all be uploaded first");
+  const int64_t nt = s->n_trk;
+  const int NP = s->NP, P = s->cfg.num_polar, A = s->cfg.num_azim;
+
+  /* angle classes: 2D -> azim; 3D -> (azim, polar).  2D inverse sines follow the
+   * ExpEvaluator sharing rule (src/Solver.cpp:763-779): azim a >= A/4 uses A/2-1-a. */
+  const int n_class = s->cfg.solve_3d ? s->A2 * P : s->A2;
+  std::vector<double> cw((size_t)n_class * NP), cis((size_t)n_class * NP);
+  for (int a = 0; a < s->A2; a++) {
+    if (s->cfg.solve_3d) {
+      for (int p = 0; p < P; p++) {
+        cw[a * P + p] = s->h_weight[a * P + p];
+        cis[a * P + p] = 1.0;  /* 3D segments carry the 3D length: F1(tau) directly (CPUSolver.cpp:2419-2433) */
+      }
+    } else {
+      int ae = a;
+      if (ae >= A / 4) ae = A / 2 - 1 - a;
+      for (int p = 0; p < NP; p++) {
+        cw[a * NP + p] = s->h_weight[a * P + p];
+        cis[a * NP + p] = 1.0 / s->h_sin[ae * P + p];
+      }
+    }
+  }
+  std::vector<int32_t> cls(nt);
+  for (int64_t t = 0; t < nt; t++)
+    cls[t] = s->cfg.solve_3d ? s->h_azim[t] * P + s->h_polar[t] : s->h_azim[t];
+
+  /* boundary hand-off table and copy-through flags */
+  std::vector<int64_t> out_slot(2 * nt, -1);
+  std::vector<uint8_t> carry(2 * nt, 1);
+  for (int64_t t = 0; t < nt; t++) {
+    for (int d = 0; d < 2; d++) {
+      uint8_t bc = d == 0 ? s->h_bc_fwd[t] : s->h_bc_bwd[t];
+      if (bc != B200_BC_REFLECTIVE && bc != B200_BC_PERIODIC) continue;
+      int64_t nx = d == 0 ? s->h_next_fwd[t] : s->h_next_bwd[t];
+      int next_is_fwd = d == 0 ? (s->h_flags[t] & 1) : ((s->h_flags[t] >> 1) & 1);
+      int64_t slot = nx * 2 + (next_is_fwd ? 0 : 1);   /* _start_flux(next, !next_is_fwd) CPUSolver.cpp:2574-2588 */
+      out_slot[t * 2 + d] = slot;
+      carry[slot] = 0;
+    }
+  }
+
+  /* work order: natural track order keeps neighbouring (parallel) tracks, which
+   * cross the same FSRs, in the same warp / CTA */
+  std::vector<int32_t> order(nt);
+  std::iota(order.begin(), order.end(), 0);
+
+  CU(s->cls_w.upload(cw.data(), cw.size(), s->stream));
+  CU(s->cls_inv_sin.upload(cis.data(), cis.size(), s->stream));
+  CU(s->trk_class.upload(cls.data(), nt, s->stream));
+  CU(s->out_slot.upload(out_slot.data(), 2 * nt, s->stream));
+  CU(s->carry.upload(carry.data(), 2 * nt, s->stream));
+  CU(s->order.upload(order.data(), nt, s->stream));
+
+  /* state arrays (zero-initialised like CPUSolver::initializeFluxArrays, CPUSolver.cpp:281-370) */
+  const size_t nphi = (size_t)s->n_fsr * s->G, npsi = (size_t)nt * 2 * s->F;
+  CU(s->phi.alloc(nphi)); CU(s->phi_old.alloc(nphi)); CU(s->fixed.alloc(nphi));
+  CU(s->stab.alloc(nphi)); CU(s->qst.alloc(nphi)); CU(s->scratch.alloc(std::max(nphi, (size_t)s->n_fsr)));
+  CU(s->psi_a.alloc(npsi)); CU(s->psi_b.alloc(npsi));
+  CU(cudaMemsetAsync(s->phi.p, 0, nphi * 8, s->stream));
+  CU(cudaMemsetAsync(s->phi_old.p, 0, nphi * 8, s->stream));
+  CU(cudaMemsetAsync(s->fixed.p, 0, nphi * 8, s->stream));
+  CU(cudaMemsetAsync(s->stab.p, 0, nphi * 8, s->stream));
+  CU(cudaMemsetAsync(s->qst.p, 0, nphi * 16, s->stream));
+  if (npsi) {
+    CU(cudaMemsetAsync(s->psi_a.p, 0, npsi * 4, s->stream));
+    CU(cudaMemsetAsync(s->psi_b.p, 0, npsi * 4, s->stream));
+  }
+  s->psi_start = s->psi_a.p;
+  s->psi_other = s->psi_b.p;
+
+  /* fissionable-FSR count (Solver::countFissionableFSRs, src/Solver.cpp:882-892) */
+  s->n_fissionable = 0;
+  for (int64_t r = 0; r < s->n_fsr; r++)
+    if (s->h_fissionable[s->h_fsr_mat[r]]) s->n_fissionable++;
+
+  /* YAMAMOTO max |sigma_s(e,e)/sigma_t(e)| over the FSRs' materials (CPUSolver.cpp:2700-2716) */
+  std::vector<double> mr(s->G, 0.);
+  std::vector<char> used(s->n_mat, 0);
+  for (int64_t r = 0; r < s->n_fsr; r++) used[s->h_fsr_mat[r]] = 1;
+  for (int m = 0; m < s->n_mat; m++) {
+    if (!used[m]) continue;
+    for (int e = 0; e < s->G; e++) {
+      double ratio = std::fabs(s->h_sigma_s[((size_t)m * s->G + e) * s->G + e] / s->h_sigma_t[(size_t)m * s->G + e]);
+      mr[e] = std::max(mr[e], ratio);
+    }
+  }
+  CU(s->max_ratio.upload(mr.data(), s->G, s->stream));
+
+  choose_lane_map(s->G, &s->gpl, &s->lpi, &s->ipw);
+  const int64_t n_items = 2 * nt;
+  const int64_t warps = (n_items + s->ipw - 1) / s->ipw;
+  s->sweep_blocks = (warps + 3) / 4;   /* 128 threads = 4 warps per CTA */
+
+  FsrArgs a = fsr_args(s);
+  fill_sigma_t_kernel<<<grid_for(nphi, 256, 1 << 30), 256, 0, s->stream>>>(a);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  s->finalized = true;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* sweep dispatch                                                             */
+/* ------------------------------------------------------------------------- */
+typedef void (*sweep_fn)(const SweepArgs);
+
+template <typename T, int NP>
+static sweep_fn pick_gpl(int gpl) {
+  switch (gpl) {
+    case 1: return sweep_kernel<T, NP, 1>;
+    case 2: return sweep_kernel<T, NP, 2>;
+    case 3: return sweep_kernel<T, NP, 3>;
+    case 4: return sweep_kernel<T, NP, 4>;
+    case 7: return sweep_kernel<T, NP, 7>;
+    case 8: return sweep_kernel<T, NP, 8>;
+  }
+  return nullptr;
+}
+template <typename T>
+static sweep_fn pick_np(int np, int gpl) {
+  switch (np) {
+    case 1: return pick_gpl<T, 1>(gpl);
+    case 2: return pick_gpl<T, 2>(gpl);
+    case 3: return pick_gpl<T, 3>(gpl);
+    case 4: return pick_gpl<T, 4>(gpl);
+    case 5: return pick_gpl<T, 5>(gpl);
+    case 6: return pick_gpl<T, 6>(gpl);
+  }
+  return nullptr;
+}
+
+static int take_events(b200_solver* s, cudaEvent_t* a, cudaEvent_t* b) {
+  if (s->ev_free.empty()) {
+    CU(cudaEventCreate(a));
+    CU(cudaEventCreate(b));
+  } else {
+    *a = s->ev_free.back().first;
+    *b = s->ev_free.back().second;
+    s->ev_free.pop_back();
+  }
+  return 0;
+}
+
+static int resolve_events(b200_solver* s) {
+  for (auto& p : s->ev_pending) {
+    float ms = 0.f;
+    CU(cudaEventSynchronize(p.second));
+    CU(cudaEventElapsedTime(&ms, p.first, p.second));
+    s->sweep_ms += ms;
+    s->ev_free.push_back(p);
+  }
+  s->ev_pending.clear();
+  return 0;
+}
+
+/* CPUSolver::transportSweep (src/CPUSolver.cpp:2338-2389): phi <- 0, start ->
+ * boundary (here: read psi_start, write the other buffer), sweep. */
+static int launch_sweep(b200_solver* s) {
+  const size_t nphi = (size_t)s->n_fsr * s->G;
+  cudaEvent_t e0, e1;
+  if (take_events(s, &e0, &e1)) return 1;
+  CU(cudaEventRecord(e0, s->stream));
+  /* flattenFSRFluxes(0) (CPUSolver.cpp:2347), skipped once the device-side loop has converged */
+  zero_phi_kernel<<<grid_for(nphi, 256), 256, 0, s->stream>>>(s->phi.p, (int64_t)nphi, s->iscal.p);
+  CU(cudaGetLastError());
+  s->n_launches++;
+  if (s->n_trk > 0) {
+    SweepArgs a;
+    a.seg_len = s->seg_len.p; a.seg_fsr = s->seg_fsr.p; a.trk_off = s->trk_off.p;
+    a.trk_class = s->trk_class.p; a.order = s->order.p; a.out_slot = s->out_slot.p;
+    a.carry = s->carry.p; a.cls_w = s->cls_w.p; a.cls_inv_sin = s->cls_inv_sin.p;
+    a.qst = s->qst.p; a.psi_in = s->psi_start; a.psi_out = s->psi_other; a.phi = s->phi.p;
+    a.done = s->iscal.p + SI_DONE;
+    a.n_items = 2 * s->n_trk; a.G = s->G; a.lpi = s->lpi; a.ipw = s->ipw;
+    sweep_fn fn = s->cfg.precision == B200_PRECISION_MIXED ? pick_np<float>(s->NP, s->gpl)
+                                                           : pick_np<double>(s->NP, s->gpl);
+    if (fn == nullptr) return fail("no sweep kernel for NP=%d GPL=%d", s->NP, s->gpl);
+    fn<<<(unsigned)s->sweep_blocks, 128, 0, s->stream>>>(a);
+    CU(cudaGetLastError());
+    s->n_launches++;
+  }
+  CU(cudaEventRecord(e1, s->stream));
+  s->ev_pending.push_back({e0, e1});
+  if (s->ev_pending.size() >= 512) { if (resolve_events(s)) return 1; }
+  std::swap(s->psi_start, s->psi_other);
+  s->n_sweeps++;
+  return 0;
+}
+
+/* After a device-converged loop some enqueued iterations were no-ops on the GPU
+ * but still flipped the host's psi double-buffer pointers: undo an odd surplus. */
+static void fix_psi_parity(b200_solver* s, int enqueued, int executed) {
+  if ((enqueued - executed) & 1) std::swap(s->psi_start, s->psi_other);
+  s->n_sweeps -= (enqueued - executed);
+}
+
+/* ------------------------------------------------------------------------- */
+/* step functions                                                             */
+/* ------------------------------------------------------------------------- */
+static int fetch_scalars(b200_solver* s) {
+  CU(cudaMemcpyAsync(s->h_scal, s->scal.p, SC_COUNT_D * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemcpyAsync(s->h_iscal, s->iscal.p, SI_COUNT_I * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+static int clear_done(b200_solver* s) {
+  CU(cudaMemsetAsync(s->iscal.p, 0, SI_COUNT_I * sizeof(int), s->stream));
+  return 0;
+}
+
+extern "C" int b200_zero_track_fluxes(b200_solver* s) {
+  NEED_FINAL(s);
+  const size_t npsi = (size_t)s->n_trk * 2 * s->F;
+  if (npsi) {
+    CU(cudaMemsetAsync(s->psi_a.p, 0, npsi * 4, s->stream));
+    CU(cudaMemsetAsync(s->psi_b.p, 0, npsi * 4, s->stream));
+  }
+  return 0;
+}
+
+extern "C" int b200_flatten_fsr_fluxes(b200_solver* s, double value) {
+  NEED_FINAL(s);
+  const int64_t n = s->n_fsr * s->G;
+  fill_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->phi.p, value, n);
+  CU(cudaGetLastError());
+  s->n_launches++;
+  return 0;
+}
+
+extern "C" int b200_flatten_fsr_fluxes_chi_spectrum(b200_solver* s, int32_t material) {
+  NEED_FINAL(s);
+  if (material < 0 || material >= s->n_mat)
+    return fail("b200_flatten_fsr_fluxes_chi_spectrum: material %d outside [0,%d)", material, s->n_mat);
+  fill_chi_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(fsr_args(s), material);
+  CU(cudaGetLastError());
+  s->n_launches++;
+  return 0;
+}
+
+extern "C" int b200_store_fsr_fluxes(b200_solver* s) {
+  NEED_FINAL(s);
+  CU(cudaMemcpyAsync(s->phi_old.p, s->phi.p, (size_t)s->n_fsr * s->G * 8, cudaMemcpyDeviceToDevice, s->stream));
+  return 0;
+}
+
+static int launch_rate(b200_solver* s, int op) {
+  FsrArgs a = fsr_args(s);
+  const int nb = grid_for(s->n_fsr * s->G, RED_THREADS, MAX_PARTIALS);
+  rate_partials_kernel<<<nb, RED_THREADS, 0, s->stream>>>(a);
+  CU(cudaGetLastError());
+  rate_finalize_kernel<<<1, RED_THREADS, 0, s->stream>>>(a, nb, op);
+  CU(cudaGetLastError());
+  s->n_launches += 2;
+  return 0;
+}
+
+static int launch_scale(b200_solver* s) {
+  FsrArgs a = fsr_args(s);
+  scale_phi_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(a);
+  CU(cudaGetLastError());
+  const int64_t npsi = s->n_trk * 2 * (int64_t)s->F;
+  if (npsi) {
+    /* the reference scales _start_flux and _boundary_flux (CPUSolver.cpp:1922-1928);
+     * only the start buffer is ever read again */
+    scale_psi_kernel<<<grid_for(npsi, 256), 256, 0, s->stream>>>(s->psi_start, npsi, s->scal.p, s->iscal.p);
+    CU(cudaGetLastError());
+  }
+  s->n_launches += 2;
+  return 0;
+}
+
+extern "C" int b200_normalize_fluxes(b200_solver* s, double* norm_factor) {
+  NEED_FINAL(s);
+  if (clear_done(s)) return 1;
+  if (launch_rate(s, 2)) return 1;
+  if (launch_scale(s)) return 1;
+  if (norm_factor != nullptr) {
+    if (fetch_scalars(s)) return 1;
+    *norm_factor = s->h_scal[SC_NORM];
+  }
+  return 0;
+}
+
+static int launch_sources(b200_solver* s, int iteration, int mode) {
+  FsrArgs a = fsr_args(s);
+  const int64_t n = s->n_fsr * s->G;
+  sources_kernel<<<grid_for(n, 256, 1 << 30), 256, 0, s->stream>>>(a, iteration, mode, s->neg_allowed ? 1 : 0);
+  CU(cudaGetLastError());
+  s->n_launches++;
+  return 0;
+}
+
+extern "C" int b200_compute_fsr_sources(b200_solver* s, int32_t iteration) {
+  NEED_FINAL(s);
+  if (clear_done(s)) return 1;
+  return launch_sources(s, iteration, 0);
+}
+extern "C" int b200_compute_fsr_fission_sources(b200_solver* s) {
+  NEED_FINAL(s);
+  if (clear_done(s)) return 1;
+  return launch_sources(s, 0, 1);
+}
+extern "C" int b200_compute_fsr_scatter_sources(b200_solver* s) {
+  NEED_FINAL(s);
+  if (clear_done(s)) return 1;
+  return launch_sources(s, 0, 2);
+}
+
+extern "C" int b200_transport_sweep(b200_solver* s) {
+  NEED_FINAL(s);
+  if (clear_done(s)) return 1;
+  return launch_sweep(s);
+}
+
+static int launch_closure(b200_solver* s, int with_rate, int* n_partials) {
+  FsrArgs a = fsr_args(s);
+  const int nb = grid_for(s->n_fsr * s->G, RED_THREADS, MAX_PARTIALS);
+  closure_kernel<<<nb, RED_THREADS, 0, s->stream>>>(a, s->neg_allowed ? 1 : 0, with_rate);
+  CU(cudaGetLastError());
+  s->n_launches++;
+  if (n_partials) *n_partials = nb;
+  return 0;
+}
+
+extern "C" int b200_add_source_to_scalar_flux(b200_solver* s) {
+  NEED_FINAL(s);
+  if (clear_done(s)) return 1;
+  return launch_closure(s, 0, nullptr);
+}
+
+extern "C" int b200_compute_keff(b200_solver* s, double* k_eff) {
+  NEED_FINAL(s);
+  if (clear_done(s)) return 1;
+  if (launch_rate(s, 1)) return 1;
+  if (k_eff != nullptr) {
+    if (fetch_scalars(s)) return 1;
+    *k_eff = s->h_scal[SC_KEFF];
+  }
+  return 0;
+}
+
+static int launch_residual(b200_solver* s, int res_type, int scale_first, int store_after,
+                           int loop_kind, int iteration) {
+  FsrArgs a = fsr_args(s);
+  const int nb = grid_for(s->n_fsr, RED_THREADS, MAX_PARTIALS);
+  residual_kernel<<<nb, RED_THREADS, 0, s->stream>>>(a, res_type, scale_first, store_after);
+  CU(cudaGetLastError());
+  residual_finalize_kernel<<<1, RED_THREADS, 0, s->stream>>>(a, nb, res_type, loop_kind, iteration,
+                                                            s->hist_k.p, s->hist_res.p);
+  CU(cudaGetLastError());
+  s->n_launches += 2;
+  return 0;
+}
+
+extern "C" int b200_compute_residual(b200_solver* s, int32_t res_type, double* residual) {
+  NEED_FINAL(s);
+  if (res_type < 0 || res_type > 2) return fail("b200_compute_residual: unknown residual type %d", res_type);
+  if (res_type == B200_RES_FISSION_SOURCE && s->n_fissionable == 0)
+    return fail("The Solver is unable to compute a FISSION_SOURCE residual without fissionable FSRs");
+  if (clear_done(s)) return 1;
+  if (launch_residual(s, res_type, 0, 0, 0, 0)) return 1;
+  if (fetch_scalars(s)) return 1;
+  if (residual != nullptr) *residual = s->h_scal[SC_RESIDUAL];
+  return 0;
+}
+
+extern "C" int b200_compute_stabilizing_flux(b200_solver* s) {
+  NEED_FINAL(s);
+  stabilizing_flux_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(
+      fsr_args(s), s->stab_type, s->stab_factor, s->max_ratio.p);
+  CU(cudaGetLastError());
+  s->n_launches++;
+  return 0;
+}
+extern "C" int b200_stabilize_flux(b200_solver* s) {
+  NEED_FINAL(s);
+  stabilize_flux_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(
+      fsr_args(s), s->stab_type, s->stab_factor, s->max_ratio.p);
+  CU(cudaGetLastError());
+  s->n_launches++;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* public Solver API                                                          */
+/* ------------------------------------------------------------------------- */
+extern "C" int b200_get_fluxes(b200_solver* s, double* out, int64_t n) {
+  NEED_FINAL(s);
+  if (n != s->n_fsr * s->G)
+    return fail("Unable to get FSR scalar fluxes since there are %d groups and %lld FSRs which does "
+                "not match the requested %lld flux values", s->G, (long long)s->n_fsr, (long long)n);
+  CU(cudaMemcpyAsync(out, s->phi.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+extern "C" int b200_set_fluxes(b200_solver* s, const double* in, int64_t n) {
+  NEED_FINAL(s);
+  if (n != s->n_fsr * s->G)
+    return fail("Unable to set an array with %lld flux values for %lld FSRs and %d groups",
+                (long long)n, (long long)s->n_fsr, s->G);
+  CU(cudaMemcpyAsync(s->phi.p, in, n * 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+extern "C" int b200_set_fixed_source_by_fsr(b200_solver* s, int64_t fsr_id, int32_t group, double source) {
+  NEED_FINAL(s);
+  if (group <= 0 || group > s->G)
+    return fail("Unable to use fixed source for group %d in a %d energy group problem", group, s->G);
+  if (fsr_id < 0 || fsr_id >= s->n_fsr)
+    return fail("Unable to use fixed source for FSR %lld with only %lld FSRs in the geometry",
+                (long long)fsr_id, (long long)s->n_fsr);
+  CU(cudaMemcpyAsync(s->fixed.p + fsr_id * s->G + (group - 1), &source, 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->fixed_on = true;
+  return 0;
+}
+extern "C" int b200_reset_fixed_sources(b200_solver* s) {
+  NEED_FINAL(s);
+  CU(cudaMemsetAsync(s->fixed.p, 0, (size_t)s->n_fsr * s->G * 8, s->stream));
+  s->fixed_on = false;
+  return 0;
+}
+extern "C" int b200_compute_fsr_fission_rates(b200_solver* s, double* out, int64_t n, int32_t nu) {
+  NEED_FINAL(s);
+  if (n != s->n_fsr) return fail("b200_compute_fsr_fission_rates: %lld values requested for %lld FSRs", (long long)n, (long long)s->n_fsr);
+  fission_rates_kernel<<<grid_for(s->n_fsr, 256), 256, 0, s->stream>>>(fsr_args(s), s->scratch.p, nu);
+  CU(cudaGetLastError());
+  s->n_launches++;
+  CU(cudaMemcpyAsync(out, s->scratch.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+extern "C" int b200_stabilize_transport(b200_solver* s, double factor, int32_t type) {
+  NEED(s);
+  if (type < 0 || type > 2) return fail("b200_stabilize_transport: unknown stabilization type %d", type);
+  s->stabilize = true;
+  s->stab_factor = factor;
+  s->stab_type = type;
+  return 0;
+}
+extern "C" int b200_allow_negative_fluxes(b200_solver* s, int32_t allowed) {
+  NEED(s);
+  s->neg_allowed = allowed != 0;
+  return 0;
+}
+extern "C" int b200_get_keff(b200_solver* s, double* k) {
+  NEED(s);
+  if (fetch_scalars(s)) return 1;
+  if (k) *k = s->h_scal[SC_KEFF];
+  return 0;
+}
+extern "C" int b200_set_keff(b200_solver* s, double k) {
+  NEED(s);
+  CU(cudaMemcpyAsync(s->scal.p + SC_KEFF, &k, 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+extern "C" int b200_get_fsr_sources(b200_solver* s, double* out, int64_t n) {
+  NEED_FINAL(s);
+  if (n != s->n_fsr * s->G) return fail("b200_get_fsr_sources: size mismatch");
+  extract_q_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->qst.p, s->scratch.p, n);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, s->scratch.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+extern "C" int b200_set_fsr_sources(b200_solver* s, const double* in, int64_t n) {
+  NEED_FINAL(s);
+  if (n != s->n_fsr * s->G) return fail("b200_set_fsr_sources: size mismatch");
+  CU(cudaMemcpyAsync(s->scratch.p, in, n * 8, cudaMemcpyHostToDevice, s->stream));
+  insert_q_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->qst.p, s->scratch.p, n);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+extern "C" int b200_get_start_fluxes(b200_solver* s, float* out, int64_t n) {
+  NEED_FINAL(s);
+  if (n != s->n_trk * 2 * (int64_t)s->F) return fail("b200_get_start_fluxes: size mismatch");
+  if (n) CU(cudaMemcpyAsync(out, s->psi_start, n * 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+extern "C" int b200_set_start_fluxes(b200_solver* s, const float* in, int64_t n) {
+  NEED_FINAL(s);
+  if (n != s->n_trk * 2 * (int64_t)s->F) return fail("b200_set_start_fluxes: size mismatch");
+  if (n) CU(cudaMemcpyAsync(s->psi_start, in, n * 4, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* fused drivers                                                              */
+/* ------------------------------------------------------------------------- */
+/* one source iteration of Solver::computeEigenvalue (src/Solver.cpp:1614-1681) */
+static int enqueue_eigen_iteration(b200_solver* s, int i, int res_type, int loop_kind) {
+  if (i > 0 && s->stabilize) { if (b200_compute_stabilizing_flux(s)) return 1; }
+  if (launch_sources(s, i, 0)) return 1;
+  if (launch_sweep(s)) return 1;
+  FsrArgs a = fsr_args(s);
+  if (!s->stabilize) {
+    /* closure + the one nu-fission reduction that feeds both computeKeff and
+     * normalizeFluxes (identical sums when no stabilisation sits in between) */
+    int nb = 0;
+    if (launch_closure(s, 1, &nb)) return 1;
+    rate_finalize_kernel<<<1, RED_THREADS, 0, s->stream>>>(a, nb, 3);
+    CU(cudaGetLastError());
+    s->n_launches++;
+  } else {
+    if (launch_closure(s, 0, nullptr)) return 1;
+    if (launch_rate(s, 1)) return 1;
+    if (i > 0) { if (b200_stabilize_flux(s)) return 1; }
+    if (launch_rate(s, 2)) return 1;
+  }
+  /* normalizeFluxes' scaling of phi fused into the residual pass, storeFSRFluxes after */
+  const int64_t npsi = s->n_trk * 2 * (int64_t)s->F;
+  if (npsi) {
+    scale_psi_kernel<<<grid_for(npsi, 256), 256, 0, s->stream>>>(s->psi_start, npsi, s->scal.p, s->iscal.p);
+    CU(cudaGetLastError());
+    s->n_launches++;
+  }
+  if (launch_residual(s, res_type, 1, 1, loop_kind, i)) return 1;
+  return 0;
+}
+
+static int prepare_history(b200_solver* s, int max_iters) {
+  CU(s->hist_k.alloc(std::max(max_iters, 1)));
+  CU(s->hist_res.alloc(std::max(max_iters, 1)));
+  return 0;
+}
+
+extern "C" int b200_compute_eigenvalue(b200_solver* s, int32_t max_iters, double tol, int32_t res_type,
+                                       int32_t* num_iterations) {
+  NEED_FINAL(s);
+  if (res_type < 0 || res_type > 2) return fail("b200_compute_eigenvalue: unknown residual type %d", res_type);
+  if (res_type == B200_RES_FISSION_SOURCE && s->n_fissionable == 0)
+    return fail("The Solver is unable to compute a FISSION_SOURCE residual without fissionable FSRs");
+  if (prepare_history(s, max_iters)) return 1;
+  /* _k_eff = 1, flux arrays zeroed, flat unit flux guess normalised and stored
+   * (Solver.cpp:1566-1600, computeInitialFluxGuess :1710-1731) */
+  double init[SC_COUNT_D] = {0};
+  init[SC_KEFF] = 1.0; init[SC_KPREV] = 1.0; init[SC_TOL] = tol;
+  CU(cudaMemcpyAsync(s->scal.p, init, sizeof init, cudaMemcpyHostToDevice, s->stream));
+  if (clear_done(s)) return 1;
+  if (b200_zero_track_fluxes(s)) return 1;
+  CU(cudaMemsetAsync(s->phi_old.p, 0, (size_t)s->n_fsr * s->G * 8, s->stream));
+  if (b200_flatten_fsr_fluxes(s, 1.0)) return 1;
+  if (launch_rate(s, 2)) return 1;
+  if (launch_scale(s)) return 1;
+  if (b200_store_fsr_fluxes(s)) return 1;
+
+  const int batch = 8;
+  int done = 0, i = 0;
+  while (i < max_iters && !done) {
+    const int end = std::min(max_iters, i + batch);
+    for (; i < end; i++)
+      if (enqueue_eigen_iteration(s, i, res_type, 1)) return 1;
+    if (fetch_scalars(s)) return 1;
+    done = s->h_iscal[SI_DONE];
+  }
+  fix_psi_parity(s, i, s->h_iscal[SI_EXEC]);
+  if (num_iterations) *num_iterations = s->h_iscal[SI_ITERS];
+  if (clear_done(s)) return 1;
+  return resolve_events(s);
+}
+
+extern "C" int b200_iterate(b200_solver* s, int32_t n, int32_t res_type, double* k_eff, double* residual) {
+  NEED_FINAL(s);
+  if (res_type < 0 || res_type > 2) return fail("b200_iterate: unknown residual type %d", res_type);
+  if (clear_done(s)) return 1;
+  for (int i = 0; i < n; i++)
+    if (enqueue_eigen_iteration(s, 1000 + i, res_type, 0)) return 1;
+  if (k_eff != nullptr || residual != nullptr) {
+    if (fetch_scalars(s)) return 1;
+    if (k_eff) *k_eff = s->h_scal[SC_KEFF];
+    if (residual) *residual = s->h_scal[SC_RESIDUAL];
+  }
+  return 0;
+}
+
+/* the common loop of computeFlux (Solver.cpp:1397-1413) and computeSource (:1492-1508) */
+static int flux_source_loop(b200_solver* s, int max_iters, double tol, int res_type, bool sources_each_iter,
+                            int32_t* num_iterations) {
+  if (prepare_history(s, max_iters)) return 1;
+  CU(cudaMemcpyAsync(s->scal.p + SC_TOL, &tol, 8, cudaMemcpyHostToDevice, s->stream));
+  if (clear_done(s)) return 1;
+  const int batch = 8;
+  int done = 0, i = 0;
+  while (i < max_iters && !done) {
+    const int end = std::min(max_iters, i + batch);
+    for (; i < end; i++) {
+      if (sources_each_iter) { if (launch_sources(s, i, 0)) return 1; }
+      if (launch_sweep(s)) return 1;
+      if (launch_closure(s, 0, nullptr)) return 1;
+      if (launch_residual(s, res_type, 0, 1, 2, i)) return 1;
+    }
+    if (fetch_scalars(s)) return 1;
+    done = s->h_iscal[SI_DONE];
+  }
+  fix_psi_parity(s, i, s->h_iscal[SI_EXEC]);
+  if (num_iterations) *num_iterations = done ? s->h_iscal[SI_ITERS] : max_iters;
+  if (clear_done(s)) return 1;
+  return resolve_events(s);
+}
+
+extern "C" int b200_compute_flux(b200_solver* s, int32_t max_iters, double tol, int32_t only_fixed_source,
+                                 int32_t* num_iterations) {
+  NEED_FINAL(s);
+  if (b200_set_keff(s, 1.0)) return 1;
+  if (only_fixed_source) {
+    if (b200_zero_track_fluxes(s)) return 1;
+    if (b200_flatten_fsr_fluxes(s, 0.0)) return 1;
+    if (b200_store_fsr_fluxes(s)) return 1;
+  }
+  if (clear_done(s)) return 1;
+  if (launch_sources(s, 0, 0)) return 1;
+  return flux_source_loop(s, max_iters, tol, B200_RES_SCALAR_FLUX, false, num_iterations);
+}
+
+extern "C" int b200_compute_source(b200_solver* s, int32_t max_iters, double k_eff, double tol,
+                                   int32_t res_type, int32_t* num_iterations) {
+  NEED_FINAL(s);
+  if (k_eff <= 0.)
+    return fail("The Solver is unable to compute the source with keff = %f since it is not a positive value", k_eff);
+  if (res_type < 0 || res_type > 2) return fail("b200_compute_source: unknown residual type %d", res_type);
+  if (b200_set_keff(s, k_eff)) return 1;
+  if (b200_zero_track_fluxes(s)) return 1;
+  if (b200_flatten_fsr_fluxes(s, 1.0)) return 1;
+  if (b200_store_fsr_fluxes(s)) return 1;
+  return flux_source_loop(s, max_iters, tol, res_type, true, num_iterations);
+}
+
+/* ------------------------------------------------------------------------- */
+/* instrumentation / plumbing                                                 */
+/* ------------------------------------------------------------------------- */
+extern "C" int b200_get_sweep_stats(b200_solver* s, double* ms, int64_t* n_sweeps, int64_t* launches) {
+  NEED(s);
+  if (resolve_events(s)) return 1;
+  if (ms) *ms = s->sweep_ms;
+  if (n_sweeps) *n_sweeps = s->n_sweeps;
+  if (launches) *launches = s->n_launches;
+  return 0;
+}
+extern "C" int b200_reset_sweep_stats(b200_solver* s) {
+  NEED(s);
+  if (resolve_events(s)) return 1;
+  s->sweep_ms = 0.;
+  s->n_sweeps = 0;
+  s->n_launches = 0;
+  return 0;
+}
+extern "C" int b200_synchronize(b200_solver* s) {
+  NEED(s);
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+extern "C" int b200_device_pointer(b200_solver* s, const char* name, void** ptr, int64_t* n) {
+  NEED_FINAL(s);
+  if (!name || !ptr || !n) return fail("b200_device_pointer: null argument");
+  const int64_t nphi = s->n_fsr * s->G;
+  if (!strcmp(name, "scalar_flux")) { *ptr = s->phi.p; *n = nphi; }
+  else if (!strcmp(name, "old_scalar_flux")) { *ptr = s->phi_old.p; *n = nphi; }
+  else if (!strcmp(name, "reduced_sources")) { *ptr = s->qst.p; *n = 2 * nphi; }
+  else if (!strcmp(name, "start_flux")) { *ptr = s->psi_start; *n = s->n_trk * 2 * (int64_t)s->F; }
+  else return fail("b200_device_pointer: unknown array '%s'", name);
+  return 0;
+}
+extern "C" int b200_set_stream(b200_solver* s, void* cuda_stream) {
+  NEED(s);
+  CU(cudaStreamSynchronize(s->stream));
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  s->stream = (cudaStream_t)cuda_stream;
+  s->own_stream = false;
+  return 0;
+}

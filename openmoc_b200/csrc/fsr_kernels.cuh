@@ -1,0 +1,392 @@
+/*
+ * fsr_kernels.cuh - the per-FSR steps around the sweep as fused elementwise /
+ * reduction kernels.  Each kernel cites the CPUSolver method it replaces
+ * (src/CPUSolver.cpp) and the reference GPUSolver kernel it supersedes
+ * (src/accel/cuda/GPUSolver.cu).
+ *
+ * Reductions are two-pass and order-fixed (per-block partials, then one block
+ * folds them in index order) so results do not depend on block scheduling.
+ */
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+constexpr double FOUR_PI = 12.566370614359172;          /* src/constants.h:27 */
+constexpr double ONE_OVER_FOUR_PI = 0.07957747154594767; /* src/constants.h:30 */
+constexpr double FLUX_EPSILON = 1.0e-25;                 /* src/constants.h:15 */
+constexpr double VOL_EPSILON = 1.0e-12;                  /* reference FLT_EPSILON, constants.h:12 */
+
+constexpr int RED_THREADS = 256;
+constexpr int MAX_PARTIALS = 1024;
+
+/* device scalar block (double) */
+enum { SC_KEFF = 0, SC_RATE, SC_NORM, SC_RESIDUAL, SC_KPREV, SC_TOL, SC_COUNT_D };
+/* device scalar block (int) */
+enum { SI_DONE = 0, SI_ITERS, SI_EXEC, SI_NEG_SRC, SI_NEG_FLUX, SI_COUNT_I };
+
+struct FsrArgs {
+  int G;
+  int64_t n_fsr;
+  int64_t n_fsr_global;
+  int64_t n_fissionable;
+  const int32_t* __restrict__ fsr_mat;
+  const double* __restrict__ vol;
+  const double* __restrict__ sigma_t;     /* [mat][G] */
+  const double* __restrict__ sigma_s;     /* [mat][dest*G+orig] */
+  const double* __restrict__ fiss;        /* [mat][dest*G+orig] */
+  const double* __restrict__ nu_sigma_f;  /* [mat][G] */
+  const double* __restrict__ sigma_f;
+  const double* __restrict__ chi;
+  const uint8_t* __restrict__ fissionable;
+  double* __restrict__ phi;
+  double* __restrict__ phi_old;
+  double2* __restrict__ qst;              /* {q, sigma_t} per (fsr, group) */
+  double* __restrict__ fixed;             /* may be NULL */
+  double* __restrict__ stab;              /* may be NULL */
+  double* __restrict__ scal;              /* SC_* */
+  int* __restrict__ iscal;                /* SI_* */
+  double* __restrict__ partials;          /* MAX_PARTIALS */
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+/* all threads of the block must call; result valid in thread 0 */
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[RED_THREADS / 32];
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.;
+  if (w == 0) {
+    r = (l < RED_THREADS / 32) ? sh[l] : 0.;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+__device__ __forceinline__ double fold_partials(const double* partials, int n) {
+  /* one block, fixed order */
+  double v = 0.;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += partials[i];
+  return block_sum(v);
+}
+
+/* ---- computeFSRSources (src/CPUSolver.cpp:1939-2023; GPUSolver.cu:288-338) ----
+ * one thread per (fsr, destination group); the FSR's G fluxes are re-read from
+ * L1 by its G threads.  mode 0: total, 1: fission only, 2: scatter only
+ * (computeFSRFissionSources :2030, computeFSRScatterSources :2072). */
+__global__ void __launch_bounds__(256)
+sources_kernel(const FsrArgs a, int iteration, int mode, int neg_allowed) {
+  if (a.iscal[SI_DONE]) return;
+  const int G = a.G;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.n_fsr * G) return;
+  const int64_t r = idx / G;
+  const int Gd = (int)(idx - r * G);
+  const int m = a.fsr_mat[r];
+  const double* __restrict__ ss = a.sigma_s + ((int64_t)m * G + Gd) * G;
+  const double* __restrict__ fm = a.fiss + ((int64_t)m * G + Gd) * G;
+  const double* __restrict__ ph = a.phi + r * G;
+  const bool fissionable = a.fissionable[m];
+  double scatter = 0., fission = 0.;
+  for (int g = 0; g < G; g++) {
+    const double f = ph[g];
+    scatter = fma(ss[g], f, scatter);
+    if (fissionable) fission = fma(fm[g], f, fission);
+  }
+  double q;
+  if (mode == 0) {
+    q = fission / a.scal[SC_KEFF];
+    q += scatter;
+    if (a.fixed != nullptr) q += a.fixed[idx];
+  } else if (mode == 1) {
+    q = fission;
+  } else {
+    q = scatter;
+  }
+  q *= ONE_OVER_FOUR_PI;
+  if (mode == 0 && q < 0.0) {
+    atomicAdd(&a.iscal[SI_NEG_SRC], 1);
+    if (iteration < 30 && !neg_allowed) q = FLUX_EPSILON;
+  }
+  a.qst[idx].x = q;
+}
+
+/* sigma_t half of the {q, sigma_t} table, once per material upload */
+__global__ void fill_sigma_t_kernel(const FsrArgs a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.n_fsr * a.G) return;
+  const int64_t r = idx / a.G;
+  const int e = (int)(idx - r * a.G);
+  a.qst[idx].y = a.sigma_t[(int64_t)a.fsr_mat[r] * a.G + e];
+}
+
+/* ---- addSourceToScalarFlux (src/CPUSolver.cpp:2608-2659; GPUSolver.cu:666-695)
+ *      fused with the nu-fission rate partial sums that computeKeff (:2258) and
+ *      normalizeFluxes (:1860) both need ---- */
+__global__ void __launch_bounds__(RED_THREADS)
+closure_kernel(const FsrArgs a, int neg_allowed, int with_rate) {
+  if (a.iscal[SI_DONE]) return;
+  const int G = a.G;
+  const int64_t n = a.n_fsr * G;
+  double local = 0.;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / G;
+    const int e = (int)(idx - r * G);
+    double volume = a.vol[r];
+    if (volume < VOL_EPSILON) volume = 1e30;
+    const double2 qs = a.qst[idx];
+    double f = a.phi[idx];
+    f /= (qs.y * volume);
+    f += FOUR_PI * qs.x / qs.y;
+    if (f < 0.0 && !neg_allowed) {
+      f = FLUX_EPSILON;
+      atomicAdd(&a.iscal[SI_NEG_FLUX], 1);
+    }
+    a.phi[idx] = f;
+    local += a.nu_sigma_f[(int64_t)a.fsr_mat[r] * G + e] * f * a.vol[r];
+  }
+  if (with_rate) {
+    const double s = block_sum(local);
+    if (threadIdx.x == 0) a.partials[blockIdx.x] = s;
+  }
+}
+
+/* nu-fission (which=0) / fission (1) / absorption-free generic rate partials:
+ * sum_r V_r sum_e sigma[e] phi[r,e]   (computeKeff :2279-2297, normalizeFluxes :1871-1888) */
+__global__ void __launch_bounds__(RED_THREADS)
+rate_partials_kernel(const FsrArgs a) {
+  if (a.iscal[SI_DONE]) return;
+  const int G = a.G;
+  const int64_t n = a.n_fsr * G;
+  double local = 0.;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / G;
+    const int e = (int)(idx - r * G);
+    local += a.nu_sigma_f[(int64_t)a.fsr_mat[r] * G + e] * a.phi[idx] * a.vol[r];
+  }
+  const double s = block_sum(local);
+  if (threadIdx.x == 0) a.partials[blockIdx.x] = s;
+}
+
+/* fold the rate partials; op 0: rate only, 1: k *= rate/N (computeKeff :2327),
+ * 2: norm = N/rate (normalizeFluxes :1910), 3: both (fused iteration) */
+__global__ void __launch_bounds__(RED_THREADS)
+rate_finalize_kernel(const FsrArgs a, int n_partials, int op) {
+  if (a.iscal[SI_DONE]) return;
+  const double rate = fold_partials(a.partials, n_partials);
+  if (threadIdx.x == 0) {
+    a.scal[SC_RATE] = rate;
+    if (op & 1) {
+      a.scal[SC_KPREV] = a.scal[SC_KEFF];
+      a.scal[SC_KEFF] *= rate / (double)a.n_fsr_global;
+    }
+    if (op & 2) a.scal[SC_NORM] = (double)a.n_fsr_global / rate;
+  }
+}
+
+/* phi *= norm (normalizeFluxes :1915-1919) */
+__global__ void scale_phi_kernel(const FsrArgs a) {
+  if (a.iscal[SI_DONE]) return;
+  const double norm = a.scal[SC_NORM];
+  const int64_t n = a.n_fsr * a.G;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x)
+    a.phi[idx] *= norm;
+}
+
+/* psi *= norm, float *= double rounded to float (normalizeFluxes :1922-1928) */
+__global__ void scale_psi_kernel(float* __restrict__ psi, int64_t n, const double* __restrict__ scal,
+                                 const int* __restrict__ iscal) {
+  if (iscal[SI_DONE]) return;
+  const double norm = scal[SC_NORM];
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x)
+    psi[idx] = (float)((double)psi[idx] * norm);
+}
+
+/* ---- computeResidual (src/CPUSolver.cpp:2113-2252; GPUSolver.cu:1728-1951's
+ *      ~25 Thrust calls) as one pass: one thread per FSR.  Options fuse
+ *      normalizeFluxes' phi scaling before and storeFSRFluxes (:1846) after. ---- */
+__global__ void __launch_bounds__(RED_THREADS)
+residual_kernel(const FsrArgs a, int res_type, int scale_first, int store_after) {
+  if (a.iscal[SI_DONE]) return;
+  const int G = a.G;
+  const double norm = scale_first ? a.scal[SC_NORM] : 1.0;
+  const double inv_k = 1.0 / a.scal[SC_KEFF];
+  double local = 0.;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_fsr;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const int m = a.fsr_mat[r];
+    double* __restrict__ ph = a.phi + r * G;
+    double* __restrict__ po = a.phi_old + r * G;
+    if (scale_first)
+      for (int e = 0; e < G; e++) ph[e] *= norm;
+    double res = 0.;
+    if (res_type == 0) {
+      for (int e = 0; e < G; e++)
+        if (po[e] > 0.) {
+          const double d = (ph[e] - po[e]) / po[e];
+          res += d * d;
+        }
+    } else if (res_type == 1) {
+      if (a.fissionable[m]) {
+        const double* __restrict__ nsf = a.nu_sigma_f + (int64_t)m * G;
+        double nw = 0., od = 0.;
+        for (int e = 0; e < G; e++) { nw += ph[e] * nsf[e]; od += po[e] * nsf[e]; }
+        if (od > 0.) { const double d = (nw - od) / od; res = d * d; }
+      }
+    } else {
+      double nw = 0., od = 0.;
+      if (a.fissionable[m]) {
+        const double* __restrict__ nsf = a.nu_sigma_f + (int64_t)m * G;
+        for (int e = 0; e < G; e++) { nw += ph[e] * nsf[e]; od += po[e] * nsf[e]; }
+        nw *= inv_k; od *= inv_k;
+      }
+      const double* __restrict__ ss = a.sigma_s + (int64_t)m * G * G;
+      for (int Gd = 0; Gd < G; Gd++)
+        for (int g = 0; g < G; g++) {
+          nw += ss[Gd * G + g] * ph[g];
+          od += ss[Gd * G + g] * po[g];
+        }
+      if (od > 0.) { const double d = (nw - od) / od; res = d * d; }
+    }
+    local += res;
+    if (store_after)
+      for (int e = 0; e < G; e++) po[e] = ph[e];
+  }
+  const double s = block_sum(local);
+  if (threadIdx.x == 0) a.partials[blockIdx.x] = s;
+}
+
+/* fold residual partials, RMS, and (fused loops) the stopping rule of
+ * Solver::computeEigenvalue (src/Solver.cpp:1643,1680): residual < tol and
+ * integer-truncated |delta-k| pcm < 1.  loop_kind 0: none, 1: eigenvalue,
+ * 2: flux/source loops (stop when i > 1 && residual < tol, :1409,:1506). */
+__global__ void __launch_bounds__(RED_THREADS)
+residual_finalize_kernel(const FsrArgs a, int n_partials, int res_type, int loop_kind, int iteration,
+                         double* __restrict__ hist_k, double* __restrict__ hist_res) {
+  if (a.iscal[SI_DONE]) return;
+  double residual = fold_partials(a.partials, n_partials);
+  if (threadIdx.x == 0) {
+    int64_t norm = (res_type == 1) ? a.n_fissionable : a.n_fsr_global;
+    if (residual < 0.0) residual = 0.0;
+    if (norm <= 0) norm = 1;
+    residual = sqrt(residual / (double)norm);
+    a.scal[SC_RESIDUAL] = residual;
+    if (loop_kind != 0) {
+      a.iscal[SI_ITERS] = iteration + 1;
+      a.iscal[SI_EXEC] = iteration + 1;   /* iterations that really ran on the device */
+      if (hist_k != nullptr) { hist_k[iteration] = a.scal[SC_KEFF]; hist_res[iteration] = residual; }
+      if (loop_kind == 1) {
+        const int dk = (int)(1e5 * (a.scal[SC_KEFF] - a.scal[SC_KPREV]));
+        if (residual < a.scal[SC_TOL] && abs(dk) < 1) a.iscal[SI_DONE] = 1;
+      } else {
+        if (iteration > 1 && residual < a.scal[SC_TOL]) { a.iscal[SI_DONE] = 1; a.iscal[SI_ITERS] = iteration; }
+      }
+    }
+  }
+}
+
+/* storeFSRFluxes / flattenFSRFluxes / flattenFSRFluxesChiSpectrum (:1846,:1816,:1829) */
+__global__ void copy_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t n,
+                            const int* __restrict__ iscal) {
+  if (iscal != nullptr && iscal[SI_DONE]) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void zero_phi_kernel(double* __restrict__ dst, int64_t n, const int* __restrict__ iscal) {
+  if (iscal[SI_DONE]) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) dst[i] = 0.0;
+}
+__global__ void fill_kernel(double* __restrict__ dst, double v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+__global__ void fill_chi_kernel(const FsrArgs a, int material) {
+  const int64_t n = a.n_fsr * a.G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) a.phi[i] = a.chi[(int64_t)material * a.G + (i % a.G)];
+}
+
+/* ---- computeStabilizingFlux / stabilizeFlux (src/CPUSolver.cpp:2665-2805;
+ *      the reference GPU solver only has GLOBAL, GPUSolver.cu:189-229) ----
+ * max_ratio[e] (YAMAMOTO) is a material-table quantity: computed on the host. */
+__global__ void stabilizing_flux_kernel(const FsrArgs a, int type, double factor,
+                                        const double* __restrict__ max_ratio) {
+  const int G = a.G;
+  const int64_t n = a.n_fsr * G;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / G;
+    const int e = (int)(idx - r * G);
+    const int m = a.fsr_mat[r];
+    if (type == 0) {
+      const double ss = a.sigma_s[((int64_t)m * G + e) * G + e];
+      if (ss < 0.0) a.stab[idx] = -a.phi[idx] * factor * ss / a.sigma_t[(int64_t)m * G + e];
+    } else if (type == 1) {
+      a.stab[idx] = a.phi[idx] * (max_ratio[e] * factor);
+    } else {
+      a.stab[idx] = (1.0 / factor - 1.0) * a.phi[idx];
+    }
+  }
+}
+__global__ void stabilize_flux_kernel(const FsrArgs a, int type, double factor,
+                                      const double* __restrict__ max_ratio) {
+  const int G = a.G;
+  const int64_t n = a.n_fsr * G;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / G;
+    const int e = (int)(idx - r * G);
+    const int m = a.fsr_mat[r];
+    if (type == 0) {
+      const double ss = a.sigma_s[((int64_t)m * G + e) * G + e];
+      if (ss < 0.0) {
+        double f = a.phi[idx] + a.stab[idx];
+        f /= (1.0 - factor * ss / a.sigma_t[(int64_t)m * G + e]);
+        a.phi[idx] = f;
+      }
+    } else if (type == 1) {
+      double f = a.phi[idx] + a.stab[idx];
+      f /= (1 + max_ratio[e] * factor);
+      a.phi[idx] = f;
+    } else {
+      a.phi[idx] = (a.phi[idx] + a.stab[idx]) * factor;
+    }
+  }
+}
+
+/* computeFSRFissionRates (src/CPUSolver.cpp:2825-2856; GPUSolver.cu:711-762) */
+__global__ void fission_rates_kernel(const FsrArgs a, double* __restrict__ out, int nu) {
+  const int G = a.G;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_fsr;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const double* __restrict__ sg = (nu ? a.nu_sigma_f : a.sigma_f) + (int64_t)a.fsr_mat[r] * G;
+    double v = 0.;
+    for (int e = 0; e < G; e++) v += sg[e] * a.phi[r * G + e] * a.vol[r];
+    out[r] = v;
+  }
+}
+
+__global__ void extract_q_kernel(const double2* __restrict__ qst, double* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) out[i] = qst[i].x;
+}
+__global__ void insert_q_kernel(double2* __restrict__ qst, const double* __restrict__ in, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) qst[i].x = in[i];
+}
+
+}  // namespace b200

@@ -1,0 +1,225 @@
+/*
+ * sweep.cuh - the MOC transport sweep as one sm_100a kernel.
+ *
+ * Replaces CPUSolver::transportSweep -> TransportSweep::onTrack ->
+ * tallyScalarFlux / accumulateScalarFluxContribution / transferBoundaryFlux
+ * (src/CPUSolver.cpp:2338-2601, src/TrackTraversingAlgorithms.cpp:890-1052) and
+ * the reference GPUSolver's transportSweepOnDevice (GPUSolver.cu:577-654).
+ *
+ * Work decomposition:
+ *   item   = (track, direction).  The sweep is Jacobi across tracks AND across
+ *            the two directions of one track (each reads its own start flux,
+ *            src/CPUSolver.cpp:2351,2586), so 2*N_trk items are independent.
+ *   lanes  = LPI consecutive lanes own one item; lane `sub` owns energy groups
+ *            sub, sub+LPI, ... (GPL of them) and all NP polar angles of each
+ *            (psi in registers, fp32 like the reference's float track flux).
+ *            G=7: LPI=7, four items per warp; G=70: LPI=10 x GPL=7, three items.
+ *   stream = segments of a track are contiguous SoA (f64 length, i32 FSR id);
+ *            lanes of an item read the same address (one L1 broadcast), two
+ *            segments are prefetched ahead, the {q, sigma_t} pair of the next
+ *            segment's FSR is gathered one step ahead as a single 16-byte load.
+ *   tally  = per-lane register accumulation while consecutive segments share an
+ *            FSR (mirrors TrackTraversingAlgorithms.cpp:982,1030), then one
+ *            fire-and-forget RED.ADD.F64 per (FSR, group).
+ */
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+/* ---- (1-exp(-x))/x, 5/6-order rational of src/exponentials.h:156-192 ---- */
+template <typename T> struct F1Coef;
+template <> struct F1Coef<double> {
+  static constexpr double p0 = 1.0, p1 = 2.4172687328033081e-1, p2 = 6.2804790965268531e-2,
+      p3 = 1.0567595009016521e-2, p4 = 1.0059468082903561e-3, p5 = 1.9309063097411041e-4;
+  static constexpr double d0 = 1.0, d1 = 7.4169266112320541e-1, d2 = 2.6722515319494311e-1,
+      d3 = 6.1643725066901411e-2, d4 = 1.0590759992367811e-2, d5 = 1.0057980007137651e-3,
+      d6 = 1.9309063097411041e-4;
+};
+template <> struct F1Coef<float> {
+  static constexpr float p0 = 1.0f, p1 = 2.4172687328033081e-1f, p2 = 6.2804790965268531e-2f,
+      p3 = 1.0567595009016521e-2f, p4 = 1.0059468082903561e-3f, p5 = 1.9309063097411041e-4f;
+  static constexpr float d0 = 1.0f, d1 = 7.4169266112320541e-1f, d2 = 2.6722515319494311e-1f,
+      d3 = 6.1643725066901411e-2f, d4 = 1.0590759992367811e-2f, d5 = 1.0057980007137651e-3f,
+      d6 = 1.9309063097411041e-4f;
+};
+
+/* 1/d for d >= 1: hardware seed + two Newton steps (4 DFMA) instead of the
+ * IEEE division slow path; the denominator polynomial is >= 1 for x >= 0. */
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+__device__ __forceinline__ float fast_rcp(float d) { return __frcp_rn(d); }
+
+template <typename T>
+__device__ __forceinline__ T expF1(T x) {
+  using C = F1Coef<T>;
+  T den = fma(C::d6, x, C::d5);
+  den = fma(den, x, C::d4);
+  den = fma(den, x, C::d3);
+  den = fma(den, x, C::d2);
+  den = fma(den, x, C::d1);
+  den = fma(den, x, C::d0);
+  T num = fma(C::p5, x, C::p4);
+  num = fma(num, x, C::p3);
+  num = fma(num, x, C::p2);
+  num = fma(num, x, C::p1);
+  num = fma(num, x, C::p0);
+  return num * fast_rcp(den);
+}
+
+struct SweepArgs {
+  /* segment stream */
+  const double* __restrict__ seg_len;
+  const int32_t* __restrict__ seg_fsr;
+  /* per track */
+  const int64_t* __restrict__ trk_off;     /* n_trk + 1 */
+  const int32_t* __restrict__ trk_class;   /* angle class -> rows of cls_w / cls_inv_sin */
+  const int32_t* __restrict__ order;       /* item>>1 -> track id */
+  /* per (track, dir) */
+  const int64_t* __restrict__ out_slot;    /* start-flux slot fed by this end, -1: none (vacuum) */
+  const uint8_t* __restrict__ carry;       /* 1: nobody feeds this slot -> copy psi_in through */
+  /* angle-class tables [n_class][NP] */
+  const double* __restrict__ cls_w;
+  const double* __restrict__ cls_inv_sin;
+  /* per (FSR, group): {q, sigma_t} */
+  const double2* __restrict__ qst;
+  /* fluxes */
+  const float* __restrict__ psi_in;
+  float* __restrict__ psi_out;
+  double* __restrict__ phi;                /* tally target [n_fsr*G] */
+  const int* __restrict__ done;            /* device convergence flag (may be NULL) */
+  int64_t n_items;
+  int G, lpi, ipw;
+};
+
+template <typename T, int NP, int GPL>
+__global__ void __launch_bounds__(128)
+sweep_kernel(const SweepArgs a) {
+  if (a.done != nullptr && *a.done) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int slot = lane / a.lpi;
+  const int sub = lane - slot * a.lpi;
+  const int64_t item = warp * a.ipw + slot;
+  if (slot >= a.ipw || item >= a.n_items) return;
+
+  const int G = a.G;
+  const int64_t t = a.order[item >> 1];
+  const int dir = (int)(item & 1);
+  const int64_t s0 = a.trk_off[t], s1 = a.trk_off[t + 1];
+  const int n = (int)(s1 - s0);
+  const int cls = a.trk_class[t];
+
+  /* energy groups of this lane (clamped duplicates are computed but never stored) */
+  int e[GPL];
+  bool valid[GPL];
+#pragma unroll
+  for (int j = 0; j < GPL; j++) {
+    int ej = sub + j * a.lpi;
+    valid[j] = ej < G;
+    e[j] = valid[j] ? ej : G - 1;
+  }
+
+  T w[NP], inv_sin[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    w[p] = (T)a.cls_w[cls * NP + p];
+    inv_sin[p] = (T)a.cls_inv_sin[cls * NP + p];
+  }
+
+  /* incoming angular flux */
+  const int F = G * NP;
+  const int64_t slot_in = (t * 2 + dir) * (int64_t)F;
+  float psi[NP][GPL];
+#pragma unroll
+  for (int p = 0; p < NP; p++)
+#pragma unroll
+    for (int j = 0; j < GPL; j++) psi[p][j] = a.psi_in[slot_in + p * G + e[j]];
+
+  if (a.carry[t * 2 + dir]) {
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+      for (int j = 0; j < GPL; j++)
+        if (valid[j]) a.psi_out[slot_in + p * G + e[j]] = psi[p][j];
+  }
+
+  double acc[GPL];
+#pragma unroll
+  for (int j = 0; j < GPL; j++) acc[j] = 0.0;
+
+  /* software pipeline: segment data two steps ahead, {q, sigma_t} one step ahead */
+  const int64_t step = dir ? -1 : 1;
+  int64_t s = dir ? s1 - 1 : s0;
+  double L0 = 0., L1 = 0.;
+  int f0 = -1, f1 = -1;
+  double2 qs0[GPL], qs1[GPL];
+  if (n > 0) { L0 = a.seg_len[s]; f0 = a.seg_fsr[s]; }
+  if (n > 1) { L1 = a.seg_len[s + step]; f1 = a.seg_fsr[s + step]; }
+  if (n > 0) {
+#pragma unroll
+    for (int j = 0; j < GPL; j++) qs0[j] = __ldg(&a.qst[(int64_t)f0 * G + e[j]]);
+  }
+
+  for (int i = 0; i < n; i++) {
+    double L2 = 0.;
+    int f2 = -1;
+    if (i + 2 < n) { L2 = a.seg_len[s + 2 * step]; f2 = a.seg_fsr[s + 2 * step]; }
+    if (i + 1 < n) {
+#pragma unroll
+      for (int j = 0; j < GPL; j++) qs1[j] = __ldg(&a.qst[(int64_t)f1 * G + e[j]]);
+    }
+
+    const T len = (T)L0;
+#pragma unroll
+    for (int j = 0; j < GPL; j++) {
+      const T tau = (T)qs0[j].y * len;        /* sigma_t * length */
+      const T lq = len * (T)qs0[j].x;          /* length * q */
+      T sum = (T)0;
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
+        /* ExpEvaluator::computeExponential (src/ExpEvaluator.h:170-183) */
+        const T ex = inv_sin[p] * expF1<T>(tau * inv_sin[p]);
+        const T dpsi = (tau * (T)psi[p][j] - lq) * ex;
+        psi[p][j] = (float)((T)psi[p][j] - dpsi);
+        sum = fma(w[p], dpsi, sum);
+      }
+      acc[j] += (double)sum;
+    }
+
+    /* flush before the FSR changes (and at the end of the track) */
+    if (f1 != f0) {
+#pragma unroll
+      for (int j = 0; j < GPL; j++) {
+        if (valid[j]) atomicAdd(&a.phi[(int64_t)f0 * G + e[j]], acc[j]);
+        acc[j] = 0.0;
+      }
+    }
+    L0 = L1; f0 = f1; L1 = L2; f1 = f2;
+#pragma unroll
+    for (int j = 0; j < GPL; j++) qs0[j] = qs1[j];
+    s += step;
+  }
+
+  /* transferBoundaryFlux (src/CPUSolver.cpp:2560-2601): reflective / periodic
+   * ends feed the next track's start flux; vacuum ends just drop it. */
+  const int64_t out = a.out_slot[t * 2 + dir];
+  if (out >= 0) {
+    const int64_t base = out * (int64_t)F;
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+      for (int j = 0; j < GPL; j++)
+        if (valid[j]) a.psi_out[base + p * G + e[j]] = psi[p][j];
+  }
+}
+
+}  // namespace b200

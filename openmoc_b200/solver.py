@@ -1,0 +1,350 @@
+"""Host-side mirror of the reference ``Solver`` interface on top of the C ABI.
+
+``B200Solver`` keeps the names, argument meaning and error behaviour of
+OpenMOC's ``Solver`` / ``CPUSolver`` public API (src/Solver.h:440-585,
+openmoc/swig/openmoc.i) so a script - or a parity test - written against
+``openmoc.CPUSolver`` reads the same here.  It takes the flattened tracks
+(``FlatTracks``; on the OpenMOC side ``b200_flatten`` produces them from a
+``TrackGenerator``) instead of the ``TrackGenerator`` object, because OpenMOC's
+SWIG module cannot be built in this image.  All numerics happen in
+``libb200moc.so``; this file only moves pointers.
+
+Multi-GPU (one process per GPU, ``torch.distributed``): tracks are partitioned by
+azimuthal reflective pair (``openmoc_b200.partition``), FSR data are replicated,
+and the raw FSR tally is summed with one all-reduce per sweep.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+from .capi import (B200Error, Config, FISSION_SOURCE, SCALAR_FLUX, TOTAL_SOURCE, DIAGONAL,
+                   PRECISION_DOUBLE, PRECISION_MIXED, check)
+from .trackfile import FlatTracks
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _DeviceArray:
+    """Exposes a raw device pointer through __cuda_array_interface__ (for torch)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+class B200Solver:
+    """B200 implementation of the OpenMOC source-iteration solver (flat source).
+
+    Parameters
+    ----------
+    tracks : FlatTracks        flattened TrackGenerator (see openmoc_b200.trackfile)
+    device : int               CUDA device ordinal
+    precision : int            capi.PRECISION_DOUBLE (reference double build) or PRECISION_MIXED
+    process_group : optional   torch.distributed group; when its world size > 1 the
+                               tracks are sharded by azimuthal pair across the ranks
+    """
+
+    def __init__(self, tracks: FlatTracks, device: int = 0, precision: int = PRECISION_DOUBLE,
+                 process_group=None, use_distributed: Optional[bool] = None):
+        self._lib = capi.load()
+        self._h = C.c_void_p()
+        self._global_tracks = tracks
+        self._dist = None
+        self._rank, self._world = 0, 1
+        if use_distributed is None:
+            use_distributed = process_group is not None
+        if use_distributed:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self._dist = dist
+                self._pg = process_group
+                self._rank = dist.get_rank(process_group)
+                self._world = dist.get_world_size(process_group)
+        if self._world > 1:
+            from .partition import partition_by_azim_pair
+            tracks = partition_by_azim_pair(tracks, self._world)[self._rank]
+        self.tracks = tracks
+        self._num_groups = tracks.num_groups
+        self._num_FSRs = tracks.n_fsrs
+        self._converge_thresh = 1e-5           # Solver.cpp default
+        self._num_iterations = 0
+        self._k_eff = 1.0
+        self._total_time = 0.0
+        self._device = device
+        self._phi_tensor = None
+
+        cfg = Config(num_groups=tracks.num_groups, num_azim=tracks.num_azim, num_polar=tracks.num_polar,
+                     solve_3d=tracks.solve_3d, n_tracks=tracks.n_tracks, n_segments=tracks.n_segments,
+                     n_fsrs=tracks.n_fsrs, n_materials=tracks.n_materials, device=device,
+                     precision=precision, deterministic=0, n_fsrs_global=tracks.n_fsrs)
+        check(self._lib.b200_create(C.byref(cfg), C.byref(self._h)))
+        self._upload(tracks)
+
+    # ------------------------------------------------------------------ setup
+    def _upload(self, ft: FlatTracks) -> None:
+        a = ft.arrays
+        c = lambda k, dt: np.ascontiguousarray(a[k], dtype=dt)
+        L, h = self._lib, self._h
+        keep = [c("seg_length", "f8"), c("seg_fsr", "i4"), c("trk_seg_offset", "i8"), c("trk_azim", "i4"),
+                c("trk_polar", "i4"), c("trk_next_fwd", "i8"), c("trk_next_bwd", "i8"), c("trk_flags", "u1"),
+                c("trk_bc_fwd", "u1"), c("trk_bc_bwd", "u1")]
+        check(L.b200_upload_tracks(h, *[_ptr(x) for x in keep]))
+        w, st = c("quad_weight", "f8"), c("quad_sin_theta", "f8")
+        check(L.b200_upload_quadrature(h, _ptr(w), _ptr(st)))
+        v, fm = c("fsr_volume", "f8"), c("fsr_mat", "i4")
+        check(L.b200_upload_fsrs(h, _ptr(v), _ptr(fm)))
+        mats = [c("mat_sigma_t", "f8"), c("mat_sigma_s", "f8"), c("mat_fiss_matrix", "f8"),
+                c("mat_nu_sigma_f", "f8"), c("mat_sigma_f", "f8"), c("mat_chi", "f8"),
+                c("mat_fissionable", "u1")]
+        check(L.b200_upload_materials(h, *[_ptr(x) for x in mats]))
+        check(L.b200_finalize(h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------- Solver getters / setters
+    def getNumIterations(self) -> int: return self._num_iterations
+    def getTotalTime(self) -> float: return self._total_time
+    def getConvergenceThreshold(self) -> float: return self._converge_thresh
+    def getNumEnergyGroups(self) -> int: return self._num_groups
+    def isUsingDoublePrecision(self) -> bool: return True
+    def is3D(self) -> bool: return bool(self.tracks.solve_3d)
+    def setNumThreads(self, num_threads: int) -> None: pass   # CPUSolver.cpp:132; no host threads here
+
+    def getKeff(self) -> float:
+        k = C.c_double()
+        check(self._lib.b200_get_keff(self._h, C.byref(k)))
+        self._k_eff = k.value
+        return k.value
+
+    def setConvergenceThreshold(self, threshold: float) -> None:
+        if threshold <= 0.0:   # Solver.cpp setConvergenceThreshold
+            raise B200Error("Unable to set the convergence threshold to %f since it is not a positive number"
+                            % threshold)
+        self._converge_thresh = float(threshold)
+
+    def getFluxes(self, num_fluxes: Optional[int] = None) -> np.ndarray:
+        """ARGOUT_ARRAY1 in the reference (numpy_typemaps.i:52): returns a new float64 array."""
+        n = self._num_FSRs * self._num_groups if num_fluxes is None else int(num_fluxes)
+        out = np.empty(n, dtype=np.float64)
+        check(self._lib.b200_get_fluxes(self._h, _ptr(out), n))
+        return out
+
+    def setFluxes(self, in_fluxes) -> None:
+        x = np.ascontiguousarray(in_fluxes, dtype=np.float64).ravel()
+        check(self._lib.b200_set_fluxes(self._h, _ptr(x), x.size))
+
+    def getFlux(self, fsr_id: int, group: int) -> float:
+        """1-based group like Solver::getFlux (Solver.cpp:277-305)."""
+        if fsr_id < 0 or fsr_id >= self._num_FSRs:
+            raise B200Error("Unable to return a scalar flux for FSR ID = %d since the max FSR ID = %d"
+                            % (fsr_id, self._num_FSRs - 1))
+        if group <= 0 or group > self._num_groups:
+            raise B200Error("Unable to return a scalar flux in group %d since there are only %d groups"
+                            % (group, self._num_groups))
+        return float(self.getFluxes()[fsr_id * self._num_groups + group - 1])
+
+    def getFSRSources(self) -> np.ndarray:
+        n = self._num_FSRs * self._num_groups
+        out = np.empty(n, dtype=np.float64)
+        check(self._lib.b200_get_fsr_sources(self._h, _ptr(out), n))
+        return out
+
+    def setFSRSources(self, q) -> None:
+        x = np.ascontiguousarray(q, dtype=np.float64).ravel()
+        check(self._lib.b200_set_fsr_sources(self._h, _ptr(x), x.size))
+
+    def getStartFluxes(self) -> np.ndarray:
+        n = self.tracks.n_tracks * 2 * self.tracks.fluxes_per_track
+        out = np.empty(n, dtype=np.float32)
+        check(self._lib.b200_get_start_fluxes(self._h, _ptr(out), n))
+        return out
+
+    def setStartFluxes(self, psi) -> None:
+        x = np.ascontiguousarray(psi, dtype=np.float32).ravel()
+        check(self._lib.b200_set_start_fluxes(self._h, _ptr(x), x.size))
+
+    def setFixedSourceByFSR(self, fsr_id: int, group: int, source: float) -> None:
+        check(self._lib.b200_set_fixed_source_by_fsr(self._h, int(fsr_id), int(group), float(source)))
+
+    def resetFixedSources(self) -> None:
+        check(self._lib.b200_reset_fixed_sources(self._h))
+
+    def computeFSRFissionRates(self, num_FSRs: Optional[int] = None, nu: bool = False) -> np.ndarray:
+        n = self._num_FSRs if num_FSRs is None else int(num_FSRs)
+        out = np.empty(n, dtype=np.float64)
+        check(self._lib.b200_compute_fsr_fission_rates(self._h, _ptr(out), n, int(nu)))
+        return out
+
+    def stabilizeTransport(self, stabilization_factor: float, stabilization_type: int = DIAGONAL) -> None:
+        check(self._lib.b200_stabilize_transport(self._h, float(stabilization_factor), int(stabilization_type)))
+
+    def allowNegativeFluxes(self, negative_fluxes_on: bool) -> None:
+        check(self._lib.b200_allow_negative_fluxes(self._h, int(bool(negative_fluxes_on))))
+
+    # ------------------------------------------------ Solver virtual steps (1:1)
+    def zeroTrackFluxes(self): check(self._lib.b200_zero_track_fluxes(self._h))
+    def flattenFSRFluxes(self, value): check(self._lib.b200_flatten_fsr_fluxes(self._h, float(value)))
+    def flattenFSRFluxesChiSpectrum(self, material): check(self._lib.b200_flatten_fsr_fluxes_chi_spectrum(self._h, int(material)))
+    def storeFSRFluxes(self): check(self._lib.b200_store_fsr_fluxes(self._h))
+    def computeStabilizingFlux(self): check(self._lib.b200_compute_stabilizing_flux(self._h))
+    def stabilizeFlux(self): check(self._lib.b200_stabilize_flux(self._h))
+    def computeFSRSources(self, iteration): check(self._lib.b200_compute_fsr_sources(self._h, int(iteration)))
+    def computeFSRFissionSources(self): check(self._lib.b200_compute_fsr_fission_sources(self._h))
+    def computeFSRScatterSources(self): check(self._lib.b200_compute_fsr_scatter_sources(self._h))
+    def addSourceToScalarFlux(self): check(self._lib.b200_add_source_to_scalar_flux(self._h))
+
+    def normalizeFluxes(self) -> float:
+        v = C.c_double()
+        check(self._lib.b200_normalize_fluxes(self._h, C.byref(v)))
+        return v.value
+
+    def computeResidual(self, res_type) -> float:
+        v = C.c_double()
+        check(self._lib.b200_compute_residual(self._h, int(res_type), C.byref(v)))
+        return v.value
+
+    def computeKeff(self) -> float:
+        v = C.c_double()
+        check(self._lib.b200_compute_keff(self._h, C.byref(v)))
+        self._k_eff = v.value
+        return v.value
+
+    def transportSweep(self) -> None:
+        """CPUSolver::transportSweep; with several ranks the per-rank FSR tallies
+        are summed here (replaces the MPI path of CPUSolver.cpp:2380-2384)."""
+        check(self._lib.b200_transport_sweep(self._h))
+        if self._world > 1:
+            self._allreduce_scalar_flux()
+
+    def _allreduce_scalar_flux(self) -> None:
+        import torch
+        if self._phi_tensor is None:
+            p, n = C.c_void_p(), C.c_int64()
+            check(self._lib.b200_device_pointer(self._h, b"scalar_flux", C.byref(p), C.byref(n)))
+            with torch.cuda.device(self._device):
+                # run the engine on torch's current stream so NCCL is ordered after the sweep
+                check(self._lib.b200_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                self._phi_tensor = torch.as_tensor(_DeviceArray(p.value, n.value, "<f8"),
+                                                   device=torch.device("cuda", self._device))
+        self._dist.all_reduce(self._phi_tensor, op=self._dist.ReduceOp.SUM, group=self._pg)
+
+    # ------------------------------------------------------------- drivers
+    def computeEigenvalue(self, max_iters: int = 1000, res_type: int = FISSION_SOURCE) -> None:
+        """Solver::computeEigenvalue (src/Solver.cpp:1542-1689), no CMFD."""
+        t0 = time.perf_counter()
+        if self._world == 1:
+            n = C.c_int32()
+            check(self._lib.b200_compute_eigenvalue(self._h, int(max_iters), self._converge_thresh,
+                                                    int(res_type), C.byref(n)))
+            self._num_iterations = n.value
+        else:
+            self._num_iterations = self._eigenvalue_loop(max_iters, res_type)
+        self.getKeff()
+        self._total_time = time.perf_counter() - t0
+
+    def _eigenvalue_loop(self, max_iters: int, res_type: int) -> int:
+        """The same loop driven step by step from the host (multi-GPU path)."""
+        check(self._lib.b200_set_keff(self._h, 1.0))
+        self.zeroTrackFluxes()
+        self.flattenFSRFluxes(0.0)
+        self.storeFSRFluxes()
+        self.flattenFSRFluxes(1.0)
+        self.normalizeFluxes()
+        self.storeFSRFluxes()
+        k_prev, iters = 1.0, 0
+        for i in range(max_iters):
+            self.computeFSRSources(i)
+            self.transportSweep()
+            self.addSourceToScalarFlux()
+            k = self.computeKeff()
+            self.normalizeFluxes()
+            residual = self.computeResidual(res_type)
+            dk = int(1e5 * (k - k_prev))
+            k_prev = k
+            self.storeFSRFluxes()
+            iters += 1
+            if residual < self._converge_thresh and abs(dk) < 1:
+                break
+        return iters
+
+    def computeFlux(self, max_iters: int = 1000, only_fixed_source: bool = True) -> None:
+        """Solver::computeFlux (src/Solver.cpp:1352-1420)."""
+        if self._world > 1:
+            raise B200Error("computeFlux is single-GPU in this build")
+        t0 = time.perf_counter()
+        n = C.c_int32()
+        check(self._lib.b200_compute_flux(self._h, int(max_iters), self._converge_thresh,
+                                          int(bool(only_fixed_source)), C.byref(n)))
+        self._num_iterations = n.value
+        self._total_time = time.perf_counter() - t0
+
+    def computeSource(self, max_iters: int = 1000, k_eff: float = 1.0, res_type: int = TOTAL_SOURCE) -> None:
+        """Solver::computeSource (src/Solver.cpp:1459-1516)."""
+        if self._world > 1:
+            raise B200Error("computeSource is single-GPU in this build")
+        t0 = time.perf_counter()
+        n = C.c_int32()
+        check(self._lib.b200_compute_source(self._h, int(max_iters), float(k_eff), self._converge_thresh,
+                                            int(res_type), C.byref(n)))
+        self._num_iterations = n.value
+        self._total_time = time.perf_counter() - t0
+
+    def fissionTransportSweep(self) -> None:
+        """Solver::fissionTransportSweep (src/Solver.cpp:1282-1287)."""
+        self.computeFSRFissionSources()
+        self.transportSweep()
+        self.addSourceToScalarFlux()
+
+    def scatterTransportSweep(self) -> None:
+        """Solver::scatterTransportSweep (src/Solver.cpp:1292-1297)."""
+        self.computeFSRScatterSources()
+        self.transportSweep()
+        self.addSourceToScalarFlux()
+
+    def iterate(self, n: int, res_type: int = FISSION_SOURCE):
+        """n fused source iterations without convergence test (benchmark hook)."""
+        if self._world > 1:
+            for i in range(n):
+                self.computeFSRSources(1000 + i)
+                self.transportSweep()
+                self.addSourceToScalarFlux()
+                self.computeKeff()
+                self.normalizeFluxes()
+                self.computeResidual(res_type)
+                self.storeFSRFluxes()
+            return
+        check(self._lib.b200_iterate(self._h, int(n), int(res_type), None, None))
+
+    # ------------------------------------------------------- instrumentation
+    def synchronize(self) -> None:
+        check(self._lib.b200_synchronize(self._h))
+
+    def getSweepStats(self):
+        """(accumulated sweep milliseconds, number of sweeps, kernel launches) - the
+        "Transport Sweep" timer split of the reference (Solver.cpp:1901-1929)."""
+        ms, ns, nl = C.c_double(), C.c_int64(), C.c_int64()
+        check(self._lib.b200_get_sweep_stats(self._h, C.byref(ms), C.byref(ns), C.byref(nl)))
+        return ms.value, ns.value, nl.value
+
+    def resetSweepStats(self) -> None:
+        check(self._lib.b200_reset_sweep_stats(self._h))
+
+    def integrationsPerSweep(self) -> int:
+        """W = 2 * F * N_seg of the reference's timer report (Solver.cpp:1901-1902)."""
+        return 2 * self.tracks.fluxes_per_track * self.tracks.n_segments

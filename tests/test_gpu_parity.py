@@ -1,0 +1,254 @@
+"""Parity of the CUDA path (through the C ABI) against the pinned CPU oracle and
+the reference's goldens.  Every test needs a GPU.
+
+Tolerances (north_star): k_eff within 1 pcm, FSR scalar flux within 1e-4 max
+relative error at the same convergence criterion.  The double path is in fact
+held to far tighter bounds (1e-9) so that regressions are visible.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_case
+from openmoc_b200 import capi
+from openmoc_b200.capi import FISSION_SOURCE, SCALAR_FLUX, TOTAL_SOURCE, PRECISION_DOUBLE, PRECISION_MIXED
+from oracle.oracle_py import OracleSolver, format_harness_results
+
+pytestmark = pytest.mark.gpu
+
+GOLDENS = json.load(open(os.path.join(GOLDEN, "ref_goldens.json")))
+CASES = ["pin_cell", "simple_lattice", "hom_inf", "lattice3d_7g", "lattice3d_70g", "c5g7_2d_coarse"]
+
+K_TOL_PCM = 1.0          # north_star
+PHI_RTOL = 1e-4          # north_star
+TIGHT = 2e-9             # what the double path actually achieves
+
+
+def make(name, precision=PRECISION_DOUBLE):
+    from openmoc_b200.solver import B200Solver
+    ft, ref = load_case(name)
+    return B200Solver(ft, precision=precision), OracleSolver(ft), ft, ref
+
+
+def rel_err(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+# ----------------------------------------------------------------- one sweep
+@pytest.mark.parametrize("name", CASES)
+def test_single_sweep_matches_oracle(name):
+    gpu, cpu, ft, _ = make(name)
+    rng = np.random.default_rng(1234)
+    q = rng.uniform(0.0, 1.0, ft.n_fsrs * ft.num_groups)
+    psi = rng.uniform(0.0, 1.0, ft.n_tracks * 2 * ft.fluxes_per_track).astype(np.float32)
+    for s in (gpu, cpu):
+        s.zeroTrackFluxes()
+    gpu.setFSRSources(q); cpu.setSources(q)
+    gpu.setStartFluxes(psi); cpu.setStartFluxes(psi)
+    gpu.transportSweep(); cpu.transportSweep()
+    phi_g, phi_c = gpu.getFluxes(), cpu.getFluxes()
+    np.testing.assert_allclose(phi_g, phi_c, rtol=1e-10, atol=1e-12 * np.abs(phi_c).max())
+    psi_g, psi_c = gpu.getStartFluxes(), cpu.getStartFluxes()
+    # float psi: the Newton reciprocal may differ from the IEEE division by 1 ulp of
+    # double, which can flip the last float bit
+    np.testing.assert_allclose(psi_g, psi_c, rtol=3e-7, atol=1e-12)
+    # a second sweep exercises the double-buffer hand-off
+    gpu.transportSweep(); cpu.transportSweep()
+    np.testing.assert_allclose(gpu.getFluxes(), cpu.getFluxes(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(gpu.getStartFluxes(), cpu.getStartFluxes(), rtol=1e-6, atol=1e-9)
+
+
+# ------------------------------------------------------------ step functions
+@pytest.mark.parametrize("name", ["simple_lattice", "lattice3d_70g"])
+def test_step_functions_match_oracle(name):
+    gpu, cpu, ft, _ = make(name)
+    rng = np.random.default_rng(7)
+    phi = rng.uniform(0.5, 1.5, ft.n_fsrs * ft.num_groups)
+    for s in (gpu, cpu):
+        s.zeroTrackFluxes()
+        s.setFluxes(phi)
+        s.storeFSRFluxes()
+    ng, nc = gpu.normalizeFluxes(), cpu.normalizeFluxes()
+    assert abs(ng - nc) / nc < 1e-13
+    np.testing.assert_allclose(gpu.getFluxes(), cpu.getFluxes(), rtol=1e-13)
+    gpu.computeFSRSources(0); cpu.computeFSRSources(0)
+    np.testing.assert_allclose(gpu.getFSRSources(), cpu.getSources(), rtol=1e-12, atol=1e-300)
+    gpu.transportSweep(); cpu.transportSweep()
+    gpu.addSourceToScalarFlux(); cpu.addSourceToScalarFlux()
+    np.testing.assert_allclose(gpu.getFluxes(), cpu.getFluxes(), rtol=1e-10)
+    kg = gpu.computeKeff(); cpu.computeKeff()
+    assert abs(kg - cpu.getKeff()) < 1e-11
+    for rt in (SCALAR_FLUX, FISSION_SOURCE, TOTAL_SOURCE):
+        rg, rc = gpu.computeResidual(rt), cpu.computeResidual(rt)
+        assert abs(rg - rc) <= 1e-9 * max(rc, 1e-30), (rt, rg, rc)
+    gpu.computeFSRFissionSources(); cpu.computeFSRFissionSources()
+    np.testing.assert_allclose(gpu.getFSRSources(), cpu.getSources(), rtol=1e-12, atol=1e-300)
+    gpu.computeFSRScatterSources(); cpu.computeFSRScatterSources()
+    np.testing.assert_allclose(gpu.getFSRSources(), cpu.getSources(), rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(gpu.computeFSRFissionRates(nu=True), cpu.computeFSRFissionRates(nu=True), rtol=1e-12)
+
+
+# -------------------------------------------------------- converged solutions
+def solve_both(name, tol, max_iters=500, precision=PRECISION_DOUBLE):
+    gpu, cpu, ft, ref = make(name, precision)
+    gpu.setConvergenceThreshold(tol)
+    gpu.computeEigenvalue(max_iters, FISSION_SOURCE)
+    cpu.computeEigenvalue(max_iters, tol, FISSION_SOURCE)
+    return gpu, cpu, ft, ref
+
+
+@pytest.mark.parametrize("name,tol", [("pin_cell", 1e-5), ("simple_lattice", 1e-5), ("hom_inf", 1e-5),
+                                      ("lattice3d_7g", 1e-5), ("lattice3d_70g", 5e-3)])
+def test_eigenvalue_matches_oracle_and_reference(name, tol):
+    gpu, cpu, ft, ref = solve_both(name, tol)
+    dk_pcm = abs(gpu.getKeff() - cpu.getKeff()) * 1e5
+    assert dk_pcm < K_TOL_PCM
+    assert dk_pcm < 1e-4, dk_pcm                       # tight
+    assert gpu.getNumIterations() == cpu.getNumIterations() == ref["iterations"]
+    assert rel_err(gpu.getFluxes(), cpu.getFluxes()) < TIGHT
+    # against the unmodified reference CPUSolver's own run
+    assert abs(gpu.getKeff() - ref["keff"]) * 1e5 < 1e-4
+    if "fluxes" in ref:
+        assert rel_err(gpu.getFluxes(), np.array(ref["fluxes"])) < TIGHT
+
+
+def test_pin_cell_golden_bytes_from_gpu():
+    gpu, _, _, _ = solve_both("pin_cell", 1e-5)
+    out = format_harness_results(gpu.getNumIterations(), gpu.getKeff(), gpu.getFluxes())
+    assert out == GOLDENS["test_forward_pin_cell"]
+
+
+def test_simple_lattice_golden_sha512_from_gpu():
+    gpu, _, _, _ = solve_both("simple_lattice", 1e-5)
+    out = format_harness_results(gpu.getNumIterations(), gpu.getKeff(), gpu.getFluxes())
+    assert hashlib.sha512(out.encode()).hexdigest() == GOLDENS["test_forward_simple_lattice"].strip()
+
+
+def test_3d_goldens_from_gpu():
+    gpu, _, _, _ = solve_both("lattice3d_70g", 5e-3)
+    assert format_harness_results(gpu.getNumIterations(), gpu.getKeff()) == GOLDENS["test_forward_3D_lattice_70g"]
+    gpu, _, _, _ = solve_both("lattice3d_7g", 1e-5)
+    assert format_harness_results(gpu.getNumIterations(), gpu.getKeff()) == GOLDENS["test_forward_3D_lattice"]
+
+
+def test_c5g7_coarse_40_iterations():
+    gpu, cpu, ft, ref = solve_both("c5g7_2d_coarse", 1e-5, max_iters=40)
+    assert gpu.getNumIterations() == 40
+    assert abs(gpu.getKeff() - ref["keff"]) * 1e5 < 1e-3
+    assert rel_err(gpu.getFluxes(), cpu.getFluxes()) < 1e-8
+
+
+@pytest.mark.parametrize("name,tol", [("pin_cell", 1e-5), ("simple_lattice", 1e-5), ("lattice3d_70g", 5e-3)])
+def test_mixed_precision_within_north_star_tolerance(name, tol):
+    gpu, cpu, ft, ref = solve_both(name, tol, precision=PRECISION_MIXED)
+    assert abs(gpu.getKeff() - cpu.getKeff()) * 1e5 < K_TOL_PCM
+    assert rel_err(gpu.getFluxes(), cpu.getFluxes()) < PHI_RTOL
+    assert abs(gpu.getNumIterations() - cpu.getNumIterations()) <= 1
+
+
+def test_step_loop_equals_fused_loop():
+    """Driving the virtual steps one by one (what Solver::computeEigenvalue does
+    through B200Solver) gives the same answer as the fused device-side loop."""
+    gpu, cpu, ft, ref = solve_both("simple_lattice", 1e-5)
+    from openmoc_b200.solver import B200Solver
+    step = B200Solver(ft)
+    step.setConvergenceThreshold(1e-5)
+    n = step._eigenvalue_loop(500, FISSION_SOURCE)
+    assert n == gpu.getNumIterations()
+    assert abs(step.getKeff() - gpu.getKeff()) < 1e-12
+    assert rel_err(step.getFluxes(), gpu.getFluxes()) < 1e-10
+
+
+# ------------------------------------------------------- fixed-source drivers
+def test_compute_flux_fixed_source():
+    gpu, cpu, ft, _ = make("simple_lattice")
+    for s in (gpu, cpu):
+        s.setFixedSourceByFSR(3, 1, 1.0)
+        s.setFixedSourceByFSR(100, 2, 0.5)
+    gpu.setConvergenceThreshold(1e-6)
+    gpu.computeFlux(300)
+    cpu.computeFlux(300, 1e-6)
+    assert gpu.getNumIterations() == cpu.getNumIterations()
+    np.testing.assert_allclose(gpu.getFluxes(), cpu.getFluxes(), rtol=1e-8, atol=1e-14)
+
+
+def test_compute_source_subcritical():
+    gpu, cpu, ft, _ = make("pin_cell")
+    for s in (gpu, cpu):
+        s.setFixedSourceByFSR(1, 1, 1.0)
+    gpu.setConvergenceThreshold(1e-6)
+    gpu.computeSource(500, k_eff=1.5, res_type=TOTAL_SOURCE)
+    cpu.computeSource(500, 1.5, 1e-6, TOTAL_SOURCE)
+    assert gpu.getNumIterations() == cpu.getNumIterations()
+    np.testing.assert_allclose(gpu.getFluxes(), cpu.getFluxes(), rtol=1e-8)
+
+
+def test_stabilized_eigenvalue_matches_oracle():
+    for stab_type in (0, 1, 2):
+        gpu, cpu, ft, _ = make("pin_cell")
+        gpu.stabilizeTransport(0.5, stab_type); cpu.stabilizeTransport(0.5, stab_type)
+        gpu.setConvergenceThreshold(1e-5)
+        gpu.computeEigenvalue(600, FISSION_SOURCE)
+        cpu.computeEigenvalue(600, 1e-5, FISSION_SOURCE)
+        assert gpu.getNumIterations() == cpu.getNumIterations(), stab_type
+        assert abs(gpu.getKeff() - cpu.getKeff()) * 1e5 < 1e-3
+        assert rel_err(gpu.getFluxes(), cpu.getFluxes()) < 1e-8
+
+
+# ----------------------------------------------------------- properties / API
+def test_sweep_is_linear_in_source_and_flux():
+    """Size-independent property: one sweep is linear in (q, psi_in)."""
+    gpu, _, ft, _ = make("c5g7_2d_coarse")
+    rng = np.random.default_rng(3)
+    n_q, n_psi = ft.n_fsrs * ft.num_groups, ft.n_tracks * 2 * ft.fluxes_per_track
+    def sweep(q, psi):
+        gpu.setFSRSources(q); gpu.setStartFluxes(psi); gpu.transportSweep()
+        return gpu.getFluxes()
+    q1, q2 = rng.uniform(0, 1, n_q), rng.uniform(0, 1, n_q)
+    z = np.zeros(n_psi, dtype=np.float32)
+    a, b, c = sweep(q1, z), sweep(q2, z), sweep(q1 + q2, z)
+    np.testing.assert_allclose(a + b, c, rtol=2e-6, atol=1e-9)     # psi is fp32
+    # zero source and zero incoming flux give exactly zero
+    assert np.all(sweep(np.zeros(n_q), z) == 0.0)
+
+
+def test_get_set_and_error_behaviour():
+    gpu, _, ft, _ = make("pin_cell")
+    x = np.arange(ft.n_fsrs * ft.num_groups, dtype=float) + 1
+    gpu.setFluxes(x)
+    assert np.array_equal(gpu.getFluxes(), x)
+    assert gpu.getFlux(1, 2) == x[ft.num_groups + 1]
+    with pytest.raises(capi.B200Error):
+        gpu.getFluxes(5)
+    with pytest.raises(capi.B200Error):
+        gpu.setFixedSourceByFSR(0, 8, 1.0)          # group out of range (1-based)
+    with pytest.raises(capi.B200Error):
+        gpu.setFixedSourceByFSR(99, 1, 1.0)
+    with pytest.raises(capi.B200Error):
+        gpu.getFlux(0, 0)
+    with pytest.raises(capi.B200Error):
+        gpu.computeSource(10, k_eff=-1.0)
+    with pytest.raises(capi.B200Error):
+        gpu.setConvergenceThreshold(0.0)
+
+
+def test_fission_residual_without_fissionable_fsrs_errors():
+    from openmoc_b200.solver import B200Solver
+    ft, _ = load_case("pin_cell")
+    ft.arrays["mat_fissionable"] = np.zeros_like(ft.arrays["mat_fissionable"])
+    s = B200Solver(ft)
+    with pytest.raises(capi.B200Error, match="FISSION_SOURCE"):
+        s.computeResidual(FISSION_SOURCE)
+
+
+def test_sweep_stats_count_integrations():
+    gpu, _, ft, _ = make("simple_lattice")
+    gpu.resetSweepStats()
+    gpu.iterate(5)
+    gpu.synchronize()
+    ms, n_sweeps, launches = gpu.getSweepStats()
+    assert n_sweeps == 5 and launches >= 5 and ms > 0
+    assert gpu.integrationsPerSweep() == 2 * 21 * 1984
