@@ -71,7 +71,12 @@ int main(int argc, char** argv) {
   else if (quad_name == "gl") quad = new GLPolarQuad();
   else if (quad_name == "equal-weight") quad = new EqualWeightPolarQuad();
   else if (quad_name == "leonard") quad = new LeonardPolarQuad();
-  if (quad != NULL) quad->setNumPolarAngles(num_polar);
+  if (quad != NULL) {
+    /* without the azimuthal count generateTracks() silently discards a user
+     * quadrature (src/TrackGenerator.cpp:802-806) */
+    quad->setNumAzimAngles(num_azim);
+    quad->setNumPolarAngles(num_polar);
+  }
 
   TrackGenerator* tg;
   if (dims == 3) {

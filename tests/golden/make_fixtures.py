@@ -28,8 +28,10 @@ CASES = {
     "lattice3d_7g": ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2",
                      "--spacing", "0.24", "--zspacing", "0.9"],                       # test_forward_3D_lattice
     "hom_inf": ["--model", "hom-inf", "--azim", "4", "--spacing", "0.1"],            # test_forward_hom_inf_medium
+    # C3 deck, coarse tracks.  Default (TY) quadrature: that is what c5g7-2d.py really runs, its
+    # EqualAnglePolarQuad is discarded by generateTracks for want of setNumAzimAngles.
     "c5g7_2d_coarse": ["--model", "c5g7-2d", "--azim", "4", "--spacing", "0.5", "--polar", "6",
-                       "--quad", "equal-angle", "--max-iters", "40", "--no-fluxes"],  # C3 deck, coarse tracks
+                       "--max-iters", "40", "--no-fluxes"],
 }
 
 def main():
