@@ -745,8 +745,10 @@ extern "C" int b200_compute_residual(b200_solver* s, int32_t res_type, double* r
     return fail("The Solver is unable to compute a FISSION_SOURCE residual without fissionable FSRs");
   if (clear_done(s)) return 1;
   if (launch_residual(s, res_type, 0, 0, 0, 0)) return 1;
-  if (fetch_scalars(s)) return 1;
-  if (residual != nullptr) *residual = s->h_scal[SC_RESIDUAL];
+  if (residual != nullptr) {      /* NULL: leave the value on the device, no host sync */
+    if (fetch_scalars(s)) return 1;
+    *residual = s->h_scal[SC_RESIDUAL];
+  }
   return 0;
 }
 

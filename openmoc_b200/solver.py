@@ -209,21 +209,37 @@ class B200Solver:
     def computeFSRScatterSources(self): check(self._lib.b200_compute_fsr_scatter_sources(self._h))
     def addSourceToScalarFlux(self): check(self._lib.b200_add_source_to_scalar_flux(self._h))
 
-    def normalizeFluxes(self) -> float:
+    def normalizeFluxes(self, fetch: bool = True):
+        """fetch=False leaves the factor on the device (no host synchronisation)."""
+        if not fetch:
+            check(self._lib.b200_normalize_fluxes(self._h, None))
+            return None
         v = C.c_double()
         check(self._lib.b200_normalize_fluxes(self._h, C.byref(v)))
         return v.value
 
-    def computeResidual(self, res_type) -> float:
+    def computeResidual(self, res_type, fetch: bool = True):
+        if not fetch:
+            check(self._lib.b200_compute_residual(self._h, int(res_type), None))
+            return None
         v = C.c_double()
         check(self._lib.b200_compute_residual(self._h, int(res_type), C.byref(v)))
         return v.value
 
-    def computeKeff(self) -> float:
+    def computeKeff(self, fetch: bool = True):
+        if not fetch:
+            check(self._lib.b200_compute_keff(self._h, None))
+            return None
         v = C.c_double()
         check(self._lib.b200_compute_keff(self._h, C.byref(v)))
         self._k_eff = v.value
         return v.value
+
+    def useTorchStream(self) -> None:
+        """Launch on torch's current CUDA stream (so torch events / NCCL order with us)."""
+        import torch
+        with torch.cuda.device(self._device):
+            check(self._lib.b200_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
     def transportSweep(self) -> None:
         """CPUSolver::transportSweep; with several ranks the per-rank FSR tallies
@@ -237,9 +253,9 @@ class B200Solver:
         if self._phi_tensor is None:
             p, n = C.c_void_p(), C.c_int64()
             check(self._lib.b200_device_pointer(self._h, b"scalar_flux", C.byref(p), C.byref(n)))
+            # run the engine on torch's current stream so NCCL is ordered after the sweep
+            self.useTorchStream()
             with torch.cuda.device(self._device):
-                # run the engine on torch's current stream so NCCL is ordered after the sweep
-                check(self._lib.b200_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
                 self._phi_tensor = torch.as_tensor(_DeviceArray(p.value, n.value, "<f8"),
                                                    device=torch.device("cuda", self._device))
         self._dist.all_reduce(self._phi_tensor, op=self._dist.ReduceOp.SUM, group=self._pg)
@@ -324,9 +340,9 @@ class B200Solver:
                 self.computeFSRSources(1000 + i)
                 self.transportSweep()
                 self.addSourceToScalarFlux()
-                self.computeKeff()
-                self.normalizeFluxes()
-                self.computeResidual(res_type)
+                self.computeKeff(fetch=False)
+                self.normalizeFluxes(fetch=False)
+                self.computeResidual(res_type, fetch=False)
                 self.storeFSRFluxes()
             return
         check(self._lib.b200_iterate(self._h, int(n), int(res_type), None, None))
