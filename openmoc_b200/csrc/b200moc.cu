@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -136,7 +137,7 @@ struct b200_solver {
   int* h_iscal = nullptr;
 
   /* sweep launch geometry */
-  int gpl = 1, lpi = 1, ipw = 1;
+  int gpl = 1, lpi = 1, ipc = 32;   /* groups/thread, threads/item, items/CTA */
   int64_t sweep_blocks = 0;
 
   /* options */
@@ -366,17 +367,27 @@ extern "C" int b200_upload_materials(b200_solver* s, const double* sigma_t, cons
   return 0;
 }
 
-/* choose groups-per-lane so that lanes-per-item * items-per-warp fills the warp */
-static void choose_lane_map(int G, int* gpl, int* lpi, int* ipw) {
+/* Groups per thread (GPL) and threads per item (LPI = ceil(G/GPL) <= 32).  With the
+ * flat thread->item mapping every LPI fills the warps, so prefer the smallest GPL
+ * (fewest registers, most resident warps) whose slots are >= 95 % used. */
+static void choose_lane_map(int G, int* gpl, int* lpi, int* ipc) {
   static const int cand[] = {1, 2, 3, 4, 7, 8};
+  const char* force = getenv("B200_GPL");
   double best = -1.;
+  *gpl = 0;
   for (int c : cand) {
+    if (force != nullptr && atoi(force) != c) continue;
     int l = (G + c - 1) / c;
     if (l > 32) continue;
-    int i = 32 / l;
-    double util = (double)i * G / (32.0 * c);
-    if (util > best + 1e-9) { best = util; *gpl = c; *lpi = l; *ipw = i; }
+    double util = (double)G / ((double)c * l);
+    if (util >= 0.95) { *gpl = c; *lpi = l; break; }
+    if (util > best) { best = util; *gpl = c; *lpi = l; }
   }
+  if (*gpl == 0) { *gpl = 8; *lpi = (G + 7) / 8; }
+  /* items per CTA: keep CTAs at <= 256 threads */
+  *ipc = (*lpi <= 8) ? 32 : (*lpi <= 16 ? 16 : 8);
+  const char* fipc = getenv("B200_IPC");
+  if (fipc != nullptr && atoi(fipc) > 0 && atoi(fipc) * *lpi <= 256) *ipc = atoi(fipc);
 }
 
 extern "C" int b200_finalize(b200_solver* s) {
@@ -471,10 +482,9 @@ extern "C" int b200_finalize(b200_solver* s) {
   }
   CU(s->max_ratio.upload(mr.data(), s->G, s->stream));
 
-  choose_lane_map(s->G, &s->gpl, &s->lpi, &s->ipw);
+  choose_lane_map(s->G, &s->gpl, &s->lpi, &s->ipc);
   const int64_t n_items = 2 * nt;
-  const int64_t warps = (n_items + s->ipw - 1) / s->ipw;
-  s->sweep_blocks = (warps + 3) / 4;   /* 128 threads = 4 warps per CTA */
+  s->sweep_blocks = (n_items + s->ipc - 1) / s->ipc;
 
   FsrArgs a = fsr_args(s);
   fill_sigma_t_kernel<<<grid_for(nphi, 256, 1 << 30), 256, 0, s->stream>>>(a);
@@ -556,11 +566,11 @@ static int launch_sweep(b200_solver* s) {
     a.carry = s->carry.p; a.cls_w = s->cls_w.p; a.cls_inv_sin = s->cls_inv_sin.p;
     a.qst = s->qst.p; a.psi_in = s->psi_start; a.psi_out = s->psi_other; a.phi = s->phi.p;
     a.done = s->iscal.p + SI_DONE;
-    a.n_items = 2 * s->n_trk; a.G = s->G; a.lpi = s->lpi; a.ipw = s->ipw;
+    a.n_items = 2 * s->n_trk; a.G = s->G; a.lpi = s->lpi;
     sweep_fn fn = s->cfg.precision == B200_PRECISION_MIXED ? pick_np<float>(s->NP, s->gpl)
                                                            : pick_np<double>(s->NP, s->gpl);
     if (fn == nullptr) return fail("no sweep kernel for NP=%d GPL=%d", s->NP, s->gpl);
-    fn<<<(unsigned)s->sweep_blocks, 128, 0, s->stream>>>(a);
+    fn<<<(unsigned)s->sweep_blocks, s->lpi * s->ipc, 0, s->stream>>>(a);
     CU(cudaGetLastError());
     s->n_launches++;
   }

@@ -10,10 +10,11 @@
  *   item   = (track, direction).  The sweep is Jacobi across tracks AND across
  *            the two directions of one track (each reads its own start flux,
  *            src/CPUSolver.cpp:2351,2586), so 2*N_trk items are independent.
- *   lanes  = LPI consecutive lanes own one item; lane `sub` owns energy groups
+ *   lanes  = LPI consecutive threads own one item; thread `sub` owns energy groups
  *            sub, sub+LPI, ... (GPL of them) and all NP polar angles of each
  *            (psi in registers, fp32 like the reference's float track flux).
- *            G=7: LPI=7, four items per warp; G=70: LPI=10 x GPL=7, three items.
+ *            G=7: LPI=7, 32 items per 224-thread CTA (items may straddle warps,
+ *            so no lane idles); G=70: LPI=10 x GPL=7.
  *   stream = segments of a track are contiguous SoA (f64 length, i32 FSR id);
  *            lanes of an item read the same address (one L1 broadcast), two
  *            segments are prefetched ahead, the {q, sigma_t} pair of the next
@@ -97,19 +98,19 @@ struct SweepArgs {
   double* __restrict__ phi;                /* tally target [n_fsr*G] */
   const int* __restrict__ done;            /* device convergence flag (may be NULL) */
   int64_t n_items;
-  int G, lpi, ipw;
+  int G, lpi;
 };
 
 template <typename T, int NP, int GPL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 sweep_kernel(const SweepArgs a) {
   if (a.done != nullptr && *a.done) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int slot = lane / a.lpi;
-  const int sub = lane - slot * a.lpi;
-  const int64_t item = warp * a.ipw + slot;
-  if (slot >= a.ipw || item >= a.n_items) return;
+  /* flat mapping: LPI consecutive threads own one item; an item may straddle two
+   * warps (no warp collectives are used), so every lane of every warp is busy */
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t item = gtid / a.lpi;
+  const int sub = (int)(gtid - item * a.lpi);
+  if (item >= a.n_items) return;
 
   const int G = a.G;
   const int64_t t = a.order[item >> 1];
