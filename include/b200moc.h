@@ -133,6 +133,11 @@ int b200_compute_source(b200_solver* s, int32_t max_iters, double k_eff, double 
  * benchmark hook.  residual/k of the last iteration are returned if non-NULL */
 int b200_iterate(b200_solver* s, int32_t n, int32_t res_type, double* k_eff, double* residual);
 
+/* the device's (1-exp(-x))/x, i.e. expF1_fractional (src/exponentials.h:156-192), evaluated
+ * for n host values - the hook for the reference's known-answer vectors
+ * (tests/unit_tests/test_exponentials.py:74-77) */
+int b200_eval_expF1(int32_t device, int32_t precision, const double* x, int64_t n, double* out);
+
 /* ---- instrumentation (the "Transport Sweep" timer split, src/CPUSolver.cpp:2365-2378) ---- */
 int b200_get_sweep_stats(b200_solver* s, double* sweep_ms_total, int64_t* num_sweeps,
                          int64_t* kernel_launches);

@@ -79,7 +79,8 @@ SIGNATURES = {
     "b200_set_stream": [_vp],
 }
 #: every symbol include/b200moc.h declares (checked by tests/test_abi.py)
-EXPORTS = sorted(list(SIGNATURES) + ["b200_last_error", "b200_version", "b200_device_count", "b200_create"])
+EXPORTS = sorted(list(SIGNATURES) + ["b200_last_error", "b200_version", "b200_device_count", "b200_create",
+                                      "b200_eval_expF1"])
 
 
 def load():
@@ -99,12 +100,23 @@ def load():
     L.b200_device_count.restype = C.c_int
     L.b200_create.restype = C.c_int
     L.b200_create.argtypes = [C.POINTER(Config), C.POINTER(_vp)]
+    L.b200_eval_expF1.restype = C.c_int
+    L.b200_eval_expF1.argtypes = [_i32, _i32, _vp, _i64, _vp]
     for name, args in SIGNATURES.items():
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [_vp] + args
     _lib = L
     return L
+
+
+def eval_expF1(x, precision: int = PRECISION_DOUBLE, device: int = 0):
+    """Device evaluation of expF1_fractional for an array of optical lengths."""
+    import numpy as np
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    check(load().b200_eval_expF1(device, precision, x.ctypes.data_as(_vp), x.size, out.ctypes.data_as(_vp)))
+    return out
 
 
 def check(status: int) -> None:

@@ -117,6 +117,7 @@ struct b200_solver {
   /* device: tracks */
   DevBuf<double> seg_len;
   DevBuf<int32_t> seg_fsr;
+  DevBuf<SegRec> seg_rec;
   DevBuf<int64_t> trk_off, out_slot;
   DevBuf<int32_t> trk_class, order;
   DevBuf<uint8_t> carry;
@@ -243,7 +244,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   cudaStreamSynchronize(s->stream);
   for (auto& p : s->ev_pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto& p : s->ev_free) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-  s->seg_len.release(); s->seg_fsr.release(); s->trk_off.release(); s->out_slot.release();
+  s->seg_len.release(); s->seg_fsr.release(); s->seg_rec.release(); s->trk_off.release(); s->out_slot.release();
   s->trk_class.release(); s->order.release(); s->carry.release(); s->cls_w.release();
   s->cls_inv_sin.release(); s->fsr_mat.release(); s->vol.release(); s->sigma_t.release();
   s->sigma_s.release(); s->fiss.release(); s->nu_sigma_f.release(); s->sigma_f.release();
@@ -482,6 +483,15 @@ extern "C" int b200_finalize(b200_solver* s) {
   }
   CU(s->max_ratio.upload(mr.data(), s->G, s->stream));
 
+  /* device segment stream: padded 16-byte records with the FSR id premultiplied by G */
+  if ((double)s->n_fsr * s->G >= 4294967296.0)
+    return fail("b200_finalize: n_fsrs*G = %.3g exceeds the 32-bit tally index of this build", (double)s->n_fsr * s->G);
+  if (s->seg_len.n != (size_t)s->n_seg) return fail("b200_finalize: tracks must be re-uploaded before finalize");
+  CU(s->seg_rec.alloc((size_t)s->n_seg + 2 * SEG_PAD));
+  build_segrec_kernel<<<grid_for(s->n_seg + 2 * SEG_PAD, 256), 256, 0, s->stream>>>(
+      s->seg_rec.p, s->seg_len.p, s->seg_fsr.p, s->n_seg, s->G);
+  CU(cudaGetLastError());
+
   choose_lane_map(s->G, &s->gpl, &s->lpi, &s->ipc);
   const int64_t n_items = 2 * nt;
   s->sweep_blocks = (n_items + s->ipc - 1) / s->ipc;
@@ -561,7 +571,7 @@ static int launch_sweep(b200_solver* s) {
   s->n_launches++;
   if (s->n_trk > 0) {
     SweepArgs a;
-    a.seg_len = s->seg_len.p; a.seg_fsr = s->seg_fsr.p; a.trk_off = s->trk_off.p;
+    a.seg = s->seg_rec.p + SEG_PAD; a.trk_off = s->trk_off.p;
     a.trk_class = s->trk_class.p; a.order = s->order.p; a.out_slot = s->out_slot.p;
     a.carry = s->carry.p; a.cls_w = s->cls_w.p; a.cls_inv_sin = s->cls_inv_sin.p;
     a.qst = s->qst.p; a.psi_in = s->psi_start; a.psi_out = s->psi_other; a.phi = s->phi.p;
@@ -1025,6 +1035,30 @@ extern "C" int b200_compute_source(b200_solver* s, int32_t max_iters, double k_e
   if (b200_flatten_fsr_fluxes(s, 1.0)) return 1;
   if (b200_store_fsr_fluxes(s)) return 1;
   return flux_source_loop(s, max_iters, tol, res_type, true, num_iterations);
+}
+
+/* ------------------------------------------------------------------------- */
+/* exponential evaluator exposed for known-answer tests                        */
+/* ------------------------------------------------------------------------- */
+__global__ void eval_expf1_kernel(const double* __restrict__ x, double* __restrict__ out, int64_t n, int precision) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = precision == B200_PRECISION_MIXED ? (double)expF1((float)x[i]) : expF1(x[i]);
+}
+
+extern "C" int b200_eval_expF1(int32_t device, int32_t precision, const double* x, int64_t n, double* out) {
+  if (!x || !out || n < 0) return fail("b200_eval_expF1: bad argument");
+  CU(cudaSetDevice(device));
+  double *dx = nullptr, *dout = nullptr;
+  if (n == 0) return 0;
+  CU(cudaMalloc((void**)&dx, n * 8));
+  CU(cudaMalloc((void**)&dout, n * 8));
+  CU(cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice));
+  eval_expf1_kernel<<<grid_for(n, 256), 256>>>(dx, dout, n, precision);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dx);
+  cudaFree(dout);
+  return 0;
 }
 
 /* ------------------------------------------------------------------------- */

@@ -15,10 +15,11 @@
  *            (psi in registers, fp32 like the reference's float track flux).
  *            G=7: LPI=7, 32 items per 224-thread CTA (items may straddle warps,
  *            so no lane idles); G=70: LPI=10 x GPL=7.
- *   stream = segments of a track are contiguous SoA (f64 length, i32 FSR id);
- *            lanes of an item read the same address (one L1 broadcast), two
- *            segments are prefetched ahead, the {q, sigma_t} pair of the next
- *            segment's FSR is gathered one step ahead as a single 16-byte load.
+ *   stream = segments of a track are contiguous 16-byte records {f64 length,
+ *            u32 FSR*G}; threads of an item read the same address (one L1
+ *            broadcast, one LDG.128), the record two steps ahead and the
+ *            {q, sigma_t} pair of the next segment's FSR (a single 16-byte
+ *            gather) are in flight while the current segment is attenuated.
  *   tally  = per-lane register accumulation while consecutive segments share an
  *            FSR (mirrors TrackTraversingAlgorithms.cpp:982,1030), then one
  *            fire-and-forget RED.ADD.F64 per (FSR, group).
@@ -59,6 +60,29 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }
 __device__ __forceinline__ float fast_rcp(float d) { return __frcp_rn(d); }
 
+/* The double coefficients live in constant memory so that every DFMA takes its
+ * coefficient straight from the constant bank: as literals the compiler
+ * re-materialises all 13 of them with 23 UMOV/IMAD.MOV per segment. */
+__constant__ double c_F1[13] = {
+    F1Coef<double>::d1, F1Coef<double>::d2, F1Coef<double>::d3, F1Coef<double>::d4,
+    F1Coef<double>::d5, F1Coef<double>::d6, F1Coef<double>::p1, F1Coef<double>::p2,
+    F1Coef<double>::p3, F1Coef<double>::p4, F1Coef<double>::p5, 1.0, 0.0};
+
+__device__ __forceinline__ double expF1(double x) {
+  double den = fma(c_F1[5], x, c_F1[4]);
+  den = fma(den, x, c_F1[3]);
+  den = fma(den, x, c_F1[2]);
+  den = fma(den, x, c_F1[1]);
+  den = fma(den, x, c_F1[0]);
+  den = fma(den, x, 1.0);
+  double num = fma(c_F1[10], x, c_F1[9]);
+  num = fma(num, x, c_F1[8]);
+  num = fma(num, x, c_F1[7]);
+  num = fma(num, x, c_F1[6]);
+  num = fma(num, x, 1.0);
+  return num * fast_rcp(den);
+}
+
 template <typename T>
 __device__ __forceinline__ T expF1(T x) {
   using C = F1Coef<T>;
@@ -76,10 +100,20 @@ __device__ __forceinline__ T expF1(T x) {
   return num * fast_rcp(den);
 }
 
+/* One segment of the device stream: 16 bytes, read with a single LDG.128.
+ * `base` is the FSR id premultiplied by G, so {q, sigma_t} and the tally slot of
+ * group e sit at element base + e (32-bit index arithmetic in the hot loop). */
+struct __align__(16) SegRec {
+  double len;
+  uint32_t base;
+  uint32_t spare;
+};
+constexpr int SEG_PAD = 2;   /* sentinel records before and after the stream */
+
 struct SweepArgs {
-  /* segment stream */
-  const double* __restrict__ seg_len;
-  const int32_t* __restrict__ seg_fsr;
+  /* segment stream, padded by SEG_PAD records at both ends; element i of the
+   * logical stream is seg[i] (the pointer already skips the front padding) */
+  const SegRec* __restrict__ seg;
   /* per track */
   const int64_t* __restrict__ trk_off;     /* n_trk + 1 */
   const int32_t* __restrict__ trk_class;   /* angle class -> rows of cls_w / cls_inv_sin */
@@ -120,13 +154,13 @@ sweep_kernel(const SweepArgs a) {
   const int cls = a.trk_class[t];
 
   /* energy groups of this lane (clamped duplicates are computed but never stored) */
-  int e[GPL];
+  uint32_t e[GPL];
   bool valid[GPL];
 #pragma unroll
   for (int j = 0; j < GPL; j++) {
     int ej = sub + j * a.lpi;
     valid[j] = ej < G;
-    e[j] = valid[j] ? ej : G - 1;
+    e[j] = (uint32_t)(valid[j] ? ej : G - 1);
   }
 
   T w[NP], inv_sin[NP];
@@ -157,27 +191,26 @@ sweep_kernel(const SweepArgs a) {
 #pragma unroll
   for (int j = 0; j < GPL; j++) acc[j] = 0.0;
 
-  /* software pipeline: segment data two steps ahead, {q, sigma_t} one step ahead */
-  const int64_t step = dir ? -1 : 1;
-  int64_t s = dir ? s1 - 1 : s0;
-  double L0 = 0., L1 = 0.;
-  int f0 = -1, f1 = -1;
+  /* Software pipeline: the segment record two steps ahead and the {q, sigma_t}
+   * pair one step ahead are in flight while the current segment is attenuated.
+   * The stream is padded, so the look-ahead needs no bounds predicate: past the
+   * end of the track it reads the neighbouring track's (or a sentinel) record,
+   * whose only effect is an early flush of the tally. */
+  const int step = dir ? -1 : 1;
+  const SegRec* __restrict__ ps = a.seg + (dir ? s1 - 1 : s0);
+  const int4 r0 = __ldg(reinterpret_cast<const int4*>(ps));
+  const int4 r1 = __ldg(reinterpret_cast<const int4*>(ps + step));
+  double L0 = __hiloint2double(r0.y, r0.x), L1 = __hiloint2double(r1.y, r1.x);
+  uint32_t b0 = (uint32_t)r0.z, b1 = (uint32_t)r1.z;
   double2 qs0[GPL], qs1[GPL];
-  if (n > 0) { L0 = a.seg_len[s]; f0 = a.seg_fsr[s]; }
-  if (n > 1) { L1 = a.seg_len[s + step]; f1 = a.seg_fsr[s + step]; }
-  if (n > 0) {
 #pragma unroll
-    for (int j = 0; j < GPL; j++) qs0[j] = __ldg(&a.qst[(int64_t)f0 * G + e[j]]);
-  }
+  for (int j = 0; j < GPL; j++) qs0[j] = __ldg(&a.qst[b0 + e[j]]);
+  ps += 2 * step;
 
   for (int i = 0; i < n; i++) {
-    double L2 = 0.;
-    int f2 = -1;
-    if (i + 2 < n) { L2 = a.seg_len[s + 2 * step]; f2 = a.seg_fsr[s + 2 * step]; }
-    if (i + 1 < n) {
+    const int4 r2 = __ldg(reinterpret_cast<const int4*>(ps));
 #pragma unroll
-      for (int j = 0; j < GPL; j++) qs1[j] = __ldg(&a.qst[(int64_t)f1 * G + e[j]]);
-    }
+    for (int j = 0; j < GPL; j++) qs1[j] = __ldg(&a.qst[b1 + e[j]]);
 
     const T len = (T)L0;
 #pragma unroll
@@ -188,7 +221,7 @@ sweep_kernel(const SweepArgs a) {
 #pragma unroll
       for (int p = 0; p < NP; p++) {
         /* ExpEvaluator::computeExponential (src/ExpEvaluator.h:170-183) */
-        const T ex = inv_sin[p] * expF1<T>(tau * inv_sin[p]);
+        const T ex = inv_sin[p] * expF1(tau * inv_sin[p]);
         const T dpsi = (tau * (T)psi[p][j] - lq) * ex;
         psi[p][j] = (float)((T)psi[p][j] - dpsi);
         sum = fma(w[p], dpsi, sum);
@@ -196,18 +229,27 @@ sweep_kernel(const SweepArgs a) {
       acc[j] += (double)sum;
     }
 
-    /* flush before the FSR changes (and at the end of the track) */
-    if (f1 != f0) {
+    /* flush before the FSR changes */
+    if (b1 != b0) {
 #pragma unroll
       for (int j = 0; j < GPL; j++) {
-        if (valid[j]) atomicAdd(&a.phi[(int64_t)f0 * G + e[j]], acc[j]);
+        if (valid[j]) atomicAdd(&a.phi[b0 + e[j]], acc[j]);
         acc[j] = 0.0;
       }
     }
-    L0 = L1; f0 = f1; L1 = L2; f1 = f2;
+    L0 = L1; b0 = b1;
+    L1 = __hiloint2double(r2.y, r2.x); b1 = (uint32_t)r2.z;
 #pragma unroll
     for (int j = 0; j < GPL; j++) qs0[j] = qs1[j];
-    s += step;
+    ps += step;
+  }
+  /* the look-ahead may have hidden the last FSR change: flush what is left.  b0 has
+   * been rotated once past the last segment, so recompute its slot from the stream. */
+  if (n > 0) {
+    const uint32_t blast = a.seg[dir ? s0 : s1 - 1].base;
+#pragma unroll
+    for (int j = 0; j < GPL; j++)
+      if (valid[j] && acc[j] != 0.0) atomicAdd(&a.phi[blast + e[j]], acc[j]);
   }
 
   /* transferBoundaryFlux (src/CPUSolver.cpp:2560-2601): reflective / periodic
@@ -220,6 +262,21 @@ sweep_kernel(const SweepArgs a) {
 #pragma unroll
       for (int j = 0; j < GPL; j++)
         if (valid[j]) a.psi_out[base + p * G + e[j]] = psi[p][j];
+  }
+}
+
+/* builds the padded SegRec stream from the uploaded SoA arrays (once per upload) */
+__global__ void build_segrec_kernel(SegRec* __restrict__ out, const double* __restrict__ len,
+                                    const int32_t* __restrict__ fsr, int64_t n_seg, int G) {
+  const int64_t total = n_seg + 2 * SEG_PAD;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i - SEG_PAD;
+    SegRec r;
+    if (s >= 0 && s < n_seg) { r.len = len[s]; r.base = (uint32_t)fsr[s] * (uint32_t)G; }
+    else { r.len = 0.0; r.base = 0u; }
+    r.spare = 0u;
+    out[i] = r;
   }
 }
 

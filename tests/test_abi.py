@@ -13,7 +13,7 @@ from openmoc_b200 import capi
 
 def header_symbols():
     text = open(os.path.join(ROOT, "include", "b200moc.h")).read()
-    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(b200_[A-Za-z0-9_]+)\s*\(", text)))
 
 
 def test_header_and_binding_agree():

@@ -37,6 +37,26 @@ def rel_err(a, b):
     return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
 
 
+# ------------------------------------------------------- exponential evaluator
+def test_expF1_known_answers_and_oracle():
+    # tests/unit_tests/test_exponentials.py:13,74-77 (expF1_fractional), tol 1e-8 there
+    taus = np.array([1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1, 10, 100])
+    expect = np.array([0.9999999950003422, 0.9999999500034228, 0.9999995000343784, 0.9999950003587617,
+                       0.9999500050851808, 0.9995002005718668, 0.9950169413610763, 0.9516272442309586,
+                       0.6321211831479621, 0.09999547551656497, 0.010000005017389789])
+    got = capi.eval_expF1(taus)
+    assert np.all(np.abs(got - expect) < 1e-8)
+    # dense comparison against the oracle's plain-C rational, over the whole range the
+    # solver can see (segments are split at tau = 100, polar factor up to ~6)
+    from oracle.oracle_py import lib
+    x = np.concatenate([np.linspace(0, 20, 20001), np.logspace(-12, 3, 3001)])
+    ref = np.array([lib().moc_oracle_expF1(v) for v in x])
+    got = capi.eval_expF1(x)
+    assert np.max(np.abs(got - ref) / ref) < 4e-16          # Newton reciprocal: <= 1-2 ulp
+    got32 = capi.eval_expF1(x, precision=PRECISION_MIXED)
+    assert np.max(np.abs(got32 - ref) / ref) < 5e-7
+
+
 # ----------------------------------------------------------------- one sweep
 @pytest.mark.parametrize("name", CASES)
 def test_single_sweep_matches_oracle(name):
