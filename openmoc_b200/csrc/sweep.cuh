@@ -59,6 +59,12 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return r;
 }
 __device__ __forceinline__ float fast_rcp(float d) { return __frcp_rn(d); }
+__device__ __forceinline__ double fast_rcp_seed(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  return r;
+}
+__device__ __forceinline__ float fast_rcp_seed(float d) { return __frcp_rn(d); }
 
 /* The double coefficients live in constant memory so that every DFMA takes its
  * coefficient straight from the constant bank: as literals the compiler
@@ -103,12 +109,65 @@ __device__ __forceinline__ T expF1(T x) {
 /* One segment of the device stream: 16 bytes, read with a single LDG.128.
  * `base` is the FSR id premultiplied by G, so {q, sigma_t} and the tally slot of
  * group e sit at element base + e (32-bit index arithmetic in the hot loop). */
+/* NP rationals at once, every Horner step issued for all of them before the next */
+template <typename T, int NP>
+__device__ __forceinline__ void expF1_batch(const T (&x)[NP], T (&out)[NP]) {
+  T den[NP], num[NP];
+  if constexpr (sizeof(T) == 8) {
+#pragma unroll
+    for (int p = 0; p < NP; p++) den[p] = fma(c_F1[5], x[p], c_F1[4]);
+#pragma unroll
+    for (int p = 0; p < NP; p++) num[p] = fma(c_F1[10], x[p], c_F1[9]);
+#pragma unroll
+    for (int k = 3; k >= 0; k--) {
+#pragma unroll
+      for (int p = 0; p < NP; p++) den[p] = fma(den[p], x[p], c_F1[k]);
+#pragma unroll
+      for (int p = 0; p < NP; p++) num[p] = fma(num[p], x[p], k > 0 ? c_F1[5 + k] : 1.0);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; p++) den[p] = fma(den[p], x[p], 1.0);
+  } else {
+    using C = F1Coef<float>;
+    const float dc[6] = {C::d1, C::d2, C::d3, C::d4, C::d5, C::d6};
+    const float pc[5] = {C::p1, C::p2, C::p3, C::p4, C::p5};
+#pragma unroll
+    for (int p = 0; p < NP; p++) den[p] = fma(dc[5], x[p], dc[4]);
+#pragma unroll
+    for (int p = 0; p < NP; p++) num[p] = fma(pc[4], x[p], pc[3]);
+#pragma unroll
+    for (int k = 3; k >= 0; k--) {
+#pragma unroll
+      for (int p = 0; p < NP; p++) den[p] = fma(den[p], x[p], dc[k]);
+#pragma unroll
+      for (int p = 0; p < NP; p++) num[p] = fma(num[p], x[p], k > 0 ? pc[k - 1] : 1.0f);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; p++) den[p] = fma(den[p], x[p], 1.0f);
+  }
+  T r[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) r[p] = fast_rcp_seed(den[p]);
+  if constexpr (sizeof(T) == 8) {
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+      T e[NP];
+#pragma unroll
+      for (int p = 0; p < NP; p++) e[p] = fma(-den[p], r[p], (T)1);
+#pragma unroll
+      for (int p = 0; p < NP; p++) r[p] = fma(r[p], e[p], r[p]);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) out[p] = num[p] * r[p];
+}
+
 struct __align__(16) SegRec {
   double len;
   uint32_t base;
   uint32_t spare;
 };
-constexpr int SEG_PAD = 2;   /* sentinel records before and after the stream */
+constexpr int SEG_PAD = 40;  /* sentinel records before and after the stream (covers look-ahead + L2 prefetch distance) */
 
 struct SweepArgs {
   /* segment stream, padded by SEG_PAD records at both ends; element i of the
@@ -207,7 +266,12 @@ sweep_kernel(const SweepArgs a) {
   for (int j = 0; j < GPL; j++) qs0[j] = __ldg(&a.qst[b0 + e[j]]);
   ps += 2 * step;
 
+  double* __restrict__ const phi = a.phi;
+  constexpr int PF_DIST = 24;   /* records: three 128-byte lines ahead of the register look-ahead */
   for (int i = 0; i < n; i++) {
+    /* pull the stream (DRAM, read once) into L2 ahead of use, once per 128-byte line */
+    if ((reinterpret_cast<uintptr_t>(ps) & 0x70) == 0)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + PF_DIST * step));
     const int4 r2 = __ldg(reinterpret_cast<const int4*>(ps));
 #pragma unroll
     for (int j = 0; j < GPL; j++) qs1[j] = __ldg(&a.qst[b1 + e[j]]);
@@ -217,11 +281,17 @@ sweep_kernel(const SweepArgs a) {
     for (int j = 0; j < GPL; j++) {
       const T tau = (T)qs0[j].y * len;        /* sigma_t * length */
       const T lq = len * (T)qs0[j].x;          /* length * q */
+      /* ExpEvaluator::computeExponential (src/ExpEvaluator.h:170-183) for the NP polar
+       * angles in lock-step: NP independent Horner chains keep the FP64 pipe fed
+       * instead of one dependent chain after the other */
+      T x[NP], f1[NP];
+#pragma unroll
+      for (int p = 0; p < NP; p++) x[p] = tau * inv_sin[p];
+      expF1_batch<T, NP>(x, f1);
       T sum = (T)0;
 #pragma unroll
       for (int p = 0; p < NP; p++) {
-        /* ExpEvaluator::computeExponential (src/ExpEvaluator.h:170-183) */
-        const T ex = inv_sin[p] * expF1(tau * inv_sin[p]);
+        const T ex = inv_sin[p] * f1[p];
         const T dpsi = (tau * (T)psi[p][j] - lq) * ex;
         psi[p][j] = (float)((T)psi[p][j] - dpsi);
         sum = fma(w[p], dpsi, sum);
@@ -233,7 +303,7 @@ sweep_kernel(const SweepArgs a) {
     if (b1 != b0) {
 #pragma unroll
       for (int j = 0; j < GPL; j++) {
-        if (valid[j]) atomicAdd(&a.phi[b0 + e[j]], acc[j]);
+        if (valid[j]) atomicAdd(&phi[b0 + e[j]], acc[j]);
         acc[j] = 0.0;
       }
     }
@@ -249,7 +319,7 @@ sweep_kernel(const SweepArgs a) {
     const uint32_t blast = a.seg[dir ? s0 : s1 - 1].base;
 #pragma unroll
     for (int j = 0; j < GPL; j++)
-      if (valid[j] && acc[j] != 0.0) atomicAdd(&a.phi[blast + e[j]], acc[j]);
+      if (valid[j] && acc[j] != 0.0) atomicAdd(&phi[blast + e[j]], acc[j]);
   }
 
   /* transferBoundaryFlux (src/CPUSolver.cpp:2560-2601): reflective / periodic
