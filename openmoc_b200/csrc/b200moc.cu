@@ -139,6 +139,8 @@ struct b200_solver {
 
   /* sweep launch geometry */
   int gpl = 1, lpi = 1, ipc = 32;   /* groups/thread, threads/item, items/CTA */
+  bool staged = true;               /* cp.async-staged sweep (default) vs register-pipelined */
+  bool smem_attr_set = false;
   int64_t sweep_blocks = 0;
 
   /* options */
@@ -495,6 +497,8 @@ extern "C" int b200_finalize(b200_solver* s) {
   choose_lane_map(s->G, &s->gpl, &s->lpi, &s->ipc);
   const int64_t n_items = 2 * nt;
   s->sweep_blocks = (n_items + s->ipc - 1) / s->ipc;
+  s->staged = !(getenv("B200_SWEEP") != nullptr && !strcmp(getenv("B200_SWEEP"), "regs"));
+  s->smem_attr_set = false;
 
   FsrArgs a = fsr_args(s);
   fill_sigma_t_kernel<<<grid_for(nphi, 256, 1 << 30), 256, 0, s->stream>>>(a);
@@ -508,6 +512,32 @@ extern "C" int b200_finalize(b200_solver* s) {
 /* sweep dispatch                                                             */
 /* ------------------------------------------------------------------------- */
 typedef void (*sweep_fn)(const SweepArgs);
+
+constexpr int STAGE_DQ = 4;   /* gathers 4 segments ahead, records 8 ahead */
+template <typename T, int NP>
+static sweep_fn pick_gpl_staged(int gpl) {
+  switch (gpl) {
+    case 1: return sweep_kernel_staged<T, NP, 1, STAGE_DQ>;
+    case 2: return sweep_kernel_staged<T, NP, 2, STAGE_DQ>;
+    case 3: return sweep_kernel_staged<T, NP, 3, STAGE_DQ>;
+    case 4: return sweep_kernel_staged<T, NP, 4, STAGE_DQ>;
+    case 7: return sweep_kernel_staged<T, NP, 7, STAGE_DQ>;
+    case 8: return sweep_kernel_staged<T, NP, 8, STAGE_DQ>;
+  }
+  return nullptr;
+}
+template <typename T>
+static sweep_fn pick_np_staged(int np, int gpl) {
+  switch (np) {
+    case 1: return pick_gpl_staged<T, 1>(gpl);
+    case 2: return pick_gpl_staged<T, 2>(gpl);
+    case 3: return pick_gpl_staged<T, 3>(gpl);
+    case 4: return pick_gpl_staged<T, 4>(gpl);
+    case 5: return pick_gpl_staged<T, 5>(gpl);
+    case 6: return pick_gpl_staged<T, 6>(gpl);
+  }
+  return nullptr;
+}
 
 template <typename T, int NP>
 static sweep_fn pick_gpl(int gpl) {
@@ -577,10 +607,22 @@ static int launch_sweep(b200_solver* s) {
     a.qst = s->qst.p; a.psi_in = s->psi_start; a.psi_out = s->psi_other; a.phi = s->phi.p;
     a.done = s->iscal.p + SI_DONE;
     a.n_items = 2 * s->n_trk; a.G = s->G; a.lpi = s->lpi;
-    sweep_fn fn = s->cfg.precision == B200_PRECISION_MIXED ? pick_np<float>(s->NP, s->gpl)
-                                                           : pick_np<double>(s->NP, s->gpl);
+    const bool mixed = s->cfg.precision == B200_PRECISION_MIXED;
+    const int nthr = s->lpi * s->ipc;
+    sweep_fn fn;
+    size_t smem = 0;
+    if (s->staged) {
+      fn = mixed ? pick_np_staged<float>(s->NP, s->gpl) : pick_np_staged<double>(s->NP, s->gpl);
+      smem = (size_t)nthr * 16 * (2 * STAGE_DQ + STAGE_DQ * s->gpl);
+    } else {
+      fn = mixed ? pick_np<float>(s->NP, s->gpl) : pick_np<double>(s->NP, s->gpl);
+    }
     if (fn == nullptr) return fail("no sweep kernel for NP=%d GPL=%d", s->NP, s->gpl);
-    fn<<<(unsigned)s->sweep_blocks, s->lpi * s->ipc, 0, s->stream>>>(a);
+    if (smem > 48 * 1024 && !s->smem_attr_set) {
+      CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      s->smem_attr_set = true;
+    }
+    fn<<<(unsigned)s->sweep_blocks, nthr, smem, s->stream>>>(a);
     CU(cudaGetLastError());
     s->n_launches++;
   }

@@ -195,7 +195,7 @@ struct SweepArgs {
 };
 
 template <typename T, int NP, int GPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (GPL == 1 ? 3 : 1))
 sweep_kernel(const SweepArgs a) {
   if (a.done != nullptr && *a.done) return;
   /* flat mapping: LPI consecutive threads own one item; an item may straddle two
@@ -324,6 +324,162 @@ sweep_kernel(const SweepArgs a) {
 
   /* transferBoundaryFlux (src/CPUSolver.cpp:2560-2601): reflective / periodic
    * ends feed the next track's start flux; vacuum ends just drop it. */
+  const int64_t out = a.out_slot[t * 2 + dir];
+  if (out >= 0) {
+    const int64_t base = out * (int64_t)F;
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+      for (int j = 0; j < GPL; j++)
+        if (valid[j]) a.psi_out[base + p * G + e[j]] = psi[p][j];
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Staged variant: the segment records and the {q, sigma_t} gathers are copied  */
+/* global -> shared with cp.async (LDGSTS) into per-thread rings, DQ segments    */
+/* ahead for the gathers and 2*DQ ahead for the records, so neither DRAM nor L2   */
+/* latency is ever waited for and no register holds in-flight data (ptxas sinks   */
+/* plain look-ahead loads next to their use, which exposed ~20 % long-scoreboard  */
+/* stalls in the register-pipelined kernel above: profiles/).                     */
+/* Rings are laid out [slot][thread] in 16-byte words: conflict-free LDS.128.     */
+/* ------------------------------------------------------------------------- */
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+template <typename T, int NP, int GPL, int DQ>
+__global__ void __launch_bounds__(256)
+sweep_kernel_staged(const SweepArgs a) {
+  constexpr int D = 2 * DQ;                 /* record look-ahead (power of two) */
+  extern __shared__ int4 smem[];            /* [D][nthr] records, then [DQ][GPL][nthr] {q, sigma_t} */
+  if (a.done != nullptr && *a.done) return;
+  const int nthr = blockDim.x;
+  const int tid = threadIdx.x;
+  const int64_t gtid = (int64_t)blockIdx.x * nthr + tid;
+  const int64_t item = gtid / a.lpi;
+  const int sub = (int)(gtid - item * a.lpi);
+  if (item >= a.n_items) return;            /* no block-wide barrier is used below */
+
+  int4* const rec_ring = smem + tid;                       /* slot stride nthr */
+  int4* const qs_ring = smem + D * nthr + tid;             /* slot stride GPL*nthr, group stride nthr */
+  const uint32_t rec_s = (uint32_t)__cvta_generic_to_shared(rec_ring);
+  const uint32_t qs_s = (uint32_t)__cvta_generic_to_shared(qs_ring);
+  const uint32_t slot_b = (uint32_t)nthr * 16u;
+
+  const int G = a.G;
+  const int64_t t = a.order[item >> 1];
+  const int dir = (int)(item & 1);
+  const int64_t s0 = a.trk_off[t], s1 = a.trk_off[t + 1];
+  const int n = (int)(s1 - s0);
+  const int cls = a.trk_class[t];
+
+  uint32_t e[GPL];
+  bool valid[GPL];
+#pragma unroll
+  for (int j = 0; j < GPL; j++) {
+    int ej = sub + j * a.lpi;
+    valid[j] = ej < G;
+    e[j] = (uint32_t)(valid[j] ? ej : G - 1);
+  }
+  T w[NP], inv_sin[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    w[p] = (T)a.cls_w[cls * NP + p];
+    inv_sin[p] = (T)a.cls_inv_sin[cls * NP + p];
+  }
+  const int F = G * NP;
+  const int64_t slot_in = (t * 2 + dir) * (int64_t)F;
+  float psi[NP][GPL];
+#pragma unroll
+  for (int p = 0; p < NP; p++)
+#pragma unroll
+    for (int j = 0; j < GPL; j++) psi[p][j] = a.psi_in[slot_in + p * G + e[j]];
+  if (a.carry[t * 2 + dir]) {
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+      for (int j = 0; j < GPL; j++)
+        if (valid[j]) a.psi_out[slot_in + p * G + e[j]] = psi[p][j];
+  }
+  double acc[GPL];
+#pragma unroll
+  for (int j = 0; j < GPL; j++) acc[j] = 0.0;
+
+  const int step = dir ? -1 : 1;
+  const SegRec* __restrict__ const first = a.seg + (dir ? s1 - 1 : s0);
+  const double2* __restrict__ const qst = a.qst;
+  double* __restrict__ const phi = a.phi;
+
+  /* prologue: records 0..D-DQ-1 synchronously, then DQ groups {rec[D-DQ+j], qs[j]} */
+#pragma unroll
+  for (int k = 0; k < D - DQ; k++) cp_async16(rec_s + k * slot_b, first + k * step);
+  cp_async_commit();
+  cp_async_wait<0>();
+#pragma unroll
+  for (int j = 0; j < DQ; j++) {
+    cp_async16(rec_s + (D - DQ + j) * slot_b, first + (D - DQ + j) * step);
+    const uint32_t bj = (uint32_t)rec_ring[j * nthr].z;
+#pragma unroll
+    for (int g = 0; g < GPL; g++) cp_async16(qs_s + (j * GPL + g) * slot_b, qst + (bj + e[g]));
+    cp_async_commit();
+  }
+  int4 rc = rec_ring[0];
+  double L0 = __hiloint2double(rc.y, rc.x);
+  uint32_t b0 = (uint32_t)rc.z;
+
+  for (int i = 0; i < n; i++) {
+    cp_async_wait<DQ - 1>();                /* group of step i-DQ: qs[i], rec[i+DQ] have landed */
+    const int sr = i & (D - 1), sq = i & (DQ - 1);
+    double2 qs[GPL];
+#pragma unroll
+    for (int g = 0; g < GPL; g++) {
+      const int4 v = qs_ring[(sq * GPL + g) * nthr];
+      qs[g] = make_double2(__hiloint2double(v.y, v.x), __hiloint2double(v.w, v.z));
+    }
+    const int4 rn = rec_ring[((i + 1) & (D - 1)) * nthr];            /* next record (flush test) */
+    const uint32_t bq = (uint32_t)rec_ring[((i + DQ) & (D - 1)) * nthr].z;
+    /* refill the two slots just consumed: rec[i+D] -> slot of rec[i], qs[i+DQ] -> slot of qs[i] */
+    cp_async16(rec_s + sr * slot_b, first + (int64_t)(i + D) * step);
+#pragma unroll
+    for (int g = 0; g < GPL; g++) cp_async16(qs_s + (sq * GPL + g) * slot_b, qst + (bq + e[g]));
+    cp_async_commit();
+    const uint32_t b1 = (uint32_t)rn.z;
+
+    const T len = (T)L0;
+#pragma unroll
+    for (int j = 0; j < GPL; j++) {
+      const T tau = (T)qs[j].y * len;
+      const T lq = len * (T)qs[j].x;
+      T x[NP], f1[NP];
+#pragma unroll
+      for (int p = 0; p < NP; p++) x[p] = tau * inv_sin[p];
+      expF1_batch<T, NP>(x, f1);
+      T sum = (T)0;
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
+        const T ex = inv_sin[p] * f1[p];
+        const T dpsi = (tau * (T)psi[p][j] - lq) * ex;
+        psi[p][j] = (float)((T)psi[p][j] - dpsi);
+        sum = fma(w[p], dpsi, sum);
+      }
+      acc[j] += (double)sum;
+    }
+    if (b1 != b0 || i == n - 1) {
+#pragma unroll
+      for (int j = 0; j < GPL; j++) {
+        if (valid[j]) atomicAdd(&phi[b0 + e[j]], acc[j]);
+        acc[j] = 0.0;
+      }
+    }
+    L0 = __hiloint2double(rn.y, rn.x);
+    b0 = b1;
+  }
+  cp_async_wait<0>();
+
   const int64_t out = a.out_slot[t * 2 + dir];
   if (out >= 0) {
     const int64_t base = out * (int64_t)F;
