@@ -139,7 +139,7 @@ struct b200_solver {
 
   /* sweep launch geometry */
   int gpl = 1, lpi = 1, ipc = 32;   /* groups/thread, threads/item, items/CTA */
-  bool staged = true;               /* cp.async-staged sweep (default) vs register-pipelined */
+  int variant = 0;                  /* 0: 2-deep register pipeline (default, fastest measured), 1: 4-deep register ring, 2: cp.async-staged */
   bool smem_attr_set = false;
   int64_t sweep_blocks = 0;
 
@@ -387,10 +387,11 @@ static void choose_lane_map(int G, int* gpl, int* lpi, int* ipc) {
     if (util > best) { best = util; *gpl = c; *lpi = l; }
   }
   if (*gpl == 0) { *gpl = 8; *lpi = (G + 7) / 8; }
-  /* items per CTA: keep CTAs at <= 256 threads */
-  *ipc = (*lpi <= 8) ? 32 : (*lpi <= 16 ? 16 : 8);
+  /* items per CTA: CTAs of at most 224 threads (the kernels' launch bound) */
+  *ipc = 224 / *lpi;
+  if (*ipc > 32) *ipc = 32;
   const char* fipc = getenv("B200_IPC");
-  if (fipc != nullptr && atoi(fipc) > 0 && atoi(fipc) * *lpi <= 256) *ipc = atoi(fipc);
+  if (fipc != nullptr && atoi(fipc) > 0 && atoi(fipc) * *lpi <= 224) *ipc = atoi(fipc);
 }
 
 extern "C" int b200_finalize(b200_solver* s) {
@@ -497,7 +498,12 @@ extern "C" int b200_finalize(b200_solver* s) {
   choose_lane_map(s->G, &s->gpl, &s->lpi, &s->ipc);
   const int64_t n_items = 2 * nt;
   s->sweep_blocks = (n_items + s->ipc - 1) / s->ipc;
-  s->staged = !(getenv("B200_SWEEP") != nullptr && !strcmp(getenv("B200_SWEEP"), "regs"));
+  s->variant = 0;
+  if (const char* v = getenv("B200_SWEEP")) {
+    if (!strcmp(v, "regs")) s->variant = 0;
+    else if (!strcmp(v, "ring")) s->variant = 1;
+    else if (!strcmp(v, "staged")) s->variant = 2;
+  }
   s->smem_attr_set = false;
 
   FsrArgs a = fsr_args(s);
@@ -512,6 +518,30 @@ extern "C" int b200_finalize(b200_solver* s) {
 /* sweep dispatch                                                             */
 /* ------------------------------------------------------------------------- */
 typedef void (*sweep_fn)(const SweepArgs);
+
+template <typename T>
+static sweep_fn pick_ring(int np, int gpl) {
+  if (gpl == 1) {
+    switch (np) {
+      case 1: return sweep_kernel_ring<T, 1, 1>;
+      case 2: return sweep_kernel_ring<T, 2, 1>;
+      case 3: return sweep_kernel_ring<T, 3, 1>;
+      case 4: return sweep_kernel_ring<T, 4, 1>;
+      case 5: return sweep_kernel_ring<T, 5, 1>;
+      case 6: return sweep_kernel_ring<T, 6, 1>;
+    }
+  } else if (gpl == 2) {
+    switch (np) {
+      case 1: return sweep_kernel_ring<T, 1, 2>;
+      case 2: return sweep_kernel_ring<T, 2, 2>;
+      case 3: return sweep_kernel_ring<T, 3, 2>;
+      case 4: return sweep_kernel_ring<T, 4, 2>;
+      case 5: return sweep_kernel_ring<T, 5, 2>;
+      case 6: return sweep_kernel_ring<T, 6, 2>;
+    }
+  }
+  return nullptr;
+}
 
 constexpr int STAGE_DQ = 4;   /* gathers 4 segments ahead, records 8 ahead */
 template <typename T, int NP>
@@ -611,9 +641,11 @@ static int launch_sweep(b200_solver* s) {
     const int nthr = s->lpi * s->ipc;
     sweep_fn fn;
     size_t smem = 0;
-    if (s->staged) {
+    if (s->variant == 2) {
       fn = mixed ? pick_np_staged<float>(s->NP, s->gpl) : pick_np_staged<double>(s->NP, s->gpl);
       smem = (size_t)nthr * 16 * (2 * STAGE_DQ + STAGE_DQ * s->gpl);
+    } else if (s->variant == 1 && s->gpl <= 2) {
+      fn = mixed ? pick_ring<float>(s->NP, s->gpl) : pick_ring<double>(s->NP, s->gpl);
     } else {
       fn = mixed ? pick_np<float>(s->NP, s->gpl) : pick_np<double>(s->NP, s->gpl);
     }
