@@ -165,6 +165,35 @@ __device__ __forceinline__ void expF1_batch(const T (&x)[NP], T (&out)[NP]) {
   for (int p = 0; p < NP; p++) out[p] = num[p] * r[p];
 }
 
+#ifndef B200_REC_HINT
+#define B200_REC_HINT 0     /* 0: ld.global.nc  1: L1::evict_last */
+#endif
+#ifndef B200_QS_HINT
+#define B200_QS_HINT 0      /* 0: ld.global.nc  1: L1::evict_first  2: L1::no_allocate */
+#endif
+__device__ __forceinline__ int4 ld_rec(const void* p) {
+  int4 r;
+#if B200_REC_HINT == 1
+  asm volatile("ld.global.nc.L1::evict_last.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#else
+  r = __ldg(reinterpret_cast<const int4*>(p));
+#endif
+  return r;
+}
+__device__ __forceinline__ double2 ld_qs(const double2* p) {
+#if B200_QS_HINT == 1
+  double2 r;
+  asm volatile("ld.global.nc.L1::evict_first.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+#elif B200_QS_HINT == 2
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+#else
+  return __ldg(p);
+#endif
+}
+
 struct __align__(16) SegRec {
   double len;
   uint32_t base;
@@ -263,13 +292,13 @@ sweep_kernel(const SweepArgs a) {
    * whose only effect is an early flush of the tally. */
   const int step = dir ? -1 : 1;
   const SegRec* __restrict__ ps = a.seg + (dir ? s1 - 1 : s0);
-  const int4 r0 = __ldg(reinterpret_cast<const int4*>(ps));
-  const int4 r1 = __ldg(reinterpret_cast<const int4*>(ps + step));
+  const int4 r0 = ld_rec(ps);
+  const int4 r1 = ld_rec(ps + step);
   double L0 = __hiloint2double(r0.y, r0.x), L1 = __hiloint2double(r1.y, r1.x);
   uint32_t b0 = (uint32_t)r0.z, b1 = (uint32_t)r1.z;
   double2 qs0[GPL], qs1[GPL];
 #pragma unroll
-  for (int j = 0; j < GPL; j++) qs0[j] = __ldg(&a.qst[b0 + e[j]]);
+  for (int j = 0; j < GPL; j++) qs0[j] = ld_qs(&a.qst[b0 + e[j]]);
   ps += 2 * step;
 
   double* __restrict__ const phi = a.phi;
@@ -278,9 +307,9 @@ sweep_kernel(const SweepArgs a) {
     /* pull the stream (DRAM, read once) into L2 ahead of use, once per 128-byte line */
     if ((reinterpret_cast<uintptr_t>(ps) & 0x70) == 0)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + PF_DIST * step));
-    const int4 r2 = __ldg(reinterpret_cast<const int4*>(ps));
+    const int4 r2 = ld_rec(ps);
 #pragma unroll
-    for (int j = 0; j < GPL; j++) qs1[j] = __ldg(&a.qst[b1 + e[j]]);
+    for (int j = 0; j < GPL; j++) qs1[j] = ld_qs(&a.qst[b1 + e[j]]);
 
     const T len = (T)L0;
 #pragma unroll

