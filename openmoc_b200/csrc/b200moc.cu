@@ -637,6 +637,11 @@ static int launch_sweep(b200_solver* s) {
     a.qst = s->qst.p; a.psi_in = s->psi_start; a.psi_out = s->psi_other; a.phi = s->phi.p;
     a.done = s->iscal.p + SI_DONE;
     a.n_items = 2 * s->n_trk; a.G = s->G; a.lpi = s->lpi;
+    {
+      using C = F1Coef<double>;
+      const double cf[11] = {C::d1, C::d2, C::d3, C::d4, C::d5, C::d6, C::p1, C::p2, C::p3, C::p4, C::p5};
+      for (int k = 0; k < 11; k++) a.cf[k] = cf[k];
+    }
     const bool mixed = s->cfg.precision == B200_PRECISION_MIXED;
     const int nthr = s->lpi * s->ipc;
     sweep_fn fn;

@@ -114,19 +114,19 @@ __device__ __forceinline__ T expF1(T x) {
  * group e sit at element base + e (32-bit index arithmetic in the hot loop). */
 /* NP rationals at once, every Horner step issued for all of them before the next */
 template <typename T, int NP>
-__device__ __forceinline__ void expF1_batch(const T (&x)[NP], T (&out)[NP]) {
+__device__ __forceinline__ void expF1_batch(const T (&x)[NP], T (&out)[NP], const double (&cf)[11]) {
   T den[NP], num[NP];
   if constexpr (sizeof(T) == 8) {
 #pragma unroll
-    for (int p = 0; p < NP; p++) den[p] = fma(c_F1[5], x[p], c_F1[4]);
+    for (int p = 0; p < NP; p++) den[p] = fma(x[p], cf[5], cf[4]);
 #pragma unroll
-    for (int p = 0; p < NP; p++) num[p] = fma(c_F1[10], x[p], c_F1[9]);
+    for (int p = 0; p < NP; p++) num[p] = fma(x[p], cf[10], cf[9]);
 #pragma unroll
     for (int k = 3; k >= 0; k--) {
 #pragma unroll
-      for (int p = 0; p < NP; p++) den[p] = fma(den[p], x[p], c_F1[k]);
+      for (int p = 0; p < NP; p++) den[p] = fma(den[p], x[p], cf[k]);
 #pragma unroll
-      for (int p = 0; p < NP; p++) num[p] = fma(num[p], x[p], k > 0 ? c_F1[5 + k] : 1.0);
+      for (int p = 0; p < NP; p++) num[p] = fma(num[p], x[p], k > 0 ? cf[5 + k] : 1.0);
     }
 #pragma unroll
     for (int p = 0; p < NP; p++) den[p] = fma(den[p], x[p], 1.0);
@@ -224,6 +224,11 @@ struct SweepArgs {
   const int* __restrict__ done;            /* device convergence flag (may be NULL) */
   int64_t n_items;
   int G, lpi;
+  /* expF1 coefficients d1..d6, p1..p5 (src/exponentials.h:159-173).  As kernel parameters
+   * they sit in constant bank 0 and every Horner DFMA takes its coefficient as a c[0][..]
+   * operand: two register pairs per DFMA, which the register file can feed every 2 cycles
+   * (three distinct 64-bit register operands cost a third cycle). */
+  double cf[11];
 };
 
 /* CTAs are at most 224 threads (7 warps: 32 items of 7 lanes for G = 7).  For the
@@ -309,7 +314,11 @@ sweep_kernel(const SweepArgs a) {
       asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + PF_DIST * step));
     const int4 r2 = ld_rec(ps);
 #pragma unroll
+#ifndef B200_EXP_NOGATHER
     for (int j = 0; j < GPL; j++) qs1[j] = ld_qs(&a.qst[b1 + e[j]]);
+#else
+    for (int j = 0; j < GPL; j++) qs1[j] = make_double2(1.0 + 1e-9 * (double)b1, 0.5);
+#endif
 
     const T len = (T)L0;
 #pragma unroll
@@ -322,7 +331,7 @@ sweep_kernel(const SweepArgs a) {
       T x[NP], f1[NP];
 #pragma unroll
       for (int p = 0; p < NP; p++) x[p] = tau * inv_sin[p];
-      expF1_batch<T, NP>(x, f1);
+      expF1_batch<T, NP>(x, f1, a.cf);
       T sum = (T)0;
 #pragma unroll
       for (int p = 0; p < NP; p++) {
@@ -338,8 +347,12 @@ sweep_kernel(const SweepArgs a) {
     if (b1 != b0) {
 #pragma unroll
       for (int j = 0; j < GPL; j++) {
+#ifndef B200_EXP_NORED
         if (valid[j]) atomicAdd(&phi[b0 + e[j]], acc[j]);
         acc[j] = 0.0;
+#else
+        if (valid[j] && acc[j] == 123.456) atomicAdd(&phi[b0 + e[j]], acc[j]);
+#endif
       }
     }
     L0 = L1; b0 = b1;
@@ -468,7 +481,7 @@ sweep_kernel_ring(const SweepArgs a) {
       const T lq = len * (T)QC[j].x;                                                           \
       T x[NP], f1[NP];                                                                         \
       _Pragma("unroll") for (int p = 0; p < NP; p++) x[p] = tau * inv_sin[p];                  \
-      expF1_batch<T, NP>(x, f1);                                                               \
+      expF1_batch<T, NP>(x, f1, a.cf);                                                               \
       T sum = (T)0;                                                                            \
       _Pragma("unroll") for (int p = 0; p < NP; p++) {                                         \
         const T ex = inv_sin[p] * f1[p];                                                       \
@@ -630,7 +643,7 @@ sweep_kernel_staged(const SweepArgs a) {
       T x[NP], f1[NP];
 #pragma unroll
       for (int p = 0; p < NP; p++) x[p] = tau * inv_sin[p];
-      expF1_batch<T, NP>(x, f1);
+      expF1_batch<T, NP>(x, f1, a.cf);
       T sum = (T)0;
 #pragma unroll
       for (int p = 0; p < NP; p++) {
