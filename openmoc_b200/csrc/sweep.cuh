@@ -52,13 +52,17 @@ template <> struct F1Coef<float> {
 
 /* 1/d for d >= 1: hardware seed + two Newton steps (4 DFMA) instead of the
  * IEEE division slow path; the denominator polynomial is >= 1 for x >= 0. */
+#ifndef B200_NR_STEPS
+#define B200_NR_STEPS 2
+#endif
 __device__ __forceinline__ double fast_rcp(double d) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  double e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
+#pragma unroll
+  for (int it = 0; it < B200_NR_STEPS; it++) {
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+  }
   return r;
 }
 __device__ __forceinline__ float fast_rcp(float d) { return __frcp_rn(d); }
@@ -149,11 +153,16 @@ __device__ __forceinline__ void expF1_batch(const T (&x)[NP], T (&out)[NP], cons
     for (int p = 0; p < NP; p++) den[p] = fma(den[p], x[p], 1.0f);
   }
   T r[NP];
+#ifdef B200_EXP_NORCP
+#pragma unroll
+  for (int p = 0; p < NP; p++) r[p] = den[p] * (T)0.37;
+#else
 #pragma unroll
   for (int p = 0; p < NP; p++) r[p] = fast_rcp_seed(den[p]);
+#endif
   if constexpr (sizeof(T) == 8) {
 #pragma unroll
-    for (int it = 0; it < 2; it++) {
+    for (int it = 0; it < B200_NR_STEPS; it++) {
       T e[NP];
 #pragma unroll
       for (int p = 0; p < NP; p++) e[p] = fma(-den[p], r[p], (T)1);
@@ -193,6 +202,15 @@ __device__ __forceinline__ double2 ld_qs(const double2* p) {
   return __ldg(p);
 #endif
 }
+
+__device__ __forceinline__ void red_add_if(double* addr, double v, bool p) {
+  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %2, 0;\n\t@pp red.global.add.f64 [%0], %1;\n\t}"
+               ::"l"(addr), "d"(v), "r"((uint32_t)p) : "memory");
+}
+
+#ifndef B200_SWEEP_UNROLL
+#define B200_SWEEP_UNROLL 1
+#endif
 
 struct __align__(16) SegRec {
   double len;
@@ -272,7 +290,11 @@ sweep_kernel(const SweepArgs a) {
   /* incoming angular flux */
   const int F = G * NP;
   const int64_t slot_in = (t * 2 + dir) * (int64_t)F;
+#ifdef B200_EXP_PSID
+  double psi[NP][GPL];
+#else
   float psi[NP][GPL];
+#endif
 #pragma unroll
   for (int p = 0; p < NP; p++)
 #pragma unroll
@@ -307,11 +329,9 @@ sweep_kernel(const SweepArgs a) {
   ps += 2 * step;
 
   double* __restrict__ const phi = a.phi;
-  constexpr int PF_DIST = 24;   /* records: three 128-byte lines ahead of the register look-ahead */
+  constexpr int kUnroll = B200_SWEEP_UNROLL;
+#pragma unroll kUnroll
   for (int i = 0; i < n; i++) {
-    /* pull the stream (DRAM, read once) into L2 ahead of use, once per 128-byte line */
-    if ((reinterpret_cast<uintptr_t>(ps) & 0x70) == 0)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + PF_DIST * step));
     const int4 r2 = ld_rec(ps);
 #pragma unroll
 #ifndef B200_EXP_NOGATHER
@@ -337,22 +357,23 @@ sweep_kernel(const SweepArgs a) {
       for (int p = 0; p < NP; p++) {
         const T ex = inv_sin[p] * f1[p];
         const T dpsi = (tau * (T)psi[p][j] - lq) * ex;
+#ifdef B200_EXP_PSID
+        psi[p][j] = psi[p][j] - dpsi;
+#else
         psi[p][j] = (float)((T)psi[p][j] - dpsi);
+#endif
         sum = fma(w[p], dpsi, sum);
       }
       acc[j] += (double)sum;
     }
 
     /* flush before the FSR changes */
-    if (b1 != b0) {
+    {
+      const bool flush = b1 != b0;
 #pragma unroll
       for (int j = 0; j < GPL; j++) {
-#ifndef B200_EXP_NORED
-        if (valid[j]) atomicAdd(&phi[b0 + e[j]], acc[j]);
-        acc[j] = 0.0;
-#else
-        if (valid[j] && acc[j] == 123.456) atomicAdd(&phi[b0 + e[j]], acc[j]);
-#endif
+        red_add_if(&phi[b0 + e[j]], acc[j], flush && valid[j]);   /* predicated RED, no branch */
+        acc[j] = flush ? 0.0 : acc[j];
       }
     }
     L0 = L1; b0 = b1;
@@ -393,10 +414,6 @@ sweep_kernel(const SweepArgs a) {
 /* which covers L2 latency; DRAM latency is covered by the L2 prefetch.            */
 /* The tally flush is a predicated RED instead of a branch: one basic block/step.  */
 /* ------------------------------------------------------------------------- */
-__device__ __forceinline__ void red_add_if(double* addr, double v, bool p) {
-  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %2, 0;\n\t@pp red.global.add.f64 [%0], %1;\n\t}"
-               ::"l"(addr), "d"(v), "r"((uint32_t)p) : "memory");
-}
 
 template <typename T, int NP, int GPL>
 __global__ void __launch_bounds__(224, B200_RING_MINB)
