@@ -187,6 +187,32 @@ static inline int grid_for(int64_t n, int threads, int cap = 148 * 8) {
   return (int)b;
 }
 
+
+/* tables derived from the material data: sigma_t half of {q, sigma_t}, fissionable-FSR
+ * count (Solver::countFissionableFSRs, src/Solver.cpp:882-892) and the YAMAMOTO
+ * max |sigma_s(e,e)/sigma_t(e)| over the FSRs' materials (CPUSolver.cpp:2700-2716) */
+static int refresh_material_tables(b200_solver* s) {
+  s->n_fissionable = 0;
+  for (int64_t r = 0; r < s->n_fsr; r++)
+    if (s->h_fissionable[s->h_fsr_mat[r]]) s->n_fissionable++;
+  std::vector<double> mr(s->G, 0.);
+  std::vector<char> used(s->n_mat, 0);
+  for (int64_t r = 0; r < s->n_fsr; r++) used[s->h_fsr_mat[r]] = 1;
+  for (int m = 0; m < s->n_mat; m++) {
+    if (!used[m]) continue;
+    for (int e = 0; e < s->G; e++) {
+      double ratio = std::fabs(s->h_sigma_s[((size_t)m * s->G + e) * s->G + e] / s->h_sigma_t[(size_t)m * s->G + e]);
+      mr[e] = std::max(mr[e], ratio);
+    }
+  }
+  CU(s->max_ratio.upload(mr.data(), s->G, s->stream));
+  FsrArgs a = fsr_args(s);
+  fill_sigma_t_kernel<<<grid_for((int64_t)s->n_fsr * s->G, 256, 1 << 30), 256, 0, s->stream>>>(a);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
 /* ------------------------------------------------------------------------- */
 /* create / destroy / uploads                                                 */
 /* ------------------------------------------------------------------------- */
@@ -366,7 +392,9 @@ extern "C" int b200_upload_materials(b200_solver* s, const double* sigma_t, cons
   s->h_sigma_s.assign(sigma_s, sigma_s + nGG);
   CU(cudaStreamSynchronize(s->stream));
   s->have_mats = true;
-  s->finalized = false;
+  /* a finalized solver stays usable: only the material-derived tables are rebuilt
+   * (adjoint <-> forward switches re-upload transposed matrices, Solver.cpp:806) */
+  if (s->finalized) return refresh_material_tables(s);
   return 0;
 }
 
@@ -468,24 +496,6 @@ extern "C" int b200_finalize(b200_solver* s) {
   s->psi_start = s->psi_a.p;
   s->psi_other = s->psi_b.p;
 
-  /* fissionable-FSR count (Solver::countFissionableFSRs, src/Solver.cpp:882-892) */
-  s->n_fissionable = 0;
-  for (int64_t r = 0; r < s->n_fsr; r++)
-    if (s->h_fissionable[s->h_fsr_mat[r]]) s->n_fissionable++;
-
-  /* YAMAMOTO max |sigma_s(e,e)/sigma_t(e)| over the FSRs' materials (CPUSolver.cpp:2700-2716) */
-  std::vector<double> mr(s->G, 0.);
-  std::vector<char> used(s->n_mat, 0);
-  for (int64_t r = 0; r < s->n_fsr; r++) used[s->h_fsr_mat[r]] = 1;
-  for (int m = 0; m < s->n_mat; m++) {
-    if (!used[m]) continue;
-    for (int e = 0; e < s->G; e++) {
-      double ratio = std::fabs(s->h_sigma_s[((size_t)m * s->G + e) * s->G + e] / s->h_sigma_t[(size_t)m * s->G + e]);
-      mr[e] = std::max(mr[e], ratio);
-    }
-  }
-  CU(s->max_ratio.upload(mr.data(), s->G, s->stream));
-
   /* device segment stream: padded 16-byte records with the FSR id premultiplied by G */
   if ((double)s->n_fsr * s->G >= 4294967296.0)
     return fail("b200_finalize: n_fsrs*G = %.3g exceeds the 32-bit tally index of this build", (double)s->n_fsr * s->G);
@@ -506,10 +516,7 @@ extern "C" int b200_finalize(b200_solver* s) {
   }
   s->smem_attr_set = false;
 
-  FsrArgs a = fsr_args(s);
-  fill_sigma_t_kernel<<<grid_for(nphi, 256, 1 << 30), 256, 0, s->stream>>>(a);
-  CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(s->stream));
+  if (refresh_material_tables(s)) return 1;
   s->finalized = true;
   return 0;
 }

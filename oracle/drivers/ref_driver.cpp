@@ -9,7 +9,9 @@
  * Usage: ref_driver --model NAME [--dims 2|3] [--azim N] [--spacing S]
  *                   [--polar N] [--zspacing S] [--formation explicit|otf-tracks|otf-stacks]
  *                   [--quad ty|equal-angle|gl|equal-weight|leonard] [--groups70]
- *                   [--solver cpu|cpuls] [--mode eigen|none] [--tol T]
+ *                   [--solver cpu|cpuls|b200|b200-fused|both] [--mode eigen|none] [--tol T]
+ *        --solver both: CPUSolver and B200Solver in the same process on the same tracks,
+ *        prints delta k_eff (pcm), max relative flux error and both sweep times.
  *                   [--max-iters N] [--threads N] [--res fission|flux|total]
  *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet]
  */
@@ -25,6 +27,7 @@
 
 #include "models.h"
 #include "../../openmoc_b200/cpp/b200_flatten.h"
+#include "../../openmoc_b200/cpp/B200Solver.h"
 
 static const char* arg(int argc, char** argv, const char* key, const char* dflt) {
   for (int i = 1; i < argc - 1; i++)
@@ -94,18 +97,64 @@ int main(int argc, char** argv) {
   tg->setNumThreads(dims == 3 ? threads : 1);
   tg->generateTracks();
 
-  CPUSolver* solver = (solver_name == "cpuls") ? new CPULSSolver(tg) : new CPUSolver(tg);
-  solver->setNumThreads(threads);
-  solver->setConvergenceThreshold(tol);
-
   residualType rt = FISSION_SOURCE;
   if (res == "flux") rt = SCALAR_FLUX;
   else if (res == "total") rt = TOTAL_SOURCE;
 
-  if (mode == "eigen")
-    solver->computeEigenvalue(max_iters, rt);
-  else
+  /* B200Solver in the reference's own process, next to CPUSolver on the same tracks */
+  if (solver_name == "both") {
+    long n_fsr = geometry->getNumFSRs();
+    int G = geometry->getNumEnergyGroups();
+    CPUSolver cpu(tg);
+    cpu.setNumThreads(threads);
+    cpu.setConvergenceThreshold(tol);
+    cpu.computeEigenvalue(max_iters, rt);
+    Timer timer;
+    double cpu_sweep = timer.getSplit("Transport Sweep");
+    std::vector<FP_PRECISION> phi_cpu(n_fsr * G), phi_gpu(n_fsr * G);
+    cpu.getFluxes(phi_cpu.data(), n_fsr * G);
+    double k_cpu = cpu.getKeff();
+    int it_cpu = cpu.getNumIterations();
+
+    B200Solver gpu(tg);
+    gpu.setConvergenceThreshold(tol);
+    gpu.computeEigenvalue(max_iters, rt);
+    double gpu_sweep = timer.getSplit("Transport Sweep");
+    gpu.getFluxes(phi_gpu.data(), n_fsr * G);
+    double err = 0.;
+    for (long i = 0; i < n_fsr * G; i++) {
+      double d = fabs(phi_gpu[i] - phi_cpu[i]) / fabs(phi_cpu[i]);
+      if (d > err) err = d;
+    }
+    double dev_ms = 0.; long sweeps = 0;
+    gpu.getSweepStats(&dev_ms, &sweeps);
+    long n_seg = tg->getNumSegments();
+    int F = (dims == 3) ? G : G * tg->getQuadrature()->getNumPolarAngles() / 2;
+    printf("{\"model\": \"%s\", \"n_segments\": %ld, \"n_fsrs\": %ld, \"cpu_threads\": %d, "
+           "\"cpu_keff\": %.12f, \"b200_keff\": %.12f, \"dk_pcm\": %.3e, \"max_rel_flux_err\": %.3e, "
+           "\"cpu_iters\": %d, \"b200_iters\": %d, \"cpu_sweep_s\": %.6g, \"b200_sweep_s\": %.6g, "
+           "\"b200_sweep_kernel_s\": %.6g, \"cpu_integrations_per_s\": %.4e, \"b200_integrations_per_s\": %.4e}\n",
+           model_name.c_str(), n_seg, n_fsr, threads, k_cpu, gpu.getKeff(), fabs(gpu.getKeff() - k_cpu) * 1e5, err,
+           it_cpu, gpu.getNumIterations(), cpu_sweep, gpu_sweep, dev_ms * 1e-3,
+           2.0 * F * n_seg * it_cpu / cpu_sweep, 2.0 * F * n_seg * gpu.getNumIterations() / gpu_sweep);
+    return 0;
+  }
+
+  Solver* solver;
+  CPUSolver* cpu_solver = NULL;
+  B200Solver* b200_solver = NULL;
+  if (solver_name == "b200" || solver_name == "b200-fused") solver = b200_solver = new B200Solver(tg);
+  else if (solver_name == "cpuls") solver = cpu_solver = new CPULSSolver(tg);
+  else solver = cpu_solver = new CPUSolver(tg);
+  if (cpu_solver != NULL) cpu_solver->setNumThreads(threads);
+  solver->setConvergenceThreshold(tol);
+
+  if (mode == "eigen") {
+    if (solver_name == "b200-fused") b200_solver->computeEigenvalueFused(max_iters, rt);
+    else solver->computeEigenvalue(max_iters, rt);
+  } else {
     solver->initializeSolver(FORWARD);
+  }
 
   long n_fsr = geometry->getNumFSRs();
   int G = geometry->getNumEnergyGroups();

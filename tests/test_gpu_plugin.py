@@ -1,0 +1,52 @@
+"""The C++ drop-in: `B200Solver : public Solver` (openmoc_b200/cpp/B200Solver.cpp) running
+inside the reference's own process, next to the unmodified CPUSolver, on the same
+TrackGenerator (oracle/_ref/ref_driver --solver both; built by oracle/Makefile in the CPU
+container, travels to the GPU box as a prebuilt binary)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+
+def run(args):
+    if not os.path.exists(DRIVER):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    out = subprocess.run([DRIVER] + args + ["--quiet"], check=True, capture_output=True, text=True).stdout
+    line = [l for l in out.splitlines() if l.startswith("{")][-1]
+    return json.loads(line)
+
+
+@pytest.mark.parametrize("args,iters", [
+    (["--model", "pin-cell", "--azim", "4", "--spacing", "0.1"], 261),                       # test_forward_pin_cell
+    (["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12"], 187),                # test_forward_simple_lattice
+    (["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "2.1",
+      "--zspacing", "2.8", "--groups70", "--tol", "5e-3"], 258),                              # test_forward_3D_lattice_70g
+    (["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
+      "--zspacing", "0.9", "--formation", "otf-stacks"], None),                               # OTF_STACKS flattening
+    (["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
+      "--zspacing", "0.9", "--formation", "explicit"], None),                                 # EXPLICIT_3D flattening
+])
+def test_b200solver_matches_cpusolver_in_process(args, iters):
+    r = run(args + ["--solver", "both"])
+    assert r["dk_pcm"] < 1.0                     # north_star
+    assert r["max_rel_flux_err"] < 1e-4          # north_star
+    assert r["dk_pcm"] < 1e-3 and r["max_rel_flux_err"] < 1e-7   # what it actually achieves
+    assert r["b200_iters"] == r["cpu_iters"]
+    if iters is not None:
+        assert r["cpu_iters"] == iters
+
+
+def test_fused_loop_through_the_plugin(tmp_path):
+    js = os.path.join(tmp_path, "r.json")
+    if not os.path.exists(DRIVER):
+        pytest.skip("ref_driver not built")
+    subprocess.run([DRIVER, "--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--solver", "b200-fused",
+                    "--quiet", "--json", js, "--results", os.path.join(tmp_path, "res.dat")], check=True)
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_goldens.json")))["test_forward_pin_cell"]
+    assert open(os.path.join(tmp_path, "res.dat")).read() == golden
