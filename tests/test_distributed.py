@@ -1,0 +1,116 @@
+"""Multi-process path: azimuthal-pair partition + all-reduce of the FSR tally.
+
+CPU (gloo, world_size 2): the host-side logic - partition, per-rank sweep (through the
+oracle, the checker), torch.distributed all-reduce, replicated FSR steps - reproduces the
+single-process solution.  GPU (nccl, needs >= 2 devices): the same through B200Solver.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _tracks():
+    from openmoc_b200.synth import make_tracks
+    return make_tracks("simple-lattice", num_azim=8, spacing=0.1)
+
+
+# ------------------------------------------------------------------ gloo / CPU
+def _cpu_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    from openmoc_b200.partition import partition_by_azim_pair
+    from oracle.oracle_py import OracleSolver, FISSION_SOURCE
+    ft = _tracks()
+    part = partition_by_azim_pair(ft, world)[rank]
+    s = OracleSolver(part)
+    # Solver::computeEigenvalue step by step; every FSR step is replicated on all ranks
+    s.setKeff(1.0); s.zeroTrackFluxes()
+    s.flattenFSRFluxes(0.0); s.storeFSRFluxes()
+    s.flattenFSRFluxes(1.0); s.normalizeFluxes(); s.storeFSRFluxes()
+    k_prev, iters = 1.0, 0
+    for i in range(400):
+        s.computeFSRSources(i)
+        s.transportSweep()
+        phi = torch.from_numpy(s.getFluxes())
+        dist.all_reduce(phi, op=dist.ReduceOp.SUM)          # the one data-path collective
+        s.setFluxes(phi.numpy())
+        s.addSourceToScalarFlux()
+        s.computeKeff(); k = s.getKeff()
+        s.normalizeFluxes()
+        res = s.computeResidual(FISSION_SOURCE)
+        dk = int(1e5 * (k - k_prev)); k_prev = k
+        s.storeFSRFluxes(); iters += 1
+        if res < 1e-5 and abs(dk) < 1:
+            break
+    np.save(os.path.join(out_dir, f"phi{rank}.npy"), s.getFluxes())
+    np.save(os.path.join(out_dir, f"k{rank}.npy"), np.array([s.getKeff(), iters]))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_matches_single_process(tmp_path):
+    from oracle.oracle_py import OracleSolver, FISSION_SOURCE
+    port = _free_port()
+    mp.spawn(_cpu_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ft = _tracks()
+    ref = OracleSolver(ft)
+    n = ref.computeEigenvalue(400, 1e-5, FISSION_SOURCE)
+    for r in range(2):
+        k, iters = np.load(os.path.join(tmp_path, f"k{r}.npy"))
+        phi = np.load(os.path.join(tmp_path, f"phi{r}.npy"))
+        assert int(iters) == n
+        assert abs(k - ref.getKeff()) * 1e5 < 1e-4
+        np.testing.assert_allclose(phi, ref.getFluxes(), rtol=1e-8)
+    # ranks hold bit-identical replicated state
+    assert np.array_equal(np.load(os.path.join(tmp_path, "phi0.npy")), np.load(os.path.join(tmp_path, "phi1.npy")))
+
+
+# ------------------------------------------------------------------ nccl / GPU
+def _gpu_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    from openmoc_b200.solver import B200Solver
+    from openmoc_b200.capi import FISSION_SOURCE
+    s = B200Solver(_tracks(), device=rank, process_group=dist.group.WORLD)
+    s.setConvergenceThreshold(1e-5)
+    s.computeEigenvalue(400, FISSION_SOURCE)
+    np.save(os.path.join(out_dir, f"phi{rank}.npy"), s.getFluxes())
+    np.save(os.path.join(out_dir, f"k{rank}.npy"), np.array([s.getKeff(), s.getNumIterations()]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_nccl_world2_matches_single_gpu(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from openmoc_b200.solver import B200Solver
+    from openmoc_b200.capi import FISSION_SOURCE
+    port = _free_port()
+    mp.spawn(_gpu_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    one = B200Solver(_tracks())
+    one.setConvergenceThreshold(1e-5)
+    one.computeEigenvalue(400, FISSION_SOURCE)
+    for r in range(2):
+        k, iters = np.load(os.path.join(tmp_path, f"k{r}.npy"))
+        phi = np.load(os.path.join(tmp_path, f"phi{r}.npy"))
+        assert int(iters) == one.getNumIterations()
+        assert abs(k - one.getKeff()) * 1e5 < 1e-3
+        np.testing.assert_allclose(phi, one.getFluxes(), rtol=1e-7)
