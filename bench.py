@@ -57,13 +57,15 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append((time.time(), l)) for l in self.proc.stdout],
+                                      daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
@@ -75,7 +77,10 @@ class ClockSampler:
         self.proc.terminate()
         self.t.join(timeout=2)
         sm, mx, reasons = [], None, set()
-        for l in self.lines:
+        for ts, l in self.lines:
+            # keep the samples taken while the timed region ran
+            if self.t0 is not None and not (self.t0 <= ts <= self.t1 + 0.12):
+                continue
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -157,7 +162,7 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5g7-2d", choices=sorted(WORKLOADS))
@@ -218,18 +223,20 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
-    solver.iterate(args.warmup)
-    barrier()
-    solver.resetSweepStats()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    solver.iterate(args.warmup)
+    barrier()
+    solver.resetSweepStats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.t0 = time.time()
     ev0.record()
     solver.iterate(args.steps)
     ev1.record()
     torch.cuda.synchronize()
+    sampler.t1 = time.time()
     ms = ev0.elapsed_time(ev1)
     if dist is not None:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -310,7 +317,8 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "b200::sweep_kernel", "bytes_per_integration": b_alg,
                          "kernel_ms": sweep_avg_ms, "kernel_share_of_step": sweep_ms / ms if ms > 0 else None,
-                         "note": "FP64-pipe bound for G*P/2=21: ~24 DFMA-class ops per integration vs 0.34 B"},
+                         "note": "FP64-issue bound, not HBM bound, for G*P/2=21 (SURVEY 8d): 23 FP64 instr per integration vs "
+                                 "0.34 algorithmic bytes; see DESIGN.md 4.1 and profiles/"},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "integrations/s", "h2d_bytes_per_step": n_phi * 8,
                     "d2h_bytes_per_step": n_phi * 8 + 8, "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps},
