@@ -51,7 +51,7 @@ typedef struct b200_config {
   int32_t n_materials;
   int32_t device;          /* CUDA device ordinal */
   int32_t precision;       /* B200_PRECISION_* */
-  int32_t deterministic;   /* 1: order-independent (fixed-point) FSR tally */
+  int32_t deterministic;   /* 1: order-independent 64-bit fixed-point FSR tally: bitwise reproducible runs */
   int64_t n_fsrs_global;   /* normalisation count when FSRs are sharded; 0 => n_fsrs */
 } b200_config;
 
@@ -148,6 +148,11 @@ int b200_synchronize(b200_solver* s);
  *      host framework (torch.distributed / NCCL) can reduce them in place.
  *      name in {"scalar_flux","old_scalar_flux","reduced_sources","start_flux"} */
 int b200_device_pointer(b200_solver* s, const char* name, void** ptr, int64_t* num_elements);
+/* deterministic mode across GPUs: defer=1 makes b200_transport_sweep leave the tally in
+ * the int64 fixed-point buffer ("scalar_flux_fixed") so the host can sum it exactly across
+ * ranks (integer all-reduce); b200_finish_fixed_tally then converts it into scalar_flux. */
+int b200_defer_fixed_tally(b200_solver* s, int32_t defer);
+int b200_finish_fixed_tally(b200_solver* s);
 /* use an externally owned cudaStream_t (passed as void*) for all launches */
 int b200_set_stream(b200_solver* s, void* cuda_stream);
 

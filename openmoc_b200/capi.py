@@ -77,6 +77,8 @@ SIGNATURES = {
     "b200_synchronize": [],
     "b200_device_pointer": [C.c_char_p, C.POINTER(_vp), C.POINTER(_i64)],
     "b200_set_stream": [_vp],
+    "b200_defer_fixed_tally": [_i32],
+    "b200_finish_fixed_tally": [],
 }
 #: every symbol include/b200moc.h declares (checked by tests/test_abi.py)
 EXPORTS = sorted(list(SIGNATURES) + ["b200_last_error", "b200_version", "b200_device_count", "b200_create",

@@ -128,6 +128,7 @@ struct b200_solver {
   DevBuf<uint8_t> fissionable;
   /* device: state */
   DevBuf<double> phi, phi_old, fixed, stab, scratch;
+  DevBuf<unsigned long long> phi_fx, fx_bits;   /* deterministic mode */
   DevBuf<double2> qst;
   DevBuf<float> psi_a, psi_b;
   float* psi_start = nullptr;  /* what the next sweep reads (= reference _start_flux) */
@@ -141,6 +142,7 @@ struct b200_solver {
   int gpl = 1, lpi = 1, ipc = 32;   /* groups/thread, threads/item, items/CTA */
   int variant = 0;                  /* 0: 2-deep register pipeline (default, fastest measured), 1: 4-deep register ring, 2: cp.async-staged */
   bool smem_attr_set = false;
+  bool defer_fx_convert = false;    /* multi-GPU deterministic mode: the host reduces the integers first */
   int64_t sweep_blocks = 0;
 
   /* options */
@@ -233,7 +235,8 @@ extern "C" int b200_create(const b200_config* cfg, b200_solver** out) {
     return fail("b200_create: negative or empty problem size");
   if (cfg->precision != B200_PRECISION_DOUBLE && cfg->precision != B200_PRECISION_MIXED)
     return fail("b200_create: unknown precision %d", cfg->precision);
-  if (cfg->deterministic) return fail("b200_create: deterministic tally mode is not available in this build");
+  if (cfg->deterministic && cfg->precision != B200_PRECISION_DOUBLE)
+    return fail("b200_create: the deterministic tally needs B200_PRECISION_DOUBLE");
   if (!cfg->solve_3d && cfg->num_polar / 2 > 6)
     return fail("b200_create: %d polar angles per 2D track not supported (max 6)", cfg->num_polar / 2);
   if (cfg->num_groups > 256) return fail("b200_create: %d energy groups not supported (max 256)", cfg->num_groups);
@@ -277,6 +280,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   s->cls_inv_sin.release(); s->fsr_mat.release(); s->vol.release(); s->sigma_t.release();
   s->sigma_s.release(); s->fiss.release(); s->nu_sigma_f.release(); s->sigma_f.release();
   s->chi.release(); s->max_ratio.release(); s->fissionable.release(); s->phi.release();
+  s->phi_fx.release(); s->fx_bits.release();
   s->phi_old.release(); s->fixed.release(); s->stab.release(); s->scratch.release();
   s->qst.release(); s->psi_a.release(); s->psi_b.release(); s->scal.release();
   s->partials.release(); s->hist_k.release(); s->hist_res.release(); s->iscal.release();
@@ -484,6 +488,11 @@ extern "C" int b200_finalize(b200_solver* s) {
   CU(s->phi.alloc(nphi)); CU(s->phi_old.alloc(nphi)); CU(s->fixed.alloc(nphi));
   CU(s->stab.alloc(nphi)); CU(s->qst.alloc(nphi)); CU(s->scratch.alloc(std::max(nphi, (size_t)s->n_fsr)));
   CU(s->psi_a.alloc(npsi)); CU(s->psi_b.alloc(npsi));
+  if (s->cfg.deterministic) {
+    CU(s->phi_fx.alloc(nphi)); CU(s->fx_bits.alloc(4));
+    CU(cudaMemsetAsync(s->phi_fx.p, 0, nphi * 8, s->stream));
+    CU(cudaMemsetAsync(s->fx_bits.p, 0, 4 * 8, s->stream));
+  }
   CU(cudaMemsetAsync(s->phi.p, 0, nphi * 8, s->stream));
   CU(cudaMemsetAsync(s->phi_old.p, 0, nphi * 8, s->stream));
   CU(cudaMemsetAsync(s->fixed.p, 0, nphi * 8, s->stream));
@@ -576,27 +585,27 @@ static sweep_fn pick_np_staged(int np, int gpl) {
   return nullptr;
 }
 
-template <typename T, int NP>
+template <typename T, int NP, bool DET>
 static sweep_fn pick_gpl(int gpl) {
   switch (gpl) {
-    case 1: return sweep_kernel<T, NP, 1>;
-    case 2: return sweep_kernel<T, NP, 2>;
-    case 3: return sweep_kernel<T, NP, 3>;
-    case 4: return sweep_kernel<T, NP, 4>;
-    case 7: return sweep_kernel<T, NP, 7>;
-    case 8: return sweep_kernel<T, NP, 8>;
+    case 1: return sweep_kernel<T, NP, 1, DET>;
+    case 2: return sweep_kernel<T, NP, 2, DET>;
+    case 3: return sweep_kernel<T, NP, 3, DET>;
+    case 4: return sweep_kernel<T, NP, 4, DET>;
+    case 7: return sweep_kernel<T, NP, 7, DET>;
+    case 8: return sweep_kernel<T, NP, 8, DET>;
   }
   return nullptr;
 }
-template <typename T>
+template <typename T, bool DET>
 static sweep_fn pick_np(int np, int gpl) {
   switch (np) {
-    case 1: return pick_gpl<T, 1>(gpl);
-    case 2: return pick_gpl<T, 2>(gpl);
-    case 3: return pick_gpl<T, 3>(gpl);
-    case 4: return pick_gpl<T, 4>(gpl);
-    case 5: return pick_gpl<T, 5>(gpl);
-    case 6: return pick_gpl<T, 6>(gpl);
+    case 1: return pick_gpl<T, 1, DET>(gpl);
+    case 2: return pick_gpl<T, 2, DET>(gpl);
+    case 3: return pick_gpl<T, 3, DET>(gpl);
+    case 4: return pick_gpl<T, 4, DET>(gpl);
+    case 5: return pick_gpl<T, 5, DET>(gpl);
+    case 6: return pick_gpl<T, 6, DET>(gpl);
   }
   return nullptr;
 }
@@ -636,12 +645,23 @@ static int launch_sweep(b200_solver* s) {
   zero_phi_kernel<<<grid_for(nphi, 256), 256, 0, s->stream>>>(s->phi.p, (int64_t)nphi, s->iscal.p);
   CU(cudaGetLastError());
   s->n_launches++;
+  if (s->cfg.deterministic) {
+    FsrArgs fa = fsr_args(s);
+    const int64_t npsi = s->n_trk * 2 * (int64_t)s->F;
+    fx_bound_kernel<<<grid_for(std::max<int64_t>(npsi, (int64_t)nphi), RED_THREADS), RED_THREADS, 0, s->stream>>>(
+        fa, s->psi_start, npsi, s->fx_bits.p);
+    CU(cudaGetLastError());
+    fx_scale_kernel<<<1, 1, 0, s->stream>>>(fa, s->fx_bits.p);
+    CU(cudaGetLastError());
+    s->n_launches += 2;
+  }
   if (s->n_trk > 0) {
     SweepArgs a;
     a.seg = s->seg_rec.p + SEG_PAD; a.trk_off = s->trk_off.p;
     a.trk_class = s->trk_class.p; a.order = s->order.p; a.out_slot = s->out_slot.p;
     a.carry = s->carry.p; a.cls_w = s->cls_w.p; a.cls_inv_sin = s->cls_inv_sin.p;
     a.qst = s->qst.p; a.psi_in = s->psi_start; a.psi_out = s->psi_other; a.phi = s->phi.p;
+    a.phi_fx = s->phi_fx.p; a.fx_scale = s->scal.p + SC_FXSCALE;
     a.done = s->iscal.p + SI_DONE;
     a.n_items = 2 * s->n_trk; a.G = s->G; a.lpi = s->lpi;
     {
@@ -659,7 +679,8 @@ static int launch_sweep(b200_solver* s) {
     } else if (s->variant == 1 && s->gpl <= 2) {
       fn = mixed ? pick_ring<float>(s->NP, s->gpl) : pick_ring<double>(s->NP, s->gpl);
     } else {
-      fn = mixed ? pick_np<float>(s->NP, s->gpl) : pick_np<double>(s->NP, s->gpl);
+      if (s->cfg.deterministic) fn = pick_np<double, true>(s->NP, s->gpl);
+      else fn = mixed ? pick_np<float, false>(s->NP, s->gpl) : pick_np<double, false>(s->NP, s->gpl);
     }
     if (fn == nullptr) return fail("no sweep kernel for NP=%d GPL=%d", s->NP, s->gpl);
     if (smem > 48 * 1024 && !s->smem_attr_set) {
@@ -667,6 +688,11 @@ static int launch_sweep(b200_solver* s) {
       s->smem_attr_set = true;
     }
     fn<<<(unsigned)s->sweep_blocks, nthr, smem, s->stream>>>(a);
+    CU(cudaGetLastError());
+    s->n_launches++;
+  }
+  if (s->cfg.deterministic && !s->defer_fx_convert) {
+    fx_to_double_kernel<<<grid_for(nphi, 256), 256, 0, s->stream>>>(fsr_args(s), s->phi_fx.p);
     CU(cudaGetLastError());
     s->n_launches++;
   }
@@ -1179,9 +1205,31 @@ extern "C" int b200_device_pointer(b200_solver* s, const char* name, void** ptr,
   else if (!strcmp(name, "old_scalar_flux")) { *ptr = s->phi_old.p; *n = nphi; }
   else if (!strcmp(name, "reduced_sources")) { *ptr = s->qst.p; *n = 2 * nphi; }
   else if (!strcmp(name, "start_flux")) { *ptr = s->psi_start; *n = s->n_trk * 2 * (int64_t)s->F; }
+  else if (!strcmp(name, "scalar_flux_fixed")) {
+    if (!s->cfg.deterministic) return fail("b200_device_pointer: 'scalar_flux_fixed' exists in deterministic mode only");
+    *ptr = s->phi_fx.p; *n = nphi;
+  }
   else return fail("b200_device_pointer: unknown array '%s'", name);
   return 0;
 }
+/* deterministic multi-GPU: with defer=1 b200_transport_sweep leaves the tally in the int64
+ * buffer ("scalar_flux_fixed") so that the host can sum it across ranks exactly;
+ * b200_finish_fixed_tally then converts it into scalar_flux. */
+extern "C" int b200_defer_fixed_tally(b200_solver* s, int32_t defer) {
+  NEED(s);
+  if (!s->cfg.deterministic) return fail("b200_defer_fixed_tally: deterministic mode only");
+  s->defer_fx_convert = defer != 0;
+  return 0;
+}
+extern "C" int b200_finish_fixed_tally(b200_solver* s) {
+  NEED_FINAL(s);
+  if (!s->cfg.deterministic) return fail("b200_finish_fixed_tally: deterministic mode only");
+  fx_to_double_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(fsr_args(s), s->phi_fx.p);
+  CU(cudaGetLastError());
+  s->n_launches++;
+  return 0;
+}
+
 extern "C" int b200_set_stream(b200_solver* s, void* cuda_stream) {
   NEED(s);
   CU(cudaStreamSynchronize(s->stream));

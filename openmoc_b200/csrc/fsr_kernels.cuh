@@ -22,7 +22,7 @@ constexpr int RED_THREADS = 256;
 constexpr int MAX_PARTIALS = 1024;
 
 /* device scalar block (double) */
-enum { SC_KEFF = 0, SC_RATE, SC_NORM, SC_RESIDUAL, SC_KPREV, SC_TOL, SC_COUNT_D };
+enum { SC_KEFF = 0, SC_RATE, SC_NORM, SC_RESIDUAL, SC_KPREV, SC_TOL, SC_FXSCALE, SC_FXBOUND, SC_COUNT_D };
 /* device scalar block (int) */
 enum { SI_DONE = 0, SI_ITERS, SI_EXEC, SI_NEG_SRC, SI_NEG_FLUX, SI_COUNT_I };
 
@@ -377,6 +377,56 @@ __global__ void fission_rates_kernel(const FsrArgs a, double* __restrict__ out, 
     double v = 0.;
     for (int e = 0; e < G; e++) v += sg[e] * a.phi[r * G + e] * a.vol[r];
     out[r] = v;
+  }
+}
+
+/* ---- deterministic (fixed-point) tally support --------------------------------------
+ * |sum w dpsi| <= 4 pi Sigma_t V M for every (FSR, group), with M the largest angular flux
+ * that can occur: max(|psi_in|, |q| / Sigma_t) (psi along a track is a convex combination
+ * of its start value and the local q / Sigma_t).  A power-of-two scale with 2^5 head room
+ * under 2^62 therefore cannot overflow; resolution is ~1e-17 of the bound. */
+__global__ void __launch_bounds__(RED_THREADS)
+fx_bound_kernel(const FsrArgs a, const float* __restrict__ psi, int64_t n_psi, unsigned long long* __restrict__ bits) {
+  /* bits[0]: max |psi|, bits[1]: max |q|/sigma_t, bits[2]: max sigma_t*V  (non-negative doubles order like integers) */
+  double m_psi = 0., m_q = 0., m_sv = 0.;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n_psi; i += nth) m_psi = fmax(m_psi, fabs((double)psi[i]));
+  const int64_t n = a.n_fsr * a.G;
+  for (int64_t i = tid; i < n; i += nth) {
+    const double2 qs = a.qst[i];
+    m_q = fmax(m_q, fabs(qs.x) / qs.y);
+    m_sv = fmax(m_sv, qs.y * a.vol[i / a.G]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m_psi = fmax(m_psi, __shfl_xor_sync(0xffffffffu, m_psi, o));
+    m_q = fmax(m_q, __shfl_xor_sync(0xffffffffu, m_q, o));
+    m_sv = fmax(m_sv, __shfl_xor_sync(0xffffffffu, m_sv, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&bits[0], (unsigned long long)__double_as_longlong(m_psi));
+    atomicMax(&bits[1], (unsigned long long)__double_as_longlong(m_q));
+    atomicMax(&bits[2], (unsigned long long)__double_as_longlong(m_sv));
+  }
+}
+__global__ void fx_scale_kernel(const FsrArgs a, unsigned long long* __restrict__ bits) {
+  if (a.iscal[SI_DONE]) return;
+  const double m = fmax(__longlong_as_double((long long)bits[0]), __longlong_as_double((long long)bits[1]));
+  double bound = FOUR_PI * __longlong_as_double((long long)bits[2]) * m;
+  if (!(bound > 0.)) bound = 1.0;
+  int ex;
+  frexp(bound, &ex);                       /* bound < 2^ex */
+  a.scal[SC_FXBOUND] = bound;
+  a.scal[SC_FXSCALE] = ldexp(1.0, 62 - 5 - ex);
+  bits[0] = bits[1] = bits[2] = 0ull;
+}
+__global__ void fx_to_double_kernel(const FsrArgs a, unsigned long long* __restrict__ fx) {
+  if (a.iscal[SI_DONE]) return;
+  const double inv = 1.0 / a.scal[SC_FXSCALE];
+  const int64_t n = a.n_fsr * a.G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    a.phi[i] = (double)(long long)fx[i] * inv;
+    fx[i] = 0ull;
   }
 }
 

@@ -239,6 +239,10 @@ struct SweepArgs {
   const float* __restrict__ psi_in;
   float* __restrict__ psi_out;
   double* __restrict__ phi;                /* tally target [n_fsr*G] */
+  /* deterministic mode: the tally is accumulated as 64-bit fixed point (integer adds are
+   * associative, so the result does not depend on the order the atomics land in) */
+  unsigned long long* __restrict__ phi_fx; /* [n_fsr*G], used by the DET kernels */
+  const double* __restrict__ fx_scale;     /* device scalar: power-of-two scale */
   const int* __restrict__ done;            /* device convergence flag (may be NULL) */
   int64_t n_items;
   int G, lpi;
@@ -252,7 +256,7 @@ struct SweepArgs {
 /* CTAs are at most 224 threads (7 warps: 32 items of 7 lanes for G = 7).  For the
  * small-G shapes four CTAs per SM (28 warps) are worth more than registers: the
  * bound caps the kernel at 72 registers. */
-template <typename T, int NP, int GPL>
+template <typename T, int NP, int GPL, bool DET>
 __global__ void __launch_bounds__(224, (GPL == 1 && NP <= 3) ? 4 : 1)
 sweep_kernel(const SweepArgs a) {
   if (a.done != nullptr && *a.done) return;
@@ -329,6 +333,7 @@ sweep_kernel(const SweepArgs a) {
   ps += 2 * step;
 
   double* __restrict__ const phi = a.phi;
+  const double fx_scale = DET ? *a.fx_scale : 0.0;
   constexpr int kUnroll = B200_SWEEP_UNROLL;
 #pragma unroll kUnroll
   for (int i = 0; i < n; i++) {
@@ -372,7 +377,12 @@ sweep_kernel(const SweepArgs a) {
       const bool flush = b1 != b0;
 #pragma unroll
       for (int j = 0; j < GPL; j++) {
-        red_add_if(&phi[b0 + e[j]], acc[j], flush && valid[j]);   /* predicated RED, no branch */
+        if constexpr (DET) {
+          if (flush && valid[j])
+            atomicAdd(&a.phi_fx[b0 + e[j]], (unsigned long long)__double2ll_rn(acc[j] * fx_scale));
+        } else {
+          red_add_if(&phi[b0 + e[j]], acc[j], flush && valid[j]);   /* predicated RED, no branch */
+        }
         acc[j] = flush ? 0.0 : acc[j];
       }
     }
@@ -388,7 +398,10 @@ sweep_kernel(const SweepArgs a) {
     const uint32_t blast = a.seg[dir ? s0 : s1 - 1].base;
 #pragma unroll
     for (int j = 0; j < GPL; j++)
-      if (valid[j] && acc[j] != 0.0) atomicAdd(&phi[blast + e[j]], acc[j]);
+      if (valid[j] && acc[j] != 0.0) {
+        if constexpr (DET) atomicAdd(&a.phi_fx[blast + e[j]], (unsigned long long)__double2ll_rn(acc[j] * fx_scale));
+        else atomicAdd(&phi[blast + e[j]], acc[j]);
+      }
   }
 
   /* transferBoundaryFlux (src/CPUSolver.cpp:2560-2601): reflective / periodic

@@ -49,10 +49,12 @@ class B200Solver:
     precision : int            capi.PRECISION_DOUBLE (reference double build) or PRECISION_MIXED
     process_group : optional   torch.distributed group; when its world size > 1 the
                                tracks are sharded by azimuthal pair across the ranks
+    deterministic : bool       accumulate the FSR tally in 64-bit fixed point: results are
+                               bitwise reproducible run to run (and across GPU counts)
     """
 
     def __init__(self, tracks: FlatTracks, device: int = 0, precision: int = PRECISION_DOUBLE,
-                 process_group=None, use_distributed: Optional[bool] = None):
+                 process_group=None, use_distributed: Optional[bool] = None, deterministic: bool = False):
         self._lib = capi.load()
         self._h = C.c_void_p()
         self._global_tracks = tracks
@@ -83,9 +85,12 @@ class B200Solver:
         cfg = Config(num_groups=tracks.num_groups, num_azim=tracks.num_azim, num_polar=tracks.num_polar,
                      solve_3d=tracks.solve_3d, n_tracks=tracks.n_tracks, n_segments=tracks.n_segments,
                      n_fsrs=tracks.n_fsrs, n_materials=tracks.n_materials, device=device,
-                     precision=precision, deterministic=0, n_fsrs_global=tracks.n_fsrs)
+                     precision=precision, deterministic=int(bool(deterministic)), n_fsrs_global=tracks.n_fsrs)
+        self._deterministic = bool(deterministic)
         check(self._lib.b200_create(C.byref(cfg), C.byref(self._h)))
         self._upload(tracks)
+        if self._deterministic and self._world > 1:
+            check(self._lib.b200_defer_fixed_tally(self._h, 1))
 
     # ------------------------------------------------------------------ setup
     def _upload(self, ft: FlatTracks) -> None:
@@ -252,13 +257,18 @@ class B200Solver:
         import torch
         if self._phi_tensor is None:
             p, n = C.c_void_p(), C.c_int64()
-            check(self._lib.b200_device_pointer(self._h, b"scalar_flux", C.byref(p), C.byref(n)))
+            # deterministic mode reduces the int64 fixed-point tally: integer sums are exact,
+            # so the answer does not depend on the reduction order or the number of ranks
+            name, typ = (b"scalar_flux_fixed", "<i8") if self._deterministic else (b"scalar_flux", "<f8")
+            check(self._lib.b200_device_pointer(self._h, name, C.byref(p), C.byref(n)))
             # run the engine on torch's current stream so NCCL is ordered after the sweep
             self.useTorchStream()
             with torch.cuda.device(self._device):
-                self._phi_tensor = torch.as_tensor(_DeviceArray(p.value, n.value, "<f8"),
+                self._phi_tensor = torch.as_tensor(_DeviceArray(p.value, n.value, typ),
                                                    device=torch.device("cuda", self._device))
         self._dist.all_reduce(self._phi_tensor, op=self._dist.ReduceOp.SUM, group=self._pg)
+        if self._deterministic:
+            check(self._lib.b200_finish_fixed_tally(self._h))
 
     # ------------------------------------------------------------- drivers
     def computeEigenvalue(self, max_iters: int = 1000, res_type: int = FISSION_SOURCE) -> None:

@@ -185,6 +185,35 @@ def test_step_loop_equals_fused_loop():
     assert rel_err(step.getFluxes(), gpu.getFluxes()) < 1e-10
 
 
+# ------------------------------------------------------- deterministic tally
+def test_deterministic_mode_is_bitwise_reproducible_and_accurate():
+    from openmoc_b200.solver import B200Solver
+    ft, ref = load_case("c5g7_2d_coarse")
+    runs = []
+    for _ in range(3):
+        s = B200Solver(ft, deterministic=True)
+        s.setConvergenceThreshold(1e-5)
+        s.computeEigenvalue(25, FISSION_SOURCE)
+        runs.append((s.getKeff(), s.getFluxes()))
+    assert runs[0][0] == runs[1][0] == runs[2][0]                       # bitwise equal k_eff
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][1], runs[2][1])
+    plain = B200Solver(ft)
+    plain.setConvergenceThreshold(1e-5)
+    plain.computeEigenvalue(25, FISSION_SOURCE)
+    assert abs(plain.getKeff() - runs[0][0]) * 1e5 < 1e-5
+    assert rel_err(runs[0][1], plain.getFluxes()) < 1e-9
+    # full solve against the oracle and the reference golden
+    gpu, cpu, _, _ = make("pin_cell")
+    det = B200Solver(load_case("pin_cell")[0], deterministic=True)
+    det.setConvergenceThreshold(1e-5)
+    det.computeEigenvalue(500, FISSION_SOURCE)
+    cpu.computeEigenvalue(500, 1e-5, FISSION_SOURCE)
+    assert det.getNumIterations() == cpu.getNumIterations() == 261
+    assert format_harness_results(261, det.getKeff(), det.getFluxes()) == GOLDENS["test_forward_pin_cell"]
+    with pytest.raises(capi.B200Error):
+        B200Solver(load_case("pin_cell")[0], deterministic=True, precision=PRECISION_MIXED)
+
+
 # ------------------------------------------------------- fixed-source drivers
 def test_compute_flux_fixed_source():
     gpu, cpu, ft, _ = make("simple_lattice")
