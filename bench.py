@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--azim", type=int, default=None)
     ap.add_argument("--spacing", type=float, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition", default="pair", choices=["pair", "chain"])
+    ap.add_argument("--deterministic", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -207,7 +209,8 @@ def main():
 
     t0 = time.perf_counter()
     solver = B200Solver(ft, device=local_rank, precision=precision,
-                        process_group=(dist.group.WORLD if world > 1 else None))
+                        process_group=(dist.group.WORLD if world > 1 else None),
+                        partition=args.partition, deterministic=args.deterministic)
     solver.useTorchStream()
     t_setup = time.perf_counter() - t0
     local_W = 2.0 * F * solver.tracks.n_segments
@@ -308,7 +311,8 @@ def main():
                        "num_polar": num_polar, "n_tracks": ft.n_tracks, "n_segments": ft.n_segments,
                        "n_fsrs": ft.n_fsrs, "groups": G, "fluxes_per_track": F,
                        "integrations_per_sweep": W_sweep,
-                       "parallelism": "1 GPU" if world == 1 else f"azimuthal-pair partition x{world} + NCCL all-reduce of the FSR tally",
+                       "parallelism": "1 GPU" if world == 1 else f"{args.partition} partition x{world} + NCCL all-reduce of the FSR tally",
+                       "deterministic_tally": bool(args.deterministic),
                        "l2": "segment stream (%.2f GB) is larger than the 126 MB L2; no flush" % (12.0 * ft.n_segments / 1e9)
                              if 12.0 * ft.n_segments > 2.5e8 else "inputs fit in L2; not flushed (launch-bound shape)",
                        "k_eff_after_timed_steps": k_dev, "track_generation_s": round(t_gen, 2),

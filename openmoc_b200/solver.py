@@ -49,12 +49,15 @@ class B200Solver:
     precision : int            capi.PRECISION_DOUBLE (reference double build) or PRECISION_MIXED
     process_group : optional   torch.distributed group; when its world size > 1 the
                                tracks are sharded by azimuthal pair across the ranks
+    partition : str            "pair": whole azimuthal reflective pairs per rank (north-star
+                               partition); "chain": whole track chains, balanced by segments
     deterministic : bool       accumulate the FSR tally in 64-bit fixed point: results are
                                bitwise reproducible run to run (and across GPU counts)
     """
 
     def __init__(self, tracks: FlatTracks, device: int = 0, precision: int = PRECISION_DOUBLE,
-                 process_group=None, use_distributed: Optional[bool] = None, deterministic: bool = False):
+                 process_group=None, use_distributed: Optional[bool] = None, deterministic: bool = False,
+                 partition: str = "pair"):
         self._lib = capi.load()
         self._h = C.c_void_p()
         self._global_tracks = tracks
@@ -70,8 +73,13 @@ class B200Solver:
                 self._rank = dist.get_rank(process_group)
                 self._world = dist.get_world_size(process_group)
         if self._world > 1:
-            from .partition import partition_by_azim_pair
-            tracks = partition_by_azim_pair(tracks, self._world)[self._rank]
+            from .partition import partition_by_azim_pair, partition_by_chain
+            if partition == "chain":
+                tracks = partition_by_chain(tracks, self._world)[self._rank]
+            elif partition == "pair":
+                tracks = partition_by_azim_pair(tracks, self._world)[self._rank]
+            else:
+                raise B200Error("unknown partition %r (pair, chain)" % partition)
         self.tracks = tracks
         self._num_groups = tracks.num_groups
         self._num_FSRs = tracks.n_fsrs

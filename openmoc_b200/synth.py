@@ -158,11 +158,43 @@ def _renumber_by_discovery(arrays: Dict[str, np.ndarray]) -> None:
     arrays["fsr_mat"] = arrays["fsr_mat"][uniq[order]]
 
 
+def materials_70g(names: List[str]) -> Dict[str, np.ndarray]:
+    """The synthetic 70-group set of tests/test_forward_3D_lattice_70g/
+    test_forward_3D_lattice_70g.py:43-61 (UO2 and Water; every other material gets the
+    Water data), in solver storage order."""
+    G = 70
+    n = len(names)
+    t = {k: np.zeros(n * G) for k in ("mat_sigma_t", "mat_sigma_a", "mat_sigma_f", "mat_nu_sigma_f", "mat_chi")}
+    t["mat_sigma_s"] = np.zeros(n * G * G)
+    t["mat_fiss_matrix"] = np.zeros(n * G * G)
+    t["mat_fissionable"] = np.zeros(n, dtype=np.uint8)
+    for m, name in enumerate(names):
+        if name == "UO2":
+            nsf, chi = np.linspace(0, 1, G) * 7, np.full(G, 1 / 70.)
+            s_in, sig_t = (np.linspace(0, 1, G * G) / 1000).reshape(G, G), np.linspace(2, 3, G)
+        else:
+            nsf, chi = np.zeros(G), np.zeros(G)
+            s_in, sig_t = (np.linspace(1, 2, G * G) / 1000).reshape(G, G), np.linspace(3, 4, G)
+        if chi.sum() > 0:
+            chi = chi / chi.sum()
+        sl = slice(m * G, (m + 1) * G)
+        t["mat_sigma_t"][sl], t["mat_nu_sigma_f"][sl], t["mat_chi"][sl] = sig_t, nsf, chi
+        t["mat_sigma_a"][sl] = sig_t - s_in.sum(axis=1)
+        t["mat_sigma_s"][m * G * G:(m + 1) * G * G] = s_in.T.ravel()
+        t["mat_fiss_matrix"][m * G * G:(m + 1) * G * G] = np.outer(chi, nsf).ravel()
+        t["mat_fissionable"][m] = 1 if nsf.sum() > 0 else 0
+    return t
+
+
 def make_tracks(model: str, num_azim: int = 4, spacing: float = 0.1, num_polar: int = 6,
                 polar_quad: int = None, num_threads: int = 0,
-                fsr_numbering: str = "discovery") -> FlatTracks:
+                fsr_numbering: str = "discovery", groups70: bool = False,
+                as_3d: bool = False) -> FlatTracks:
     """fsr_numbering: "discovery" (reference order, untouched regions dropped) or
-    "lattice" (by lattice cell, every geometric region kept)."""
+    "lattice" (by lattice cell, every geometric region kept).
+    groups70: swap the C5G7 data for the reference's synthetic 70-group set.
+    as_3d: label the tracks as 3D tracks of polar index 0 (one angular flux per group per
+    track, F = G) - a kernel-shape stand-in for 3D decks, not a physical 3D problem."""
     L = _load()
     nx, ny, px, py, xmin, ymin, cells, types, bcs, default_quad = _model(model)
     if polar_quad is None:
@@ -192,10 +224,12 @@ def make_tracks(model: str, num_azim: int = 4, spacing: float = 0.1, num_polar: 
     if fsr_numbering == "discovery":
         _renumber_by_discovery(arrays)
     names, mats = c5g7_materials()
-    arrays.update(mats)
     G = 7
-    ft = FlatTracks(num_groups=G, num_azim=num_azim, num_polar=num_polar, solve_3d=0,
-                    fluxes_per_track=G * num_polar // 2, n_tracks=int(arrays["trk_azim"].size),
+    if groups70:
+        mats, G = materials_70g(names), 70
+    arrays.update(mats)
+    ft = FlatTracks(num_groups=G, num_azim=num_azim, num_polar=num_polar, solve_3d=int(as_3d),
+                    fluxes_per_track=G if as_3d else G * num_polar // 2, n_tracks=int(arrays["trk_azim"].size),
                     n_segments=int(arrays["seg_length"].size), n_fsrs=int(arrays["fsr_volume"].size),
                     n_materials=len(names), arrays=arrays)
     return ft

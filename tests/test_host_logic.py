@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import load_case
-from openmoc_b200.partition import assign_pairs, partition_by_azim_pair
+from openmoc_b200.partition import assign_pairs, partition_by_azim_pair, partition_by_chain, track_components
 from openmoc_b200.trackfile import FlatTracks, read_trackfile, write_trackfile, REFLECTIVE, PERIODIC
 from oracle.oracle_py import OracleSolver
 
@@ -135,3 +135,24 @@ def test_partitioned_sweep_sums_to_whole():
     base.setSources(q)
     base.transportSweep()
     np.testing.assert_allclose(phi_whole, base.getFluxes(), rtol=1e-12, atol=1e-13)
+
+
+def test_chain_partition_is_closed_balanced_and_sums_to_whole():
+    """Track chains (connected components of the hand-off graph) can be sharded even when
+    there is a single azimuthal pair; per-rank tallies still add up to the whole."""
+    ft, _ = load_case("simple_lattice")          # 4 azimuthal angles = ONE pair
+    assert track_components(ft).max() + 1 >= 2
+    parts = partition_by_chain(ft, 2)
+    assert sum(p.n_tracks for p in parts) == ft.n_tracks
+    assert abs(parts[0].n_segments - parts[1].n_segments) <= 0.1 * ft.n_segments
+    rng = np.random.default_rng(5)
+    q = rng.uniform(0.0, 1.0, ft.n_fsrs * ft.num_groups)
+    whole = OracleSolver(ft); whole.setSources(q); whole.transportSweep()
+    total = np.zeros(ft.n_fsrs * ft.num_groups)
+    for p in parts:
+        p.validate()
+        o = OracleSolver(p); o.setSources(q); o.transportSweep()
+        total += o.getFluxes()
+    np.testing.assert_allclose(total, whole.getFluxes(), rtol=1e-12, atol=1e-13)
+    with pytest.raises(ValueError):
+        partition_by_chain(ft, 1000)

@@ -14,9 +14,13 @@ ap.add_argument("--azim", type=int, default=64)
 ap.add_argument("--spacing", type=float, default=0.02)
 ap.add_argument("--sweeps", type=int, default=10)
 ap.add_argument("--precision", default="double")
+ap.add_argument("--groups70", action="store_true")
+ap.add_argument("--as3d", action="store_true")
+ap.add_argument("--deterministic", action="store_true")
 args = ap.parse_args()
-ft = make_tracks(args.model, num_azim=args.azim, spacing=args.spacing)
-s = B200Solver(ft, precision=capi.PRECISION_MIXED if args.precision == "mixed" else capi.PRECISION_DOUBLE)
+ft = make_tracks(args.model, num_azim=args.azim, spacing=args.spacing, groups70=args.groups70, as_3d=args.as3d)
+s = B200Solver(ft, precision=capi.PRECISION_MIXED if args.precision == "mixed" else capi.PRECISION_DOUBLE,
+               deterministic=args.deterministic)
 s.zeroTrackFluxes(); s.flattenFSRFluxes(1.0); s.normalizeFluxes(); s.storeFSRFluxes()
 s.computeFSRSources(0)
 for _ in range(3):
@@ -27,5 +31,5 @@ for _ in range(args.sweeps):
 s.synchronize()
 ms, n, _ = s.getSweepStats()
 W = s.integrationsPerSweep()
-print(f"GPL={os.environ.get('B200_GPL','auto')} IPC={os.environ.get('B200_IPC','auto')} {args.precision}: "
+print(f"GPL={os.environ.get('B200_GPL','auto')} IPC={os.environ.get('B200_IPC','auto')} {args.precision} G={ft.num_groups} 3d={ft.solve_3d} det={args.deterministic}: "
       f"N_seg={ft.n_segments} sweep {ms/n:.3f} ms  {W/(ms/n*1e-3):.3e} integrations/s")
