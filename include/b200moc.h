@@ -129,6 +129,16 @@ int b200_compute_flux(b200_solver* s, int32_t max_iters, double tolerance,
                       int32_t only_fixed_source, int32_t* num_iterations);
 int b200_compute_source(b200_solver* s, int32_t max_iters, double k_eff, double tolerance,
                         int32_t res_type, int32_t* num_iterations);
+/* the same loop in pieces, for hosts that reduce the FSR tally across GPUs inside every
+ * iteration: init; then per iteration begin (sources + sweep) -> [all-reduce scalar_flux] ->
+ * end (closure, k_eff, normalisation, residual, store, device-side stopping rule); status
+ * fetches the convergence flag (poll it every few iterations; once done, later begin/end
+ * calls are no-ops on the device). */
+int b200_eigen_loop_init(b200_solver* s, int32_t max_iters, double tolerance);
+int b200_iteration_begin(b200_solver* s, int32_t iteration);
+int b200_iteration_end(b200_solver* s, int32_t iteration, int32_t res_type, int32_t check_convergence);
+int b200_eigen_loop_status(b200_solver* s, int32_t enqueued, int32_t* done, int32_t* iterations,
+                           double* k_eff, double* residual);
 /* run exactly n source iterations (sources..store) without convergence test;
  * benchmark hook.  residual/k of the last iteration are returned if non-NULL */
 int b200_iterate(b200_solver* s, int32_t n, int32_t res_type, double* k_eff, double* residual);

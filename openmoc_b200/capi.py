@@ -72,6 +72,10 @@ SIGNATURES = {
     "b200_compute_flux": [_i32, _dbl, _i32, C.POINTER(_i32)],
     "b200_compute_source": [_i32, _dbl, _dbl, _i32, C.POINTER(_i32)],
     "b200_iterate": [_i32, _i32, C.POINTER(_dbl), C.POINTER(_dbl)],
+    "b200_eigen_loop_init": [_i32, _dbl],
+    "b200_iteration_begin": [_i32],
+    "b200_iteration_end": [_i32, _i32, _i32],
+    "b200_eigen_loop_status": [_i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_dbl), C.POINTER(_dbl)],
     "b200_get_sweep_stats": [C.POINTER(_dbl), C.POINTER(_i64), C.POINTER(_i64)],
     "b200_reset_sweep_stats": [],
     "b200_synchronize": [],

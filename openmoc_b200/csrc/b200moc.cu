@@ -1012,10 +1012,13 @@ extern "C" int b200_set_start_fluxes(b200_solver* s, const float* in, int64_t n)
 /* fused drivers                                                              */
 /* ------------------------------------------------------------------------- */
 /* one source iteration of Solver::computeEigenvalue (src/Solver.cpp:1614-1681) */
-static int enqueue_eigen_iteration(b200_solver* s, int i, int res_type, int loop_kind) {
+static int enqueue_iteration_begin(b200_solver* s, int i) {
   if (i > 0 && s->stabilize) { if (b200_compute_stabilizing_flux(s)) return 1; }
   if (launch_sources(s, i, 0)) return 1;
-  if (launch_sweep(s)) return 1;
+  return launch_sweep(s);
+}
+
+static int enqueue_iteration_end(b200_solver* s, int i, int res_type, int loop_kind) {
   FsrArgs a = fsr_args(s);
   if (!s->stabilize) {
     /* closure + the one nu-fission reduction that feeds both computeKeff and
@@ -1040,6 +1043,11 @@ static int enqueue_eigen_iteration(b200_solver* s, int i, int res_type, int loop
   }
   if (launch_residual(s, res_type, 1, 1, loop_kind, i)) return 1;
   return 0;
+}
+
+static int enqueue_eigen_iteration(b200_solver* s, int i, int res_type, int loop_kind) {
+  if (enqueue_iteration_begin(s, i)) return 1;
+  return enqueue_iteration_end(s, i, res_type, loop_kind);
 }
 
 static int prepare_history(b200_solver* s, int max_iters) {
@@ -1081,6 +1089,59 @@ extern "C" int b200_compute_eigenvalue(b200_solver* s, int32_t max_iters, double
   if (num_iterations) *num_iterations = s->h_iscal[SI_ITERS];
   if (clear_done(s)) return 1;
   return resolve_events(s);
+}
+
+/* ---- the fused eigenvalue loop in pieces, for hosts that must reduce the FSR tally across
+ *      GPUs in the middle of every iteration (multi-GPU angular decomposition) ---- */
+extern "C" int b200_eigen_loop_init(b200_solver* s, int32_t max_iters, double tol) {
+  NEED_FINAL(s);
+  if (prepare_history(s, max_iters)) return 1;
+  double init[SC_COUNT_D] = {0};
+  init[SC_KEFF] = 1.0; init[SC_KPREV] = 1.0; init[SC_TOL] = tol;
+  CU(cudaMemcpyAsync(s->scal.p, init, sizeof init, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (clear_done(s)) return 1;
+  if (b200_zero_track_fluxes(s)) return 1;
+  CU(cudaMemsetAsync(s->phi_old.p, 0, (size_t)s->n_fsr * s->G * 8, s->stream));
+  if (b200_flatten_fsr_fluxes(s, 1.0)) return 1;
+  if (launch_rate(s, 2)) return 1;
+  if (launch_scale(s)) return 1;
+  return b200_store_fsr_fluxes(s);
+}
+/* Between begin and end the host all-reduces scalar_flux in place.  Once the loop has
+ * converged the kernels of later iterations are no-ops, but the host's all-reduce still runs
+ * and would sum the final flux over the ranks: begin saves it, end restores it. */
+extern "C" int b200_iteration_begin(b200_solver* s, int32_t iteration) {
+  NEED_FINAL(s);
+  if (enqueue_iteration_begin(s, iteration)) return 1;
+  const int64_t n = s->n_fsr * s->G;
+  copy_if_done_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->scratch.p, s->phi.p, n, s->iscal.p);
+  CU(cudaGetLastError());
+  return 0;
+}
+extern "C" int b200_iteration_end(b200_solver* s, int32_t iteration, int32_t res_type, int32_t check_convergence) {
+  NEED_FINAL(s);
+  if (res_type < 0 || res_type > 2) return fail("b200_iteration_end: unknown residual type %d", res_type);
+  if (check_convergence && s->hist_k.n <= (size_t)iteration)
+    return fail("b200_iteration_end: iteration %d beyond the max_iters given to b200_eigen_loop_init", iteration);
+  const int64_t n = s->n_fsr * s->G;
+  copy_if_done_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->phi.p, s->scratch.p, n, s->iscal.p);
+  CU(cudaGetLastError());
+  return enqueue_iteration_end(s, iteration, res_type, check_convergence ? 1 : 0);
+}
+extern "C" int b200_eigen_loop_status(b200_solver* s, int32_t enqueued, int32_t* done, int32_t* iterations,
+                                      double* k_eff, double* residual) {
+  NEED_FINAL(s);
+  if (fetch_scalars(s)) return 1;
+  if (done) *done = s->h_iscal[SI_DONE];
+  if (iterations) *iterations = s->h_iscal[SI_ITERS];
+  if (k_eff) *k_eff = s->h_scal[SC_KEFF];
+  if (residual) *residual = s->h_scal[SC_RESIDUAL];
+  if (s->h_iscal[SI_DONE]) {          /* loop over: undo the host-side psi flips of no-op iterations */
+    fix_psi_parity(s, enqueued, s->h_iscal[SI_EXEC]);
+    if (clear_done(s)) return 1;
+  }
+  return 0;
 }
 
 extern "C" int b200_iterate(b200_solver* s, int32_t n, int32_t res_type, double* k_eff, double* residual) {

@@ -310,6 +310,13 @@ __global__ void zero_phi_kernel(double* __restrict__ dst, int64_t n, const int* 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) dst[i] = 0.0;
 }
+/* copy that only runs once the device-side loop has converged (see b200_iteration_begin) */
+__global__ void copy_if_done_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t n,
+                                    const int* __restrict__ iscal) {
+  if (!iscal[SI_DONE]) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
 __global__ void fill_kernel(double* __restrict__ dst, double v, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) dst[i] = v;

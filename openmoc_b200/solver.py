@@ -288,12 +288,30 @@ class B200Solver:
                                                     int(res_type), C.byref(n)))
             self._num_iterations = n.value
         else:
-            self._num_iterations = self._eigenvalue_loop(max_iters, res_type)
+            self._num_iterations = self._eigenvalue_loop_distributed(max_iters, res_type)
         self.getKeff()
         self._total_time = time.perf_counter() - t0
 
+    def _eigenvalue_loop_distributed(self, max_iters: int, res_type: int, poll: int = 8) -> int:
+        """Multi-GPU loop: the device-side fused iteration split around the all-reduce of the
+        FSR tally; the stopping rule is evaluated on the device and polled every `poll`
+        iterations (once it fires, the remaining enqueued iterations are no-ops)."""
+        L, h = self._lib, self._h
+        check(L.b200_eigen_loop_init(h, int(max_iters), self._converge_thresh))
+        done, iters = C.c_int32(0), C.c_int32(0)
+        i = 0
+        while i < max_iters and not done.value:
+            end = min(max_iters, i + poll)
+            while i < end:
+                check(L.b200_iteration_begin(h, i))
+                self._allreduce_scalar_flux()
+                check(L.b200_iteration_end(h, i, int(res_type), 1))
+                i += 1
+            check(L.b200_eigen_loop_status(h, i, C.byref(done), C.byref(iters), None, None))
+        return iters.value
+
     def _eigenvalue_loop(self, max_iters: int, res_type: int) -> int:
-        """The same loop driven step by step from the host (multi-GPU path)."""
+        """The same loop driven step by step from the host through the Solver virtuals."""
         check(self._lib.b200_set_keff(self._h, 1.0))
         self.zeroTrackFluxes()
         self.flattenFSRFluxes(0.0)
@@ -355,13 +373,9 @@ class B200Solver:
         """n fused source iterations without convergence test (benchmark hook)."""
         if self._world > 1:
             for i in range(n):
-                self.computeFSRSources(1000 + i)
-                self.transportSweep()
-                self.addSourceToScalarFlux()
-                self.computeKeff(fetch=False)
-                self.normalizeFluxes(fetch=False)
-                self.computeResidual(res_type, fetch=False)
-                self.storeFSRFluxes()
+                check(self._lib.b200_iteration_begin(self._h, 1000 + i))
+                self._allreduce_scalar_flux()
+                check(self._lib.b200_iteration_end(self._h, 1000 + i, int(res_type), 0))
             return
         check(self._lib.b200_iterate(self._h, int(n), int(res_type), None, None))
 
