@@ -113,6 +113,9 @@ int b200_reset_fixed_sources(b200_solver* s);
 int b200_compute_fsr_fission_rates(b200_solver* s, double* fission_rates, int64_t num_fsrs, int32_t nu);
 int b200_stabilize_transport(b200_solver* s, double factor, int32_t stabilization_type);
 int b200_allow_negative_fluxes(b200_solver* s, int32_t allowed);
+/* Solver::setKeffFromNeutronBalance (src/Solver.cpp:2047): k = fission / (absorption + leakage),
+ * with the vacuum leakage tallied in the sweep (src/CPUSolver.cpp:2264-2325, 2592-2600) */
+int b200_set_keff_from_neutron_balance(b200_solver* s, int32_t on);
 int b200_get_keff(b200_solver* s, double* k_eff);
 int b200_set_keff(b200_solver* s, double k_eff);
 int b200_get_fsr_sources(b200_solver* s, double* out, int64_t n);       /* reduced sources q */

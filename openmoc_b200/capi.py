@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200_compute_fsr_fission_rates": [_vp, _i64, _i32],
     "b200_stabilize_transport": [_dbl, _i32],
     "b200_allow_negative_fluxes": [_i32],
+    "b200_set_keff_from_neutron_balance": [_i32],
     "b200_get_keff": [C.POINTER(_dbl)],
     "b200_set_keff": [_dbl],
     "b200_get_fsr_sources": [_vp, _i64],

@@ -134,10 +134,8 @@ void B200Solver::pushKeff() {
 /* ------------------------------ hooks ------------------------------------ */
 void B200Solver::initializeExpEvaluators() {
   Solver::initializeExpEvaluators();
-  if (!_keff_from_fission_rates)
-    log_printf(ERROR, "B200Solver computes k_eff from fission rates only "
-               "(setKeffFromNeutronBalance is not supported)");
   ensureDevice();
+  check(b200_set_keff_from_neutron_balance(_h, !_keff_from_fission_rates), "b200_set_keff_from_neutron_balance");
 }
 
 void B200Solver::initializeMaterials(solverMode mode) {

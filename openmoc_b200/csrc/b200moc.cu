@@ -124,7 +124,8 @@ struct b200_solver {
   DevBuf<double> cls_w, cls_inv_sin;
   /* device: FSR + materials */
   DevBuf<int32_t> fsr_mat;
-  DevBuf<double> vol, sigma_t, sigma_s, fiss, nu_sigma_f, sigma_f, chi, max_ratio;
+  DevBuf<double> vol, sigma_t, sigma_s, fiss, nu_sigma_f, sigma_f, sigma_a, chi, max_ratio, part3;
+  DevBuf<float> leakage;
   DevBuf<uint8_t> fissionable;
   /* device: state */
   DevBuf<double> phi, phi_old, fixed, stab, scratch;
@@ -146,7 +147,7 @@ struct b200_solver {
   int64_t sweep_blocks = 0;
 
   /* options */
-  bool fixed_on = false, stabilize = false, neg_allowed = false;
+  bool fixed_on = false, stabilize = false, neg_allowed = false, balance = false;
   double stab_factor = 1.0;
   int stab_type = 0;
 
@@ -169,6 +170,7 @@ static FsrArgs fsr_args(b200_solver* s) {
   a.fiss = s->fiss.p;
   a.nu_sigma_f = s->nu_sigma_f.p;
   a.sigma_f = s->sigma_f.p;
+  a.sigma_a = s->sigma_a.p;
   a.chi = s->chi.p;
   a.fissionable = s->fissionable.p;
   a.phi = s->phi.p;
@@ -279,7 +281,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   s->trk_class.release(); s->order.release(); s->carry.release(); s->cls_w.release();
   s->cls_inv_sin.release(); s->fsr_mat.release(); s->vol.release(); s->sigma_t.release();
   s->sigma_s.release(); s->fiss.release(); s->nu_sigma_f.release(); s->sigma_f.release();
-  s->chi.release(); s->max_ratio.release(); s->fissionable.release(); s->phi.release();
+  s->chi.release(); s->max_ratio.release(); s->sigma_a.release(); s->part3.release(); s->leakage.release(); s->fissionable.release(); s->phi.release();
   s->phi_fx.release(); s->fx_bits.release();
   s->phi_old.release(); s->fixed.release(); s->stab.release(); s->scratch.release();
   s->qst.release(); s->psi_a.release(); s->psi_b.release(); s->scal.release();
@@ -394,6 +396,17 @@ extern "C" int b200_upload_materials(b200_solver* s, const double* sigma_t, cons
   s->h_fissionable.assign(fissionable, fissionable + s->n_mat);
   s->h_sigma_t.assign(sigma_t, sigma_t + nG);
   s->h_sigma_s.assign(sigma_s, sigma_s + nGG);
+  {
+    /* absorption = total minus out-scatter, the default of Material::getSigmaA (src/Material.cpp:241-249) */
+    std::vector<double> sa(nG);
+    for (int m = 0; m < s->n_mat; m++)
+      for (int g = 0; g < s->G; g++) {
+        double v = sigma_t[(size_t)m * s->G + g];
+        for (int gp = 0; gp < s->G; gp++) v -= sigma_s[((size_t)m * s->G + gp) * s->G + g];
+        sa[(size_t)m * s->G + g] = v;
+      }
+    CU(s->sigma_a.upload(sa.data(), nG, s->stream));
+  }
   CU(cudaStreamSynchronize(s->stream));
   s->have_mats = true;
   /* a finalized solver stays usable: only the material-derived tables are rebuilt
@@ -488,6 +501,9 @@ extern "C" int b200_finalize(b200_solver* s) {
   CU(s->phi.alloc(nphi)); CU(s->phi_old.alloc(nphi)); CU(s->fixed.alloc(nphi));
   CU(s->stab.alloc(nphi)); CU(s->qst.alloc(nphi)); CU(s->scratch.alloc(std::max(nphi, (size_t)s->n_fsr)));
   CU(s->psi_a.alloc(npsi)); CU(s->psi_b.alloc(npsi));
+  CU(s->leakage.alloc(std::max<size_t>(nt, 1)));
+  CU(cudaMemsetAsync(s->leakage.p, 0, std::max<size_t>(nt, 1) * 4, s->stream));
+  CU(s->part3.alloc(3 * MAX_PARTIALS));
   if (s->cfg.deterministic) {
     CU(s->phi_fx.alloc(nphi)); CU(s->fx_bits.alloc(4));
     CU(cudaMemsetAsync(s->phi_fx.p, 0, nphi * 8, s->stream));
@@ -662,8 +678,14 @@ static int launch_sweep(b200_solver* s) {
     a.carry = s->carry.p; a.cls_w = s->cls_w.p; a.cls_inv_sin = s->cls_inv_sin.p;
     a.qst = s->qst.p; a.psi_in = s->psi_start; a.psi_out = s->psi_other; a.phi = s->phi.p;
     a.phi_fx = s->phi_fx.p; a.fx_scale = s->scal.p + SC_FXSCALE;
+    a.leakage = s->balance ? s->leakage.p : nullptr;
+    if (s->balance) {
+      zero_float_kernel<<<grid_for(s->n_trk, 256), 256, 0, s->stream>>>(s->leakage.p, s->n_trk, s->iscal.p);
+      CU(cudaGetLastError());
+      s->n_launches++;
+    }
     a.done = s->iscal.p + SI_DONE;
-    a.n_items = 2 * s->n_trk; a.G = s->G; a.lpi = s->lpi;
+    a.n_items = 2 * s->n_trk; a.G = s->G; a.lpi = s->lpi; a.exact = (s->gpl * s->lpi == s->G) ? 1 : 0;
     {
       using C = F1Coef<double>;
       const double cf[11] = {C::d1, C::d2, C::d3, C::d4, C::d5, C::d6, C::p1, C::p2, C::p3, C::p4, C::p5};
@@ -846,10 +868,27 @@ extern "C" int b200_add_source_to_scalar_flux(b200_solver* s) {
   return launch_closure(s, 0, nullptr);
 }
 
+static int launch_balance_keff(b200_solver* s) {
+  FsrArgs a = fsr_args(s);
+  const int nb = grid_for(std::max<int64_t>(s->n_fsr * s->G, s->n_trk), RED_THREADS, MAX_PARTIALS);
+  balance_partials_kernel<<<dim3(nb, 3), RED_THREADS, 0, s->stream>>>(a, s->leakage.p, s->n_trk, s->part3.p);
+  CU(cudaGetLastError());
+  balance_finalize_kernel<<<1, RED_THREADS, 0, s->stream>>>(a, s->part3.p, nb);
+  CU(cudaGetLastError());
+  s->n_launches += 2;
+  return 0;
+}
+
+extern "C" int b200_set_keff_from_neutron_balance(b200_solver* s, int32_t on) {
+  NEED(s);
+  s->balance = on != 0;
+  return 0;
+}
+
 extern "C" int b200_compute_keff(b200_solver* s, double* k_eff) {
   NEED_FINAL(s);
   if (clear_done(s)) return 1;
-  if (launch_rate(s, 1)) return 1;
+  if (s->balance ? launch_balance_keff(s) : launch_rate(s, 1)) return 1;
   if (k_eff != nullptr) {
     if (fetch_scalars(s)) return 1;
     *k_eff = s->h_scal[SC_KEFF];
@@ -1020,7 +1059,12 @@ static int enqueue_iteration_begin(b200_solver* s, int i) {
 
 static int enqueue_iteration_end(b200_solver* s, int i, int res_type, int loop_kind) {
   FsrArgs a = fsr_args(s);
-  if (!s->stabilize) {
+  if (s->balance) {
+    if (launch_closure(s, 0, nullptr)) return 1;
+    if (launch_balance_keff(s)) return 1;
+    if (i > 0 && s->stabilize) { if (b200_stabilize_flux(s)) return 1; }
+    if (launch_rate(s, 2)) return 1;
+  } else if (!s->stabilize) {
     /* closure + the one nu-fission reduction that feeds both computeKeff and
      * normalizeFluxes (identical sums when no stabilisation sits in between) */
     int nb = 0;

@@ -38,6 +38,7 @@ struct FsrArgs {
   const double* __restrict__ fiss;        /* [mat][dest*G+orig] */
   const double* __restrict__ nu_sigma_f;  /* [mat][G] */
   const double* __restrict__ sigma_f;
+  const double* __restrict__ sigma_a;     /* [mat][G], Material::getSigmaA */
   const double* __restrict__ chi;
   const uint8_t* __restrict__ fissionable;
   double* __restrict__ phi;
@@ -177,6 +178,48 @@ rate_partials_kernel(const FsrArgs a) {
   }
   const double s = block_sum(local);
   if (threadIdx.x == 0) a.partials[blockIdx.x] = s;
+}
+
+/* ---- k_eff from the neutron balance (src/CPUSolver.cpp:2264-2325, Solver::setKeffFromNeutronBalance):
+ *      k = fission / (absorption + leakage); three fixed-order reductions ---- */
+__global__ void __launch_bounds__(RED_THREADS)
+balance_partials_kernel(const FsrArgs a, const float* __restrict__ leakage, int64_t n_trk, double* __restrict__ out3) {
+  /* grid = 3 x nb blocks: blockIdx.y selects fission / absorption / leakage */
+  if (a.iscal[SI_DONE]) return;
+  const int G = a.G;
+  double local = 0.;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (blockIdx.y < 2) {
+    const double* __restrict__ sig = blockIdx.y == 0 ? a.nu_sigma_f : a.sigma_a;
+    const int64_t n = a.n_fsr * G;
+    for (int64_t idx = tid; idx < n; idx += nth) {
+      const int64_t r = idx / G;
+      local += sig[(int64_t)a.fsr_mat[r] * G + (idx - r * G)] * a.phi[idx] * a.vol[r];
+    }
+  } else {
+    for (int64_t t = tid; t < n_trk; t += nth) local += (double)leakage[t];
+  }
+  const double s = block_sum(local);
+  if (threadIdx.x == 0) out3[blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(RED_THREADS)
+balance_finalize_kernel(const FsrArgs a, const double* __restrict__ part3, int nb) {
+  if (a.iscal[SI_DONE]) return;
+  __shared__ double r[3];
+  for (int k = 0; k < 3; k++) {
+    const double v = fold_partials(part3 + k * nb, nb);
+    if (threadIdx.x == 0) r[k] = v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    a.scal[SC_KPREV] = a.scal[SC_KEFF];
+    a.scal[SC_KEFF] = r[0] / (r[1] + r[2]);
+    a.scal[SC_RATE] = r[0];
+  }
+}
+__global__ void zero_float_kernel(float* __restrict__ p, int64_t n, const int* __restrict__ iscal) {
+  if (iscal[SI_DONE]) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
 
 /* fold the rate partials; op 0: rate only, 1: k *= rate/N (computeKeff :2327),

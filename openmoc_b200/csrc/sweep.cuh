@@ -243,9 +243,11 @@ struct SweepArgs {
    * associative, so the result does not depend on the order the atomics land in) */
   unsigned long long* __restrict__ phi_fx; /* [n_fsr*G], used by the DET kernels */
   const double* __restrict__ fx_scale;     /* device scalar: power-of-two scale */
+  float* __restrict__ leakage;             /* [n_trk] vacuum leakage tally, NULL unless k_eff from neutron balance */
   const int* __restrict__ done;            /* device convergence flag (may be NULL) */
   int64_t n_items;
   int G, lpi;
+  int exact;                               /* G == GPL * LPI */
   /* expF1 coefficients d1..d6, p1..p5 (src/exponentials.h:159-173).  As kernel parameters
    * they sit in constant bank 0 and every Horner DFMA takes its coefficient as a c[0][..]
    * operand: two register pairs per DFMA, which the register file can feed every 2 cycles
@@ -280,7 +282,8 @@ sweep_kernel(const SweepArgs a) {
 #pragma unroll
   for (int j = 0; j < GPL; j++) {
     int ej = sub + j * a.lpi;
-    valid[j] = ej < G;
+    /* a.exact: G == GPL*LPI, every slot is a real group (G = 7, 70, ...): no clamping */
+    valid[j] = a.exact || ej < G;
     e[j] = (uint32_t)(valid[j] ? ej : G - 1);
   }
 
@@ -414,6 +417,16 @@ sweep_kernel(const SweepArgs a) {
 #pragma unroll
       for (int j = 0; j < GPL; j++)
         if (valid[j]) a.psi_out[base + p * G + e[j]] = psi[p][j];
+  } else if (a.leakage != nullptr) {
+    /* vacuum end: leakage tally of transferBoundaryFlux (src/CPUSolver.cpp:2592-2600); the
+     * reference weighs every flux of a 2D track with the weight of polar index 0 */
+    double lk = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+      for (int j = 0; j < GPL; j++)
+        if (valid[j]) lk += (double)psi[p][j];
+    atomicAdd(&a.leakage[t], (float)((double)a.cls_w[cls * NP] * lk));
   }
 }
 
@@ -548,6 +561,16 @@ sweep_kernel_ring(const SweepArgs a) {
 #pragma unroll
       for (int j = 0; j < GPL; j++)
         if (valid[j]) a.psi_out[base + p * G + e[j]] = psi[p][j];
+  } else if (a.leakage != nullptr) {
+    /* vacuum end: leakage tally of transferBoundaryFlux (src/CPUSolver.cpp:2592-2600); the
+     * reference weighs every flux of a 2D track with the weight of polar index 0 */
+    double lk = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+      for (int j = 0; j < GPL; j++)
+        if (valid[j]) lk += (double)psi[p][j];
+    atomicAdd(&a.leakage[t], (float)((double)a.cls_w[cls * NP] * lk));
   }
 }
 
@@ -704,6 +727,16 @@ sweep_kernel_staged(const SweepArgs a) {
 #pragma unroll
       for (int j = 0; j < GPL; j++)
         if (valid[j]) a.psi_out[base + p * G + e[j]] = psi[p][j];
+  } else if (a.leakage != nullptr) {
+    /* vacuum end: leakage tally of transferBoundaryFlux (src/CPUSolver.cpp:2592-2600); the
+     * reference weighs every flux of a 2D track with the weight of polar index 0 */
+    double lk = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+      for (int j = 0; j < GPL; j++)
+        if (valid[j]) lk += (double)psi[p][j];
+    atomicAdd(&a.leakage[t], (float)((double)a.cls_w[cls * NP] * lk));
   }
 }
 

@@ -207,6 +207,12 @@ class B200Solver:
     def stabilizeTransport(self, stabilization_factor: float, stabilization_type: int = DIAGONAL) -> None:
         check(self._lib.b200_stabilize_transport(self._h, float(stabilization_factor), int(stabilization_type)))
 
+    def setKeffFromNeutronBalance(self) -> None:
+        """Solver::setKeffFromNeutronBalance: k = fission / (absorption + leakage)."""
+        if self._world > 1:
+            raise B200Error("k_eff from the neutron balance is single-GPU in this build")
+        check(self._lib.b200_set_keff_from_neutron_balance(self._h, 1))
+
     def allowNegativeFluxes(self, negative_fluxes_on: bool) -> None:
         check(self._lib.b200_allow_negative_fluxes(self._h, int(bool(negative_fluxes_on))))
 

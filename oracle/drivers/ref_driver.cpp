@@ -13,7 +13,7 @@
  *        --solver both: CPUSolver and B200Solver in the same process on the same tracks,
  *        prints delta k_eff (pcm), max relative flux error and both sweep times.
  *                   [--max-iters N] [--threads N] [--res fission|flux|total]
- *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet]
+ *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
  */
 #include <cstdio>
 #include <cstdlib>
@@ -108,6 +108,7 @@ int main(int argc, char** argv) {
     CPUSolver cpu(tg);
     cpu.setNumThreads(threads);
     cpu.setConvergenceThreshold(tol);
+    if (flag(argc, argv, "--balance")) cpu.setKeffFromNeutronBalance();
     cpu.computeEigenvalue(max_iters, rt);
     Timer timer;
     double cpu_sweep = timer.getSplit("Transport Sweep");
@@ -118,6 +119,7 @@ int main(int argc, char** argv) {
 
     B200Solver gpu(tg);
     gpu.setConvergenceThreshold(tol);
+    if (flag(argc, argv, "--balance")) gpu.setKeffFromNeutronBalance();
     gpu.computeEigenvalue(max_iters, rt);
     double gpu_sweep = timer.getSplit("Transport Sweep");
     gpu.getFluxes(phi_gpu.data(), n_fsr * G);
@@ -148,6 +150,7 @@ int main(int argc, char** argv) {
   else solver = cpu_solver = new CPUSolver(tg);
   if (cpu_solver != NULL) cpu_solver->setNumThreads(threads);
   solver->setConvergenceThreshold(tol);
+  if (flag(argc, argv, "--balance")) solver->setKeffFromNeutronBalance();   /* Solver.cpp:2047 */
 
   if (mode == "eigen") {
     if (solver_name == "b200-fused") b200_solver->computeEigenvalueFused(max_iters, rt);

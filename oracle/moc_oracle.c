@@ -39,7 +39,8 @@ struct moc_oracle {
   double* phi; double* phi_old; double* q; double* fixed; double* stab;
   float* psi_start; float* psi_bound;
   double k_eff;
-  int fixed_on, stabilize, stab_type, threads;
+  int fixed_on, stabilize, stab_type, threads, balance;
+  float* leakage; double* sigma_a;
   double stab_factor;
   double sweep_seconds;
   double* scratch;
@@ -142,6 +143,15 @@ moc_oracle* moc_oracle_create(
   size_t npsi = (size_t)n_tracks * 2 * o->F;
   o->psi_start = calloc(npsi, 4); o->psi_bound = calloc(npsi, 4);
   o->scratch = calloc(n_fsrs > 0 ? n_fsrs : 1, 8);
+  o->leakage = calloc(n_tracks > 0 ? n_tracks : 1, 4);
+  /* Material::getSigmaA when never set: sigma_t minus the out-scatter sum (src/Material.cpp:241-249) */
+  o->sigma_a = calloc((size_t)n_materials * G, 8);
+  for (int m = 0; m < n_materials; m++)
+    for (int g = 0; g < G; g++) {
+      double a = o->sigma_t[(size_t)m * G + g];
+      for (int gp = 0; gp < G; gp++) a -= o->sigma_s[((size_t)m * G + gp) * G + g];
+      o->sigma_a[(size_t)m * G + g] = a;
+    }
   o->k_eff = 1.0;
   o->threads = 1;
   /* src/Solver.cpp:882-892 */
@@ -158,7 +168,7 @@ void moc_oracle_destroy(moc_oracle* o) {
   free(o->sigma_t); free(o->sigma_s); free(o->fiss); free(o->nu_sigma_f); free(o->sigma_f);
   free(o->chi); free(o->fissionable);
   free(o->phi); free(o->phi_old); free(o->q); free(o->fixed); free(o->stab);
-  free(o->psi_start); free(o->psi_bound); free(o->scratch);
+  free(o->psi_start); free(o->psi_bound); free(o->scratch); free(o->leakage); free(o->sigma_a);
   free(o);
 }
 
@@ -341,6 +351,12 @@ static void sweep_track(moc_oracle* o, int64_t t, double* fsr_flux) {
       float* out = o->psi_start + ((size_t)nxt * 2 + (next_is_fwd ? 0 : 1)) * F;
       memcpy(out, track_flux, F * 4);
     }
+    /* leakage tally (src/CPUSolver.cpp:2592-2600): weight of (azim, polar_index), where
+     * polar_index is 0 for every 2D track (TrackTraversingAlgorithms.cpp:901) */
+    if (o->balance && bc == BC_VACUUM) {
+      double weight = wrow[o->solve_3d ? polar : 0];
+      for (int pe = 0; pe < F; pe++) o->leakage[t] += weight * track_flux[pe];
+    }
   }
 }
 
@@ -349,6 +365,7 @@ void moc_oracle_transport_sweep(moc_oracle* o) {
   double t0 = omp_get_wtime();
   memset(o->phi, 0, (size_t)o->n_fsr * o->G * 8);                    /* :2347 */
   memcpy(o->psi_bound, o->psi_start, (size_t)o->n_trk * 2 * o->F * 4); /* :2351 */
+  memset(o->leakage, 0, (size_t)o->n_trk * 4);                          /* :2360 */
 #pragma omp parallel num_threads(o->threads)
   {
     double* fsr_flux = (double*)malloc(o->G * 8);
@@ -392,8 +409,26 @@ void moc_oracle_compute_keff(moc_oracle* o) {
   }
   free(gr);
   double rate = pairwise_sum(o->scratch, o->n_fsr);
-  o->k_eff *= rate / o->n_fsr;
+  if (!o->balance) {
+    o->k_eff *= rate / o->n_fsr;
+    return;
+  }
+  /* k = fission / (absorption + leakage), src/CPUSolver.cpp:2264-2325 */
+  gr = (double*)malloc(G * 8);
+  for (int64_t r = 0; r < o->n_fsr; r++) {
+    const double* sigma = o->sigma_a + (size_t)o->fsr_mat[r] * G;
+    for (int e = 0; e < G; e++) gr[e] = sigma[e] * o->phi[r * G + e];
+    o->scratch[r] = pairwise_sum(gr, G);
+    o->scratch[r] *= o->vol[r];
+  }
+  free(gr);
+  double absorption = pairwise_sum(o->scratch, o->n_fsr);
+  double leak = 0.;
+  for (int64_t t = 0; t < o->n_trk; t++) leak += o->leakage[t];
+  o->k_eff = rate / (absorption + leak);
 }
+
+void moc_oracle_set_keff_from_neutron_balance(moc_oracle* o, int on) { o->balance = on; }
 
 /* src/CPUSolver.cpp:2113-2252 */
 double moc_oracle_compute_residual(moc_oracle* o, int res_type) {

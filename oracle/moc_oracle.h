@@ -79,6 +79,8 @@ void   moc_oracle_set_fixed_source(moc_oracle* o, int64_t fsr, int group0, doubl
 void   moc_oracle_stabilize_transport(moc_oracle* o, double factor, int type);
 void   moc_oracle_compute_fission_rates(moc_oracle* o, double* out, int nu);
 void   moc_oracle_set_num_threads(moc_oracle* o, int n);
+/* Solver::setKeffFromNeutronBalance (src/Solver.cpp:2047): k = fission/(absorption+leakage) */
+void   moc_oracle_set_keff_from_neutron_balance(moc_oracle* o, int on);
 /* seconds spent inside transport_sweep since creation / last reset */
 double moc_oracle_sweep_seconds(moc_oracle* o, int reset);
 

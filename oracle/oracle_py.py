@@ -69,6 +69,8 @@ def lib():
         L.moc_oracle_compute_fission_rates.argtypes = [vp, vp, i32]
         L.moc_oracle_set_num_threads.restype = None
         L.moc_oracle_set_num_threads.argtypes = [vp, i32]
+        L.moc_oracle_set_keff_from_neutron_balance.restype = None
+        L.moc_oracle_set_keff_from_neutron_balance.argtypes = [vp, i32]
         L.moc_oracle_sweep_seconds.restype = dbl
         L.moc_oracle_sweep_seconds.argtypes = [vp, i32]
         L.moc_oracle_expF1.restype = dbl
@@ -172,6 +174,7 @@ class OracleSolver:
         out = np.empty(self.ft.n_fsrs); lib().moc_oracle_compute_fission_rates(self.h, _p(out), int(nu)); return out
 
     def setNumThreads(self, n): lib().moc_oracle_set_num_threads(self.h, int(n))
+    def setKeffFromNeutronBalance(self): lib().moc_oracle_set_keff_from_neutron_balance(self.h, 1)
     def sweepSeconds(self, reset=False): return lib().moc_oracle_sweep_seconds(self.h, int(reset))
 
 

@@ -185,6 +185,24 @@ def test_step_loop_equals_fused_loop():
     assert rel_err(step.getFluxes(), gpu.getFluxes()) < 1e-10
 
 
+# ------------------------------------------------------- k_eff from neutron balance
+@pytest.mark.parametrize("name", ["c5g7_2d_coarse", "lattice3d_7g"])
+def test_keff_from_neutron_balance(name):
+    # reference run of the unmodified CPUSolver with setKeffFromNeutronBalance (c5g7 coarse, 40 it):
+    # k = 1.0327748189958241 (oracle/_ref/ref_driver --balance)
+    gpu, cpu, ft, _ = make(name)
+    gpu.setKeffFromNeutronBalance(); cpu.setKeffFromNeutronBalance()
+    gpu.setConvergenceThreshold(1e-5)
+    gpu.computeEigenvalue(40, FISSION_SOURCE)
+    cpu.computeEigenvalue(40, 1e-5, FISSION_SOURCE)
+    assert gpu.getNumIterations() == cpu.getNumIterations()
+    assert abs(gpu.getKeff() - cpu.getKeff()) * 1e5 < 1e-2      # float leakage tally, atomic order
+    assert rel_err(gpu.getFluxes(), cpu.getFluxes()) < 1e-6
+    if name == "c5g7_2d_coarse":
+        assert abs(cpu.getKeff() - 1.0327748189958241) < 1e-12
+        assert abs(gpu.getKeff() - 1.0327748189958241) * 1e5 < 1e-2
+
+
 # ------------------------------------------------------- deterministic tally
 def test_deterministic_mode_is_bitwise_reproducible_and_accurate():
     from openmoc_b200.solver import B200Solver
