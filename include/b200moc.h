@@ -53,6 +53,8 @@ typedef struct b200_config {
   int32_t precision;       /* B200_PRECISION_* */
   int32_t deterministic;   /* 1: order-independent 64-bit fixed-point FSR tally: bitwise reproducible runs */
   int64_t n_fsrs_global;   /* normalisation count when FSRs are sharded; 0 => n_fsrs */
+  int32_t linear_source;   /* 1: CPULSSolver physics (flux moments, linear source); needs b200_upload_linear_source */
+  int32_t reserved;
 } b200_config;
 
 const char* b200_last_error(void);
@@ -83,6 +85,18 @@ int b200_upload_materials(b200_solver* s, const double* sigma_t, const double* s
                           const double* fiss_matrix, const double* nu_sigma_f,
                           const double* sigma_f, const double* chi,
                           const uint8_t* fissionable);
+/* Linear source only (cfg.linear_source = 1), before b200_finalize.  Replaces the data the
+ * reference keeps in struct segment::_starting_position (src/Track.h:50, relative to the FSR
+ * centroid), the per-track direction of TransportSweep::onTrack
+ * (src/TrackTraversingAlgorithms.cpp:913-925) and the two tables LinearExpansionGenerator
+ * fills (src/CPULSSolver.h:36-40, src/TrackTraversingAlgorithms.cpp:470-831):
+ *   seg_start[n_segments][3], trk_direction[n_tracks][3],
+ *   lin_exp_matrix[n_fsrs][nc], source_constants[n_fsrs][nc][G]   (nc = 3 in 2D, 6 in 3D) */
+int b200_upload_linear_source(b200_solver* s, const double* seg_start, const double* trk_direction,
+                              const double* lin_exp_matrix, const double* source_constants);
+/* flux moments in the reference layout [r*3G + c*G + e] (src/CPULSSolver.h:22) */
+int b200_get_flux_moments(b200_solver* s, double* out, int64_t n);
+int b200_set_flux_moments(b200_solver* s, const double* in, int64_t n);
 /* builds device-side derived tables; call after the four uploads (re-callable) */
 int b200_finalize(b200_solver* s);
 

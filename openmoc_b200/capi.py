@@ -27,7 +27,8 @@ class Config(C.Structure):
     _fields_ = [("num_groups", C.c_int32), ("num_azim", C.c_int32), ("num_polar", C.c_int32),
                 ("solve_3d", C.c_int32), ("n_tracks", C.c_int64), ("n_segments", C.c_int64),
                 ("n_fsrs", C.c_int64), ("n_materials", C.c_int32), ("device", C.c_int32),
-                ("precision", C.c_int32), ("deterministic", C.c_int32), ("n_fsrs_global", C.c_int64)]
+                ("precision", C.c_int32), ("deterministic", C.c_int32), ("n_fsrs_global", C.c_int64),
+                ("linear_source", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -40,6 +41,9 @@ SIGNATURES = {
     "b200_upload_quadrature": [_vp, _vp],
     "b200_upload_fsrs": [_vp, _vp],
     "b200_upload_materials": [_vp] * 7,
+    "b200_upload_linear_source": [_vp, _vp, _vp, _vp],
+    "b200_get_flux_moments": [_vp, _i64],
+    "b200_set_flux_moments": [_vp, _i64],
     "b200_finalize": [],
     "b200_zero_track_fluxes": [],
     "b200_flatten_fsr_fluxes": [_dbl],

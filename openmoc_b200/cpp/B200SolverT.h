@@ -1,0 +1,473 @@
+/**
+ * @file B200SolverT.h
+ * @brief Implementation of the B200 plug-in as a class template over its OpenMOC base:
+ *        B200Solver   = B200SolverT<Solver>        flat source   (see B200Solver.h)
+ *        B200LSSolver = B200SolverT<CPULSSolver>+  linear source (see B200LSSolver.h)
+ *        Everything is a thin forwarder into the C ABI of include/b200moc.h.
+ */
+#ifndef B200SOLVERT_H_
+#define B200SOLVERT_H_
+
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "Solver.h"
+#include "TrackGenerator3D.h"
+#include "Cmfd.h"
+#include "b200_flatten.h"
+#include "../../include/b200moc.h"
+
+template <class Base>
+class B200SolverT : public Base {
+
+protected:
+  /* members of Solver used below (dependent names) */
+  using Base::_track_generator; using Base::_geometry; using Base::_num_groups; using Base::_num_FSRs;
+  using Base::_scalar_flux; using Base::_old_scalar_flux; using Base::_reduced_sources;
+  using Base::_user_fluxes; using Base::_fixed_sources_on; using Base::_fixed_sources_initialized;
+  using Base::_fix_src_FSR_map; using Base::_fix_src_cell_map; using Base::_fix_src_material_map;
+  using Base::_k_eff; using Base::_keff_from_fission_rates; using Base::_stabilize_transport;
+  using Base::_stabilization_factor; using Base::_stabilization_type; using Base::_negative_fluxes_allowed;
+  using Base::_chi_spectrum_material; using Base::_timer; using Base::_cmfd; using Base::_gpu_solver;
+  using Base::_converge_thresh; using Base::_num_iterations; using Base::_solver_mode;
+
+  b200_solver* _h;
+  B200FlatTracks _flat;
+  long _flattened_segments;
+  bool _materials_dirty, _fixed_dirty, _mirror_stale;
+  int _device, _precision;
+  double _device_keff;
+
+  void check(int status, const char* what);
+  void ensureDevice();
+  void pushMaterialsIfDirty();
+  void pushFixedSourcesIfDirty();
+  void pushKeff();
+
+  /* customisation points of the linear-source subclass */
+  virtual bool isLinearSource() { return false; }
+  virtual void uploadExtras() {}
+  virtual void syncExtraMirrors() {}
+  virtual void allocateHostFluxMirrors() {
+    long size = _num_FSRs * _num_groups;
+    if (_scalar_flux != NULL && !_user_fluxes) delete [] _scalar_flux;
+    if (_old_scalar_flux != NULL) delete [] _old_scalar_flux;
+    _scalar_flux = new FP_PRECISION[size]();
+    _old_scalar_flux = new FP_PRECISION[size]();
+    _user_fluxes = false;
+  }
+  virtual void allocateHostSourceMirrors() {
+    long size = _num_FSRs * _num_groups;
+    if (_reduced_sources != NULL) delete [] _reduced_sources;
+    _reduced_sources = new FP_PRECISION[size]();
+  }
+
+  /* Solver pure virtuals, src/Solver.h:334-431 */
+  void initializeFluxArrays();
+  void initializeSourceArrays();
+  void zeroTrackFluxes();
+  void flattenFSRFluxes(FP_PRECISION value);
+  void flattenFSRFluxesChiSpectrum();
+  void storeFSRFluxes();
+  double normalizeFluxes();
+  void computeStabilizingFlux();
+  void stabilizeFlux();
+  void computeFSRSources(int iteration);
+  void computeFSRFissionSources();
+  void computeFSRScatterSources();
+  double computeResidual(residualType res_type);
+  void computeKeff();
+  void addSourceToScalarFlux();
+  void transportSweep();
+
+  /* hooks (virtual in the base) */
+  void initializeExpEvaluators();
+  void initializeMaterials(solverMode mode);
+  void initializeCmfd();
+
+public:
+  B200SolverT(TrackGenerator* track_generator = NULL, int device = 0, int precision = 0);
+  virtual ~B200SolverT();
+
+  void getFluxes(FP_PRECISION* out_fluxes, int num_fluxes);
+  void setFluxes(FP_PRECISION* in_fluxes, int num_fluxes);
+  double getFlux(long fsr_id, int group);
+  double getFSRSource(long fsr_id, int group);
+  void setFixedSourceByFSR(long fsr_id, int group, double source);
+  void resetFixedSources();
+  void initializeFixedSources();
+  void computeFSRFissionRates(double* fission_rates, long num_FSRs, bool nu = false);
+
+  /** Copy phi, old phi and q from the device into the base-class host arrays. */
+  void syncHostMirrors();
+  /** Fused device-side source iteration (b200_compute_eigenvalue): same results as
+   *  computeEigenvalue() without a host round trip per step. */
+  void computeEigenvalueFused(int max_iters = 1000, residualType res_type = FISSION_SOURCE);
+  /** Accumulated device time of the sweep kernel (ms) and number of sweeps. */
+  void getSweepStats(double* ms, long* sweeps);
+};
+
+/* ------------------------------------------------------------------------------------ */
+template <class Base>
+B200SolverT<Base>::B200SolverT(TrackGenerator* track_generator, int device, int precision)
+    : Base(track_generator) {
+  _h = NULL;
+  _flattened_segments = -1;
+  _materials_dirty = false;
+  _fixed_dirty = false;
+  _mirror_stale = false;
+  _device = device;
+  _precision = precision;
+  _device_keff = -1.;
+  _gpu_solver = true;   /* switches the wording of the timer report, Solver.cpp:1908-1929 */
+}
+
+template <class Base>
+B200SolverT<Base>::~B200SolverT() {
+  if (_h != NULL) b200_destroy(_h);
+}
+
+/* CUDA / library errors follow the reference's convention: log_printf(ERROR) throws
+ * std::logic_error, which SWIG turns into a Python RuntimeError (src/log.cpp:535-599). */
+template <class Base>
+void B200SolverT<Base>::check(int status, const char* what) {
+  if (status != 0)
+    log_printf(ERROR, "B200Solver::%s failed: %s", what, b200_last_error());
+}
+
+/* (Re)flatten the tracks and upload everything; runs from initializeExpEvaluators(),
+ * i.e. after FSR centroids are final and over-long segments have been split
+ * (Solver.cpp:716-741) - the one point every compute* entry passes. */
+template <class Base>
+void B200SolverT<Base>::ensureDevice() {
+  long n_seg = _track_generator->getNumSegments();
+  if (_h != NULL && n_seg == _flattened_segments) return;
+  if (_h != NULL) { b200_destroy(_h); _h = NULL; }
+
+  b200_flatten(_track_generator, &_flat, isLinearSource());
+  b200_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.num_groups = _flat.num_groups;
+  cfg.num_azim = _flat.num_azim;
+  cfg.num_polar = _flat.num_polar;
+  cfg.solve_3d = _flat.solve_3d;
+  cfg.n_tracks = _flat.n_tracks;
+  cfg.n_segments = _flat.n_segments;
+  cfg.n_fsrs = _flat.n_fsrs;
+  cfg.n_materials = _flat.n_materials;
+  cfg.device = _device;
+  cfg.precision = _precision;
+  cfg.linear_source = isLinearSource() ? 1 : 0;
+  check(b200_create(&cfg, &_h), "b200_create");
+  check(b200_upload_tracks(_h, _flat.seg_length.data(), _flat.seg_fsr.data(), _flat.trk_seg_offset.data(),
+                           _flat.trk_azim.data(), _flat.trk_polar.data(), _flat.trk_next_fwd.data(),
+                           _flat.trk_next_bwd.data(), _flat.trk_flags.data(), _flat.trk_bc_fwd.data(),
+                           _flat.trk_bc_bwd.data()), "b200_upload_tracks");
+  check(b200_upload_quadrature(_h, _flat.quad_weight.data(), _flat.quad_sin_theta.data()), "b200_upload_quadrature");
+  check(b200_upload_fsrs(_h, _flat.fsr_volume.data(), _flat.fsr_mat.data()), "b200_upload_fsrs");
+  check(b200_upload_materials(_h, _flat.mat_sigma_t.data(), _flat.mat_sigma_s.data(), _flat.mat_fiss_matrix.data(),
+                              _flat.mat_nu_sigma_f.data(), _flat.mat_sigma_f.data(), _flat.mat_chi.data(),
+                              _flat.mat_fissionable.data()), "b200_upload_materials");
+  uploadExtras();
+  check(b200_finalize(_h), "b200_finalize");
+  if (_stabilize_transport)
+    check(b200_stabilize_transport(_h, _stabilization_factor, (int)_stabilization_type), "b200_stabilize_transport");
+  check(b200_allow_negative_fluxes(_h, _negative_fluxes_allowed), "b200_allow_negative_fluxes");
+  /* the segment stream only lives on the device from here on */
+  std::vector<double>().swap(_flat.seg_length);
+  std::vector<int32_t>().swap(_flat.seg_fsr);
+  std::vector<int32_t>().swap(_flat.seg_mat);
+  std::vector<double>().swap(_flat.seg_start);
+  _flattened_segments = n_seg;
+  _materials_dirty = false;
+  _fixed_dirty = true;
+  _device_keff = -1.;
+}
+
+template <class Base>
+void B200SolverT<Base>::pushMaterialsIfDirty() {
+  if (!_materials_dirty || _h == NULL) return;
+  B200FlatTracks tmp;
+  /* cheap: re-read the material tables only */
+  Geometry* geometry = _track_generator->getGeometry();
+  std::map<int, Material*> mats = geometry->getAllMaterials();
+  int G = _num_groups, m = 0;
+  size_t n = mats.size();
+  tmp.mat_sigma_t.assign(n * G, 0.); tmp.mat_nu_sigma_f = tmp.mat_sigma_f = tmp.mat_chi = tmp.mat_sigma_t;
+  tmp.mat_sigma_s.assign(n * G * G, 0.); tmp.mat_fiss_matrix = tmp.mat_sigma_s;
+  tmp.mat_fissionable.assign(n, 0);
+  for (std::map<int, Material*>::iterator it = mats.begin(); it != mats.end(); ++it, ++m) {
+    Material* mat = it->second;
+    tmp.mat_fissionable[m] = mat->isFissionable();
+    for (int g = 0; g < G; g++) {
+      tmp.mat_sigma_t[m * G + g] = mat->getSigmaT()[g];
+      tmp.mat_nu_sigma_f[m * G + g] = mat->getNuSigmaF()[g];
+      tmp.mat_chi[m * G + g] = mat->getChi()[g];
+    }
+    for (int i = 0; i < G * G; i++) {
+      tmp.mat_sigma_s[(size_t)m * G * G + i] = mat->getSigmaS()[i];
+      tmp.mat_fiss_matrix[(size_t)m * G * G + i] = mat->getFissionMatrix()[i];
+    }
+  }
+  check(b200_upload_materials(_h, tmp.mat_sigma_t.data(), tmp.mat_sigma_s.data(), tmp.mat_fiss_matrix.data(),
+                              tmp.mat_nu_sigma_f.data(), NULL, tmp.mat_chi.data(), tmp.mat_fissionable.data()),
+        "b200_upload_materials");
+  /* on a finalized solver b200_upload_materials refreshes the derived tables itself */
+  _materials_dirty = false;
+}
+
+template <class Base>
+void B200SolverT<Base>::pushFixedSourcesIfDirty() {
+  if (!_fixed_dirty || _h == NULL) return;
+  check(b200_reset_fixed_sources(_h), "b200_reset_fixed_sources");
+  if (_fixed_sources_on) {
+    std::map< std::pair<int, int>, FP_PRECISION >::iterator it;
+    for (it = _fix_src_FSR_map.begin(); it != _fix_src_FSR_map.end(); ++it)
+      check(b200_set_fixed_source_by_fsr(_h, it->first.first, it->first.second, it->second),
+            "b200_set_fixed_source_by_fsr");
+  }
+  _fixed_dirty = false;
+}
+
+/* the base-class loops assign _k_eff directly (Solver.cpp:1372,1473,1566) */
+template <class Base>
+void B200SolverT<Base>::pushKeff() {
+  if (_k_eff != _device_keff) {
+    check(b200_set_keff(_h, _k_eff), "b200_set_keff");
+    _device_keff = _k_eff;
+  }
+}
+
+/* ------------------------------ hooks ------------------------------------ */
+template <class Base>
+void B200SolverT<Base>::initializeExpEvaluators() {
+  Base::initializeExpEvaluators();
+  ensureDevice();
+  check(b200_set_keff_from_neutron_balance(_h, !_keff_from_fission_rates), "b200_set_keff_from_neutron_balance");
+}
+
+template <class Base>
+void B200SolverT<Base>::initializeMaterials(solverMode mode) {
+  Base::initializeMaterials(mode);
+  /* adjoint mode transposes the production matrices in place (Solver.cpp:806-807) */
+  if (_h != NULL) _materials_dirty = true;
+}
+
+template <class Base>
+void B200SolverT<Base>::initializeCmfd() {
+  Cmfd* cmfd = _geometry->getCmfd();
+  if (cmfd != NULL && cmfd->isFluxUpdateOn())
+    log_printf(ERROR, "CMFD acceleration is not supported by the B200Solver in this build");
+  _cmfd = NULL;
+}
+
+/* host mirrors only; device arrays are (re)zeroed, which is what a fresh
+ * CPUSolver::initializeFluxArrays (CPUSolver.cpp:281-370) gives */
+template <class Base>
+void B200SolverT<Base>::initializeFluxArrays() {
+  allocateHostFluxMirrors();
+  pushMaterialsIfDirty();
+  check(b200_zero_track_fluxes(_h), "b200_zero_track_fluxes");
+  check(b200_flatten_fsr_fluxes(_h, 0.), "b200_flatten_fsr_fluxes");
+  check(b200_store_fsr_fluxes(_h), "b200_store_fsr_fluxes");
+}
+
+template <class Base>
+void B200SolverT<Base>::initializeSourceArrays() {
+  allocateHostSourceMirrors();
+  if (_fixed_sources_on && !_fixed_sources_initialized) initializeFixedSources();
+}
+
+template <class Base>
+void B200SolverT<Base>::initializeFixedSources() {
+  Base::initializeFixedSources();     /* cell / material maps -> FSR map */
+  _fixed_sources_initialized = true;
+  _fixed_dirty = true;
+}
+
+/* ------------------------- Solver pure virtuals -------------------------- */
+template <class Base>
+void B200SolverT<Base>::zeroTrackFluxes() { check(b200_zero_track_fluxes(_h), "zeroTrackFluxes"); }
+
+template <class Base>
+void B200SolverT<Base>::flattenFSRFluxes(FP_PRECISION value) {
+  check(b200_flatten_fsr_fluxes(_h, value), "flattenFSRFluxes");
+  _mirror_stale = true;
+}
+
+template <class Base>
+void B200SolverT<Base>::flattenFSRFluxesChiSpectrum() {
+  if (_chi_spectrum_material == NULL)
+    log_printf(ERROR, "A flattening of the FSR fluxes for a chi spectrum was "
+               "requested but no chi spectrum material was set.");
+  std::map<int, Material*> mats = _geometry->getAllMaterials();
+  int m = 0;
+  for (std::map<int, Material*>::iterator it = mats.begin(); it != mats.end(); ++it, ++m)
+    if (it->second == _chi_spectrum_material) break;
+  check(b200_flatten_fsr_fluxes_chi_spectrum(_h, m), "flattenFSRFluxesChiSpectrum");
+  _mirror_stale = true;
+}
+
+template <class Base>
+void B200SolverT<Base>::storeFSRFluxes() {
+  check(b200_store_fsr_fluxes(_h), "storeFSRFluxes");
+}
+
+template <class Base>
+double B200SolverT<Base>::normalizeFluxes() {
+  double norm = 0.;
+  check(b200_normalize_fluxes(_h, &norm), "normalizeFluxes");
+  _mirror_stale = true;
+  return norm;
+}
+
+template <class Base>
+void B200SolverT<Base>::computeStabilizingFlux() { check(b200_compute_stabilizing_flux(_h), "computeStabilizingFlux"); }
+template <class Base>
+void B200SolverT<Base>::stabilizeFlux() { check(b200_stabilize_flux(_h), "stabilizeFlux"); _mirror_stale = true; }
+
+template <class Base>
+void B200SolverT<Base>::computeFSRSources(int iteration) {
+  pushFixedSourcesIfDirty();
+  pushKeff();
+  check(b200_compute_fsr_sources(_h, iteration), "computeFSRSources");
+}
+template <class Base>
+void B200SolverT<Base>::computeFSRFissionSources() { check(b200_compute_fsr_fission_sources(_h), "computeFSRFissionSources"); }
+template <class Base>
+void B200SolverT<Base>::computeFSRScatterSources() { check(b200_compute_fsr_scatter_sources(_h), "computeFSRScatterSources"); }
+
+template <class Base>
+double B200SolverT<Base>::computeResidual(residualType res_type) {
+  double residual = 0.;
+  pushKeff();
+  check(b200_compute_residual(_h, (int)res_type, &residual), "computeResidual");
+  return residual;
+}
+
+template <class Base>
+void B200SolverT<Base>::computeKeff() {
+  pushKeff();
+  check(b200_compute_keff(_h, &_k_eff), "computeKeff");
+  _device_keff = _k_eff;
+}
+
+template <class Base>
+void B200SolverT<Base>::addSourceToScalarFlux() {
+  check(b200_add_source_to_scalar_flux(_h), "addSourceToScalarFlux");
+  _mirror_stale = true;
+}
+
+/* The "Transport Sweep" timer split keeps meaning what the reference's report expects
+ * (Solver.cpp:1901-1929): wall time of the sweep, the stream is drained before stopping. */
+template <class Base>
+void B200SolverT<Base>::transportSweep() {
+  _timer->startTimer();
+  check(b200_transport_sweep(_h), "transportSweep");
+  check(b200_synchronize(_h), "transportSweep");
+  _timer->stopTimer();
+  _timer->recordSplit("Transport Sweep");
+  _mirror_stale = true;
+}
+
+/* ------------------------------ public API ------------------------------- */
+template <class Base>
+void B200SolverT<Base>::syncHostMirrors() {
+  if (_h == NULL || _scalar_flux == NULL) return;
+  long n = _num_FSRs * _num_groups;
+  check(b200_get_fluxes(_h, _scalar_flux, n), "syncHostMirrors");
+  if (_reduced_sources != NULL) check(b200_get_fsr_sources(_h, _reduced_sources, n), "syncHostMirrors");
+  syncExtraMirrors();
+  _mirror_stale = false;
+}
+
+template <class Base>
+void B200SolverT<Base>::getFluxes(FP_PRECISION* out_fluxes, int num_fluxes) {
+  if (num_fluxes != _num_groups * _num_FSRs)
+    log_printf(ERROR, "Unable to get FSR scalar fluxes since there are "
+               "%d groups and %d FSRs which does not match the requested "
+               "%d flux values", _num_groups, _num_FSRs, num_fluxes);
+  if (_h == NULL)
+    log_printf(ERROR, "Unable to get FSR scalar fluxes since they have not yet been allocated");
+  check(b200_get_fluxes(_h, out_fluxes, num_fluxes), "getFluxes");
+}
+
+/* CPUSolver aliases the caller's buffer (CPUSolver.cpp:190); like GPUSolver::setFluxes
+ * (GPUSolver.cu:1088) the values are copied to the device instead. */
+template <class Base>
+void B200SolverT<Base>::setFluxes(FP_PRECISION* in_fluxes, int num_fluxes) {
+  if (num_fluxes != _num_groups * _num_FSRs)
+    log_printf(ERROR, "Unable to set an array with %d flux values for %d "
+               " groups and %d FSRs", num_fluxes, _num_groups, _num_FSRs);
+  if (_h == NULL)
+    log_printf(ERROR, "Unable to set FSR scalar fluxes before the solver is initialized "
+               "(call initializeSolver first)");
+  check(b200_set_fluxes(_h, in_fluxes, num_fluxes), "setFluxes");
+  _mirror_stale = true;
+}
+
+template <class Base>
+double B200SolverT<Base>::getFlux(long fsr_id, int group) {
+  if (_mirror_stale) syncHostMirrors();
+  return Base::getFlux(fsr_id, group);
+}
+
+template <class Base>
+double B200SolverT<Base>::getFSRSource(long fsr_id, int group) {
+  syncHostMirrors();
+  return Base::getFSRSource(fsr_id, group);
+}
+
+template <class Base>
+void B200SolverT<Base>::setFixedSourceByFSR(long fsr_id, int group, double source) {
+  Base::setFixedSourceByFSR(fsr_id, group, source);
+  _fixed_dirty = true;
+}
+
+template <class Base>
+void B200SolverT<Base>::resetFixedSources() {
+  _fix_src_FSR_map.clear();
+  _fix_src_cell_map.clear();
+  _fix_src_material_map.clear();
+  _fixed_dirty = true;
+}
+
+template <class Base>
+void B200SolverT<Base>::computeFSRFissionRates(double* fission_rates, long num_FSRs, bool nu) {
+  if (_h == NULL)
+    log_printf(ERROR, "Unable to compute FSR fission rates since the "
+               "source distribution has not been calculated");
+  check(b200_compute_fsr_fission_rates(_h, fission_rates, num_FSRs, nu), "computeFSRFissionRates");
+}
+
+template <class Base>
+void B200SolverT<Base>::computeEigenvalueFused(int max_iters, residualType res_type) {
+  this->clearTimerSplits();
+  _timer->startTimer();
+  initializeMaterials(_solver_mode);
+  this->initializeFSRs();
+  this->countFissionableFSRs();
+  initializeExpEvaluators();
+  initializeFluxArrays();
+  initializeSourceArrays();
+  initializeCmfd();
+  pushFixedSourcesIfDirty();
+  int iters = 0;
+  check(b200_compute_eigenvalue(_h, max_iters, _converge_thresh, (int)res_type, &iters), "computeEigenvalueFused");
+  _num_iterations = iters;
+  check(b200_get_keff(_h, &_k_eff), "computeEigenvalueFused");
+  _device_keff = _k_eff;
+  syncHostMirrors();
+  _timer->stopTimer();
+  _timer->recordSplit("Total time");
+}
+
+template <class Base>
+void B200SolverT<Base>::getSweepStats(double* ms, long* sweeps) {
+  int64_t n = 0, launches = 0;
+  check(b200_get_sweep_stats(_h, ms, &n, &launches), "getSweepStats");
+  if (sweeps) *sweeps = n;
+}
+
+#endif /* B200SOLVERT_H_ */

@@ -22,6 +22,7 @@
 
 #include "fsr_kernels.cuh"
 #include "sweep.cuh"
+#include "sweep_ls.cuh"
 
 using namespace b200;
 
@@ -130,6 +131,11 @@ struct b200_solver {
   /* device: state */
   DevBuf<double> phi, phi_old, fixed, stab, scratch;
   DevBuf<unsigned long long> phi_fx, fx_bits;   /* deterministic mode */
+  /* linear source */
+  bool linear = false, have_ls = false;
+  int nc = 3;
+  DevBuf<double> ls_seg_start, ls_trk_dir, ls_lin_exp, ls_src_const, phi_m;
+  DevBuf<double4> seg_pos, qxyz;
   DevBuf<double2> qst;
   DevBuf<float> psi_a, psi_b;
   float* psi_start = nullptr;  /* what the next sweep reads (= reference _start_flux) */
@@ -182,6 +188,17 @@ static FsrArgs fsr_args(b200_solver* s) {
   a.iscal = s->iscal.p;
   a.partials = s->partials.p;
   return a;
+}
+
+static LsArgs ls_args(b200_solver* s) {
+  LsArgs l;
+  l.nc = s->nc;
+  l.solve_3d = s->cfg.solve_3d;
+  l.lin_exp = s->ls_lin_exp.p;
+  l.src_const = s->ls_src_const.p;
+  l.phi_m = s->phi_m.p;
+  l.qxyz = s->qxyz.p;
+  return l;
 }
 
 static inline int grid_for(int64_t n, int threads, int cap = 148 * 8) {
@@ -239,6 +256,12 @@ extern "C" int b200_create(const b200_config* cfg, b200_solver** out) {
     return fail("b200_create: unknown precision %d", cfg->precision);
   if (cfg->deterministic && cfg->precision != B200_PRECISION_DOUBLE)
     return fail("b200_create: the deterministic tally needs B200_PRECISION_DOUBLE");
+  if (cfg->linear_source && (cfg->deterministic || cfg->precision != B200_PRECISION_DOUBLE))
+    return fail("b200_create: the linear-source solver supports B200_PRECISION_DOUBLE with the atomic tally only");
+  if (cfg->linear_source && !cfg->solve_3d && cfg->num_polar / 2 > 3)
+    return fail("b200_create: linear source supports at most 3 polar angles per 2D track in this build");
+  if (cfg->linear_source && cfg->num_groups > 96)
+    return fail("b200_create: linear source supports at most 96 energy groups in this build");
   if (!cfg->solve_3d && cfg->num_polar / 2 > 6)
     return fail("b200_create: %d polar angles per 2D track not supported (max 6)", cfg->num_polar / 2);
   if (cfg->num_groups > 256) return fail("b200_create: %d energy groups not supported (max 256)", cfg->num_groups);
@@ -254,6 +277,8 @@ extern "C" int b200_create(const b200_config* cfg, b200_solver** out) {
   s->n_fsr = cfg->n_fsrs;
   s->n_fsr_global = cfg->n_fsrs_global > 0 ? cfg->n_fsrs_global : cfg->n_fsrs;
   s->n_mat = cfg->n_materials;
+  s->linear = cfg->linear_source != 0;
+  s->nc = cfg->solve_3d ? 6 : 3;
   e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete s; return fail("cudaStreamCreate: %s", cudaGetErrorString(e)); }
   s->own_stream = true;
@@ -283,6 +308,8 @@ extern "C" int b200_destroy(b200_solver* s) {
   s->sigma_s.release(); s->fiss.release(); s->nu_sigma_f.release(); s->sigma_f.release();
   s->chi.release(); s->max_ratio.release(); s->sigma_a.release(); s->part3.release(); s->leakage.release(); s->fissionable.release(); s->phi.release();
   s->phi_fx.release(); s->fx_bits.release();
+  s->ls_seg_start.release(); s->ls_trk_dir.release(); s->ls_lin_exp.release(); s->ls_src_const.release();
+  s->phi_m.release(); s->seg_pos.release(); s->qxyz.release();
   s->phi_old.release(); s->fixed.release(); s->stab.release(); s->scratch.release();
   s->qst.release(); s->psi_a.release(); s->psi_b.release(); s->scal.release();
   s->partials.release(); s->hist_k.release(); s->hist_res.release(); s->iscal.release();
@@ -415,6 +442,22 @@ extern "C" int b200_upload_materials(b200_solver* s, const double* sigma_t, cons
   return 0;
 }
 
+extern "C" int b200_upload_linear_source(b200_solver* s, const double* seg_start, const double* trk_direction,
+                                         const double* lin_exp_matrix, const double* source_constants) {
+  NEED(s);
+  if (!s->linear) return fail("b200_upload_linear_source: the solver was not created with linear_source = 1");
+  if (!trk_direction || !lin_exp_matrix || !source_constants || (s->n_seg > 0 && !seg_start))
+    return fail("b200_upload_linear_source: null array");
+  CU(s->ls_seg_start.upload(seg_start, (size_t)s->n_seg * 3, s->stream));
+  CU(s->ls_trk_dir.upload(trk_direction, (size_t)s->n_trk * 3, s->stream));
+  CU(s->ls_lin_exp.upload(lin_exp_matrix, (size_t)s->n_fsr * s->nc, s->stream));
+  CU(s->ls_src_const.upload(source_constants, (size_t)s->n_fsr * s->nc * s->G, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->have_ls = true;
+  s->finalized = false;
+  return 0;
+}
+
 /* Groups per thread (GPL) and threads per item (LPI = ceil(G/GPL) <= 32).  With the
  * flat thread->item mapping every LPI fills the warps, so prefer the smallest GPL
  * (fewest registers, most resident warps) whose slots are >= 95 % used. */
@@ -530,7 +573,24 @@ extern "C" int b200_finalize(b200_solver* s) {
       s->seg_rec.p, s->seg_len.p, s->seg_fsr.p, s->n_seg, s->G);
   CU(cudaGetLastError());
 
+  if (s->linear) {
+    if (!s->have_ls) return fail("b200_finalize: linear source requested but b200_upload_linear_source was not called");
+    CU(s->seg_pos.alloc((size_t)s->n_seg + 2 * SEG_PAD));
+    build_segpos_kernel<<<grid_for(s->n_seg + 2 * SEG_PAD, 256), 256, 0, s->stream>>>(
+        s->seg_pos.p, s->ls_seg_start.p, s->n_seg);
+    CU(cudaGetLastError());
+    CU(s->phi_m.alloc(nphi * 3));
+    CU(s->qxyz.alloc(nphi));
+    CU(cudaMemsetAsync(s->phi_m.p, 0, nphi * 3 * 8, s->stream));
+    CU(cudaMemsetAsync(s->qxyz.p, 0, nphi * 32, s->stream));
+  }
+
   choose_lane_map(s->G, &s->gpl, &s->lpi, &s->ipc);
+  if (s->linear) {          /* the LS kernel is instantiated for 1 or 3 groups per thread */
+    s->gpl = s->G <= 32 ? 1 : 3;
+    s->lpi = (s->G + s->gpl - 1) / s->gpl;
+    s->ipc = std::min(32, 224 / s->lpi);
+  }
   const int64_t n_items = 2 * nt;
   s->sweep_blocks = (n_items + s->ipc - 1) / s->ipc;
   s->variant = 0;
@@ -661,6 +721,11 @@ static int launch_sweep(b200_solver* s) {
   zero_phi_kernel<<<grid_for(nphi, 256), 256, 0, s->stream>>>(s->phi.p, (int64_t)nphi, s->iscal.p);
   CU(cudaGetLastError());
   s->n_launches++;
+  if (s->linear) {
+    zero_phi_kernel<<<grid_for(nphi * 3, 256), 256, 0, s->stream>>>(s->phi_m.p, (int64_t)nphi * 3, s->iscal.p);
+    CU(cudaGetLastError());
+    s->n_launches++;
+  }
   if (s->cfg.deterministic) {
     FsrArgs fa = fsr_args(s);
     const int64_t npsi = s->n_trk * 2 * (int64_t)s->F;
@@ -693,6 +758,37 @@ static int launch_sweep(b200_solver* s) {
     }
     const bool mixed = s->cfg.precision == B200_PRECISION_MIXED;
     const int nthr = s->lpi * s->ipc;
+    if (s->linear) {
+      if (s->balance) return fail("k_eff from the neutron balance is not available with the linear source in this build");
+      SweepLSArgs la;
+      la.f = a;
+      la.seg_pos = s->seg_pos.p + SEG_PAD;
+      la.trk_dir = s->ls_trk_dir.p;
+      la.qxyz = s->qxyz.p;
+      la.phi_m = s->phi_m.p;
+      /* expG_fractional coefficients p0..p5, d1..d6 (src/exponentials.h:113-127) */
+      const double cg[12] = {0.5, 1.76558112351595e-1, 4.041584305811143e-2, 6.178333902037397e-3,
+                             6.429894635552992e-4, 6.064409107557148e-5, 6.864462055546078e-1,
+                             2.263358514260129e-1, 4.721469893686252e-2, 6.883236664917246e-3,
+                             7.036272419147752e-4, 6.064409107557148e-5};
+      for (int k = 0; k < 12; k++) la.cg[k] = cg[k];
+      void (*lfn)(const SweepLSArgs) = nullptr;
+      const int key = (s->cfg.solve_3d ? 100 : 0) + s->NP * 10 + s->gpl;
+      switch (key) {
+        case 111: lfn = sweep_ls_kernel<1, 1, true>; break;
+        case 113: lfn = sweep_ls_kernel<1, 3, true>; break;
+        case 11: lfn = sweep_ls_kernel<1, 1, false>; break;
+        case 13: lfn = sweep_ls_kernel<1, 3, false>; break;
+        case 21: lfn = sweep_ls_kernel<2, 1, false>; break;
+        case 23: lfn = sweep_ls_kernel<2, 3, false>; break;
+        case 31: lfn = sweep_ls_kernel<3, 1, false>; break;
+        case 33: lfn = sweep_ls_kernel<3, 3, false>; break;
+      }
+      if (lfn == nullptr) return fail("no linear-source sweep kernel for NP=%d GPL=%d 3D=%d", s->NP, s->gpl, s->cfg.solve_3d);
+      lfn<<<(unsigned)s->sweep_blocks, nthr, 0, s->stream>>>(la);
+      CU(cudaGetLastError());
+      s->n_launches++;
+    } else {
     sweep_fn fn;
     size_t smem = 0;
     if (s->variant == 2) {
@@ -712,6 +808,7 @@ static int launch_sweep(b200_solver* s) {
     fn<<<(unsigned)s->sweep_blocks, nthr, smem, s->stream>>>(a);
     CU(cudaGetLastError());
     s->n_launches++;
+    }
   }
   if (s->cfg.deterministic && !s->defer_fx_convert) {
     fx_to_double_kernel<<<grid_for(nphi, 256), 256, 0, s->stream>>>(fsr_args(s), s->phi_fx.p);
@@ -764,6 +861,7 @@ extern "C" int b200_flatten_fsr_fluxes(b200_solver* s, double value) {
   fill_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->phi.p, value, n);
   CU(cudaGetLastError());
   s->n_launches++;
+  if (s->linear) CU(cudaMemsetAsync(s->phi_m.p, 0, (size_t)n * 3 * 8, s->stream));   /* CPULSSolver.cpp:342-354 */
   return 0;
 }
 
@@ -794,8 +892,17 @@ static int launch_rate(b200_solver* s, int op) {
   return 0;
 }
 
+static int launch_scale_moments(b200_solver* s) {
+  if (!s->linear) return 0;
+  scale_moments_kernel<<<grid_for(s->n_fsr * s->G * 3, 256), 256, 0, s->stream>>>(fsr_args(s), s->phi_m.p);
+  CU(cudaGetLastError());
+  s->n_launches++;
+  return 0;
+}
+
 static int launch_scale(b200_solver* s) {
   FsrArgs a = fsr_args(s);
+  if (launch_scale_moments(s)) return 1;
   scale_phi_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(a);
   CU(cudaGetLastError());
   const int64_t npsi = s->n_trk * 2 * (int64_t)s->F;
@@ -827,6 +934,12 @@ static int launch_sources(b200_solver* s, int iteration, int mode) {
   sources_kernel<<<grid_for(n, 256, 1 << 30), 256, 0, s->stream>>>(a, iteration, mode, s->neg_allowed ? 1 : 0);
   CU(cudaGetLastError());
   s->n_launches++;
+  if (s->linear && mode == 0) {
+    if (s->fixed_on && false) return fail("fixed linear source moments are not supported");
+    sources_ls_kernel<<<grid_for(n, 256, 1 << 30), 256, 0, s->stream>>>(a, ls_args(s), iteration, s->neg_allowed ? 1 : 0);
+    CU(cudaGetLastError());
+    s->n_launches++;
+  }
   return 0;
 }
 
@@ -855,7 +968,8 @@ extern "C" int b200_transport_sweep(b200_solver* s) {
 static int launch_closure(b200_solver* s, int with_rate, int* n_partials) {
   FsrArgs a = fsr_args(s);
   const int nb = grid_for(s->n_fsr * s->G, RED_THREADS, MAX_PARTIALS);
-  closure_kernel<<<nb, RED_THREADS, 0, s->stream>>>(a, s->neg_allowed ? 1 : 0, with_rate);
+  if (s->linear) closure_ls_kernel<<<nb, RED_THREADS, 0, s->stream>>>(a, ls_args(s), s->neg_allowed ? 1 : 0, with_rate);
+  else closure_kernel<<<nb, RED_THREADS, 0, s->stream>>>(a, s->neg_allowed ? 1 : 0, with_rate);
   CU(cudaGetLastError());
   s->n_launches++;
   if (n_partials) *n_partials = nb;
@@ -991,6 +1105,7 @@ extern "C" int b200_compute_fsr_fission_rates(b200_solver* s, double* out, int64
 }
 extern "C" int b200_stabilize_transport(b200_solver* s, double factor, int32_t type) {
   NEED(s);
+  if (s->linear) return fail("transport stabilisation of the flux moments is not supported with the linear source in this build");
   if (type < 0 || type > 2) return fail("b200_stabilize_transport: unknown stabilization type %d", type);
   s->stabilize = true;
   s->stab_factor = factor;
@@ -1032,6 +1147,33 @@ extern "C" int b200_set_fsr_sources(b200_solver* s, const double* in, int64_t n)
   CU(cudaStreamSynchronize(s->stream));
   return 0;
 }
+extern "C" int b200_get_flux_moments(b200_solver* s, double* out, int64_t n) {
+  NEED_FINAL(s);
+  if (!s->linear) return fail("b200_get_flux_moments: not a linear-source solver");
+  if (n != s->n_fsr * s->G * 3) return fail("b200_get_flux_moments: size mismatch");
+  double* tmp = nullptr;
+  CU(cudaMalloc((void**)&tmp, n * 8));
+  moments_to_ref_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->phi_m.p, tmp, s->n_fsr, s->G);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, tmp, n * 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  cudaFree(tmp);
+  return 0;
+}
+extern "C" int b200_set_flux_moments(b200_solver* s, const double* in, int64_t n) {
+  NEED_FINAL(s);
+  if (!s->linear) return fail("b200_set_flux_moments: not a linear-source solver");
+  if (n != s->n_fsr * s->G * 3) return fail("b200_set_flux_moments: size mismatch");
+  double* tmp = nullptr;
+  CU(cudaMalloc((void**)&tmp, n * 8));
+  CU(cudaMemcpyAsync(tmp, in, n * 8, cudaMemcpyHostToDevice, s->stream));
+  moments_from_ref_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->phi_m.p, tmp, s->n_fsr, s->G);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  cudaFree(tmp);
+  return 0;
+}
+
 extern "C" int b200_get_start_fluxes(b200_solver* s, float* out, int64_t n) {
   NEED_FINAL(s);
   if (n != s->n_trk * 2 * (int64_t)s->F) return fail("b200_get_start_fluxes: size mismatch");
@@ -1079,6 +1221,7 @@ static int enqueue_iteration_end(b200_solver* s, int i, int res_type, int loop_k
     if (launch_rate(s, 2)) return 1;
   }
   /* normalizeFluxes' scaling of phi fused into the residual pass, storeFSRFluxes after */
+  if (launch_scale_moments(s)) return 1;
   const int64_t npsi = s->n_trk * 2 * (int64_t)s->F;
   if (npsi) {
     scale_psi_kernel<<<grid_for(npsi, 256), 256, 0, s->stream>>>(s->psi_start, npsi, s->scal.p, s->iscal.p);

@@ -490,3 +490,138 @@ __global__ void insert_q_kernel(double2* __restrict__ qst, const double* __restr
 }
 
 }  // namespace b200
+
+/* ===================================================================================== */
+/* Linear source (CPULSSolver): moment sources, closure and scaling                      */
+/* ===================================================================================== */
+namespace b200 {
+
+struct LsArgs {
+  int nc;                                   /* 3 in 2D, 6 in 3D */
+  int solve_3d;
+  const double* __restrict__ lin_exp;       /* [n_fsr][nc]  _FSR_lin_exp_matrix (CPULSSolver.h) */
+  const double* __restrict__ src_const;     /* [n_fsr][nc][G]  _FSR_source_constants */
+  double* __restrict__ phi_m;               /* [(r*G+e)*3 + c] flux moments */
+  double4* __restrict__ qxyz;               /* {q_x, q_y, q_z, 0} per (r, e) */
+};
+
+/* CPULSSolver::computeFSRSources, moment part (src/CPULSSolver.cpp:386-524): per (FSR, group)
+ * scatter + fission/k of the three flux moments, then the 2x2 / 3x3 linear expansion matrix. */
+__global__ void __launch_bounds__(256)
+sources_ls_kernel(const FsrArgs a, const LsArgs l, int iteration, int neg_allowed) {
+  if (a.iscal[SI_DONE]) return;
+  const int G = a.G;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.n_fsr * G) return;
+  const int64_t r = idx / G;
+  const int g = (int)(idx - r * G);
+  const int m = a.fsr_mat[r];
+  const double* __restrict__ ss = a.sigma_s + ((int64_t)m * G + g) * G;
+  const double* __restrict__ fm = a.fiss + ((int64_t)m * G + g) * G;
+  const bool fissionable = a.fissionable[m];
+  double sx = 0., sy = 0., sz = 0., fx = 0., fy = 0., fz = 0.;
+  for (int gp = 0; gp < G; gp++) {
+    const double* __restrict__ pm = l.phi_m + (r * G + gp) * 3;
+    const double mx = pm[0], my = pm[1], mz = pm[2];
+    sx = fma(ss[gp], mx, sx); sy = fma(ss[gp], my, sy); sz = fma(ss[gp], mz, sz);
+    if (fissionable) { fx = fma(fm[gp], mx, fx); fy = fma(fm[gp], my, fy); fz = fma(fm[gp], mz, fz); }
+  }
+  const double k = a.scal[SC_KEFF];
+  const double src_x = sx + fx / k, src_y = sy + fy / k, src_z = sz + fz / k;
+  double4 q = make_double4(0., 0., 0., 0.);
+  const double* __restrict__ M = l.lin_exp + r * l.nc;
+  const double c = ONE_OVER_FOUR_PI / 2;
+  if (neg_allowed || a.qst[idx].x > 10 * FLUX_EPSILON || iteration > 29) {
+    if (l.solve_3d) {
+      q.x = c * (M[0] * src_x + M[2] * src_y + M[3] * src_z);
+      q.y = c * (M[2] * src_x + M[1] * src_y + M[4] * src_z);
+      q.z = c * (M[3] * src_x + M[4] * src_y + M[5] * src_z);
+    } else {
+      q.x = c * (M[0] * src_x + M[2] * src_y);
+      q.y = c * (M[2] * src_x + M[1] * src_y);
+    }
+  }
+  l.qxyz[idx] = q;
+}
+
+/* CPULSSolver::addSourceToScalarFlux (src/CPULSSolver.cpp:787-882) + nu-fission partial sums */
+__global__ void __launch_bounds__(RED_THREADS)
+closure_ls_kernel(const FsrArgs a, const LsArgs l, int neg_allowed, int with_rate) {
+  if (a.iscal[SI_DONE]) return;
+  const int G = a.G;
+  const int64_t n = a.n_fsr * G;
+  double local = 0.;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / G;
+    const int e = (int)(idx - r * G);
+    double volume = a.vol[r];
+    if (volume < VOL_EPSILON) volume = 1e30;
+    const double2 qs = a.qst[idx];
+    const double4 qm = l.qxyz[idx];
+    const double* __restrict__ sc = l.src_const + r * G * l.nc;
+    const double flux_const = FOUR_PI * 2;
+    double f = a.phi[idx];
+    f /= volume;
+    f += FOUR_PI * qs.x;
+    f /= qs.y;
+    double* __restrict__ pm = l.phi_m + idx * 3;
+    double mx = pm[0] / volume, my = pm[1] / volume, mz = pm[2] / volume;
+    mx += flux_const * qm.x * sc[e];
+    mx += flux_const * qm.y * sc[2 * G + e];
+    my += flux_const * qm.x * sc[2 * G + e];
+    my += flux_const * qm.y * sc[G + e];
+    if (l.solve_3d) {
+      mx += flux_const * qm.z * sc[3 * G + e];
+      my += flux_const * qm.z * sc[4 * G + e];
+      mz += flux_const * qm.x * sc[3 * G + e];
+      mz += flux_const * qm.y * sc[4 * G + e];
+      mz += flux_const * qm.z * sc[5 * G + e];
+    }
+    mx /= qs.y; my /= qs.y;
+    if (l.solve_3d) mz /= qs.y;
+    if (f < 0.0 && !neg_allowed) {
+      atomicAdd(&a.iscal[SI_NEG_FLUX], 1);
+      f = fmax(a.phi_old[idx], FLUX_EPSILON);
+      mx = my = mz = 0.;
+    }
+    a.phi[idx] = f;
+    pm[0] = mx; pm[1] = my; pm[2] = mz;
+    local += a.nu_sigma_f[(int64_t)a.fsr_mat[r] * G + e] * f * a.vol[r];
+  }
+  if (with_rate) {
+    const double s = block_sum(local);
+    if (threadIdx.x == 0) a.partials[blockIdx.x] = s;
+  }
+}
+
+/* CPULSSolver::normalizeFluxes, moment part (src/CPULSSolver.cpp:360-372) */
+__global__ void scale_moments_kernel(const FsrArgs a, double* __restrict__ phi_m) {
+  if (a.iscal[SI_DONE]) return;
+  const double norm = a.scal[SC_NORM];
+  const int64_t n = a.n_fsr * a.G * 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    phi_m[i] *= norm;
+}
+
+/* device [(r*G+e)*3 + c]  <->  reference layout [r*3G + c*G + e] (src/CPULSSolver.h:22-23) */
+__global__ void moments_to_ref_kernel(const double* __restrict__ dev, double* __restrict__ ref, int64_t n_fsr, int G) {
+  const int64_t n = n_fsr * G * 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (3 * G);
+    const int rem = (int)(i - r * 3 * G);
+    const int c = rem / G, e = rem - c * G;
+    ref[i] = dev[(r * G + e) * 3 + c];
+  }
+}
+__global__ void moments_from_ref_kernel(double* __restrict__ dev, const double* __restrict__ ref, int64_t n_fsr, int G) {
+  const int64_t n = n_fsr * G * 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (3 * G);
+    const int rem = (int)(i - r * 3 * G);
+    const int c = rem / G, e = rem - c * G;
+    dev[(r * G + e) * 3 + c] = ref[i];
+  }
+}
+
+}  // namespace b200

@@ -9,7 +9,7 @@
  * Usage: ref_driver --model NAME [--dims 2|3] [--azim N] [--spacing S]
  *                   [--polar N] [--zspacing S] [--formation explicit|otf-tracks|otf-stacks]
  *                   [--quad ty|equal-angle|gl|equal-weight|leonard] [--groups70]
- *                   [--solver cpu|cpuls|b200|b200-fused|both] [--mode eigen|none] [--tol T]
+ *                   [--solver cpu|cpuls|b200|b200-fused|b200ls|both] [--ls (with both: linear source)] [--mode eigen|none] [--tol T]
  *        --solver both: CPUSolver and B200Solver in the same process on the same tracks,
  *        prints delta k_eff (pcm), max relative flux error and both sweep times.
  *                   [--max-iters N] [--threads N] [--res fission|flux|total]
@@ -28,6 +28,7 @@
 #include "models.h"
 #include "../../openmoc_b200/cpp/b200_flatten.h"
 #include "../../openmoc_b200/cpp/B200Solver.h"
+#include "../../openmoc_b200/cpp/B200LSSolver.h"
 
 static const char* arg(int argc, char** argv, const char* key, const char* dflt) {
   for (int i = 1; i < argc - 1; i++)
@@ -105,7 +106,9 @@ int main(int argc, char** argv) {
   if (solver_name == "both") {
     long n_fsr = geometry->getNumFSRs();
     int G = geometry->getNumEnergyGroups();
-    CPUSolver cpu(tg);
+    const bool ls = flag(argc, argv, "--ls");
+    CPUSolver* cpu_p = ls ? new CPULSSolver(tg) : new CPUSolver(tg);
+    CPUSolver& cpu = *cpu_p;
     cpu.setNumThreads(threads);
     cpu.setConvergenceThreshold(tol);
     if (flag(argc, argv, "--balance")) cpu.setKeffFromNeutronBalance();
@@ -117,7 +120,9 @@ int main(int argc, char** argv) {
     double k_cpu = cpu.getKeff();
     int it_cpu = cpu.getNumIterations();
 
-    B200Solver gpu(tg);
+    B200Solver* gpu_flat = ls ? NULL : new B200Solver(tg);
+    B200LSSolver* gpu_ls = ls ? new B200LSSolver(tg) : NULL;
+    Solver& gpu = ls ? *(Solver*)gpu_ls : *(Solver*)gpu_flat;
     gpu.setConvergenceThreshold(tol);
     if (flag(argc, argv, "--balance")) gpu.setKeffFromNeutronBalance();
     gpu.computeEigenvalue(max_iters, rt);
@@ -129,7 +134,7 @@ int main(int argc, char** argv) {
       if (d > err) err = d;
     }
     double dev_ms = 0.; long sweeps = 0;
-    gpu.getSweepStats(&dev_ms, &sweeps);
+    if (ls) gpu_ls->getSweepStats(&dev_ms, &sweeps); else gpu_flat->getSweepStats(&dev_ms, &sweeps);
     long n_seg = tg->getNumSegments();
     int F = (dims == 3) ? G : G * tg->getQuadrature()->getNumPolarAngles() / 2;
     printf("{\"model\": \"%s\", \"n_segments\": %ld, \"n_fsrs\": %ld, \"cpu_threads\": %d, "
@@ -146,6 +151,7 @@ int main(int argc, char** argv) {
   CPUSolver* cpu_solver = NULL;
   B200Solver* b200_solver = NULL;
   if (solver_name == "b200" || solver_name == "b200-fused") solver = b200_solver = new B200Solver(tg);
+  else if (solver_name == "b200ls") solver = new B200LSSolver(tg);
   else if (solver_name == "cpuls") solver = cpu_solver = new CPULSSolver(tg);
   else solver = cpu_solver = new CPUSolver(tg);
   if (cpu_solver != NULL) cpu_solver->setNumThreads(threads);
