@@ -50,3 +50,35 @@ def test_fused_loop_through_the_plugin(tmp_path):
                     "--quiet", "--json", js, "--results", os.path.join(tmp_path, "res.dat")], check=True)
     golden = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_goldens.json")))["test_forward_pin_cell"]
     assert open(os.path.join(tmp_path, "res.dat")).read() == golden
+
+
+# ---------------------------------------------------------------- linear source (CPULSSolver)
+@pytest.mark.parametrize("args,iters", [
+    (["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.6",
+      "--zspacing", "2.8", "--groups70", "--tol", "5e-3"], 186),          # test_forward_3D_lattice_linear_70g
+    (["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12"], None),               # 2D, 3 polar, rings+sectors
+    (["--model", "pin-cell", "--azim", "8", "--spacing", "0.05"], None),
+    (["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
+      "--zspacing", "0.9"], None),                                                            # test_forward_3D_lattice_linear shape
+    (["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
+      "--zspacing", "0.9", "--formation", "otf-stacks"], None),
+])
+def test_b200lssolver_matches_cpulssolver_in_process(args, iters):
+    """B200LSSolver next to the unmodified CPULSSolver on the same TrackGenerator."""
+    r = run(args + ["--solver", "both", "--ls"])
+    assert r["dk_pcm"] < 1.0 and r["max_rel_flux_err"] < 1e-4          # north_star
+    assert r["dk_pcm"] < 1e-3 and r["max_rel_flux_err"] < 1e-7         # achieved
+    assert r["b200_iters"] == r["cpu_iters"]
+    if iters is not None:
+        assert r["cpu_iters"] == iters
+
+
+def test_linear_source_reference_golden_from_gpu(tmp_path):
+    # tests/test_forward_3D_lattice_linear_70g/results_true.dat: 186 iterations, keff 8.71566E-01
+    if not os.path.exists(DRIVER):
+        pytest.skip("ref_driver not built")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([DRIVER, "--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2",
+                    "--spacing", "0.6", "--zspacing", "2.8", "--groups70", "--tol", "5e-3", "--solver", "b200ls",
+                    "--quiet", "--no-fluxes", "--results", res], check=True, capture_output=True)
+    assert open(res).read() == "# Iterations: 186\nkeff:  8.71566E-01\n"
