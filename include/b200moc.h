@@ -94,6 +94,14 @@ int b200_upload_materials(b200_solver* s, const double* sigma_t, const double* s
  *   lin_exp_matrix[n_fsrs][nc], source_constants[n_fsrs][nc][G]   (nc = 3 in 2D, 6 in 3D) */
 int b200_upload_linear_source(b200_solver* s, const double* seg_start, const double* trk_direction,
                               const double* lin_exp_matrix, const double* source_constants);
+/* CMFD surface-current tally inside the sweep (Cmfd::tallyCurrent, src/Cmfd.h:572-670; the
+ * reference calls it per segment from TransportSweep::onTrack).  seg_cmfd_fwd/bwd are
+ * segment::_cmfd_surface_fwd/_bwd (src/Track.h:42-46: cell*26 + surface, or -1).  The tally
+ * lands in a dense array [(cell*26 + surface)*ncg + g] the host hands to Cmfd. */
+int b200_upload_cmfd_surfaces(b200_solver* s, const int32_t* seg_cmfd_fwd, const int32_t* seg_cmfd_bwd);
+int b200_set_cmfd_groups(b200_solver* s, const int32_t* moc_to_cmfd_group, int32_t num_cmfd_groups,
+                         int64_t num_cmfd_cells);   /* num_cmfd_groups <= 0 switches the tally off */
+int b200_get_cmfd_currents(b200_solver* s, double* out, int64_t n);
 /* flux moments in the reference layout [r*3G + c*G + e] (src/CPULSSolver.h:22) */
 int b200_get_flux_moments(b200_solver* s, double* out, int64_t n);
 int b200_set_flux_moments(b200_solver* s, const double* in, int64_t n);

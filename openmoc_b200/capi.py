@@ -42,6 +42,9 @@ SIGNATURES = {
     "b200_upload_fsrs": [_vp, _vp],
     "b200_upload_materials": [_vp] * 7,
     "b200_upload_linear_source": [_vp, _vp, _vp, _vp],
+    "b200_upload_cmfd_surfaces": [_vp, _vp],
+    "b200_set_cmfd_groups": [_vp, _i32, _i64],
+    "b200_get_cmfd_currents": [_vp, _i64],
     "b200_get_flux_moments": [_vp, _i64],
     "b200_set_flux_moments": [_vp, _i64],
     "b200_finalize": [],

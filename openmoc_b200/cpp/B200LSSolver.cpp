@@ -39,6 +39,12 @@ void B200LSSolver::syncExtraMirrors() {
     check(b200_get_flux_moments(_h, _scalar_flux_xyz, (long)_num_FSRs * _num_groups * 3), "syncHostMirrors");
 }
 
+/* Cmfd::updateMOCFlux rescales the moments too (src/Cmfd.cpp:1552-1559, setFluxMoments) */
+void B200LSSolver::pushExtraHostFlux() {
+  if (_scalar_flux_xyz != NULL)
+    check(b200_set_flux_moments(_h, _scalar_flux_xyz, (long)_num_FSRs * _num_groups * 3), "pushHostFluxIfNewer");
+}
+
 void B200LSSolver::getFluxMoments(FP_PRECISION* out, long n) {
   check(b200_get_flux_moments(_h, out, n), "getFluxMoments");
 }

@@ -18,6 +18,7 @@ protected:
   bool isLinearSource() { return true; }
   void uploadExtras();
   void syncExtraMirrors();
+  void pushExtraHostFlux();
   void allocateHostFluxMirrors();
   void allocateHostSourceMirrors();
 public:

@@ -30,12 +30,14 @@ protected:
   using Base::_k_eff; using Base::_keff_from_fission_rates; using Base::_stabilize_transport;
   using Base::_stabilization_factor; using Base::_stabilization_type; using Base::_negative_fluxes_allowed;
   using Base::_chi_spectrum_material; using Base::_timer; using Base::_cmfd; using Base::_gpu_solver;
-  using Base::_converge_thresh; using Base::_num_iterations; using Base::_solver_mode;
+  using Base::_converge_thresh; using Base::_SOLVE_3D; using Base::_num_iterations; using Base::_solver_mode;
 
   b200_solver* _h;
   B200FlatTracks _flat;
   long _flattened_segments;
   bool _materials_dirty, _fixed_dirty, _mirror_stale;
+  bool _cmfd_active, _host_flux_newer;
+  std::vector<double> _cmfd_currents;
   int _device, _precision;
   double _device_keff;
 
@@ -44,11 +46,14 @@ protected:
   void pushMaterialsIfDirty();
   void pushFixedSourcesIfDirty();
   void pushKeff();
+  void handCurrentsToCmfd();
+  void pushHostFluxIfNewer();
 
   /* customisation points of the linear-source subclass */
   virtual bool isLinearSource() { return false; }
   virtual void uploadExtras() {}
   virtual void syncExtraMirrors() {}
+  virtual void pushExtraHostFlux() {}
   virtual void allocateHostFluxMirrors() {
     long size = _num_FSRs * _num_groups;
     if (_scalar_flux != NULL && !_user_fluxes) delete [] _scalar_flux;
@@ -117,6 +122,8 @@ B200SolverT<Base>::B200SolverT(TrackGenerator* track_generator, int device, int 
   _materials_dirty = false;
   _fixed_dirty = false;
   _mirror_stale = false;
+  _cmfd_active = false;
+  _host_flux_newer = false;
   _device = device;
   _precision = precision;
   _device_keff = -1.;
@@ -170,6 +177,12 @@ void B200SolverT<Base>::ensureDevice() {
                               _flat.mat_nu_sigma_f.data(), _flat.mat_sigma_f.data(), _flat.mat_chi.data(),
                               _flat.mat_fissionable.data()), "b200_upload_materials");
   uploadExtras();
+  {
+    Cmfd* cmfd = _geometry->getCmfd();
+    if (cmfd != NULL && cmfd->isFluxUpdateOn())
+      check(b200_upload_cmfd_surfaces(_h, _flat.seg_cmfd_fwd.data(), _flat.seg_cmfd_bwd.data()),
+            "b200_upload_cmfd_surfaces");
+  }
   check(b200_finalize(_h), "b200_finalize");
   if (_stabilize_transport)
     check(b200_stabilize_transport(_h, _stabilization_factor, (int)_stabilization_type), "b200_stabilize_transport");
@@ -179,6 +192,8 @@ void B200SolverT<Base>::ensureDevice() {
   std::vector<int32_t>().swap(_flat.seg_fsr);
   std::vector<int32_t>().swap(_flat.seg_mat);
   std::vector<double>().swap(_flat.seg_start);
+  std::vector<int32_t>().swap(_flat.seg_cmfd_fwd);
+  std::vector<int32_t>().swap(_flat.seg_cmfd_bwd);
   _flattened_segments = n_seg;
   _materials_dirty = false;
   _fixed_dirty = true;
@@ -256,10 +271,84 @@ void B200SolverT<Base>::initializeMaterials(solverMode mode) {
 
 template <class Base>
 void B200SolverT<Base>::initializeCmfd() {
-  Cmfd* cmfd = _geometry->getCmfd();
-  if (cmfd != NULL && cmfd->isFluxUpdateOn())
-    log_printf(ERROR, "CMFD acceleration is not supported by the B200Solver in this build");
-  _cmfd = NULL;
+  /* Solver::initializeCmfd (src/Solver.cpp:1145-1181) hands Cmfd the HOST arrays (_scalar_flux,
+   * _reduced_sources, volumes, materials): the CMFD solve stays the reference's host code,
+   * fed every iteration with the device's fluxes and surface currents (addSourceToScalarFlux)
+   * and read back before the next device step (pushHostFluxIfNewer). */
+  Base::initializeCmfd();
+  _cmfd_active = (_cmfd != NULL && _cmfd->isFluxUpdateOn());
+  if (!_cmfd_active) {
+    check(b200_set_cmfd_groups(_h, NULL, 0, 0), "b200_set_cmfd_groups");
+    return;
+  }
+  if (_cmfd->isSigmaTRebalanceOn())
+    log_printf(ERROR, "CMFD sigma-t rebalance (tallyStartingCurrents) is not supported by the B200 solvers");
+  std::vector<int32_t> map(_num_groups);
+  for (int e = 0; e < _num_groups; e++) map[e] = _cmfd->getCmfdGroup(e);
+  check(b200_set_cmfd_groups(_h, map.data(), _cmfd->getNumCmfdGroups(), _cmfd->getNumCells()),
+        "b200_set_cmfd_groups");
+  _cmfd_currents.assign((size_t)_cmfd->getNumCells() * NUM_SURFACES * _cmfd->getNumCmfdGroups(), 0.);
+}
+
+/* Device tallies -> Cmfd.  Faces go straight into the public current Vector
+ * (Cmfd::getLocalCurrents, src/Cmfd.h:442, layout [cell][surface*ncg + g]); edge and corner
+ * currents live in a private map (Cmfd.h:233) and are replayed through the public
+ * Cmfd::tallyCurrent with a synthetic one-surface segment whose float "track flux" carries the
+ * value as a hi + lo pair (so that the double is not rounded to float). */
+template <class Base>
+void B200SolverT<Base>::handCurrentsToCmfd() {
+  const int ncg = _cmfd->getNumCmfdGroups();
+  const long n_cells = _cmfd->getNumCells();
+  check(b200_get_cmfd_currents(_h, _cmfd_currents.data(), (long)_cmfd_currents.size()), "b200_get_cmfd_currents");
+  Vector* faces = _cmfd->getLocalCurrents();
+  /* first MOC group of every CMFD group, for the replay */
+  std::vector<int> first_moc(ncg, -1);
+  for (int e = _num_groups - 1; e >= 0; e--) first_moc[_cmfd->getCmfdGroup(e)] = e;
+  Quadrature* quad = _track_generator->getQuadrature();
+  const bool solve3d = _SOLVE_3D;
+  const int np = solve3d ? 1 : quad->getNumPolarAngles() / 2;
+  std::vector<float> flux((size_t)np * _num_groups + _num_groups, 0.f);
+  const double w0 = quad->getWeightInline(0, 0);
+  const double w1 = (!solve3d && np > 1) ? quad->getWeightInline(0, 1) : w0;
+  for (long cell = 0; cell < n_cells; cell++) {
+    for (int surf = 0; surf < NUM_SURFACES; surf++) {
+      const double* v = &_cmfd_currents[((size_t)cell * NUM_SURFACES + surf) * ncg];
+      if (surf < NUM_FACES) {
+        for (int g = 0; g < ncg; g++)
+          if (v[g] != 0.) faces->incrementValue(cell, surf * ncg + g, v[g]);
+        continue;
+      }
+      bool any = false;
+      for (int g = 0; g < ncg; g++) any |= (v[g] != 0.);
+      if (!any) continue;
+      segment seg;
+      seg._cmfd_surface_fwd = cell * NUM_SURFACES + surf;
+      /* 2D: hi part in polar 0, lo part in polar 1 of the same call; 3D: two calls */
+      std::fill(flux.begin(), flux.end(), 0.f);
+      std::vector<float> lo(flux.size(), 0.f);
+      bool need_lo = false;
+      for (int g = 0; g < ncg; g++) {
+        const int e = first_moc[g];
+        const float hi = (float)(v[g] / w0);
+        flux[e] = hi;
+        const double rest = v[g] - (double)hi * w0;
+        if (!solve3d && np > 1) flux[_num_groups + e] = (float)(rest / w1);
+        else { lo[e] = (float)(rest / w0); need_lo |= (lo[e] != 0.f); }
+      }
+      _cmfd->tallyCurrent(&seg, flux.data(), 0, 0, true);
+      if (need_lo) _cmfd->tallyCurrent(&seg, lo.data(), 0, 0, true);
+    }
+  }
+}
+
+/* Cmfd::computeKeff rescales the host fluxes (updateMOCFlux, src/Cmfd.cpp:1509-1560); the next
+ * device step must see them. */
+template <class Base>
+void B200SolverT<Base>::pushHostFluxIfNewer() {
+  if (!_host_flux_newer) return;
+  check(b200_set_fluxes(_h, _scalar_flux, (long)_num_FSRs * _num_groups), "pushHostFluxIfNewer");
+  pushExtraHostFlux();
+  _host_flux_newer = false;
 }
 
 /* host mirrors only; device arrays are (re)zeroed, which is what a fresh
@@ -311,12 +400,14 @@ void B200SolverT<Base>::flattenFSRFluxesChiSpectrum() {
 
 template <class Base>
 void B200SolverT<Base>::storeFSRFluxes() {
+  pushHostFluxIfNewer();
   check(b200_store_fsr_fluxes(_h), "storeFSRFluxes");
 }
 
 template <class Base>
 double B200SolverT<Base>::normalizeFluxes() {
   double norm = 0.;
+  pushHostFluxIfNewer();
   check(b200_normalize_fluxes(_h, &norm), "normalizeFluxes");
   _mirror_stale = true;
   return norm;
@@ -325,11 +416,12 @@ double B200SolverT<Base>::normalizeFluxes() {
 template <class Base>
 void B200SolverT<Base>::computeStabilizingFlux() { check(b200_compute_stabilizing_flux(_h), "computeStabilizingFlux"); }
 template <class Base>
-void B200SolverT<Base>::stabilizeFlux() { check(b200_stabilize_flux(_h), "stabilizeFlux"); _mirror_stale = true; }
+void B200SolverT<Base>::stabilizeFlux() { pushHostFluxIfNewer(); check(b200_stabilize_flux(_h), "stabilizeFlux"); _mirror_stale = true; }
 
 template <class Base>
 void B200SolverT<Base>::computeFSRSources(int iteration) {
   pushFixedSourcesIfDirty();
+  pushHostFluxIfNewer();
   pushKeff();
   check(b200_compute_fsr_sources(_h, iteration), "computeFSRSources");
 }
@@ -341,6 +433,7 @@ void B200SolverT<Base>::computeFSRScatterSources() { check(b200_compute_fsr_scat
 template <class Base>
 double B200SolverT<Base>::computeResidual(residualType res_type) {
   double residual = 0.;
+  pushHostFluxIfNewer();
   pushKeff();
   check(b200_compute_residual(_h, (int)res_type, &residual), "computeResidual");
   return residual;
@@ -357,12 +450,20 @@ template <class Base>
 void B200SolverT<Base>::addSourceToScalarFlux() {
   check(b200_add_source_to_scalar_flux(_h), "addSourceToScalarFlux");
   _mirror_stale = true;
+  if (_cmfd_active) {
+    /* the base-class loop calls _cmfd->computeKeff() right after this step (Solver.cpp:1628-1629) */
+    syncHostMirrors();
+    handCurrentsToCmfd();
+    _host_flux_newer = true;
+  }
 }
 
 /* The "Transport Sweep" timer split keeps meaning what the reference's report expects
  * (Solver.cpp:1901-1929): wall time of the sweep, the stream is drained before stopping. */
 template <class Base>
 void B200SolverT<Base>::transportSweep() {
+  pushHostFluxIfNewer();
+  if (_cmfd_active) _cmfd->zeroCurrents();       /* CPUSolver.cpp:2343-2344 */
   _timer->startTimer();
   check(b200_transport_sweep(_h), "transportSweep");
   check(b200_synchronize(_h), "transportSweep");
@@ -390,6 +491,7 @@ void B200SolverT<Base>::getFluxes(FP_PRECISION* out_fluxes, int num_fluxes) {
                "%d flux values", _num_groups, _num_FSRs, num_fluxes);
   if (_h == NULL)
     log_printf(ERROR, "Unable to get FSR scalar fluxes since they have not yet been allocated");
+  pushHostFluxIfNewer();
   check(b200_get_fluxes(_h, out_fluxes, num_fluxes), "getFluxes");
 }
 

@@ -131,6 +131,13 @@ struct b200_solver {
   /* device: state */
   DevBuf<double> phi, phi_old, fixed, stab, scratch;
   DevBuf<unsigned long long> phi_fx, fx_bits;   /* deterministic mode */
+  /* CMFD current tally */
+  bool cmfd_on = false, have_cmfd_surf = false;
+  int ncg = 0;
+  int64_t n_cmfd_slots = 0;           /* n_cells * 26 */
+  DevBuf<int32_t> cmfd_fwd, cmfd_bwd, cmfd_group;
+  DevBuf<int2> seg_cmfd;
+  DevBuf<double> currents;
   /* linear source */
   bool linear = false, have_ls = false;
   int nc = 3;
@@ -310,6 +317,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   s->phi_fx.release(); s->fx_bits.release();
   s->ls_seg_start.release(); s->ls_trk_dir.release(); s->ls_lin_exp.release(); s->ls_src_const.release();
   s->phi_m.release(); s->seg_pos.release(); s->qxyz.release();
+  s->cmfd_fwd.release(); s->cmfd_bwd.release(); s->cmfd_group.release(); s->seg_cmfd.release(); s->currents.release();
   s->phi_old.release(); s->fixed.release(); s->stab.release(); s->scratch.release();
   s->qst.release(); s->psi_a.release(); s->psi_b.release(); s->scal.release();
   s->partials.release(); s->hist_k.release(); s->hist_res.release(); s->iscal.release();
@@ -458,6 +466,49 @@ extern "C" int b200_upload_linear_source(b200_solver* s, const double* seg_start
   return 0;
 }
 
+extern "C" int b200_upload_cmfd_surfaces(b200_solver* s, const int32_t* seg_cmfd_fwd, const int32_t* seg_cmfd_bwd) {
+  NEED(s);
+  if (s->n_seg > 0 && (!seg_cmfd_fwd || !seg_cmfd_bwd)) return fail("b200_upload_cmfd_surfaces: null array");
+  CU(s->cmfd_fwd.upload(seg_cmfd_fwd, s->n_seg, s->stream));
+  CU(s->cmfd_bwd.upload(seg_cmfd_bwd, s->n_seg, s->stream));
+  CU(s->seg_cmfd.alloc((size_t)s->n_seg + 2 * SEG_PAD));
+  build_segcmfd_kernel<<<grid_for(s->n_seg + 2 * SEG_PAD, 256), 256, 0, s->stream>>>(
+      s->seg_cmfd.p, s->cmfd_fwd.p, s->cmfd_bwd.p, s->n_seg);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  s->cmfd_fwd.release(); s->cmfd_bwd.release();
+  s->have_cmfd_surf = true;
+  return 0;
+}
+
+extern "C" int b200_set_cmfd_groups(b200_solver* s, const int32_t* moc_to_cmfd_group, int32_t num_cmfd_groups,
+                                    int64_t num_cmfd_cells) {
+  NEED(s);
+  if (num_cmfd_groups <= 0) { s->cmfd_on = false; return 0; }      /* switches the tally off */
+  if (!s->have_cmfd_surf) return fail("b200_set_cmfd_groups: b200_upload_cmfd_surfaces has not been called");
+  if (!moc_to_cmfd_group || num_cmfd_cells <= 0) return fail("b200_set_cmfd_groups: bad argument");
+  for (int e = 0; e < s->G; e++)
+    if (moc_to_cmfd_group[e] < 0 || moc_to_cmfd_group[e] >= num_cmfd_groups)
+      return fail("b200_set_cmfd_groups: MOC group %d maps to CMFD group %d outside [0,%d)", e, moc_to_cmfd_group[e], num_cmfd_groups);
+  s->ncg = num_cmfd_groups;
+  s->n_cmfd_slots = num_cmfd_cells * 26;     /* NUM_SURFACES, src/constants.h:119 */
+  CU(s->cmfd_group.upload(moc_to_cmfd_group, s->G, s->stream));
+  CU(s->currents.alloc((size_t)s->n_cmfd_slots * s->ncg));
+  CU(cudaMemsetAsync(s->currents.p, 0, (size_t)s->n_cmfd_slots * s->ncg * 8, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->cmfd_on = true;
+  return 0;
+}
+
+extern "C" int b200_get_cmfd_currents(b200_solver* s, double* out, int64_t n) {
+  NEED(s);
+  if (!s->cmfd_on) return fail("b200_get_cmfd_currents: CMFD tallies are off");
+  if (n != s->n_cmfd_slots * s->ncg) return fail("b200_get_cmfd_currents: expected %lld values", (long long)(s->n_cmfd_slots * s->ncg));
+  CU(cudaMemcpyAsync(out, s->currents.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
 /* Groups per thread (GPL) and threads per item (LPI = ceil(G/GPL) <= 32).  With the
  * flat thread->item mapping every LPI fills the warps, so prefer the smallest GPL
  * (fewest registers, most resident warps) whose slots are >= 95 % used. */
@@ -593,12 +644,7 @@ extern "C" int b200_finalize(b200_solver* s) {
   }
   const int64_t n_items = 2 * nt;
   s->sweep_blocks = (n_items + s->ipc - 1) / s->ipc;
-  s->variant = 0;
-  if (const char* v = getenv("B200_SWEEP")) {
-    if (!strcmp(v, "regs")) s->variant = 0;
-    else if (!strcmp(v, "ring")) s->variant = 1;
-    else if (!strcmp(v, "staged")) s->variant = 2;
-  }
+
   s->smem_attr_set = false;
 
   if (refresh_material_tables(s)) return 1;
@@ -611,77 +657,27 @@ extern "C" int b200_finalize(b200_solver* s) {
 /* ------------------------------------------------------------------------- */
 typedef void (*sweep_fn)(const SweepArgs);
 
-template <typename T>
-static sweep_fn pick_ring(int np, int gpl) {
-  if (gpl == 1) {
-    switch (np) {
-      case 1: return sweep_kernel_ring<T, 1, 1>;
-      case 2: return sweep_kernel_ring<T, 2, 1>;
-      case 3: return sweep_kernel_ring<T, 3, 1>;
-      case 4: return sweep_kernel_ring<T, 4, 1>;
-      case 5: return sweep_kernel_ring<T, 5, 1>;
-      case 6: return sweep_kernel_ring<T, 6, 1>;
-    }
-  } else if (gpl == 2) {
-    switch (np) {
-      case 1: return sweep_kernel_ring<T, 1, 2>;
-      case 2: return sweep_kernel_ring<T, 2, 2>;
-      case 3: return sweep_kernel_ring<T, 3, 2>;
-      case 4: return sweep_kernel_ring<T, 4, 2>;
-      case 5: return sweep_kernel_ring<T, 5, 2>;
-      case 6: return sweep_kernel_ring<T, 6, 2>;
-    }
-  }
-  return nullptr;
-}
-
-constexpr int STAGE_DQ = 4;   /* gathers 4 segments ahead, records 8 ahead */
-template <typename T, int NP>
-static sweep_fn pick_gpl_staged(int gpl) {
-  switch (gpl) {
-    case 1: return sweep_kernel_staged<T, NP, 1, STAGE_DQ>;
-    case 2: return sweep_kernel_staged<T, NP, 2, STAGE_DQ>;
-    case 3: return sweep_kernel_staged<T, NP, 3, STAGE_DQ>;
-    case 4: return sweep_kernel_staged<T, NP, 4, STAGE_DQ>;
-    case 7: return sweep_kernel_staged<T, NP, 7, STAGE_DQ>;
-    case 8: return sweep_kernel_staged<T, NP, 8, STAGE_DQ>;
-  }
-  return nullptr;
-}
-template <typename T>
-static sweep_fn pick_np_staged(int np, int gpl) {
-  switch (np) {
-    case 1: return pick_gpl_staged<T, 1>(gpl);
-    case 2: return pick_gpl_staged<T, 2>(gpl);
-    case 3: return pick_gpl_staged<T, 3>(gpl);
-    case 4: return pick_gpl_staged<T, 4>(gpl);
-    case 5: return pick_gpl_staged<T, 5>(gpl);
-    case 6: return pick_gpl_staged<T, 6>(gpl);
-  }
-  return nullptr;
-}
-
-template <typename T, int NP, bool DET>
+template <typename T, int NP, bool DET, bool CMFD>
 static sweep_fn pick_gpl(int gpl) {
   switch (gpl) {
-    case 1: return sweep_kernel<T, NP, 1, DET>;
-    case 2: return sweep_kernel<T, NP, 2, DET>;
-    case 3: return sweep_kernel<T, NP, 3, DET>;
-    case 4: return sweep_kernel<T, NP, 4, DET>;
-    case 7: return sweep_kernel<T, NP, 7, DET>;
-    case 8: return sweep_kernel<T, NP, 8, DET>;
+    case 1: return sweep_kernel<T, NP, 1, DET, CMFD>;
+    case 2: return sweep_kernel<T, NP, 2, DET, CMFD>;
+    case 3: return sweep_kernel<T, NP, 3, DET, CMFD>;
+    case 4: return sweep_kernel<T, NP, 4, DET, CMFD>;
+    case 7: return sweep_kernel<T, NP, 7, DET, CMFD>;
+    case 8: return sweep_kernel<T, NP, 8, DET, CMFD>;
   }
   return nullptr;
 }
-template <typename T, bool DET>
+template <typename T, bool DET, bool CMFD>
 static sweep_fn pick_np(int np, int gpl) {
   switch (np) {
-    case 1: return pick_gpl<T, 1, DET>(gpl);
-    case 2: return pick_gpl<T, 2, DET>(gpl);
-    case 3: return pick_gpl<T, 3, DET>(gpl);
-    case 4: return pick_gpl<T, 4, DET>(gpl);
-    case 5: return pick_gpl<T, 5, DET>(gpl);
-    case 6: return pick_gpl<T, 6, DET>(gpl);
+    case 1: return pick_gpl<T, 1, DET, CMFD>(gpl);
+    case 2: return pick_gpl<T, 2, DET, CMFD>(gpl);
+    case 3: return pick_gpl<T, 3, DET, CMFD>(gpl);
+    case 4: return pick_gpl<T, 4, DET, CMFD>(gpl);
+    case 5: return pick_gpl<T, 5, DET, CMFD>(gpl);
+    case 6: return pick_gpl<T, 6, DET, CMFD>(gpl);
   }
   return nullptr;
 }
@@ -744,6 +740,14 @@ static int launch_sweep(b200_solver* s) {
     a.qst = s->qst.p; a.psi_in = s->psi_start; a.psi_out = s->psi_other; a.phi = s->phi.p;
     a.phi_fx = s->phi_fx.p; a.fx_scale = s->scal.p + SC_FXSCALE;
     a.leakage = s->balance ? s->leakage.p : nullptr;
+    a.seg_cmfd = nullptr; a.cmfd_group = nullptr; a.currents = nullptr; a.ncg = 0;
+    if (s->cmfd_on) {
+      a.seg_cmfd = s->seg_cmfd.p + SEG_PAD; a.cmfd_group = s->cmfd_group.p; a.currents = s->currents.p; a.ncg = s->ncg;
+      zero_phi_kernel<<<grid_for(s->n_cmfd_slots * s->ncg, 256), 256, 0, s->stream>>>(
+          s->currents.p, s->n_cmfd_slots * s->ncg, s->iscal.p);          /* Cmfd::zeroCurrents */
+      CU(cudaGetLastError());
+      s->n_launches++;
+    }
     if (s->balance) {
       zero_float_kernel<<<grid_for(s->n_trk, 256), 256, 0, s->stream>>>(s->leakage.p, s->n_trk, s->iscal.p);
       CU(cudaGetLastError());
@@ -790,22 +794,17 @@ static int launch_sweep(b200_solver* s) {
       s->n_launches++;
     } else {
     sweep_fn fn;
-    size_t smem = 0;
-    if (s->variant == 2) {
-      fn = mixed ? pick_np_staged<float>(s->NP, s->gpl) : pick_np_staged<double>(s->NP, s->gpl);
-      smem = (size_t)nthr * 16 * (2 * STAGE_DQ + STAGE_DQ * s->gpl);
-    } else if (s->variant == 1 && s->gpl <= 2) {
-      fn = mixed ? pick_ring<float>(s->NP, s->gpl) : pick_ring<double>(s->NP, s->gpl);
+    if (s->cmfd_on) {
+      if (mixed || s->cfg.deterministic)
+        return fail("CMFD current tallies need B200_PRECISION_DOUBLE with the atomic tally in this build");
+      fn = pick_np<double, false, true>(s->NP, s->gpl);
+    } else if (s->cfg.deterministic) {
+      fn = pick_np<double, true, false>(s->NP, s->gpl);
     } else {
-      if (s->cfg.deterministic) fn = pick_np<double, true>(s->NP, s->gpl);
-      else fn = mixed ? pick_np<float, false>(s->NP, s->gpl) : pick_np<double, false>(s->NP, s->gpl);
+      fn = mixed ? pick_np<float, false, false>(s->NP, s->gpl) : pick_np<double, false, false>(s->NP, s->gpl);
     }
     if (fn == nullptr) return fail("no sweep kernel for NP=%d GPL=%d", s->NP, s->gpl);
-    if (smem > 48 * 1024 && !s->smem_attr_set) {
-      CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      s->smem_attr_set = true;
-    }
-    fn<<<(unsigned)s->sweep_blocks, nthr, smem, s->stream>>>(a);
+    fn<<<(unsigned)s->sweep_blocks, nthr, 0, s->stream>>>(a);
     CU(cudaGetLastError());
     s->n_launches++;
     }

@@ -243,6 +243,11 @@ struct SweepArgs {
    * associative, so the result does not depend on the order the atomics land in) */
   unsigned long long* __restrict__ phi_fx; /* [n_fsr*G], used by the DET kernels */
   const double* __restrict__ fx_scale;     /* device scalar: power-of-two scale */
+  /* CMFD surface-current tally (Cmfd::tallyCurrent, src/Cmfd.h:572-670); NULL when CMFD is off */
+  const int2* __restrict__ seg_cmfd;       /* {surface crossed at the forward end, at the backward end} or -1, padded like seg */
+  const int32_t* __restrict__ cmfd_group;  /* MOC group -> CMFD group */
+  double* __restrict__ currents;           /* [(cell*26 + surface)*ncg + g] */
+  int ncg;
   float* __restrict__ leakage;             /* [n_trk] vacuum leakage tally, NULL unless k_eff from neutron balance */
   const int* __restrict__ done;            /* device convergence flag (may be NULL) */
   int64_t n_items;
@@ -258,8 +263,8 @@ struct SweepArgs {
 /* CTAs are at most 224 threads (7 warps: 32 items of 7 lanes for G = 7).  For the
  * small-G shapes four CTAs per SM (28 warps) are worth more than registers: the
  * bound caps the kernel at 72 registers. */
-template <typename T, int NP, int GPL, bool DET>
-__global__ void __launch_bounds__(224, (GPL == 1 && NP <= 3) ? 4 : 1)
+template <typename T, int NP, int GPL, bool DET, bool CMFD>
+__global__ void __launch_bounds__(224, (GPL == 1 && NP <= 3 && !CMFD) ? 4 : 1)
 sweep_kernel(const SweepArgs a) {
   if (a.done != nullptr && *a.done) return;
   /* flat mapping: LPI consecutive threads own one item; an item may straddle two
@@ -337,6 +342,12 @@ sweep_kernel(const SweepArgs a) {
 
   double* __restrict__ const phi = a.phi;
   const double fx_scale = DET ? *a.fx_scale : 0.0;
+  [[maybe_unused]] const int2* __restrict__ pc = CMFD ? a.seg_cmfd + (dir ? s1 - 1 : s0) : nullptr;
+  [[maybe_unused]] int cg[GPL];
+  if constexpr (CMFD) {
+#pragma unroll
+    for (int j = 0; j < GPL; j++) cg[j] = a.cmfd_group[e[j]];
+  }
   constexpr int kUnroll = B200_SWEEP_UNROLL;
 #pragma unroll kUnroll
   for (int i = 0; i < n; i++) {
@@ -430,6 +441,7 @@ sweep_kernel(const SweepArgs a) {
   }
 }
 
+#ifdef B200_EXPERIMENTAL_SWEEPS   /* measured and rejected variants: profiles/r01_sweep_ablation.md */
 /* ------------------------------------------------------------------------- */
 /* Ring variant (default for GPL <= 2): a 4-deep register ring of segment        */
 /* records and {q, sigma_t} pairs, the loop unrolled by 4 so that the ring never   */
@@ -740,6 +752,8 @@ sweep_kernel_staged(const SweepArgs a) {
   }
 }
 
+#endif  /* B200_EXPERIMENTAL_SWEEPS */
+
 /* builds the padded SegRec stream from the uploaded SoA arrays (once per upload) */
 __global__ void build_segrec_kernel(SegRec* __restrict__ out, const double* __restrict__ len,
                                     const int32_t* __restrict__ fsr, int64_t n_seg, int G) {
@@ -752,6 +766,17 @@ __global__ void build_segrec_kernel(SegRec* __restrict__ out, const double* __re
     else { r.len = 0.0; r.base = 0u; }
     r.spare = 0u;
     out[i] = r;
+  }
+}
+
+/* padded {fwd, bwd} CMFD surface stream */
+__global__ void build_segcmfd_kernel(int2* __restrict__ out, const int32_t* __restrict__ fwd,
+                                     const int32_t* __restrict__ bwd, int64_t n_seg) {
+  const int64_t total = n_seg + 2 * SEG_PAD;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i - SEG_PAD;
+    out[i] = (s >= 0 && s < n_seg) ? make_int2(fwd[s], bwd[s]) : make_int2(-1, -1);
   }
 }
 

@@ -164,6 +164,20 @@ sweep_ls_kernel(const SweepLSArgs la) {
       }
     }
 
+    if (a.seg_cmfd != nullptr) {      /* CMFD surface currents, src/Cmfd.h:572-670 */
+      const int2 c = a.seg_cmfd[s];
+      const int surf = dir ? c.y : c.x;
+      if (surf >= 0) {
+#pragma unroll
+        for (int j = 0; j < GPL; j++) {
+          double cur = 0.0;
+#pragma unroll
+          for (int p = 0; p < NP; p++) cur = fma(w[p], (double)psi[p][j], cur);
+          if (valid[j]) atomicAdd(&a.currents[(size_t)surf * a.ncg + a.cmfd_group[e[j]]], cur);
+        }
+      }
+    }
+
     if (bnext != rec.base || i == n - 1) {
 #pragma unroll
       for (int j = 0; j < GPL; j++) {

@@ -13,7 +13,7 @@
  *        --solver both: CPUSolver and B200Solver in the same process on the same tracks,
  *        prints delta k_eff (pcm), max relative flux error and both sweep times.
  *                   [--max-iters N] [--threads N] [--res fission|flux|total]
- *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
+ *                   [--cmfd NXxNY[xNZ]] [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
  */
 #include <cstdio>
 #include <cstdlib>
@@ -22,6 +22,7 @@
 
 #include "CPUSolver.h"
 #include "CPULSSolver.h"
+#include "Cmfd.h"
 #include "TrackGenerator3D.h"
 #include "log.h"
 
@@ -67,6 +68,24 @@ int main(int argc, char** argv) {
   Model md = build_model(model_name, dims);
   if (flag(argc, argv, "--groups70")) set_70_group_xs(md);
   Geometry* geometry = md.geometry;
+  /* CMFD as in tests/test_cmfd_pwr_assembly / sample-input/benchmarks/c5g7/c5g7-2d.py:51-56 */
+  std::string cmfd_arg = arg(argc, argv, "--cmfd", "");
+  if (!cmfd_arg.empty()) {
+    int nx = 1, ny = 1, nz = 1;
+    sscanf(cmfd_arg.c_str(), "%dx%dx%d", &nx, &ny, &nz);
+    Cmfd* cmfd = new Cmfd();
+    cmfd->setSORRelaxationFactor(1.5);
+    if (dims == 3) cmfd->setLatticeStructure(nx, ny, nz);
+    else cmfd->setLatticeStructure(nx, ny);
+    if (geometry->getNumEnergyGroups() == 7 && !flag(argc, argv, "--groups70")) {
+      std::vector<std::vector<int> > groups(2);
+      for (int g = 1; g <= 3; g++) groups[0].push_back(g);
+      for (int g = 4; g <= 7; g++) groups[1].push_back(g);
+      cmfd->setGroupStructure(groups);
+    }
+    cmfd->setKNearest(3);
+    geometry->setCmfd(cmfd);
+  }
   geometry->initializeFlatSourceRegions();
 
   Quadrature* quad = NULL;
