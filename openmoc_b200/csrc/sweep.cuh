@@ -386,6 +386,22 @@ sweep_kernel(const SweepArgs a) {
       acc[j] += (double)sum;
     }
 
+    if constexpr (CMFD) {
+      /* outgoing flux of this segment across a CMFD cell surface (src/Cmfd.h:572-670) */
+      const int2 c = *pc;
+      pc += step;
+      const int surf = dir ? c.y : c.x;
+      if (surf >= 0) {
+#pragma unroll
+        for (int j = 0; j < GPL; j++) {
+          double cur = 0.0;
+#pragma unroll
+          for (int p = 0; p < NP; p++) cur = fma((double)w[p], (double)psi[p][j], cur);
+          if (valid[j]) atomicAdd(&a.currents[(size_t)surf * a.ncg + cg[j]], cur);
+        }
+      }
+    }
+
     /* flush before the FSR changes */
     {
       const bool flush = b1 != b0;
