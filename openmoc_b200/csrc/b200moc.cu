@@ -578,10 +578,19 @@ extern "C" int b200_finalize(b200_solver* s) {
     }
   }
 
-  /* work order: natural track order keeps neighbouring (parallel) tracks, which
-   * cross the same FSRs, in the same warp / CTA */
   std::vector<int32_t> order(nt);
   std::iota(order.begin(), order.end(), 0);
+  /* Longest tracks first (stable sort): the last wave of CTAs is then made of short tracks
+   * and the tail shrinks (+2 % on 82.8 M segments, +11 % on the 10 M-segment shards of an
+   * 8-GPU run); neighbours in the sorted order are still mostly neighbouring tracks, which
+   * cross the same FSRs.  B200_ORDER=natural keeps the Track uid order. */
+  {
+    const char* o = getenv("B200_ORDER");
+    if (o == nullptr || strcmp(o, "natural") != 0)
+      std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+        return (s->h_off[x + 1] - s->h_off[x]) > (s->h_off[y + 1] - s->h_off[y]);
+      });
+  }
 
   CU(s->cls_w.upload(cw.data(), cw.size(), s->stream));
   CU(s->cls_inv_sin.upload(cis.data(), cis.size(), s->stream));
