@@ -581,7 +581,7 @@ extern "C" int b200_finalize(b200_solver* s) {
   std::vector<int32_t> order(nt);
   std::iota(order.begin(), order.end(), 0);
   /* Longest tracks first (stable sort): the last wave of CTAs is then made of short tracks
-   * and the tail shrinks (+2 % on 82.8 M segments, +11 % on the 10 M-segment shards of an
+   * and the tail shrinks (+2 % on 82.8 M segments, more on the 10 M-segment shards of an
    * 8-GPU run); neighbours in the sorted order are still mostly neighbouring tracks, which
    * cross the same FSRs.  B200_ORDER=natural keeps the Track uid order. */
   {
