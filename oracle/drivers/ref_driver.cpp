@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <string>
 
 #include "CPUSolver.h"
@@ -169,7 +170,19 @@ int main(int argc, char** argv) {
   Solver* solver;
   CPUSolver* cpu_solver = NULL;
   B200Solver* b200_solver = NULL;
-  if (solver_name == "b200" || solver_name == "b200-fused") solver = b200_solver = new B200Solver(tg);
+  if (solver_name == "refgpu") {
+    /* the reference's own GPUSolver, recompiled for sm_100a (oracle/Makefile), loaded late so
+     * that ref_driver itself does not need a CUDA runtime */
+    std::string self = argv[0];
+    std::string dir = self.find('/') == std::string::npos ? "." : self.substr(0, self.rfind('/'));
+    void* so = dlopen((dir + "/libopenmoc_refgpu.so").c_str(), RTLD_NOW | RTLD_GLOBAL);
+    if (so == NULL) { fprintf(stderr, "ref_driver: %s\n", dlerror()); return 2; }
+    typedef Solver* (*factory_t)(TrackGenerator*, int, int);
+    factory_t make = (factory_t)dlsym(so, "make_ref_gpu_solver");
+    if (make == NULL) { fprintf(stderr, "ref_driver: %s\n", dlerror()); return 2; }
+    solver = make(tg, atoi(arg(argc, argv, "--gpu-blocks", "0")), atoi(arg(argc, argv, "--gpu-threads", "0")));
+  }
+  else if (solver_name == "b200" || solver_name == "b200-fused") solver = b200_solver = new B200Solver(tg);
   else if (solver_name == "b200ls") solver = new B200LSSolver(tg);
   else if (solver_name == "cpuls") solver = cpu_solver = new CPULSSolver(tg);
   else solver = cpu_solver = new CPUSolver(tg);
