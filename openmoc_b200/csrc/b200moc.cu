@@ -119,6 +119,7 @@ struct b200_solver {
   DevBuf<double> seg_len;
   DevBuf<int32_t> seg_fsr;
   DevBuf<SegRec> seg_rec;
+  int n_rep = 1;                      /* tally replicas */
   DevBuf<int64_t> trk_off, out_slot;
   DevBuf<int32_t> trk_class, order;
   DevBuf<uint8_t> carry;
@@ -601,18 +602,30 @@ extern "C" int b200_finalize(b200_solver* s) {
 
   /* state arrays (zero-initialised like CPUSolver::initializeFluxArrays, CPUSolver.cpp:281-370) */
   const size_t nphi = (size_t)s->n_fsr * s->G, npsi = (size_t)nt * 2 * s->F;
-  CU(s->phi.alloc(nphi)); CU(s->phi_old.alloc(nphi)); CU(s->fixed.alloc(nphi));
+  /* tally replicas (sweep.cuh: SweepArgs::rep_mask): enough copies that FSRs x copies >= 16 Ki
+   * rows, at most 64, at most 256 MB; B200_PHI_REPLICAS overrides (power of two) */
+  {
+    int R = 1;
+    while ((int64_t)s->n_fsr * R < 16384 && R < 64) R *= 2;
+    if (const char* e = getenv("B200_PHI_REPLICAS")) {
+      const int v = atoi(e);
+      if (v >= 1 && v <= 1024 && (v & (v - 1)) == 0) R = v;
+    }
+    while (R > 1 && (double)nphi * 8.0 * (s->linear ? 4.0 : 1.0) * R > 256e6) R /= 2;
+    s->n_rep = R;
+  }
+  CU(s->phi.alloc(nphi * s->n_rep)); CU(s->phi_old.alloc(nphi)); CU(s->fixed.alloc(nphi));
   CU(s->stab.alloc(nphi)); CU(s->qst.alloc(nphi)); CU(s->scratch.alloc(std::max(nphi, (size_t)s->n_fsr)));
   CU(s->psi_a.alloc(npsi)); CU(s->psi_b.alloc(npsi));
   CU(s->leakage.alloc(std::max<size_t>(nt, 1)));
   CU(cudaMemsetAsync(s->leakage.p, 0, std::max<size_t>(nt, 1) * 4, s->stream));
   CU(s->part3.alloc(3 * MAX_PARTIALS));
   if (s->cfg.deterministic) {
-    CU(s->phi_fx.alloc(nphi)); CU(s->fx_bits.alloc(4));
-    CU(cudaMemsetAsync(s->phi_fx.p, 0, nphi * 8, s->stream));
+    CU(s->phi_fx.alloc(nphi * s->n_rep)); CU(s->fx_bits.alloc(4));
+    CU(cudaMemsetAsync(s->phi_fx.p, 0, nphi * s->n_rep * 8, s->stream));
     CU(cudaMemsetAsync(s->fx_bits.p, 0, 4 * 8, s->stream));
   }
-  CU(cudaMemsetAsync(s->phi.p, 0, nphi * 8, s->stream));
+  CU(cudaMemsetAsync(s->phi.p, 0, nphi * s->n_rep * 8, s->stream));
   CU(cudaMemsetAsync(s->phi_old.p, 0, nphi * 8, s->stream));
   CU(cudaMemsetAsync(s->fixed.p, 0, nphi * 8, s->stream));
   CU(cudaMemsetAsync(s->stab.p, 0, nphi * 8, s->stream));
@@ -639,9 +652,9 @@ extern "C" int b200_finalize(b200_solver* s) {
     build_segpos_kernel<<<grid_for(s->n_seg + 2 * SEG_PAD, 256), 256, 0, s->stream>>>(
         s->seg_pos.p, s->ls_seg_start.p, s->n_seg);
     CU(cudaGetLastError());
-    CU(s->phi_m.alloc(nphi * 3));
+    CU(s->phi_m.alloc(nphi * 3 * s->n_rep));
     CU(s->qxyz.alloc(nphi));
-    CU(cudaMemsetAsync(s->phi_m.p, 0, nphi * 3 * 8, s->stream));
+    CU(cudaMemsetAsync(s->phi_m.p, 0, nphi * 3 * s->n_rep * 8, s->stream));
     CU(cudaMemsetAsync(s->qxyz.p, 0, nphi * 32, s->stream));
   }
 
@@ -748,6 +761,7 @@ static int launch_sweep(b200_solver* s) {
     a.carry = s->carry.p; a.cls_w = s->cls_w.p; a.cls_inv_sin = s->cls_inv_sin.p;
     a.qst = s->qst.p; a.psi_in = s->psi_start; a.psi_out = s->psi_other; a.phi = s->phi.p;
     a.phi_fx = s->phi_fx.p; a.fx_scale = s->scal.p + SC_FXSCALE;
+    a.rep_stride = (int64_t)nphi; a.rep_mask = s->n_rep - 1;
     a.leakage = s->balance ? s->leakage.p : nullptr;
     a.seg_cmfd = nullptr; a.cmfd_group = nullptr; a.currents = nullptr; a.ncg = 0;
     if (s->cmfd_on) {
@@ -801,6 +815,12 @@ static int launch_sweep(b200_solver* s) {
       lfn<<<(unsigned)s->sweep_blocks, nthr, 0, s->stream>>>(la);
       CU(cudaGetLastError());
       s->n_launches++;
+      if (s->n_rep > 1) {
+        fold_replicas_kernel<double><<<grid_for(nphi * 3, 256), 256, 0, s->stream>>>(
+            s->phi_m.p, (int64_t)nphi * 3, (int64_t)nphi * 3, s->n_rep);
+        CU(cudaGetLastError());
+        s->n_launches++;
+      }
     } else {
     sweep_fn fn;
     if (s->cmfd_on) {
@@ -816,6 +836,16 @@ static int launch_sweep(b200_solver* s) {
     fn<<<(unsigned)s->sweep_blocks, nthr, 0, s->stream>>>(a);
     CU(cudaGetLastError());
     s->n_launches++;
+    }
+    if (s->n_rep > 1) {
+      if (s->cfg.deterministic)
+        fold_replicas_kernel<unsigned long long><<<grid_for(nphi, 256), 256, 0, s->stream>>>(
+            s->phi_fx.p, (int64_t)nphi, (int64_t)nphi, s->n_rep);
+      else
+        fold_replicas_kernel<double><<<grid_for(nphi, 256), 256, 0, s->stream>>>(
+            s->phi.p, (int64_t)nphi, (int64_t)nphi, s->n_rep);
+      CU(cudaGetLastError());
+      s->n_launches++;
     }
   }
   if (s->cfg.deterministic && !s->defer_fx_convert) {

@@ -66,6 +66,16 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return r;
 }
 __device__ __forceinline__ float fast_rcp(float d) { return __frcp_rn(d); }
+/* n/d: MUFU.RCP64H seed (error e ~ 2^-20) times (1 + e + e^2): relative error e^3 */
+__device__ __forceinline__ double fast_div(double n, double d) {
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+  double e = fma(-d, r0, 1.0);
+  const double n0 = n * r0;
+  e = fma(e, e, e);
+  return fma(n0, e, n0);
+}
+__device__ __forceinline__ float fast_div(float n, float d) { return n * __frcp_rn(d); }
 __device__ __forceinline__ double fast_rcp_seed(double d) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
@@ -93,7 +103,7 @@ __device__ __forceinline__ double expF1(double x) {
   num = fma(num, x, c_F1[7]);
   num = fma(num, x, c_F1[6]);
   num = fma(num, x, 1.0);
-  return num * fast_rcp(den);
+  return fast_div(num, den);
 }
 
 template <typename T>
@@ -110,7 +120,7 @@ __device__ __forceinline__ T expF1(T x) {
   num = fma(num, x, C::p2);
   num = fma(num, x, C::p1);
   num = fma(num, x, C::p0);
-  return num * fast_rcp(den);
+  return fast_div(num, den);
 }
 
 /* One segment of the device stream: 16 bytes, read with a single LDG.128.
@@ -152,26 +162,26 @@ __device__ __forceinline__ void expF1_batch(const T (&x)[NP], T (&out)[NP], cons
 #pragma unroll
     for (int p = 0; p < NP; p++) den[p] = fma(den[p], x[p], 1.0f);
   }
-  T r[NP];
-#ifdef B200_EXP_NORCP
-#pragma unroll
-  for (int p = 0; p < NP; p++) r[p] = den[p] * (T)0.37;
-#else
-#pragma unroll
-  for (int p = 0; p < NP; p++) r[p] = fast_rcp_seed(den[p]);
-#endif
   if constexpr (sizeof(T) == 8) {
+    /* num/den without a division: seed r0 = MUFU.RCP64H (relative error e ~ 2^-20), then
+     * 1/den = r0/(1-e) = r0 (1 + e + e^2) (1 + O(e^3)), i.e. full double precision from four
+     * DFMA/DMUL, two of them independent (two Newton steps + the product take five, in one
+     * dependent chain) */
+    T r0[NP], e[NP], n0[NP];
 #pragma unroll
-    for (int it = 0; it < B200_NR_STEPS; it++) {
-      T e[NP];
+    for (int p = 0; p < NP; p++) r0[p] = fast_rcp_seed(den[p]);
 #pragma unroll
-      for (int p = 0; p < NP; p++) e[p] = fma(-den[p], r[p], (T)1);
+    for (int p = 0; p < NP; p++) e[p] = fma(-den[p], r0[p], (T)1);
 #pragma unroll
-      for (int p = 0; p < NP; p++) r[p] = fma(r[p], e[p], r[p]);
-    }
+    for (int p = 0; p < NP; p++) n0[p] = num[p] * r0[p];
+#pragma unroll
+    for (int p = 0; p < NP; p++) e[p] = fma(e[p], e[p], e[p]);
+#pragma unroll
+    for (int p = 0; p < NP; p++) out[p] = fma(n0[p], e[p], n0[p]);
+  } else {
+#pragma unroll
+    for (int p = 0; p < NP; p++) out[p] = num[p] * fast_rcp_seed(den[p]);
   }
-#pragma unroll
-  for (int p = 0; p < NP; p++) out[p] = num[p] * r[p];
 }
 
 #ifndef B200_REC_HINT
@@ -239,6 +249,12 @@ struct SweepArgs {
   const float* __restrict__ psi_in;
   float* __restrict__ psi_out;
   double* __restrict__ phi;                /* tally target [n_fsr*G] */
+  /* Tally replicas: CTA b adds into copy (b & rep_mask) of the tally (copies rep_stride
+   * elements apart, copy 0 = phi itself) and fold_replicas_kernel sums them after the
+   * sweep.  With few FSRs (512 in the lattice decks) same-address RED contention, not
+   * arithmetic, bounds the sweep; R copies divide it by R.  rep_mask = 0: one copy. */
+  int64_t rep_stride;
+  int rep_mask;
   /* deterministic mode: the tally is accumulated as 64-bit fixed point (integer adds are
    * associative, so the result does not depend on the order the atomics land in) */
   unsigned long long* __restrict__ phi_fx; /* [n_fsr*G], used by the DET kernels */
@@ -259,6 +275,19 @@ struct SweepArgs {
    * (three distinct 64-bit register operands cost a third cycle). */
   double cf[11];
 };
+
+/* sums the tally replicas into copy 0 and clears the others for the next sweep */
+template <typename V>
+__global__ void fold_replicas_kernel(V* __restrict__ base, int64_t n, int64_t stride, int n_rep) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    V sum = base[i];
+    for (int r = 1; r < n_rep; r++) {
+      sum += base[r * stride + i];
+      base[r * stride + i] = V(0);
+    }
+    base[i] = sum;
+  }
+}
 
 /* CTAs are at most 224 threads (7 warps: 32 items of 7 lanes for G = 7).  For the
  * small-G shapes four CTAs per SM (28 warps) are worth more than registers: the
@@ -340,7 +369,9 @@ sweep_kernel(const SweepArgs a) {
   for (int j = 0; j < GPL; j++) qs0[j] = ld_qs(&a.qst[b0 + e[j]]);
   ps += 2 * step;
 
-  double* __restrict__ const phi = a.phi;
+  const int64_t rep_off = (int64_t)(blockIdx.x & a.rep_mask) * a.rep_stride;
+  double* __restrict__ const phi = a.phi + rep_off;
+  [[maybe_unused]] unsigned long long* __restrict__ const phi_fx = DET ? a.phi_fx + rep_off : nullptr;
   const double fx_scale = DET ? *a.fx_scale : 0.0;
   [[maybe_unused]] const int2* __restrict__ pc = CMFD ? a.seg_cmfd + (dir ? s1 - 1 : s0) : nullptr;
   [[maybe_unused]] int cg[GPL];
@@ -409,7 +440,7 @@ sweep_kernel(const SweepArgs a) {
       for (int j = 0; j < GPL; j++) {
         if constexpr (DET) {
           if (flush && valid[j])
-            atomicAdd(&a.phi_fx[b0 + e[j]], (unsigned long long)__double2ll_rn(acc[j] * fx_scale));
+            atomicAdd(&phi_fx[b0 + e[j]], (unsigned long long)__double2ll_rn(acc[j] * fx_scale));
         } else {
           red_add_if(&phi[b0 + e[j]], acc[j], flush && valid[j]);   /* predicated RED, no branch */
         }
@@ -429,7 +460,7 @@ sweep_kernel(const SweepArgs a) {
 #pragma unroll
     for (int j = 0; j < GPL; j++)
       if (valid[j] && acc[j] != 0.0) {
-        if constexpr (DET) atomicAdd(&a.phi_fx[blast + e[j]], (unsigned long long)__double2ll_rn(acc[j] * fx_scale));
+        if constexpr (DET) atomicAdd(&phi_fx[blast + e[j]], (unsigned long long)__double2ll_rn(acc[j] * fx_scale));
         else atomicAdd(&phi[blast + e[j]], acc[j]);
       }
   }

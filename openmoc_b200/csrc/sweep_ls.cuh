@@ -44,7 +44,7 @@ __device__ __forceinline__ double expG(double x, const double (&c)[12]) {
   num = fma(num, x, c[2]);
   num = fma(num, x, c[1]);
   num = fma(num, x, c[0]);
-  return num * fast_rcp(den);
+  return fast_div(num, den);
 }
 
 template <int NP, int GPL, bool IS3D>
@@ -81,6 +81,10 @@ sweep_ls_kernel(const SweepLSArgs la) {
   /* direction of travel; the reverse item flips it (TrackTraversingAlgorithms.cpp:1006-1008) */
   const double sgn = dir ? -1.0 : 1.0;
   const double dx = sgn * la.trk_dir[t * 3], dy = sgn * la.trk_dir[t * 3 + 1], dz = sgn * la.trk_dir[t * 3 + 2];
+
+  const int64_t rep = (int64_t)(blockIdx.x & a.rep_mask);
+  double* __restrict__ const phi = a.phi + rep * a.rep_stride;
+  double* __restrict__ const phi_m = la.phi_m + rep * a.rep_stride * 3;
 
   const int F = G * NP;
   const int64_t slot_in = (t * 2 + dir) * (int64_t)F;
@@ -183,10 +187,10 @@ sweep_ls_kernel(const SweepLSArgs la) {
       for (int j = 0; j < GPL; j++) {
         if (valid[j]) {
           const uint32_t idx = rec.base + e[j];
-          atomicAdd(&a.phi[idx], wflush * acc[j]);
-          atomicAdd(&la.phi_m[(size_t)idx * 3], wflush * accx[j]);
-          atomicAdd(&la.phi_m[(size_t)idx * 3 + 1], wflush * accy[j]);
-          if (IS3D) atomicAdd(&la.phi_m[(size_t)idx * 3 + 2], wflush * accz[j]);
+          atomicAdd(&phi[idx], wflush * acc[j]);
+          atomicAdd(&phi_m[(size_t)idx * 3], wflush * accx[j]);
+          atomicAdd(&phi_m[(size_t)idx * 3 + 1], wflush * accy[j]);
+          if (IS3D) atomicAdd(&phi_m[(size_t)idx * 3 + 2], wflush * accz[j]);
         }
         acc[j] = accx[j] = accy[j] = accz[j] = 0.0;
       }
