@@ -218,6 +218,9 @@ __device__ __forceinline__ void red_add_if(double* addr, double v, bool p) {
                ::"l"(addr), "d"(v), "r"((uint32_t)p) : "memory");
 }
 
+#ifndef B200_ACC_DIRECT
+#define B200_ACC_DIRECT 1
+#endif
 #ifndef B200_SWEEP_UNROLL
 #define B200_SWEEP_UNROLL 1
 #endif
@@ -402,6 +405,18 @@ sweep_kernel(const SweepArgs a) {
 #pragma unroll
       for (int p = 0; p < NP; p++) x[p] = tau * inv_sin[p];
       expF1_batch<T, NP>(x, f1, a.cf);
+#if B200_ACC_DIRECT
+      /* fsr_flux[e] += weight * delta_psi, polar angle after polar angle as the reference does
+       * (CPUSolver.cpp:2463-2470): NP DFMA on the accumulator, no separate sum */
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
+        const T ex = inv_sin[p] * f1[p];
+        const T dpsi = (tau * (T)psi[p][j] - lq) * ex;
+        psi[p][j] = (float)((T)psi[p][j] - dpsi);
+        if constexpr (sizeof(T) == 8) acc[j] = fma((double)w[p], (double)dpsi, acc[j]);
+        else acc[j] += (double)(w[p] * dpsi);
+      }
+#else
       T sum = (T)0;
 #pragma unroll
       for (int p = 0; p < NP; p++) {
@@ -415,6 +430,7 @@ sweep_kernel(const SweepArgs a) {
         sum = fma(w[p], dpsi, sum);
       }
       acc[j] += (double)sum;
+#endif
     }
 
     if constexpr (CMFD) {
