@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <vector>
+#include <omp.h>
 
 #include "Solver.h"
 #include "TrackGenerator3D.h"
@@ -104,6 +105,13 @@ public:
   void initializeFixedSources();
   void computeFSRFissionRates(double* fission_rates, long num_FSRs, bool nu = false);
 
+  /** Host threads for what stays on the CPU (track flattening, the reference Cmfd, the
+   *  linear-source pre-pass); same meaning as CPUSolver::setNumThreads (CPUSolver.cpp:132-159). */
+  void setNumThreads(int num_threads) {
+    if (num_threads <= 0)
+      log_printf(ERROR, "Unable to set the number of threads to %d since it is less than or equal to 0", num_threads);
+    omp_set_num_threads(num_threads);
+  }
   /** Copy phi, old phi and q from the device into the base-class host arrays. */
   void syncHostMirrors();
   /** Fused device-side source iteration (b200_compute_eigenvalue): same results as

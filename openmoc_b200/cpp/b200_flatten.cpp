@@ -36,9 +36,14 @@ class FlattenPass : public TraverseSegments {
 
   void execute() {
     if (_segment_formation != EXPLICIT_2D && _segment_formation != EXPLICIT_3D) {
+      /* on-the-fly formations re-trace into the TrackGenerator's per-thread buffers: keep
+       * the calling thread only (a team of one, as the orphaned `omp for` then binds) */
       MOCKernel* kernel = getKernel<SegmentationKernel>();
       loopOverTracks(kernel);
     } else {
+      /* explicit segments are only read: give the reference's orphaned `omp for`
+       * (TraverseSegments.cpp:75) a team; every track writes its own slots */
+#pragma omp parallel
       loopOverTracks(NULL);
     }
   }
@@ -82,14 +87,21 @@ class FlattenPass : public TraverseSegments {
     }
 
     int n = track->getNumSegments();
+    Material* last_mat = NULL;
+    int last_idx = -1;
+    if (n_in_stack == 1) _per_track[uid].reserve(n);
     for (int s = 0; s < n; s++) {
       const segment& sg = segments[s];
       long id = uid + sg._track_idx;
       Seg o;
       o.len = sg._length;
       o.fsr = sg._region_id;
-      std::map<Material*, int>::iterator it = _mat_index->find(sg._material);
-      o.mat = (it == _mat_index->end()) ? -1 : it->second;
+      if (sg._material != last_mat) {       /* consecutive segments mostly share a material */
+        std::map<Material*, int>::iterator it = _mat_index->find(sg._material);
+        last_mat = sg._material;
+        last_idx = (it == _mat_index->end()) ? -1 : it->second;
+      }
+      o.mat = last_idx;
       o.cf = sg._cmfd_surface_fwd;
       o.cb = sg._cmfd_surface_bwd;
       o.x = sg._starting_position[0];
@@ -210,6 +222,7 @@ void b200_flatten(TrackGenerator* tg, B200FlatTracks* ft, bool with_ls_data) {
   ft->seg_length.resize(ns); ft->seg_fsr.resize(ns); ft->seg_mat.resize(ns);
   ft->seg_cmfd_fwd.resize(ns); ft->seg_cmfd_bwd.resize(ns);
   if (with_ls_data) ft->seg_start.resize(3 * ns);
+#pragma omp parallel for schedule(static, 256)
   for (size_t t = 0; t < nt; t++) {
     size_t o = ft->trk_seg_offset[t];
     std::vector<FlattenPass::Seg>& v = pass._per_track[t];

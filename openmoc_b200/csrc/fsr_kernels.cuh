@@ -501,7 +501,8 @@ struct LsArgs {
   int solve_3d;
   const double* __restrict__ lin_exp;       /* [n_fsr][nc]  _FSR_lin_exp_matrix (CPULSSolver.h) */
   const double* __restrict__ src_const;     /* [n_fsr][nc][G]  _FSR_source_constants */
-  double* __restrict__ phi_m;               /* [(r*G+e)*3 + c] flux moments */
+  double* __restrict__ phi_m;               /* [c*N_FSR*G + r*G+e] flux moments, one plane per component:
+                                             * the sweep's moment REDs are then as coalesced as the phi RED */
   double4* __restrict__ qxyz;               /* {q_x, q_y, q_z, 0} per (r, e) */
 };
 
@@ -521,8 +522,9 @@ sources_ls_kernel(const FsrArgs a, const LsArgs l, int iteration, int neg_allowe
   const bool fissionable = a.fissionable[m];
   double sx = 0., sy = 0., sz = 0., fx = 0., fy = 0., fz = 0.;
   for (int gp = 0; gp < G; gp++) {
-    const double* __restrict__ pm = l.phi_m + (r * G + gp) * 3;
-    const double mx = pm[0], my = pm[1], mz = pm[2];
+    const int64_t np = a.n_fsr * G;
+    const double* __restrict__ pm = l.phi_m + (r * G + gp);
+    const double mx = pm[0], my = pm[np], mz = pm[2 * np];
     sx = fma(ss[gp], mx, sx); sy = fma(ss[gp], my, sy); sz = fma(ss[gp], mz, sz);
     if (fissionable) { fx = fma(fm[gp], mx, fx); fy = fma(fm[gp], my, fy); fz = fma(fm[gp], mz, fz); }
   }
@@ -565,8 +567,9 @@ closure_ls_kernel(const FsrArgs a, const LsArgs l, int neg_allowed, int with_rat
     f /= volume;
     f += FOUR_PI * qs.x;
     f /= qs.y;
-    double* __restrict__ pm = l.phi_m + idx * 3;
-    double mx = pm[0] / volume, my = pm[1] / volume, mz = pm[2] / volume;
+    const int64_t np = a.n_fsr * G;
+    double* __restrict__ pm = l.phi_m + idx;
+    double mx = pm[0] / volume, my = pm[np] / volume, mz = pm[2 * np] / volume;
     mx += flux_const * qm.x * sc[e];
     mx += flux_const * qm.y * sc[2 * G + e];
     my += flux_const * qm.x * sc[2 * G + e];
@@ -586,7 +589,7 @@ closure_ls_kernel(const FsrArgs a, const LsArgs l, int neg_allowed, int with_rat
       mx = my = mz = 0.;
     }
     a.phi[idx] = f;
-    pm[0] = mx; pm[1] = my; pm[2] = mz;
+    pm[0] = mx; pm[np] = my; pm[2 * np] = mz;
     local += a.nu_sigma_f[(int64_t)a.fsr_mat[r] * G + e] * f * a.vol[r];
   }
   if (with_rate) {
@@ -611,7 +614,7 @@ __global__ void moments_to_ref_kernel(const double* __restrict__ dev, double* __
     const int64_t r = i / (3 * G);
     const int rem = (int)(i - r * 3 * G);
     const int c = rem / G, e = rem - c * G;
-    ref[i] = dev[(r * G + e) * 3 + c];
+    ref[i] = dev[(int64_t)c * n_fsr * G + r * G + e];
   }
 }
 __global__ void moments_from_ref_kernel(double* __restrict__ dev, const double* __restrict__ ref, int64_t n_fsr, int G) {
@@ -620,7 +623,7 @@ __global__ void moments_from_ref_kernel(double* __restrict__ dev, const double* 
     const int64_t r = i / (3 * G);
     const int rem = (int)(i - r * 3 * G);
     const int c = rem / G, e = rem - c * G;
-    dev[(r * G + e) * 3 + c] = ref[i];
+    dev[(int64_t)c * n_fsr * G + r * G + e] = ref[i];
   }
 }
 

@@ -27,7 +27,7 @@ struct SweepLSArgs {
   const double4* __restrict__ seg_pos;      /* {x, y, z, 0} per segment, padded like seg */
   const double* __restrict__ trk_dir;       /* [n_trk][3] unit vector of the forward direction */
   const double4* __restrict__ qxyz;         /* {q_x, q_y, q_z, 0} per (FSR, group) */
-  double* __restrict__ phi_m;               /* moment tallies [(fsr*G+e)*3 + c] */
+  double* __restrict__ phi_m;               /* moment tallies [c*N_FSR*G + fsr*G+e] */
   double cg[12];                            /* expG coefficients p0..p5, d1..d6 */
 };
 
@@ -45,6 +45,23 @@ __device__ __forceinline__ double expG(double x, const double (&c)[12]) {
   num = fma(num, x, c[1]);
   num = fma(num, x, c[0]);
   return fast_div(num, den);
+}
+
+__device__ __forceinline__ double4 ld_pos(const double4* p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+/* {q, sigma_t} and the source moments of one (FSR, group); q_z is not read in 2D */
+template <bool IS3D>
+__device__ __forceinline__ void ld_src(const double2* __restrict__ qst, const double4* __restrict__ qxyz,
+                                       uint32_t idx, double2& qs, double4& qm) {
+  qs = __ldg(&qst[idx]);
+  const double2* qmp = reinterpret_cast<const double2*>(&qxyz[idx]);
+  const double2 q01 = __ldg(qmp);
+  double2 q23 = make_double2(0.0, 0.0);
+  if (IS3D) q23 = __ldg(qmp + 1);
+  qm = make_double4(q01.x, q01.y, q23.x, q23.y);
 }
 
 template <int NP, int GPL, bool IS3D>
@@ -111,11 +128,37 @@ sweep_ls_kernel(const SweepLSArgs la) {
    * (TrackTraversingAlgorithms.cpp:904-910), 2D tracks per polar angle */
   const double wflush = IS3D ? w[0] : 1.0;
 
+  /* Software pipeline as in the flat kernel: record and starting point two segments ahead,
+   * the {q, sigma_t} / {q_x, q_y, q_z} gathers one segment ahead when a thread owns a single
+   * group (with three groups the 36 extra registers cost more than the latency they hide).
+   * Both streams are padded by SEG_PAD records, so the look-ahead needs no bounds test. */
+  constexpr bool PFG = (GPL == 1);
+  int4 r0 = ld_rec(a.seg + s), r1 = ld_rec(a.seg + s + step);
+  double4 p0 = ld_pos(la.seg_pos + s), p1 = ld_pos(la.seg_pos + s + step);
+  double2 qsN[GPL];
+  double4 qmN[GPL];
+  if (PFG) {
+#pragma unroll
+    for (int j = 0; j < GPL; j++) ld_src<IS3D>(a.qst, la.qxyz, (uint32_t)r0.z + e[j], qsN[j], qmN[j]);
+  }
+
   for (int i = 0; i < n; i++, s += step) {
-    const SegRec rec = a.seg[s];
-    const double4 pos4 = la.seg_pos[s];
-    const uint32_t bnext = a.seg[s + step].base;     /* padded stream: always readable */
-    const double len = rec.len;
+    const int4 r2 = ld_rec(a.seg + s + 2 * step);
+    const double4 p2 = ld_pos(la.seg_pos + s + 2 * step);
+    const uint32_t base = (uint32_t)r0.z, bnext = (uint32_t)r1.z;
+    double2 qsC[GPL];
+    double4 qmC[GPL];
+#pragma unroll
+    for (int j = 0; j < GPL; j++) {
+      if (PFG) {
+        qsC[j] = qsN[j]; qmC[j] = qmN[j];
+        ld_src<IS3D>(a.qst, la.qxyz, bnext + e[j], qsN[j], qmN[j]);
+      } else {
+        ld_src<IS3D>(a.qst, la.qxyz, base + e[j], qsC[j], qmC[j]);
+      }
+    }
+    const double len = __hiloint2double(r0.y, r0.x);
+    const double4 pos4 = p0;
     /* starting point of this traversal: the stored point forward, the segment's end backward */
     const double px = dir ? pos4.x - dx * len : pos4.x;   /* pos + dir_fwd*len, dir_fwd = -d */
     const double py = dir ? pos4.y - dy * len : pos4.y;
@@ -125,14 +168,16 @@ sweep_ls_kernel(const SweepLSArgs la) {
 
 #pragma unroll
     for (int j = 0; j < GPL; j++) {
-      const double2 qs = __ldg(&a.qst[rec.base + e[j]]);
-      const double2* qmp = reinterpret_cast<const double2*>(&la.qxyz[rec.base + e[j]]);
-      const double2 qm01 = __ldg(qmp), qm23 = __ldg(qmp + 1);
-      const double4 qm = make_double4(qm01.x, qm01.y, qm23.x, qm23.y);
+      const double2 qs = qsC[j];
+      const double4 qm = qmC[j];
       const double tau = qs.y * len;
       double src_flat = qs.x + qm.x * cx + qm.y * cy;
       double src_lin = qm.x * dx + qm.y * dy;
       if (IS3D) { src_flat += qm.z * cz; src_lin += qm.z * dz; }
+      const double lsf = len * src_flat, l2sl = len * len * src_lin, tl = tau * len;
+      /* sum over the polar angles of the (weighted) delta psi and of the H term: the three
+       * moment tallies take them once per segment instead of once per polar angle */
+      double sumd = 0.0, sumh = 0.0;
 #pragma unroll
       for (int p = 0; p < NP; p++) {
         double f1, f2, h;
@@ -151,21 +196,20 @@ sweep_ls_kernel(const SweepLSArgs la) {
           h = f1 - g;
         }
         const double psid = (double)psi[p][j];
-        double dpsi;
-        if (IS3D) {
-          h *= len * psid * tau;
-          dpsi = (tau * psid - len * src_flat) * f1 - src_lin * len * len * f2;
-        } else {
-          h *= w[p] * tau * len * psid;
-          dpsi = (tau * psid - len * src_flat) * f1 - len * len * src_lin * f2;
-        }
+        const double dpsi = fma(-l2sl, f2, (tau * psid - lsf) * f1);
         psi[p][j] = (float)(psid - dpsi);
-        if (!IS3D) dpsi *= w[p];
-        acc[j] += dpsi;
-        accx[j] += h * dx + dpsi * px;
-        accy[j] += h * dy + dpsi * py;
-        if (IS3D) accz[j] += h * dz + dpsi * pz;
+        if (IS3D) {
+          sumh = fma(h * tl, psid, sumh);
+          sumd += dpsi;
+        } else {
+          sumh = fma(h * (w[p] * tl), psid, sumh);
+          sumd = fma(w[p], dpsi, sumd);
+        }
       }
+      acc[j] += sumd;
+      accx[j] += fma(sumh, dx, sumd * px);
+      accy[j] += fma(sumh, dy, sumd * py);
+      if (IS3D) accz[j] += fma(sumh, dz, sumd * pz);
     }
 
     if (a.seg_cmfd != nullptr) {      /* CMFD surface currents, src/Cmfd.h:572-670 */
@@ -182,19 +226,21 @@ sweep_ls_kernel(const SweepLSArgs la) {
       }
     }
 
-    if (bnext != rec.base || i == n - 1) {
+    if (bnext != base || i == n - 1) {
 #pragma unroll
       for (int j = 0; j < GPL; j++) {
         if (valid[j]) {
-          const uint32_t idx = rec.base + e[j];
+          const uint32_t idx = base + e[j];
           atomicAdd(&phi[idx], wflush * acc[j]);
-          atomicAdd(&phi_m[(size_t)idx * 3], wflush * accx[j]);
-          atomicAdd(&phi_m[(size_t)idx * 3 + 1], wflush * accy[j]);
-          if (IS3D) atomicAdd(&phi_m[(size_t)idx * 3 + 2], wflush * accz[j]);
+          atomicAdd(&phi_m[(size_t)idx], wflush * accx[j]);
+          atomicAdd(&phi_m[(size_t)idx + a.rep_stride], wflush * accy[j]);
+          if (IS3D) atomicAdd(&phi_m[(size_t)idx + 2 * a.rep_stride], wflush * accz[j]);
         }
         acc[j] = accx[j] = accy[j] = accz[j] = 0.0;
       }
     }
+    r0 = r1; r1 = r2;
+    p0 = p1; p1 = p2;
   }
 
   const int64_t out = a.out_slot[t * 2 + dir];

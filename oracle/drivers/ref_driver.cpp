@@ -143,6 +143,7 @@ int main(int argc, char** argv) {
     B200Solver* gpu_flat = ls ? NULL : new B200Solver(tg);
     B200LSSolver* gpu_ls = ls ? new B200LSSolver(tg) : NULL;
     Solver& gpu = ls ? *(Solver*)gpu_ls : *(Solver*)gpu_flat;
+    if (ls) gpu_ls->setNumThreads(threads); else gpu_flat->setNumThreads(threads);
     gpu.setConvergenceThreshold(tol);
     if (flag(argc, argv, "--balance")) gpu.setKeffFromNeutronBalance();
     gpu.computeEigenvalue(max_iters, rt);
@@ -183,10 +184,11 @@ int main(int argc, char** argv) {
     solver = make(tg, atoi(arg(argc, argv, "--gpu-blocks", "0")), atoi(arg(argc, argv, "--gpu-threads", "0")));
   }
   else if (solver_name == "b200" || solver_name == "b200-fused") solver = b200_solver = new B200Solver(tg);
-  else if (solver_name == "b200ls") solver = new B200LSSolver(tg);
+  else if (solver_name == "b200ls") { B200LSSolver* ls = new B200LSSolver(tg); ls->setNumThreads(threads); solver = ls; }
   else if (solver_name == "cpuls") solver = cpu_solver = new CPULSSolver(tg);
   else solver = cpu_solver = new CPUSolver(tg);
   if (cpu_solver != NULL) cpu_solver->setNumThreads(threads);
+  if (b200_solver != NULL) b200_solver->setNumThreads(threads);   /* host side: flatten, Cmfd */
   solver->setConvergenceThreshold(tol);
   if (flag(argc, argv, "--balance")) solver->setKeffFromNeutronBalance();   /* Solver.cpp:2047 */
 
