@@ -170,7 +170,7 @@ def main():
     ap.add_argument("--azim", type=int, default=None)
     ap.add_argument("--spacing", type=float, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--partition", default="pair", choices=["pair", "chain"])
+    ap.add_argument("--partition", default="pair", choices=["pair", "chain", "track"])
     ap.add_argument("--deterministic", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -311,7 +311,8 @@ def main():
                        "num_polar": num_polar, "n_tracks": ft.n_tracks, "n_segments": ft.n_segments,
                        "n_fsrs": ft.n_fsrs, "groups": G, "fluxes_per_track": F,
                        "integrations_per_sweep": W_sweep,
-                       "parallelism": "1 GPU" if world == 1 else f"{args.partition} partition x{world} + NCCL all-reduce of the FSR tally",
+                       "parallelism": "1 GPU" if world == 1 else f"{args.partition} partition x{world} + NCCL all-reduce of the FSR tally"
+                                      + (" + NCCL send/recv of cross-rank boundary fluxes" if args.partition == "track" else ""),
                        "deterministic_tally": bool(args.deterministic),
                        "l2": "segment stream (%.2f GB) is larger than the 126 MB L2; no flush" % (12.0 * ft.n_segments / 1e9)
                              if 12.0 * ft.n_segments > 2.5e8 else "inputs fit in L2; not flushed (launch-bound shape)",

@@ -1,4 +1,5 @@
-"""Decomposition of flattened tracks across GPUs without angular-flux exchange.
+"""Decomposition of flattened tracks across GPUs: two partitions without angular-flux
+exchange (pairs, chains) and one with it (`partition_by_track`, at the end of the file).
 
 Boundary hand-offs (`trk_next_fwd/bwd`) define a graph over the tracks; its connected
 components - the cyclic track chains of the reference's cyclic tracking, or open paths
@@ -89,8 +90,9 @@ def partition_by_azim_pair(ft: FlatTracks, world: int) -> List[FlatTracks]:
     return [_extract(ft, np.nonzero(np.isin(azim, owned[rank]))[0]) for rank in range(world)]
 
 
-def _extract(ft: FlatTracks, ids: np.ndarray) -> FlatTracks:
-    """The sub-problem made of tracks `ids` (closed under links), renumbered 0..n-1."""
+def _extract(ft: FlatTracks, ids: np.ndarray, closed: bool = True) -> FlatTracks:
+    """The sub-problem made of tracks `ids`, renumbered 0..n-1.  `closed`: the set must be
+    closed under links; otherwise links that leave it are returned as -2."""
     a = ft.arrays
     off = a["trk_seg_offset"].astype(np.int64)
     nseg = np.diff(off)
@@ -123,9 +125,162 @@ def _extract(ft: FlatTracks, ids: np.ndarray) -> FlatTracks:
         linked = (bc == REFLECTIVE) | (bc == PERIODIC)
         mapped = np.where(linked, new_id[np.clip(nxt, 0, ft.n_tracks - 1)], -1)
         if linked.any() and mapped[linked].min() < 0:
-            raise ValueError("track partition is not closed under boundary links")
+            if closed:
+                raise ValueError("track partition is not closed under boundary links")
+            mapped = np.where(linked & (mapped < 0), -2, mapped)
         b["trk_next_" + d] = mapped
     for k, v in a.items():
         if k.startswith(("quad_", "fsr_", "mat_")):
             b[k] = v
     return sub
+
+
+# ---------------------------------------------------------------------------------------
+# Partition with angular-flux exchange
+# ---------------------------------------------------------------------------------------
+class ExchangePlan:
+    """What one rank sends and receives after every sweep (all sizes in start-flux slots of
+    F floats; a slot is (track, direction), index track*2 + direction).
+
+    ghost0        first ghost slot: outgoing fluxes bound for other ranks are written by the
+                  sweep itself into slots ghost0 .. ghost0 + n_send - 1, grouped by destination
+    send_counts   [world] slots sent to each rank (contiguous ranges of the ghost slots)
+    recv_counts   [world] slots received from each rank
+    recv_slots    [n_recv] local slot every received flux is stored to, in arrival order
+                  (source rank major, then the sender's order)
+    """
+    def __init__(self, ghost0, send_counts, recv_counts, recv_slots):
+        self.ghost0 = int(ghost0)
+        self.send_counts = [int(x) for x in send_counts]
+        self.recv_counts = [int(x) for x in recv_counts]
+        self.recv_slots = np.asarray(recv_slots, dtype=np.int64)
+        self.n_send = sum(self.send_counts)
+        self.n_recv = sum(self.recv_counts)
+
+
+def assign_tracks(ft: FlatTracks, world: int) -> np.ndarray:
+    """Owner rank per track: tracks sorted by segment count and dealt in a snake
+    (0..w-1, w-1..0, ...), so every rank gets the same number of segments to within one
+    track and the same mix of long and short tracks - for any number of ranks."""
+    nseg = np.diff(ft.arrays["trk_seg_offset"].astype(np.int64))
+    order = np.argsort(-nseg, kind="stable")
+    pos = np.arange(ft.n_tracks) % (2 * world)
+    owner = np.empty(ft.n_tracks, dtype=np.int64)
+    owner[order] = np.where(pos < world, pos, 2 * world - 1 - pos)
+    return owner
+
+
+def partition_by_track(ft: FlatTracks, world: int, owner: np.ndarray = None, only: int = None):
+    """Shard individual tracks across `world` ranks; hand-offs that cross ranks are exchanged
+    after every sweep (the role of the reference's interface-flux exchange,
+    CPUSolver::transferAllInterfaceFluxes, src/CPUSolver.cpp:1063-1211, here with
+    torch.distributed send/recv over NCCL).  Unlike the reference's domain decomposition the
+    exchanged flux is used by the very next sweep, exactly as in a single-process run, so the
+    iteration (and its count) does not depend on the number of ranks.
+
+    Returns [(FlatTracks, ExchangePlan)] per rank (`only`: build that rank's entry, None for
+    the others).  A remote hand-off is expressed with plain
+    track data: every rank gets ceil(n_send/2) *ghost tracks* with no segments and vacuum ends,
+    appended after its own; the link of a track whose successor lives elsewhere points at a
+    ghost (track, direction), so the sweep kernel packs the send buffer by itself."""
+    a = ft.arrays
+    nt = ft.n_tracks
+    if owner is None:
+        owner = assign_tracks(ft, world)
+    owner = np.asarray(owner, dtype=np.int64)
+    ids_of = [np.nonzero(owner == r)[0] for r in range(world)]
+    new_id = np.empty(nt, dtype=np.int64)
+    for r in range(world):
+        new_id[ids_of[r]] = np.arange(ids_of[r].size)
+
+    # every cross-rank hand-off: (source rank, destination rank, global target slot, source slot)
+    src_slot, dst_slot = [], []
+    for d, bit in (("fwd", 1), ("bwd", 2)):
+        bc = a["trk_bc_" + d]
+        linked = np.nonzero((bc == REFLECTIVE) | (bc == PERIODIC))[0]
+        nx = a["trk_next_" + d][linked].astype(np.int64)
+        to_fwd = (a["trk_flags"][linked] & bit) != 0
+        remote = owner[nx] != owner[linked]
+        src_slot.append(linked[remote] * 2 + (0 if d == "fwd" else 1))
+        dst_slot.append(nx[remote] * 2 + np.where(to_fwd[remote], 0, 1))
+    src_slot = np.concatenate(src_slot) if src_slot else np.zeros(0, np.int64)
+    dst_slot = np.concatenate(dst_slot) if dst_slot else np.zeros(0, np.int64)
+    src_rank, dst_rank = owner[src_slot // 2], owner[dst_slot // 2]
+
+    out = []
+    for r in range(world):
+        if only is not None and r != only:
+            out.append(None)
+            continue
+        sub = _extract(ft, ids_of[r], closed=False)
+        n_loc = sub.n_tracks
+        mine = np.nonzero(src_rank == r)[0]
+        # send order: destination rank, then target slot (the receiver sorts the same way)
+        mine = mine[np.lexsort((dst_slot[mine], dst_rank[mine]))]
+        n_send = mine.size
+        n_ghost = (n_send + 1) // 2
+        b = sub.arrays
+        nf, nb, fl = b["trk_next_fwd"].copy(), b["trk_next_bwd"].copy(), b["trk_flags"].copy()
+        k = np.arange(n_send)
+        ghost_trk, ghost_is_fwd = n_loc + k // 2, (k % 2 == 0)
+        st = new_id[src_slot[mine] // 2]
+        sd = src_slot[mine] % 2
+        f = sd == 0
+        nf[st[f]] = ghost_trk[f]
+        fl[st[f]] = (fl[st[f]] & ~np.uint8(1)) | ghost_is_fwd[f].astype(np.uint8)
+        nb[st[~f]] = ghost_trk[~f]
+        fl[st[~f]] = (fl[st[~f]] & ~np.uint8(2)) | (ghost_is_fwd[~f].astype(np.uint8) << 1)
+        assert not (nf == -2).any() and not (nb == -2).any()
+
+        def pad(key, fill, dtype=None):
+            v = b[key]
+            b[key] = np.concatenate([v, np.full(n_ghost, fill, dtype=dtype or v.dtype)])
+        b["trk_next_fwd"], b["trk_next_bwd"], b["trk_flags"] = nf, nb, fl
+        for key, fill in (("trk_next_fwd", -1), ("trk_next_bwd", -1), ("trk_flags", 0), ("trk_bc_fwd", 0),
+                          ("trk_bc_bwd", 0), ("trk_azim", 0), ("trk_polar", 0), ("trk_xy", 0),
+                          ("trk_phi", 0.0), ("trk_theta", 0.0)):
+            if key in b:
+                pad(key, fill)
+        b["trk_seg_offset"] = np.concatenate([b["trk_seg_offset"],
+                                              np.full(n_ghost, b["trk_seg_offset"][-1], dtype=np.int64)])
+        sub.n_tracks = n_loc + n_ghost
+
+        theirs = np.nonzero(dst_rank == r)[0]
+        theirs = theirs[np.lexsort((dst_slot[theirs], src_rank[theirs]))]
+        recv_slots = new_id[dst_slot[theirs] // 2] * 2 + dst_slot[theirs] % 2
+        plan = ExchangePlan(2 * n_loc, np.bincount(dst_rank[mine], minlength=world),
+                            np.bincount(src_rank[theirs], minlength=world), recv_slots)
+        out.append((sub, plan))
+    return out
+
+
+def exchange_boundary_fluxes(psi, plan: ExchangePlan, dist, group=None):
+    """One hand-off round after a sweep.  `psi` is this rank's start-flux array as a torch
+    tensor of shape [slots, F] (a zero-copy view of the device buffer on the GPU): the ghost
+    slots are sent (and cleared, so that the ghost tracks carry nothing into the next sweep and
+    its leakage tally), the received fluxes are stored to the slots the plan names.
+    Point-to-point `isend/irecv` batched in one group: NCCL send/recv over NVLink on GPUs,
+    gloo on CPUs."""
+    import torch
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    send = psi[plan.ghost0:plan.ghost0 + plan.n_send].clone()
+    psi[plan.ghost0:plan.ghost0 + plan.n_send].zero_()
+    recv = torch.empty((plan.n_recv, psi.shape[1]), dtype=psi.dtype, device=psi.device)
+    ops, so, ro = [], 0, 0
+    for q in range(world):
+        ns, nr = plan.send_counts[q], plan.recv_counts[q]
+        peer = q if group is None else dist.get_global_rank(group, q)
+        if q != rank and ns:
+            ops.append(dist.P2POp(dist.isend, send[so:so + ns], peer, group))
+        if q != rank and nr:
+            ops.append(dist.P2POp(dist.irecv, recv[ro:ro + nr], peer, group))
+        so += ns
+        ro += nr
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if plan.n_recv:
+        if not hasattr(plan, "_recv_idx") or plan._recv_idx.device != psi.device:
+            plan._recv_idx = torch.as_tensor(plan.recv_slots, device=psi.device)
+        psi.index_copy_(0, plan._recv_idx, recv)

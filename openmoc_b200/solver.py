@@ -50,7 +50,10 @@ class B200Solver:
     process_group : optional   torch.distributed group; when its world size > 1 the
                                tracks are sharded by azimuthal pair across the ranks
     partition : str            "pair": whole azimuthal reflective pairs per rank (north-star
-                               partition); "chain": whole track chains, balanced by segments
+                               partition); "chain": whole track chains, balanced by segments;
+                               "track": single tracks dealt by length, any number of ranks, the
+                               boundary fluxes that cross ranks are exchanged after every sweep
+                               (NCCL send/recv)
     deterministic : bool       accumulate the FSR tally in 64-bit fixed point: results are
                                bitwise reproducible run to run (and across GPU counts)
     """
@@ -62,6 +65,8 @@ class B200Solver:
         self._h = C.c_void_p()
         self._global_tracks = tracks
         self._dist = None
+        self._plan = None                      # ExchangePlan of partition="track"
+        self._psi_views = {}
         self._rank, self._world = 0, 1
         if use_distributed is None:
             use_distributed = process_group is not None
@@ -73,13 +78,15 @@ class B200Solver:
                 self._rank = dist.get_rank(process_group)
                 self._world = dist.get_world_size(process_group)
         if self._world > 1:
-            from .partition import partition_by_azim_pair, partition_by_chain
+            from .partition import partition_by_azim_pair, partition_by_chain, partition_by_track
             if partition == "chain":
                 tracks = partition_by_chain(tracks, self._world)[self._rank]
             elif partition == "pair":
                 tracks = partition_by_azim_pair(tracks, self._world)[self._rank]
+            elif partition == "track":
+                tracks, self._plan = partition_by_track(tracks, self._world, only=self._rank)[self._rank]
             else:
-                raise B200Error("unknown partition %r (pair, chain)" % partition)
+                raise B200Error("unknown partition %r (pair, chain, track)" % partition)
         self.tracks = tracks
         self._num_groups = tracks.num_groups
         self._num_FSRs = tracks.n_fsrs
@@ -266,6 +273,25 @@ class B200Solver:
         check(self._lib.b200_transport_sweep(self._h))
         if self._world > 1:
             self._allreduce_scalar_flux()
+            self._exchange_boundary_fluxes()
+
+    def _exchange_boundary_fluxes(self) -> None:
+        """partition="track": hand the outgoing fluxes whose next track lives on another rank
+        over (replaces CPUSolver::transferAllInterfaceFluxes, src/CPUSolver.cpp:1063-1211)."""
+        if self._plan is None:
+            return
+        import torch
+        from .partition import exchange_boundary_fluxes
+        p, n = C.c_void_p(), C.c_int64()
+        check(self._lib.b200_device_pointer(self._h, b"start_flux", C.byref(p), C.byref(n)))
+        view = self._psi_views.get(p.value)
+        if view is None:
+            self.useTorchStream()
+            with torch.cuda.device(self._device):
+                flat = torch.as_tensor(_DeviceArray(p.value, n.value, "<f4"), device=torch.device("cuda", self._device))
+            view = self._psi_views[p.value] = flat.view(-1, self.tracks.fluxes_per_track)
+        with torch.cuda.device(self._device):
+            exchange_boundary_fluxes(view, self._plan, self._dist, self._pg)
 
     def _allreduce_scalar_flux(self) -> None:
         import torch
@@ -305,12 +331,15 @@ class B200Solver:
         L, h = self._lib, self._h
         check(L.b200_eigen_loop_init(h, int(max_iters), self._converge_thresh))
         done, iters = C.c_int32(0), C.c_int32(0)
+        if self._plan is not None:
+            poll = 1          # the host moves boundary fluxes every iteration: no no-op iterations
         i = 0
         while i < max_iters and not done.value:
             end = min(max_iters, i + poll)
             while i < end:
                 check(L.b200_iteration_begin(h, i))
                 self._allreduce_scalar_flux()
+                self._exchange_boundary_fluxes()
                 check(L.b200_iteration_end(h, i, int(res_type), 1))
                 i += 1
             check(L.b200_eigen_loop_status(h, i, C.byref(done), C.byref(iters), None, None))
@@ -381,6 +410,7 @@ class B200Solver:
             for i in range(n):
                 check(self._lib.b200_iteration_begin(self._h, 1000 + i))
                 self._allreduce_scalar_flux()
+                self._exchange_boundary_fluxes()
                 check(self._lib.b200_iteration_end(self._h, 1000 + i, int(res_type), 0))
             return
         check(self._lib.b200_iterate(self._h, int(n), int(res_type), None, None))

@@ -166,7 +166,7 @@ Model hom_inf(int) {
 }
 
 /* ------- sample-input/benchmarks/c5g7/{surfaces,cells,universes,lattices,c5g7-2d}.py ------- */
-Model c5g7_2d(int) {
+Model c5g7_2d(int dims) {
   Model md;
   md.materials = make_c5g7_materials();
   std::map<std::string, Material*>& M = md.materials;
@@ -272,6 +272,13 @@ Model c5g7_2d(int) {
   Cell* root_cell = new Cell();
   root_cell->addSurface(+1, xmin); root_cell->addSurface(-1, xmax);
   root_cell->addSurface(+1, ymin); root_cell->addSurface(-1, ymax);
+  if (dims == 3) {
+    /* axially uniform ("extruded") core between the planes the 3D decks use
+     * (profile/models/c5g7/c5g7-3d-cmfd.cpp: -32.13 reflective, +32.13 vacuum) */
+    ZPlane* zmin = new ZPlane(-32.13); ZPlane* zmax = new ZPlane(32.13);
+    zmin->setBoundaryType(REFLECTIVE); zmax->setBoundaryType(VACUUM);
+    root_cell->addSurface(+1, zmin); root_cell->addSurface(-1, zmax);
+  }
   root_cell->setFill(root_lat);
   Universe* root = new Universe();
   root->addCell(root_cell);

@@ -80,8 +80,60 @@ def test_gloo_world2_matches_single_process(tmp_path):
     assert np.array_equal(np.load(os.path.join(tmp_path, "phi0.npy")), np.load(os.path.join(tmp_path, "phi1.npy")))
 
 
+def _cpu_worker_track(rank, world, port, out_dir):
+    """partition_by_track + the isend/irecv exchange of boundary fluxes, over gloo"""
+    import sys
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    from openmoc_b200.partition import partition_by_track, exchange_boundary_fluxes
+    from oracle.oracle_py import OracleSolver, FISSION_SOURCE
+    ft = _tracks()
+    part, plan = partition_by_track(ft, world)[rank]
+    F = part.fluxes_per_track
+    s = OracleSolver(part)
+    s.setKeff(1.0); s.zeroTrackFluxes()
+    s.flattenFSRFluxes(0.0); s.storeFSRFluxes()
+    s.flattenFSRFluxes(1.0); s.normalizeFluxes(); s.storeFSRFluxes()
+    k_prev, iters = 1.0, 0
+    for i in range(400):
+        s.computeFSRSources(i)
+        s.transportSweep()
+        phi = torch.from_numpy(s.getFluxes())
+        dist.all_reduce(phi, op=dist.ReduceOp.SUM)
+        s.setFluxes(phi.numpy())
+        psi = torch.from_numpy(s.getStartFluxes()).view(-1, F)
+        exchange_boundary_fluxes(psi, plan, dist)
+        s.setStartFluxes(psi.numpy().ravel())
+        s.addSourceToScalarFlux()
+        s.computeKeff(); k = s.getKeff()
+        s.normalizeFluxes()
+        res = s.computeResidual(FISSION_SOURCE)
+        dk = int(1e5 * (k - k_prev)); k_prev = k
+        s.storeFSRFluxes(); iters += 1
+        if res < 1e-5 and abs(dk) < 1:
+            break
+    np.save(os.path.join(out_dir, f"phi{rank}.npy"), s.getFluxes())
+    np.save(os.path.join(out_dir, f"k{rank}.npy"), np.array([s.getKeff(), iters]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_track_partition_with_flux_exchange(tmp_path, world):
+    from oracle.oracle_py import OracleSolver, FISSION_SOURCE
+    port = _free_port()
+    mp.spawn(_cpu_worker_track, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    ref = OracleSolver(_tracks())
+    n = ref.computeEigenvalue(400, 1e-5, FISSION_SOURCE)
+    for r in range(world):
+        k, iters = np.load(os.path.join(tmp_path, f"k{r}.npy"))
+        phi = np.load(os.path.join(tmp_path, f"phi{r}.npy"))
+        assert int(iters) == n
+        assert abs(k - ref.getKeff()) * 1e5 < 1e-4
+        np.testing.assert_allclose(phi, ref.getFluxes(), rtol=1e-8)
+
+
 # ------------------------------------------------------------------ nccl / GPU
-def _gpu_worker(rank, world, port, out_dir):
+def _gpu_worker(rank, world, port, out_dir, partition="pair"):
     import sys
     sys.path.insert(0, ROOT)
     torch.cuda.set_device(rank)
@@ -89,7 +141,7 @@ def _gpu_worker(rank, world, port, out_dir):
                             device_id=torch.device("cuda", rank))
     from openmoc_b200.solver import B200Solver
     from openmoc_b200.capi import FISSION_SOURCE
-    s = B200Solver(_tracks(), device=rank, process_group=dist.group.WORLD)
+    s = B200Solver(_tracks(), device=rank, process_group=dist.group.WORLD, partition=partition)
     s.setConvergenceThreshold(1e-5)
     s.computeEigenvalue(400, FISSION_SOURCE)
     np.save(os.path.join(out_dir, f"phi{rank}.npy"), s.getFluxes())
@@ -98,13 +150,14 @@ def _gpu_worker(rank, world, port, out_dir):
 
 
 @pytest.mark.gpu
-def test_nccl_world2_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("partition", ["pair", "chain", "track"])
+def test_nccl_world2_matches_single_gpu(tmp_path, partition):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     from openmoc_b200.solver import B200Solver
     from openmoc_b200.capi import FISSION_SOURCE
     port = _free_port()
-    mp.spawn(_gpu_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_gpu_worker, args=(2, port, str(tmp_path), partition), nprocs=2, join=True)
     one = B200Solver(_tracks())
     one.setConvergenceThreshold(1e-5)
     one.computeEigenvalue(400, FISSION_SOURCE)

@@ -31,6 +31,9 @@ def run(args):
       "--zspacing", "0.9", "--formation", "otf-stacks"], None),                               # OTF_STACKS flattening
     (["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
       "--zspacing", "0.9", "--formation", "explicit"], None),                                 # EXPLICIT_3D flattening
+    # configs[4] shape at coarse tracks: extruded 3D C5G7 core, OTF_STACKS
+    (["--model", "c5g7-2d", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "1.0", "--zspacing", "10",
+      "--formation", "otf-stacks", "--max-iters", "25", "--threads", "4"], None),
 ])
 def test_b200solver_matches_cpusolver_in_process(args, iters):
     r = run(args + ["--solver", "both"])
@@ -93,6 +96,9 @@ def test_linear_source_reference_golden_from_gpu(tmp_path):
      "--zspacing", "0.9", "--cmfd", "2x2x2"],
     ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
      "--zspacing", "0.9", "--cmfd", "2x2x2", "--ls", "--formation", "otf-stacks"],
+    # configs[4]: 3D C5G7, OTF_STACKS, linear source, CMFD 51x51x3
+    ["--model", "c5g7-2d", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "1.0", "--zspacing", "10",
+     "--formation", "otf-stacks", "--cmfd", "51x51x3", "--ls", "--max-iters", "20", "--threads", "1"],
 ])
 def test_cmfd_accelerated_solve_matches_reference(args):
     """Surface currents tallied in the sweep kernel feed the reference's own host Cmfd

@@ -156,3 +156,71 @@ def test_chain_partition_is_closed_balanced_and_sums_to_whole():
     np.testing.assert_allclose(total, whole.getFluxes(), rtol=1e-12, atol=1e-13)
     with pytest.raises(ValueError):
         partition_by_chain(ft, 1000)
+
+
+# ------------------------------------------------ track partition with psi exchange
+def _simulate_track_partition(ft, world, n_iter):
+    """All ranks of partition_by_track in one process, the exchange done by hand with the
+    plan's index lists: must reproduce the single-solver iteration exactly."""
+    from openmoc_b200.partition import partition_by_track
+    from oracle.oracle_py import OracleSolver
+    parts = partition_by_track(ft, world)
+    F = ft.fluxes_per_track
+    solvers = [OracleSolver(sub) for sub, _ in parts]
+    plans = [p for _, p in parts]
+    for s in solvers:
+        s.setKeff(1.0); s.zeroTrackFluxes()
+        s.flattenFSRFluxes(0.0); s.storeFSRFluxes()
+        s.flattenFSRFluxes(1.0); s.normalizeFluxes(); s.storeFSRFluxes()
+    for i in range(n_iter):
+        for s in solvers:
+            s.computeFSRSources(i); s.transportSweep()
+        phi = sum(s.getFluxes() for s in solvers)
+        psi = [s.getStartFluxes().reshape(-1, F) for s in solvers]
+        # send buffers = ghost slots, grouped by destination rank
+        outbox = {}
+        for r, p in enumerate(plans):
+            off = p.ghost0
+            for q in range(world):
+                outbox[(r, q)] = psi[r][off:off + p.send_counts[q]].copy()
+                off += p.send_counts[q]
+            psi[r][p.ghost0:p.ghost0 + p.n_send] = 0.0
+        for q, p in enumerate(plans):
+            recv = np.concatenate([outbox[(r, q)] for r in range(world)]) if p.n_recv else np.zeros((0, F), np.float32)
+            assert recv.shape[0] == p.n_recv and [outbox[(r, q)].shape[0] for r in range(world)] == p.recv_counts
+            psi[q][p.recv_slots] = recv
+        for s, ps in zip(solvers, psi):
+            s.setStartFluxes(ps.ravel()); s.setFluxes(phi)
+            s.addSourceToScalarFlux(); s.computeKeff(); s.normalizeFluxes(); s.storeFSRFluxes()
+    return solvers[0].getKeff(), solvers[0].getFluxes()
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_track_partition_with_flux_exchange_equals_single_solver(world):
+    from ragged import make_ragged
+    from openmoc_b200.synth import make_tracks
+    from oracle.oracle_py import OracleSolver
+    for ft in (make_tracks("simple-lattice", num_azim=4, spacing=0.2), make_ragged(G=3, NP=2, seed=4, n_tracks=60)):
+        k, phi = _simulate_track_partition(ft, world, 12)
+        ref = OracleSolver(ft)
+        ref.computeEigenvalue(12, 1e-30)
+        assert abs(k - ref.getKeff()) < 1e-12
+        np.testing.assert_allclose(phi, ref.getFluxes(), rtol=1e-11, atol=1e-14)
+
+
+def test_track_partition_balance_and_plan_consistency():
+    from openmoc_b200.partition import partition_by_track
+    from openmoc_b200.synth import make_tracks
+    ft = make_tracks("simple-lattice", num_azim=8, spacing=0.1)
+    for world in (2, 8):
+        parts = partition_by_track(ft, world)
+        segs = [sub.n_segments for sub, _ in parts]
+        assert sum(segs) == ft.n_segments and max(segs) - min(segs) <= np.diff(ft.trk_seg_offset).max()
+        for r, (sub, plan) in enumerate(parts):
+            sub.validate()
+            assert plan.send_counts[r] == 0 and plan.recv_counts[r] == 0
+            assert len(set(plan.recv_slots.tolist())) == plan.n_recv          # every slot fed once
+            assert plan.ghost0 + plan.n_send <= 2 * sub.n_tracks
+        for r in range(world):
+            for q in range(world):
+                assert parts[r][1].send_counts[q] == parts[q][1].recv_counts[r]
