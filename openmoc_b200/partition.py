@@ -264,9 +264,19 @@ def exchange_boundary_fluxes(psi, plan: ExchangePlan, dist, group=None):
     import torch
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
-    send = psi[plan.ghost0:plan.ghost0 + plan.n_send].clone()
-    psi[plan.ghost0:plan.ghost0 + plan.n_send].zero_()
-    recv = torch.empty((plan.n_recv, psi.shape[1]), dtype=psi.dtype, device=psi.device)
+    # persistent staging buffers: allocating per call would make torch's caching allocator
+    # fall back to cudaMalloc (a device-wide sync) whenever the host runs ahead of the GPU,
+    # because blocks still in use on NCCL's stream cannot be recycled
+    key = (psi.device, psi.dtype, psi.shape[1])
+    if getattr(plan, "_key", None) != key:
+        plan._key = key
+        plan._send = torch.empty((plan.n_send, psi.shape[1]), dtype=psi.dtype, device=psi.device)
+        plan._recv = torch.empty((plan.n_recv, psi.shape[1]), dtype=psi.dtype, device=psi.device)
+        plan._recv_idx = torch.as_tensor(plan.recv_slots, device=psi.device)
+    send, recv = plan._send, plan._recv
+    ghosts = psi[plan.ghost0:plan.ghost0 + plan.n_send]
+    send.copy_(ghosts)
+    ghosts.zero_()
     ops, so, ro = [], 0, 0
     for q in range(world):
         ns, nr = plan.send_counts[q], plan.recv_counts[q]
@@ -281,6 +291,4 @@ def exchange_boundary_fluxes(psi, plan: ExchangePlan, dist, group=None):
         for req in dist.batch_isend_irecv(ops):
             req.wait()
     if plan.n_recv:
-        if not hasattr(plan, "_recv_idx") or plan._recv_idx.device != psi.device:
-            plan._recv_idx = torch.as_tensor(plan.recv_slots, device=psi.device)
         psi.index_copy_(0, plan._recv_idx, recv)
