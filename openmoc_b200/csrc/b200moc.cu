@@ -784,7 +784,17 @@ static int launch_sweep(b200_solver* s) {
       for (int k = 0; k < 11; k++) a.cf[k] = cf[k];
     }
     const bool mixed = s->cfg.precision == B200_PRECISION_MIXED;
-    const int nthr = s->lpi * s->ipc;
+    int nthr = s->lpi * s->ipc;
+    int64_t nblk = s->sweep_blocks;
+    /* items may straddle CTAs as well as warps (no CTA-level cooperation), so any block size
+     * works; B200_CTA overrides the default of LPI x IPC threads (tuning hook) */
+    if (const char* e = getenv("B200_CTA")) {
+      const int v = atoi(e);
+      if (v >= 32 && v <= 1024 && !s->linear) {
+        nthr = v;
+        nblk = (2 * s->n_trk * (int64_t)s->lpi + nthr - 1) / nthr;
+      }
+    }
     if (s->linear) {
       if (s->balance) return fail("k_eff from the neutron balance is not available with the linear source in this build");
       SweepLSArgs la;
@@ -833,7 +843,7 @@ static int launch_sweep(b200_solver* s) {
       fn = mixed ? pick_np<float, false, false>(s->NP, s->gpl) : pick_np<double, false, false>(s->NP, s->gpl);
     }
     if (fn == nullptr) return fail("no sweep kernel for NP=%d GPL=%d", s->NP, s->gpl);
-    fn<<<(unsigned)s->sweep_blocks, nthr, 0, s->stream>>>(a);
+    fn<<<(unsigned)nblk, nthr, 0, s->stream>>>(a);
     CU(cudaGetLastError());
     s->n_launches++;
     }

@@ -296,7 +296,11 @@ __global__ void fold_replicas_kernel(V* __restrict__ base, int64_t n, int64_t st
  * small-G shapes four CTAs per SM (28 warps) are worth more than registers: the
  * bound caps the kernel at 72 registers. */
 template <typename T, int NP, int GPL, bool DET, bool CMFD>
-__global__ void __launch_bounds__(224, (GPL == 1 && NP <= 3 && !CMFD) ? 4 : 1)
+#ifndef B200_LB_THREADS
+#define B200_LB_THREADS 224
+#define B200_LB_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(B200_LB_THREADS, (GPL == 1 && NP <= 3 && !CMFD) ? B200_LB_BLOCKS : 1)
 sweep_kernel(const SweepArgs a) {
   if (a.done != nullptr && *a.done) return;
   /* flat mapping: LPI consecutive threads own one item; an item may straddle two
