@@ -612,6 +612,7 @@ extern "C" int b200_finalize(b200_solver* s) {
       if (v >= 1 && v <= 1024 && (v & (v - 1)) == 0) R = v;
     }
     while (R > 1 && (double)nphi * 8.0 * (s->linear ? 4.0 : 1.0) * R > 256e6) R /= 2;
+    while (R > 1 && (double)nphi * R >= 4294967296.0) R /= 2;      /* 32-bit tally index incl. replica */
     s->n_rep = R;
   }
   CU(s->phi.alloc(nphi * s->n_rep)); CU(s->phi_old.alloc(nphi)); CU(s->fixed.alloc(nphi));

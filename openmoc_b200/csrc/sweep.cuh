@@ -376,9 +376,14 @@ sweep_kernel(const SweepArgs a) {
   for (int j = 0; j < GPL; j++) qs0[j] = ld_qs(&a.qst[b0 + e[j]]);
   ps += 2 * step;
 
-  const int64_t rep_off = (int64_t)(blockIdx.x & a.rep_mask) * a.rep_stride;
-  double* __restrict__ const phi = a.phi + rep_off;
-  [[maybe_unused]] unsigned long long* __restrict__ const phi_fx = DET ? a.phi_fx + rep_off : nullptr;
+  /* tally replica of this CTA, folded into the 32-bit group index (n_rep * N_FSR * G < 2^32 is
+   * checked at finalize): the RED address stays one 32-bit add and one IMAD.WIDE off a uniform base */
+  const uint32_t rep_idx = (uint32_t)(blockIdx.x & a.rep_mask) * (uint32_t)a.rep_stride;
+  uint32_t et[GPL];
+#pragma unroll
+  for (int j = 0; j < GPL; j++) et[j] = e[j] + rep_idx;
+  double* __restrict__ const phi = a.phi;
+  [[maybe_unused]] unsigned long long* __restrict__ const phi_fx = DET ? a.phi_fx : nullptr;
   const double fx_scale = DET ? *a.fx_scale : 0.0;
   [[maybe_unused]] const int2* __restrict__ pc = CMFD ? a.seg_cmfd + (dir ? s1 - 1 : s0) : nullptr;
   [[maybe_unused]] int cg[GPL];
@@ -460,9 +465,9 @@ sweep_kernel(const SweepArgs a) {
       for (int j = 0; j < GPL; j++) {
         if constexpr (DET) {
           if (flush && valid[j])
-            atomicAdd(&phi_fx[b0 + e[j]], (unsigned long long)__double2ll_rn(acc[j] * fx_scale));
+            atomicAdd(&phi_fx[b0 + et[j]], (unsigned long long)__double2ll_rn(acc[j] * fx_scale));
         } else {
-          red_add_if(&phi[b0 + e[j]], acc[j], flush && valid[j]);   /* predicated RED, no branch */
+          red_add_if(&phi[b0 + et[j]], acc[j], flush && valid[j]);   /* predicated RED, no branch */
         }
         acc[j] = flush ? 0.0 : acc[j];
       }
@@ -480,8 +485,8 @@ sweep_kernel(const SweepArgs a) {
 #pragma unroll
     for (int j = 0; j < GPL; j++)
       if (valid[j] && acc[j] != 0.0) {
-        if constexpr (DET) atomicAdd(&phi_fx[blast + e[j]], (unsigned long long)__double2ll_rn(acc[j] * fx_scale));
-        else atomicAdd(&phi[blast + e[j]], acc[j]);
+        if constexpr (DET) atomicAdd(&phi_fx[blast + et[j]], (unsigned long long)__double2ll_rn(acc[j] * fx_scale));
+        else atomicAdd(&phi[blast + et[j]], acc[j]);
       }
   }
 
