@@ -322,7 +322,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "b200::sweep_kernel", "bytes_per_integration": b_alg,
                          "kernel_ms": sweep_avg_ms, "kernel_share_of_step": sweep_ms / ms if ms > 0 else None,
-                         "note": "FP64-issue bound, not HBM bound, for G*P/2=21 (SURVEY 8d): 23 FP64 instr per integration vs "
+                         "note": "FP64-issue bound, not HBM bound, for G*P/2=21 (SURVEY 8d): 22 FP64 instr per integration vs "
                                  "0.34 algorithmic bytes; see DESIGN.md 4.1 and profiles/"},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "integrations/s", "h2d_bytes_per_step": n_phi * 8,
