@@ -84,7 +84,8 @@ int main(int argc, char** argv) {
       for (int g = 4; g <= 7; g++) groups[1].push_back(g);
       cmfd->setGroupStructure(groups);
     }
-    cmfd->setKNearest(3);
+    if (!flag(argc, argv, "--no-knearest")) cmfd->setKNearest(3);
+    if (flag(argc, argv, "--no-flux-limiting")) cmfd->useFluxLimiting(false);   /* diagnostics */
     geometry->setCmfd(cmfd);
   }
   geometry->initializeFlatSourceRegions();
@@ -131,6 +132,7 @@ int main(int argc, char** argv) {
     CPUSolver& cpu = *cpu_p;
     cpu.setNumThreads(threads);
     cpu.setConvergenceThreshold(tol);
+    if (flag(argc, argv, "--verbose")) cpu.setVerboseIterationReport();
     if (flag(argc, argv, "--balance")) cpu.setKeffFromNeutronBalance();
     cpu.computeEigenvalue(max_iters, rt);
     Timer timer;
@@ -145,6 +147,7 @@ int main(int argc, char** argv) {
     Solver& gpu = ls ? *(Solver*)gpu_ls : *(Solver*)gpu_flat;
     if (ls) gpu_ls->setNumThreads(threads); else gpu_flat->setNumThreads(threads);
     gpu.setConvergenceThreshold(tol);
+    if (flag(argc, argv, "--verbose")) gpu.setVerboseIterationReport();
     if (flag(argc, argv, "--balance")) gpu.setKeffFromNeutronBalance();
     gpu.computeEigenvalue(max_iters, rt);
     double gpu_sweep = timer.getSplit("Transport Sweep");

@@ -96,9 +96,6 @@ def test_linear_source_reference_golden_from_gpu(tmp_path):
      "--zspacing", "0.9", "--cmfd", "2x2x2"],
     ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
      "--zspacing", "0.9", "--cmfd", "2x2x2", "--ls", "--formation", "otf-stacks"],
-    # configs[4]: 3D C5G7, OTF_STACKS, linear source, CMFD 51x51x3
-    ["--model", "c5g7-2d", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "1.0", "--zspacing", "10",
-     "--formation", "otf-stacks", "--cmfd", "51x51x3", "--ls", "--max-iters", "20", "--threads", "1"],
 ])
 def test_cmfd_accelerated_solve_matches_reference(args):
     """Surface currents tallied in the sweep kernel feed the reference's own host Cmfd
@@ -107,13 +104,32 @@ def test_cmfd_accelerated_solve_matches_reference(args):
     r = run(args + ["--solver", "both"])
     assert r["b200_iters"] == r["cpu_iters"]
     assert r["dk_pcm"] < 1.0 and r["max_rel_flux_err"] < 1e-4          # north_star
-    # CMFD prolongation amplifies summation-order noise (the flat solver moves by ~5e-6 between
-    # 1 and 8 OpenMP threads); still far inside the tolerance.  Exception: linear source + CMFD on
-    # the coarse 3D C5G7 deck is held to the north-star bound only.  Measured after 20 (unconverged)
-    # iterations: 0.05 pcm / 5.5e-5 with CMFD 51x51x3, 1e-3 pcm / 1.6e-6 with CMFD 3x3x3, against
-    # 2e-11 pcm / 1e-13 for the same linear-source solve without CMFD and 3e-6 pcm / 1e-7 for the
-    # flat source with CMFD 51x51x3.  Why the CMFD amplifies the LS path's rounding differences this
-    # much more is open (candidate: the flux-limiting switch |D~/D^| > 1, Cmfd.cpp:1148, met more
-    # often without Larsen's correction, Cmfd.cpp:1069); DESIGN.md section 2 lists it.
-    if not ("c5g7-2d" in args and "--ls" in args):
-        assert r["dk_pcm"] < 1e-2 and r["max_rel_flux_err"] < 2e-5
+    # CMFD prolongation amplifies summation-order noise (the reference itself moves by ~5e-6 between
+    # 1 and 8 OpenMP threads); still far inside the tolerance
+    assert r["dk_pcm"] < 1e-2 and r["max_rel_flux_err"] < 2e-5
+
+
+def test_3d_c5g7_linear_source_cmfd_in_separate_processes(tmp_path):
+    """configs[4] shape at coarse tracks: extruded 3D C5G7, OTF_STACKS, CPULSSolver, CMFD 51x51x3.
+    Run in two fresh processes: `--solver both` shares one Cmfd object between the two solves and
+    the second solve (whichever solver runs it) inherits state from the first - measured 0.05 pcm on
+    this strongly oscillating, unconverged deck against 2e-11 pcm between fresh processes."""
+    import numpy as np
+    args = ["--model", "c5g7-2d", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "1.0",
+            "--zspacing", "10", "--formation", "otf-stacks", "--cmfd", "51x51x3", "--max-iters", "20",
+            "--threads", "1", "--quiet", "--no-fluxes"]      # one thread: same FSR numbering in both runs
+    if not os.path.exists(DRIVER):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    res = {}
+    for solver in ("cpuls", "b200ls"):
+        js = os.path.join(tmp_path, solver + ".json")
+        subprocess.run([DRIVER] + args + ["--solver", solver, "--json", js], check=True, capture_output=True)
+        res[solver] = json.load(open(js))
+    a, b = res["cpuls"], res["b200ls"]
+    assert a["iterations"] == b["iterations"] == 20
+    dk_pcm = abs(a["keff"] - b["keff"]) * 1e5
+    fa, fb = np.array(a["fluxes"]), np.array(b["fluxes"])
+    err = np.max(np.abs(fa - fb) / np.abs(fa))
+    print("3D C5G7 LS + CMFD: dk = %.3e pcm, max rel flux err = %.3e" % (dk_pcm, err))
+    assert dk_pcm < 1.0 and err < 1e-4           # north_star
+    assert dk_pcm < 1e-3 and err < 1e-6          # achieved: ~1e-11 pcm
