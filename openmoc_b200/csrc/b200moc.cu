@@ -120,6 +120,9 @@ struct b200_solver {
   DevBuf<int32_t> seg_fsr;
   DevBuf<SegRec> seg_rec;
   int n_rep = 1;                      /* tally replicas */
+  bool capturing = false;             /* inside cudaStreamBeginCapture: no events, no host syncs */
+  cudaGraphExec_t iter_graph = nullptr;   /* two fused source iterations (one per psi buffer parity) */
+  int iter_graph_res = -1; const float* iter_graph_psi = nullptr; int64_t iter_graph_launches = 0;
   DevBuf<int64_t> trk_off, out_slot;
   DevBuf<int32_t> trk_class, order;
   DevBuf<uint8_t> carry;
@@ -308,6 +311,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   if (s == nullptr) return 0;
   cudaSetDevice(s->cfg.device);
   cudaStreamSynchronize(s->stream);
+  if (s->iter_graph != nullptr) cudaGraphExecDestroy(s->iter_graph);
   for (auto& p : s->ev_pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto& p : s->ev_free) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   s->seg_len.release(); s->seg_fsr.release(); s->seg_rec.release(); s->trk_off.release(); s->out_slot.release();
@@ -733,9 +737,11 @@ static int resolve_events(b200_solver* s) {
  * boundary (here: read psi_start, write the other buffer), sweep. */
 static int launch_sweep(b200_solver* s) {
   const size_t nphi = (size_t)s->n_fsr * s->G;
-  cudaEvent_t e0, e1;
-  if (take_events(s, &e0, &e1)) return 1;
-  CU(cudaEventRecord(e0, s->stream));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (!s->capturing) {
+    if (take_events(s, &e0, &e1)) return 1;
+    CU(cudaEventRecord(e0, s->stream));
+  }
   /* flattenFSRFluxes(0) (CPUSolver.cpp:2347), skipped once the device-side loop has converged */
   zero_phi_kernel<<<grid_for(nphi, 256), 256, 0, s->stream>>>(s->phi.p, (int64_t)nphi, s->iscal.p);
   CU(cudaGetLastError());
@@ -864,9 +870,11 @@ static int launch_sweep(b200_solver* s) {
     CU(cudaGetLastError());
     s->n_launches++;
   }
-  CU(cudaEventRecord(e1, s->stream));
-  s->ev_pending.push_back({e0, e1});
-  if (s->ev_pending.size() >= 512) { if (resolve_events(s)) return 1; }
+  if (!s->capturing) {
+    CU(cudaEventRecord(e1, s->stream));
+    s->ev_pending.push_back({e0, e1});
+    if (s->ev_pending.size() >= 512) { if (resolve_events(s)) return 1; }
+  }
   std::swap(s->psi_start, s->psi_other);
   s->n_sweeps++;
   return 0;
@@ -1292,6 +1300,42 @@ static int prepare_history(b200_solver* s, int max_iters) {
   return 0;
 }
 
+/* Launch-bound decks (a sweep of a few tens of microseconds followed by eight small FSR
+ * kernels) replay the fused iteration as a CUDA graph: two iterations per graph, one for each
+ * parity of the psi double buffer; the kernels read the iteration number from the device-side
+ * counter (iteration argument -1).  B200_GRAPH=0/1 forces it off/on; by default decks with fewer
+ * than 1e8 integrations per sweep use it. */
+static bool want_graph(const b200_solver* s) {
+  if (!s->own_stream) return false;      /* a borrowed stream may be the legacy default stream: no capture */
+  if (const char* e = getenv("B200_GRAPH")) return atoi(e) != 0;
+  return 2.0 * s->F * (double)s->n_seg < 1e8;
+}
+static void drop_iter_graph(b200_solver* s) {
+  if (s->iter_graph != nullptr) cudaGraphExecDestroy(s->iter_graph);
+  s->iter_graph = nullptr;
+}
+static int build_iter_graph(b200_solver* s, int res_type) {
+  if (s->iter_graph != nullptr && s->iter_graph_res == res_type && s->iter_graph_psi == s->psi_start) return 0;
+  drop_iter_graph(s);
+  cudaGraph_t g = nullptr;
+  const int64_t l0 = s->n_launches, w0 = s->n_sweeps;
+  CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+  s->capturing = true;
+  int rc = enqueue_eigen_iteration(s, -1, res_type, 1) || enqueue_eigen_iteration(s, -1, res_type, 1);
+  s->capturing = false;
+  cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+  s->iter_graph_launches = s->n_launches - l0;
+  s->n_launches = l0; s->n_sweeps = w0;            /* nothing has run yet */
+  if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+  CU(e);
+  e = cudaGraphInstantiate(&s->iter_graph, g, 0);
+  cudaGraphDestroy(g);
+  CU(e);
+  s->iter_graph_res = res_type;
+  s->iter_graph_psi = s->psi_start;                /* the buffers are baked into the graph */
+  return 0;
+}
+
 extern "C" int b200_compute_eigenvalue(b200_solver* s, int32_t max_iters, double tol, int32_t res_type,
                                        int32_t* num_iterations) {
   NEED_FINAL(s);
@@ -1299,6 +1343,7 @@ extern "C" int b200_compute_eigenvalue(b200_solver* s, int32_t max_iters, double
   if (res_type == B200_RES_FISSION_SOURCE && s->n_fissionable == 0)
     return fail("The Solver is unable to compute a FISSION_SOURCE residual without fissionable FSRs");
   if (prepare_history(s, max_iters)) return 1;
+  drop_iter_graph(s);     /* solver settings are baked into the captured launches: one graph per solve */
   /* _k_eff = 1, flux arrays zeroed, flat unit flux guess normalised and stored
    * (Solver.cpp:1566-1600, computeInitialFluxGuess :1710-1731) */
   double init[SC_COUNT_D] = {0};
@@ -1313,14 +1358,33 @@ extern "C" int b200_compute_eigenvalue(b200_solver* s, int32_t max_iters, double
   if (b200_store_fsr_fluxes(s)) return 1;
 
   const int batch = 8;
-  int done = 0, i = 0;
+  int done = 0, i = 0, flips = 0;      /* flips: host-side swaps of the psi buffers (plain launches) */
+  const bool graph = want_graph(s) && max_iters > 4;
   while (i < max_iters && !done) {
     const int end = std::min(max_iters, i + batch);
-    for (; i < end; i++)
+    if (graph && i >= 2) {
+      /* iterations 0 and 1 ran as plain launches (iteration 0 differs when stabilisation is on) */
+      if (build_iter_graph(s, res_type)) return 1;
+      cudaEvent_t e0, e1;
+      if (take_events(s, &e0, &e1)) return 1;
+      CU(cudaEventRecord(e0, s->stream));
+      for (; i + 2 <= end; i += 2) {
+        CU(cudaGraphLaunch(s->iter_graph, s->stream));
+        s->n_launches += s->iter_graph_launches;
+        s->n_sweeps += 2;
+      }
+      /* graph mode times whole iterations: the "sweep" split then includes the FSR kernels */
+      CU(cudaEventRecord(e1, s->stream));
+      s->ev_pending.push_back({e0, e1});
+    }
+    for (; i < end; i++, flips++)
       if (enqueue_eigen_iteration(s, i, res_type, 1)) return 1;
     if (fetch_scalars(s)) return 1;
     done = s->h_iscal[SI_DONE];
   }
+  /* graph iterations come in pairs, so the parity of (enqueued - executed) is also the parity
+   * of (host-side buffer swaps - executed) */
+  (void)flips;
   fix_psi_parity(s, i, s->h_iscal[SI_EXEC]);
   if (num_iterations) *num_iterations = s->h_iscal[SI_ITERS];
   if (clear_done(s)) return 1;

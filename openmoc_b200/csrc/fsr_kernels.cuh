@@ -87,6 +87,7 @@ __device__ __forceinline__ double fold_partials(const double* partials, int n) {
 __global__ void __launch_bounds__(256)
 sources_kernel(const FsrArgs a, int iteration, int mode, int neg_allowed) {
   if (a.iscal[SI_DONE]) return;
+  if (iteration < 0) iteration = a.iscal[SI_EXEC];     /* CUDA-graph replay: device-side counter */
   const int G = a.G;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.n_fsr * G) return;
@@ -322,6 +323,7 @@ residual_finalize_kernel(const FsrArgs a, int n_partials, int res_type, int loop
   if (a.iscal[SI_DONE]) return;
   double residual = fold_partials(a.partials, n_partials);
   if (threadIdx.x == 0) {
+    if (iteration < 0) iteration = a.iscal[SI_EXEC];   /* CUDA-graph replay: device-side counter */
     int64_t norm = (res_type == 1) ? a.n_fissionable : a.n_fsr_global;
     if (residual < 0.0) residual = 0.0;
     if (norm <= 0) norm = 1;
@@ -511,6 +513,7 @@ struct LsArgs {
 __global__ void __launch_bounds__(256)
 sources_ls_kernel(const FsrArgs a, const LsArgs l, int iteration, int neg_allowed) {
   if (a.iscal[SI_DONE]) return;
+  if (iteration < 0) iteration = a.iscal[SI_EXEC];
   const int G = a.G;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.n_fsr * G) return;

@@ -322,3 +322,27 @@ def test_sweep_stats_count_integrations():
     ms, n_sweeps, launches = gpu.getSweepStats()
     assert n_sweeps == 5 and launches >= 5 and ms > 0
     assert gpu.integrationsPerSweep() == 2 * 21 * 1984
+
+
+@pytest.mark.parametrize("max_iters", [1000, 37, 5, 6])
+def test_cuda_graph_replay_equals_plain_launches(monkeypatch, max_iters):
+    """b200_compute_eigenvalue replays two fused iterations as a CUDA graph on launch-bound decks
+    (B200_GRAPH=1 forces it): same iteration count, k_eff and fluxes as the plain launches, also
+    when max_iters is odd (a trailing plain iteration) or the loop stops inside a graph pair."""
+    from openmoc_b200.solver import B200Solver
+    ft, _ = load_case("simple_lattice")
+    res = {}
+    for g in ("0", "1"):
+        monkeypatch.setenv("B200_GRAPH", g)
+        s = B200Solver(ft)
+        s.setConvergenceThreshold(1e-5)
+        s.computeEigenvalue(max_iters)
+        first = (s.getNumIterations(), s.getKeff(), s.getFluxes(), s.getStartFluxes())
+        s.computeEigenvalue(max_iters)          # a second solve on the same handle re-captures
+        assert s.getNumIterations() == first[0] and abs(s.getKeff() - first[1]) < 1e-12
+        res[g] = first
+    a, b = res["0"], res["1"]
+    assert a[0] == b[0]
+    assert abs(a[1] - b[1]) < 1e-12
+    np.testing.assert_allclose(b[2], a[2], rtol=1e-11)
+    np.testing.assert_allclose(b[3], a[3], rtol=1e-5, atol=1e-12)     # boundary fluxes: buffer parity is right
