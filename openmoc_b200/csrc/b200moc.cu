@@ -616,7 +616,7 @@ extern "C" int b200_finalize(b200_solver* s) {
       if (v >= 1 && v <= 1024 && (v & (v - 1)) == 0) R = v;
     }
     while (R > 1 && (double)nphi * 8.0 * (s->linear ? 4.0 : 1.0) * R > 256e6) R /= 2;
-    while (R > 1 && (double)nphi * R >= 4294967296.0) R /= 2;      /* 32-bit tally index incl. replica */
+    while (R > 1 && (double)nphi * R * (s->linear ? 3.0 : 1.0) >= 4294967296.0) R /= 2;   /* 32-bit tally index incl. replica */
     s->n_rep = R;
   }
   CU(s->phi.alloc(nphi * s->n_rep)); CU(s->phi_old.alloc(nphi)); CU(s->fixed.alloc(nphi));
@@ -643,7 +643,7 @@ extern "C" int b200_finalize(b200_solver* s) {
   s->psi_other = s->psi_b.p;
 
   /* device segment stream: padded 16-byte records with the FSR id premultiplied by G */
-  if ((double)s->n_fsr * s->G >= 4294967296.0)
+  if ((double)s->n_fsr * s->G * (s->linear ? 3.0 : 1.0) >= 4294967296.0)
     return fail("b200_finalize: n_fsrs*G = %.3g exceeds the 32-bit tally index of this build", (double)s->n_fsr * s->G);
   if (s->seg_len.n != (size_t)s->n_seg) return fail("b200_finalize: tracks must be re-uploaded before finalize");
   CU(s->seg_rec.alloc((size_t)s->n_seg + 2 * SEG_PAD));
@@ -1250,8 +1250,9 @@ extern "C" int b200_set_start_fluxes(b200_solver* s, const float* in, int64_t n)
 /* fused drivers                                                              */
 /* ------------------------------------------------------------------------- */
 /* one source iteration of Solver::computeEigenvalue (src/Solver.cpp:1614-1681) */
+/* i < 0: captured into the CUDA graph (iterations >= 2, number read from the device counter) */
 static int enqueue_iteration_begin(b200_solver* s, int i) {
-  if (i > 0 && s->stabilize) { if (b200_compute_stabilizing_flux(s)) return 1; }
+  if (i != 0 && s->stabilize) { if (b200_compute_stabilizing_flux(s)) return 1; }
   if (launch_sources(s, i, 0)) return 1;
   return launch_sweep(s);
 }
@@ -1261,7 +1262,7 @@ static int enqueue_iteration_end(b200_solver* s, int i, int res_type, int loop_k
   if (s->balance) {
     if (launch_closure(s, 0, nullptr)) return 1;
     if (launch_balance_keff(s)) return 1;
-    if (i > 0 && s->stabilize) { if (b200_stabilize_flux(s)) return 1; }
+    if (i != 0 && s->stabilize) { if (b200_stabilize_flux(s)) return 1; }
     if (launch_rate(s, 2)) return 1;
   } else if (!s->stabilize) {
     /* closure + the one nu-fission reduction that feeds both computeKeff and
@@ -1274,7 +1275,7 @@ static int enqueue_iteration_end(b200_solver* s, int i, int res_type, int loop_k
   } else {
     if (launch_closure(s, 0, nullptr)) return 1;
     if (launch_rate(s, 1)) return 1;
-    if (i > 0) { if (b200_stabilize_flux(s)) return 1; }
+    if (i != 0) { if (b200_stabilize_flux(s)) return 1; }
     if (launch_rate(s, 2)) return 1;
   }
   /* normalizeFluxes' scaling of phi fused into the residual pass, storeFSRFluxes after */

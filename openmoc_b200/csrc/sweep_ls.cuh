@@ -99,9 +99,12 @@ sweep_ls_kernel(const SweepLSArgs la) {
   const double sgn = dir ? -1.0 : 1.0;
   const double dx = sgn * la.trk_dir[t * 3], dy = sgn * la.trk_dir[t * 3 + 1], dz = sgn * la.trk_dir[t * 3 + 2];
 
-  const int64_t rep = (int64_t)(blockIdx.x & a.rep_mask);
-  double* __restrict__ const phi = a.phi + rep * a.rep_stride;
-  double* __restrict__ const phi_m = la.phi_m + rep * a.rep_stride * 3;
+  /* tally replica of this CTA: phi copies are rep_stride apart, the three moment planes of one
+   * copy follow each other, so a copy of the moments is 3 * rep_stride long */
+  const uint32_t rep = (uint32_t)(blockIdx.x & a.rep_mask);
+  double* __restrict__ const phi = a.phi;
+  double* __restrict__ const phi_m = la.phi_m;
+  const uint32_t rep_phi = rep * (uint32_t)a.rep_stride, rep_m = 3u * rep_phi;
 
   const int F = G * NP;
   const int64_t slot_in = (t * 2 + dir) * (int64_t)F;
@@ -231,10 +234,11 @@ sweep_ls_kernel(const SweepLSArgs la) {
       for (int j = 0; j < GPL; j++) {
         if (valid[j]) {
           const uint32_t idx = base + e[j];
-          atomicAdd(&phi[idx], wflush * acc[j]);
-          atomicAdd(&phi_m[(size_t)idx], wflush * accx[j]);
-          atomicAdd(&phi_m[(size_t)idx + a.rep_stride], wflush * accy[j]);
-          if (IS3D) atomicAdd(&phi_m[(size_t)idx + 2 * a.rep_stride], wflush * accz[j]);
+          const uint32_t im = idx + rep_m, ns = (uint32_t)a.rep_stride;   /* 32-bit index math (checked at finalize) */
+          atomicAdd(&phi[idx + rep_phi], wflush * acc[j]);
+          atomicAdd(&phi_m[im], wflush * accx[j]);
+          atomicAdd(&phi_m[im + ns], wflush * accy[j]);
+          if (IS3D) atomicAdd(&phi_m[im + 2u * ns], wflush * accz[j]);
         }
         acc[j] = accx[j] = accy[j] = accz[j] = 0.0;
       }
