@@ -145,7 +145,7 @@ struct b200_solver {
   /* linear source */
   bool linear = false, have_ls = false;
   int nc = 3;
-  DevBuf<double> ls_seg_start, ls_trk_dir, ls_lin_exp, ls_src_const, phi_m;
+  DevBuf<double> ls_seg_start, ls_trk_dir, ls_lin_exp, ls_src_const, phi_m, mom_stage;
   DevBuf<double4> seg_pos, qxyz;
   DevBuf<double2> qst;
   DevBuf<float> psi_a, psi_b;
@@ -321,7 +321,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   s->chi.release(); s->max_ratio.release(); s->sigma_a.release(); s->part3.release(); s->leakage.release(); s->fissionable.release(); s->phi.release();
   s->phi_fx.release(); s->fx_bits.release();
   s->ls_seg_start.release(); s->ls_trk_dir.release(); s->ls_lin_exp.release(); s->ls_src_const.release();
-  s->phi_m.release(); s->seg_pos.release(); s->qxyz.release();
+  s->phi_m.release(); s->mom_stage.release(); s->seg_pos.release(); s->qxyz.release();
   s->cmfd_fwd.release(); s->cmfd_bwd.release(); s->cmfd_group.release(); s->seg_cmfd.release(); s->currents.release();
   s->phi_old.release(); s->fixed.release(); s->stab.release(); s->scratch.release();
   s->qst.release(); s->psi_a.release(); s->psi_b.release(); s->scal.release();
@@ -579,6 +579,11 @@ extern "C" int b200_finalize(b200_solver* s) {
       int next_is_fwd = d == 0 ? (s->h_flags[t] & 1) : ((s->h_flags[t] >> 1) & 1);
       int64_t slot = nx * 2 + (next_is_fwd ? 0 : 1);   /* _start_flux(next, !next_is_fwd) CPUSolver.cpp:2574-2588 */
       out_slot[t * 2 + d] = slot;
+      /* two ends feeding one start-flux slot would race in the sweep (the reference's serial
+       * memcpy lets the later track win); cyclic tracking never produces it */
+      if (carry[slot] == 0)
+        return fail("b200_finalize: two track ends hand their flux to the same slot (track %lld, %s start)",
+                    (long long)nx, next_is_fwd ? "forward" : "backward");
       carry[slot] = 0;
     }
   }
@@ -1208,26 +1213,26 @@ extern "C" int b200_get_flux_moments(b200_solver* s, double* out, int64_t n) {
   NEED_FINAL(s);
   if (!s->linear) return fail("b200_get_flux_moments: not a linear-source solver");
   if (n != s->n_fsr * s->G * 3) return fail("b200_get_flux_moments: size mismatch");
-  double* tmp = nullptr;
-  CU(cudaMalloc((void**)&tmp, n * 8));
+  /* staging buffer in the reference's [r][c][e] order, kept for the next call (the CMFD path
+   * moves the moments twice per iteration) */
+  if (s->mom_stage.n < (size_t)n) CU(s->mom_stage.alloc(n));
+  double* tmp = s->mom_stage.p;
   moments_to_ref_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->phi_m.p, tmp, s->n_fsr, s->G);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, tmp, n * 8, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
-  cudaFree(tmp);
   return 0;
 }
 extern "C" int b200_set_flux_moments(b200_solver* s, const double* in, int64_t n) {
   NEED_FINAL(s);
   if (!s->linear) return fail("b200_set_flux_moments: not a linear-source solver");
   if (n != s->n_fsr * s->G * 3) return fail("b200_set_flux_moments: size mismatch");
-  double* tmp = nullptr;
-  CU(cudaMalloc((void**)&tmp, n * 8));
+  if (s->mom_stage.n < (size_t)n) CU(s->mom_stage.alloc(n));
+  double* tmp = s->mom_stage.p;
   CU(cudaMemcpyAsync(tmp, in, n * 8, cudaMemcpyHostToDevice, s->stream));
   moments_from_ref_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->phi_m.p, tmp, s->n_fsr, s->G);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
-  cudaFree(tmp);
   return 0;
 }
 
@@ -1522,16 +1527,14 @@ __global__ void eval_expf1_kernel(const double* __restrict__ x, double* __restri
 extern "C" int b200_eval_expF1(int32_t device, int32_t precision, const double* x, int64_t n, double* out) {
   if (!x || !out || n < 0) return fail("b200_eval_expF1: bad argument");
   CU(cudaSetDevice(device));
-  double *dx = nullptr, *dout = nullptr;
+  struct Tmp { double* p = nullptr; ~Tmp() { if (p) cudaFree(p); } } dx, dout;   /* freed on every path */
   if (n == 0) return 0;
-  CU(cudaMalloc((void**)&dx, n * 8));
-  CU(cudaMalloc((void**)&dout, n * 8));
-  CU(cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice));
-  eval_expf1_kernel<<<grid_for(n, 256), 256>>>(dx, dout, n, precision);
+  CU(cudaMalloc((void**)&dx.p, n * 8));
+  CU(cudaMalloc((void**)&dout.p, n * 8));
+  CU(cudaMemcpy(dx.p, x, n * 8, cudaMemcpyHostToDevice));
+  eval_expf1_kernel<<<grid_for(n, 256), 256>>>(dx.p, dout.p, n, precision);
   CU(cudaGetLastError());
-  CU(cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost));
-  cudaFree(dx);
-  cudaFree(dout);
+  CU(cudaMemcpy(out, dout.p, n * 8, cudaMemcpyDeviceToHost));
   return 0;
 }
 

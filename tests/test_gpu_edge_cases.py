@@ -128,3 +128,15 @@ def test_shards_of_a_ragged_problem_add_up():
         total += s.getFluxes()
     assert n_tracks == ft.n_tracks
     np.testing.assert_allclose(total, whole.getFluxes(), rtol=1e-11, atol=1e-13)
+
+
+def test_two_ends_feeding_one_slot_is_rejected():
+    """the sweep writes hand-offs concurrently: a link table that is not one-to-one must fail loudly"""
+    from openmoc_b200.capi import B200Error
+    from openmoc_b200.solver import B200Solver
+    ft = make_ragged(G=2, NP=1, seed=1, n_tracks=20, vacuum_fraction=0.0)
+    a = ft.arrays
+    a["trk_next_fwd"][1] = a["trk_next_fwd"][2]
+    a["trk_flags"][1] = (a["trk_flags"][1] & ~np.uint8(1)) | (a["trk_flags"][2] & np.uint8(1))
+    with pytest.raises(B200Error, match="same slot"):
+        B200Solver(ft)
