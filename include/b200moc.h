@@ -20,6 +20,18 @@
  * available from b200_last_error() (the plug-in turns it into
  * log_printf(ERROR, ...) => std::logic_error => Python RuntimeError, the
  * reference's own convention, src/log.cpp:535-599).
+ *
+ * Requirements on the uploaded tracks: the hand-off table must be one-to-one (no two track
+ * ends feed the same (track, direction) start slot - cyclic tracking guarantees it;
+ * b200_finalize checks it, because the sweep performs all hand-offs concurrently).
+ *
+ * Tuning knobs read from the environment (defaults are what bench.py measures):
+ *   B200_ORDER=natural        keep the Track uid order instead of longest-track-first
+ *   B200_PHI_REPLICAS=R       copies of the FSR tally (power of two); default: enough for
+ *                             n_fsrs*R >= 16 Ki rows, 1 for large decks
+ *   B200_GRAPH=0|1            CUDA-graph replay of the fused iteration off / on; default: on
+ *                             for decks with fewer than 1e8 integrations per sweep
+ *   B200_GPL, B200_IPC, B200_CTA   lane map / CTA size of the sweep kernel (experiments)
  */
 #ifndef B200MOC_H_
 #define B200MOC_H_
