@@ -525,7 +525,7 @@ static void choose_lane_map(int G, int* gpl, int* lpi, int* ipc) {
   for (int c : cand) {
     if (force != nullptr && atoi(force) != c) continue;
     int l = (G + c - 1) / c;
-    if (l > 32) continue;
+    if (l > 32 && force == nullptr) continue;   /* (a forced GPL may exceed one warp per item: flat mapping) */
     double util = (double)G / ((double)c * l);
     if (util >= 0.95) { *gpl = c; *lpi = l; break; }
     if (util > best) { best = util; *gpl = c; *lpi = l; }
@@ -669,6 +669,13 @@ extern "C" int b200_finalize(b200_solver* s) {
   }
 
   choose_lane_map(s->G, &s->gpl, &s->lpi, &s->ipc);
+  /* 2D tracks: one group per thread whatever G is.  An item then spans several warps (and
+   * CTAs) - the flat mapping does not care - and the kernel keeps its 72 registers / 4 CTAs per
+   * SM: 2D C5G7 with 70 groups 4.5e11 -> 5.9e11 integrations/s.  3D tracks (one polar angle per
+   * track) gain from sharing the per-segment work between 3 groups instead (3.5e11 vs 3.2e11). */
+  if (!s->cfg.solve_3d && !s->linear && getenv("B200_GPL") == nullptr && s->G > 32) {
+    s->gpl = 1; s->lpi = s->G; s->ipc = std::max(1, 224 / s->G);
+  }
   if (s->linear) {          /* the LS kernel is instantiated for 1 or 3 groups per thread */
     s->gpl = s->G <= 32 ? 1 : 3;
     s->lpi = (s->G + s->gpl - 1) / s->gpl;
@@ -798,6 +805,10 @@ static int launch_sweep(b200_solver* s) {
     const bool mixed = s->cfg.precision == B200_PRECISION_MIXED;
     int nthr = s->lpi * s->ipc;
     int64_t nblk = s->sweep_blocks;
+    if (!s->linear && (nthr < 192 || nthr > 224)) {     /* LPI does not pack 224 threads: let items straddle CTAs */
+      nthr = 224;
+      nblk = (2 * s->n_trk * (int64_t)s->lpi + nthr - 1) / nthr;
+    }
     /* items may straddle CTAs as well as warps (no CTA-level cooperation), so any block size
      * works; B200_CTA overrides the default of LPI x IPC threads (tuning hook) */
     if (const char* e = getenv("B200_CTA")) {
