@@ -177,11 +177,18 @@ void b200_flatten(TrackGenerator* tg, B200FlatTracks* ft, bool with_ls_data) {
   int A2 = ft->num_azim / 2, P = ft->num_polar;
   ft->quad_weight.resize((size_t)A2 * P);
   ft->quad_sin_theta.resize((size_t)A2 * P);
-  for (int a = 0; a < A2; a++)
+  ft->quad_azim_spacing.resize(A2); ft->quad_azim_weight.resize(A2);
+  ft->quad_polar_spacing.assign((size_t)A2 * P, 0.); ft->quad_polar_weight.resize((size_t)A2 * P);
+  for (int a = 0; a < A2; a++) {
+    ft->quad_azim_spacing[a] = quad->getAzimSpacing(a);
+    ft->quad_azim_weight[a] = quad->getAzimWeight(a);
     for (int p = 0; p < P; p++) {
       ft->quad_weight[a * P + p] = quad->getWeightInline(a, p);
       ft->quad_sin_theta[a * P + p] = quad->getSinThetaInline(a, p);
+      ft->quad_polar_weight[a * P + p] = quad->getPolarWeight(a, p);
+      if (ft->solve_3d) ft->quad_polar_spacing[a * P + p] = quad->getPolarSpacing(a, p);
     }
+  }
 
   /* ---- FSRs ---- */
   FP_PRECISION* vols = tg->getFSRVolumesBuffer();
@@ -294,6 +301,8 @@ void b200_write_trackfile(const B200FlatTracks& ft, const std::string& path) {
   w.v("trk_flags", ft.trk_flags); w.v("trk_bc_fwd", ft.trk_bc_fwd); w.v("trk_bc_bwd", ft.trk_bc_bwd);
   w.v("trk_phi", ft.trk_phi); w.v("trk_theta", ft.trk_theta);
   w.v("quad_weight", ft.quad_weight); w.v("quad_sin_theta", ft.quad_sin_theta);
+  w.v("quad_azim_spacing", ft.quad_azim_spacing); w.v("quad_azim_weight", ft.quad_azim_weight);
+  w.v("quad_polar_spacing", ft.quad_polar_spacing); w.v("quad_polar_weight", ft.quad_polar_weight);
   w.v("fsr_volume", ft.fsr_volume); w.v("fsr_mat", ft.fsr_mat); w.v("fsr_centroid", ft.fsr_centroid);
   w.v("mat_sigma_t", ft.mat_sigma_t); w.v("mat_sigma_a", ft.mat_sigma_a);
   w.v("mat_sigma_f", ft.mat_sigma_f); w.v("mat_nu_sigma_f", ft.mat_nu_sigma_f);

@@ -51,6 +51,10 @@ struct B200FlatTracks {
 
   /* quadrature: [A/2][P] total weights, [A/2][P] sin(theta) */
   std::vector<double> quad_weight, quad_sin_theta;
+  /* the factors the total weight is made of (Quadrature.cpp:674-750): [A/2] azimuthal spacing and
+   * weight, [A/2][P] polar spacing (3D only, else 0) and weight - the linear-source pre-pass
+   * (LinearExpansionGenerator, TrackTraversingAlgorithms.cpp:670-692) weights tracks with them */
+  std::vector<double> quad_azim_spacing, quad_azim_weight, quad_polar_spacing, quad_polar_weight;
 
   /* FSR data */
   std::vector<double> fsr_volume;

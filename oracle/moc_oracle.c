@@ -44,6 +44,15 @@ struct moc_oracle {
   double stab_factor;
   double sweep_seconds;
   double* scratch;
+  /* linear source (CPULSSolver): see moc_oracle_enable_linear_source */
+  int ls, nc;                       /* nc: 3 coefficients in 2D, 6 in 3D */
+  double* seg_start;                /* [n_seg][3] relative to the FSR centroid; walked in place by the sweep */
+  double* seg_start0;               /* as uploaded: 3D (on-the-fly) segments are re-traced before every sweep */
+  double* trk_phi; double* trk_theta;
+  double* phi_m; double* q_m;       /* [r][c][e] = r*3G + c*G + e   (CPULSSolver.h:22-26) */
+  double* lin_exp;                  /* [r][nc] inverse expansion matrix */
+  double* src_const;                /* [r][i][e] = r*G*nc + i*G + e */
+  int num_flat;
 };
 
 static void* dup_mem(const void* src, size_t bytes) {
@@ -169,6 +178,8 @@ void moc_oracle_destroy(moc_oracle* o) {
   free(o->chi); free(o->fissionable);
   free(o->phi); free(o->phi_old); free(o->q); free(o->fixed); free(o->stab);
   free(o->psi_start); free(o->psi_bound); free(o->scratch); free(o->leakage); free(o->sigma_a);
+  free(o->seg_start); free(o->seg_start0); free(o->trk_phi); free(o->trk_theta); free(o->phi_m); free(o->q_m);
+  free(o->lin_exp); free(o->src_const);
   free(o);
 }
 
@@ -184,6 +195,7 @@ void moc_oracle_zero_track_fluxes(moc_oracle* o) {
 /* src/CPUSolver.cpp:1816-1824 */
 void moc_oracle_flatten_fsr_fluxes(moc_oracle* o, double value) {
   for (int64_t i = 0; i < o->n_fsr * o->G; i++) o->phi[i] = value;
+  if (o->ls) memset(o->phi_m, 0, (size_t)o->n_fsr * o->G * 3 * 8);   /* src/CPULSSolver.cpp:342-354 */
 }
 
 /* src/CPUSolver.cpp:1846-1853 */
@@ -210,8 +222,12 @@ double moc_oracle_normalize_fluxes(moc_oracle* o) {
     o->psi_start[i] *= norm_factor;   /* float *= double, rounded to float */
     o->psi_bound[i] *= norm_factor;
   }
+  if (o->ls)                          /* src/CPULSSolver.cpp:360-372 */
+    for (int64_t i = 0; i < o->n_fsr * G * 3; i++) o->phi_m[i] *= norm_factor;
   return norm_factor;
 }
+
+static void ls_sources(moc_oracle* o, int iteration);
 
 /* src/CPUSolver.cpp:1939-2023 */
 void moc_oracle_compute_fsr_sources(moc_oracle* o, int iteration) {
@@ -246,6 +262,7 @@ void moc_oracle_compute_fsr_sources(moc_oracle* o, int iteration) {
     }
     free(fs); free(ss);
   }
+  if (o->ls) ls_sources(o, iteration);
 }
 
 /* src/CPUSolver.cpp:2030-2066 */
@@ -360,17 +377,425 @@ static void sweep_track(moc_oracle* o, int64_t t, double* fsr_flux) {
   }
 }
 
+
+/* ===================================================================================== */
+/* Linear source: restatement of CPULSSolver (src/CPULSSolver.cpp) and of its pre-pass     */
+/* LinearExpansionGenerator (src/TrackTraversingAlgorithms.cpp:470-831)                   */
+/* ===================================================================================== */
+#define MIN_DET 1E-10                     /* src/constants.h:70 */
+
+/* src/exponentials.h:110-145: 1/x - (1-exp(-x))/x^2 */
+static inline double expG_fractional(double x) {
+  const double p0 = 0.5;
+  const double p1 = 1.76558112351595 * 1E-1;
+  const double p2 = 4.041584305811143 * 1E-2;
+  const double p3 = 6.178333902037397 * 1E-3;
+  const double p4 = 6.429894635552992 * 1E-4;
+  const double p5 = 6.064409107557148 * 1E-5;
+  const double d0 = 1.0;
+  const double d1 = 6.864462055546078 * 1E-1;
+  const double d2 = 2.263358514260129 * 1E-1;
+  const double d3 = 4.721469893686252 * 1E-2;
+  const double d4 = 6.883236664917246 * 1E-3;
+  const double d5 = 7.036272419147752 * 1E-4;
+  const double d6 = 6.064409107557148 * 1E-5;
+  double num, den;
+  den = d6 * x + d5;
+  den = den * x + d4;
+  den = den * x + d3;
+  den = den * x + d2;
+  den = den * x + d1;
+  den = den * x + d0;
+  den = 1. / den;
+  num = p5 * x + p4;
+  num = num * x + p3;
+  num = num * x + p2;
+  num = num * x + p1;
+  num = num * x + p0;
+  return num * den;
+}
+
+/* src/exponentials.h:293-323 */
+static inline double expG2_fractional(double x) {
+  const double a1 = -8.335775885589858 * 1E-2;
+  const double a2 = -3.603942303847604 * 1E-3;
+  const double a3 = 3.7673183263550827 * 1E-3;
+  const double a4 = 1.124183494990467 * 1E-5;
+  const double a5 = 1.6837426505799449 * 1E-4;
+  const double b1 = 7.454048371823628 * 1E-1;
+  const double b2 = 2.3794300531408347 * 1E-1;
+  const double b3 = 5.367250964303789 * 1E-2;
+  const double b4 = 6.125197988351906 * 1E-3;
+  const double b5 = 1.0102514456857377 * 1E-3;
+  double num, den;
+  num = a5 * x + a4;
+  num = num * x + a3;
+  num = num * x + a2;
+  num = num * x + a1;
+  num *= x;
+  den = b5 * x + b4;
+  den = den * x + b3;
+  den = den * x + b2;
+  den = den * x + b1;
+  den = den * x + 1.;
+  return num / den;
+}
+
+/* LinearExpansionGenerator::onTrack + execute (TrackTraversingAlgorithms.cpp:536-831) */
+static void ls_prepass(moc_oracle* o, const double* azim_spacing, const double* azim_weight,
+                       const double* polar_spacing, const double* polar_weight) {
+  const int G = o->G, nc = o->nc, P = o->P;
+  double* lem = (double*)calloc((size_t)o->n_fsr * nc, 8);
+  double* tsc = (double*)malloc((size_t)G * nc * 8);
+  memset(o->src_const, 0, (size_t)o->n_fsr * G * nc * 8);
+  for (int64_t t = 0; t < o->n_trk; t++) {
+    const int azim = o->trk_azim[t], polar = o->trk_polar[t];
+    const double phi = o->trk_phi[t];
+    const double sin_phi = sin(phi), cos_phi = cos(phi);
+    double wgt = azim_spacing[azim] * azim_weight[azim];
+    double sin_theta = 1, cos_theta = 0;
+    if (o->solve_3d) {
+      const double theta = o->trk_theta[t];
+      sin_theta = sin(theta);
+      cos_theta = cos(theta);
+      wgt *= polar_spacing[azim * P + polar] * polar_weight[azim * P + polar];
+    }
+    for (int64_t s = o->trk_off[t]; s < o->trk_off[t + 1]; s++) {
+      const int64_t fsr = o->seg_fsr[s];
+      const double* sigma_t = o->sigma_t + (size_t)o->fsr_mat[fsr] * G;
+      const double length = o->seg_len[s];
+      const double volume = o->vol[fsr];
+      const double x = o->seg_start[3 * s], y = o->seg_start[3 * s + 1], z = o->seg_start[3 * s + 2];
+      const double xc = x + length * 0.5 * cos_phi * sin_theta;
+      const double yc = y + length * 0.5 * sin_phi * sin_theta;
+      const double zc = z + length * 0.5 * cos_theta;
+      const double vol_impact = wgt * length / volume;
+      const double src_constant = vol_impact * length / 2.0;
+      for (int g = 0; g < G; g++) {
+        tsc[g] = vol_impact * xc * xc;
+        tsc[G + g] = vol_impact * yc * yc;
+        tsc[2 * G + g] = vol_impact * xc * yc;
+        if (o->solve_3d) {
+          tsc[3 * G + g] = vol_impact * xc * zc;
+          tsc[4 * G + g] = vol_impact * yc * zc;
+          tsc[5 * G + g] = vol_impact * zc * zc;
+        }
+        const double tau = length * sigma_t[g];
+        if (!o->solve_3d) {
+          for (int p = 0; p < P / 2; p++) {
+            const double st = o->sin_theta[azim * P + p];
+            const double G2_src = length * expG2_fractional(tau / st) * src_constant * 2
+                                  * polar_weight[azim * P + p] * st;
+            tsc[g] += cos_phi * cos_phi * G2_src;
+            tsc[G + g] += sin_phi * sin_phi * G2_src;
+            tsc[2 * G + g] += sin_phi * cos_phi * G2_src;
+          }
+        } else {
+          const double G2_src = expG2_fractional(tau) * length * src_constant;
+          tsc[g] += cos_phi * cos_phi * G2_src * sin_theta * sin_theta;
+          tsc[G + g] += sin_phi * sin_phi * G2_src * sin_theta * sin_theta;
+          tsc[2 * G + g] += sin_phi * cos_phi * G2_src * sin_theta * sin_theta;
+          tsc[3 * G + g] += cos_phi * cos_theta * G2_src * sin_theta;
+          tsc[4 * G + g] += sin_phi * cos_theta * G2_src * sin_theta;
+          tsc[5 * G + g] += cos_theta * cos_theta * G2_src;
+        }
+      }
+      lem[fsr * nc] += wgt * length / volume * (xc * xc + pow(cos_phi * sin_theta * length, 2) / 12.0);
+      lem[fsr * nc + 1] += wgt * length / volume * (yc * yc + pow(sin_phi * sin_theta * length, 2) / 12.0);
+      lem[fsr * nc + 2] += wgt * length / volume * (xc * yc + sin_phi * cos_phi * pow(sin_theta * length, 2) / 12.0);
+      if (o->solve_3d) {
+        lem[fsr * nc + 3] += wgt * length / volume * (xc * zc + cos_phi * cos_theta * sin_theta * pow(length, 2) / 12.0);
+        lem[fsr * nc + 4] += wgt * length / volume * (yc * zc + sin_phi * cos_theta * sin_theta * pow(length, 2) / 12.0);
+        lem[fsr * nc + 5] += wgt * length / volume * (zc * zc + pow(cos_theta * length, 2) / 12.0);
+      }
+      for (int g = 0; g < G; g++)
+        for (int i = 0; i < nc; i++) o->src_const[fsr * G * nc + i * G + g] += tsc[i * G + g];
+    }
+  }
+  /* invert the symmetric expansion matrix per FSR (:570-633) */
+  double* ilem = o->lin_exp;
+  o->num_flat = 0;
+  for (int64_t r = 0; r < o->n_fsr; r++) {
+    if (o->solve_3d) {
+      double det = lem[r*nc + 0] * lem[r*nc + 1] * lem[r*nc + 5] + lem[r*nc + 2] * lem[r*nc + 4] * lem[r*nc + 3] +
+                   lem[r*nc + 3] * lem[r*nc + 2] * lem[r*nc + 4] - lem[r*nc + 0] * lem[r*nc + 4] * lem[r*nc + 4] -
+                   lem[r*nc + 3] * lem[r*nc + 1] * lem[r*nc + 3] - lem[r*nc + 2] * lem[r*nc + 2] * lem[r*nc + 5];
+      if (fabs(det) < MIN_DET || o->vol[r] < 1e-6) {
+        o->num_flat++;
+        for (int i = 0; i < 6; i++) ilem[r*nc + i] = 0.0;
+      } else {
+        ilem[r*nc + 0] = (lem[r*nc + 1] * lem[r*nc + 5] - lem[r*nc + 4] * lem[r*nc + 4]) / det;
+        ilem[r*nc + 1] = (lem[r*nc + 0] * lem[r*nc + 5] - lem[r*nc + 3] * lem[r*nc + 3]) / det;
+        ilem[r*nc + 2] = (lem[r*nc + 3] * lem[r*nc + 4] - lem[r*nc + 2] * lem[r*nc + 5]) / det;
+        ilem[r*nc + 3] = (lem[r*nc + 2] * lem[r*nc + 4] - lem[r*nc + 3] * lem[r*nc + 1]) / det;
+        ilem[r*nc + 4] = (lem[r*nc + 3] * lem[r*nc + 2] - lem[r*nc + 0] * lem[r*nc + 4]) / det;
+        ilem[r*nc + 5] = (lem[r*nc + 0] * lem[r*nc + 1] - lem[r*nc + 2] * lem[r*nc + 2]) / det;
+      }
+    } else {
+      double det = lem[r*nc] * lem[r*nc + 1] - lem[r*nc + 2] * lem[r*nc + 2];
+      if (fabs(det) < MIN_DET) {
+        o->num_flat++;
+        ilem[r*nc] = ilem[r*nc + 1] = ilem[r*nc + 2] = 0.0;
+      } else {
+        ilem[r*nc + 0] = lem[r*nc + 1] / det;
+        ilem[r*nc + 1] = lem[r*nc + 0] / det;
+        ilem[r*nc + 2] = -lem[r*nc + 2] / det;
+      }
+    }
+  }
+  free(lem); free(tsc);
+}
+
+int moc_oracle_enable_linear_source(moc_oracle* o, const double* seg_start, const double* trk_phi,
+                                    const double* trk_theta, const double* azim_spacing,
+                                    const double* azim_weight, const double* polar_spacing,
+                                    const double* polar_weight) {
+  const int G = o->G;
+  o->ls = 1;
+  o->nc = o->solve_3d ? 6 : 3;
+  o->seg_start = dup_mem(seg_start, (size_t)o->n_seg * 3 * 8);
+  o->seg_start0 = dup_mem(seg_start, (size_t)o->n_seg * 3 * 8);
+  o->trk_phi = dup_mem(trk_phi, (size_t)o->n_trk * 8);
+  o->trk_theta = dup_mem(trk_theta, (size_t)o->n_trk * 8);
+  o->phi_m = calloc((size_t)o->n_fsr * G * 3, 8);
+  o->q_m = calloc((size_t)o->n_fsr * G * 3, 8);
+  o->lin_exp = calloc((size_t)o->n_fsr * o->nc, 8);
+  o->src_const = calloc((size_t)o->n_fsr * G * o->nc, 8);
+  ls_prepass(o, azim_spacing, azim_weight, polar_spacing, polar_weight);
+  return o->num_flat;
+}
+
+void moc_oracle_get_flux_moments(moc_oracle* o, double* out) {
+  memcpy(out, o->phi_m, (size_t)o->n_fsr * o->G * 3 * 8);
+}
+void moc_oracle_get_linear_source_tables(moc_oracle* o, double* lin_exp, double* src_const) {
+  memcpy(lin_exp, o->lin_exp, (size_t)o->n_fsr * o->nc * 8);
+  memcpy(src_const, o->src_const, (size_t)o->n_fsr * o->G * o->nc * 8);
+}
+
+/* CPULSSolver::computeFSRSources, moment part (src/CPULSSolver.cpp:386-524) */
+static void ls_sources(moc_oracle* o, int iteration) {
+  const int G = o->G, nc = o->nc;
+  double* buf = (double*)malloc(G * 8);
+  for (int64_t r = 0; r < o->n_fsr; r++) {
+    const int m = o->fsr_mat[r];
+    const double* sigma_s = o->sigma_s + (size_t)m * G * G;
+    const double* fm = o->fiss + (size_t)m * G * G;
+    const double* pm = o->phi_m + r * 3 * G;
+    for (int g = 0; g < G; g++) {
+      double fis[3] = {0., 0., 0.}, sca[3];
+      if (o->fissionable[m]) {
+        for (int c = 0; c < 3; c++) {
+          for (int gp = 0; gp < G; gp++) buf[gp] = fm[g * G + gp] * pm[c * G + gp];
+          fis[c] = pairwise_sum(buf, G) / o->k_eff;
+        }
+      }
+      for (int c = 0; c < 3; c++) {
+        for (int gp = 0; gp < G; gp++) buf[gp] = sigma_s[g * G + gp] * pm[c * G + gp];
+        sca[c] = pairwise_sum(buf, G);
+      }
+      const double src_x = sca[0] + fis[0], src_y = sca[1] + fis[1], src_z = sca[2] + fis[2];
+      double* qm = o->q_m + r * 3 * G;
+      const double* M = o->lin_exp + r * nc;
+      if (o->q[r * G + g] > 10 * FLUX_EPSILON || iteration > 29) {
+        if (o->solve_3d) {
+          qm[g] = ONE_OVER_FOUR_PI / 2 * (M[0] * src_x + M[2] * src_y + M[3] * src_z);
+          qm[G + g] = ONE_OVER_FOUR_PI / 2 * (M[2] * src_x + M[1] * src_y + M[4] * src_z);
+          qm[2 * G + g] = ONE_OVER_FOUR_PI / 2 * (M[3] * src_x + M[4] * src_y + M[5] * src_z);
+        } else {
+          qm[g] = ONE_OVER_FOUR_PI / 2 * (M[0] * src_x + M[2] * src_y);
+          qm[G + g] = ONE_OVER_FOUR_PI / 2 * (M[2] * src_x + M[1] * src_y);
+        }
+      } else {
+        qm[g] = qm[G + g] = 0;
+        if (o->solve_3d) qm[2 * G + g] = 0;
+      }
+    }
+  }
+  free(buf);
+}
+
+/* One track, both directions, linear source: TransportSweep::onTrack
+ * (TrackTraversingAlgorithms.cpp:890-1052) with CPULSSolver::tallyLSScalarFlux
+ * (CPULSSolver.cpp:542-739) and accumulateLinearFluxContribution (:749-780) inlined.
+ * buf = 4*G doubles: flux, x, y, z contributions of the current FSR run. */
+static void ls_sweep_track(moc_oracle* o, int64_t t, double* buf) {
+  const int G = o->G, NP = o->NP, F = o->F, P = o->P;
+  const int azim = o->trk_azim[t], polar = o->trk_polar[t];
+  const int64_t s0 = o->trk_off[t], s1 = o->trk_off[t + 1];
+  const double* wrow = o->weight + (size_t)azim * P;
+  int a_eval = azim;
+  if (a_eval >= o->A / 4) a_eval = o->A / 2 - 1 - azim;
+  const double* srow = o->sin_theta + (size_t)a_eval * P;
+  const double weight3d = o->solve_3d ? wrow[polar] : 1.0;
+  double* fx = buf + G; double* fy = buf + 2 * G; double* fz = buf + 3 * G;
+  double direction[3];
+  {
+    const double phi = o->trk_phi[t];
+    double cos_theta = 0.0, sin_theta = 1.0;
+    if (o->solve_3d) { cos_theta = cos(o->trk_theta[t]); sin_theta = sin(o->trk_theta[t]); }
+    direction[0] = cos(phi) * sin_theta;
+    direction[1] = sin(phi) * sin_theta;
+    direction[2] = cos_theta;
+  }
+  memset(buf, 0, 4 * G * 8);
+  for (int dir = 0; dir < 2; dir++) {
+    float* track_flux = o->psi_bound + ((size_t)t * 2 + dir) * F;
+    int64_t s = dir == 0 ? s0 : s1 - 1;
+    const int64_t step = dir == 0 ? 1 : -1;
+    for (int64_t n = 0; n < s1 - s0; n++, s += step) {
+      const int64_t fsr = o->seg_fsr[s];
+      const double length = o->seg_len[s];
+      const double* sigma_t = o->sigma_t + (size_t)o->fsr_mat[fsr] * G;
+      const double* q = o->q + fsr * G;
+      const double* qm = o->q_m + fsr * 3 * G;
+      double* position = o->seg_start + 3 * s;
+      if (o->solve_3d) {
+        double center_x2[3];
+        for (int i = 0; i < 3; i++) center_x2[i] = 2 * position[i] + length * direction[i];
+        for (int e = 0; e < G; e++) {
+          double src_flat = q[e];
+          for (int i = 0; i < 3; i++) src_flat += qm[i * G + e] * center_x2[i];
+          double src_linear = qm[e] * direction[0];
+          src_linear += qm[G + e] * direction[1];
+          src_linear += qm[2 * G + e] * direction[2];
+          const double tau = length * sigma_t[e];
+          const double exp_G = expG_fractional(tau > 1e-8 ? tau : 1e-8);
+          const double exp_F1 = 1. - tau * exp_G;
+          const double exp_F2 = 2. * exp_G - exp_F1;
+          double exp_H = exp_F1 - exp_G;
+          exp_H *= length * track_flux[e] * tau;
+          const double delta_psi = (tau * track_flux[e] - length * src_flat) * exp_F1
+                                   - src_linear * length * length * exp_F2;
+          track_flux[e] -= delta_psi;
+          buf[e] += delta_psi;
+          fx[e] += exp_H * direction[0] + delta_psi * position[0];
+          fy[e] += exp_H * direction[1] + delta_psi * position[1];
+          fz[e] += exp_H * direction[2] + delta_psi * position[2];
+        }
+      } else {
+        double center[2];
+        for (int i = 0; i < 2; i++) center[i] = 2 * position[i] + length * direction[i];
+        for (int p = 0; p < NP; p++) {
+          const double inv_sin_theta = 1.0 / srow[p];
+          const double wgt = wrow[p];
+          for (int e = 0; e < G; e++) {
+            const int pe = p * G + e;
+            const double tau = sigma_t[e] * length;
+            /* ExpEvaluator::retrieveExponentialComponents, src/ExpEvaluator.h:349-381 */
+            double tp = tau * inv_sin_theta;
+            if (tp < 1e-8) tp = 1e-8;
+            double exp_G = expG_fractional(tp);
+            double exp_F1 = 1. - tp * exp_G;
+            exp_F1 *= inv_sin_theta;
+            exp_G *= inv_sin_theta;
+            const double exp_F2 = 2. * exp_G - exp_F1;
+            double exp_H = exp_F1 - exp_G;
+            double src_flat = q[e];
+            for (int i = 0; i < 2; i++) src_flat += qm[i * G + e] * center[i];
+            double src_linear = direction[0] * qm[e];
+            src_linear += direction[1] * qm[G + e];
+            exp_H *= wgt * tau * length * track_flux[pe];
+            double delta_psi = (tau * track_flux[pe] - length * src_flat) * exp_F1
+                               - length * length * src_linear * exp_F2;
+            track_flux[pe] -= delta_psi;
+            delta_psi *= wgt;
+            buf[e] += delta_psi;
+            fx[e] += exp_H * direction[0] + delta_psi * position[0];
+            fy[e] += exp_H * direction[1] + delta_psi * position[1];
+          }
+        }
+      }
+      /* move the starting position to the end of the segment for the opposite direction (:736-738) */
+      for (int i = 0; i < 3; i++) position[i] += direction[i] * length;
+
+      int flush;
+      if (dir == 0) flush = (s < s1 - 1) && (fsr != o->seg_fsr[s + 1]);
+      else flush = (s == s0) || (fsr != o->seg_fsr[s - 1]);
+      if (flush) {
+        double* pm = o->phi_m + fsr * 3 * G;
+        for (int e = 0; e < G; e++) {
+#pragma omp atomic update
+          o->phi[fsr * G + e] += weight3d * buf[e];
+#pragma omp atomic update
+          pm[e] += weight3d * fx[e];
+#pragma omp atomic update
+          pm[G + e] += weight3d * fy[e];
+#pragma omp atomic update
+          pm[2 * G + e] += weight3d * fz[e];
+        }
+        memset(buf, 0, 4 * G * 8);
+      }
+    }
+    uint8_t bc = dir == 0 ? o->bc_fwd[t] : o->bc_bwd[t];
+    int64_t nxt = dir == 0 ? o->next_fwd[t] : o->next_bwd[t];
+    int next_is_fwd = dir == 0 ? (o->flags[t] & 1) : ((o->flags[t] >> 1) & 1);
+    if (bc == BC_REFLECTIVE || bc == BC_PERIODIC) {
+      float* out = o->psi_start + ((size_t)nxt * 2 + (next_is_fwd ? 0 : 1)) * F;
+      memcpy(out, track_flux, F * 4);
+    }
+    for (int i = 0; i < 3; i++) direction[i] *= -1;     /* reverse the direction (:1006-1008) */
+  }
+}
+
+/* CPULSSolver::addSourceToScalarFlux (src/CPULSSolver.cpp:787-882) */
+static void ls_closure(moc_oracle* o) {
+  const int G = o->G, nc = o->nc;
+  for (int64_t r = 0; r < o->n_fsr; r++) {
+    double volume = o->vol[r];
+    if (volume < VOL_EPSILON) volume = 1e30;
+    const double* sigma_t = o->sigma_t + (size_t)o->fsr_mat[r] * G;
+    double* pm = o->phi_m + r * 3 * G;
+    const double* qm = o->q_m + r * 3 * G;
+    const double* sc = o->src_const + r * G * nc;
+    for (int e = 0; e < G; e++) {
+      const double flux_const = FOUR_PI * 2;
+      o->phi[r * G + e] /= volume;
+      o->phi[r * G + e] += FOUR_PI * o->q[r * G + e];
+      o->phi[r * G + e] /= sigma_t[e];
+      pm[e] /= volume;
+      pm[e] += flux_const * qm[e] * sc[e];
+      pm[e] += flux_const * qm[G + e] * sc[2 * G + e];
+      pm[G + e] /= volume;
+      pm[G + e] += flux_const * qm[e] * sc[2 * G + e];
+      pm[G + e] += flux_const * qm[G + e] * sc[G + e];
+      if (o->solve_3d) {
+        pm[e] += flux_const * qm[2 * G + e] * sc[3 * G + e];
+        pm[G + e] += flux_const * qm[2 * G + e] * sc[4 * G + e];
+        pm[2 * G + e] /= volume;
+        pm[2 * G + e] += flux_const * qm[e] * sc[3 * G + e];
+        pm[2 * G + e] += flux_const * qm[G + e] * sc[4 * G + e];
+        pm[2 * G + e] += flux_const * qm[2 * G + e] * sc[5 * G + e];
+      }
+      pm[e] /= sigma_t[e];
+      pm[G + e] /= sigma_t[e];
+      if (o->solve_3d) pm[2 * G + e] /= sigma_t[e];
+      if (o->phi[r * G + e] < 0.0) {
+        o->phi[r * G + e] = o->phi_old[r * G + e] > FLUX_EPSILON ? o->phi_old[r * G + e] : FLUX_EPSILON;
+        pm[e] = pm[G + e] = pm[2 * G + e] = 0;
+      }
+    }
+  }
+}
+
 /* src/CPUSolver.cpp:2338-2389 */
 void moc_oracle_transport_sweep(moc_oracle* o) {
   double t0 = omp_get_wtime();
   memset(o->phi, 0, (size_t)o->n_fsr * o->G * 8);                    /* :2347 */
   memcpy(o->psi_bound, o->psi_start, (size_t)o->n_trk * 2 * o->F * 4); /* :2351 */
   memset(o->leakage, 0, (size_t)o->n_trk * 4);                          /* :2360 */
+  if (o->ls) memset(o->phi_m, 0, (size_t)o->n_fsr * o->G * 3 * 8);     /* CPULSSolver::flattenFSRFluxes */
+  /* explicit 2D segments keep the positions the previous sweep left (forward: += d*l, backward:
+   * -= d*l, CPULSSolver.cpp:736-738); on-the-fly 3D segments are traced afresh every sweep */
+  if (o->ls && o->solve_3d) memcpy(o->seg_start, o->seg_start0, (size_t)o->n_seg * 3 * 8);
 #pragma omp parallel num_threads(o->threads)
   {
-    double* fsr_flux = (double*)malloc(o->G * 8);
+    double* fsr_flux = (double*)malloc(4 * o->G * 8);
 #pragma omp for schedule(dynamic)
-    for (int64_t t = 0; t < o->n_trk; t++) sweep_track(o, t, fsr_flux);
+    for (int64_t t = 0; t < o->n_trk; t++) {
+      if (o->ls) ls_sweep_track(o, t, fsr_flux);
+      else sweep_track(o, t, fsr_flux);
+    }
     free(fsr_flux);
   }
   o->sweep_seconds += omp_get_wtime() - t0;
@@ -385,6 +810,7 @@ double moc_oracle_sweep_seconds(moc_oracle* o, int reset) {
 /* src/CPUSolver.cpp:2608-2659 */
 void moc_oracle_add_source_to_scalar_flux(moc_oracle* o) {
   int G = o->G;
+  if (o->ls) { ls_closure(o); return; }
   for (int64_t r = 0; r < o->n_fsr; r++) {
     double volume = o->vol[r];
     const double* sigma_t = o->sigma_t + (size_t)o->fsr_mat[r] * G;

@@ -12,6 +12,9 @@
  *   tests/test_forward_pin_cell/results_true.dat           (261 it, k, 14 fluxes)
  *   tests/test_forward_simple_lattice/results_true.dat     (SHA-512, 3584 fluxes)
  *   tests/test_forward_3D_lattice_70g/results_true.dat     (258 it, k)
+ *   tests/test_forward_3D_lattice/results_true.dat, test_forward_hom_inf_medium
+ *   tests/test_forward_3D_lattice_linear/results_true.dat      (linear source: 156 it, k, 480 FSRs)
+ *   tests/test_forward_3D_lattice_linear_70g/results_true.dat  (linear source: 186 it, k)
  *   tests/unit_tests/test_exponentials.py:74-77            (expF1 known answers)
  *
  * Every function cites the reference file:line it follows
@@ -83,6 +86,18 @@ void   moc_oracle_set_num_threads(moc_oracle* o, int n);
 void   moc_oracle_set_keff_from_neutron_balance(moc_oracle* o, int on);
 /* seconds spent inside transport_sweep since creation / last reset */
 double moc_oracle_sweep_seconds(moc_oracle* o, int reset);
+
+/* Linear source (CPULSSolver).  Call once after create: runs the LinearExpansionGenerator
+ * pre-pass (src/TrackTraversingAlgorithms.cpp:470-831); afterwards every step function above
+ * follows src/CPULSSolver.cpp.  seg_start [n_seg*3] is relative to the FSR centroids, the
+ * quadrature factors are the chunks quad_azim_spacing/_weight [A/2], quad_polar_spacing/_weight
+ * [A/2*P] of the track file.  Returns the number of FSRs that fall back to a flat source. */
+int    moc_oracle_enable_linear_source(moc_oracle* o, const double* seg_start, const double* trk_phi,
+                                       const double* trk_theta, const double* azim_spacing,
+                                       const double* azim_weight, const double* polar_spacing,
+                                       const double* polar_weight);
+void   moc_oracle_get_flux_moments(moc_oracle* o, double* out);  /* [n_fsrs][3][G] */
+void   moc_oracle_get_linear_source_tables(moc_oracle* o, double* lin_exp, double* src_const);
 
 /* scalar exponential, src/exponentials.h:156-192 */
 double moc_oracle_expF1(double x);

@@ -75,6 +75,12 @@ def lib():
         L.moc_oracle_sweep_seconds.argtypes = [vp, i32]
         L.moc_oracle_expF1.restype = dbl
         L.moc_oracle_expF1.argtypes = [dbl]
+        L.moc_oracle_enable_linear_source.restype = i32
+        L.moc_oracle_enable_linear_source.argtypes = [vp] * 8
+        L.moc_oracle_get_flux_moments.restype = None
+        L.moc_oracle_get_flux_moments.argtypes = [vp, vp]
+        L.moc_oracle_get_linear_source_tables.restype = None
+        L.moc_oracle_get_linear_source_tables.argtypes = [vp, vp, vp]
         _lib = L
     return _lib
 
@@ -86,7 +92,7 @@ def _p(a):
 class OracleSolver:
     """Method names follow the reference Solver (src/Solver.h)."""
 
-    def __init__(self, ft):
+    def __init__(self, ft, linear_source=False):
         L = lib()
         a = ft.arrays
         c = lambda k, dt: np.ascontiguousarray(a[k], dtype=dt)
@@ -105,6 +111,25 @@ class OracleSolver:
                                      ft.n_tracks, ft.n_segments, ft.n_fsrs, ft.n_materials,
                                      *[_p(x) for x in self._keep])
         self.num_iterations = 0
+        self.linear_source = bool(linear_source)
+        if linear_source:
+            # CPULSSolver: needs the LS chunks of the track file (dumped after a CPULSSolver run)
+            ls = [c("seg_start", "f8"), c("trk_phi", "f8"), c("trk_theta", "f8"), c("quad_azim_spacing", "f8"),
+                  c("quad_azim_weight", "f8"), c("quad_polar_spacing", "f8"), c("quad_polar_weight", "f8")]
+            assert ls[0].size == 3 * ft.n_segments, "track file has no segment starting points"
+            self.num_flat_fsrs = L.moc_oracle_enable_linear_source(self.h, *[_p(x) for x in ls])
+
+    def getFluxMoments(self):
+        """[n_fsrs][3][G] as CPULSSolver stores them (src/CPULSSolver.h:22-26)"""
+        out = np.empty(self.ft.n_fsrs * 3 * self.G)
+        lib().moc_oracle_get_flux_moments(self.h, _p(out))
+        return out
+
+    def getLinearSourceTables(self):
+        nc = 6 if self.ft.solve_3d else 3
+        a, b = np.empty(self.ft.n_fsrs * nc), np.empty(self.ft.n_fsrs * self.G * nc)
+        lib().moc_oracle_get_linear_source_tables(self.h, _p(a), _p(b))
+        return a, b
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -32,6 +32,14 @@ CASES = {
     # EqualAnglePolarQuad is discarded by generateTracks for want of setNumAzimAngles.
     "c5g7_2d_coarse": ["--model", "c5g7-2d", "--azim", "4", "--spacing", "0.5", "--polar", "6",
                        "--max-iters", "40", "--no-fluxes"],
+    # linear source (CPULSSolver): the track files carry the centroid-relative segment starting
+    # points and the quadrature factors the LinearExpansionGenerator pre-pass needs
+    "simple_lattice_ls": ["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12", "--solver", "cpuls"],
+    "lattice3d_ls_70g": ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2",
+                         "--spacing", "0.6", "--zspacing", "2.8", "--groups70", "--tol", "5e-3",
+                         "--solver", "cpuls"],                                  # test_forward_3D_lattice_linear_70g
+    "lattice3d_ls_7g": ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2",
+                        "--spacing", "0.24", "--zspacing", "0.9", "--solver", "cpuls"],  # test_forward_3D_lattice_linear
 }
 
 def main():
@@ -41,14 +49,15 @@ def main():
         js = os.path.join(HERE, name + ".json")
         subprocess.check_call([DRIVER] + args + ["--quiet", "--dump-tracks", trk, "--json", js])
         d = json.load(open(js))
-        if name.startswith("c5g7") or name.startswith("lattice3d_70g"):
+        if name.startswith("c5g7") or name.startswith("lattice3d_70g") or name.startswith("lattice3d_ls"):
             d.pop("fluxes", None)    # keep the fixture small; phi is compared through the oracle
         d.pop("sweep_time_s", None); d.pop("total_time_s", None)
         json.dump(d, open(js, "w"))
         print(name, d.get("iterations"), d.get("keff"), d["n_tracks"], d["n_segments"], d["n_fsrs"])
     gold = {}
     for t in ("test_forward_pin_cell", "test_forward_simple_lattice", "test_forward_3D_lattice_70g",
-              "test_forward_3D_lattice", "test_forward_hom_inf_medium"):
+              "test_forward_3D_lattice", "test_forward_hom_inf_medium",
+              "test_forward_3D_lattice_linear", "test_forward_3D_lattice_linear_70g"):
         gold[t] = open(os.path.join(REF, "tests", t, "results_true.dat")).read()
     json.dump(gold, open(os.path.join(HERE, "ref_goldens.json"), "w"), indent=1)
 

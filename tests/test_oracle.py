@@ -97,3 +97,54 @@ def test_fixed_source_flux_positive_and_converges():
     phi = s.getFluxes().reshape(-1, ft.num_groups)
     # computeFlux evaluates the source once (Solver.cpp:1390): only the fixed-source group is lit
     assert np.all(phi[:, 0] > 0) and np.all(phi[:, 1:] == 0)
+
+
+# ------------------------------------------------------------------ linear source
+def solve_ls(name, tol=1e-5, max_iters=500):
+    ft, ref = load_case(name)
+    ft.validate()
+    s = OracleSolver(ft, linear_source=True)
+    n = s.computeEigenvalue(max_iters, tol, FISSION_SOURCE)
+    return s, n, ref
+
+
+def test_linear_source_3d_70g_golden_bytes():
+    # tests/test_forward_3D_lattice_linear_70g/results_true.dat: 186 iterations, keff 8.71566E-01
+    s, n, ref = solve_ls("lattice3d_ls_70g", tol=5e-3)
+    assert format_harness_results(n, s.getKeff()) == GOLDENS["test_forward_3D_lattice_linear_70g"]
+    assert n == ref["iterations"] and abs(s.getKeff() - ref["keff"]) < 1e-11
+    assert s.num_flat_fsrs == 200         # "Unable to form linear source components in 200 / 280 source regions"
+
+
+def test_linear_source_3d_7g_golden_bytes():
+    # tests/test_forward_3D_lattice_linear/results_true.dat: 156 iterations, keff 6.89615E-01, 480 FSRs
+    s, n, ref = solve_ls("lattice3d_ls_7g")
+    out = format_harness_results(n, s.getKeff()) + "# FSRs: {0}\n".format(s.ft.n_fsrs)
+    assert out == GOLDENS["test_forward_3D_lattice_linear"]
+    assert n == ref["iterations"] and abs(s.getKeff() - ref["keff"]) < 1e-11
+
+
+def test_linear_source_2d_matches_reference_run():
+    # CPULSSolver on the 2D simple lattice (rings and sectors: centroids away from the cell centres)
+    s, n, ref = solve_ls("simple_lattice_ls")
+    assert n == ref["iterations"] == 188
+    assert abs(s.getKeff() - ref["keff"]) * 1e5 < 1e-6
+    phi, rf = s.getFluxes(), np.array(ref["fluxes"])
+    assert np.max(np.abs(phi - rf) / np.abs(rf)) < 1e-12
+    # the linear source really is in play: the flat-source answer on the same tracks differs
+    flat, n_flat, _ = solve("simple_lattice")
+    assert abs(flat.getKeff() - s.getKeff()) * 1e5 > 50
+    m = s.getFluxMoments().reshape(-1, 3, 7)
+    assert np.abs(m[:, :2]).max() > 1e-3 and np.all(m[:, 2] == 0.0)      # no z moment in 2D
+
+
+def test_linear_source_threads_do_not_change_answer():
+    ft, _ = load_case("simple_lattice_ls")
+    res = []
+    for threads in (1, 4):
+        s = OracleSolver(ft, linear_source=True)
+        s.setNumThreads(threads)
+        s.computeEigenvalue(40, 1e-30, FISSION_SOURCE)
+        res.append((s.getKeff(), s.getFluxes()))
+    assert abs(res[0][0] - res[1][0]) < 1e-12
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-11)
