@@ -224,3 +224,20 @@ def test_track_partition_balance_and_plan_consistency():
         for r in range(world):
             for q in range(world):
                 assert parts[r][1].send_counts[q] == parts[q][1].recv_counts[r]
+
+
+# ------------------------------------------------ linear-source pre-pass (product side, numpy)
+@pytest.mark.parametrize("name", ["simple_lattice_ls", "lattice3d_ls_70g", "lattice3d_ls_7g"])
+def test_linear_expansion_tables_match_the_oracle(name):
+    """openmoc_b200.linear_source restates LinearExpansionGenerator for the Python path; the oracle's
+    restatement of the same pre-pass is pinned to the reference's LS goldens (tests/test_oracle.py)."""
+    from openmoc_b200.linear_source import linear_expansion_tables, track_directions
+    ft, _ = load_case(name)
+    lin_exp, src_const, n_flat = linear_expansion_tables(ft)
+    o = OracleSolver(ft, linear_source=True)
+    ref_lin, ref_src = o.getLinearSourceTables()
+    assert n_flat == o.num_flat_fsrs
+    np.testing.assert_allclose(lin_exp, ref_lin, rtol=1e-9, atol=1e-9 * np.abs(ref_lin).max())
+    np.testing.assert_allclose(src_const, ref_src, rtol=1e-10, atol=1e-13 * np.abs(ref_src).max())
+    d = track_directions(ft)
+    np.testing.assert_allclose(np.linalg.norm(d, axis=1), 1.0, rtol=1e-14)
