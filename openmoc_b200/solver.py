@@ -56,11 +56,15 @@ class B200Solver:
                                (NCCL send/recv)
     deterministic : bool       accumulate the FSR tally in 64-bit fixed point: results are
                                bitwise reproducible run to run (and across GPU counts)
+    linear_source : bool       CPULSSolver physics (src/CPULSSolver.cpp): needs a track file dumped
+                               after a linear-source initialisation (centroid-relative segment
+                               starting points, quadrature factors); the pre-pass tables come from
+                               openmoc_b200.linear_source.  One GPU only in this build.
     """
 
     def __init__(self, tracks: FlatTracks, device: int = 0, precision: int = PRECISION_DOUBLE,
                  process_group=None, use_distributed: Optional[bool] = None, deterministic: bool = False,
-                 partition: str = "pair"):
+                 partition: str = "pair", linear_source: bool = False):
         self._lib = capi.load()
         self._h = C.c_void_p()
         self._global_tracks = tracks
@@ -77,6 +81,21 @@ class B200Solver:
                 self._pg = process_group
                 self._rank = dist.get_rank(process_group)
                 self._world = dist.get_world_size(process_group)
+        self._linear = bool(linear_source)
+        self._ls_tables = None
+        if self._linear:
+            if self._world > 1:
+                raise B200Error("linear source across several GPUs is not supported in this build "
+                                "(the moment tallies are not all-reduced)")
+            if deterministic:
+                raise B200Error("the deterministic tally is not available with the linear source")
+            from .linear_source import linear_expansion_tables, track_directions
+            if tracks.arrays.get("seg_start", np.zeros(0)).size != 3 * tracks.n_segments:
+                raise B200Error("linear source needs the segment starting points (seg_start) in the track file")
+            lin_exp, src_const, self.num_flat_fsrs = linear_expansion_tables(tracks)
+            self._ls_tables = (np.ascontiguousarray(tracks.arrays["seg_start"], dtype="f8"),
+                               np.ascontiguousarray(track_directions(tracks).ravel(), dtype="f8"),
+                               np.ascontiguousarray(lin_exp), np.ascontiguousarray(src_const))
         if self._world > 1:
             from .partition import partition_by_azim_pair, partition_by_chain, partition_by_track
             if partition == "chain":
@@ -100,7 +119,8 @@ class B200Solver:
         cfg = Config(num_groups=tracks.num_groups, num_azim=tracks.num_azim, num_polar=tracks.num_polar,
                      solve_3d=tracks.solve_3d, n_tracks=tracks.n_tracks, n_segments=tracks.n_segments,
                      n_fsrs=tracks.n_fsrs, n_materials=tracks.n_materials, device=device,
-                     precision=precision, deterministic=int(bool(deterministic)), n_fsrs_global=tracks.n_fsrs)
+                     precision=precision, deterministic=int(bool(deterministic)), n_fsrs_global=tracks.n_fsrs,
+                     linear_source=int(self._linear))
         self._deterministic = bool(deterministic)
         check(self._lib.b200_create(C.byref(cfg), C.byref(self._h)))
         self._upload(tracks)
@@ -124,6 +144,8 @@ class B200Solver:
                 c("mat_nu_sigma_f", "f8"), c("mat_sigma_f", "f8"), c("mat_chi", "f8"),
                 c("mat_fissionable", "u1")]
         check(L.b200_upload_materials(h, *[_ptr(x) for x in mats]))
+        if self._ls_tables is not None:
+            check(L.b200_upload_linear_source(h, *[_ptr(x) for x in self._ls_tables]))
         check(L.b200_finalize(h))
 
     def close(self) -> None:
@@ -168,6 +190,12 @@ class B200Solver:
     def setFluxes(self, in_fluxes) -> None:
         x = np.ascontiguousarray(in_fluxes, dtype=np.float64).ravel()
         check(self._lib.b200_set_fluxes(self._h, _ptr(x), x.size))
+
+    def getFluxMoments(self) -> np.ndarray:
+        """Scalar flux moments [n_fsrs][3][G] of the linear-source solver (src/CPULSSolver.h:22-26)."""
+        out = np.empty(self._num_FSRs * 3 * self._num_groups, dtype=np.float64)
+        check(self._lib.b200_get_flux_moments(self._h, _ptr(out), out.size))
+        return out
 
     def getFlux(self, fsr_id: int, group: int) -> float:
         """1-based group like Solver::getFlux (Solver.cpp:277-305)."""
@@ -314,7 +342,10 @@ class B200Solver:
     def computeEigenvalue(self, max_iters: int = 1000, res_type: int = FISSION_SOURCE) -> None:
         """Solver::computeEigenvalue (src/Solver.cpp:1542-1689), no CMFD."""
         t0 = time.perf_counter()
-        if self._world == 1:
+        if self._linear:
+            # step by step through the Solver virtuals, exactly what B200LSSolver does in the reference's loop
+            self._num_iterations = self._eigenvalue_loop(max_iters, res_type)
+        elif self._world == 1:
             n = C.c_int32()
             check(self._lib.b200_compute_eigenvalue(self._h, int(max_iters), self._converge_thresh,
                                                     int(res_type), C.byref(n)))
