@@ -346,28 +346,3 @@ def test_cuda_graph_replay_equals_plain_launches(monkeypatch, max_iters):
     assert abs(a[1] - b[1]) < 1e-12
     np.testing.assert_allclose(b[2], a[2], rtol=1e-11)
     np.testing.assert_allclose(b[3], a[3], rtol=1e-5, atol=1e-12)     # boundary fluxes: buffer parity is right
-
-
-# ------------------------------------------------------------ linear source, Python path
-# Written after the round's GPU budget was spent: the device kernels behind it are the ones the C++
-# plug-in tests exercise (tests/test_gpu_plugin.py), the pre-pass tables are checked on the CPU
-# (tests/test_host_logic.py), but this ctypes path itself has not run on hardware yet - hence
-# xfail(strict=False): a pass shows up as XPASS, a failure does not break the suite.
-@pytest.mark.xfail(reason="not yet run on hardware (added after the GPU budget was spent)", strict=False)
-@pytest.mark.parametrize("name,tol", [("simple_lattice_ls", 1e-5), ("lattice3d_ls_70g", 5e-3), ("lattice3d_ls_7g", 1e-5)])
-def test_python_linear_source_matches_oracle_and_goldens(name, tol):
-    from openmoc_b200.solver import B200Solver
-    ft, ref = load_case(name)
-    gpu = B200Solver(ft, linear_source=True)
-    cpu = OracleSolver(ft, linear_source=True)
-    gpu.setConvergenceThreshold(tol)
-    gpu.computeEigenvalue(500, FISSION_SOURCE)
-    n = cpu.computeEigenvalue(500, tol, FISSION_SOURCE)
-    assert gpu.getNumIterations() == n == ref["iterations"]
-    assert abs(gpu.getKeff() - cpu.getKeff()) * 1e5 < K_TOL_PCM
-    assert rel_err(gpu.getFluxes(), cpu.getFluxes()) < PHI_RTOL
-    assert abs(gpu.getKeff() - ref["keff"]) * 1e5 < 1e-4 and rel_err(gpu.getFluxes(), cpu.getFluxes()) < 1e-8
-    m_g, m_c = gpu.getFluxMoments(), cpu.getFluxMoments()
-    np.testing.assert_allclose(m_g, m_c, rtol=1e-6, atol=1e-9 * np.abs(m_c).max())
-    if name == "lattice3d_ls_70g":
-        assert format_harness_results(gpu.getNumIterations(), gpu.getKeff()) == GOLDENS["test_forward_3D_lattice_linear_70g"]

@@ -1,0 +1,62 @@
+"""Linear source through the Python mirror (B200Solver(linear_source=True)) against the LS oracle and
+the reference's LS goldens.
+
+Written after the round's GPU budget was spent.  The device kernels behind it are the ones the C++
+plug-in tests exercise (tests/test_gpu_plugin.py) and the pre-pass tables are checked on the CPU
+(tests/test_host_logic.py), but this ctypes path itself has not run on hardware yet.  Hence:
+  * xfail(strict=False): a pass shows up as XPASS, a failure does not break the suite;
+  * the GPU work runs in a child process, so that a fault could not leave a poisoned CUDA context
+    behind for other tests (the file name sorts last for the same reason).
+"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+
+CHILD = r"""
+import json, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+import numpy as np
+from conftest import load_case
+from openmoc_b200.solver import B200Solver
+from openmoc_b200.capi import FISSION_SOURCE
+from oracle.oracle_py import OracleSolver, format_harness_results
+ft, ref = load_case(%(name)r)
+gpu = B200Solver(ft, linear_source=True)
+cpu = OracleSolver(ft, linear_source=True)
+gpu.setConvergenceThreshold(%(tol)r)
+gpu.computeEigenvalue(500, FISSION_SOURCE)
+n = cpu.computeEigenvalue(500, %(tol)r, FISSION_SOURCE)
+pg, pc = gpu.getFluxes(), cpu.getFluxes()
+mg, mc = gpu.getFluxMoments(), cpu.getFluxMoments()
+print("RESULT " + json.dumps({
+    "gpu_iters": gpu.getNumIterations(), "cpu_iters": n, "ref_iters": ref["iterations"],
+    "dk_pcm": abs(gpu.getKeff() - cpu.getKeff()) * 1e5, "dk_ref_pcm": abs(gpu.getKeff() - ref["keff"]) * 1e5,
+    "flux_err": float(np.max(np.abs(pg - pc) / np.abs(pc))),
+    "moment_err": float(np.max(np.abs(mg - mc)) / np.abs(mc).max()),
+    "harness": format_harness_results(gpu.getNumIterations(), gpu.getKeff())}))
+"""
+
+
+@pytest.mark.xfail(reason="not yet run on hardware (added after the GPU budget was spent)", strict=False)
+@pytest.mark.parametrize("name,tol,golden", [("simple_lattice_ls", 1e-5, None),
+                                             ("lattice3d_ls_70g", 5e-3, "test_forward_3D_lattice_linear_70g"),
+                                             ("lattice3d_ls_7g", 1e-5, None)])
+def test_python_linear_source_matches_oracle_and_goldens(name, tol, golden):
+    out = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT, "name": name, "tol": tol}],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    print(r)
+    assert r["gpu_iters"] == r["cpu_iters"] == r["ref_iters"]
+    assert r["dk_pcm"] < 1.0 and r["flux_err"] < 1e-4             # north_star
+    assert r["dk_ref_pcm"] < 1e-4 and r["flux_err"] < 1e-8 and r["moment_err"] < 1e-8
+    if golden:
+        goldens = json.load(open(os.path.join(GOLDEN, "ref_goldens.json")))
+        assert r["harness"] == goldens[golden]
