@@ -64,6 +64,8 @@ struct Gen {
   std::vector<uint8_t> trk_flags, trk_bc_fwd, trk_bc_bwd;
   std::vector<double> trk_phi, trk_theta, trk_start;
   std::vector<double> quad_weight, quad_sin_theta;
+  /* factors of the total weight, for the linear-source pre-pass (track file chunks of the same name) */
+  std::vector<double> quad_azim_spacing, quad_azim_weight, quad_polar_spacing, quad_polar_weight;
   std::vector<double> fsr_volume;
   std::vector<int32_t> fsr_mat;
   std::vector<int64_t> fsr_base;
@@ -288,12 +290,17 @@ int build(Gen& g, int polar_quad) {
   /* total weights, 2D form (src/Quadrature.cpp:727-741), mirrored over polar halves */
   g.quad_weight.assign((size_t)A2 * P, 0.);
   g.quad_sin_theta.assign((size_t)A2 * P, 0.);
+  g.quad_azim_spacing.assign(azim_spacing.begin(), azim_spacing.end());
+  g.quad_azim_weight.assign(azim_weight.begin(), azim_weight.end());
+  g.quad_polar_spacing.assign((size_t)A2 * P, 0.);          /* 2D: no polar spacing */
+  g.quad_polar_weight.assign((size_t)A2 * P, 0.);
   for (int a = 0; a < A2; a++)
     for (int p = 0; p < P2; p++) {
       const double st = sin(theta[p]);
       const double w = 2.0 * M_PI * azim_weight[a] * azim_spacing[a] * pw[p] * 2.0 * st;
       g.quad_weight[a * P + p] = g.quad_weight[a * P + (P - 1 - p)] = w;
       g.quad_sin_theta[a * P + p] = g.quad_sin_theta[a * P + (P - 1 - p)] = st;
+      g.quad_polar_weight[a * P + p] = g.quad_polar_weight[a * P + (P - 1 - p)] = pw[p];
     }
 
   /* ---- tracks: start / end points (src/TrackGenerator.cpp:1013-1062) ---- */
@@ -463,6 +470,7 @@ int64_t b200_trackgen_get(b200_trackgen* h, const char* name, void* dst) {
   OUT(seg_length) OUT(seg_fsr) OUT(seg_mat) OUT(trk_seg_offset) OUT(trk_next_fwd) OUT(trk_next_bwd)
   OUT(trk_azim) OUT(trk_polar) OUT(trk_xy) OUT(trk_flags) OUT(trk_bc_fwd) OUT(trk_bc_bwd) OUT(trk_phi)
   OUT(trk_theta) OUT(trk_start) OUT(quad_weight) OUT(quad_sin_theta) OUT(fsr_volume) OUT(fsr_mat)
+  OUT(quad_azim_spacing) OUT(quad_azim_weight) OUT(quad_polar_spacing) OUT(quad_polar_weight)
 #undef OUT
   return -1;
 }

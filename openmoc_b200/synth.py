@@ -189,10 +189,11 @@ def materials_70g(names: List[str]) -> Dict[str, np.ndarray]:
 def make_tracks(model: str, num_azim: int = 4, spacing: float = 0.1, num_polar: int = 6,
                 polar_quad: int = None, num_threads: int = 0,
                 fsr_numbering: str = "discovery", groups70: bool = False,
-                as_3d: bool = False) -> FlatTracks:
+                as_3d: bool = False, linear_source: bool = False) -> FlatTracks:
     """fsr_numbering: "discovery" (reference order, untouched regions dropped) or
     "lattice" (by lattice cell, every geometric region kept).
     groups70: swap the C5G7 data for the reference's synthetic 70-group set.
+    linear_source: also produce the FSR centroids and centroid-relative segment starting points.
     as_3d: label the tracks as 3D tracks of polar index 0 (one angular flux per group per
     track, F = G) - a kernel-shape stand-in for 3D decks, not a physical 3D problem."""
     L = _load()
@@ -212,7 +213,9 @@ def make_tracks(model: str, num_azim: int = 4, spacing: float = 0.1, num_polar: 
                   "trk_next_fwd": "i8", "trk_next_bwd": "i8", "trk_azim": "i4", "trk_polar": "i4",
                   "trk_xy": "i4", "trk_flags": "u1", "trk_bc_fwd": "u1", "trk_bc_bwd": "u1",
                   "trk_phi": "f8", "trk_theta": "f8", "trk_start": "f8", "quad_weight": "f8",
-                  "quad_sin_theta": "f8", "fsr_volume": "f8", "fsr_mat": "i4"}
+                  "quad_sin_theta": "f8", "fsr_volume": "f8", "fsr_mat": "i4",
+                  "quad_azim_spacing": "f8", "quad_azim_weight": "f8", "quad_polar_spacing": "f8",
+                  "quad_polar_weight": "f8"}
         arrays = {}
         for k, dt in dtypes.items():
             n = L.b200_trackgen_get(h, k.encode(), None)
@@ -232,4 +235,35 @@ def make_tracks(model: str, num_azim: int = 4, spacing: float = 0.1, num_polar: 
                     fluxes_per_track=G if as_3d else G * num_polar // 2, n_tracks=int(arrays["trk_azim"].size),
                     n_segments=int(arrays["seg_length"].size), n_fsrs=int(arrays["fsr_volume"].size),
                     n_materials=len(names), arrays=arrays)
+    if linear_source:
+        add_linear_source_data(ft)
     return ft
+
+
+def add_linear_source_data(ft: FlatTracks) -> None:
+    """What a linear-source solve needs on top of the flat data (2D decks): FSR centroids from the
+    tracks (CentroidGenerator::onTrack, src/TrackTraversingAlgorithms.cpp:377-460) and the starting
+    point of every segment relative to the centroid of its FSR (RecenterSegments, :1322-1332)."""
+    if ft.solve_3d:
+        raise ValueError("synthetic linear-source data exist for 2D decks only")
+    a = ft.arrays
+    off = a["trk_seg_offset"].astype(np.int64)
+    nseg = np.diff(off)
+    trk = np.repeat(np.arange(ft.n_tracks), nseg)
+    length = a["seg_length"]
+    before = np.cumsum(length) - length                       # arc length before each segment ...
+    first = np.minimum(off[:-1], max(ft.n_segments - 1, 0))
+    before -= np.repeat(np.where(nseg > 0, before[first], 0.0), nseg)    # ... counted from the track start
+    phi = a["trk_phi"][trk]
+    cos_phi, sin_phi = np.cos(phi), np.sin(phi)
+    start = a["trk_start"].reshape(-1, 2)[trk]
+    x = start[:, 0] + before * cos_phi
+    y = start[:, 1] + before * sin_phi
+    azim = a["trk_azim"][trk].astype(np.int64)
+    wgt = a["quad_azim_spacing"][azim] * a["quad_azim_weight"][azim]
+    fsr = a["seg_fsr"].astype(np.int64)
+    vol = a["fsr_volume"][fsr]
+    cx = np.bincount(fsr, weights=wgt * (x + cos_phi * length / 2.0) * length / vol, minlength=ft.n_fsrs)
+    cy = np.bincount(fsr, weights=wgt * (y + sin_phi * length / 2.0) * length / vol, minlength=ft.n_fsrs)
+    a["fsr_centroid"] = np.stack([cx, cy, np.zeros_like(cx)], axis=1).ravel()
+    a["seg_start"] = np.stack([x - cx[fsr], y - cy[fsr], np.zeros_like(x)], axis=1).ravel()

@@ -69,3 +69,22 @@ def test_bad_arguments():
         make_tracks("pin-cell", num_azim=6)
     with pytest.raises(ValueError):
         make_tracks("pin-cell", num_polar=8)      # TY has 2, 4, 6
+
+
+def test_linear_source_data_match_a_reference_cpulssolver_dump():
+    """FSR centroids, centroid-relative segment starting points and the quadrature factors of the
+    synthetic generator against the track file dumped after a reference CPULSSolver run; the LS oracle
+    (pinned to the reference's LS goldens) then gives the reference's k_eff on the synthetic tracks."""
+    import numpy as np
+    from oracle.oracle_py import OracleSolver
+    ref, rj = load_case("simple_lattice_ls")
+    ft = make_tracks("simple-lattice", num_azim=4, spacing=0.12, linear_source=True)
+    assert np.array_equal(ft.arrays["seg_fsr"], ref.arrays["seg_fsr"])
+    for k in ("quad_azim_spacing", "quad_azim_weight", "quad_polar_weight", "quad_polar_spacing"):
+        np.testing.assert_allclose(ft.arrays[k], ref.arrays[k], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(ft.arrays["fsr_centroid"], ref.arrays["fsr_centroid"], atol=1e-9)
+    np.testing.assert_allclose(ft.arrays["seg_start"], ref.arrays["seg_start"], atol=5e-8)
+    o = OracleSolver(ft, linear_source=True)
+    n = o.computeEigenvalue(500, 1e-5)
+    assert n == rj["iterations"]
+    assert abs(o.getKeff() - rj["keff"]) * 1e5 < 1e-3
