@@ -17,10 +17,12 @@ ap.add_argument("--precision", default="double")
 ap.add_argument("--groups70", action="store_true")
 ap.add_argument("--as3d", action="store_true")
 ap.add_argument("--deterministic", action="store_true")
+ap.add_argument("--ls", action="store_true", help="linear source (2D synthetic decks)")
 args = ap.parse_args()
-ft = make_tracks(args.model, num_azim=args.azim, spacing=args.spacing, groups70=args.groups70, as_3d=args.as3d)
+ft = make_tracks(args.model, num_azim=args.azim, spacing=args.spacing, groups70=args.groups70, as_3d=args.as3d,
+                 linear_source=args.ls)
 s = B200Solver(ft, precision=capi.PRECISION_MIXED if args.precision == "mixed" else capi.PRECISION_DOUBLE,
-               deterministic=args.deterministic)
+               deterministic=args.deterministic, linear_source=args.ls)
 s.zeroTrackFluxes(); s.flattenFSRFluxes(1.0); s.normalizeFluxes(); s.storeFSRFluxes()
 s.computeFSRSources(0)
 for _ in range(3):
