@@ -61,9 +61,10 @@ def track_components(ft: FlatTracks) -> np.ndarray:
     return labels
 
 
-def partition_by_chain(ft: FlatTracks, world: int) -> List[FlatTracks]:
+def partition_by_chain(ft: FlatTracks, world: int, only: int = None) -> List[FlatTracks]:
     """Shard whole track chains (connected components of the link graph) across `world`
-    ranks, longest-processing-time first by segment count."""
+    ranks, longest-processing-time first by segment count.  `only`: build that rank's shard
+    alone (None for the others)."""
     labels = track_components(ft)
     nseg = np.diff(ft.arrays["trk_seg_offset"].astype(np.int64))
     n_comp = int(labels.max()) + 1 if labels.size else 0
@@ -78,16 +79,18 @@ def partition_by_chain(ft: FlatTracks, world: int) -> List[FlatTracks]:
         owner[c] = r
         totals[r] += load[c]
     track_owner = owner[labels]
-    return [_extract(ft, np.nonzero(track_owner == r)[0]) for r in range(world)]
+    return [_extract(ft, np.nonzero(track_owner == r)[0]) if only is None or r == only else None
+            for r in range(world)]
 
 
-def partition_by_azim_pair(ft: FlatTracks, world: int) -> List[FlatTracks]:
+def partition_by_azim_pair(ft: FlatTracks, world: int, only: int = None) -> List[FlatTracks]:
     a = ft.arrays
     nseg = np.diff(a["trk_seg_offset"].astype(np.int64))
     azim = a["trk_azim"].astype(np.int64)
     seg_per_azim = np.bincount(azim, weights=nseg, minlength=ft.num_azim // 2)
     owned = assign_pairs(ft.num_azim, seg_per_azim, world)
-    return [_extract(ft, np.nonzero(np.isin(azim, owned[rank]))[0]) for rank in range(world)]
+    return [_extract(ft, np.nonzero(np.isin(azim, owned[rank]))[0]) if only is None or rank == only else None
+            for rank in range(world)]
 
 
 def _extract(ft: FlatTracks, ids: np.ndarray, closed: bool = True) -> FlatTracks:

@@ -99,9 +99,9 @@ class B200Solver:
         if self._world > 1:
             from .partition import partition_by_azim_pair, partition_by_chain, partition_by_track
             if partition == "chain":
-                tracks = partition_by_chain(tracks, self._world)[self._rank]
+                tracks = partition_by_chain(tracks, self._world, only=self._rank)[self._rank]
             elif partition == "pair":
-                tracks = partition_by_azim_pair(tracks, self._world)[self._rank]
+                tracks = partition_by_azim_pair(tracks, self._world, only=self._rank)[self._rank]
             elif partition == "track":
                 tracks, self._plan = partition_by_track(tracks, self._world, only=self._rank)[self._rank]
             else:
