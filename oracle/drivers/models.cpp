@@ -165,6 +165,45 @@ Model hom_inf(int) {
   return md;
 }
 
+/* ------- tests/test_compute_flux/test_compute_flux.py:18-79 (same deck in test_compute_source) ------- */
+Model water_box(int) {
+  Model md;
+  md.materials = make_c5g7_materials();
+  Material* water = md.materials["Water"];
+  const double length = 2.5; const int n = 10;
+  XPlane* xmin = new XPlane(-length / 2.); XPlane* xmax = new XPlane(length / 2.);
+  YPlane* ymin = new YPlane(-length / 2.); YPlane* ymax = new YPlane(length / 2.);
+  xmin->setBoundaryType(VACUUM); xmax->setBoundaryType(VACUUM);
+  ymin->setBoundaryType(VACUUM); ymax->setBoundaryType(VACUUM);
+  Cell* root_cell = new Cell();
+  root_cell->addSurface(+1, xmin); root_cell->addSurface(-1, xmax);
+  root_cell->addSurface(+1, ymin); root_cell->addSurface(-1, ymax);
+  Cell* water_cell = new Cell();
+  water_cell->setFill(water);
+  Universe* water_u = new Universe();
+  water_u->addCell(water_cell);
+  Cell* source_cell = new Cell();
+  source_cell->setFill(water);
+  Universe* source_u = new Universe();
+  source_u->addCell(source_cell);
+  /* universes[0][int(lat_x)][int(lat_y)] with lat = (max - 0.5) / width = 3: fourth row from the
+   * top, fourth column (the nested list is rows top-down) */
+  std::vector<Universe*> rows(n * n, water_u);
+  const double w = length / n;
+  const int lat_x = (int)((length / 2. - 0.5) / w), lat_y = (int)((length / 2. - 0.5) / w);
+  rows[lat_x * n + lat_y] = source_u;
+  Lattice* lat = new Lattice();
+  lat->setWidth(w, w);
+  fill_lattice(lat, n, n, rows);
+  root_cell->setFill(lat);
+  Universe* root = new Universe();
+  root->addCell(root_cell);
+  md.geometry = new Geometry();
+  md.geometry->setRootUniverse(root);
+  md.source_cell = source_cell;
+  return md;
+}
+
 /* ------- sample-input/benchmarks/c5g7/{surfaces,cells,universes,lattices,c5g7-2d}.py ------- */
 Model c5g7_2d(int dims) {
   Model md;
@@ -303,6 +342,7 @@ Model build_model(const std::string& name, int dims) {
   if (name == "pin-cell") return pin_cell(dims);
   if (name == "simple-lattice") return simple_lattice(dims);
   if (name == "hom-inf") return hom_inf(dims);
+  if (name == "water-box") return water_box(dims);
   if (name == "c5g7-2d") return c5g7_2d(dims);
   log_printf(ERROR, "unknown model %s", name.c_str());
   return Model();

@@ -9,6 +9,9 @@
  *  c5g7-2d         sample-input/benchmarks/c5g7/{surfaces,cells,universes,
  *                  lattices,c5g7-2d}.py
  *  hom-inf         tests/input_set.py:32-92    (HomInfMedInput)
+ *  water-box       tests/test_compute_flux/test_compute_flux.py:18-79 and test_compute_source:
+ *                  HomInfMedInput's 10x10 lattice with VACUUM sides, filled with C5G7 water, one
+ *                  lattice cell (the "source" cell) holding the fixed source
  */
 #ifndef ORACLE_MODELS_H_
 #define ORACLE_MODELS_H_
@@ -19,9 +22,11 @@
 class Geometry;
 class Material;
 
+class Cell;
 struct Model {
   Geometry* geometry;
   std::map<std::string, Material*> materials;
+  Cell* source_cell = nullptr;      /* water-box: the cell Solver::setFixedSourceByCell is given */
 };
 
 /** dims = 2 or 3 (only simple-lattice and pin-cell honour 3). */

@@ -195,12 +195,31 @@ int main(int argc, char** argv) {
   solver->setConvergenceThreshold(tol);
   if (flag(argc, argv, "--balance")) solver->setKeffFromNeutronBalance();   /* Solver.cpp:2047 */
 
+  /* --fixed-source g:value[,g:value...] on the model's source cell (Solver::setFixedSourceByCell) */
+  std::string fixed = arg(argc, argv, "--fixed-source", "");
+  if (!fixed.empty()) {
+    if (md.source_cell == NULL) { fprintf(stderr, "ref_driver: model has no source cell\n"); return 2; }
+    size_t pos = 0;
+    while (pos < fixed.size()) {
+      int g = 0; double v = 0.; int used = 0;
+      if (sscanf(fixed.c_str() + pos, "%d:%lf%n", &g, &v, &used) != 2) break;
+      solver->setFixedSourceByCell(md.source_cell, g, v);
+      pos += used;
+      if (pos < fixed.size() && fixed[pos] == ',') pos++;
+    }
+  }
+
   if (mode == "eigen") {
     if (solver_name == "b200-fused") b200_solver->computeEigenvalueFused(max_iters, rt);
     else solver->computeEigenvalue(max_iters, rt);
+  } else if (mode == "flux") {
+    solver->computeFlux(max_iters);                       /* tests/testing_harness.py:151 */
+  } else if (mode == "source") {
+    solver->computeSource(max_iters, 1.0, rt);            /* tests/testing_harness.py:153 */
   } else {
     solver->initializeSolver(FORWARD);
   }
+  const bool solved = (mode == "eigen" || mode == "flux" || mode == "source");
 
   long n_fsr = geometry->getNumFSRs();
   int G = geometry->getNumEnergyGroups();
@@ -208,13 +227,13 @@ int main(int argc, char** argv) {
   long n_seg = tg->getNumSegments();
   int F = (dims == 3) ? G : G * tg->getQuadrature()->getNumPolarAngles() / 2;
 
-  if (mode == "eigen" && !flag(argc, argv, "--quiet")) solver->printTimerReport();
+  if (solved && !flag(argc, argv, "--quiet")) solver->printTimerReport();
 
   /* ---- results in the harness format ---- */
-  if (mode == "eigen" && !results.empty()) {
+  if (solved && !results.empty()) {
     FILE* f = fopen(results.c_str(), "w");
     fprintf(f, "# Iterations: %d\n", solver->getNumIterations());
-    fprintf(f, "keff: %12.5E\n", solver->getKeff());
+    if (mode == "eigen") fprintf(f, "keff: %12.5E\n", solver->getKeff());
     if (fluxes_in_results) {
       fprintf(f, "fluxes:\n");
       std::vector<FP_PRECISION> phi(n_fsr * G);
@@ -228,7 +247,7 @@ int main(int argc, char** argv) {
   if (!json.empty()) {
     FILE* f = fopen(json.c_str(), "w");
     double sweep_time = 0., total_time = 0.;
-    if (mode == "eigen") {
+    if (solved) {
       Timer timer;  /* splits are static/shared in the reference's Timer */
       sweep_time = timer.getSplit("Transport Sweep");
       total_time = timer.getSplit("Total time");
@@ -239,8 +258,19 @@ int main(int argc, char** argv) {
             (int)tg->getQuadrature()->getNumPolarAngles(), solver_name.c_str(), threads, tol);
     fprintf(f, " \"n_tracks\": %ld, \"n_segments\": %ld, \"n_fsrs\": %ld, \"num_groups\": %d, "
                "\"fluxes_per_track\": %d,\n", n_trk, n_seg, n_fsr, G, F);
-    if (mode == "eigen") {
+    if (solved) {
       int it = solver->getNumIterations();
+      /* FSRs of the source cell, so that a flattened replay can place the same fixed source */
+      if (md.source_cell != NULL) {
+        fprintf(f, " \"source_fsrs\": [");
+        bool first_fsr = true;
+        for (long r = 0; r < n_fsr; r++)
+          if (geometry->findCellContainingFSR(r) == md.source_cell) {
+            fprintf(f, "%s%ld", first_fsr ? "" : ", ", r);
+            first_fsr = false;
+          }
+        fprintf(f, "],\n");
+      }
       fprintf(f, " \"iterations\": %d, \"keff\": %.17g, \"sweep_time_s\": %.9g, "
                  "\"total_time_s\": %.9g, \"integrations\": %.17g,\n",
               it, solver->getKeff(), sweep_time, total_time, 2.0 * F * (double)n_seg * it);

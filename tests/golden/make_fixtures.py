@@ -32,6 +32,9 @@ CASES = {
     # EqualAnglePolarQuad is discarded by generateTracks for want of setNumAzimAngles.
     "c5g7_2d_coarse": ["--model", "c5g7-2d", "--azim", "4", "--spacing", "0.5", "--polar", "6",
                        "--max-iters", "40", "--no-fluxes"],
+    # fixed-source decks: the track file is shared by test_compute_flux and test_compute_source
+    "water_box": ["--model", "water-box", "--azim", "4", "--spacing", "0.1", "--mode", "flux",
+                  "--fixed-source", "1:1.0,2:0.5,3:0.25", "--res", "flux"],
     # linear source (CPULSSolver): the track files carry the centroid-relative segment starting
     # points and the quadrature factors the LinearExpansionGenerator pre-pass needs
     "simple_lattice_ls": ["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12", "--solver", "cpuls"],
@@ -57,7 +60,8 @@ def main():
     gold = {}
     for t in ("test_forward_pin_cell", "test_forward_simple_lattice", "test_forward_3D_lattice_70g",
               "test_forward_3D_lattice", "test_forward_hom_inf_medium",
-              "test_forward_3D_lattice_linear", "test_forward_3D_lattice_linear_70g"):
+              "test_forward_3D_lattice_linear", "test_forward_3D_lattice_linear_70g",
+              "test_compute_flux", "test_compute_source"):
         gold[t] = open(os.path.join(REF, "tests", t, "results_true.dat")).read()
     json.dump(gold, open(os.path.join(HERE, "ref_goldens.json"), "w"), indent=1)
 

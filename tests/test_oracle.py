@@ -148,3 +148,33 @@ def test_linear_source_threads_do_not_change_answer():
         res.append((s.getKeff(), s.getFluxes()))
     assert abs(res[0][0] - res[1][0]) < 1e-12
     np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-11)
+
+
+# ------------------------------------------------------------------ fixed-source drivers
+def format_flux_results(num_iters, fluxes):
+    """tests/testing_harness.py:158-207 for solution types without an eigenvalue"""
+    return ("# Iterations: {0}\n".format(num_iters) + "fluxes:\n"
+            + "\n".join("{0:12.6E}".format(f) for f in np.ravel(fluxes)) + "\n")
+
+
+def test_compute_flux_golden_bytes():
+    # tests/test_compute_flux: water box with VACUUM sides, fixed source 1.0 / 0.5 / 0.25 in groups 1-3
+    ft, ref = load_case("water_box")
+    s = OracleSolver(ft)
+    for fsr in ref["source_fsrs"]:
+        for group, value in ((1, 1.0), (2, 0.5), (3, 0.25)):
+            s.setFixedSourceByFSR(fsr, group, value)
+    n = s.computeFlux(500, 1e-5, True)
+    assert format_flux_results(n, s.getFluxes()) == GOLDENS["test_compute_flux"]
+    np.testing.assert_allclose(s.getFluxes(), ref["fluxes"], rtol=1e-12)
+
+
+def test_compute_source_golden_bytes():
+    # tests/test_compute_source: same deck, source 1.0 in group 1, computeSource with TOTAL_SOURCE residual
+    ft, ref = load_case("water_box")
+    s = OracleSolver(ft)
+    for fsr in ref["source_fsrs"]:
+        s.setFixedSourceByFSR(fsr, 1, 1.0)
+    n = s.computeSource(500, 1.0, 1e-5, TOTAL_SOURCE)
+    assert n == 130
+    assert format_flux_results(n, s.getFluxes()) == GOLDENS["test_compute_source"]

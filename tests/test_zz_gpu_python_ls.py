@@ -1,5 +1,5 @@
 """Linear source through the Python mirror (B200Solver(linear_source=True)) against the LS oracle and
-the reference's LS goldens.
+the reference's LS goldens; the reference's compute_flux / compute_source goldens from the GPU.
 
 Written after the round's GPU budget was spent.  The device kernels behind it are the ones the C++
 plug-in tests exercise (tests/test_gpu_plugin.py) and the pre-pass tables are checked on the CPU
@@ -60,3 +60,42 @@ def test_python_linear_source_matches_oracle_and_goldens(name, tol, golden):
     if golden:
         goldens = json.load(open(os.path.join(GOLDEN, "ref_goldens.json")))
         assert r["harness"] == goldens[golden]
+
+
+# ---- fixed-source goldens from the GPU (same status: written after the GPU budget was spent) ----
+CHILD_FIXED = r"""
+import json, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+import numpy as np
+from conftest import load_case
+from openmoc_b200.solver import B200Solver
+from openmoc_b200.capi import TOTAL_SOURCE
+ft, ref = load_case("water_box")
+def fmt(n, fluxes):
+    return "# Iterations: {0}\n".format(n) + "fluxes:\n" + "\n".join("{0:12.6E}".format(f) for f in fluxes) + "\n"
+s = B200Solver(ft)
+s.setConvergenceThreshold(1e-5)
+for fsr in ref["source_fsrs"]:
+    for group, value in ((1, 1.0), (2, 0.5), (3, 0.25)):
+        s.setFixedSourceByFSR(fsr, group, value)
+s.computeFlux(500)
+flux = fmt(s.getNumIterations(), s.getFluxes())
+s = B200Solver(ft)
+s.setConvergenceThreshold(1e-5)
+for fsr in ref["source_fsrs"]:
+    s.setFixedSourceByFSR(fsr, 1, 1.0)
+s.computeSource(500, 1.0, TOTAL_SOURCE)
+source = fmt(s.getNumIterations(), s.getFluxes())
+print("RESULT " + json.dumps({"flux": flux, "source": source}))
+"""
+
+
+@pytest.mark.xfail(reason="not yet run on hardware (added after the GPU budget was spent)", strict=False)
+def test_compute_flux_and_source_goldens_from_gpu():
+    """tests/test_compute_flux and tests/test_compute_source results_true.dat, byte for byte from the GPU"""
+    out = subprocess.run([sys.executable, "-c", CHILD_FIXED % {"root": ROOT}], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    goldens = json.load(open(os.path.join(GOLDEN, "ref_goldens.json")))
+    assert r["flux"] == goldens["test_compute_flux"]
+    assert r["source"] == goldens["test_compute_source"]
