@@ -15,6 +15,8 @@
  *   tests/test_forward_3D_lattice/results_true.dat, test_forward_hom_inf_medium
  *   tests/test_forward_3D_lattice_linear/results_true.dat      (linear source: 156 it, k, 480 FSRs)
  *   tests/test_forward_3D_lattice_linear_70g/results_true.dat  (linear source: 186 it, k)
+ *   tests/test_compute_flux, tests/test_compute_source         (fixed-source drivers: 2 / 130 it)
+ *   tests/test_adjoint_{pin_cell,simple_lattice,hom_inf_medium} (transposed production matrices)
  *   tests/unit_tests/test_exponentials.py:74-77            (expF1 known answers)
  *
  * Every function cites the reference file:line it follows

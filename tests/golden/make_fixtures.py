@@ -61,7 +61,8 @@ def main():
     for t in ("test_forward_pin_cell", "test_forward_simple_lattice", "test_forward_3D_lattice_70g",
               "test_forward_3D_lattice", "test_forward_hom_inf_medium",
               "test_forward_3D_lattice_linear", "test_forward_3D_lattice_linear_70g",
-              "test_compute_flux", "test_compute_source"):
+              "test_compute_flux", "test_compute_source",
+              "test_adjoint_pin_cell", "test_adjoint_simple_lattice", "test_adjoint_hom_inf_medium"):
         gold[t] = open(os.path.join(REF, "tests", t, "results_true.dat")).read()
     json.dump(gold, open(os.path.join(HERE, "ref_goldens.json"), "w"), indent=1)
 

@@ -178,3 +178,29 @@ def test_compute_source_golden_bytes():
     n = s.computeSource(500, 1.0, 1e-5, TOTAL_SOURCE)
     assert n == 130
     assert format_flux_results(n, s.getFluxes()) == GOLDENS["test_compute_source"]
+
+
+# ------------------------------------------------------------------ adjoint mode
+def adjoint_tracks(name):
+    """Solver::initializeMaterials(ADJOINT) transposes the scattering and fission matrices of every
+    material (src/Solver.cpp:805-806, Material::transposeProductionMatrices); on flattened data that
+    is a transpose of two arrays."""
+    import copy
+    ft, ref = load_case(name)
+    ft = copy.deepcopy(ft)
+    G = ft.num_groups
+    for k in ("mat_sigma_s", "mat_fiss_matrix"):
+        ft.arrays[k] = ft.arrays[k].reshape(-1, G, G).transpose(0, 2, 1).copy().ravel()
+    return ft
+
+
+@pytest.mark.parametrize("fixture,test,iters", [("pin_cell", "test_adjoint_pin_cell", 331),
+                                                ("simple_lattice", "test_adjoint_simple_lattice", 315),
+                                                ("hom_inf", "test_adjoint_hom_inf_medium", 163)])
+def test_adjoint_goldens(fixture, test, iters):
+    s = OracleSolver(adjoint_tracks(fixture))
+    n = s.computeEigenvalue(500, 1e-5, FISSION_SOURCE)
+    assert n == iters
+    out = format_harness_results(n, s.getKeff(), s.getFluxes())
+    gold = GOLDENS[test]
+    assert out == gold or hashlib.sha512(out.encode()).hexdigest() == gold.strip()

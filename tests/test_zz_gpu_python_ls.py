@@ -99,3 +99,40 @@ def test_compute_flux_and_source_goldens_from_gpu():
     goldens = json.load(open(os.path.join(GOLDEN, "ref_goldens.json")))
     assert r["flux"] == goldens["test_compute_flux"]
     assert r["source"] == goldens["test_compute_source"]
+
+
+# ---- adjoint goldens from the GPU: the forward path on transposed production matrices ----
+CHILD_ADJOINT = r"""
+import copy, hashlib, json, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+from conftest import load_case
+from openmoc_b200.solver import B200Solver
+from openmoc_b200.capi import FISSION_SOURCE
+from oracle.oracle_py import format_harness_results
+res = {}
+for fixture in ("pin_cell", "simple_lattice", "hom_inf"):
+    ft, _ = load_case(fixture)
+    ft = copy.deepcopy(ft)
+    G = ft.num_groups
+    for k in ("mat_sigma_s", "mat_fiss_matrix"):
+        ft.arrays[k] = ft.arrays[k].reshape(-1, G, G).transpose(0, 2, 1).copy().ravel()
+    s = B200Solver(ft)
+    s.setConvergenceThreshold(1e-5)
+    s.computeEigenvalue(500, FISSION_SOURCE)
+    out = format_harness_results(s.getNumIterations(), s.getKeff(), s.getFluxes())
+    res[fixture] = [out, hashlib.sha512(out.encode()).hexdigest()]
+print("RESULT " + json.dumps(res))
+"""
+
+
+@pytest.mark.xfail(reason="not yet run on hardware (added after the GPU budget was spent)", strict=False)
+def test_adjoint_goldens_from_gpu():
+    """tests/test_adjoint_{pin_cell,simple_lattice,hom_inf_medium}/results_true.dat from the GPU"""
+    out = subprocess.run([sys.executable, "-c", CHILD_ADJOINT % {"root": ROOT}], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    goldens = json.load(open(os.path.join(GOLDEN, "ref_goldens.json")))
+    for fixture, test in (("pin_cell", "test_adjoint_pin_cell"), ("simple_lattice", "test_adjoint_simple_lattice"),
+                          ("hom_inf", "test_adjoint_hom_inf_medium")):
+        text, sha = r[fixture]
+        assert text == goldens[test] or sha == goldens[test].strip(), test
