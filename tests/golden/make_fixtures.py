@@ -32,6 +32,7 @@ CASES = {
     # EqualAnglePolarQuad is discarded by generateTracks for want of setNumAzimAngles.
     "c5g7_2d_coarse": ["--model", "c5g7-2d", "--azim", "4", "--spacing", "0.5", "--polar", "6",
                        "--max-iters", "40", "--no-fluxes"],
+    "pin_cell_70g": ["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--groups70", "--res", "flux"],  # test_forward_pin_cell_70g
     # fixed-source decks: the track file is shared by test_compute_flux and test_compute_source
     "water_box": ["--model", "water-box", "--azim", "4", "--spacing", "0.1", "--mode", "flux",
                   "--fixed-source", "1:1.0,2:0.5,3:0.25", "--res", "flux"],
@@ -62,7 +63,7 @@ def main():
               "test_forward_3D_lattice", "test_forward_hom_inf_medium",
               "test_forward_3D_lattice_linear", "test_forward_3D_lattice_linear_70g",
               "test_compute_flux", "test_compute_source",
-              "test_adjoint_pin_cell", "test_adjoint_simple_lattice", "test_adjoint_hom_inf_medium"):
+              "test_forward_pin_cell_70g", "test_adjoint_pin_cell", "test_adjoint_simple_lattice", "test_adjoint_hom_inf_medium"):
         gold[t] = open(os.path.join(REF, "tests", t, "results_true.dat")).read()
     json.dump(gold, open(os.path.join(HERE, "ref_goldens.json"), "w"), indent=1)
 

@@ -204,3 +204,12 @@ def test_adjoint_goldens(fixture, test, iters):
     out = format_harness_results(n, s.getKeff(), s.getFluxes())
     gold = GOLDENS[test]
     assert out == gold or hashlib.sha512(out.encode()).hexdigest() == gold.strip()
+
+
+def test_pin_cell_70g_golden_bytes():
+    # tests/test_forward_pin_cell_70g: 70 groups in 2D (F = 210), SCALAR_FLUX residual, 8 iterations
+    ft, ref = load_case("pin_cell_70g")
+    s = OracleSolver(ft)
+    n = s.computeEigenvalue(500, 1e-5, SCALAR_FLUX)
+    assert n == 8
+    assert format_harness_results(n, s.getKeff(), s.getFluxes()) == GOLDENS["test_forward_pin_cell_70g"]
