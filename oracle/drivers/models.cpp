@@ -129,7 +129,7 @@ Model simple_lattice(int dims) {
 }
 
 /* ---------------- tests/input_set.py:32-92 ---------------- */
-Model hom_inf(int) {
+Model hom_inf(int, int vacuum_mask = 0) {   /* bit 0 xmin, 1 xmax, 2 ymin, 3 ymax set to VACUUM */
   Model md;
   double sigma_f[2] = {0.000625, 0.135416667};
   double nu_sigma_f[2] = {0.0015, 0.325};
@@ -145,8 +145,10 @@ Model hom_inf(int) {
   const double length = 2.5; const int n = 10;
   XPlane* xmin = new XPlane(-length / 2.); XPlane* xmax = new XPlane(length / 2.);
   YPlane* ymin = new YPlane(-length / 2.); YPlane* ymax = new YPlane(length / 2.);
-  xmin->setBoundaryType(REFLECTIVE); xmax->setBoundaryType(REFLECTIVE);
-  ymin->setBoundaryType(REFLECTIVE); ymax->setBoundaryType(REFLECTIVE);
+  xmin->setBoundaryType((vacuum_mask & 1) ? VACUUM : REFLECTIVE);
+  xmax->setBoundaryType((vacuum_mask & 2) ? VACUUM : REFLECTIVE);
+  ymin->setBoundaryType((vacuum_mask & 4) ? VACUUM : REFLECTIVE);
+  ymax->setBoundaryType((vacuum_mask & 8) ? VACUUM : REFLECTIVE);
   Cell* fill = new Cell();
   fill->setFill(m);
   Cell* root_cell = new Cell();
@@ -342,6 +344,8 @@ Model build_model(const std::string& name, int dims) {
   if (name == "pin-cell") return pin_cell(dims);
   if (name == "simple-lattice") return simple_lattice(dims);
   if (name == "hom-inf") return hom_inf(dims);
+  if (name == "gradient-1d") return hom_inf(dims, 1 | 2);     /* tests/test_1d_gradient: VACUUM in x */
+  if (name == "gradient-2d") return hom_inf(dims, 1 | 8);     /* tests/test_2d_gradient: VACUUM on xmin, ymax */
   if (name == "water-box") return water_box(dims);
   if (name == "c5g7-2d") return c5g7_2d(dims);
   log_printf(ERROR, "unknown model %s", name.c_str());

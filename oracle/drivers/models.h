@@ -9,6 +9,7 @@
  *  c5g7-2d         sample-input/benchmarks/c5g7/{surfaces,cells,universes,
  *                  lattices,c5g7-2d}.py
  *  hom-inf         tests/input_set.py:32-92    (HomInfMedInput)
+ *  gradient-1d/2d  tests/test_1d_gradient, tests/test_2d_gradient: hom-inf with VACUUM sides
  *  water-box       tests/test_compute_flux/test_compute_flux.py:18-79 and test_compute_source:
  *                  HomInfMedInput's 10x10 lattice with VACUUM sides, filled with C5G7 water, one
  *                  lattice cell (the "source" cell) holding the fixed source

@@ -33,6 +33,8 @@ CASES = {
     "c5g7_2d_coarse": ["--model", "c5g7-2d", "--azim", "4", "--spacing", "0.5", "--polar", "6",
                        "--max-iters", "40", "--no-fluxes"],
     "pin_cell_70g": ["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--groups70", "--res", "flux"],  # test_forward_pin_cell_70g
+    "gradient_1d": ["--model", "gradient-1d", "--azim", "4", "--spacing", "0.1"],    # test_1d_gradient (VACUUM in x)
+    "gradient_2d": ["--model", "gradient-2d", "--azim", "4", "--spacing", "0.1"],    # test_2d_gradient (VACUUM xmin, ymax)
     # fixed-source decks: the track file is shared by test_compute_flux and test_compute_source
     "water_box": ["--model", "water-box", "--azim", "4", "--spacing", "0.1", "--mode", "flux",
                   "--fixed-source", "1:1.0,2:0.5,3:0.25", "--res", "flux"],
@@ -63,7 +65,7 @@ def main():
               "test_forward_3D_lattice", "test_forward_hom_inf_medium",
               "test_forward_3D_lattice_linear", "test_forward_3D_lattice_linear_70g",
               "test_compute_flux", "test_compute_source",
-              "test_forward_pin_cell_70g", "test_adjoint_pin_cell", "test_adjoint_simple_lattice", "test_adjoint_hom_inf_medium"):
+              "test_forward_pin_cell_70g", "test_1d_gradient", "test_2d_gradient", "test_adjoint_pin_cell", "test_adjoint_simple_lattice", "test_adjoint_hom_inf_medium"):
         gold[t] = open(os.path.join(REF, "tests", t, "results_true.dat")).read()
     json.dump(gold, open(os.path.join(HERE, "ref_goldens.json"), "w"), indent=1)
 

@@ -213,3 +213,12 @@ def test_pin_cell_70g_golden_bytes():
     n = s.computeEigenvalue(500, 1e-5, SCALAR_FLUX)
     assert n == 8
     assert format_harness_results(n, s.getKeff(), s.getFluxes()) == GOLDENS["test_forward_pin_cell_70g"]
+
+
+@pytest.mark.parametrize("fixture,test,iters", [("gradient_1d", "test_1d_gradient", 46),
+                                                ("gradient_2d", "test_2d_gradient", 52)])
+def test_vacuum_gradient_goldens(fixture, test, iters):
+    # tests/test_1d_gradient, tests/test_2d_gradient: 2-group cube with VACUUM on two sides
+    s, n, _ = solve(fixture)
+    assert n == iters
+    assert format_harness_results(n, s.getKeff(), s.getFluxes()) == GOLDENS[test]

@@ -162,3 +162,32 @@ def test_pin_cell_70g_golden_from_gpu():
     r = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
     goldens = json.load(open(os.path.join(GOLDEN, "ref_goldens.json")))
     assert r["out"] == goldens["test_forward_pin_cell_70g"]
+
+
+# ---- VACUUM-sided 2-group cubes (tests/test_1d_gradient, tests/test_2d_gradient) from the GPU ----
+CHILD_GRADIENT = r"""
+import json, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+from conftest import load_case
+from openmoc_b200.solver import B200Solver
+from openmoc_b200.capi import FISSION_SOURCE
+from oracle.oracle_py import format_harness_results
+res = {}
+for fixture in ("gradient_1d", "gradient_2d"):
+    ft, _ = load_case(fixture)
+    s = B200Solver(ft)
+    s.setConvergenceThreshold(1e-5)
+    s.computeEigenvalue(500, FISSION_SOURCE)
+    res[fixture] = format_harness_results(s.getNumIterations(), s.getKeff(), s.getFluxes())
+print("RESULT " + json.dumps(res))
+"""
+
+
+@pytest.mark.xfail(reason="not yet run on hardware (added after the GPU budget was spent)", strict=False)
+def test_vacuum_gradient_goldens_from_gpu():
+    out = subprocess.run([sys.executable, "-c", CHILD_GRADIENT % {"root": ROOT}], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    goldens = json.load(open(os.path.join(GOLDEN, "ref_goldens.json")))
+    assert r["gradient_1d"] == goldens["test_1d_gradient"]
+    assert r["gradient_2d"] == goldens["test_2d_gradient"]
