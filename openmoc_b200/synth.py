@@ -32,7 +32,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200trackgen.so")
 
 KIND_PIN, KIND_GRID = 0, 1
-QUAD_TY, QUAD_EQUAL_ANGLE = 0, 1
+QUAD_TY, QUAD_EQUAL_ANGLE, QUAD_GAUSS_LEGENDRE, QUAD_EQUAL_WEIGHT = 0, 1, 2, 3
 
 
 class CellType(C.Structure):
@@ -55,6 +55,12 @@ def _load():
                                               C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                               C.POINTER(C.c_int)]
+        L.b200_trackgen_create_3d.restype = C.c_void_p
+        L.b200_trackgen_create_3d.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                              C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                              C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double,
+                                              C.c_int, C.POINTER(C.c_int)]
         L.b200_trackgen_destroy.argtypes = [C.c_void_p]
         L.b200_trackgen_error.restype = C.c_char_p
         L.b200_trackgen_error.argtypes = [C.c_void_p]
@@ -267,3 +273,72 @@ def add_linear_source_data(ft: FlatTracks) -> None:
     cy = np.bincount(fsr, weights=wgt * (y + sin_phi * length / 2.0) * length / vol, minlength=ft.n_fsrs)
     a["fsr_centroid"] = np.stack([cx, cy, np.zeros_like(cx)], axis=1).ravel()
     a["seg_start"] = np.stack([x - cx[fsr], y - cy[fsr], np.zeros_like(x)], axis=1).ravel()
+
+
+# ----------------------------------------------------------------------- 3D decks
+#: axial extent and z boundary conditions of the reference's 3D decks:
+#:   pin-cell / simple-lattice  tests/input_set.py (PinCellInput / SimpleLatticeInput, num_dimensions=3)
+#:   c5g7-3d                    profile/models/c5g7/c5g7-3d-cmfd.cpp (z in [-32.13, 32.13], reflective
+#:                              bottom, vacuum top; the 2D C5G7 core extruded)
+AXIAL = {"pin-cell": (-2.0, 2.0, REFLECTIVE, REFLECTIVE),
+         "simple-lattice": (-5.0, 5.0, REFLECTIVE, VACUUM),
+         "c5g7-2d": (-32.13, 32.13, REFLECTIVE, VACUUM)}
+
+_DT3 = {"seg_length": "f8", "seg_fsr": "i4", "seg_mat": "i4", "trk_seg_offset": "i8",
+        "trk_next_fwd": "i8", "trk_next_bwd": "i8", "trk_azim": "i4", "trk_polar": "i4",
+        "trk_xy": "i4", "trk_2d": "i4", "trk_lz": "i4", "trk_flags": "u1", "trk_bc_fwd": "u1", "trk_bc_bwd": "u1",
+        "trk_phi": "f8", "trk_theta": "f8", "trk_start": "f8", "trk_end": "f8", "trk_l0": "f8", "z_mesh": "f8",
+        "quad_weight": "f8", "quad_sin_theta": "f8", "fsr_volume": "f8", "fsr_mat": "i4",
+        "quad_azim_spacing": "f8", "quad_azim_weight": "f8", "quad_polar_spacing": "f8", "quad_polar_weight": "f8",
+        "seg2d_length": "f8", "seg2d_fsr": "i4", "seg2d_mat": "i4", "trk2d_seg_offset": "i8",
+        "trk2d_start": "f8", "trk2d_phi": "f8", "fsr2d_mat": "i4"}
+
+
+def make_tracks_3d(model: str, num_azim: int = 4, spacing: float = 0.1, num_polar: int = 2,
+                   z_spacing: float = 0.1, n_axial: int = 1, polar_quad: int = QUAD_GAUSS_LEGENDRE,
+                   num_threads: int = 0, expand: bool = True, fsr_numbering: str = "discovery",
+                   groups70: bool = False) -> FlatTracks:
+    """3D tracks (z-stacks over the 2D tracks, TrackGenerator3D) of the named deck extruded in
+    n_axial equal layers.  polar_quad defaults to Gauss-Legendre, the reference's 3D default
+    (TrackGenerator3D::initializeDefaultQuadrature).
+
+    expand=True: explicit 3D segments + FSR volumes from the host tracer (tests, small decks).
+    expand=False: the arrays of the device tracer instead (2D segments `seg2d_*`, `trk2d_*`,
+    the axial mesh `z_mesh`, per-track `trk_2d`, `trk_l0`, `trk_start`): the solver traces the
+    z-stacks on the GPU (b200_upload_tracks_otf); FSR numbering is then always "lattice"."""
+    L = _load()
+    nx, ny, px, py, xmin, ymin, cells, types, bcs, _ = _model(model)
+    zmin, zmax, bc_zmin, bc_zmax = AXIAL[model]
+    cells = np.ascontiguousarray(cells, dtype="i4")
+    tarr = (CellType * len(types))(*types)
+    status = C.c_int()
+    h = L.b200_trackgen_create_3d(nx, ny, px, py, xmin, ymin, cells.ctypes.data_as(C.c_void_p),
+                                  C.cast(tarr, C.c_void_p), len(types), bcs[0], bcs[1], bcs[2], bcs[3],
+                                  num_azim, float(spacing), num_polar, polar_quad, num_threads,
+                                  zmin, zmax, bc_zmin, bc_zmax, int(n_axial), float(z_spacing),
+                                  int(bool(expand)), C.byref(status))
+    try:
+        if status.value != 0:
+            raise ValueError("3D track generation failed: " + L.b200_trackgen_error(h).decode())
+        arrays = {}
+        for k, dt in _DT3.items():
+            n = L.b200_trackgen_get(h, k.encode(), None)
+            if n < 0:
+                raise RuntimeError("trackgen has no array %r" % k)
+            a = np.empty(n, dtype=dt)
+            L.b200_trackgen_get(h, k.encode(), a.ctypes.data_as(C.c_void_p))
+            arrays[k] = a
+    finally:
+        L.b200_trackgen_destroy(h)
+    if expand and fsr_numbering == "discovery":
+        _renumber_by_discovery(arrays)
+    names, mats = c5g7_materials()
+    G = 7
+    if groups70:
+        mats, G = materials_70g(names), 70
+    arrays.update(mats)
+    ft = FlatTracks(num_groups=G, num_azim=num_azim, num_polar=num_polar, solve_3d=1, fluxes_per_track=G,
+                    n_tracks=int(arrays["trk_azim"].size), n_segments=int(arrays["seg_length"].size),
+                    n_fsrs=int(arrays["fsr_volume"].size), n_materials=len(names), arrays=arrays)
+    ft.n_axial = int(n_axial)
+    return ft
