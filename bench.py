@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Benchmark of the MOC transport-sweep hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5g7-2d|simple-lattice|pin-cell]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--also NAME,NAME|none]
   python bench.py --impl reference ...      # the reference's own CPUSolver on the host cores
+  python bench.py --impl refgpu ...         # the reference's own GPUSolver recompiled for sm_100a
 
 metric   segment-group integrations / s (the reference's own count W = 2*F*N_seg per
          sweep, src/Solver.cpp:1901-1902), whole job over all N GPUs.
@@ -13,6 +14,11 @@ e2e      the same iteration driven through the public host API with HOST buffers
          way openmoc.krylov drives a solver (setFluxes(numpy) -> sweep -> getFluxes(),
          openmoc/krylov.py:160-240): H2D of the scalar flux from pinned memory and D2H
          of the new flux + k_eff every step, wall-clock timed.
+workloads  the primary workload (default c5g7-2d = configs[2], the deck the north-star target is
+         quoted on) fills the top-level keys; every workload named by --also (default: c5g7-3d =
+         configs[4]'s deck at the reference's own 3D parameters) is measured the same way in the
+         same run and reported under "workloads" - so a 1/2/4/8-GPU series of this command also
+         is the 3D strong-scaling series.
 One JSON line on stdout (rank 0).  Nothing here reads /root/reference at run time.
 """
 import argparse
@@ -28,15 +34,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (synth model, num_azim, spacing cm, num_polar, BASELINE.json config it is)
-    "c5g7-2d": ("c5g7-2d", 128, 0.01, 6, "configs[2]: 2D C5G7 quarter core, 128 azim, 0.01 cm"),
-    "simple-lattice": ("simple-lattice", 128, 0.01, 6, "configs[1]: simple-lattice 2D, 128 azim, 0.01 cm"),
-    "pin-cell": ("pin-cell", 128, 0.01, 6, "configs[0]: pin-cell 2D, 128 azim, 0.01 cm"),
+    # 2D decks: TY polar quadrature (what the reference's decks really run)
+    "c5g7-2d": dict(dims=2, model="c5g7-2d", azim=128, spacing=0.01, polar=6,
+                    desc="configs[2]: 2D C5G7 quarter core, 128 azim, 0.01 cm",
+                    cpu_sample=dict(azim=128, spacing=0.05)),
+    "simple-lattice": dict(dims=2, model="simple-lattice", azim=128, spacing=0.01, polar=6,
+                           desc="configs[1]: simple-lattice 2D, 128 azim, 0.01 cm",
+                           cpu_sample=dict(azim=128, spacing=0.01)),
+    "pin-cell": dict(dims=2, model="pin-cell", azim=128, spacing=0.01, polar=6,
+                     desc="configs[0]: pin-cell 2D, 128 azim, 0.01 cm", cpu_sample=dict(azim=128, spacing=0.01)),
+    # configs[4]: the parameters of profile/models/c5g7/c5g7-3d-cmfd.cpp:15-27,537-573 (16 azim, 0.1 cm,
+    # 8 polar equal-angle, 1.0 cm axial spacing, 9 x 15 = 135 axial layers of 0.476 cm, OTF tracks)
+    "c5g7-3d": dict(dims=3, model="c5g7-2d", azim=16, spacing=0.1, polar=8, zspacing=1.0, n_axial=135,
+                    quad="equal-angle",
+                    desc="configs[4]: 3D C5G7 extruded core, 16 azim, 0.1 cm, 8 polar (equal angle), 1.0 cm axial "
+                         "spacing, 135 axial layers, on-the-fly axial ray tracing on the device",
+                    cpu_sample=dict(azim=4, spacing=0.5, polar=4, zspacing=4.0, n_axial=9)),
 }
-# bounded CPU sample of the same deck for the reference arm (same per-integration work,
-# coarser track laydown so that ~10-30 s of host time suffice)
-CPU_SAMPLE = {"c5g7-2d": (32, 0.05), "simple-lattice": (64, 0.02), "pin-cell": (128, 0.01)}
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md
+# FP64-pipe instructions per integration in the flat sweep kernels (cuobjdump of libb200moc.so,
+# profiles/r02_sass.md): 11 Horner DFMA + 4 for the quotient + tau, L*q, delta-psi, psi update,
+# tally (+ F2F conversions), per polar angle
+FP64_PER_INTEGRATION = {2: 65.0 / 3.0, 3: 21.0}
 
 
 def measured_peak():
@@ -50,19 +69,19 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed regions."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
-        self.t0 = self.t1 = None
+        self.windows = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append((time.time(), l)) for l in self.proc.stdout],
                                       daemon=True)
@@ -73,13 +92,13 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         self.t.join(timeout=2)
         sm, mx, reasons = [], None, set()
         for ts, l in self.lines:
-            # keep the samples taken while the timed region ran
-            if self.t0 is not None and not (self.t0 <= ts <= self.t1 + 0.12):
+            # keep the samples taken while a timed region ran (nvidia-smi reports with some lag)
+            if not any(t0 <= ts <= t1 + 0.1 for t0, t1 in self.windows):
                 continue
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
@@ -97,33 +116,58 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------- reference arm
-def run_reference_cpu(workload, iters, threads):
-    """Times the UNMODIFIED reference CPUSolver (oracle/_ref/ref_driver, built from
-    /root/reference by oracle/Makefile) on a bounded sample of the workload's deck;
-    falls back to the plain-C oracle port when the reference build is absent."""
-    model, _, _, num_polar, _ = WORKLOADS[workload]
-    azim, spacing = CPU_SAMPLE[workload]
+def _driver_args(wl, sample):
+    """ref_driver command line of the bounded sample of a workload's deck"""
+    a = ["--model", wl["model"], "--azim", str(sample["azim"]), "--spacing", str(sample["spacing"]),
+         "--polar", str(sample.get("polar", wl["polar"]))]
+    if wl["dims"] == 3:
+        a += ["--dims", "3", "--zspacing", str(sample["zspacing"]), "--axial", str(sample["n_axial"]),
+              "--quad", wl.get("quad", "gl"), "--formation", "otf-stacks"]
+    return a
+
+
+def sample_text(wl, sample):
+    s = f"{wl['model']} deck, {sample['azim']} azim, {sample['spacing']} cm"
+    if wl["dims"] == 3:
+        s += (f", {sample.get('polar', wl['polar'])} polar, {sample['zspacing']} cm axial spacing, "
+              f"{sample['n_axial']} axial layers, OTF_STACKS")
+    return s
+
+
+def run_reference(workload, iters, threads, solver="cpu", keep_fluxes=False):
+    """Times the UNMODIFIED reference (oracle/_ref/ref_driver, built from /root/reference by
+    oracle/Makefile) - CPUSolver on the host cores, or its own GPUSolver recompiled for sm_100a -
+    on a bounded sample of the workload's deck: same geometry, materials and angles per track,
+    coarser track laydown.  Falls back to the plain-C oracle port when the reference build is absent."""
+    wl = WORKLOADS[workload]
+    sample = wl["cpu_sample"]
     driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
-    sample = f"{model} deck, {azim} azim, {spacing} cm, {iters} source iterations"
+    text = sample_text(wl, sample) + f", {iters} source iterations"
     if os.path.exists(driver):
         with tempfile.TemporaryDirectory() as td:
             js = os.path.join(td, "ref.json")
             env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+            cmd = [driver] + _driver_args(wl, sample) + ["--max-iters", str(iters), "--threads", str(threads),
+                                                         "--tol", "1e-30", "--quiet", "--json", js, "--solver", solver]
+            if not keep_fluxes:
+                cmd.append("--no-fluxes")
             t0 = time.perf_counter()
-            subprocess.run([driver, "--model", model, "--azim", str(azim), "--spacing", str(spacing),
-                            "--polar", str(num_polar), "--max-iters", str(iters), "--threads", str(threads),
-                            "--quiet", "--no-fluxes", "--json", js], check=True, env=env,
-                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=td)
+            subprocess.run(cmd, check=True, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=td)
             wall = time.perf_counter() - t0
             d = json.load(open(js))
-        return {"kind": "reference", "value": d["integrations"] / d["sweep_time_s"], "cores": threads,
-                "sample": sample + f" (N_seg={d['n_segments']}, sweep timer {d['sweep_time_s']:.2f} s, "
-                                   f"whole run incl. ray tracing {wall:.1f} s)",
-                "sweep_time_s": d["sweep_time_s"], "iterations": d["iterations"],
-                "integrations": d["integrations"], "total_time_s": d["total_time_s"]}
-    from openmoc_b200.synth import make_tracks
+        out = {"kind": "reference", "value": d["integrations"] / d["sweep_time_s"], "cores": threads,
+               "sample": text + f" (N_seg={d['n_segments']}, sweep timer {d['sweep_time_s']:.2f} s, "
+                                f"whole run incl. ray tracing {wall:.1f} s)",
+               "sweep_time_s": d["sweep_time_s"], "iterations": d["iterations"],
+               "integrations": d["integrations"], "total_time_s": d["total_time_s"], "keff": d.get("keff"),
+               "n_segments": d["n_segments"], "n_fsrs": d.get("n_fsrs")}
+        if keep_fluxes:
+            out["fluxes"] = d.get("fluxes")
+        return out
+    if solver != "cpu":
+        return None
     from oracle.oracle_py import OracleSolver
-    ft = make_tracks(model, num_azim=azim, spacing=spacing, num_polar=num_polar)
+    ft = make_sample_tracks(workload)
     s = OracleSolver(ft)
     s.setNumThreads(threads)
     t0 = time.perf_counter()
@@ -131,8 +175,26 @@ def run_reference_cpu(workload, iters, threads):
     wall = time.perf_counter() - t0
     W = 2.0 * ft.fluxes_per_track * ft.n_segments * iters
     return {"kind": "port", "value": W / s.sweepSeconds(), "cores": threads,
-            "sample": sample + f" (N_seg={ft.n_segments}, oracle port, sweep {s.sweepSeconds():.2f} s)",
-            "sweep_time_s": s.sweepSeconds(), "iterations": iters, "integrations": W, "total_time_s": wall}
+            "sample": text + f" (N_seg={ft.n_segments}, oracle port, sweep {s.sweepSeconds():.2f} s)",
+            "sweep_time_s": s.sweepSeconds(), "iterations": iters, "integrations": W, "total_time_s": wall,
+            "keff": s.getKeff(), "n_segments": ft.n_segments, "n_fsrs": ft.n_fsrs,
+            "fluxes": list(map(float, s.getFluxes())) if keep_fluxes else None}
+
+
+def make_sample_tracks(workload, expand=True):
+    from openmoc_b200.synth import make_tracks, make_tracks_3d
+    wl = WORKLOADS[workload]
+    s = wl["cpu_sample"]
+    if wl["dims"] == 2:
+        return make_tracks(wl["model"], num_azim=s["azim"], spacing=s["spacing"], num_polar=wl["polar"])
+    return make_tracks_3d(wl["model"], num_azim=s["azim"], spacing=s["spacing"], num_polar=s.get("polar", wl["polar"]),
+                          z_spacing=s["zspacing"], n_axial=s["n_axial"], polar_quad=_quad(wl), expand=expand)
+
+
+def _quad(wl):
+    from openmoc_b200 import synth
+    return {"ty": synth.QUAD_TY, "equal-angle": synth.QUAD_EQUAL_ANGLE, "gl": synth.QUAD_GAUSS_LEGENDRE,
+            "equal-weight": synth.QUAD_EQUAL_WEIGHT}[wl.get("quad", "gl")]
 
 
 def reference_arm(args):
@@ -141,16 +203,28 @@ def reference_arm(args):
         return
     threads = os.cpu_count() or 1
     iters = args.steps + args.warmup
-    cb = run_reference_cpu(args.workload, iters, threads)
-    model, azim, spacing, num_polar, cfgname = WORKLOADS[args.workload]
+    wl = WORKLOADS[args.workload]
+    if args.impl == "refgpu":
+        cb = run_reference(args.workload, iters, threads, solver="refgpu") if wl["dims"] == 2 else None
+        if cb is None:
+            print(json.dumps({"impl": "refgpu", "unavailable": "the reference GPUSolver handles 2D flat-source decks only "
+                                                               "and needs oracle/_ref/libopenmoc_refgpu.so"}))
+            return
+        solver, timed = "GPUSolver (reference CUDA, recompiled for sm_100a)", "reference 'Transport Sweep' timer split"
+    else:
+        cb = run_reference(args.workload, iters, threads)
+        solver, timed = "CPUSolver (OpenMP)", "reference 'Transport Sweep' timer split over all iterations"
     line = {
-        "impl": "reference", "metric": "segment-group integrations/s", "value": cb["value"],
+        "impl": args.impl, "metric": "segment-group integrations/s", "value": cb["value"],
         "unit": "integrations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * cb["total_time_s"] / max(cb["iterations"], 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "ns_per_integration_thread": 1e9 * cb["sweep_time_s"] * cb["cores"] / cb["integrations"],
-        "config": {"workload": args.workload, "deck": cfgname, "solver": "CPUSolver (OpenMP)",
-                   "timed": "reference 'Transport Sweep' timer split over all iterations"},
+        "config": {"workload": args.workload, "deck": wl["desc"], "solver": solver, "timed": timed,
+                   "sample": cb["sample"],
+                   "same_deck_coarser_tracks": "the rate is per segment-group integration; the sample keeps the deck, "
+                                               "materials, groups and polar angles per track and lays tracks coarser so "
+                                               "that the reference's own ray tracing fits the time budget"},
         "cpu_baseline": {k: cb[k] for k in ("value", "cores", "kind", "sample")} | {"unit": "integrations/s"},
         "e2e": {"value": cb["value"], "unit": "integrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -159,61 +233,55 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------ our arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5g7-2d", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="double", choices=["double", "mixed"])
-    ap.add_argument("--azim", type=int, default=None)
-    ap.add_argument("--spacing", type=float, default=None)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--partition", default="pair", choices=["pair", "chain", "track"])
-    ap.add_argument("--deterministic", action="store_true")
-    args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3
-    if args.impl == "reference":
-        return reference_arm(args)
+class Env:
+    pass
 
+
+def build_tracks(name, args, ncpu, world):
+    from openmoc_b200.synth import make_tracks, make_tracks_3d
+    wl = WORKLOADS[name]
+    azim = args.azim if (args.azim and name == args.workload) else wl["azim"]
+    spacing = args.spacing if (args.spacing and name == args.workload) else wl["spacing"]
+    if wl["dims"] == 2:
+        ft = make_tracks(wl["model"], num_azim=azim, spacing=spacing, num_polar=wl["polar"],
+                         num_threads=max(1, ncpu // world))
+    else:
+        ft = make_tracks_3d(wl["model"], num_azim=azim, spacing=spacing, num_polar=wl["polar"],
+                            z_spacing=wl["zspacing"], n_axial=wl["n_axial"], polar_quad=_quad(wl),
+                            num_threads=max(1, ncpu // world), expand=False)
+    return ft, azim, spacing
+
+
+def measure(name, args, env, primary):
+    """One workload: device-resident timing, end-to-end timing, roofline.  Returns the result dict."""
     import numpy as np
     import torch
     from openmoc_b200 import capi
     from openmoc_b200.solver import B200Solver
-    from openmoc_b200.synth import make_tracks
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    model, azim, spacing, num_polar, cfgname = WORKLOADS[args.workload]
-    azim = args.azim or azim
-    spacing = args.spacing or spacing
+    dist, rank, world, local_rank = env.dist, env.rank, env.world, env.local_rank
+    wl = WORKLOADS[name]
     ncpu = os.cpu_count() or 1
     t0 = time.perf_counter()
-    ft = make_tracks(model, num_azim=azim, spacing=spacing, num_polar=num_polar,
-                     num_threads=max(1, ncpu // world))
+    ft, azim, spacing = build_tracks(name, args, ncpu, world)
     t_gen = time.perf_counter() - t0
     F, G = ft.fluxes_per_track, ft.num_groups
-    W_sweep = 2.0 * F * ft.n_segments                     # whole job, all ranks
     precision = capi.PRECISION_MIXED if args.precision == "mixed" else capi.PRECISION_DOUBLE
+    partition = args.partition if wl["dims"] == 2 else "chain"
 
     t0 = time.perf_counter()
     solver = B200Solver(ft, device=local_rank, precision=precision,
                         process_group=(dist.group.WORLD if world > 1 else None),
-                        partition=args.partition, deterministic=args.deterministic)
+                        partition=partition, deterministic=args.deterministic)
     solver.useTorchStream()
     t_setup = time.perf_counter() - t0
-    local_W = 2.0 * F * solver.tracks.n_segments
+    local_seg = solver.num_segments
+    n_seg = local_seg
+    if dist is not None:
+        t = torch.tensor([local_seg], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        n_seg = int(t.item())
+    W_sweep = 2.0 * F * n_seg                              # whole job, all ranks
+    local_W = 2.0 * F * local_seg
 
     # initial state of Solver::computeEigenvalue: psi = 0, phi = 1 normalised, stored
     solver.zeroTrackFluxes()
@@ -225,56 +293,58 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    steps, warmup = args.steps, args.warmup
+    if not primary:
+        # secondary workloads share the run's time budget: bounded so that a sweep of ~0.1 s still fits
+        steps, warmup = max(5, min(args.steps, 20)), 3
     # ---------------- device-resident timing ----------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    solver.iterate(args.warmup)
+    solver.iterate(warmup)
     barrier()
     solver.resetSweepStats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.t0 = time.time()
+    w0 = time.time()
     ev0.record()
-    solver.iterate(args.steps)
+    solver.iterate(steps)
     ev1.record()
     torch.cuda.synchronize()
-    sampler.t1 = time.time()
+    env.sampler.windows.append((w0, time.time()))
     ms = ev0.elapsed_time(ev1)
     if dist is not None:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
     sweep_ms, n_sweeps, launches = solver.getSweepStats()
     k_dev = solver.getKeff()
-    value = W_sweep * args.steps / (ms * 1e-3)
+    value = W_sweep * steps / (ms * 1e-3)
 
     # ---------------- end to end through the host API ----------------
     n_phi = ft.n_fsrs * G
     host_phi = torch.empty(n_phi, dtype=torch.float64).pin_memory()
     host_np = host_phi.numpy()
     host_np[:] = solver.getFluxes()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(steps, 10))
 
     def e2e_step(i):
         solver.setFluxes(host_np)                 # H2D, pinned
         solver.computeFSRSources(1000 + i)
         solver.transportSweep()
         solver.addSourceToScalarFlux()
-        k = solver.computeKeff()                   # D2H scalar
+        solver.computeKeff(fetch=False)
         solver.normalizeFluxes(fetch=False)
-        host_np[:] = solver.getFluxes()            # D2H
-        return k
+        solver.getFluxes(out=host_np)              # D2H into the pinned buffer; the one host sync of the step
+        return solver.getKeffNoSync()
     for i in range(2):
         e2e_step(i)
     barrier()
+    w0 = time.time()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         e2e_step(i)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    env.sampler.windows.append((w0, time.time()))
     if dist is not None:
         t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -283,56 +353,176 @@ def main():
 
     # ---------------- roofline of the dominant kernel (the sweep) ----------------
     peak, peak_src = measured_peak()
-    b_alg = (12.0 * ft.n_segments + 16.0 * F * ft.n_tracks + 16.0 * G * ft.n_fsrs) / W_sweep
+    n_trk_total = ft.n_tracks
+    b_alg = (12.0 * n_seg + 16.0 * F * n_trk_total + 16.0 * G * ft.n_fsrs) / W_sweep
     sweep_avg_ms = sweep_ms / max(n_sweeps, 1)
     achieved = b_alg * local_W / (sweep_avg_ms * 1e-3) / 1e9       # GB/s of algorithmic bytes, this rank
     traffic = None
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get(args.workload, {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(prof)).get(name, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    rate_local = local_W / (sweep_avg_ms * 1e-3)                    # integrations/s of this rank's sweep kernel
+    fp64_ceiling = env.fp64_rate / FP64_PER_INTEGRATION[wl["dims"]]
+    # flat 2D tracks merge the tally over the NP polar angles and over runs of segments in one FSR;
+    # 3D tracks change FSR at (nearly) every segment: one RED.ADD.F64 per integration at worst
+    red_ceiling = env.red_rate if wl["dims"] == 3 else env.red_rate * (F / G)
+    binding = min(("fp64_issue", fp64_ceiling), ("red_f64", red_ceiling), key=lambda x: x[1])
 
-    if rank == 0:
+    res = {
+        "value": value, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+        "ns_per_integration": 1e9 / value,
+        "config": {"workload": name, "deck": wl["desc"], "num_azim": azim, "spacing_cm": spacing,
+                   "num_polar": wl["polar"], "n_tracks": ft.n_tracks, "n_segments": n_seg,
+                   "n_fsrs": ft.n_fsrs, "groups": G, "fluxes_per_track": F,
+                   "integrations_per_sweep": W_sweep,
+                   "parallelism": "1 GPU" if world == 1 else f"{partition} partition x{world} + NCCL all-reduce of the FSR tally"
+                                  + (" + NCCL send/recv of cross-rank boundary fluxes" if partition == "track" else ""),
+                   "deterministic_tally": bool(args.deterministic),
+                   "l2": "segment stream (%.2f GB) is larger than the 126 MB L2; no flush" % (16.0 * n_seg / world / 1e9)
+                         if 16.0 * n_seg / world > 2.5e8 else "inputs fit in L2; not flushed (launch-bound shape)",
+                   "k_eff_after_timed_steps": k_dev, "track_generation_s": round(t_gen, 2),
+                   "upload_and_setup_s": round(t_setup, 2)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "b200::sweep_kernel", "bytes_per_integration": b_alg,
+                     "kernel_ms": sweep_avg_ms, "kernel_share_of_step": sweep_ms / (ms * n_sweeps / steps) if ms > 0 and n_sweeps else None,
+                     "binding_bound": binding[0], "binding_peak": binding[1], "binding_unit": "integrations/s",
+                     "binding_achieved": rate_local, "binding_frac": rate_local / binding[1],
+                     "ceilings": {"fp64_instr_per_s": env.fp64_rate, "fp64_instr_per_integration": FP64_PER_INTEGRATION[wl["dims"]],
+                                  "red_f64_per_s": env.red_rate, "fp64_issue_integrations_per_s": fp64_ceiling,
+                                  "red_integrations_per_s": red_ceiling,
+                                  "how": "b200_measure_ceilings (csrc/microbench.cuh) run on this GPU before the timed region"},
+                     "note": "HBM is not what binds this kernel (SURVEY 8d): the machine-readable fraction of the binding "
+                             "resource is binding_frac"},
+        "e2e": {"value": e2e_value, "unit": "integrations/s", "h2d_bytes_per_step": n_phi * 8,
+                "d2h_bytes_per_step": n_phi * 8 + 8, "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps},
+        "gpu_launches": int(launches),
+    }
+    solver.close()
+    del solver
+    torch.cuda.empty_cache()
+    return res
+
+
+def parity_check(workload, cb, env):
+    """The CUDA path on the very deck the CPU baseline just ran (synthetic tracks of the same
+    parameters), same number of source iterations from the same initial state: k_eff and scalar
+    fluxes against the reference's.  The reference is the checker here, not the thing measured."""
+    import numpy as np
+    from openmoc_b200.solver import B200Solver
+    from openmoc_b200.capi import FISSION_SOURCE
+    wl = WORKLOADS[workload]
+    ft = make_sample_tracks(workload, expand=(wl["dims"] == 2))
+    s = B200Solver(ft, device=env.local_rank)
+    s.setConvergenceThreshold(1e-30)
+    s.computeEigenvalue(int(cb["iterations"]), FISSION_SOURCE)
+    out = {"deck": sample_text(wl, wl["cpu_sample"]), "iterations": int(cb["iterations"]),
+           "k_eff_b200": s.getKeff(), "k_eff_reference": cb["keff"],
+           "dk_pcm": abs(s.getKeff() - cb["keff"]) * 1e5 if cb.get("keff") is not None else None,
+           "n_segments_b200": s.num_segments, "n_segments_reference": cb.get("n_segments"),
+           "tolerance": "north star: 1 pcm, 1e-4"}
+    ref_phi = cb.get("fluxes")
+    if ref_phi is not None and wl["dims"] == 2 and len(ref_phi) == ft.n_fsrs * ft.num_groups:
+        phi = s.getFluxes()
+        ref_phi = np.asarray(ref_phi)
+        out["max_rel_phi_err"] = float(np.max(np.abs(phi - ref_phi) / np.maximum(np.abs(ref_phi), 1e-300)))
+    elif ref_phi is not None:
+        # 3D: the reference numbers its FSRs in hash-map order; compare the sorted flux spectra
+        vol = s.getVolumes() if ft.n_segments == 0 else ft.arrays["fsr_volume"]
+        phi = np.sort(s.getFluxes()[np.repeat(vol > 0, ft.num_groups)])
+        ref_sorted = np.sort(np.asarray(ref_phi))
+        if phi.size == ref_sorted.size:
+            out["max_rel_sorted_phi_err"] = float(np.max(np.abs(phi - ref_sorted) / np.maximum(np.abs(ref_sorted), 1e-300)))
+    s.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "refgpu"])
+    ap.add_argument("--workload", default="c5g7-2d", choices=sorted(WORKLOADS))
+    ap.add_argument("--also", default="c5g7-3d", help="comma-separated secondary workloads, or 'none'")
+    ap.add_argument("--precision", default="double", choices=["double", "mixed"])
+    ap.add_argument("--azim", type=int, default=None)
+    ap.add_argument("--spacing", type=float, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition", default="pair", choices=["pair", "chain", "track"])
+    ap.add_argument("--deterministic", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl != "b200":
+        return reference_arm(args)
+
+    import torch
+    from openmoc_b200 import capi
+
+    env = Env()
+    env.rank = int(os.environ.get("RANK", "0"))
+    env.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    env.world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(env.local_rank)
+    env.dist = None
+    if env.world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", env.local_rank))
+        env.dist = dist
+    env.fp64_rate, env.red_rate = capi.measure_ceilings(env.local_rank, 23869)
+    env.sampler = ClockSampler(env.local_rank)
+    if env.rank == 0:
+        env.sampler.start()
+
+    also = [w for w in args.also.split(",") if w and w != "none" and w != args.workload]
+    for w in also:
+        if w not in WORKLOADS:
+            raise SystemExit(f"unknown workload {w!r}")
+    main_res = measure(args.workload, args, env, primary=True)
+    others = {w: measure(w, args, env, primary=False) for w in also}
+    clocks = env.sampler.stop() if env.rank == 0 else None
+
+    if env.rank == 0:
+        ncpu = os.cpu_count() or 1
         cpu_baseline = None
-        if world == 1 and not args.no_cpu_baseline:
-            cb = run_reference_cpu(args.workload, 6, ncpu)
-            cpu_baseline = {"value": cb["value"], "unit": "integrations/s", "cores": cb["cores"],
-                            "kind": cb["kind"], "sample": cb["sample"]}
+        if env.world == 1 and not args.no_cpu_baseline:
+            for w in [args.workload] + also:
+                cb = run_reference(w, 6, ncpu, keep_fluxes=True)
+                block = {"value": cb["value"], "unit": "integrations/s", "cores": cb["cores"],
+                         "kind": cb["kind"], "sample": cb["sample"]}
+                try:
+                    block["parity"] = parity_check(w, cb, env)
+                except Exception as e:                     # a failed check must not lose the measurement
+                    block["parity"] = {"error": repr(e)}
+                if w == args.workload:
+                    cpu_baseline = block
+                else:
+                    others[w]["cpu_baseline"] = block
+        precision = args.precision
         line = {
-            "metric": "segment-group integrations/s", "value": value, "unit": "integrations/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "metric": "segment-group integrations/s", "value": main_res["value"], "unit": "integrations/s",
+            "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if precision == capi.PRECISION_DOUBLE else "f32 segment math, f64 tally",
+            "dtype": "f64" if precision == "double" else "f32 segment math, f64 tally",
             "data": "synthetic",
-            "ns_per_integration": 1e9 / value,
-            "config": {"workload": args.workload, "deck": cfgname, "num_azim": azim, "spacing_cm": spacing,
-                       "num_polar": num_polar, "n_tracks": ft.n_tracks, "n_segments": ft.n_segments,
-                       "n_fsrs": ft.n_fsrs, "groups": G, "fluxes_per_track": F,
-                       "integrations_per_sweep": W_sweep,
-                       "parallelism": "1 GPU" if world == 1 else f"{args.partition} partition x{world} + NCCL all-reduce of the FSR tally"
-                                      + (" + NCCL send/recv of cross-rank boundary fluxes" if args.partition == "track" else ""),
-                       "deterministic_tally": bool(args.deterministic),
-                       "l2": "segment stream (%.2f GB) is larger than the 126 MB L2; no flush" % (12.0 * ft.n_segments / 1e9)
-                             if 12.0 * ft.n_segments > 2.5e8 else "inputs fit in L2; not flushed (launch-bound shape)",
-                       "k_eff_after_timed_steps": k_dev, "track_generation_s": round(t_gen, 2),
-                       "upload_and_setup_s": round(t_setup, 2)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "b200::sweep_kernel", "bytes_per_integration": b_alg,
-                         "kernel_ms": sweep_avg_ms, "kernel_share_of_step": sweep_ms / ms if ms > 0 else None,
-                         "note": "FP64-issue bound, not HBM bound, for G*P/2=21 (SURVEY 8d): 22 FP64 instr per integration vs "
-                                 "0.34 algorithmic bytes; see DESIGN.md 4.1 and profiles/"},
+            "ns_per_integration": main_res["ns_per_integration"],
+            "config": main_res["config"],
+            "roofline": main_res["roofline"],
             "cpu_baseline": cpu_baseline,
-            "e2e": {"value": e2e_value, "unit": "integrations/s", "h2d_bytes_per_step": n_phi * 8,
-                    "d2h_bytes_per_step": n_phi * 8 + 8, "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps},
-            "gpu_launches": int(launches),
+            "e2e": main_res["e2e"],
+            "gpu_launches": main_res["gpu_launches"],
             "clocks": clocks,
+            "workloads": others,
         }
         print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    if env.dist is not None:
+        env.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

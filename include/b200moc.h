@@ -117,6 +117,44 @@ int b200_get_cmfd_currents(b200_solver* s, double* out, int64_t n);
 /* flux moments in the reference layout [r*3G + c*G + e] (src/CPULSSolver.h:22) */
 int b200_get_flux_moments(b200_solver* s, double* out, int64_t n);
 int b200_set_flux_moments(b200_solver* s, const double* in, int64_t n);
+/* ---- axial on-the-fly ray tracing on the device (3D solvers) ----
+ * Replaces TraverseSegments::traceSegmentsOTF / traceStackOTF + SegmentationKernel
+ * (src/TraverseSegments.cpp:304-505, 523-911; src/MOCKernel.cpp:216-268) and the per-sweep
+ * TrackGenerator3D::getTrackOTF (src/TrackGenerator3D.cpp:1697): the host never materialises a 3D
+ * segment.  It hands over the 2D segments of the radial tracks (length + extruded FSR id,
+ * struct segment of the 2D Track), the axial meshes of the extruded FSRs (struct ExtrudedFSR,
+ * src/Geometry.h:84-107: extruded FSR e owns 3D FSRs ext_fsr_ids[ext_offset[e]..ext_offset[e+1])
+ * bottom-up and the planes ext_mesh[ext_offset[e]+e .. ext_offset[e+1]+e]), or - with
+ * n_extruded_fsrs = 0 - one global mesh of n_axial_global layers in ext_mesh[0..n_axial_global]
+ * (TrackGenerator3D::useGlobalZMesh; 3D FSR id = extruded id * n_axial_global + layer), and the
+ * corrected polar angles theta[A/2][P] (Quadrature::getTheta).  Call with cfg.n_segments = 0. */
+int b200_upload_otf_geometry(b200_solver* s, int64_t n_tracks_2d, int64_t n_segments_2d,
+                             const double* seg2d_length, const int32_t* seg2d_extruded_fsr,
+                             const int64_t* trk2d_seg_offset, int64_t n_extruded_fsrs,
+                             const int64_t* ext_offset, const double* ext_mesh,
+                             const int32_t* ext_fsr_ids, int32_t n_axial_global, const double* theta);
+/* FSR volumes from the tracks (VolumeKernel, src/MOCKernel.cpp:80-162): every 3D track given here
+ * (2D track id, distance of its start point from the start of the 2D track, start height, angle
+ * indices) is traced and class_weight[azim*P+polar] * length tallied (class weight = azimuthal
+ * spacing * azimuthal weight * polar spacing * polar weight).  A multi-GPU host passes ALL tracks
+ * of the problem here and only its shard to b200_upload_tracks_otf.  Afterwards
+ * b200_upload_fsrs accepts volume = NULL. */
+int b200_otf_compute_volumes(b200_solver* s, int64_t n_tracks, const int32_t* trk_2d, const double* trk_l0,
+                             const double* trk_z0, const int32_t* trk_azim, const int32_t* trk_polar,
+                             const double* class_weight);
+/* the solver's own 3D tracks (cfg.n_tracks of them): start data as above, links as in
+ * b200_upload_tracks.  The device counts the 3D segments of every track, then writes its
+ * segment stream in place; the total is returned and available from b200_get_num_segments. */
+int b200_upload_tracks_otf(b200_solver* s, const int32_t* trk_2d, const double* trk_l0, const double* trk_z0,
+                           const int32_t* trk_azim, const int32_t* trk_polar,
+                           const int64_t* trk_next_fwd, const int64_t* trk_next_bwd,
+                           const uint8_t* trk_flags, const uint8_t* trk_bc_fwd, const uint8_t* trk_bc_bwd,
+                           int64_t* n_segments);
+int b200_get_num_segments(b200_solver* s, int64_t* n_segments);
+/* host copies of the device segment stream (tests, track dumps); trk_seg_offset may be NULL */
+int b200_get_segments(b200_solver* s, double* seg_length, int32_t* seg_fsr, int64_t n_segments,
+                      int64_t* trk_seg_offset);
+int b200_get_volumes(b200_solver* s, double* volume, int64_t n_fsrs);
 /* builds device-side derived tables; call after the four uploads (re-callable) */
 int b200_finalize(b200_solver* s);
 
@@ -142,6 +180,8 @@ int b200_transport_sweep(b200_solver* s);
 /* ---- public Solver API (src/Solver.h:440-585) ---- */
 int b200_get_fluxes(b200_solver* s, double* out_fluxes, int64_t num_fluxes);
 int b200_set_fluxes(b200_solver* s, const double* in_fluxes, int64_t num_fluxes);
+/* getFluxes and getKeff behind one host synchronisation */
+int b200_get_fluxes_keff(b200_solver* s, double* out_fluxes, int64_t num_fluxes, double* k_eff);
 int b200_set_fixed_source_by_fsr(b200_solver* s, int64_t fsr_id, int32_t group /*1-based*/, double source);
 int b200_reset_fixed_sources(b200_solver* s);
 int b200_compute_fsr_fission_rates(b200_solver* s, double* fission_rates, int64_t num_fsrs, int32_t nu);
@@ -184,6 +224,12 @@ int b200_iterate(b200_solver* s, int32_t n, int32_t res_type, double* k_eff, dou
  * for n host values - the hook for the reference's known-answer vectors
  * (tests/unit_tests/test_exponentials.py:74-77) */
 int b200_eval_expF1(int32_t device, int32_t precision, const double* x, int64_t n, double* out);
+
+/* the two machine ceilings that bound the sweep besides HBM, measured on the spot: sustained FP64
+ * instruction rate (DFMA, the sweep's instruction mix and occupancy) and RED.ADD.F64 rate into an
+ * L2-resident table of table_rows x 7 doubles (the tally pattern of the sweep).  bench.py reports the
+ * roofline fraction of the binding one next to the HBM fraction. */
+int b200_measure_ceilings(int32_t device, int64_t table_rows, double* fp64_instr_per_s, double* red_f64_per_s);
 
 /* ---- instrumentation (the "Transport Sweep" timer split, src/CPUSolver.cpp:2365-2378) ---- */
 int b200_get_sweep_stats(b200_solver* s, double* sweep_ms_total, int64_t* num_sweeps,

@@ -47,6 +47,12 @@ SIGNATURES = {
     "b200_get_cmfd_currents": [_vp, _i64],
     "b200_get_flux_moments": [_vp, _i64],
     "b200_set_flux_moments": [_vp, _i64],
+    "b200_upload_otf_geometry": [_i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp],
+    "b200_otf_compute_volumes": [_i64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "b200_upload_tracks_otf": [_vp] * 10 + [C.POINTER(_i64)],
+    "b200_get_num_segments": [C.POINTER(_i64)],
+    "b200_get_segments": [_vp, _vp, _i64, _vp],
+    "b200_get_volumes": [_vp, _i64],
     "b200_finalize": [],
     "b200_zero_track_fluxes": [],
     "b200_flatten_fsr_fluxes": [_dbl],
@@ -64,6 +70,7 @@ SIGNATURES = {
     "b200_transport_sweep": [],
     "b200_get_fluxes": [_vp, _i64],
     "b200_set_fluxes": [_vp, _i64],
+    "b200_get_fluxes_keff": [_vp, _i64, C.POINTER(_dbl)],
     "b200_set_fixed_source_by_fsr": [_i64, _i32, _dbl],
     "b200_reset_fixed_sources": [],
     "b200_compute_fsr_fission_rates": [_vp, _i64, _i32],
@@ -94,7 +101,7 @@ SIGNATURES = {
 }
 #: every symbol include/b200moc.h declares (checked by tests/test_abi.py)
 EXPORTS = sorted(list(SIGNATURES) + ["b200_last_error", "b200_version", "b200_device_count", "b200_create",
-                                      "b200_eval_expF1"])
+                                      "b200_eval_expF1", "b200_measure_ceilings"])
 
 
 def load():
@@ -116,6 +123,8 @@ def load():
     L.b200_create.argtypes = [C.POINTER(Config), C.POINTER(_vp)]
     L.b200_eval_expF1.restype = C.c_int
     L.b200_eval_expF1.argtypes = [_i32, _i32, _vp, _i64, _vp]
+    L.b200_measure_ceilings.restype = C.c_int
+    L.b200_measure_ceilings.argtypes = [_i32, _i64, C.POINTER(_dbl), C.POINTER(_dbl)]
     for name, args in SIGNATURES.items():
         f = getattr(L, name)
         f.restype = C.c_int
@@ -131,6 +140,13 @@ def eval_expF1(x, precision: int = PRECISION_DOUBLE, device: int = 0):
     out = np.empty_like(x)
     check(load().b200_eval_expF1(device, precision, x.ctypes.data_as(_vp), x.size, out.ctypes.data_as(_vp)))
     return out
+
+
+def measure_ceilings(device: int = 0, table_rows: int = 23869):
+    """(FP64 instructions / s, RED.ADD.F64 / s) measured on the device (microbench.cuh)."""
+    a, b = _dbl(), _dbl()
+    check(load().b200_measure_ceilings(device, table_rows, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def check(status: int) -> None:

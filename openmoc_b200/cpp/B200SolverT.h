@@ -31,11 +31,13 @@ protected:
   using Base::_k_eff; using Base::_keff_from_fission_rates; using Base::_stabilize_transport;
   using Base::_stabilization_factor; using Base::_stabilization_type; using Base::_negative_fluxes_allowed;
   using Base::_chi_spectrum_material; using Base::_timer; using Base::_cmfd; using Base::_gpu_solver;
+  using Base::_FSR_volumes;
   using Base::_converge_thresh; using Base::_SOLVE_3D; using Base::_num_iterations; using Base::_solver_mode;
 
   b200_solver* _h;
   B200FlatTracks _flat;
   long _flattened_segments;
+  double _flattened_key;           /* fingerprint of the tracks the device image was built from */
   bool _materials_dirty, _fixed_dirty, _mirror_stale;
   bool _cmfd_active, _host_flux_newer;
   std::vector<double> _cmfd_currents;
@@ -127,6 +129,7 @@ B200SolverT<Base>::B200SolverT(TrackGenerator* track_generator, int device, int 
     : Base(track_generator) {
   _h = NULL;
   _flattened_segments = -1;
+  _flattened_key = -1.;
   _materials_dirty = false;
   _fixed_dirty = false;
   _mirror_stale = false;
@@ -157,8 +160,20 @@ void B200SolverT<Base>::check(int status, const char* what) {
 template <class Base>
 void B200SolverT<Base>::ensureDevice() {
   long n_seg = _track_generator->getNumSegments();
-  if (_h != NULL && n_seg == _flattened_segments) return;
+  /* The device image is reused only for the very same tracks: a re-traced geometry can keep its
+   * segment count while volumes, quadrature or FSR numbering change, so the key also covers the
+   * track counts, the FSR volumes and the quadrature weights. */
+  double key = (double)n_seg * 1e-3 + (double)_track_generator->getNumTracks() + 7. * (double)_num_FSRs;
+  if (_FSR_volumes != NULL)
+    for (long r = 0; r < _num_FSRs; r++) key += (double)_FSR_volumes[r] * (1. + 1e-3 * (double)(r % 977));
+  {
+    Quadrature* q = _track_generator->getQuadrature();
+    for (int a = 0; a < q->getNumAzimAngles() / 2; a++)
+      for (int p = 0; p < q->getNumPolarAngles(); p++) key += 13. * q->getWeightInline(a, p) * (1 + a) * (3 + p);
+  }
+  if (_h != NULL && n_seg == _flattened_segments && key == _flattened_key) return;
   if (_h != NULL) { b200_destroy(_h); _h = NULL; }
+  _flattened_key = key;
 
   b200_flatten(_track_generator, &_flat, isLinearSource());
   b200_config cfg;
@@ -192,9 +207,6 @@ void B200SolverT<Base>::ensureDevice() {
             "b200_upload_cmfd_surfaces");
   }
   check(b200_finalize(_h), "b200_finalize");
-  if (_stabilize_transport)
-    check(b200_stabilize_transport(_h, _stabilization_factor, (int)_stabilization_type), "b200_stabilize_transport");
-  check(b200_allow_negative_fluxes(_h, _negative_fluxes_allowed), "b200_allow_negative_fluxes");
   /* the segment stream only lives on the device from here on */
   std::vector<double>().swap(_flat.seg_length);
   std::vector<int32_t>().swap(_flat.seg_fsr);
@@ -267,7 +279,11 @@ template <class Base>
 void B200SolverT<Base>::initializeExpEvaluators() {
   Base::initializeExpEvaluators();
   ensureDevice();
+  /* solver options may change between two solves on the same tracks: pushed every time */
   check(b200_set_keff_from_neutron_balance(_h, !_keff_from_fission_rates), "b200_set_keff_from_neutron_balance");
+  if (_stabilize_transport)
+    check(b200_stabilize_transport(_h, _stabilization_factor, (int)_stabilization_type), "b200_stabilize_transport");
+  check(b200_allow_negative_fluxes(_h, _negative_fluxes_allowed), "b200_allow_negative_fluxes");
 }
 
 template <class Base>
@@ -562,6 +578,9 @@ void B200SolverT<Base>::computeEigenvalueFused(int max_iters, residualType res_t
   initializeFluxArrays();
   initializeSourceArrays();
   initializeCmfd();
+  if (_cmfd_active)
+    log_printf(ERROR, "computeEigenvalueFused runs the whole source iteration on the device and cannot "
+               "hand currents to the host Cmfd every iteration: use computeEigenvalue() with CMFD");
   pushFixedSourcesIfDirty();
   int iters = 0;
   check(b200_compute_eigenvalue(_h, max_iters, _converge_thresh, (int)res_type, &iters), "computeEigenvalueFused");

@@ -23,6 +23,8 @@
 #include "fsr_kernels.cuh"
 #include "sweep.cuh"
 #include "sweep_ls.cuh"
+#include "otf.cuh"
+#include "microbench.cuh"
 
 using namespace b200;
 
@@ -119,6 +121,15 @@ struct b200_solver {
   DevBuf<double> seg_len;
   DevBuf<int32_t> seg_fsr;
   DevBuf<SegRec> seg_rec;
+  bool seg_rec_ready = false;         /* the stream was written by the device tracer (no seg_len / seg_fsr copies) */
+  bool volumes_from_tracer = false;
+  /* axial on-the-fly tracing (otf.cuh) */
+  bool otf = false;
+  DevBuf<double> otf_seg2d_len, otf_mesh, otf_l0, otf_z0, otf_cos, otf_sin, otf_volw;
+  DevBuf<int32_t> otf_seg2d_ext, otf_ext_fsr, otf_trk2d, otf_cls, otf_count;
+  DevBuf<int64_t> otf_trk2d_off, otf_ext_off;
+  int otf_n_axial = 0;
+  int64_t otf_n_trk2d = 0, otf_n_seg2d = 0, otf_n_ext = 0;
   int n_rep = 1;                      /* tally replicas */
   bool capturing = false;             /* inside cudaStreamBeginCapture: no events, no host syncs */
   cudaGraphExec_t iter_graph = nullptr;   /* two fused source iterations (one per psi buffer parity) */
@@ -158,7 +169,6 @@ struct b200_solver {
 
   /* sweep launch geometry */
   int gpl = 1, lpi = 1, ipc = 32;   /* groups/thread, threads/item, items/CTA */
-  int variant = 0;                  /* 0: 2-deep register pipeline (default, fastest measured), 1: 4-deep register ring, 2: cp.async-staged */
   bool smem_attr_set = false;
   bool defer_fx_convert = false;    /* multi-GPU deterministic mode: the host reduces the integers first */
   int64_t sweep_blocks = 0;
@@ -323,6 +333,9 @@ extern "C" int b200_destroy(b200_solver* s) {
   s->ls_seg_start.release(); s->ls_trk_dir.release(); s->ls_lin_exp.release(); s->ls_src_const.release();
   s->phi_m.release(); s->mom_stage.release(); s->seg_pos.release(); s->qxyz.release();
   s->cmfd_fwd.release(); s->cmfd_bwd.release(); s->cmfd_group.release(); s->seg_cmfd.release(); s->currents.release();
+  s->otf_seg2d_len.release(); s->otf_mesh.release(); s->otf_l0.release(); s->otf_z0.release(); s->otf_cos.release();
+  s->otf_sin.release(); s->otf_volw.release(); s->otf_seg2d_ext.release(); s->otf_ext_fsr.release(); s->otf_trk2d.release();
+  s->otf_cls.release(); s->otf_count.release(); s->otf_trk2d_off.release(); s->otf_ext_off.release();
   s->phi_old.release(); s->fixed.release(); s->stab.release(); s->scratch.release();
   s->qst.release(); s->psi_a.release(); s->psi_b.release(); s->scal.release();
   s->partials.release(); s->hist_k.release(); s->hist_res.release(); s->iscal.release();
@@ -367,6 +380,8 @@ extern "C" int b200_upload_tracks(b200_solver* s, const double* seg_length, cons
   for (int64_t i = 0; i < ns; i++)
     if (seg_fsr[i] < 0 || seg_fsr[i] >= s->n_fsr)
       return fail("b200_upload_tracks: segment %lld FSR id %d outside [0,%lld)", (long long)i, seg_fsr[i], (long long)s->n_fsr);
+  s->seg_rec_ready = false;
+  s->otf = false;
   CU(s->seg_len.upload(seg_length, ns, s->stream));
   CU(s->seg_fsr.upload(seg_fsr, ns, s->stream));
   CU(s->trk_off.upload(trk_seg_offset, nt + 1, s->stream));
@@ -400,11 +415,13 @@ extern "C" int b200_upload_quadrature(b200_solver* s, const double* weight, cons
 
 extern "C" int b200_upload_fsrs(b200_solver* s, const double* volume, const int32_t* fsr_material) {
   NEED(s);
-  if (!volume || !fsr_material) return fail("b200_upload_fsrs: null array");
+  if (!fsr_material) return fail("b200_upload_fsrs: null array");
+  if (!volume && !s->volumes_from_tracer)
+    return fail("b200_upload_fsrs: volume may only be NULL after b200_otf_compute_volumes");
   for (int64_t r = 0; r < s->n_fsr; r++)
     if (fsr_material[r] < 0 || fsr_material[r] >= s->n_mat)
       return fail("b200_upload_fsrs: FSR %lld material %d outside [0,%d)", (long long)r, fsr_material[r], s->n_mat);
-  CU(s->vol.upload(volume, s->n_fsr, s->stream));
+  if (volume) { CU(s->vol.upload(volume, s->n_fsr, s->stream)); s->volumes_from_tracer = false; }
   CU(s->fsr_mat.upload(fsr_material, s->n_fsr, s->stream));
   s->h_fsr_mat.assign(fsr_material, fsr_material + s->n_fsr);
   CU(cudaStreamSynchronize(s->stream));
@@ -424,13 +441,16 @@ extern "C" int b200_upload_materials(b200_solver* s, const double* sigma_t, cons
   for (size_t i = 0; i < nG; i++)
     if (!(sigma_t[i] > 0.0))
       return fail("b200_upload_materials: sigma_t[%zu]=%g must be positive", i, sigma_t[i]);
+  /* sigma_f is optional (only computeFSRFissionRates(nu = false) reads it): NULL keeps a table
+   * uploaded earlier - material refreshes (adjoint <-> forward) do not touch it - else zeros */
   std::vector<double> zeros;
-  if (sigma_f == nullptr) { zeros.assign(nG, 0.); sigma_f = zeros.data(); }
+  const bool keep_sigma_f = sigma_f == nullptr && s->sigma_f.n == nG;
+  if (sigma_f == nullptr && !keep_sigma_f) { zeros.assign(nG, 0.); sigma_f = zeros.data(); }
   CU(s->sigma_t.upload(sigma_t, nG, s->stream));
   CU(s->sigma_s.upload(sigma_s, nGG, s->stream));
   CU(s->fiss.upload(fiss_matrix, nGG, s->stream));
   CU(s->nu_sigma_f.upload(nu_sigma_f, nG, s->stream));
-  CU(s->sigma_f.upload(sigma_f, nG, s->stream));
+  if (!keep_sigma_f) CU(s->sigma_f.upload(sigma_f, nG, s->stream));
   CU(s->chi.upload(chi, nG, s->stream));
   CU(s->fissionable.upload(fissionable, s->n_mat, s->stream));
   s->h_fissionable.assign(fissionable, fissionable + s->n_mat);
@@ -510,6 +530,237 @@ extern "C" int b200_get_cmfd_currents(b200_solver* s, double* out, int64_t n) {
   if (!s->cmfd_on) return fail("b200_get_cmfd_currents: CMFD tallies are off");
   if (n != s->n_cmfd_slots * s->ncg) return fail("b200_get_cmfd_currents: expected %lld values", (long long)(s->n_cmfd_slots * s->ncg));
   CU(cudaMemcpyAsync(out, s->currents.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* axial on-the-fly tracing (otf.cuh)                                          */
+/* ------------------------------------------------------------------------- */
+static OtfGeom otf_geom(b200_solver* s) {
+  OtfGeom g;
+  g.seg2d_len = s->otf_seg2d_len.p; g.seg2d_ext = s->otf_seg2d_ext.p; g.trk2d_off = s->otf_trk2d_off.p;
+  g.ext_off = s->otf_n_ext > 0 ? s->otf_ext_off.p : nullptr;
+  g.ext_mesh = s->otf_mesh.p; g.ext_fsr = s->otf_ext_fsr.p; g.n_axial = s->otf_n_axial;
+  g.trk_2d = s->otf_trk2d.p; g.trk_l0 = s->otf_l0.p; g.trk_z0 = s->otf_z0.p; g.trk_class = s->otf_cls.p;
+  g.cls_cos_theta = s->otf_cos.p; g.cls_sin_theta = s->otf_sin.p;
+  g.n_trk = s->n_trk;
+  return g;
+}
+
+extern "C" int b200_upload_otf_geometry(b200_solver* s, int64_t n_tracks_2d, int64_t n_segments_2d,
+                                        const double* seg2d_length, const int32_t* seg2d_extruded_fsr,
+                                        const int64_t* trk2d_seg_offset, int64_t n_extruded_fsrs,
+                                        const int64_t* ext_offset, const double* ext_mesh,
+                                        const int32_t* ext_fsr_ids, int32_t n_axial_global,
+                                        const double* theta /* [A/2][P] */) {
+  NEED(s);
+  if (!s->cfg.solve_3d) return fail("b200_upload_otf_geometry: axial on-the-fly tracing is for 3D solvers");
+  if (n_tracks_2d < 1 || n_segments_2d < 0 || !seg2d_length || !seg2d_extruded_fsr || !trk2d_seg_offset || !ext_mesh || !theta)
+    return fail("b200_upload_otf_geometry: null or empty argument");
+  if (trk2d_seg_offset[0] != 0 || trk2d_seg_offset[n_tracks_2d] != n_segments_2d)
+    return fail("b200_upload_otf_geometry: trk2d_seg_offset must run from 0 to n_segments_2d");
+  const bool global = n_extruded_fsrs <= 0;
+  int64_t n_ext_seen = 0;
+  for (int64_t i = 0; i < n_segments_2d; i++) {
+    if (seg2d_extruded_fsr[i] < 0) return fail("b200_upload_otf_geometry: negative extruded FSR id");
+    n_ext_seen = std::max<int64_t>(n_ext_seen, seg2d_extruded_fsr[i] + 1);
+    if (!(seg2d_length[i] >= 0.0)) return fail("b200_upload_otf_geometry: 2D segment %lld has length %g", (long long)i, seg2d_length[i]);
+  }
+  if (global) {
+    if (n_axial_global < 1) return fail("b200_upload_otf_geometry: a global axial mesh needs n_axial_global >= 1");
+    if (n_ext_seen * n_axial_global > s->n_fsr)
+      return fail("b200_upload_otf_geometry: %lld extruded FSRs x %d layers exceed n_fsrs = %lld", (long long)n_ext_seen,
+                  n_axial_global, (long long)s->n_fsr);
+    for (int k = 0; k < n_axial_global; k++)
+      if (!(ext_mesh[k + 1] > ext_mesh[k])) return fail("b200_upload_otf_geometry: the axial mesh must increase");
+    CU(s->otf_mesh.upload(ext_mesh, n_axial_global + 1, s->stream));
+    s->otf_n_ext = 0;
+  } else {
+    if (!ext_offset || !ext_fsr_ids) return fail("b200_upload_otf_geometry: per-FSR axial meshes need ext_offset and ext_fsr_ids");
+    if (n_ext_seen > n_extruded_fsrs) return fail("b200_upload_otf_geometry: a 2D segment refers to extruded FSR %lld of %lld",
+                                                  (long long)n_ext_seen - 1, (long long)n_extruded_fsrs);
+    if (ext_offset[0] != 0) return fail("b200_upload_otf_geometry: ext_offset must start at 0");
+    for (int64_t e = 0; e < n_extruded_fsrs; e++) {
+      const int64_t n = ext_offset[e + 1] - ext_offset[e];
+      if (n < 1) return fail("b200_upload_otf_geometry: extruded FSR %lld has no axial FSR", (long long)e);
+      for (int64_t k = 0; k < n; k++) {
+        const int32_t f = ext_fsr_ids[ext_offset[e] + k];
+        if (f < 0 || f >= s->n_fsr) return fail("b200_upload_otf_geometry: FSR id %d outside [0,%lld)", f, (long long)s->n_fsr);
+        if (!(ext_mesh[ext_offset[e] + e + k + 1] > ext_mesh[ext_offset[e] + e + k]))
+          return fail("b200_upload_otf_geometry: the axial mesh of extruded FSR %lld must increase", (long long)e);
+      }
+    }
+    const int64_t ntot = ext_offset[n_extruded_fsrs];
+    CU(s->otf_ext_off.upload(ext_offset, n_extruded_fsrs + 1, s->stream));
+    CU(s->otf_mesh.upload(ext_mesh, ntot + n_extruded_fsrs, s->stream));
+    CU(s->otf_ext_fsr.upload(ext_fsr_ids, ntot, s->stream));
+    s->otf_n_ext = n_extruded_fsrs;
+  }
+  s->otf_n_axial = global ? n_axial_global : 0;
+  CU(s->otf_seg2d_len.upload(seg2d_length, n_segments_2d, s->stream));
+  CU(s->otf_seg2d_ext.upload(seg2d_extruded_fsr, n_segments_2d, s->stream));
+  CU(s->otf_trk2d_off.upload(trk2d_seg_offset, n_tracks_2d + 1, s->stream));
+  const size_t ncls = (size_t)s->A2 * s->cfg.num_polar;
+  std::vector<double> c(ncls), sn(ncls);
+  for (size_t i = 0; i < ncls; i++) {
+    if (!(theta[i] > 0.0 && theta[i] < M_PI) || theta[i] == M_PI_2)
+      return fail("b200_upload_otf_geometry: polar angle %g of class %zu outside (0, pi) or horizontal", theta[i], i);
+    c[i] = cos(theta[i]); sn[i] = sin(theta[i]);
+  }
+  CU(s->otf_cos.upload(c.data(), ncls, s->stream));
+  CU(s->otf_sin.upload(sn.data(), ncls, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->otf_n_trk2d = n_tracks_2d; s->otf_n_seg2d = n_segments_2d;
+  return 0;
+}
+
+struct OtfStarts { DevBuf<int32_t> trk2d, cls; DevBuf<double> l0, z0; };
+static int otf_upload_track_starts(b200_solver* s, int64_t n, const int32_t* trk_2d, const double* trk_l0,
+                                   const double* trk_z0, const int32_t* trk_azim, const int32_t* trk_polar,
+                                   DevBuf<int32_t>& d_trk2d, DevBuf<double>& d_l0, DevBuf<double>& d_z0, DevBuf<int32_t>& d_cls) {
+  std::vector<int32_t> cls(n);
+  for (int64_t t = 0; t < n; t++) {
+    if (trk_2d[t] < 0 || trk_2d[t] >= s->otf_n_trk2d)
+      return fail("axial tracer: track %lld lies over 2D track %d outside [0,%lld)", (long long)t, trk_2d[t], (long long)s->otf_n_trk2d);
+    if (trk_azim[t] < 0 || trk_azim[t] >= s->A2 || trk_polar[t] < 0 || trk_polar[t] >= s->cfg.num_polar)
+      return fail("axial tracer: track %lld has angle indices (%d, %d) out of range", (long long)t, trk_azim[t], trk_polar[t]);
+    cls[t] = trk_azim[t] * s->cfg.num_polar + trk_polar[t];
+  }
+  CU(d_trk2d.upload(trk_2d, n, s->stream));
+  CU(d_l0.upload(trk_l0, n, s->stream));
+  CU(d_z0.upload(trk_z0, n, s->stream));
+  CU(d_cls.upload(cls.data(), n, s->stream));
+  CU(cudaStreamSynchronize(s->stream));      /* cls is a local */
+  return 0;
+}
+
+extern "C" int b200_otf_compute_volumes(b200_solver* s, int64_t n, const int32_t* trk_2d, const double* trk_l0,
+                                        const double* trk_z0, const int32_t* trk_azim, const int32_t* trk_polar,
+                                        const double* class_weight /* [A/2][P] */) {
+  NEED(s);
+  if (s->otf_n_trk2d == 0) return fail("b200_otf_compute_volumes: b200_upload_otf_geometry has not been called");
+  if (n < 0 || (n > 0 && (!trk_2d || !trk_l0 || !trk_z0 || !trk_azim || !trk_polar)) || !class_weight)
+    return fail("b200_otf_compute_volumes: null argument");
+  /* the tracks given here (normally ALL tracks of the problem) are independent of the solver's own
+   * (possibly sharded) track set: temporary buffers */
+  OtfStarts tmp;
+  struct Guard { OtfStarts& t; ~Guard() { t.trk2d.release(); t.cls.release(); t.l0.release(); t.z0.release(); } } guard{tmp};
+  if (otf_upload_track_starts(s, n, trk_2d, trk_l0, trk_z0, trk_azim, trk_polar, tmp.trk2d, tmp.l0, tmp.z0, tmp.cls)) return 1;
+  CU(s->otf_volw.upload(class_weight, (size_t)s->A2 * s->cfg.num_polar, s->stream));
+  CU(s->vol.alloc(s->n_fsr));
+  CU(cudaMemsetAsync(s->vol.p, 0, (size_t)s->n_fsr * 8, s->stream));
+  OtfGeom g = otf_geom(s);
+  g.trk_2d = tmp.trk2d.p; g.trk_l0 = tmp.l0.p; g.trk_z0 = tmp.z0.p; g.trk_class = tmp.cls.p;
+  g.n_trk = n;
+  if (n > 0) {
+    otf_fill_kernel<<<grid_for(n, 128, 1 << 20), 128, 0, s->stream>>>(g, nullptr, nullptr, s->G, s->otf_volw.p, s->vol.p);
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  s->volumes_from_tracer = true;
+  return 0;
+}
+
+extern "C" int b200_upload_tracks_otf(b200_solver* s, const int32_t* trk_2d, const double* trk_l0, const double* trk_z0,
+                                      const int32_t* trk_azim, const int32_t* trk_polar,
+                                      const int64_t* trk_next_fwd, const int64_t* trk_next_bwd,
+                                      const uint8_t* trk_flags, const uint8_t* trk_bc_fwd, const uint8_t* trk_bc_bwd,
+                                      int64_t* n_segments_out) {
+  NEED(s);
+  if (s->otf_n_trk2d == 0) return fail("b200_upload_tracks_otf: b200_upload_otf_geometry has not been called");
+  if (s->linear) return fail("b200_upload_tracks_otf: the linear source needs explicit segments (starting points) in this build");
+  const int64_t nt = s->n_trk;
+  if (nt > 0 && (!trk_2d || !trk_l0 || !trk_z0 || !trk_azim || !trk_polar || !trk_next_fwd || !trk_next_bwd ||
+                 !trk_flags || !trk_bc_fwd || !trk_bc_bwd))
+    return fail("b200_upload_tracks_otf: null array");
+  for (int64_t t = 0; t < nt; t++) {
+    const uint8_t bcs[2] = {trk_bc_fwd[t], trk_bc_bwd[t]};
+    const int64_t nx[2] = {trk_next_fwd[t], trk_next_bwd[t]};
+    for (int d = 0; d < 2; d++) {
+      if (bcs[d] == B200_BC_INTERFACE)
+        return fail("b200_upload_tracks_otf: track %lld ends on a domain INTERFACE; spatial domain "
+                    "decomposition is not supported by this build", (long long)t);
+      if ((bcs[d] == B200_BC_REFLECTIVE || bcs[d] == B200_BC_PERIODIC) && (nx[d] < 0 || nx[d] >= nt))
+        return fail("b200_upload_tracks_otf: track %lld links to track %lld outside [0,%lld)",
+                    (long long)t, (long long)nx[d], (long long)nt);
+    }
+  }
+  if (otf_upload_track_starts(s, nt, trk_2d, trk_l0, trk_z0, trk_azim, trk_polar, s->otf_trk2d, s->otf_l0, s->otf_z0, s->otf_cls)) return 1;
+  /* pass 1: count, prefix sum on the host (one int per track) */
+  CU(s->otf_count.alloc(std::max<int64_t>(nt, 1)));
+  OtfGeom g = otf_geom(s);
+  std::vector<int32_t> cnt(nt);
+  if (nt > 0) {
+    otf_count_kernel<<<grid_for(nt, 128, 1 << 20), 128, 0, s->stream>>>(g, s->otf_count.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cnt.data(), s->otf_count.p, nt * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  s->h_off.assign(nt + 1, 0);
+  for (int64_t t = 0; t < nt; t++) s->h_off[t + 1] = s->h_off[t] + cnt[t];
+  const int64_t ns = s->h_off[nt];
+  s->n_seg = ns;
+  s->cfg.n_segments = ns;
+  CU(s->trk_off.upload(s->h_off.data(), nt + 1, s->stream));
+  /* pass 2: the device segment stream, written in place */
+  s->seg_len.release(); s->seg_fsr.release();
+  CU(s->seg_rec.alloc((size_t)ns + 2 * SEG_PAD));
+  otf_pad_kernel<<<1, 2 * SEG_PAD, 0, s->stream>>>(s->seg_rec.p, ns);
+  CU(cudaGetLastError());
+  if (nt > 0) {
+    otf_fill_kernel<<<grid_for(nt, 128, 1 << 20), 128, 0, s->stream>>>(g, s->trk_off.p, s->seg_rec.p + SEG_PAD, s->G, nullptr, nullptr);
+    CU(cudaGetLastError());
+  }
+  s->h_azim.assign(trk_azim, trk_azim + nt);
+  s->h_polar.assign(trk_polar, trk_polar + nt);
+  s->h_next_fwd.assign(trk_next_fwd, trk_next_fwd + nt);
+  s->h_next_bwd.assign(trk_next_bwd, trk_next_bwd + nt);
+  s->h_flags.assign(trk_flags, trk_flags + nt);
+  s->h_bc_fwd.assign(trk_bc_fwd, trk_bc_fwd + nt);
+  s->h_bc_bwd.assign(trk_bc_bwd, trk_bc_bwd + nt);
+  CU(cudaStreamSynchronize(s->stream));
+  s->seg_rec_ready = true;
+  s->otf = true;
+  s->have_tracks = true;
+  s->finalized = false;
+  if (n_segments_out) *n_segments_out = ns;
+  return 0;
+}
+
+extern "C" int b200_get_num_segments(b200_solver* s, int64_t* n_segments) {
+  NEED(s);
+  if (n_segments) *n_segments = s->n_seg;
+  return 0;
+}
+
+extern "C" int b200_get_segments(b200_solver* s, double* seg_length, int32_t* seg_fsr, int64_t n, int64_t* trk_seg_offset) {
+  NEED(s);
+  if (!s->have_tracks) return fail("b200_get_segments: no tracks uploaded");
+  if (n != s->n_seg) return fail("b200_get_segments: %lld segments requested, the solver holds %lld", (long long)n, (long long)s->n_seg);
+  if (trk_seg_offset) memcpy(trk_seg_offset, s->h_off.data(), (s->n_trk + 1) * sizeof(int64_t));
+  if (n == 0) return 0;
+  if (!s->seg_rec_ready) {
+    if (seg_length) CU(cudaMemcpyAsync(seg_length, s->seg_len.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (seg_fsr) CU(cudaMemcpyAsync(seg_fsr, s->seg_fsr.p, n * 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+  }
+  struct Tmp { void* p = nullptr; ~Tmp() { if (p) cudaFree(p); } } dl, df;
+  CU(cudaMalloc(&dl.p, n * 8));
+  CU(cudaMalloc(&df.p, n * 4));
+  otf_unpack_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->seg_rec.p + SEG_PAD, n, s->G, (double*)dl.p, (int32_t*)df.p);
+  CU(cudaGetLastError());
+  if (seg_length) CU(cudaMemcpyAsync(seg_length, dl.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (seg_fsr) CU(cudaMemcpyAsync(seg_fsr, df.p, n * 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+extern "C" int b200_get_volumes(b200_solver* s, double* out, int64_t n) {
+  NEED(s);
+  if (n != s->n_fsr || s->vol.n != (size_t)s->n_fsr) return fail("b200_get_volumes: size mismatch or no volumes yet");
+  CU(cudaMemcpyAsync(out, s->vol.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   return 0;
 }
@@ -650,11 +901,13 @@ extern "C" int b200_finalize(b200_solver* s) {
   /* device segment stream: padded 16-byte records with the FSR id premultiplied by G */
   if ((double)s->n_fsr * s->G * (s->linear ? 3.0 : 1.0) >= 4294967296.0)
     return fail("b200_finalize: n_fsrs*G = %.3g exceeds the 32-bit tally index of this build", (double)s->n_fsr * s->G);
-  if (s->seg_len.n != (size_t)s->n_seg) return fail("b200_finalize: tracks must be re-uploaded before finalize");
-  CU(s->seg_rec.alloc((size_t)s->n_seg + 2 * SEG_PAD));
-  build_segrec_kernel<<<grid_for(s->n_seg + 2 * SEG_PAD, 256), 256, 0, s->stream>>>(
-      s->seg_rec.p, s->seg_len.p, s->seg_fsr.p, s->n_seg, s->G);
-  CU(cudaGetLastError());
+  if (!s->seg_rec_ready) {
+    if (s->seg_len.n != (size_t)s->n_seg) return fail("b200_finalize: tracks must be re-uploaded before finalize");
+    CU(s->seg_rec.alloc((size_t)s->n_seg + 2 * SEG_PAD));
+    build_segrec_kernel<<<grid_for(s->n_seg + 2 * SEG_PAD, 256), 256, 0, s->stream>>>(
+        s->seg_rec.p, s->seg_len.p, s->seg_fsr.p, s->n_seg, s->G);
+    CU(cudaGetLastError());
+  }
 
   if (s->linear) {
     if (!s->have_ls) return fail("b200_finalize: linear source requested but b200_upload_linear_source was not called");
@@ -765,9 +1018,7 @@ static int launch_sweep(b200_solver* s) {
   }
   if (s->cfg.deterministic) {
     FsrArgs fa = fsr_args(s);
-    const int64_t npsi = s->n_trk * 2 * (int64_t)s->F;
-    fx_bound_kernel<<<grid_for(std::max<int64_t>(npsi, (int64_t)nphi), RED_THREADS), RED_THREADS, 0, s->stream>>>(
-        fa, s->psi_start, npsi, s->fx_bits.p);
+    fx_bound_kernel<<<grid_for((int64_t)nphi, RED_THREADS), RED_THREADS, 0, s->stream>>>(fa, s->fx_bits.p);
     CU(cudaGetLastError());
     fx_scale_kernel<<<1, 1, 0, s->stream>>>(fa, s->fx_bits.p);
     CU(cudaGetLastError());
@@ -925,6 +1176,7 @@ extern "C" int b200_zero_track_fluxes(b200_solver* s) {
     CU(cudaMemsetAsync(s->psi_a.p, 0, npsi * 4, s->stream));
     CU(cudaMemsetAsync(s->psi_b.p, 0, npsi * 4, s->stream));
   }
+  CU(cudaMemsetAsync(s->scal.p + SC_PSIMAX, 0, sizeof(double), s->stream));    /* bound on |psi| (deterministic tally) */
   return 0;
 }
 
@@ -1110,21 +1362,30 @@ extern "C" int b200_compute_residual(b200_solver* s, int32_t res_type, double* r
   return 0;
 }
 
-extern "C" int b200_compute_stabilizing_flux(b200_solver* s) {
-  NEED_FINAL(s);
+static int launch_stabilizing_flux(b200_solver* s) {
   stabilizing_flux_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(
       fsr_args(s), s->stab_type, s->stab_factor, s->max_ratio.p);
   CU(cudaGetLastError());
   s->n_launches++;
   return 0;
 }
-extern "C" int b200_stabilize_flux(b200_solver* s) {
-  NEED_FINAL(s);
+static int launch_stabilize_flux(b200_solver* s) {
   stabilize_flux_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(
       fsr_args(s), s->stab_type, s->stab_factor, s->max_ratio.p);
   CU(cudaGetLastError());
   s->n_launches++;
   return 0;
+}
+
+extern "C" int b200_compute_stabilizing_flux(b200_solver* s) {
+  NEED_FINAL(s);
+  if (clear_done(s)) return 1;
+  return launch_stabilizing_flux(s);
+}
+extern "C" int b200_stabilize_flux(b200_solver* s) {
+  NEED_FINAL(s);
+  if (clear_done(s)) return 1;
+  return launch_stabilize_flux(s);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -1137,6 +1398,19 @@ extern "C" int b200_get_fluxes(b200_solver* s, double* out, int64_t n) {
                 "not match the requested %lld flux values", s->G, (long long)s->n_fsr, (long long)n);
   CU(cudaMemcpyAsync(out, s->phi.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+/* getFluxes + the current k_eff behind ONE host synchronisation (hosts that drive the solver step by
+ * step, openmoc/krylov.py style, need both after every iteration) */
+extern "C" int b200_get_fluxes_keff(b200_solver* s, double* out, int64_t n, double* k_eff) {
+  NEED_FINAL(s);
+  if (n != s->n_fsr * s->G)
+    return fail("Unable to get FSR scalar fluxes since there are %d groups and %lld FSRs which does "
+                "not match the requested %lld flux values", s->G, (long long)s->n_fsr, (long long)n);
+  CU(cudaMemcpyAsync(out, s->phi.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemcpyAsync(s->h_scal, s->scal.p, SC_COUNT_D * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (k_eff) *k_eff = s->h_scal[SC_KEFF];
   return 0;
 }
 extern "C" int b200_set_fluxes(b200_solver* s, const double* in, int64_t n) {
@@ -1258,6 +1532,9 @@ extern "C" int b200_set_start_fluxes(b200_solver* s, const float* in, int64_t n)
   NEED_FINAL(s);
   if (n != s->n_trk * 2 * (int64_t)s->F) return fail("b200_set_start_fluxes: size mismatch");
   if (n) CU(cudaMemcpyAsync(s->psi_start, in, n * 4, cudaMemcpyHostToDevice, s->stream));
+  double m = 0.;
+  for (int64_t i = 0; i < n; i++) m = std::max(m, (double)std::fabs(in[i]));
+  CU(cudaMemcpyAsync(s->scal.p + SC_PSIMAX, &m, sizeof(double), cudaMemcpyHostToDevice, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   return 0;
 }
@@ -1268,7 +1545,7 @@ extern "C" int b200_set_start_fluxes(b200_solver* s, const float* in, int64_t n)
 /* one source iteration of Solver::computeEigenvalue (src/Solver.cpp:1614-1681) */
 /* i < 0: captured into the CUDA graph (iterations >= 2, number read from the device counter) */
 static int enqueue_iteration_begin(b200_solver* s, int i) {
-  if (i != 0 && s->stabilize) { if (b200_compute_stabilizing_flux(s)) return 1; }
+  if (i != 0 && s->stabilize) { if (launch_stabilizing_flux(s)) return 1; }
   if (launch_sources(s, i, 0)) return 1;
   return launch_sweep(s);
 }
@@ -1278,7 +1555,7 @@ static int enqueue_iteration_end(b200_solver* s, int i, int res_type, int loop_k
   if (s->balance) {
     if (launch_closure(s, 0, nullptr)) return 1;
     if (launch_balance_keff(s)) return 1;
-    if (i != 0 && s->stabilize) { if (b200_stabilize_flux(s)) return 1; }
+    if (i != 0 && s->stabilize) { if (launch_stabilize_flux(s)) return 1; }
     if (launch_rate(s, 2)) return 1;
   } else if (!s->stabilize) {
     /* closure + the one nu-fission reduction that feeds both computeKeff and
@@ -1291,7 +1568,7 @@ static int enqueue_iteration_end(b200_solver* s, int i, int res_type, int loop_k
   } else {
     if (launch_closure(s, 0, nullptr)) return 1;
     if (launch_rate(s, 1)) return 1;
-    if (i != 0) { if (b200_stabilize_flux(s)) return 1; }
+    if (i != 0) { if (launch_stabilize_flux(s)) return 1; }
     if (launch_rate(s, 2)) return 1;
   }
   /* normalizeFluxes' scaling of phi fused into the residual pass, storeFSRFluxes after */
@@ -1546,6 +1823,55 @@ extern "C" int b200_eval_expF1(int32_t device, int32_t precision, const double* 
   eval_expf1_kernel<<<grid_for(n, 256), 256>>>(dx.p, dout.p, n, precision);
   CU(cudaGetLastError());
   CU(cudaMemcpy(out, dout.p, n * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* machine ceilings (microbench.cuh)                                           */
+/* ------------------------------------------------------------------------- */
+extern "C" int b200_measure_ceilings(int32_t device, int64_t table_rows, double* fp64_instr_per_s,
+                                     double* red_f64_per_s) {
+  if (table_rows < 1) return fail("b200_measure_ceilings: table_rows must be positive");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int sms = prop.multiProcessorCount;
+  struct Tmp { void* p = nullptr; ~Tmp() { if (p) cudaFree(p); } } out, table;
+  struct Ev { cudaEvent_t e = nullptr; ~Ev() { if (e) cudaEventDestroy(e); } } e0, e1;
+  CU(cudaEventCreate(&e0.e)); CU(cudaEventCreate(&e1.e));
+  float ms = 0.f;
+  {
+    const int threads = 224, blocks = sms * 4, iters = 2048;       /* 28 warps per SM like the sweep */
+    CU(cudaMalloc(&out.p, (size_t)threads * blocks * 8));
+    mb_fp64_kernel<<<blocks, threads>>>((double*)out.p, 16, 1.0000001);
+    double best = 1e30;
+    for (int rep = 0; rep < 3; rep++) {
+      CU(cudaEventRecord(e0.e));
+      mb_fp64_kernel<<<blocks, threads>>>((double*)out.p, iters, 1.0000001);
+      CU(cudaEventRecord(e1.e));
+      CU(cudaEventSynchronize(e1.e));
+      CU(cudaEventElapsedTime(&ms, e0.e, e1.e));
+      best = std::min(best, (double)ms);
+    }
+    if (fp64_instr_per_s) *fp64_instr_per_s = (double)threads * blocks * iters * 48.0 / (best * 1e-3);
+  }
+  {
+    const int threads = 224, blocks = sms * 4, iters = 1000;
+    CU(cudaMalloc(&table.p, (size_t)table_rows * 7 * 8));
+    CU(cudaMemset(table.p, 0, (size_t)table_rows * 7 * 8));
+    mb_red_kernel<<<blocks, threads>>>((double*)table.p, (int)table_rows, 8);
+    double best = 1e30;
+    for (int rep = 0; rep < 3; rep++) {
+      CU(cudaEventRecord(e0.e));
+      mb_red_kernel<<<blocks, threads>>>((double*)table.p, (int)table_rows, iters);
+      CU(cudaEventRecord(e1.e));
+      CU(cudaEventSynchronize(e1.e));
+      CU(cudaEventElapsedTime(&ms, e0.e, e1.e));
+      best = std::min(best, (double)ms);
+    }
+    if (red_f64_per_s) *red_f64_per_s = (double)threads * blocks * iters / (best * 1e-3);
+  }
+  CU(cudaGetLastError());
   return 0;
 }
 

@@ -22,7 +22,7 @@ constexpr int RED_THREADS = 256;
 constexpr int MAX_PARTIALS = 1024;
 
 /* device scalar block (double) */
-enum { SC_KEFF = 0, SC_RATE, SC_NORM, SC_RESIDUAL, SC_KPREV, SC_TOL, SC_FXSCALE, SC_FXBOUND, SC_COUNT_D };
+enum { SC_KEFF = 0, SC_RATE, SC_NORM, SC_RESIDUAL, SC_KPREV, SC_TOL, SC_FXSCALE, SC_FXBOUND, SC_PSIMAX, SC_COUNT_D };
 /* device scalar block (int) */
 enum { SI_DONE = 0, SI_ITERS, SI_EXEC, SI_NEG_SRC, SI_NEG_FLUX, SI_COUNT_I };
 
@@ -235,7 +235,12 @@ rate_finalize_kernel(const FsrArgs a, int n_partials, int op) {
       a.scal[SC_KPREV] = a.scal[SC_KEFF];
       a.scal[SC_KEFF] *= rate / (double)a.n_fsr_global;
     }
-    if (op & 2) a.scal[SC_NORM] = (double)a.n_fsr_global / rate;
+    if (op & 2) {
+      a.scal[SC_NORM] = (double)a.n_fsr_global / rate;
+      /* every normalisation factor is applied to the track fluxes exactly once (scale_psi_kernel):
+       * the bound on |psi| that the deterministic tally keeps follows it */
+      a.scal[SC_PSIMAX] *= fabs(a.scal[SC_NORM]);
+    }
   }
 }
 
@@ -377,6 +382,7 @@ __global__ void fill_chi_kernel(const FsrArgs a, int material) {
  * max_ratio[e] (YAMAMOTO) is a material-table quantity: computed on the host. */
 __global__ void stabilizing_flux_kernel(const FsrArgs a, int type, double factor,
                                         const double* __restrict__ max_ratio) {
+  if (a.iscal[SI_DONE]) return;      /* a converged device-side loop leaves the flux untouched */
   const int G = a.G;
   const int64_t n = a.n_fsr * G;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
@@ -396,6 +402,7 @@ __global__ void stabilizing_flux_kernel(const FsrArgs a, int type, double factor
 }
 __global__ void stabilize_flux_kernel(const FsrArgs a, int type, double factor,
                                       const double* __restrict__ max_ratio) {
+  if (a.iscal[SI_DONE]) return;
   const int G = a.G;
   const int64_t n = a.n_fsr * G;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
@@ -434,15 +441,15 @@ __global__ void fission_rates_kernel(const FsrArgs a, double* __restrict__ out, 
 
 /* ---- deterministic (fixed-point) tally support --------------------------------------
  * |sum w dpsi| <= 4 pi Sigma_t V M for every (FSR, group), with M the largest angular flux
- * that can occur: max(|psi_in|, |q| / Sigma_t) (psi along a track is a convex combination
+ * that can occur: max(bound on |psi_in|, |q| / Sigma_t) (psi along a track is a convex combination
  * of its start value and the local q / Sigma_t).  A power-of-two scale with 2^5 head room
  * under 2^62 therefore cannot overflow; resolution is ~1e-17 of the bound. */
 __global__ void __launch_bounds__(RED_THREADS)
-fx_bound_kernel(const FsrArgs a, const float* __restrict__ psi, int64_t n_psi, unsigned long long* __restrict__ bits) {
-  /* bits[0]: max |psi|, bits[1]: max |q|/sigma_t, bits[2]: max sigma_t*V  (non-negative doubles order like integers) */
-  double m_psi = 0., m_q = 0., m_sv = 0.;
+fx_bound_kernel(const FsrArgs a, unsigned long long* __restrict__ bits) {
+  /* bits[1]: max |q|/sigma_t, bits[2]: max sigma_t*V  (non-negative doubles order like integers).
+   * Both are replicated quantities: every rank of a multi-GPU run derives the same scale. */
+  double m_q = 0., m_sv = 0.;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = tid; i < n_psi; i += nth) m_psi = fmax(m_psi, fabs((double)psi[i]));
   const int64_t n = a.n_fsr * a.G;
   for (int64_t i = tid; i < n; i += nth) {
     const double2 qs = a.qst[i];
@@ -451,19 +458,22 @@ fx_bound_kernel(const FsrArgs a, const float* __restrict__ psi, int64_t n_psi, u
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    m_psi = fmax(m_psi, __shfl_xor_sync(0xffffffffu, m_psi, o));
     m_q = fmax(m_q, __shfl_xor_sync(0xffffffffu, m_q, o));
     m_sv = fmax(m_sv, __shfl_xor_sync(0xffffffffu, m_sv, o));
   }
   if ((threadIdx.x & 31) == 0) {
-    atomicMax(&bits[0], (unsigned long long)__double_as_longlong(m_psi));
     atomicMax(&bits[1], (unsigned long long)__double_as_longlong(m_q));
     atomicMax(&bits[2], (unsigned long long)__double_as_longlong(m_sv));
   }
 }
+/* The bound on |psi| is kept as a recursion instead of a scan of this GPU's track fluxes (which
+ * differ from rank to rank in a multi-GPU run and would give every rank its own scale): no flux
+ * leaving this sweep exceeds max(bound on the incoming ones, max |q|/sigma_t); normalisations
+ * rescale it (rate_finalize_kernel), zeroTrackFluxes resets it. */
 __global__ void fx_scale_kernel(const FsrArgs a, unsigned long long* __restrict__ bits) {
   if (a.iscal[SI_DONE]) return;
-  const double m = fmax(__longlong_as_double((long long)bits[0]), __longlong_as_double((long long)bits[1]));
+  const double m = fmax(a.scal[SC_PSIMAX], __longlong_as_double((long long)bits[1]));
+  a.scal[SC_PSIMAX] = m;
   double bound = FOUR_PI * __longlong_as_double((long long)bits[2]) * m;
   if (!(bound > 0.)) bound = 1.0;
   int ex;

@@ -42,6 +42,18 @@ def assign_pairs(num_azim: int, seg_per_azim: np.ndarray, world: int) -> List[Li
     return [sorted(o) for o in owned]
 
 
+def track_load(ft: FlatTracks) -> np.ndarray:
+    """Work per track: its segment count, or - for an on-the-fly 3D track set, whose segments
+    only exist on the device - its length (segments per cm are nearly uniform over a deck)."""
+    a = ft.arrays
+    if "trk_seg_offset" in a and a["trk_seg_offset"].size == ft.n_tracks + 1 and ft.n_segments > 0:
+        return np.diff(a["trk_seg_offset"].astype(np.int64)).astype(np.float64)
+    if "trk_end" in a and a["trk_end"].size == 3 * ft.n_tracks:
+        d = a["trk_end"].reshape(-1, 3) - a["trk_start"].reshape(-1, 3)
+        return np.sqrt((d * d).sum(axis=1))
+    return np.ones(ft.n_tracks)
+
+
 def track_components(ft: FlatTracks) -> np.ndarray:
     """Connected components of the boundary hand-off graph: label per track."""
     from scipy.sparse import coo_matrix
@@ -66,7 +78,7 @@ def partition_by_chain(ft: FlatTracks, world: int, only: int = None) -> List[Fla
     ranks, longest-processing-time first by segment count.  `only`: build that rank's shard
     alone (None for the others)."""
     labels = track_components(ft)
-    nseg = np.diff(ft.arrays["trk_seg_offset"].astype(np.int64))
+    nseg = track_load(ft)
     n_comp = int(labels.max()) + 1 if labels.size else 0
     if n_comp < world:
         raise ValueError(f"{world} ranks but only {n_comp} independent track chains")
@@ -85,7 +97,7 @@ def partition_by_chain(ft: FlatTracks, world: int, only: int = None) -> List[Fla
 
 def partition_by_azim_pair(ft: FlatTracks, world: int, only: int = None) -> List[FlatTracks]:
     a = ft.arrays
-    nseg = np.diff(a["trk_seg_offset"].astype(np.int64))
+    nseg = track_load(ft)
     azim = a["trk_azim"].astype(np.int64)
     seg_per_azim = np.bincount(azim, weights=nseg, minlength=ft.num_azim // 2)
     owned = assign_pairs(ft.num_azim, seg_per_azim, world)
@@ -97,10 +109,11 @@ def _extract(ft: FlatTracks, ids: np.ndarray, closed: bool = True) -> FlatTracks
     """The sub-problem made of tracks `ids`, renumbered 0..n-1.  `closed`: the set must be
     closed under links; otherwise links that leave it are returned as -2."""
     a = ft.arrays
-    off = a["trk_seg_offset"].astype(np.int64)
+    explicit = "trk_seg_offset" in a and a["trk_seg_offset"].size == ft.n_tracks + 1
+    off = a["trk_seg_offset"].astype(np.int64) if explicit else np.zeros(ft.n_tracks + 1, dtype=np.int64)
     nseg = np.diff(off)
     per_track = ("trk_azim", "trk_polar", "trk_xy", "trk_flags", "trk_bc_fwd", "trk_bc_bwd",
-                 "trk_phi", "trk_theta")
+                 "trk_phi", "trk_theta", "trk_2d", "trk_l0", "trk_lz")
     per_seg = ("seg_length", "seg_fsr", "seg_mat", "seg_cmfd_fwd", "seg_cmfd_bwd")
     new_id = np.full(ft.n_tracks, -1, dtype=np.int64)
     new_id[ids] = np.arange(ids.size)
@@ -117,6 +130,9 @@ def _extract(ft: FlatTracks, ids: np.ndarray, closed: bool = True) -> FlatTracks
     for k in per_track:
         if k in a:
             b[k] = a[k][ids]
+    for k in ("trk_start", "trk_end"):
+        if k in a and ft.n_tracks and a[k].size % ft.n_tracks == 0:
+            b[k] = a[k].reshape(ft.n_tracks, -1)[ids].ravel()
     for k in per_seg:
         if k in a and a[k].size == ft.n_segments:
             b[k] = a[k][seg_idx]
@@ -133,7 +149,7 @@ def _extract(ft: FlatTracks, ids: np.ndarray, closed: bool = True) -> FlatTracks
             mapped = np.where(linked & (mapped < 0), -2, mapped)
         b["trk_next_" + d] = mapped
     for k, v in a.items():
-        if k.startswith(("quad_", "fsr_", "mat_")):
+        if k.startswith(("quad_", "fsr_", "mat_", "seg2d_", "trk2d_", "fsr2d_")) or k == "z_mesh":
             b[k] = v
     return sub
 

@@ -107,6 +107,9 @@ class B200Solver:
             else:
                 raise B200Error("unknown partition %r (pair, chain, track)" % partition)
         self.tracks = tracks
+        # a 3D track set without explicit segments: the device traces the z-stacks (b200_upload_tracks_otf)
+        self._otf = bool(tracks.solve_3d) and tracks.n_segments == 0 and "seg2d_length" in tracks.arrays
+        self.num_segments = tracks.n_segments
         self._num_groups = tracks.num_groups
         self._num_FSRs = tracks.n_fsrs
         self._converge_thresh = 1e-5           # Solver.cpp default
@@ -132,14 +135,17 @@ class B200Solver:
         a = ft.arrays
         c = lambda k, dt: np.ascontiguousarray(a[k], dtype=dt)
         L, h = self._lib, self._h
-        keep = [c("seg_length", "f8"), c("seg_fsr", "i4"), c("trk_seg_offset", "i8"), c("trk_azim", "i4"),
-                c("trk_polar", "i4"), c("trk_next_fwd", "i8"), c("trk_next_bwd", "i8"), c("trk_flags", "u1"),
-                c("trk_bc_fwd", "u1"), c("trk_bc_bwd", "u1")]
-        check(L.b200_upload_tracks(h, *[_ptr(x) for x in keep]))
+        if self._otf:
+            self._upload_otf(ft)
+        else:
+            keep = [c("seg_length", "f8"), c("seg_fsr", "i4"), c("trk_seg_offset", "i8"), c("trk_azim", "i4"),
+                    c("trk_polar", "i4"), c("trk_next_fwd", "i8"), c("trk_next_bwd", "i8"), c("trk_flags", "u1"),
+                    c("trk_bc_fwd", "u1"), c("trk_bc_bwd", "u1")]
+            check(L.b200_upload_tracks(h, *[_ptr(x) for x in keep]))
         w, st = c("quad_weight", "f8"), c("quad_sin_theta", "f8")
         check(L.b200_upload_quadrature(h, _ptr(w), _ptr(st)))
         v, fm = c("fsr_volume", "f8"), c("fsr_mat", "i4")
-        check(L.b200_upload_fsrs(h, _ptr(v), _ptr(fm)))
+        check(L.b200_upload_fsrs(h, None if self._otf else _ptr(v), _ptr(fm)))
         mats = [c("mat_sigma_t", "f8"), c("mat_sigma_s", "f8"), c("mat_fiss_matrix", "f8"),
                 c("mat_nu_sigma_f", "f8"), c("mat_sigma_f", "f8"), c("mat_chi", "f8"),
                 c("mat_fissionable", "u1")]
@@ -147,6 +153,50 @@ class B200Solver:
         if self._ls_tables is not None:
             check(L.b200_upload_linear_source(h, *[_ptr(x) for x in self._ls_tables]))
         check(L.b200_finalize(h))
+
+    def _upload_otf(self, ft: FlatTracks) -> None:
+        """Axial on-the-fly track set (synth.make_tracks_3d(expand=False), or what b200_flatten
+        hands over for OTF_TRACKS / OTF_STACKS): the device traces the z-stacks itself.  The FSR
+        volumes come from ALL tracks of the problem, the segment stream from this rank's shard."""
+        L, h = self._lib, self._h
+        g = self._global_tracks.arrays
+        a = ft.arrays
+        c = lambda d, k, dt: np.ascontiguousarray(d[k], dtype=dt)
+        P = ft.num_polar
+        theta = np.zeros(ft.num_azim // 2 * P)
+        theta[g["trk_azim"].astype(np.int64) * P + g["trk_polar"]] = g["trk_theta"]
+        geo = [c(g, "seg2d_length", "f8"), c(g, "seg2d_fsr", "i4"), c(g, "trk2d_seg_offset", "i8")]
+        mesh = c(g, "z_mesh", "f8")
+        check(L.b200_upload_otf_geometry(h, geo[2].size - 1, geo[0].size, _ptr(geo[0]), _ptr(geo[1]), _ptr(geo[2]),
+                                         0, None, _ptr(mesh), None, mesh.size - 1, _ptr(theta)))
+        # VolumeKernel weight (src/MOCKernel.cpp:80-100): azimuthal spacing x weight x polar spacing x weight
+        A2 = ft.num_azim // 2
+        cw = (np.repeat(g["quad_azim_spacing"] * g["quad_azim_weight"], P)
+              * g["quad_polar_spacing"] * g["quad_polar_weight"]).astype("f8")
+        assert cw.size == A2 * P
+        z0 = lambda d: np.ascontiguousarray(d["trk_start"].reshape(-1, 3)[:, 2])
+        allt = [c(g, "trk_2d", "i4"), c(g, "trk_l0", "f8"), z0(g), c(g, "trk_azim", "i4"), c(g, "trk_polar", "i4")]
+        check(L.b200_otf_compute_volumes(h, allt[0].size, *[_ptr(x) for x in allt], _ptr(cw)))
+        mine = [c(a, "trk_2d", "i4"), c(a, "trk_l0", "f8"), z0(a), c(a, "trk_azim", "i4"), c(a, "trk_polar", "i4"),
+                c(a, "trk_next_fwd", "i8"), c(a, "trk_next_bwd", "i8"), c(a, "trk_flags", "u1"),
+                c(a, "trk_bc_fwd", "u1"), c(a, "trk_bc_bwd", "u1")]
+        ns = C.c_int64()
+        check(L.b200_upload_tracks_otf(h, *[_ptr(x) for x in mine], C.byref(ns)))
+        self.num_segments = int(ns.value)
+
+    def getSegments(self):
+        """(seg_length, seg_fsr, trk_seg_offset) as the device holds them (tests, track dumps)."""
+        n = C.c_int64()
+        check(self._lib.b200_get_num_segments(self._h, C.byref(n)))
+        length, fsr = np.empty(n.value, "f8"), np.empty(n.value, "i4")
+        off = np.empty(self.tracks.n_tracks + 1, "i8")
+        check(self._lib.b200_get_segments(self._h, _ptr(length), _ptr(fsr), n.value, _ptr(off)))
+        return length, fsr, off
+
+    def getVolumes(self) -> np.ndarray:
+        out = np.empty(self._num_FSRs, "f8")
+        check(self._lib.b200_get_volumes(self._h, _ptr(out), out.size))
+        return out
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -180,12 +230,25 @@ class B200Solver:
                             % threshold)
         self._converge_thresh = float(threshold)
 
-    def getFluxes(self, num_fluxes: Optional[int] = None) -> np.ndarray:
-        """ARGOUT_ARRAY1 in the reference (numpy_typemaps.i:52): returns a new float64 array."""
+    def getFluxes(self, num_fluxes: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """ARGOUT_ARRAY1 in the reference (numpy_typemaps.i:52): returns a new float64 array.
+        out: write into this (e.g. pinned) float64 array instead; k_eff is fetched in the same host
+        synchronisation and available from getKeffNoSync()."""
         n = self._num_FSRs * self._num_groups if num_fluxes is None else int(num_fluxes)
-        out = np.empty(n, dtype=np.float64)
-        check(self._lib.b200_get_fluxes(self._h, _ptr(out), n))
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+            check(self._lib.b200_get_fluxes(self._h, _ptr(out), n))
+            return out
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.size != n:
+            raise B200Error("getFluxes(out=...) needs a contiguous float64 array of %d values" % n)
+        k = C.c_double()
+        check(self._lib.b200_get_fluxes_keff(self._h, _ptr(out), n, C.byref(k)))
+        self._k_eff = k.value
         return out
+
+    def getKeffNoSync(self) -> float:
+        """k_eff as of the last call that fetched it (getKeff, computeKeff, getFluxes(out=...))."""
+        return self._k_eff
 
     def setFluxes(self, in_fluxes) -> None:
         x = np.ascontiguousarray(in_fluxes, dtype=np.float64).ravel()
@@ -462,4 +525,4 @@ class B200Solver:
 
     def integrationsPerSweep(self) -> int:
         """W = 2 * F * N_seg of the reference's timer report (Solver.cpp:1901-1902)."""
-        return 2 * self.tracks.fluxes_per_track * self.tracks.n_segments
+        return 2 * self.tracks.fluxes_per_track * self.num_segments

@@ -32,6 +32,8 @@ std::map<std::string, Material*> make_c5g7_materials() {
   return out;
 }
 
+int g_axial_layers = 1;
+
 void fill_lattice(Lattice* lat, int ny, int nx, const std::vector<Universe*>& rows_top_down) {
   /* rows_top_down is row-major starting at the upper-left corner, exactly the
    * nested-list convention of Lattice::setUniverses (Universe.cpp:1604-1616) */
@@ -308,8 +310,17 @@ Model c5g7_2d(int dims) {
 
   /* c5g7-2d.py:34-37 */
   Lattice* root_lat = new Lattice();
-  root_lat->setWidth(21.42, 21.42);
-  fill_lattice(root_lat, 3, 3, {uu, mu, ri, mu, uu, ri, rb, rb, rc});
+  if (dims == 3 && g_axial_layers > 1) {
+    /* N identical axial layers: the 3 x 3 x N root lattice of profile/models/c5g7/c5g7-3d-cmfd.cpp */
+    root_lat->setWidth(21.42, 21.42, 64.26 / g_axial_layers);
+    std::vector<Universe*> all;
+    for (int k = 0; k < g_axial_layers; k++)
+      for (Universe* u9 : {uu, mu, ri, mu, uu, ri, rb, rb, rc}) all.push_back(u9);
+    root_lat->setUniverses(g_axial_layers, 3, 3, all.data());
+  } else {
+    root_lat->setWidth(21.42, 21.42);
+    fill_lattice(root_lat, 3, 3, {uu, mu, ri, mu, uu, ri, rb, rb, rc});
+  }
   Cell* root_cell = new Cell();
   root_cell->addSurface(+1, xmin); root_cell->addSurface(-1, xmax);
   root_cell->addSurface(+1, ymin); root_cell->addSurface(-1, ymax);
@@ -339,6 +350,8 @@ std::vector<double> linspace(double a, double b, int n) {
 
 }  // namespace
 
+
+void set_axial_layers(int n) { g_axial_layers = n < 1 ? 1 : n; }
 
 Model build_model(const std::string& name, int dims) {
   if (name == "pin-cell") return pin_cell(dims);

@@ -32,6 +32,9 @@ struct Model {
 
 /** dims = 2 or 3 (only simple-lattice and pin-cell honour 3). */
 Model build_model(const std::string& name, int dims);
+/** c5g7-2d with dims = 3: number of equal axial layers of the root lattice (3 x 3 x N, the structure of
+ *  profile/models/c5g7/c5g7-3d-cmfd.cpp:520-535 with identical layers); default 1. */
+void set_axial_layers(int n);
 
 /** Replace the UO2/Water data by the synthetic 70-group set of
  *  tests/test_forward_3D_lattice_70g/test_forward_3D_lattice_70g.py:43-61. */

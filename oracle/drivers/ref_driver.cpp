@@ -13,6 +13,7 @@
  *        --solver both: CPUSolver and B200Solver in the same process on the same tracks,
  *        prints delta k_eff (pcm), max relative flux error and both sweep times.
  *                   [--max-iters N] [--threads N] [--res fission|flux|total]
+ *                   [--axial N (c5g7-2d, dims 3: axial layers of the root lattice)]
  *                   [--cmfd NXxNY[xNZ]] [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
  */
 #include <cstdio>
@@ -66,6 +67,7 @@ int main(int argc, char** argv) {
   if (flag(argc, argv, "--quiet")) set_log_level("WARNING");
   else set_log_level("NORMAL");
 
+  set_axial_layers(atoi(arg(argc, argv, "--axial", "1")));
   Model md = build_model(model_name, dims);
   if (flag(argc, argv, "--groups70")) set_70_group_xs(md);
   Geometry* geometry = md.geometry;
