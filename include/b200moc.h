@@ -26,7 +26,8 @@
  * b200_finalize checks it, because the sweep performs all hand-offs concurrently).
  *
  * Tuning knobs read from the environment (defaults are what bench.py measures):
- *   B200_ORDER=natural        keep the Track uid order instead of longest-track-first
+ *   B200_ORDER=natural|sorted Track uid order / longest track first; default: sorted for 2D decks,
+ *                             natural for 3D decks (FSR locality in L2)
  *   B200_PHI_REPLICAS=R       copies of the FSR tally (power of two); default: enough for
  *                             n_fsrs*R >= 16 Ki rows, 1 for large decks
  *   B200_GRAPH=0|1            CUDA-graph replay of the fused iteration off / on; default: on

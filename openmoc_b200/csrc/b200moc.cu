@@ -841,13 +841,21 @@ extern "C" int b200_finalize(b200_solver* s) {
 
   std::vector<int32_t> order(nt);
   std::iota(order.begin(), order.end(), 0);
-  /* Longest tracks first (stable sort): the last wave of CTAs is then made of short tracks
-   * and the tail shrinks (+2 % on 82.8 M segments, more on the 10 M-segment shards of an
-   * 8-GPU run); neighbours in the sorted order are still mostly neighbouring tracks, which
-   * cross the same FSRs.  B200_ORDER=natural keeps the Track uid order. */
+  /* 2D decks: longest tracks first (stable sort): the last wave of CTAs is then made of short tracks
+   * and the tail shrinks (+2 % on 82.8 M segments, more on the 10 M-segment shards of an 8-GPU
+   * run); neighbours in the sorted order are still mostly neighbouring tracks, which cross the
+   * same FSRs.  3D decks keep the Track uid order (azimuthal angle, 2D track, polar angle, position
+   * in the z-stack): the tracks resident on the GPU at any time then belong to a few neighbouring
+   * z-stacks, i.e. a thin slab of the core whose FSR rows stay in L2.  On the 3D C5G7 deck
+   * (3.2 M FSRs, 540 MB of {q, sigma_t} and tally rows) the sorted order moves 292 GB through HBM
+   * per sweep, the uid order 24.5 GB (ncu, profiles/r02_sweep3d.md): 80.7 -> 48.8 ms.
+   * B200_ORDER=natural / sorted overrides. */
   {
     const char* o = getenv("B200_ORDER");
-    if (o == nullptr || strcmp(o, "natural") != 0)
+    bool sorted = !s->cfg.solve_3d;
+    if (o != nullptr && strcmp(o, "natural") == 0) sorted = false;
+    if (o != nullptr && strcmp(o, "sorted") == 0) sorted = true;
+    if (sorted)
       std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
         return (s->h_off[x + 1] - s->h_off[x]) > (s->h_off[y + 1] - s->h_off[y]);
       });
