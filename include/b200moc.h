@@ -247,6 +247,9 @@ int b200_device_pointer(b200_solver* s, const char* name, void** ptr, int64_t* n
  * ranks (integer all-reduce); b200_finish_fixed_tally then converts it into scalar_flux. */
 int b200_defer_fixed_tally(b200_solver* s, int32_t defer);
 int b200_finish_fixed_tally(b200_solver* s);
+/* bracket a stream capture made by the host (CUDA graph of begin -> all-reduce -> end): while set,
+ * no timing events are recorded and nothing synchronises with the host */
+int b200_set_capturing(b200_solver* s, int32_t capturing);
 /* use an externally owned cudaStream_t (passed as void*) for all launches */
 int b200_set_stream(b200_solver* s, void* cuda_stream);
 

@@ -96,6 +96,7 @@ SIGNATURES = {
     "b200_synchronize": [],
     "b200_device_pointer": [C.c_char_p, C.POINTER(_vp), C.POINTER(_i64)],
     "b200_set_stream": [_vp],
+    "b200_set_capturing": [_i32],
     "b200_defer_fixed_tally": [_i32],
     "b200_finish_fixed_tally": [],
 }

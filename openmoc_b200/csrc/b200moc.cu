@@ -1724,7 +1724,7 @@ extern "C" int b200_iteration_begin(b200_solver* s, int32_t iteration) {
 extern "C" int b200_iteration_end(b200_solver* s, int32_t iteration, int32_t res_type, int32_t check_convergence) {
   NEED_FINAL(s);
   if (res_type < 0 || res_type > 2) return fail("b200_iteration_end: unknown residual type %d", res_type);
-  if (check_convergence && s->hist_k.n <= (size_t)iteration)
+  if (check_convergence && iteration >= 0 && s->hist_k.n <= (size_t)iteration)
     return fail("b200_iteration_end: iteration %d beyond the max_iters given to b200_eigen_loop_init", iteration);
   const int64_t n = s->n_fsr * s->G;
   copy_if_done_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->phi.p, s->scratch.p, n, s->iscal.p);
@@ -1915,6 +1915,10 @@ extern "C" int b200_device_pointer(b200_solver* s, const char* name, void** ptr,
   else if (!strcmp(name, "old_scalar_flux")) { *ptr = s->phi_old.p; *n = nphi; }
   else if (!strcmp(name, "reduced_sources")) { *ptr = s->qst.p; *n = 2 * nphi; }
   else if (!strcmp(name, "start_flux")) { *ptr = s->psi_start; *n = s->n_trk * 2 * (int64_t)s->F; }
+  else if (!strcmp(name, "scalar_flux_moments")) {
+    if (!s->linear) return fail("b200_device_pointer: 'scalar_flux_moments' exists for linear-source solvers only");
+    *ptr = s->phi_m.p; *n = 3 * nphi;
+  }
   else if (!strcmp(name, "scalar_flux_fixed")) {
     if (!s->cfg.deterministic) return fail("b200_device_pointer: 'scalar_flux_fixed' exists in deterministic mode only");
     *ptr = s->phi_fx.p; *n = nphi;
@@ -1937,6 +1941,15 @@ extern "C" int b200_finish_fixed_tally(b200_solver* s) {
   fx_to_double_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(fsr_args(s), s->phi_fx.p);
   CU(cudaGetLastError());
   s->n_launches++;
+  return 0;
+}
+
+/* A host that captures its own CUDA graph around the split iteration (begin -> all-reduce -> end,
+ * e.g. torch.cuda.graph with an NCCL all-reduce inside) brackets the capture with this: while set,
+ * the engine records no timing events and issues no host synchronisation. */
+extern "C" int b200_set_capturing(b200_solver* s, int32_t capturing) {
+  NEED(s);
+  s->capturing = capturing != 0;
   return 0;
 }
 

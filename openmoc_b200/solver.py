@@ -56,6 +56,7 @@ class B200Solver:
                                (NCCL send/recv)
     deterministic : bool       accumulate the FSR tally in 64-bit fixed point: results are
                                bitwise reproducible run to run (and across GPU counts)
+    global_tracks : optional   the whole problem's tracks when `tracks` already is one rank's shard
     linear_source : bool       CPULSSolver physics (src/CPULSSolver.cpp): needs a track file dumped
                                after a linear-source initialisation (centroid-relative segment
                                starting points, quadrature factors); the pre-pass tables come from
@@ -64,10 +65,13 @@ class B200Solver:
 
     def __init__(self, tracks: FlatTracks, device: int = 0, precision: int = PRECISION_DOUBLE,
                  process_group=None, use_distributed: Optional[bool] = None, deterministic: bool = False,
-                 partition: str = "pair", linear_source: bool = False):
+                 partition: str = "pair", linear_source: bool = False,
+                 global_tracks: Optional[FlatTracks] = None):
         self._lib = capi.load()
         self._h = C.c_void_p()
-        self._global_tracks = tracks
+        # global_tracks: the full track set when `tracks` already is one rank's shard (the FSR volumes of
+        # on-the-fly 3D tracks and the linear-source pre-pass are sums over ALL tracks)
+        self._global_tracks = global_tracks or tracks
         self._dist = None
         self._plan = None                      # ExchangePlan of partition="track"
         self._psi_views = {}
@@ -84,18 +88,14 @@ class B200Solver:
         self._linear = bool(linear_source)
         self._ls_tables = None
         if self._linear:
-            if self._world > 1:
-                raise B200Error("linear source across several GPUs is not supported in this build "
-                                "(the moment tallies are not all-reduced)")
             if deterministic:
                 raise B200Error("the deterministic tally is not available with the linear source")
             from .linear_source import linear_expansion_tables, track_directions
             if tracks.arrays.get("seg_start", np.zeros(0)).size != 3 * tracks.n_segments:
                 raise B200Error("linear source needs the segment starting points (seg_start) in the track file")
-            lin_exp, src_const, self.num_flat_fsrs = linear_expansion_tables(tracks)
-            self._ls_tables = (np.ascontiguousarray(tracks.arrays["seg_start"], dtype="f8"),
-                               np.ascontiguousarray(track_directions(tracks).ravel(), dtype="f8"),
-                               np.ascontiguousarray(lin_exp), np.ascontiguousarray(src_const))
+            # the pre-pass tables are sums over ALL tracks (replicated); starting points and directions
+            # follow this rank's shard below
+            lin_exp, src_const, self.num_flat_fsrs = linear_expansion_tables(global_tracks or tracks)
         if self._world > 1:
             from .partition import partition_by_azim_pair, partition_by_chain, partition_by_track
             if partition == "chain":
@@ -106,6 +106,10 @@ class B200Solver:
                 tracks, self._plan = partition_by_track(tracks, self._world, only=self._rank)[self._rank]
             else:
                 raise B200Error("unknown partition %r (pair, chain, track)" % partition)
+        if self._linear:
+            self._ls_tables = (np.ascontiguousarray(tracks.arrays["seg_start"], dtype="f8"),
+                               np.ascontiguousarray(track_directions(tracks).ravel(), dtype="f8"),
+                               np.ascontiguousarray(lin_exp), np.ascontiguousarray(src_const))
         self.tracks = tracks
         # a 3D track set without explicit segments: the device traces the z-stacks (b200_upload_tracks_otf)
         self._otf = bool(tracks.solve_3d) and tracks.n_segments == 0 and "seg2d_length" in tracks.arrays
@@ -125,6 +129,9 @@ class B200Solver:
                      precision=precision, deterministic=int(bool(deterministic)), n_fsrs_global=tracks.n_fsrs,
                      linear_source=int(self._linear))
         self._deterministic = bool(deterministic)
+        self._cs = None                        # private torch stream of the multi-GPU loop
+        self._graphs = {}                      # (res_type, check) -> CUDA graph of two split iterations
+        self._mom_tensor = None
         check(self._lib.b200_create(C.byref(cfg), C.byref(self._h)))
         self._upload(tracks)
         if self._deterministic and self._world > 1:
@@ -355,16 +362,21 @@ class B200Solver:
     def useTorchStream(self) -> None:
         """Launch on torch's current CUDA stream (so torch events / NCCL order with us)."""
         import torch
+        if self._cs is not None:
+            return          # the multi-GPU loop owns a private stream, ordered with the caller's on entry / exit
         with torch.cuda.device(self._device):
             check(self._lib.b200_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
     def transportSweep(self) -> None:
         """CPUSolver::transportSweep; with several ranks the per-rank FSR tallies
         are summed here (replaces the MPI path of CPUSolver.cpp:2380-2384)."""
-        check(self._lib.b200_transport_sweep(self._h))
         if self._world > 1:
-            self._allreduce_scalar_flux()
-            self._exchange_boundary_fluxes()
+            with self._on_private_stream():
+                check(self._lib.b200_transport_sweep(self._h))
+                self._allreduce_scalar_flux()
+                self._exchange_boundary_fluxes()
+            return
+        check(self._lib.b200_transport_sweep(self._h))
 
     def _exchange_boundary_fluxes(self) -> None:
         """partition="track": hand the outgoing fluxes whose next track lives on another rank
@@ -384,20 +396,34 @@ class B200Solver:
         with torch.cuda.device(self._device):
             exchange_boundary_fluxes(view, self._plan, self._dist, self._pg)
 
-    def _allreduce_scalar_flux(self) -> None:
+    def _tally_views(self) -> None:
+        """zero-copy torch views of the device tallies the ranks sum"""
         import torch
-        if self._phi_tensor is None:
-            p, n = C.c_void_p(), C.c_int64()
-            # deterministic mode reduces the int64 fixed-point tally: integer sums are exact,
-            # so the answer does not depend on the reduction order or the number of ranks
-            name, typ = (b"scalar_flux_fixed", "<i8") if self._deterministic else (b"scalar_flux", "<f8")
-            check(self._lib.b200_device_pointer(self._h, name, C.byref(p), C.byref(n)))
-            # run the engine on torch's current stream so NCCL is ordered after the sweep
-            self.useTorchStream()
+        if self._phi_tensor is not None:
+            return
+        p, n = C.c_void_p(), C.c_int64()
+        # deterministic mode reduces the int64 fixed-point tally: integer sums are exact,
+        # so the answer does not depend on the reduction order or the number of ranks
+        name, typ = (b"scalar_flux_fixed", "<i8") if self._deterministic else (b"scalar_flux", "<f8")
+        check(self._lib.b200_device_pointer(self._h, name, C.byref(p), C.byref(n)))
+        # run the engine on torch's current stream so NCCL is ordered after the sweep
+        self.useTorchStream()
+        with torch.cuda.device(self._device):
+            self._phi_tensor = torch.as_tensor(_DeviceArray(p.value, n.value, typ),
+                                               device=torch.device("cuda", self._device))
+        if self._linear:
+            # the three flux-moment tallies of the linear source (CPULSSolver.cpp:749-780) are sums over
+            # tracks exactly like the scalar-flux tally
+            check(self._lib.b200_device_pointer(self._h, b"scalar_flux_moments", C.byref(p), C.byref(n)))
             with torch.cuda.device(self._device):
-                self._phi_tensor = torch.as_tensor(_DeviceArray(p.value, n.value, typ),
+                self._mom_tensor = torch.as_tensor(_DeviceArray(p.value, n.value, "<f8"),
                                                    device=torch.device("cuda", self._device))
+
+    def _allreduce_scalar_flux(self) -> None:
+        self._tally_views()
         self._dist.all_reduce(self._phi_tensor, op=self._dist.ReduceOp.SUM, group=self._pg)
+        if self._linear:
+            self._dist.all_reduce(self._mom_tensor, op=self._dist.ReduceOp.SUM, group=self._pg)
         if self._deterministic:
             check(self._lib.b200_finish_fixed_tally(self._h))
 
@@ -427,17 +453,80 @@ class B200Solver:
         done, iters = C.c_int32(0), C.c_int32(0)
         if self._plan is not None:
             poll = 1          # the host moves boundary fluxes every iteration: no no-op iterations
+        use_graph = self._graph_ok() and max_iters > 4
         i = 0
-        while i < max_iters and not done.value:
-            end = min(max_iters, i + poll)
-            while i < end:
-                check(L.b200_iteration_begin(h, i))
-                self._allreduce_scalar_flux()
-                self._exchange_boundary_fluxes()
-                check(L.b200_iteration_end(h, i, int(res_type), 1))
-                i += 1
-            check(L.b200_eigen_loop_status(h, i, C.byref(done), C.byref(iters), None, None))
+        with self._on_private_stream():
+            while i < max_iters and not done.value:
+                end = min(max_iters, i + poll)
+                if use_graph and i >= 2:
+                    # iterations 0 and 1 ran as plain launches (communicators, allocations, iteration 0
+                    # of the stabilisation); from here on two split iterations per graph replay
+                    g = self._split_iteration_graph(int(res_type), 1)
+                    while i + 2 <= end:
+                        g.replay()
+                        i += 2
+                while i < end:
+                    check(L.b200_iteration_begin(h, i))
+                    self._allreduce_scalar_flux()
+                    self._exchange_boundary_fluxes()
+                    check(L.b200_iteration_end(h, i, int(res_type), 1))
+                    i += 1
+                check(L.b200_eigen_loop_status(h, i, C.byref(done), C.byref(iters), None, None))
         return iters.value
+
+    # ---------------------------------------------------- CUDA graph of the split iteration
+    def _graph_ok(self) -> bool:
+        """One CUDA graph holds sources -> sweep -> NCCL all-reduce -> closure ... residual of two
+        iterations (one per parity of the psi double buffer): no launch gaps, no Python between
+        the kernels.  Not with the host-orchestrated boundary-flux exchange of partition="track"."""
+        import os
+        return self._world > 1 and self._plan is None and os.environ.get("B200_DIST_GRAPH", "1") != "0"
+
+    def _on_private_stream(self):
+        """Everything of the multi-GPU loop (engine kernels and NCCL) runs on one private torch
+        stream, ordered after / before the caller's current stream on entry / exit."""
+        import contextlib
+        import torch
+        if self._world == 1 or self._dist is None or not torch.cuda.is_available():
+            return contextlib.nullcontext()
+        solver = self
+
+        @contextlib.contextmanager
+        def ctx():
+            with torch.cuda.device(solver._device):
+                if solver._cs is None:
+                    solver._cs = torch.cuda.Stream()
+                    with torch.cuda.stream(solver._cs):
+                        check(solver._lib.b200_set_stream(solver._h, C.c_void_p(solver._cs.cuda_stream)))
+                outer = torch.cuda.current_stream()
+                solver._cs.wait_stream(outer)
+                with torch.cuda.stream(solver._cs):
+                    yield
+                outer.wait_stream(solver._cs)
+        return ctx()
+
+    def _split_iteration_graph(self, res_type: int, check_convergence: int):
+        import torch
+        key = (res_type, check_convergence)
+        g = self._graphs.get(key)
+        if g is not None:
+            return g
+        L, h = self._lib, self._h
+        self._tally_views()
+        g = torch.cuda.CUDAGraph()
+        check(L.b200_set_capturing(h, 1))
+        try:
+            with torch.cuda.graph(g, stream=self._cs):
+                for _ in range(2):
+                    check(L.b200_iteration_begin(h, -1))
+                    self._allreduce_scalar_flux()
+                    check(L.b200_iteration_end(h, -1, res_type, check_convergence))
+        finally:
+            check(L.b200_set_capturing(h, 0))
+        self._graphs[key] = g
+        return g
+
+
 
     def _eigenvalue_loop(self, max_iters: int, res_type: int) -> int:
         """The same loop driven step by step from the host through the Solver virtuals."""
@@ -501,11 +590,23 @@ class B200Solver:
     def iterate(self, n: int, res_type: int = FISSION_SOURCE):
         """n fused source iterations without convergence test (benchmark hook)."""
         if self._world > 1:
-            for i in range(n):
-                check(self._lib.b200_iteration_begin(self._h, 1000 + i))
-                self._allreduce_scalar_flux()
-                self._exchange_boundary_fluxes()
-                check(self._lib.b200_iteration_end(self._h, 1000 + i, int(res_type), 0))
+            with self._on_private_stream():
+                i = 0
+                if self._graph_ok() and n >= 4:
+                    for i in range(2):          # plain launches first: communicators, lazy allocations
+                        check(self._lib.b200_iteration_begin(self._h, 1000 + i))
+                        self._allreduce_scalar_flux()
+                        check(self._lib.b200_iteration_end(self._h, 1000 + i, int(res_type), 0))
+                    i = 2
+                    g = self._split_iteration_graph(int(res_type), 0)
+                    while i + 2 <= n:
+                        g.replay()
+                        i += 2
+                for i in range(i, n):
+                    check(self._lib.b200_iteration_begin(self._h, 1000 + i))
+                    self._allreduce_scalar_flux()
+                    self._exchange_boundary_fluxes()
+                    check(self._lib.b200_iteration_end(self._h, 1000 + i, int(res_type), 0))
             return
         check(self._lib.b200_iterate(self._h, int(n), int(res_type), None, None))
 

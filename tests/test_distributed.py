@@ -167,3 +167,109 @@ def test_nccl_world2_matches_single_gpu(tmp_path, partition):
         assert int(iters) == one.getNumIterations()
         assert abs(k - one.getKeff()) * 1e5 < 1e-3
         np.testing.assert_allclose(phi, one.getFluxes(), rtol=1e-7)
+
+
+# ------------------------------------------- one process, several shards on ONE GPU
+def _simulated_ranks(ft, world, max_iters=400, tol=1e-5, deterministic=False, linear=False):
+    """The multi-GPU loop with every rank's solver living on cuda:0 of this process and the
+    all-reduce done by hand (sum of the ranks' device tallies, written back to every rank): the
+    same b200_iteration_begin -> reduce -> b200_iteration_end sequence B200Solver drives over NCCL,
+    runnable on a single-GPU lease."""
+    import ctypes as C
+    from openmoc_b200.solver import B200Solver, _DeviceArray
+    from openmoc_b200.capi import FISSION_SOURCE, check
+    from openmoc_b200.partition import partition_by_chain
+    parts = partition_by_chain(ft, world)
+    solvers = [B200Solver(p, deterministic=deterministic, linear_source=linear,
+                          global_tracks=ft) for p in parts]
+    L = solvers[0]._lib
+    views = []
+    for s in solvers:
+        s.useTorchStream()
+        if deterministic:
+            check(L.b200_defer_fixed_tally(s._h, 1))
+        v = []
+        names = [(b"scalar_flux_fixed", "<i8")] if deterministic else [(b"scalar_flux", "<f8")]
+        if linear:
+            names.append((b"scalar_flux_moments", "<f8"))
+        for name, typ in names:
+            p, n = C.c_void_p(), C.c_int64()
+            check(L.b200_device_pointer(s._h, name, C.byref(p), C.byref(n)))
+            v.append(torch.as_tensor(_DeviceArray(p.value, n.value, typ), device="cuda:0"))
+        views.append(v)
+        check(L.b200_eigen_loop_init(s._h, max_iters, tol))
+    done, iters = C.c_int32(0), C.c_int32(0)
+    i = 0
+    while i < max_iters and not done.value:
+        for s in solvers:
+            check(L.b200_iteration_begin(s._h, i))
+        for k in range(len(views[0])):
+            total = views[0][k].clone()
+            for r in range(1, world):
+                total += views[r][k]
+            for r in range(world):
+                views[r][k].copy_(total)
+        for s in solvers:
+            if deterministic:
+                check(L.b200_finish_fixed_tally(s._h))
+            check(L.b200_iteration_end(s._h, i, FISSION_SOURCE, 1))
+        i += 1
+        for s in solvers:
+            check(L.b200_eigen_loop_status(s._h, i, C.byref(done), C.byref(iters), None, None))
+    return solvers, iters.value
+
+
+@pytest.mark.gpu
+def test_simulated_ranks_deterministic_tally_is_bitwise_equal_to_one_gpu():
+    """The fixed-point scale derives from replicated quantities only, so 1, 2 and 3 ranks sum the
+    same integers: fluxes and k_eff bit-identical (the scale used to follow each rank's
+    own max |psi|)."""
+    from openmoc_b200.solver import B200Solver
+    from openmoc_b200.capi import FISSION_SOURCE
+    ft = _tracks()
+    one = B200Solver(ft, deterministic=True)
+    one.setConvergenceThreshold(1e-5)
+    one.computeEigenvalue(400, FISSION_SOURCE)
+    for world in (2, 3):
+        solvers, iters = _simulated_ranks(ft, world, deterministic=True)
+        assert iters == one.getNumIterations()
+        for s in solvers:
+            assert s.getKeff() == one.getKeff()
+            assert np.array_equal(s.getFluxes(), one.getFluxes())
+
+
+@pytest.mark.gpu
+def test_simulated_ranks_linear_source_matches_one_gpu():
+    """linear source across ranks: the moment tallies are reduced like the scalar flux"""
+    from openmoc_b200.solver import B200Solver
+    from openmoc_b200.capi import FISSION_SOURCE
+    from openmoc_b200.synth import make_tracks
+    ft = make_tracks("simple-lattice", num_azim=8, spacing=0.1, linear_source=True)
+    one = B200Solver(ft, linear_source=True)
+    one.setConvergenceThreshold(1e-5)
+    one.computeEigenvalue(400, FISSION_SOURCE)
+    solvers, iters = _simulated_ranks(ft, 2, linear=True)
+    assert iters == one.getNumIterations()
+    for s in solvers:
+        assert abs(s.getKeff() - one.getKeff()) * 1e5 < 1e-4
+        np.testing.assert_allclose(s.getFluxes(), one.getFluxes(), rtol=1e-8)
+        np.testing.assert_allclose(s.getFluxMoments(), one.getFluxMoments(), rtol=1e-6, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_simulated_ranks_3d_on_the_fly_tracks():
+    """3D deck, device-side axial tracing, chains sharded over 3 ranks: volumes from all tracks,
+    segments from each rank's shard"""
+    from openmoc_b200.solver import B200Solver
+    from openmoc_b200.capi import FISSION_SOURCE
+    from openmoc_b200.synth import make_tracks_3d
+    ft = make_tracks_3d("simple-lattice", num_azim=4, spacing=0.24, num_polar=2, z_spacing=0.9, n_axial=2, expand=False)
+    one = B200Solver(ft)
+    one.setConvergenceThreshold(1e-5)
+    one.computeEigenvalue(500, FISSION_SOURCE)
+    solvers, iters = _simulated_ranks(ft, 3, max_iters=500)
+    assert iters == one.getNumIterations()
+    assert sum(s.num_segments for s in solvers) == one.num_segments
+    for s in solvers:
+        assert abs(s.getKeff() - one.getKeff()) * 1e5 < 1e-4
+        np.testing.assert_allclose(s.getFluxes(), one.getFluxes(), rtol=1e-8)

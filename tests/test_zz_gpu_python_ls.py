@@ -1,12 +1,10 @@
 """Linear source through the Python mirror (B200Solver(linear_source=True)) against the LS oracle and
 the reference's LS goldens; the reference's compute_flux / compute_source goldens from the GPU.
 
-Written after the round's GPU budget was spent.  The device kernels behind it are the ones the C++
-plug-in tests exercise (tests/test_gpu_plugin.py) and the pre-pass tables are checked on the CPU
-(tests/test_host_logic.py), but this ctypes path itself has not run on hardware yet.  Hence:
-  * xfail(strict=False): a pass shows up as XPASS, a failure does not break the suite;
-  * the GPU work runs in a child process, so that a fault could not leave a poisoned CUDA context
-    behind for other tests (the file name sorts last for the same reason).
+The device kernels behind it are the ones the C++ plug-in tests exercise (tests/test_gpu_plugin.py) and
+the pre-pass tables are checked on the CPU (tests/test_host_logic.py).  Green on the B200 since round 1
+(GPUTEST_r01: 7 xpassed); the xfail marks of round 1 are gone, a regression now fails the suite.  The GPU
+work still runs in a child process so that a fault cannot leave a poisoned CUDA context behind.
 """
 import json
 import os
@@ -44,7 +42,6 @@ print("RESULT " + json.dumps({
 """
 
 
-@pytest.mark.xfail(reason="not yet run on hardware (added after the GPU budget was spent)", strict=False)
 @pytest.mark.parametrize("name,tol,golden", [("simple_lattice_ls", 1e-5, None),
                                              ("lattice3d_ls_70g", 5e-3, "test_forward_3D_lattice_linear_70g"),
                                              ("lattice3d_ls_7g", 1e-5, None)])
@@ -90,7 +87,6 @@ print("RESULT " + json.dumps({"flux": flux, "source": source}))
 """
 
 
-@pytest.mark.xfail(reason="not yet run on hardware (added after the GPU budget was spent)", strict=False)
 def test_compute_flux_and_source_goldens_from_gpu():
     """tests/test_compute_flux and tests/test_compute_source results_true.dat, byte for byte from the GPU"""
     out = subprocess.run([sys.executable, "-c", CHILD_FIXED % {"root": ROOT}], capture_output=True, text=True, timeout=180)
@@ -125,7 +121,6 @@ print("RESULT " + json.dumps(res))
 """
 
 
-@pytest.mark.xfail(reason="not yet run on hardware (added after the GPU budget was spent)", strict=False)
 def test_adjoint_goldens_from_gpu():
     """tests/test_adjoint_{pin_cell,simple_lattice,hom_inf_medium}/results_true.dat from the GPU"""
     out = subprocess.run([sys.executable, "-c", CHILD_ADJOINT % {"root": ROOT}], capture_output=True, text=True, timeout=180)
@@ -154,7 +149,6 @@ print("RESULT " + json.dumps({"out": format_harness_results(s.getNumIterations()
 """
 
 
-@pytest.mark.xfail(reason="not yet run on hardware (added after the GPU budget was spent)", strict=False)
 def test_pin_cell_70g_golden_from_gpu():
     """tests/test_forward_pin_cell_70g/results_true.dat (8 iterations, SCALAR_FLUX residual) from the GPU"""
     out = subprocess.run([sys.executable, "-c", CHILD_70G % {"root": ROOT}], capture_output=True, text=True, timeout=180)
@@ -183,7 +177,6 @@ print("RESULT " + json.dumps(res))
 """
 
 
-@pytest.mark.xfail(reason="not yet run on hardware (added after the GPU budget was spent)", strict=False)
 def test_vacuum_gradient_goldens_from_gpu():
     out = subprocess.run([sys.executable, "-c", CHILD_GRADIENT % {"root": ROOT}], capture_output=True, text=True, timeout=180)
     assert out.returncode == 0, out.stderr[-2000:]
