@@ -79,6 +79,21 @@ int b200_device_count(void);
 int b200_create(const b200_config* cfg, b200_solver** out);
 int b200_destroy(b200_solver* s);
 
+/* ---- several GPUs behind one handle ----
+ * Call right after b200_create (cfg.device is then only the device the host talks to first).  The
+ * uploads are parked on the host; b200_finalize shards the tracks by whole chains (connected components
+ * of the boundary hand-off graph: no angular flux ever crosses a shard), balanced by segment count, and
+ * builds one solver per entry of `devices` (a device may appear twice: two shards on one GPU) with
+ * replicated FSR / material / quadrature data.  Every other entry point then acts on the group: FSR
+ * steps run replicated and stay bit-identical, the transport sweep runs on every shard and the shards'
+ * tallies (scalar flux, flux moments, CMFD currents, fixed-point tally) are summed by the library's own
+ * two-shot all-reduce kernels over peer memory (NVLink P2P loads, CUDA events between the shards'
+ * streams; no NCCL, no host copies).  Replaces the MPI reductions and interface exchange of
+ * src/CPUSolver.cpp:545-1211, 1900, 2224, 2317 for tracks that are decomposed by chain.
+ * Not available on a group: k_eff from the neutron balance, b200_set_stream, b200_get_segments. */
+int b200_set_devices(b200_solver* s, int32_t n_devices, const int32_t* devices);
+int b200_get_num_devices(b200_solver* s, int32_t* n_devices);
+
 /* replaces GPUSolver::initializeTracks + clone_track (GPUSolver.cu:1312-1353,
  * clone.cu:86-126): one SoA upload instead of one cudaMalloc per track. */
 int b200_upload_tracks(b200_solver* s,
@@ -152,6 +167,11 @@ int b200_upload_tracks_otf(b200_solver* s, const int32_t* trk_2d, const double* 
                            const uint8_t* trk_flags, const uint8_t* trk_bc_fwd, const uint8_t* trk_bc_bwd,
                            int64_t* n_segments);
 int b200_get_num_segments(b200_solver* s, int64_t* n_segments);
+/* number of 3D segments of arbitrary tracks over the uploaded geometry: the work estimate a host
+ * needs to balance a partition of on-the-fly tracks */
+int b200_otf_count_segments(b200_solver* s, int64_t n_tracks, const int32_t* trk_2d, const double* trk_l0,
+                            const double* trk_z0, const int32_t* trk_azim, const int32_t* trk_polar,
+                            int32_t* counts);
 /* host copies of the device segment stream (tests, track dumps); trk_seg_offset may be NULL */
 int b200_get_segments(b200_solver* s, double* seg_length, int32_t* seg_fsr, int64_t n_segments,
                       int64_t* trk_seg_offset);

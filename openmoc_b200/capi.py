@@ -53,6 +53,9 @@ SIGNATURES = {
     "b200_get_num_segments": [C.POINTER(_i64)],
     "b200_get_segments": [_vp, _vp, _i64, _vp],
     "b200_get_volumes": [_vp, _i64],
+    "b200_otf_count_segments": [_i64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "b200_set_devices": [_i32, _vp],
+    "b200_get_num_devices": [C.POINTER(_i32)],
     "b200_finalize": [],
     "b200_zero_track_fluxes": [],
     "b200_flatten_fsr_fluxes": [_dbl],

@@ -42,6 +42,7 @@ protected:
   bool _cmfd_active, _host_flux_newer;
   std::vector<double> _cmfd_currents;
   int _device, _precision;
+  std::vector<int> _devices;       /* more than one entry: one handle drives them all (b200_set_devices) */
   double _device_keff;
 
   void check(int status, const char* what);
@@ -113,6 +114,22 @@ public:
     if (num_threads <= 0)
       log_printf(ERROR, "Unable to set the number of threads to %d since it is less than or equal to 0", num_threads);
     omp_set_num_threads(num_threads);
+  }
+  /** Several GPUs behind this solver: the tracks are sharded by chain inside the library, FSR steps run
+   *  replicated, the tallies (scalar flux, LS moments, CMFD currents) are summed over NVLink peer memory
+   *  by the library's own all-reduce kernels (include/b200moc.h: b200_set_devices).  The role of the
+   *  reference's MPI decomposition (Geometry::setDomainDecomposition + CPUSolver.cpp:545-1211) on one
+   *  multi-GPU node; CMFD and the linear source work unchanged.  Call before the first compute*(). */
+  void setNumDevices(int n) {
+    if (n < 1) log_printf(ERROR, "Unable to use %d devices", n);
+    std::vector<int> d(n);
+    for (int i = 0; i < n; i++) d[i] = _device + i;
+    setDevices(d);
+  }
+  /** Explicit device list (a device may repeat: several shards on one GPU). */
+  void setDevices(const std::vector<int>& devices) {
+    _devices = devices;
+    if (_h != NULL) { b200_destroy(_h); _h = NULL; }      /* the device image is rebuilt on the next solve */
   }
   /** Copy phi, old phi and q from the device into the base-class host arrays. */
   void syncHostMirrors();
@@ -190,6 +207,8 @@ void B200SolverT<Base>::ensureDevice() {
   cfg.precision = _precision;
   cfg.linear_source = isLinearSource() ? 1 : 0;
   check(b200_create(&cfg, &_h), "b200_create");
+  if (_devices.size() > 1 || (_devices.size() == 1 && _devices[0] != _device))
+    check(b200_set_devices(_h, (int)_devices.size(), _devices.data()), "b200_set_devices");
   check(b200_upload_tracks(_h, _flat.seg_length.data(), _flat.seg_fsr.data(), _flat.trk_seg_offset.data(),
                            _flat.trk_azim.data(), _flat.trk_polar.data(), _flat.trk_next_fwd.data(),
                            _flat.trk_next_bwd.data(), _flat.trk_flags.data(), _flat.trk_bc_fwd.data(),

@@ -25,6 +25,7 @@
 #include "sweep_ls.cuh"
 #include "otf.cuh"
 #include "microbench.cuh"
+#include "group.cuh"
 
 using namespace b200;
 
@@ -182,7 +183,77 @@ struct b200_solver {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
   double sweep_ms = 0.;
   int64_t n_sweeps = 0, n_launches = 0;
+  /* several devices behind this handle (group.cuh): the handle itself then owns no device state */
+  struct b200_group* grp = nullptr;
 };
+typedef struct b200_group b200_group;
+
+/* ------------------------------------------------------------------------- */
+/* uploads are parked on the host until b200_finalize shards them             */
+/* ------------------------------------------------------------------------- */
+struct b200_group {
+  std::vector<int> devices;
+  std::vector<b200_solver*> shard;
+  std::vector<std::vector<int64_t>> ids;          /* global track ids of every shard, ascending */
+  /* explicit tracks */
+  bool have_explicit = false, have_otf = false;
+  std::vector<double> seg_length;
+  std::vector<int32_t> seg_fsr;
+  std::vector<int64_t> trk_off, next_fwd, next_bwd;
+  std::vector<int32_t> trk_azim, trk_polar;
+  std::vector<uint8_t> flags, bc_fwd, bc_bwd;
+  /* axial on-the-fly tracks */
+  bool have_geo = false;
+  int64_t n_trk2d = 0, n_seg2d = 0, n_ext = 0;
+  int32_t n_axial = 0;
+  std::vector<double> seg2d_len, ext_mesh, theta, trk_l0, trk_z0;
+  std::vector<int32_t> seg2d_ext, ext_fsr, trk_2d;
+  std::vector<int64_t> trk2d_off, ext_off;
+  /* volume tracks of b200_otf_compute_volumes */
+  bool have_voltrk = false;
+  std::vector<int32_t> v_2d, v_azim, v_polar;
+  std::vector<double> v_l0, v_z0, v_weight;
+  /* replicated tables */
+  std::vector<double> weight, sin_theta, volume, sigma_t, sigma_s, fiss, nu_sigma_f, sigma_f, chi;
+  bool have_volume = false, have_sigma_f = false;
+  std::vector<int32_t> fsr_mat;
+  std::vector<uint8_t> fissionable;
+  /* linear source */
+  bool have_ls = false;
+  std::vector<double> seg_start, trk_dir, lin_exp, src_const;
+  /* CMFD */
+  bool have_cmfd = false;
+  std::vector<int32_t> cmfd_fwd, cmfd_bwd;
+  /* all-reduce plumbing */
+  std::vector<cudaEvent_t> ev_a, ev_b;
+  std::vector<DevBuf<double>> stage;
+  int64_t n_reduces = 0;
+};
+
+/* multi-device groups (group_impl.cuh, included at the end of this file) */
+static std::vector<b200_solver*>& grp_shards(b200_solver* s);
+static int grp_finalize(b200_solver* s);
+static int grp_sweep(b200_solver* s);
+static int grp_iteration(b200_solver* s, int i, int res_type, int loop_kind);
+static int grp_sync(b200_solver* s);
+static void grp_destroy(b200_solver* s);
+static int grp_get_start_fluxes(b200_solver* s, float* out, int64_t n);
+static int grp_set_start_fluxes(b200_solver* s, const float* in, int64_t n);
+static int grp_compute_eigenvalue(b200_solver* s, int max_iters, double tol, int res_type, int32_t* num_iterations);
+static int grp_flux_source_loop(b200_solver* s, int max_iters, double tol, int res_type, bool sources_each_iter,
+                                int32_t* num_iterations);
+/* forward a call to every shard (replicated state) / to the first one (getters); `c` names the shard */
+#define GRP_ALL(s, expr)                                              \
+  do {                                                                \
+    if ((s)->grp != nullptr) {                                        \
+      for (b200_solver* c : grp_shards(s)) { if (expr) return 1; }    \
+      return 0;                                                       \
+    }                                                                 \
+  } while (0)
+#define GRP_FIRST(s, expr)                                            \
+  do {                                                                \
+    if ((s)->grp != nullptr) { b200_solver* c = grp_shards(s)[0]; return (expr); } \
+  } while (0)
 
 static FsrArgs fsr_args(b200_solver* s) {
   FsrArgs a;
@@ -319,6 +390,7 @@ extern "C" int b200_create(const b200_config* cfg, b200_solver** out) {
 
 extern "C" int b200_destroy(b200_solver* s) {
   if (s == nullptr) return 0;
+  if (s->grp != nullptr) grp_destroy(s);
   cudaSetDevice(s->cfg.device);
   cudaStreamSynchronize(s->stream);
   if (s->iter_graph != nullptr) cudaGraphExecDestroy(s->iter_graph);
@@ -380,6 +452,17 @@ extern "C" int b200_upload_tracks(b200_solver* s, const double* seg_length, cons
   for (int64_t i = 0; i < ns; i++)
     if (seg_fsr[i] < 0 || seg_fsr[i] >= s->n_fsr)
       return fail("b200_upload_tracks: segment %lld FSR id %d outside [0,%lld)", (long long)i, seg_fsr[i], (long long)s->n_fsr);
+  if (s->grp != nullptr) {
+    b200_group* g = s->grp;
+    g->seg_length.assign(seg_length, seg_length + ns); g->seg_fsr.assign(seg_fsr, seg_fsr + ns);
+    g->trk_off.assign(trk_seg_offset, trk_seg_offset + nt + 1);
+    g->trk_azim.assign(trk_azim, trk_azim + nt); g->trk_polar.assign(trk_polar, trk_polar + nt);
+    g->next_fwd.assign(trk_next_fwd, trk_next_fwd + nt); g->next_bwd.assign(trk_next_bwd, trk_next_bwd + nt);
+    g->flags.assign(trk_flags, trk_flags + nt); g->bc_fwd.assign(trk_bc_fwd, trk_bc_fwd + nt); g->bc_bwd.assign(trk_bc_bwd, trk_bc_bwd + nt);
+    g->have_explicit = true; g->have_otf = false;
+    s->have_tracks = true; s->finalized = false;
+    return 0;
+  }
   s->seg_rec_ready = false;
   s->otf = false;
   CU(s->seg_len.upload(seg_length, ns, s->stream));
@@ -408,6 +491,7 @@ extern "C" int b200_upload_quadrature(b200_solver* s, const double* weight, cons
       return fail("b200_upload_quadrature: sin_theta[%zu]=%g outside (0,1]", i, sin_theta[i]);
   s->h_weight.assign(weight, weight + n);
   s->h_sin.assign(sin_theta, sin_theta + n);
+  if (s->grp != nullptr) { s->grp->weight = s->h_weight; s->grp->sin_theta = s->h_sin; }
   s->have_quad = true;
   s->finalized = false;
   return 0;
@@ -421,6 +505,14 @@ extern "C" int b200_upload_fsrs(b200_solver* s, const double* volume, const int3
   for (int64_t r = 0; r < s->n_fsr; r++)
     if (fsr_material[r] < 0 || fsr_material[r] >= s->n_mat)
       return fail("b200_upload_fsrs: FSR %lld material %d outside [0,%d)", (long long)r, fsr_material[r], s->n_mat);
+  if (s->grp != nullptr) {
+    b200_group* g = s->grp;
+    if (volume) { g->volume.assign(volume, volume + s->n_fsr); g->have_volume = true; }
+    g->fsr_mat.assign(fsr_material, fsr_material + s->n_fsr);
+    s->h_fsr_mat = g->fsr_mat;
+    s->have_fsrs = true; s->finalized = false;
+    return 0;
+  }
   if (volume) { CU(s->vol.upload(volume, s->n_fsr, s->stream)); s->volumes_from_tracer = false; }
   CU(s->fsr_mat.upload(fsr_material, s->n_fsr, s->stream));
   s->h_fsr_mat.assign(fsr_material, fsr_material + s->n_fsr);
@@ -441,6 +533,22 @@ extern "C" int b200_upload_materials(b200_solver* s, const double* sigma_t, cons
   for (size_t i = 0; i < nG; i++)
     if (!(sigma_t[i] > 0.0))
       return fail("b200_upload_materials: sigma_t[%zu]=%g must be positive", i, sigma_t[i]);
+  if (s->grp != nullptr) {
+    b200_group* g = s->grp;
+    if (s->finalized) {          /* refresh (adjoint <-> forward): straight to the shards */
+      for (b200_solver* c : grp_shards(s))
+        if (b200_upload_materials(c, sigma_t, sigma_s, fiss_matrix, nu_sigma_f, sigma_f, chi, fissionable)) return 1;
+      s->n_fissionable = grp_shards(s)[0]->n_fissionable;
+      return 0;
+    }
+    g->sigma_t.assign(sigma_t, sigma_t + nG); g->sigma_s.assign(sigma_s, sigma_s + nGG); g->fiss.assign(fiss_matrix, fiss_matrix + nGG);
+    g->nu_sigma_f.assign(nu_sigma_f, nu_sigma_f + nG); g->chi.assign(chi, chi + nG);
+    g->fissionable.assign(fissionable, fissionable + s->n_mat);
+    g->have_sigma_f = sigma_f != nullptr;
+    if (sigma_f) g->sigma_f.assign(sigma_f, sigma_f + nG);
+    s->have_mats = true;
+    return 0;
+  }
   /* sigma_f is optional (only computeFSRFissionRates(nu = false) reads it): NULL keeps a table
    * uploaded earlier - material refreshes (adjoint <-> forward) do not touch it - else zeros */
   std::vector<double> zeros;
@@ -481,6 +589,15 @@ extern "C" int b200_upload_linear_source(b200_solver* s, const double* seg_start
   if (!s->linear) return fail("b200_upload_linear_source: the solver was not created with linear_source = 1");
   if (!trk_direction || !lin_exp_matrix || !source_constants || (s->n_seg > 0 && !seg_start))
     return fail("b200_upload_linear_source: null array");
+  if (s->grp != nullptr) {
+    b200_group* g = s->grp;
+    g->seg_start.assign(seg_start, seg_start + (size_t)s->n_seg * 3);
+    g->trk_dir.assign(trk_direction, trk_direction + (size_t)s->n_trk * 3);
+    g->lin_exp.assign(lin_exp_matrix, lin_exp_matrix + (size_t)s->n_fsr * s->nc);
+    g->src_const.assign(source_constants, source_constants + (size_t)s->n_fsr * s->nc * s->G);
+    g->have_ls = true; s->have_ls = true; s->finalized = false;
+    return 0;
+  }
   CU(s->ls_seg_start.upload(seg_start, (size_t)s->n_seg * 3, s->stream));
   CU(s->ls_trk_dir.upload(trk_direction, (size_t)s->n_trk * 3, s->stream));
   CU(s->ls_lin_exp.upload(lin_exp_matrix, (size_t)s->n_fsr * s->nc, s->stream));
@@ -494,6 +611,12 @@ extern "C" int b200_upload_linear_source(b200_solver* s, const double* seg_start
 extern "C" int b200_upload_cmfd_surfaces(b200_solver* s, const int32_t* seg_cmfd_fwd, const int32_t* seg_cmfd_bwd) {
   NEED(s);
   if (s->n_seg > 0 && (!seg_cmfd_fwd || !seg_cmfd_bwd)) return fail("b200_upload_cmfd_surfaces: null array");
+  if (s->grp != nullptr) {
+    s->grp->cmfd_fwd.assign(seg_cmfd_fwd, seg_cmfd_fwd + s->n_seg);
+    s->grp->cmfd_bwd.assign(seg_cmfd_bwd, seg_cmfd_bwd + s->n_seg);
+    s->grp->have_cmfd = true; s->have_cmfd_surf = true;
+    return 0;
+  }
   CU(s->cmfd_fwd.upload(seg_cmfd_fwd, s->n_seg, s->stream));
   CU(s->cmfd_bwd.upload(seg_cmfd_bwd, s->n_seg, s->stream));
   CU(s->seg_cmfd.alloc((size_t)s->n_seg + 2 * SEG_PAD));
@@ -509,6 +632,13 @@ extern "C" int b200_upload_cmfd_surfaces(b200_solver* s, const int32_t* seg_cmfd
 extern "C" int b200_set_cmfd_groups(b200_solver* s, const int32_t* moc_to_cmfd_group, int32_t num_cmfd_groups,
                                     int64_t num_cmfd_cells) {
   NEED(s);
+  if (s->grp != nullptr) {
+    if (!s->finalized) return fail("b200_set_cmfd_groups: call b200_finalize first on a multi-device solver");
+    for (b200_solver* c : grp_shards(s))
+      if (b200_set_cmfd_groups(c, moc_to_cmfd_group, num_cmfd_groups, num_cmfd_cells)) return 1;
+    s->cmfd_on = grp_shards(s)[0]->cmfd_on; s->ncg = grp_shards(s)[0]->ncg; s->n_cmfd_slots = grp_shards(s)[0]->n_cmfd_slots;
+    return 0;
+  }
   if (num_cmfd_groups <= 0) { s->cmfd_on = false; return 0; }      /* switches the tally off */
   if (!s->have_cmfd_surf) return fail("b200_set_cmfd_groups: b200_upload_cmfd_surfaces has not been called");
   if (!moc_to_cmfd_group || num_cmfd_cells <= 0) return fail("b200_set_cmfd_groups: bad argument");
@@ -527,6 +657,7 @@ extern "C" int b200_set_cmfd_groups(b200_solver* s, const int32_t* moc_to_cmfd_g
 
 extern "C" int b200_get_cmfd_currents(b200_solver* s, double* out, int64_t n) {
   NEED(s);
+  GRP_FIRST(s, b200_get_cmfd_currents(c, out, n));
   if (!s->cmfd_on) return fail("b200_get_cmfd_currents: CMFD tallies are off");
   if (n != s->n_cmfd_slots * s->ncg) return fail("b200_get_cmfd_currents: expected %lld values", (long long)(s->n_cmfd_slots * s->ncg));
   CU(cudaMemcpyAsync(out, s->currents.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
@@ -560,6 +691,28 @@ extern "C" int b200_upload_otf_geometry(b200_solver* s, int64_t n_tracks_2d, int
     return fail("b200_upload_otf_geometry: null or empty argument");
   if (trk2d_seg_offset[0] != 0 || trk2d_seg_offset[n_tracks_2d] != n_segments_2d)
     return fail("b200_upload_otf_geometry: trk2d_seg_offset must run from 0 to n_segments_2d");
+  if (s->grp != nullptr) {
+    b200_group* g = s->grp;
+    const bool glob = n_extruded_fsrs <= 0;
+    if (glob && n_axial_global < 1) return fail("b200_upload_otf_geometry: a global axial mesh needs n_axial_global >= 1");
+    if (!glob && (!ext_offset || !ext_fsr_ids)) return fail("b200_upload_otf_geometry: per-FSR axial meshes need ext_offset and ext_fsr_ids");
+    g->n_trk2d = n_tracks_2d; g->n_seg2d = n_segments_2d; g->n_ext = glob ? 0 : n_extruded_fsrs; g->n_axial = glob ? n_axial_global : 0;
+    g->seg2d_len.assign(seg2d_length, seg2d_length + n_segments_2d);
+    g->seg2d_ext.assign(seg2d_extruded_fsr, seg2d_extruded_fsr + n_segments_2d);
+    g->trk2d_off.assign(trk2d_seg_offset, trk2d_seg_offset + n_tracks_2d + 1);
+    if (glob) {
+      g->ext_mesh.assign(ext_mesh, ext_mesh + n_axial_global + 1);
+    } else {
+      const int64_t ntot = ext_offset[n_extruded_fsrs];
+      g->ext_off.assign(ext_offset, ext_offset + n_extruded_fsrs + 1);
+      g->ext_mesh.assign(ext_mesh, ext_mesh + ntot + n_extruded_fsrs);
+      g->ext_fsr.assign(ext_fsr_ids, ext_fsr_ids + ntot);
+    }
+    g->theta.assign(theta, theta + (size_t)s->A2 * s->cfg.num_polar);
+    g->have_geo = true;
+    s->otf_n_trk2d = n_tracks_2d;
+    return 0;            /* validated when the shards upload it */
+  }
   const bool global = n_extruded_fsrs <= 0;
   int64_t n_ext_seen = 0;
   for (int64_t i = 0; i < n_segments_2d; i++) {
@@ -642,6 +795,15 @@ extern "C" int b200_otf_compute_volumes(b200_solver* s, int64_t n, const int32_t
   if (s->otf_n_trk2d == 0) return fail("b200_otf_compute_volumes: b200_upload_otf_geometry has not been called");
   if (n < 0 || (n > 0 && (!trk_2d || !trk_l0 || !trk_z0 || !trk_azim || !trk_polar)) || !class_weight)
     return fail("b200_otf_compute_volumes: null argument");
+  if (s->grp != nullptr) {
+    b200_group* g = s->grp;
+    g->v_2d.assign(trk_2d, trk_2d + n); g->v_l0.assign(trk_l0, trk_l0 + n); g->v_z0.assign(trk_z0, trk_z0 + n);
+    g->v_azim.assign(trk_azim, trk_azim + n); g->v_polar.assign(trk_polar, trk_polar + n);
+    g->v_weight.assign(class_weight, class_weight + (size_t)s->A2 * s->cfg.num_polar);
+    g->have_voltrk = true; g->have_volume = false;
+    s->volumes_from_tracer = true;
+    return 0;
+  }
   /* the tracks given here (normally ALL tracks of the problem) are independent of the solver's own
    * (possibly sharded) track set: temporary buffers */
   OtfStarts tmp;
@@ -662,6 +824,33 @@ extern "C" int b200_otf_compute_volumes(b200_solver* s, int64_t n, const int32_t
   return 0;
 }
 
+/* number of 3D segments of arbitrary tracks over the uploaded geometry (work estimate for a partition) */
+extern "C" int b200_otf_count_segments(b200_solver* s, int64_t n, const int32_t* trk_2d, const double* trk_l0,
+                                       const double* trk_z0, const int32_t* trk_azim, const int32_t* trk_polar,
+                                       int32_t* counts) {
+  NEED(s);
+  if (s->grp != nullptr) return fail("b200_otf_count_segments: single-device solvers only");
+  if (s->otf_n_trk2d == 0) return fail("b200_otf_count_segments: b200_upload_otf_geometry has not been called");
+  if (n < 0 || (n > 0 && (!trk_2d || !trk_l0 || !trk_z0 || !trk_azim || !trk_polar || !counts)))
+    return fail("b200_otf_count_segments: null argument");
+  if (n == 0) return 0;
+  OtfStarts tmp;
+  struct Guard { OtfStarts& t; ~Guard() { t.trk2d.release(); t.cls.release(); t.l0.release(); t.z0.release(); } } guard{tmp};
+  if (otf_upload_track_starts(s, n, trk_2d, trk_l0, trk_z0, trk_azim, trk_polar, tmp.trk2d, tmp.l0, tmp.z0, tmp.cls)) return 1;
+  DevBuf<int32_t> cnt;
+  CU(cnt.alloc(n));
+  OtfGeom g = otf_geom(s);
+  g.trk_2d = tmp.trk2d.p; g.trk_l0 = tmp.l0.p; g.trk_z0 = tmp.z0.p; g.trk_class = tmp.cls.p;
+  g.n_trk = n;
+  otf_count_kernel<<<grid_for(n, 128, 1 << 20), 128, 0, s->stream>>>(g, cnt.p);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(counts, cnt.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cnt.release();
+  CU(e);
+  return 0;
+}
+
 extern "C" int b200_upload_tracks_otf(b200_solver* s, const int32_t* trk_2d, const double* trk_l0, const double* trk_z0,
                                       const int32_t* trk_azim, const int32_t* trk_polar,
                                       const int64_t* trk_next_fwd, const int64_t* trk_next_bwd,
@@ -674,6 +863,17 @@ extern "C" int b200_upload_tracks_otf(b200_solver* s, const int32_t* trk_2d, con
   if (nt > 0 && (!trk_2d || !trk_l0 || !trk_z0 || !trk_azim || !trk_polar || !trk_next_fwd || !trk_next_bwd ||
                  !trk_flags || !trk_bc_fwd || !trk_bc_bwd))
     return fail("b200_upload_tracks_otf: null array");
+  if (s->grp != nullptr) {
+    b200_group* g = s->grp;
+    g->trk_2d.assign(trk_2d, trk_2d + nt); g->trk_l0.assign(trk_l0, trk_l0 + nt); g->trk_z0.assign(trk_z0, trk_z0 + nt);
+    g->trk_azim.assign(trk_azim, trk_azim + nt); g->trk_polar.assign(trk_polar, trk_polar + nt);
+    g->next_fwd.assign(trk_next_fwd, trk_next_fwd + nt); g->next_bwd.assign(trk_next_bwd, trk_next_bwd + nt);
+    g->flags.assign(trk_flags, trk_flags + nt); g->bc_fwd.assign(trk_bc_fwd, trk_bc_fwd + nt); g->bc_bwd.assign(trk_bc_bwd, trk_bc_bwd + nt);
+    g->have_otf = true; g->have_explicit = false;
+    s->have_tracks = true; s->finalized = false;
+    if (n_segments_out) *n_segments_out = 0;       /* known after b200_finalize: b200_get_num_segments */
+    return 0;
+  }
   for (int64_t t = 0; t < nt; t++) {
     const uint8_t bcs[2] = {trk_bc_fwd[t], trk_bc_bwd[t]};
     const int64_t nx[2] = {trk_next_fwd[t], trk_next_bwd[t]};
@@ -736,6 +936,7 @@ extern "C" int b200_get_num_segments(b200_solver* s, int64_t* n_segments) {
 
 extern "C" int b200_get_segments(b200_solver* s, double* seg_length, int32_t* seg_fsr, int64_t n, int64_t* trk_seg_offset) {
   NEED(s);
+  if (s->grp != nullptr) return fail("b200_get_segments: ask the shards of a multi-device solver");
   if (!s->have_tracks) return fail("b200_get_segments: no tracks uploaded");
   if (n != s->n_seg) return fail("b200_get_segments: %lld segments requested, the solver holds %lld", (long long)n, (long long)s->n_seg);
   if (trk_seg_offset) memcpy(trk_seg_offset, s->h_off.data(), (s->n_trk + 1) * sizeof(int64_t));
@@ -759,6 +960,7 @@ extern "C" int b200_get_segments(b200_solver* s, double* seg_length, int32_t* se
 
 extern "C" int b200_get_volumes(b200_solver* s, double* out, int64_t n) {
   NEED(s);
+  GRP_FIRST(s, b200_get_volumes(c, out, n));
   if (n != s->n_fsr || s->vol.n != (size_t)s->n_fsr) return fail("b200_get_volumes: size mismatch or no volumes yet");
   CU(cudaMemcpyAsync(out, s->vol.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
@@ -791,6 +993,7 @@ static void choose_lane_map(int G, int* gpl, int* lpi, int* ipc) {
 
 extern "C" int b200_finalize(b200_solver* s) {
   NEED(s);
+  if (s->grp != nullptr) return grp_finalize(s);
   if (!s->have_tracks || !s->have_quad || !s->have_fsrs || !s->have_mats)
     return fail("b200_finalize: tracks, quadrature, FSRs and materials must all be uploaded first");
   const int64_t nt = s->n_trk;
@@ -1179,6 +1382,7 @@ static int clear_done(b200_solver* s) {
 
 extern "C" int b200_zero_track_fluxes(b200_solver* s) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_zero_track_fluxes(c));
   const size_t npsi = (size_t)s->n_trk * 2 * s->F;
   if (npsi) {
     CU(cudaMemsetAsync(s->psi_a.p, 0, npsi * 4, s->stream));
@@ -1190,6 +1394,7 @@ extern "C" int b200_zero_track_fluxes(b200_solver* s) {
 
 extern "C" int b200_flatten_fsr_fluxes(b200_solver* s, double value) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_flatten_fsr_fluxes(c, value));
   const int64_t n = s->n_fsr * s->G;
   fill_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->phi.p, value, n);
   CU(cudaGetLastError());
@@ -1200,6 +1405,7 @@ extern "C" int b200_flatten_fsr_fluxes(b200_solver* s, double value) {
 
 extern "C" int b200_flatten_fsr_fluxes_chi_spectrum(b200_solver* s, int32_t material) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_flatten_fsr_fluxes_chi_spectrum(c, material));
   if (material < 0 || material >= s->n_mat)
     return fail("b200_flatten_fsr_fluxes_chi_spectrum: material %d outside [0,%d)", material, s->n_mat);
   fill_chi_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(fsr_args(s), material);
@@ -1210,6 +1416,7 @@ extern "C" int b200_flatten_fsr_fluxes_chi_spectrum(b200_solver* s, int32_t mate
 
 extern "C" int b200_store_fsr_fluxes(b200_solver* s) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_store_fsr_fluxes(c));
   CU(cudaMemcpyAsync(s->phi_old.p, s->phi.p, (size_t)s->n_fsr * s->G * 8, cudaMemcpyDeviceToDevice, s->stream));
   return 0;
 }
@@ -1251,6 +1458,7 @@ static int launch_scale(b200_solver* s) {
 
 extern "C" int b200_normalize_fluxes(b200_solver* s, double* norm_factor) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_normalize_fluxes(c, norm_factor));
   if (clear_done(s)) return 1;
   if (launch_rate(s, 2)) return 1;
   if (launch_scale(s)) return 1;
@@ -1278,22 +1486,29 @@ static int launch_sources(b200_solver* s, int iteration, int mode) {
 
 extern "C" int b200_compute_fsr_sources(b200_solver* s, int32_t iteration) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_compute_fsr_sources(c, iteration));
   if (clear_done(s)) return 1;
   return launch_sources(s, iteration, 0);
 }
 extern "C" int b200_compute_fsr_fission_sources(b200_solver* s) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_compute_fsr_fission_sources(c));
   if (clear_done(s)) return 1;
   return launch_sources(s, 0, 1);
 }
 extern "C" int b200_compute_fsr_scatter_sources(b200_solver* s) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_compute_fsr_scatter_sources(c));
   if (clear_done(s)) return 1;
   return launch_sources(s, 0, 2);
 }
 
 extern "C" int b200_transport_sweep(b200_solver* s) {
   NEED_FINAL(s);
+  if (s->grp != nullptr) {
+    for (b200_solver* c : grp_shards(s)) { CU(cudaSetDevice(c->cfg.device)); if (clear_done(c)) return 1; }
+    return grp_sweep(s);
+  }
   if (clear_done(s)) return 1;
   return launch_sweep(s);
 }
@@ -1311,6 +1526,7 @@ static int launch_closure(b200_solver* s, int with_rate, int* n_partials) {
 
 extern "C" int b200_add_source_to_scalar_flux(b200_solver* s) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_add_source_to_scalar_flux(c));
   if (clear_done(s)) return 1;
   return launch_closure(s, 0, nullptr);
 }
@@ -1328,12 +1544,15 @@ static int launch_balance_keff(b200_solver* s) {
 
 extern "C" int b200_set_keff_from_neutron_balance(b200_solver* s, int32_t on) {
   NEED(s);
+  if (s->grp != nullptr && on) return fail("k_eff from the neutron balance is not available on a multi-device solver in this build");
+  if (s->grp != nullptr) return 0;
   s->balance = on != 0;
   return 0;
 }
 
 extern "C" int b200_compute_keff(b200_solver* s, double* k_eff) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_compute_keff(c, k_eff));
   if (clear_done(s)) return 1;
   if (s->balance ? launch_balance_keff(s) : launch_rate(s, 1)) return 1;
   if (k_eff != nullptr) {
@@ -1358,6 +1577,7 @@ static int launch_residual(b200_solver* s, int res_type, int scale_first, int st
 
 extern "C" int b200_compute_residual(b200_solver* s, int32_t res_type, double* residual) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_compute_residual(c, res_type, residual));
   if (res_type < 0 || res_type > 2) return fail("b200_compute_residual: unknown residual type %d", res_type);
   if (res_type == B200_RES_FISSION_SOURCE && s->n_fissionable == 0)
     return fail("The Solver is unable to compute a FISSION_SOURCE residual without fissionable FSRs");
@@ -1387,11 +1607,13 @@ static int launch_stabilize_flux(b200_solver* s) {
 
 extern "C" int b200_compute_stabilizing_flux(b200_solver* s) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_compute_stabilizing_flux(c));
   if (clear_done(s)) return 1;
   return launch_stabilizing_flux(s);
 }
 extern "C" int b200_stabilize_flux(b200_solver* s) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_stabilize_flux(c));
   if (clear_done(s)) return 1;
   return launch_stabilize_flux(s);
 }
@@ -1401,6 +1623,7 @@ extern "C" int b200_stabilize_flux(b200_solver* s) {
 /* ------------------------------------------------------------------------- */
 extern "C" int b200_get_fluxes(b200_solver* s, double* out, int64_t n) {
   NEED_FINAL(s);
+  GRP_FIRST(s, b200_get_fluxes(c, out, n));
   if (n != s->n_fsr * s->G)
     return fail("Unable to get FSR scalar fluxes since there are %d groups and %lld FSRs which does "
                 "not match the requested %lld flux values", s->G, (long long)s->n_fsr, (long long)n);
@@ -1412,6 +1635,7 @@ extern "C" int b200_get_fluxes(b200_solver* s, double* out, int64_t n) {
  * step, openmoc/krylov.py style, need both after every iteration) */
 extern "C" int b200_get_fluxes_keff(b200_solver* s, double* out, int64_t n, double* k_eff) {
   NEED_FINAL(s);
+  GRP_FIRST(s, b200_get_fluxes_keff(c, out, n, k_eff));
   if (n != s->n_fsr * s->G)
     return fail("Unable to get FSR scalar fluxes since there are %d groups and %lld FSRs which does "
                 "not match the requested %lld flux values", s->G, (long long)s->n_fsr, (long long)n);
@@ -1423,6 +1647,7 @@ extern "C" int b200_get_fluxes_keff(b200_solver* s, double* out, int64_t n, doub
 }
 extern "C" int b200_set_fluxes(b200_solver* s, const double* in, int64_t n) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_set_fluxes(c, in, n));
   if (n != s->n_fsr * s->G)
     return fail("Unable to set an array with %lld flux values for %lld FSRs and %d groups",
                 (long long)n, (long long)s->n_fsr, s->G);
@@ -1432,6 +1657,7 @@ extern "C" int b200_set_fluxes(b200_solver* s, const double* in, int64_t n) {
 }
 extern "C" int b200_set_fixed_source_by_fsr(b200_solver* s, int64_t fsr_id, int32_t group, double source) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_set_fixed_source_by_fsr(c, fsr_id, group, source));
   if (group <= 0 || group > s->G)
     return fail("Unable to use fixed source for group %d in a %d energy group problem", group, s->G);
   if (fsr_id < 0 || fsr_id >= s->n_fsr)
@@ -1444,12 +1670,14 @@ extern "C" int b200_set_fixed_source_by_fsr(b200_solver* s, int64_t fsr_id, int3
 }
 extern "C" int b200_reset_fixed_sources(b200_solver* s) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_reset_fixed_sources(c));
   CU(cudaMemsetAsync(s->fixed.p, 0, (size_t)s->n_fsr * s->G * 8, s->stream));
   s->fixed_on = false;
   return 0;
 }
 extern "C" int b200_compute_fsr_fission_rates(b200_solver* s, double* out, int64_t n, int32_t nu) {
   NEED_FINAL(s);
+  GRP_FIRST(s, b200_compute_fsr_fission_rates(c, out, n, nu));
   if (n != s->n_fsr) return fail("b200_compute_fsr_fission_rates: %lld values requested for %lld FSRs", (long long)n, (long long)s->n_fsr);
   fission_rates_kernel<<<grid_for(s->n_fsr, 256), 256, 0, s->stream>>>(fsr_args(s), s->scratch.p, nu);
   CU(cudaGetLastError());
@@ -1465,27 +1693,34 @@ extern "C" int b200_stabilize_transport(b200_solver* s, double factor, int32_t t
   s->stabilize = true;
   s->stab_factor = factor;
   s->stab_type = type;
+  if (s->grp != nullptr && s->finalized)
+    for (b200_solver* c : grp_shards(s)) { c->stabilize = true; c->stab_factor = factor; c->stab_type = type; }
   return 0;
 }
 extern "C" int b200_allow_negative_fluxes(b200_solver* s, int32_t allowed) {
   NEED(s);
   s->neg_allowed = allowed != 0;
+  if (s->grp != nullptr && s->finalized)
+    for (b200_solver* c : grp_shards(s)) c->neg_allowed = s->neg_allowed;
   return 0;
 }
 extern "C" int b200_get_keff(b200_solver* s, double* k) {
   NEED(s);
+  GRP_FIRST(s, b200_get_keff(c, k));
   if (fetch_scalars(s)) return 1;
   if (k) *k = s->h_scal[SC_KEFF];
   return 0;
 }
 extern "C" int b200_set_keff(b200_solver* s, double k) {
   NEED(s);
+  GRP_ALL(s, b200_set_keff(c, k));
   CU(cudaMemcpyAsync(s->scal.p + SC_KEFF, &k, 8, cudaMemcpyHostToDevice, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   return 0;
 }
 extern "C" int b200_get_fsr_sources(b200_solver* s, double* out, int64_t n) {
   NEED_FINAL(s);
+  GRP_FIRST(s, b200_get_fsr_sources(c, out, n));
   if (n != s->n_fsr * s->G) return fail("b200_get_fsr_sources: size mismatch");
   extract_q_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->qst.p, s->scratch.p, n);
   CU(cudaGetLastError());
@@ -1495,6 +1730,7 @@ extern "C" int b200_get_fsr_sources(b200_solver* s, double* out, int64_t n) {
 }
 extern "C" int b200_set_fsr_sources(b200_solver* s, const double* in, int64_t n) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_set_fsr_sources(c, in, n));
   if (n != s->n_fsr * s->G) return fail("b200_set_fsr_sources: size mismatch");
   CU(cudaMemcpyAsync(s->scratch.p, in, n * 8, cudaMemcpyHostToDevice, s->stream));
   insert_q_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->qst.p, s->scratch.p, n);
@@ -1504,6 +1740,7 @@ extern "C" int b200_set_fsr_sources(b200_solver* s, const double* in, int64_t n)
 }
 extern "C" int b200_get_flux_moments(b200_solver* s, double* out, int64_t n) {
   NEED_FINAL(s);
+  GRP_FIRST(s, b200_get_flux_moments(c, out, n));
   if (!s->linear) return fail("b200_get_flux_moments: not a linear-source solver");
   if (n != s->n_fsr * s->G * 3) return fail("b200_get_flux_moments: size mismatch");
   /* staging buffer in the reference's [r][c][e] order, kept for the next call (the CMFD path
@@ -1518,6 +1755,7 @@ extern "C" int b200_get_flux_moments(b200_solver* s, double* out, int64_t n) {
 }
 extern "C" int b200_set_flux_moments(b200_solver* s, const double* in, int64_t n) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_set_flux_moments(c, in, n));
   if (!s->linear) return fail("b200_set_flux_moments: not a linear-source solver");
   if (n != s->n_fsr * s->G * 3) return fail("b200_set_flux_moments: size mismatch");
   if (s->mom_stage.n < (size_t)n) CU(s->mom_stage.alloc(n));
@@ -1531,6 +1769,7 @@ extern "C" int b200_set_flux_moments(b200_solver* s, const double* in, int64_t n
 
 extern "C" int b200_get_start_fluxes(b200_solver* s, float* out, int64_t n) {
   NEED_FINAL(s);
+  if (s->grp != nullptr) return grp_get_start_fluxes(s, out, n);
   if (n != s->n_trk * 2 * (int64_t)s->F) return fail("b200_get_start_fluxes: size mismatch");
   if (n) CU(cudaMemcpyAsync(out, s->psi_start, n * 4, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
@@ -1538,6 +1777,7 @@ extern "C" int b200_get_start_fluxes(b200_solver* s, float* out, int64_t n) {
 }
 extern "C" int b200_set_start_fluxes(b200_solver* s, const float* in, int64_t n) {
   NEED_FINAL(s);
+  if (s->grp != nullptr) return grp_set_start_fluxes(s, in, n);
   if (n != s->n_trk * 2 * (int64_t)s->F) return fail("b200_set_start_fluxes: size mismatch");
   if (n) CU(cudaMemcpyAsync(s->psi_start, in, n * 4, cudaMemcpyHostToDevice, s->stream));
   double m = 0.;
@@ -1642,6 +1882,7 @@ extern "C" int b200_compute_eigenvalue(b200_solver* s, int32_t max_iters, double
                                        int32_t* num_iterations) {
   NEED_FINAL(s);
   if (res_type < 0 || res_type > 2) return fail("b200_compute_eigenvalue: unknown residual type %d", res_type);
+  if (s->grp != nullptr) return grp_compute_eigenvalue(s, max_iters, tol, res_type, num_iterations);
   if (res_type == B200_RES_FISSION_SOURCE && s->n_fissionable == 0)
     return fail("The Solver is unable to compute a FISSION_SOURCE residual without fissionable FSRs");
   if (prepare_history(s, max_iters)) return 1;
@@ -1697,6 +1938,7 @@ extern "C" int b200_compute_eigenvalue(b200_solver* s, int32_t max_iters, double
  *      GPUs in the middle of every iteration (multi-GPU angular decomposition) ---- */
 extern "C" int b200_eigen_loop_init(b200_solver* s, int32_t max_iters, double tol) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_eigen_loop_init(c, max_iters, tol));
   if (prepare_history(s, max_iters)) return 1;
   double init[SC_COUNT_D] = {0};
   init[SC_KEFF] = 1.0; init[SC_KPREV] = 1.0; init[SC_TOL] = tol;
@@ -1715,6 +1957,14 @@ extern "C" int b200_eigen_loop_init(b200_solver* s, int32_t max_iters, double to
  * and would sum the final flux over the ranks: begin saves it, end restores it. */
 extern "C" int b200_iteration_begin(b200_solver* s, int32_t iteration) {
   NEED_FINAL(s);
+  if (s->grp != nullptr) {
+    for (b200_solver* c : grp_shards(s)) {
+      CU(cudaSetDevice(c->cfg.device));
+      if (iteration != 0 && c->stabilize) { if (launch_stabilizing_flux(c)) return 1; }
+      if (launch_sources(c, iteration, 0)) return 1;
+    }
+    return grp_sweep(s);
+  }
   if (enqueue_iteration_begin(s, iteration)) return 1;
   const int64_t n = s->n_fsr * s->G;
   copy_if_done_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->scratch.p, s->phi.p, n, s->iscal.p);
@@ -1724,6 +1974,13 @@ extern "C" int b200_iteration_begin(b200_solver* s, int32_t iteration) {
 extern "C" int b200_iteration_end(b200_solver* s, int32_t iteration, int32_t res_type, int32_t check_convergence) {
   NEED_FINAL(s);
   if (res_type < 0 || res_type > 2) return fail("b200_iteration_end: unknown residual type %d", res_type);
+  if (s->grp != nullptr) {
+    for (b200_solver* c : grp_shards(s)) {
+      CU(cudaSetDevice(c->cfg.device));
+      if (enqueue_iteration_end(c, iteration, res_type, check_convergence ? 1 : 0)) return 1;
+    }
+    return 0;
+  }
   if (check_convergence && iteration >= 0 && s->hist_k.n <= (size_t)iteration)
     return fail("b200_iteration_end: iteration %d beyond the max_iters given to b200_eigen_loop_init", iteration);
   const int64_t n = s->n_fsr * s->G;
@@ -1734,6 +1991,7 @@ extern "C" int b200_iteration_end(b200_solver* s, int32_t iteration, int32_t res
 extern "C" int b200_eigen_loop_status(b200_solver* s, int32_t enqueued, int32_t* done, int32_t* iterations,
                                       double* k_eff, double* residual) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_eigen_loop_status(c, enqueued, done, iterations, k_eff, residual));
   if (fetch_scalars(s)) return 1;
   if (done) *done = s->h_iscal[SI_DONE];
   if (iterations) *iterations = s->h_iscal[SI_ITERS];
@@ -1749,6 +2007,19 @@ extern "C" int b200_eigen_loop_status(b200_solver* s, int32_t enqueued, int32_t*
 extern "C" int b200_iterate(b200_solver* s, int32_t n, int32_t res_type, double* k_eff, double* residual) {
   NEED_FINAL(s);
   if (res_type < 0 || res_type > 2) return fail("b200_iterate: unknown residual type %d", res_type);
+  if (s->grp != nullptr) {
+    for (b200_solver* c : grp_shards(s)) { CU(cudaSetDevice(c->cfg.device)); if (clear_done(c)) return 1; }
+    for (int i = 0; i < n; i++)
+      if (grp_iteration(s, 1000 + i, res_type, 0)) return 1;
+    if (k_eff != nullptr || residual != nullptr) {
+      if (grp_sync(s)) return 1;
+      b200_solver* c0 = grp_shards(s)[0];
+      if (fetch_scalars(c0)) return 1;
+      if (k_eff) *k_eff = c0->h_scal[SC_KEFF];
+      if (residual) *residual = c0->h_scal[SC_RESIDUAL];
+    }
+    return 0;
+  }
   if (clear_done(s)) return 1;
   for (int i = 0; i < n; i++)
     if (enqueue_eigen_iteration(s, 1000 + i, res_type, 0)) return 1;
@@ -1788,6 +2059,19 @@ static int flux_source_loop(b200_solver* s, int max_iters, double tol, int res_t
 extern "C" int b200_compute_flux(b200_solver* s, int32_t max_iters, double tol, int32_t only_fixed_source,
                                  int32_t* num_iterations) {
   NEED_FINAL(s);
+  if (s->grp != nullptr) {
+    for (b200_solver* c : grp_shards(s)) {
+      if (b200_set_keff(c, 1.0)) return 1;
+      if (only_fixed_source) {
+        if (b200_zero_track_fluxes(c)) return 1;
+        if (b200_flatten_fsr_fluxes(c, 0.0)) return 1;
+        if (b200_store_fsr_fluxes(c)) return 1;
+      }
+      if (clear_done(c)) return 1;
+      if (launch_sources(c, 0, 0)) return 1;
+    }
+    return grp_flux_source_loop(s, max_iters, tol, B200_RES_SCALAR_FLUX, false, num_iterations);
+  }
   if (b200_set_keff(s, 1.0)) return 1;
   if (only_fixed_source) {
     if (b200_zero_track_fluxes(s)) return 1;
@@ -1805,6 +2089,15 @@ extern "C" int b200_compute_source(b200_solver* s, int32_t max_iters, double k_e
   if (k_eff <= 0.)
     return fail("The Solver is unable to compute the source with keff = %f since it is not a positive value", k_eff);
   if (res_type < 0 || res_type > 2) return fail("b200_compute_source: unknown residual type %d", res_type);
+  if (s->grp != nullptr) {
+    for (b200_solver* c : grp_shards(s)) {
+      if (b200_set_keff(c, k_eff)) return 1;
+      if (b200_zero_track_fluxes(c)) return 1;
+      if (b200_flatten_fsr_fluxes(c, 1.0)) return 1;
+      if (b200_store_fsr_fluxes(c)) return 1;
+    }
+    return grp_flux_source_loop(s, max_iters, tol, res_type, true, num_iterations);
+  }
   if (b200_set_keff(s, k_eff)) return 1;
   if (b200_zero_track_fluxes(s)) return 1;
   if (b200_flatten_fsr_fluxes(s, 1.0)) return 1;
@@ -1888,6 +2181,18 @@ extern "C" int b200_measure_ceilings(int32_t device, int64_t table_rows, double*
 /* ------------------------------------------------------------------------- */
 extern "C" int b200_get_sweep_stats(b200_solver* s, double* ms, int64_t* n_sweeps, int64_t* launches) {
   NEED(s);
+  if (s->grp != nullptr) {
+    double m = 0.; int64_t nl = 0, nsw = 0;
+    for (b200_solver* c : grp_shards(s)) {
+      double cm = 0.; int64_t cs = 0, cl = 0;
+      if (b200_get_sweep_stats(c, &cm, &cs, &cl)) return 1;
+      m = std::max(m, cm); nl += cl; nsw = cs;
+    }
+    if (ms) *ms = m;
+    if (n_sweeps) *n_sweeps = nsw;
+    if (launches) *launches = nl;
+    return 0;
+  }
   if (resolve_events(s)) return 1;
   if (ms) *ms = s->sweep_ms;
   if (n_sweeps) *n_sweeps = s->n_sweeps;
@@ -1896,6 +2201,7 @@ extern "C" int b200_get_sweep_stats(b200_solver* s, double* ms, int64_t* n_sweep
 }
 extern "C" int b200_reset_sweep_stats(b200_solver* s) {
   NEED(s);
+  GRP_ALL(s, b200_reset_sweep_stats(c));
   if (resolve_events(s)) return 1;
   s->sweep_ms = 0.;
   s->n_sweeps = 0;
@@ -1904,11 +2210,13 @@ extern "C" int b200_reset_sweep_stats(b200_solver* s) {
 }
 extern "C" int b200_synchronize(b200_solver* s) {
   NEED(s);
+  GRP_ALL(s, b200_synchronize(c));
   CU(cudaStreamSynchronize(s->stream));
   return 0;
 }
 extern "C" int b200_device_pointer(b200_solver* s, const char* name, void** ptr, int64_t* n) {
   NEED_FINAL(s);
+  GRP_FIRST(s, b200_device_pointer(c, name, ptr, n));
   if (!name || !ptr || !n) return fail("b200_device_pointer: null argument");
   const int64_t nphi = s->n_fsr * s->G;
   if (!strcmp(name, "scalar_flux")) { *ptr = s->phi.p; *n = nphi; }
@@ -1931,12 +2239,14 @@ extern "C" int b200_device_pointer(b200_solver* s, const char* name, void** ptr,
  * b200_finish_fixed_tally then converts it into scalar_flux. */
 extern "C" int b200_defer_fixed_tally(b200_solver* s, int32_t defer) {
   NEED(s);
+  if (s->grp != nullptr) return fail("b200_defer_fixed_tally: a multi-device solver reduces its fixed-point tallies itself");
   if (!s->cfg.deterministic) return fail("b200_defer_fixed_tally: deterministic mode only");
   s->defer_fx_convert = defer != 0;
   return 0;
 }
 extern "C" int b200_finish_fixed_tally(b200_solver* s) {
   NEED_FINAL(s);
+  GRP_ALL(s, b200_finish_fixed_tally(c));
   if (!s->cfg.deterministic) return fail("b200_finish_fixed_tally: deterministic mode only");
   fx_to_double_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(fsr_args(s), s->phi_fx.p);
   CU(cudaGetLastError());
@@ -1949,15 +2259,19 @@ extern "C" int b200_finish_fixed_tally(b200_solver* s) {
  * the engine records no timing events and issues no host synchronisation. */
 extern "C" int b200_set_capturing(b200_solver* s, int32_t capturing) {
   NEED(s);
+  GRP_ALL(s, b200_set_capturing(c, capturing));
   s->capturing = capturing != 0;
   return 0;
 }
 
 extern "C" int b200_set_stream(b200_solver* s, void* cuda_stream) {
   NEED(s);
+  if (s->grp != nullptr) return fail("b200_set_stream: a multi-device solver owns one stream per device");
   CU(cudaStreamSynchronize(s->stream));
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
   s->stream = (cudaStream_t)cuda_stream;
   s->own_stream = false;
   return 0;
 }
+
+#include "group_impl.cuh"

@@ -56,6 +56,9 @@ class B200Solver:
                                (NCCL send/recv)
     deterministic : bool       accumulate the FSR tally in 64-bit fixed point: results are
                                bitwise reproducible run to run (and across GPU counts)
+    devices : optional         list of CUDA device ordinals: ONE solver handle drives them all (b200_set_devices);
+                               the library shards the tracks by chain and sums the tallies with its own
+                               peer-memory all-reduce.  A device may repeat (several shards on one GPU).
     global_tracks : optional   the whole problem's tracks when `tracks` already is one rank's shard
     linear_source : bool       CPULSSolver physics (src/CPULSSolver.cpp): needs a track file dumped
                                after a linear-source initialisation (centroid-relative segment
@@ -66,7 +69,7 @@ class B200Solver:
     def __init__(self, tracks: FlatTracks, device: int = 0, precision: int = PRECISION_DOUBLE,
                  process_group=None, use_distributed: Optional[bool] = None, deterministic: bool = False,
                  partition: str = "pair", linear_source: bool = False,
-                 global_tracks: Optional[FlatTracks] = None):
+                 global_tracks: Optional[FlatTracks] = None, devices=None):
         self._lib = capi.load()
         self._h = C.c_void_p()
         # global_tracks: the full track set when `tracks` already is one rank's shard (the FSR volumes of
@@ -133,6 +136,11 @@ class B200Solver:
         self._graphs = {}                      # (res_type, check) -> CUDA graph of two split iterations
         self._mom_tensor = None
         check(self._lib.b200_create(C.byref(cfg), C.byref(self._h)))
+        if devices is not None and len(devices) > 0:
+            if self._world > 1:
+                raise B200Error("devices=[...] (one process driving several GPUs) and a process group exclude each other")
+            arr = np.ascontiguousarray(devices, dtype="i4")
+            check(self._lib.b200_set_devices(self._h, arr.size, _ptr(arr)))
         self._upload(tracks)
         if self._deterministic and self._world > 1:
             check(self._lib.b200_defer_fixed_tally(self._h, 1))
@@ -160,6 +168,9 @@ class B200Solver:
         if self._ls_tables is not None:
             check(L.b200_upload_linear_source(h, *[_ptr(x) for x in self._ls_tables]))
         check(L.b200_finalize(h))
+        ns = C.c_int64()
+        check(L.b200_get_num_segments(h, C.byref(ns)))
+        self.num_segments = int(ns.value)
 
     def _upload_otf(self, ft: FlatTracks) -> None:
         """Axial on-the-fly track set (synth.make_tracks_3d(expand=False), or what b200_flatten
@@ -189,7 +200,7 @@ class B200Solver:
                 c(a, "trk_bc_fwd", "u1"), c(a, "trk_bc_bwd", "u1")]
         ns = C.c_int64()
         check(L.b200_upload_tracks_otf(h, *[_ptr(x) for x in mine], C.byref(ns)))
-        self.num_segments = int(ns.value)
+        self.num_segments = int(ns.value)        # 0 on a multi-device handle until b200_finalize
 
     def getSegments(self):
         """(seg_length, seg_fsr, trk_seg_offset) as the device holds them (tests, track dumps)."""

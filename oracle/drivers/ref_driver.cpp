@@ -14,6 +14,7 @@
  *        prints delta k_eff (pcm), max relative flux error and both sweep times.
  *                   [--max-iters N] [--threads N] [--res fission|flux|total]
  *                   [--axial N (c5g7-2d, dims 3: axial layers of the root lattice)]
+ *                   [--devices 0,1,.. (--solver both: GPUs behind the one B200Solver; a device may repeat)]
  *                   [--cmfd NXxNY[xNZ]] [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
  */
 #include <cstdio>
@@ -148,6 +149,18 @@ int main(int argc, char** argv) {
     B200LSSolver* gpu_ls = ls ? new B200LSSolver(tg) : NULL;
     Solver& gpu = ls ? *(Solver*)gpu_ls : *(Solver*)gpu_flat;
     if (ls) gpu_ls->setNumThreads(threads); else gpu_flat->setNumThreads(threads);
+    {
+      /* --devices 0,1,...: several GPUs (or several shards on one GPU) behind the one B200Solver */
+      std::string dl = arg(argc, argv, "--devices", "");
+      std::vector<int> devs;
+      for (size_t i = 0; i < dl.size();) {
+        size_t j = dl.find(',', i);
+        if (j == std::string::npos) j = dl.size();
+        devs.push_back(atoi(dl.substr(i, j - i).c_str()));
+        i = j + 1;
+      }
+      if (!devs.empty()) { if (ls) gpu_ls->setDevices(devs); else gpu_flat->setDevices(devs); }
+    }
     gpu.setConvergenceThreshold(tol);
     if (flag(argc, argv, "--verbose")) gpu.setVerboseIterationReport();
     if (flag(argc, argv, "--balance")) gpu.setKeffFromNeutronBalance();

@@ -133,3 +133,31 @@ def test_3d_c5g7_linear_source_cmfd_in_separate_processes(tmp_path):
     print("3D C5G7 LS + CMFD: dk = %.3e pcm, max rel flux err = %.3e" % (dk_pcm, err))
     assert dk_pcm < 1.0 and err < 1e-4           # north_star
     assert dk_pcm < 1e-3 and err < 1e-6          # achieved: ~1e-11 pcm
+
+
+# ---------------------------------------------------------------- several devices behind the plug-in
+def _devices():
+    import torch
+    n = torch.cuda.device_count()
+    return ["0,0", "0,0,0"] + (["0,1"] if n >= 2 else []) + ([",".join(map(str, range(n)))] if n >= 4 else [])
+
+
+@pytest.mark.parametrize("devices", _devices() if os.path.exists(DRIVER) else ["0,0"])
+@pytest.mark.parametrize("args", [
+    ["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12"],                                   # flat 2D
+    ["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12", "--ls"],                          # linear source
+    ["--model", "simple-lattice", "--azim", "8", "--spacing", "0.05", "--cmfd", "4x4"],                 # CMFD currents reduced across shards
+    ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
+     "--zspacing", "0.9", "--cmfd", "2x2x2", "--ls", "--formation", "otf-stacks"],                       # 3D + LS + CMFD
+    ["--model", "c5g7-2d", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "1.0", "--zspacing", "10",
+     "--formation", "otf-stacks", "--max-iters", "25", "--threads", "4"],                                # configs[4] shape, coarse
+])
+def test_multi_device_b200solver_matches_cpusolver_in_process(args, devices):
+    """B200Solver::setDevices: ONE solver object inside the reference's process drives several shards
+    (b200_set_devices); flat and linear source, with the reference's host Cmfd fed by the summed
+    currents.  Same tolerances as the single-device cases above."""
+    r = run(args + ["--solver", "both", "--devices", devices])
+    assert r["b200_iters"] == r["cpu_iters"]
+    assert r["dk_pcm"] < 1.0 and r["max_rel_flux_err"] < 1e-4          # north_star
+    tight = (1e-2, 2e-5) if "--cmfd" in args else (1e-3, 1e-7)
+    assert r["dk_pcm"] < tight[0] and r["max_rel_flux_err"] < tight[1]
