@@ -226,12 +226,14 @@ def test_simulated_ranks_deterministic_tally_is_bitwise_equal_to_one_gpu():
     own max |psi|)."""
     from openmoc_b200.solver import B200Solver
     from openmoc_b200.capi import FISSION_SOURCE
-    ft = _tracks()
-    one = B200Solver(ft, deterministic=True)
-    one.setConvergenceThreshold(1e-5)
-    one.computeEigenvalue(400, FISSION_SOURCE)
-    for world in (2, 3):
-        solvers, iters = _simulated_ranks(ft, world, deterministic=True)
+    from openmoc_b200.synth import make_tracks
+    # the fully reflective lattice has two chains; the C5G7 core (two vacuum sides) has many
+    for ft, world, max_iters in ((_tracks(), 2, 400), (make_tracks("c5g7-2d", num_azim=4, spacing=0.5), 3, 30),
+                                 (make_tracks("c5g7-2d", num_azim=4, spacing=0.5), 5, 30)):
+        one = B200Solver(ft, deterministic=True)
+        one.setConvergenceThreshold(1e-5)
+        one.computeEigenvalue(max_iters, FISSION_SOURCE)
+        solvers, iters = _simulated_ranks(ft, world, max_iters=max_iters, deterministic=True)
         assert iters == one.getNumIterations()
         for s in solvers:
             assert s.getKeff() == one.getKeff()
