@@ -183,6 +183,8 @@ struct b200_solver {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
   double sweep_ms = 0.;
   int64_t n_sweeps = 0, n_launches = 0;
+  /* shard of a multi-device group: the other shards' start-flux buffers for hand-offs that cross devices */
+  std::vector<float*> peer_out;       /* set by the group before every sweep (all shards flip their buffers together) */
   /* several devices behind this handle (group.cuh): the handle itself then owns no device state */
   struct b200_group* grp = nullptr;
 };
@@ -224,6 +226,7 @@ struct b200_group {
   /* CMFD */
   bool have_cmfd = false;
   std::vector<int32_t> cmfd_fwd, cmfd_bwd;
+  bool cross_links = false;        /* tracks sharded one by one: some hand-offs cross shards (peer stores) */
   /* all-reduce plumbing */
   std::vector<cudaEvent_t> ev_a, ev_b;
   std::vector<DevBuf<double>> stage;
@@ -1241,6 +1244,7 @@ static int launch_sweep(b200_solver* s) {
     a.trk_class = s->trk_class.p; a.order = s->order.p; a.out_slot = s->out_slot.p;
     a.carry = s->carry.p; a.cls_w = s->cls_w.p; a.cls_inv_sin = s->cls_inv_sin.p;
     a.qst = s->qst.p; a.psi_in = s->psi_start; a.psi_out = s->psi_other; a.phi = s->phi.p;
+    for (int j = 0; j < 16; j++) a.peer_out.p[j] = j < (int)s->peer_out.size() ? s->peer_out[j] : nullptr;
     a.phi_fx = s->phi_fx.p; a.fx_scale = s->scal.p + SC_FXSCALE;
     a.rep_stride = (int64_t)nphi; a.rep_mask = s->n_rep - 1;
     a.leakage = s->balance ? s->leakage.p : nullptr;

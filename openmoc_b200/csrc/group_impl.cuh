@@ -128,6 +128,13 @@ static int grp_reduce(b200_solver* s) {
 
 /* sweep on every shard, tallies summed: the group's b200_transport_sweep */
 static int grp_sweep(b200_solver* s) {
+  /* every shard writes the hand-offs that cross devices into the buffer the owner reads NEXT sweep: the
+   * pointers are taken before any shard flips its double buffer */
+  if (s->grp->cross_links) {
+    std::vector<float*> next_in;
+    for (b200_solver* c : grp_shards(s)) next_in.push_back(c->psi_other);
+    for (b200_solver* c : grp_shards(s)) c->peer_out = next_in;
+  }
   for (b200_solver* c : grp_shards(s)) {
     CU(cudaSetDevice(c->cfg.device));
     if (c->cfg.deterministic) c->defer_fx_convert = true;
@@ -222,12 +229,48 @@ static int grp_finalize(b200_solver* s) {
     }
   }
   if (!g->have_volume) return fail("b200_finalize: no FSR volumes (b200_upload_fsrs with volume = NULL needs b200_otf_compute_volumes)");
+  /* Partition.  Whole chains when there are enough of them (no angular flux ever crosses a shard);
+   * otherwise single tracks, dealt in a snake by decreasing load - any number of shards, also for fully
+   * reflective decks whose tracks form a handful of cycles - with the hand-offs that cross shards stored
+   * by the sweep kernel straight into the owner's start-flux buffer over peer memory (sweep.cuh: PeerOut).
+   * B200_GROUP_PARTITION=chain|track overrides. */
   std::vector<int32_t> owner;
   const int64_t n_chains = partition_chains(nt, g->next_fwd.data(), g->next_bwd.data(), g->bc_fwd.data(), g->bc_bwd.data(),
                                             load.data(), N, owner);
-  if (n_chains < 0) return fail("b200_finalize: %d devices but fewer independent track chains", N);
+  bool by_track = n_chains < (int64_t)4 * N;
+  if (const char* e = getenv("B200_GROUP_PARTITION")) {
+    if (!strcmp(e, "track")) by_track = true;
+    if (!strcmp(e, "chain")) by_track = false;
+  }
+  if (!by_track && n_chains < N) return fail("b200_finalize: %d shards but only %lld independent track chains", N, (long long)n_chains);
+  if (by_track) {
+    std::vector<int64_t> order(nt);
+    std::iota(order.begin(), order.end(), (int64_t)0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return load[a] > load[b]; });
+    owner.assign(nt, 0);
+    for (int64_t i = 0; i < nt; i++) {
+      const int64_t pos = i % (2 * N);
+      owner[order[i]] = (int32_t)(pos < N ? pos : 2 * N - 1 - pos);
+    }
+  }
+  g->cross_links = false;
   std::vector<int64_t> local(nt);
   for (int64_t t = 0; t < nt; t++) { local[t] = (int64_t)g->ids[owner[t]].size(); g->ids[owner[t]].push_back(t); }
+  /* global one-to-one check of the hand-off table (b200_finalize of a shard only sees its own links) */
+  {
+    std::vector<uint8_t> fed(2 * nt, 0);
+    for (int64_t t = 0; t < nt; t++)
+      for (int d = 0; d < 2; d++) {
+        const uint8_t bc = d == 0 ? g->bc_fwd[t] : g->bc_bwd[t];
+        if (bc != B200_BC_REFLECTIVE && bc != B200_BC_PERIODIC) continue;
+        const int64_t nx = d == 0 ? g->next_fwd[t] : g->next_bwd[t];
+        if (nx < 0 || nx >= nt) return fail("b200_finalize: track %lld links to track %lld outside [0,%lld)", (long long)t, (long long)nx, (long long)nt);
+        const int fwd = d == 0 ? (g->flags[t] & 1) : ((g->flags[t] >> 1) & 1);
+        const int64_t slot = nx * 2 + (fwd ? 0 : 1);
+        if (fed[slot]) return fail("b200_finalize: two track ends hand their flux to the same slot (track %lld)", (long long)nx);
+        fed[slot] = 1;
+      }
+  }
 
   for (int c = 0; c < N; c++) {
     const std::vector<int64_t>& ids = g->ids[c];
@@ -241,6 +284,9 @@ static int grp_finalize(b200_solver* s) {
       const bool lf = bf[k] == B200_BC_REFLECTIVE || bf[k] == B200_BC_PERIODIC, lb = bb[k] == B200_BC_REFLECTIVE || bb[k] == B200_BC_PERIODIC;
       nf[k] = lf ? local[g->next_fwd[t]] : -1;
       nb[k] = lb ? local[g->next_bwd[t]] : -1;
+      /* a hand-off that leaves the shard: uploaded as an open end, patched into a peer store below */
+      if (lf && owner[g->next_fwd[t]] != c) { nf[k] = -1; bf[k] = B200_BC_VACUUM; g->cross_links = true; }
+      if (lb && owner[g->next_bwd[t]] != c) { nb[k] = -1; bb[k] = B200_BC_VACUUM; g->cross_links = true; }
     }
     b200_config cc = cfg;
     cc.device = g->devices[c];
@@ -302,6 +348,31 @@ static int grp_finalize(b200_solver* s) {
     if (b200_finalize(sc)) return 1;
     sc->stabilize = s->stabilize; sc->stab_factor = s->stab_factor; sc->stab_type = s->stab_type;
     sc->neg_allowed = s->neg_allowed;
+  }
+  /* hand-offs that cross shards: destination = (owner + 1) << 48 | slot in the owner's buffer; the
+   * destination slot is fed, so the owner must not copy its incoming flux through */
+  if (g->cross_links) {
+    std::vector<std::vector<int64_t>> out_slot(N);
+    std::vector<std::vector<uint8_t>> carry(N);
+    for (int c = 0; c < N; c++) { out_slot[c].assign(2 * g->ids[c].size(), -1); carry[c].assign(2 * g->ids[c].size(), 1); }
+    for (int64_t t = 0; t < nt; t++)
+      for (int d = 0; d < 2; d++) {
+        const uint8_t bc = d == 0 ? g->bc_fwd[t] : g->bc_bwd[t];
+        if (bc != B200_BC_REFLECTIVE && bc != B200_BC_PERIODIC) continue;
+        const int64_t nx = d == 0 ? g->next_fwd[t] : g->next_bwd[t];
+        const int fwd = d == 0 ? (g->flags[t] & 1) : ((g->flags[t] >> 1) & 1);
+        const int co = owner[t], cd = owner[nx];
+        const int64_t slot = local[nx] * 2 + (fwd ? 0 : 1);
+        out_slot[co][local[t] * 2 + d] = cd == co ? slot : (((int64_t)(cd + 1) << PEER_SHIFT) | slot);
+        carry[cd][slot] = 0;
+      }
+    for (int c = 0; c < N; c++) {
+      b200_solver* sc = g->shard[c];
+      CU(cudaSetDevice(sc->cfg.device));
+      CU(sc->out_slot.upload(out_slot[c].data(), out_slot[c].size(), sc->stream));
+      CU(sc->carry.upload(carry[c].data(), carry[c].size(), sc->stream));
+      CU(cudaStreamSynchronize(sc->stream));
+    }
   }
   /* totals and plumbing */
   s->n_seg = 0;

@@ -229,6 +229,15 @@ struct __align__(16) SegRec {
 };
 constexpr int SEG_PAD = 40;  /* sentinel records before and after the stream (covers look-ahead + L2 prefetch distance) */
 
+/* Hand-offs that cross devices (a multi-device group whose tracks are sharded track by track,
+ * group.cuh): the destination slot carries the owning shard + 1 in its top 16 bits, and the sweep
+ * stores the outgoing flux straight into that shard's start-flux buffer through its peer pointer
+ * (NVLink P2P stores from inside the sweep kernel: the role of CPUSolver::transferAllInterfaceFluxes,
+ * src/CPUSolver.cpp:1063-1211, with no pack / send / unpack step). */
+constexpr int PEER_SHIFT = 48;
+constexpr int64_t PEER_SLOT_MASK = ((int64_t)1 << PEER_SHIFT) - 1;
+struct PeerOut { float* p[16]; };
+
 struct SweepArgs {
   /* segment stream, padded by SEG_PAD records at both ends; element i of the
    * logical stream is seg[i] (the pointer already skips the front padding) */
@@ -248,6 +257,7 @@ struct SweepArgs {
   /* fluxes */
   const float* __restrict__ psi_in;
   float* __restrict__ psi_out;
+  PeerOut peer_out;                        /* psi_out of every shard of the group (unused entries NULL) */
   double* __restrict__ phi;                /* tally target [n_fsr*G] */
   /* Tally replicas: CTA b adds into copy (b & rep_mask) of the tally (copies rep_stride
    * elements apart, copy 0 = phi itself) and fold_replicas_kernel sums them after the
@@ -491,12 +501,14 @@ sweep_kernel(const SweepArgs a) {
    * ends feed the next track's start flux; vacuum ends just drop it. */
   const int64_t out = a.out_slot[t * 2 + dir];
   if (out >= 0) {
-    const int64_t base = out * (int64_t)F;
+    const int peer = (int)(out >> PEER_SHIFT);
+    float* __restrict__ dst = peer ? a.peer_out.p[peer - 1] : a.psi_out;
+    const int64_t base = (out & PEER_SLOT_MASK) * (int64_t)F;
 #pragma unroll
     for (int p = 0; p < NP; p++)
 #pragma unroll
       for (int j = 0; j < GPL; j++)
-        if (valid[j]) a.psi_out[base + p * G + e[j]] = psi[p][j];
+        if (valid[j]) dst[base + p * G + e[j]] = psi[p][j];
   } else if (a.leakage != nullptr) {
     /* vacuum end: leakage tally of transferBoundaryFlux (src/CPUSolver.cpp:2592-2600); the
      * reference weighs every flux of a 2D track with the weight of polar index 0 */

@@ -249,12 +249,14 @@ sweep_ls_kernel(const SweepLSArgs la) {
 
   const int64_t out = a.out_slot[t * 2 + dir];
   if (out >= 0) {
-    const int64_t base = out * (int64_t)F;
+    const int peer = (int)(out >> PEER_SHIFT);
+    float* __restrict__ dst = peer ? a.peer_out.p[peer - 1] : a.psi_out;
+    const int64_t base = (out & PEER_SLOT_MASK) * (int64_t)F;
 #pragma unroll
     for (int p = 0; p < NP; p++)
 #pragma unroll
       for (int j = 0; j < GPL; j++)
-        if (valid[j]) a.psi_out[base + p * G + e[j]] = psi[p][j];
+        if (valid[j]) dst[base + p * G + e[j]] = psi[p][j];
   }
 }
 

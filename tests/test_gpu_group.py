@@ -133,3 +133,35 @@ def test_group_refuses_what_it_cannot_do():
     grp = B200Solver(ft, devices=[0, 0])
     with pytest.raises(B200Error, match="neutron balance"):
         grp.setKeffFromNeutronBalance()
+
+
+@pytest.mark.parametrize("devices", device_lists())
+def test_group_track_partition_hands_fluxes_over_through_peer_memory(devices, monkeypatch):
+    """Tracks dealt one by one (forced here; automatic when a deck has few chains, like the fully
+    reflective lattice below): a hand-off whose next track lives on another shard is stored by the sweep
+    kernel straight into that shard's start-flux buffer.  Same iteration count and fluxes as one device -
+    unlike the reference's domain decomposition, the exchanged fluxes do not lag an iteration."""
+    from openmoc_b200.solver import B200Solver
+    from openmoc_b200.synth import make_tracks
+    monkeypatch.setenv("B200_GROUP_PARTITION", "track")
+    for ft, iters in ((load_case("simple_lattice")[0], 500), (make_tracks("c5g7-2d", num_azim=4, spacing=0.5), 40)):
+        one, grp = B200Solver(ft), B200Solver(ft, devices=devices)
+        for s in (one, grp):
+            s.setConvergenceThreshold(1e-5)
+            s.computeEigenvalue(iters, FISSION_SOURCE)
+        assert grp.getNumIterations() == one.getNumIterations()
+        assert abs(grp.getKeff() - one.getKeff()) * 1e5 < 1e-4
+        np.testing.assert_allclose(grp.getFluxes(), one.getFluxes(), rtol=1e-9)
+        np.testing.assert_allclose(grp.getStartFluxes(), one.getStartFluxes(), rtol=1e-5, atol=1e-12)
+
+
+def test_group_more_shards_than_chains_falls_back_to_track_partition():
+    from openmoc_b200.solver import B200Solver
+    from openmoc_b200.synth import make_tracks
+    ft = make_tracks("simple-lattice", num_azim=8, spacing=0.1)          # fully reflective: two chains
+    one, grp = B200Solver(ft), B200Solver(ft, devices=[0] * 5)
+    for s in (one, grp):
+        s.setConvergenceThreshold(1e-5)
+        s.computeEigenvalue(400, FISSION_SOURCE)
+    assert grp.getNumIterations() == one.getNumIterations()
+    np.testing.assert_allclose(grp.getFluxes(), one.getFluxes(), rtol=1e-9)
