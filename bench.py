@@ -412,7 +412,53 @@ def measure(name, args, env, primary):
     solver.close()
     del solver
     torch.cuda.empty_cache()
+    if world > 1 and not args.no_group:
+        res["group"] = measure_group(name, ft, args, env, steps, warmup, W_sweep, precision)
     return res
+
+
+def measure_group(name, ft, args, env, steps, warmup, W_sweep, precision):
+    """The same workload with ALL GPUs of the node behind ONE solver handle in ONE process
+    (b200_set_devices: the library shards the tracks and sums the tallies with its own two-shot
+    all-reduce kernels over NVLink peer memory, no NCCL) - the mode the reference-facing plug-in
+    (B200Solver::setDevices) uses.  Rank 0 drives every GPU while the other ranks, whose own solvers
+    are closed, wait at a barrier."""
+    import torch
+    from openmoc_b200.solver import B200Solver
+    dist, rank, world = env.dist, env.rank, env.world
+    out = None
+    dist.barrier()
+    if rank == 0:
+        try:
+            t0 = time.perf_counter()
+            s = B200Solver(ft, device=0, precision=precision, devices=list(range(world)),
+                           deterministic=args.deterministic)
+            t_setup = time.perf_counter() - t0
+            s.zeroTrackFluxes()
+            s.flattenFSRFluxes(0.0); s.storeFSRFluxes()
+            s.flattenFSRFluxes(1.0); s.normalizeFluxes(); s.storeFSRFluxes()
+            s.iterate(warmup)
+            s.synchronize()
+            s.resetSweepStats()
+            w0 = time.time()
+            t0 = time.perf_counter()
+            s.iterate(steps)
+            s.synchronize()
+            dt = time.perf_counter() - t0
+            env.sampler.windows.append((w0, time.time()))
+            sweep_ms, n_sweeps, launches = s.getSweepStats()
+            out = {"value": W_sweep * steps / dt, "ms_per_step": 1e3 * dt / steps, "steps": steps,
+                   "timed": "host clock around steps enqueued on all devices + synchronize of every device "
+                            "(one process: CUDA events of one stream do not span the group)",
+                   "sweep_kernel_ms_slowest_shard": sweep_ms / max(n_sweeps, 1), "gpu_launches": int(launches),
+                   "k_eff_after_timed_steps": s.getKeff(), "setup_s": round(t_setup, 2),
+                   "collective": "library's own two-shot all-reduce over peer memory (csrc/group.cuh)"}
+            s.close()
+        except Exception as e:
+            out = {"error": repr(e)}
+        torch.cuda.empty_cache()
+    dist.barrier()
+    return out
 
 
 def parity_check(workload, cb, env):
@@ -466,6 +512,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--partition", default="pair", choices=["pair", "chain", "track"])
     ap.add_argument("--deterministic", action="store_true")
+    ap.add_argument("--no-group", action="store_true", help="skip the one-process all-GPU measurement at N > 1")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
