@@ -577,6 +577,7 @@ def main():
             "e2e": main_res["e2e"],
             "gpu_launches": main_res["gpu_launches"],
             "clocks": clocks,
+            "group": main_res.get("group"),
             "workloads": others,
         }
         print(json.dumps(line))
