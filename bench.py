@@ -427,7 +427,10 @@ def measure_group(name, ft, args, env, steps, warmup, W_sweep, precision):
     from openmoc_b200.solver import B200Solver
     dist, rank, world = env.dist, env.rank, env.world
     out = None
-    dist.barrier()
+    # the waiting ranks must not sit in an NCCL barrier: its kernel spins ON THEIR GPU and would time-slice
+    # with the shard rank 0 runs there.  A gloo barrier waits on the CPU.
+    torch.cuda.synchronize()
+    dist.barrier(group=env.cpu_group)
     if rank == 0:
         try:
             t0 = time.perf_counter()
@@ -457,7 +460,7 @@ def measure_group(name, ft, args, env, steps, warmup, W_sweep, precision):
         except Exception as e:
             out = {"error": repr(e)}
         torch.cuda.empty_cache()
-    dist.barrier()
+    dist.barrier(group=env.cpu_group)
     return out
 
 
@@ -534,6 +537,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", env.local_rank))
         env.dist = dist
+        env.cpu_group = dist.new_group(backend="gloo")
     env.fp64_rate, env.red_rate = capi.measure_ceilings(env.local_rank, 23869)
     env.sampler = ClockSampler(env.local_rank)
     if env.rank == 0:
