@@ -229,21 +229,26 @@ static int grp_finalize(b200_solver* s) {
     }
   }
   if (!g->have_volume) return fail("b200_finalize: no FSR volumes (b200_upload_fsrs with volume = NULL needs b200_otf_compute_volumes)");
-  /* Partition.  Whole chains when there are enough of them (no angular flux ever crosses a shard);
-   * otherwise single tracks, dealt in a snake by decreasing load - any number of shards, also for fully
-   * reflective decks whose tracks form a handful of cycles - with the hand-offs that cross shards stored
-   * by the sweep kernel straight into the owner's start-flux buffer over peer memory (sweep.cuh: PeerOut).
-   * B200_GROUP_PARTITION=chain|track overrides. */
+  /* Partition.  2D decks: whole chains when there are enough of them (no angular flux ever crosses a
+   * shard); otherwise single tracks, dealt in a snake by decreasing load - any number of shards, also for
+   * fully reflective decks whose tracks form a handful of cycles.  Whenever tracks are not sharded by
+   * chain, the hand-offs that cross shards are stored by the sweep kernel straight into the owner's
+   * start-flux buffer over peer memory (sweep.cuh: PeerOut).  B200_GROUP_PARTITION=chain|track|block overrides. */
   std::vector<int32_t> owner;
   const int64_t n_chains = partition_chains(nt, g->next_fwd.data(), g->next_bwd.data(), g->bc_fwd.data(), g->bc_bwd.data(),
                                             load.data(), N, owner);
-  bool by_track = n_chains < (int64_t)4 * N;
+  /* 3D decks: contiguous blocks of the Track uid order (azimuthal angle, 2D track, polar angle, z),
+   * cut where the cumulative load crosses k/N: every shard then sweeps whole neighbouring z-stacks one
+   * after the other like a single GPU does and its FSR rows stay in L2 (a chain deal spreads the millions
+   * of short chains of a 3D deck with vacuum sides all over the core). */
+  enum { CHAIN, TRACK, BLOCK } mode = s->cfg.solve_3d ? BLOCK : (n_chains < (int64_t)4 * N ? TRACK : CHAIN);
   if (const char* e = getenv("B200_GROUP_PARTITION")) {
-    if (!strcmp(e, "track")) by_track = true;
-    if (!strcmp(e, "chain")) by_track = false;
+    if (!strcmp(e, "track")) mode = TRACK;
+    if (!strcmp(e, "chain")) mode = CHAIN;
+    if (!strcmp(e, "block")) mode = BLOCK;
   }
-  if (!by_track && n_chains < N) return fail("b200_finalize: %d shards but only %lld independent track chains", N, (long long)n_chains);
-  if (by_track) {
+  if (mode == CHAIN && n_chains < N) return fail("b200_finalize: %d shards but only %lld independent track chains", N, (long long)n_chains);
+  if (mode == TRACK) {
     std::vector<int64_t> order(nt);
     std::iota(order.begin(), order.end(), (int64_t)0);
     std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return load[a] > load[b]; });
@@ -251,6 +256,15 @@ static int grp_finalize(b200_solver* s) {
     for (int64_t i = 0; i < nt; i++) {
       const int64_t pos = i % (2 * N);
       owner[order[i]] = (int32_t)(pos < N ? pos : 2 * N - 1 - pos);
+    }
+  } else if (mode == BLOCK) {
+    double total = 0., cum = 0.;
+    for (int64_t t = 0; t < nt; t++) total += load[t] + 1e-9;
+    owner.assign(nt, 0);
+    for (int64_t t = 0; t < nt; t++) {
+      const double l = load[t] + 1e-9;
+      cum += l;
+      owner[t] = (int32_t)std::min<double>(N - 1, (cum - 0.5 * l) * N / total);
     }
   }
   g->cross_links = false;

@@ -187,11 +187,23 @@ def assign_tracks(ft: FlatTracks, world: int) -> np.ndarray:
     """Owner rank per track: tracks sorted by segment count and dealt in a snake
     (0..w-1, w-1..0, ...), so every rank gets the same number of segments to within one
     track and the same mix of long and short tracks - for any number of ranks."""
-    nseg = np.diff(ft.arrays["trk_seg_offset"].astype(np.int64))
+    nseg = track_load(ft)
     order = np.argsort(-nseg, kind="stable")
     pos = np.arange(ft.n_tracks) % (2 * world)
     owner = np.empty(ft.n_tracks, dtype=np.int64)
     owner[order] = np.where(pos < world, pos, 2 * world - 1 - pos)
+    return owner
+
+
+def assign_blocks(ft: FlatTracks, world: int) -> np.ndarray:
+    """Owner rank per track: contiguous blocks of the Track uid order (azimuthal angle, 2D track,
+    polar angle, position in the z-stack), cut where the cumulative load crosses k/world.  Every rank
+    then sweeps whole neighbouring z-stacks one after the other, exactly like a single GPU does, so the
+    FSR rows its resident tracks touch stay in L2 (a chain partition deals the chains of a 3D deck with
+    vacuum sides - millions of them - all over the core: 8 GPUs, 7.9 ms per sweep instead of 6.1)."""
+    load = track_load(ft) + 1e-9
+    cum = np.cumsum(load)
+    owner = np.minimum((cum - 0.5 * load) * world / cum[-1], world - 1).astype(np.int64)
     return owner
 
 
@@ -263,9 +275,13 @@ def partition_by_track(ft: FlatTracks, world: int, owner: np.ndarray = None, onl
         b["trk_next_fwd"], b["trk_next_bwd"], b["trk_flags"] = nf, nb, fl
         for key, fill in (("trk_next_fwd", -1), ("trk_next_bwd", -1), ("trk_flags", 0), ("trk_bc_fwd", 0),
                           ("trk_bc_bwd", 0), ("trk_azim", 0), ("trk_polar", 0), ("trk_xy", 0),
-                          ("trk_phi", 0.0), ("trk_theta", 0.0)):
+                          ("trk_phi", 0.0), ("trk_theta", 0.0), ("trk_2d", 0), ("trk_lz", 0),
+                          ("trk_l0", 1e300)):      # on-the-fly ghost: starts beyond its 2D track, no segments
             if key in b:
                 pad(key, fill)
+        for key in ("trk_start", "trk_end"):
+            if key in b and n_loc and b[key].size % n_loc == 0:
+                b[key] = np.concatenate([b[key], np.zeros(n_ghost * (b[key].size // n_loc), dtype=b[key].dtype)])
         b["trk_seg_offset"] = np.concatenate([b["trk_seg_offset"],
                                               np.full(n_ghost, b["trk_seg_offset"][-1], dtype=np.int64)])
         sub.n_tracks = n_loc + n_ghost

@@ -53,7 +53,8 @@ class B200Solver:
                                partition); "chain": whole track chains, balanced by segments;
                                "track": single tracks dealt by length, any number of ranks, the
                                boundary fluxes that cross ranks are exchanged after every sweep
-                               (NCCL send/recv)
+                               (NCCL send/recv); "block": the same exchange with contiguous blocks
+                               of the Track uid order per rank (3D decks: L2 locality of the FSR rows)
     deterministic : bool       accumulate the FSR tally in 64-bit fixed point: results are
                                bitwise reproducible run to run (and across GPU counts)
     devices : optional         list of CUDA device ordinals: ONE solver handle drives them all (b200_set_devices);
@@ -107,8 +108,12 @@ class B200Solver:
                 tracks = partition_by_azim_pair(tracks, self._world, only=self._rank)[self._rank]
             elif partition == "track":
                 tracks, self._plan = partition_by_track(tracks, self._world, only=self._rank)[self._rank]
+            elif partition == "block":
+                from .partition import assign_blocks
+                tracks, self._plan = partition_by_track(tracks, self._world, owner=assign_blocks(tracks, self._world),
+                                                        only=self._rank)[self._rank]
             else:
-                raise B200Error("unknown partition %r (pair, chain, track)" % partition)
+                raise B200Error("unknown partition %r (pair, chain, track, block)" % partition)
         if self._linear:
             self._ls_tables = (np.ascontiguousarray(tracks.arrays["seg_start"], dtype="f8"),
                                np.ascontiguousarray(track_directions(tracks).ravel(), dtype="f8"),
