@@ -160,6 +160,12 @@ struct b200_solver {
   DevBuf<double> ls_seg_start, ls_trk_dir, ls_lin_exp, ls_src_const, phi_m, mom_stage;
   DevBuf<double4> seg_pos, qxyz;
   DevBuf<double2> qst;
+  /* padded private copies of the sweep (sweep.cuh: pack_pad_kernel) */
+  int GP = 0;                        /* row pitch in groups; == G: no padding */
+  bool padded = false;
+  DevBuf<double2> qst_pad;
+  DevBuf<double4> qxyz_pad;
+  DevBuf<double> tally_pad, tallym_pad;
   DevBuf<float> psi_a, psi_b;
   float* psi_start = nullptr;  /* what the next sweep reads (= reference _start_flux) */
   float* psi_other = nullptr;
@@ -374,6 +380,14 @@ extern "C" int b200_create(const b200_config* cfg, b200_solver** out) {
   s->n_mat = cfg->n_materials;
   s->linear = cfg->linear_source != 0;
   s->nc = cfg->solve_3d ? 6 : 3;
+  /* padded FSR rows (sweep.cuh: pack_pad_kernel), an experiment kept behind B200_PAD=1 */
+  s->GP = s->G;
+  {
+    bool pad = false;     /* measured on the B200: 3D C5G7 48.7 -> 48.5 ms, 2D LS 0.655 -> 0.696 ms: off by default */
+    if (const char* e = getenv("B200_PAD")) pad = atoi(e) != 0 && s->G % 8 != 0;
+    if (pad) s->GP = (s->G + 7) & ~7;
+    s->padded = s->GP != s->G;
+  }
   e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete s; return fail("cudaStreamCreate: %s", cudaGetErrorString(e)); }
   s->own_stream = true;
@@ -411,6 +425,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   s->otf_seg2d_len.release(); s->otf_mesh.release(); s->otf_l0.release(); s->otf_z0.release(); s->otf_cos.release();
   s->otf_sin.release(); s->otf_volw.release(); s->otf_seg2d_ext.release(); s->otf_ext_fsr.release(); s->otf_trk2d.release();
   s->otf_cls.release(); s->otf_count.release(); s->otf_trk2d_off.release(); s->otf_ext_off.release();
+  s->qst_pad.release(); s->qxyz_pad.release(); s->tally_pad.release(); s->tallym_pad.release();
   s->phi_old.release(); s->fixed.release(); s->stab.release(); s->scratch.release();
   s->qst.release(); s->psi_a.release(); s->psi_b.release(); s->scal.release();
   s->partials.release(); s->hist_k.release(); s->hist_res.release(); s->iscal.release();
@@ -912,7 +927,7 @@ extern "C" int b200_upload_tracks_otf(b200_solver* s, const int32_t* trk_2d, con
   otf_pad_kernel<<<1, 2 * SEG_PAD, 0, s->stream>>>(s->seg_rec.p, ns);
   CU(cudaGetLastError());
   if (nt > 0) {
-    otf_fill_kernel<<<grid_for(nt, 128, 1 << 20), 128, 0, s->stream>>>(g, s->trk_off.p, s->seg_rec.p + SEG_PAD, s->G, nullptr, nullptr);
+    otf_fill_kernel<<<grid_for(nt, 128, 1 << 20), 128, 0, s->stream>>>(g, s->trk_off.p, s->seg_rec.p + SEG_PAD, s->GP, nullptr, nullptr);
     CU(cudaGetLastError());
   }
   s->h_azim.assign(trk_azim, trk_azim + nt);
@@ -953,7 +968,7 @@ extern "C" int b200_get_segments(b200_solver* s, double* seg_length, int32_t* se
   struct Tmp { void* p = nullptr; ~Tmp() { if (p) cudaFree(p); } } dl, df;
   CU(cudaMalloc(&dl.p, n * 8));
   CU(cudaMalloc(&df.p, n * 4));
-  otf_unpack_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->seg_rec.p + SEG_PAD, n, s->G, (double*)dl.p, (int32_t*)df.p);
+  otf_unpack_kernel<<<grid_for(n, 256), 256, 0, s->stream>>>(s->seg_rec.p + SEG_PAD, n, s->GP, (double*)dl.p, (int32_t*)df.p);
   CU(cudaGetLastError());
   if (seg_length) CU(cudaMemcpyAsync(seg_length, dl.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
   if (seg_fsr) CU(cudaMemcpyAsync(seg_fsr, df.p, n * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -1085,8 +1100,9 @@ extern "C" int b200_finalize(b200_solver* s) {
       const int v = atoi(e);
       if (v >= 1 && v <= 1024 && (v & (v - 1)) == 0) R = v;
     }
-    while (R > 1 && (double)nphi * 8.0 * (s->linear ? 4.0 : 1.0) * R > 256e6) R /= 2;
-    while (R > 1 && (double)nphi * R * (s->linear ? 3.0 : 1.0) >= 4294967296.0) R /= 2;   /* 32-bit tally index incl. replica */
+    const double nphi_pad_d = (double)s->n_fsr * s->GP;
+    while (R > 1 && nphi_pad_d * 8.0 * (s->linear ? 4.0 : 1.0) * R > 256e6) R /= 2;
+    while (R > 1 && nphi_pad_d * R * (s->linear ? 3.0 : 1.0) >= 4294967296.0) R /= 2;   /* 32-bit tally index incl. replica */
     s->n_rep = R;
   }
   CU(s->phi.alloc(nphi * s->n_rep)); CU(s->phi_old.alloc(nphi)); CU(s->fixed.alloc(nphi));
@@ -1095,9 +1111,16 @@ extern "C" int b200_finalize(b200_solver* s) {
   CU(s->leakage.alloc(std::max<size_t>(nt, 1)));
   CU(cudaMemsetAsync(s->leakage.p, 0, std::max<size_t>(nt, 1) * 4, s->stream));
   CU(s->part3.alloc(3 * MAX_PARTIALS));
+  const size_t nphi_pad = (size_t)s->n_fsr * s->GP;
+  if (s->padded) {
+    CU(s->qst_pad.alloc(nphi_pad));
+    CU(cudaMemsetAsync(s->qst_pad.p, 0, nphi_pad * 16, s->stream));
+    CU(s->tally_pad.alloc(nphi_pad * s->n_rep));
+    CU(cudaMemsetAsync(s->tally_pad.p, 0, nphi_pad * s->n_rep * 8, s->stream));
+  }
   if (s->cfg.deterministic) {
-    CU(s->phi_fx.alloc(nphi * s->n_rep)); CU(s->fx_bits.alloc(4));
-    CU(cudaMemsetAsync(s->phi_fx.p, 0, nphi * s->n_rep * 8, s->stream));
+    CU(s->phi_fx.alloc(nphi_pad * s->n_rep)); CU(s->fx_bits.alloc(4));
+    CU(cudaMemsetAsync(s->phi_fx.p, 0, nphi_pad * s->n_rep * 8, s->stream));
     CU(cudaMemsetAsync(s->fx_bits.p, 0, 4 * 8, s->stream));
   }
   CU(cudaMemsetAsync(s->phi.p, 0, nphi * s->n_rep * 8, s->stream));
@@ -1113,13 +1136,13 @@ extern "C" int b200_finalize(b200_solver* s) {
   s->psi_other = s->psi_b.p;
 
   /* device segment stream: padded 16-byte records with the FSR id premultiplied by G */
-  if ((double)s->n_fsr * s->G * (s->linear ? 3.0 : 1.0) >= 4294967296.0)
-    return fail("b200_finalize: n_fsrs*G = %.3g exceeds the 32-bit tally index of this build", (double)s->n_fsr * s->G);
+  if ((double)s->n_fsr * s->GP * (s->linear ? 3.0 : 1.0) >= 4294967296.0)
+    return fail("b200_finalize: n_fsrs*G = %.3g exceeds the 32-bit tally index of this build", (double)s->n_fsr * s->GP);
   if (!s->seg_rec_ready) {
     if (s->seg_len.n != (size_t)s->n_seg) return fail("b200_finalize: tracks must be re-uploaded before finalize");
     CU(s->seg_rec.alloc((size_t)s->n_seg + 2 * SEG_PAD));
     build_segrec_kernel<<<grid_for(s->n_seg + 2 * SEG_PAD, 256), 256, 0, s->stream>>>(
-        s->seg_rec.p, s->seg_len.p, s->seg_fsr.p, s->n_seg, s->G);
+        s->seg_rec.p, s->seg_len.p, s->seg_fsr.p, s->n_seg, s->GP);
     CU(cudaGetLastError());
   }
 
@@ -1133,6 +1156,12 @@ extern "C" int b200_finalize(b200_solver* s) {
     CU(s->qxyz.alloc(nphi));
     CU(cudaMemsetAsync(s->phi_m.p, 0, nphi * 3 * s->n_rep * 8, s->stream));
     CU(cudaMemsetAsync(s->qxyz.p, 0, nphi * 32, s->stream));
+    if (s->padded) {
+      CU(s->qxyz_pad.alloc(nphi_pad));
+      CU(cudaMemsetAsync(s->qxyz_pad.p, 0, nphi_pad * 32, s->stream));
+      CU(s->tallym_pad.alloc(nphi_pad * 3 * s->n_rep));
+      CU(cudaMemsetAsync(s->tallym_pad.p, 0, nphi_pad * 3 * s->n_rep * 8, s->stream));
+    }
   }
 
   choose_lane_map(s->G, &s->gpl, &s->lpi, &s->ipc);
@@ -1221,14 +1250,26 @@ static int launch_sweep(b200_solver* s) {
     if (take_events(s, &e0, &e1)) return 1;
     CU(cudaEventRecord(e0, s->stream));
   }
-  /* flattenFSRFluxes(0) (CPUSolver.cpp:2347), skipped once the device-side loop has converged */
-  zero_phi_kernel<<<grid_for(nphi, 256), 256, 0, s->stream>>>(s->phi.p, (int64_t)nphi, s->iscal.p);
-  CU(cudaGetLastError());
-  s->n_launches++;
-  if (s->linear) {
-    zero_phi_kernel<<<grid_for(nphi * 3, 256), 256, 0, s->stream>>>(s->phi_m.p, (int64_t)nphi * 3, s->iscal.p);
+  const size_t nphi_pad = (size_t)s->n_fsr * s->GP;
+  const bool pad_tally = s->padded && !s->cfg.deterministic;   /* the fixed-point tally is padded in place */
+  if (s->padded) {
+    /* sources into the padded private copy (its tallies were cleared by the previous unpack) */
+    pack_pad_kernel<<<grid_for((int64_t)nphi_pad, 256), 256, 0, s->stream>>>(
+        s->qst.p, s->qst_pad.p, s->linear ? s->qxyz.p : nullptr, s->linear ? s->qxyz_pad.p : nullptr, s->n_fsr, s->G, s->GP,
+        s->iscal.p + SI_DONE);
     CU(cudaGetLastError());
     s->n_launches++;
+  }
+  if (!pad_tally || s->n_trk == 0) {
+    /* flattenFSRFluxes(0) (CPUSolver.cpp:2347), skipped once the device-side loop has converged */
+    zero_phi_kernel<<<grid_for(nphi, 256), 256, 0, s->stream>>>(s->phi.p, (int64_t)nphi, s->iscal.p);
+    CU(cudaGetLastError());
+    s->n_launches++;
+    if (s->linear) {
+      zero_phi_kernel<<<grid_for(nphi * 3, 256), 256, 0, s->stream>>>(s->phi_m.p, (int64_t)nphi * 3, s->iscal.p);
+      CU(cudaGetLastError());
+      s->n_launches++;
+    }
   }
   if (s->cfg.deterministic) {
     FsrArgs fa = fsr_args(s);
@@ -1243,10 +1284,11 @@ static int launch_sweep(b200_solver* s) {
     a.seg = s->seg_rec.p + SEG_PAD; a.trk_off = s->trk_off.p;
     a.trk_class = s->trk_class.p; a.order = s->order.p; a.out_slot = s->out_slot.p;
     a.carry = s->carry.p; a.cls_w = s->cls_w.p; a.cls_inv_sin = s->cls_inv_sin.p;
-    a.qst = s->qst.p; a.psi_in = s->psi_start; a.psi_out = s->psi_other; a.phi = s->phi.p;
+    a.qst = s->padded ? s->qst_pad.p : s->qst.p; a.psi_in = s->psi_start; a.psi_out = s->psi_other;
+    a.phi = pad_tally ? s->tally_pad.p : s->phi.p;
     for (int j = 0; j < 16; j++) a.peer_out.p[j] = j < (int)s->peer_out.size() ? s->peer_out[j] : nullptr;
     a.phi_fx = s->phi_fx.p; a.fx_scale = s->scal.p + SC_FXSCALE;
-    a.rep_stride = (int64_t)nphi; a.rep_mask = s->n_rep - 1;
+    a.rep_stride = (int64_t)nphi_pad; a.rep_mask = s->n_rep - 1;
     a.leakage = s->balance ? s->leakage.p : nullptr;
     a.seg_cmfd = nullptr; a.cmfd_group = nullptr; a.currents = nullptr; a.ncg = 0;
     if (s->cmfd_on) {
@@ -1290,8 +1332,8 @@ static int launch_sweep(b200_solver* s) {
       la.f = a;
       la.seg_pos = s->seg_pos.p + SEG_PAD;
       la.trk_dir = s->ls_trk_dir.p;
-      la.qxyz = s->qxyz.p;
-      la.phi_m = s->phi_m.p;
+      la.qxyz = s->padded ? s->qxyz_pad.p : s->qxyz.p;
+      la.phi_m = s->padded ? s->tallym_pad.p : s->phi_m.p;
       /* expG_fractional coefficients p0..p5, d1..d6 (src/exponentials.h:113-127) */
       const double cg[12] = {0.5, 1.76558112351595e-1, 4.041584305811143e-2, 6.178333902037397e-3,
                              6.429894635552992e-4, 6.064409107557148e-5, 6.864462055546078e-1,
@@ -1314,7 +1356,12 @@ static int launch_sweep(b200_solver* s) {
       lfn<<<(unsigned)s->sweep_blocks, nthr, 0, s->stream>>>(la);
       CU(cudaGetLastError());
       s->n_launches++;
-      if (s->n_rep > 1) {
+      if (s->padded) {
+        unpack_pad_kernel<<<grid_for(nphi * 3, 256), 256, 0, s->stream>>>(s->tallym_pad.p, s->phi_m.p, s->n_fsr, s->G, s->GP, 3,
+                                                                         s->n_rep, s->iscal.p + SI_DONE);
+        CU(cudaGetLastError());
+        s->n_launches++;
+      } else if (s->n_rep > 1) {
         fold_replicas_kernel<double><<<grid_for(nphi * 3, 256), 256, 0, s->stream>>>(
             s->phi_m.p, (int64_t)nphi * 3, (int64_t)nphi * 3, s->n_rep);
         CU(cudaGetLastError());
@@ -1336,10 +1383,15 @@ static int launch_sweep(b200_solver* s) {
     CU(cudaGetLastError());
     s->n_launches++;
     }
-    if (s->n_rep > 1) {
+    if (pad_tally) {
+      unpack_pad_kernel<<<grid_for(nphi, 256), 256, 0, s->stream>>>(s->tally_pad.p, s->phi.p, s->n_fsr, s->G, s->GP, 1, s->n_rep,
+                                                                   s->iscal.p + SI_DONE);
+      CU(cudaGetLastError());
+      s->n_launches++;
+    } else if (s->n_rep > 1) {
       if (s->cfg.deterministic)
-        fold_replicas_kernel<unsigned long long><<<grid_for(nphi, 256), 256, 0, s->stream>>>(
-            s->phi_fx.p, (int64_t)nphi, (int64_t)nphi, s->n_rep);
+        fold_replicas_kernel<unsigned long long><<<grid_for(nphi_pad, 256), 256, 0, s->stream>>>(
+            s->phi_fx.p, (int64_t)nphi_pad, (int64_t)nphi_pad, s->n_rep);
       else
         fold_replicas_kernel<double><<<grid_for(nphi, 256), 256, 0, s->stream>>>(
             s->phi.p, (int64_t)nphi, (int64_t)nphi, s->n_rep);
@@ -1348,7 +1400,7 @@ static int launch_sweep(b200_solver* s) {
     }
   }
   if (s->cfg.deterministic && !s->defer_fx_convert) {
-    fx_to_double_kernel<<<grid_for(nphi, 256), 256, 0, s->stream>>>(fsr_args(s), s->phi_fx.p);
+    fx_to_double_kernel<<<grid_for(nphi, 256), 256, 0, s->stream>>>(fsr_args(s), s->phi_fx.p, s->GP);
     CU(cudaGetLastError());
     s->n_launches++;
   }
@@ -2233,7 +2285,7 @@ extern "C" int b200_device_pointer(b200_solver* s, const char* name, void** ptr,
   }
   else if (!strcmp(name, "scalar_flux_fixed")) {
     if (!s->cfg.deterministic) return fail("b200_device_pointer: 'scalar_flux_fixed' exists in deterministic mode only");
-    *ptr = s->phi_fx.p; *n = nphi;
+    *ptr = s->phi_fx.p; *n = s->n_fsr * s->GP;
   }
   else return fail("b200_device_pointer: unknown array '%s'", name);
   return 0;
@@ -2252,7 +2304,7 @@ extern "C" int b200_finish_fixed_tally(b200_solver* s) {
   NEED_FINAL(s);
   GRP_ALL(s, b200_finish_fixed_tally(c));
   if (!s->cfg.deterministic) return fail("b200_finish_fixed_tally: deterministic mode only");
-  fx_to_double_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(fsr_args(s), s->phi_fx.p);
+  fx_to_double_kernel<<<grid_for(s->n_fsr * s->G, 256), 256, 0, s->stream>>>(fsr_args(s), s->phi_fx.p, s->GP);
   CU(cudaGetLastError());
   s->n_launches++;
   return 0;

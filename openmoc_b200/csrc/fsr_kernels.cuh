@@ -482,13 +482,16 @@ __global__ void fx_scale_kernel(const FsrArgs a, unsigned long long* __restrict_
   a.scal[SC_FXSCALE] = ldexp(1.0, 62 - 5 - ex);
   bits[0] = bits[1] = bits[2] = 0ull;
 }
-__global__ void fx_to_double_kernel(const FsrArgs a, unsigned long long* __restrict__ fx) {
+/* GP: row pitch of the fixed-point tally (padded rows, sweep.cuh) */
+__global__ void fx_to_double_kernel(const FsrArgs a, unsigned long long* __restrict__ fx, int GP) {
   if (a.iscal[SI_DONE]) return;
   const double inv = 1.0 / a.scal[SC_FXSCALE];
   const int64_t n = a.n_fsr * a.G;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    a.phi[i] = (double)(long long)fx[i] * inv;
-    fx[i] = 0ull;
+    const int64_t r = i / a.G;
+    const int64_t j = r * GP + (i - r * a.G);
+    a.phi[i] = (double)(long long)fx[j] * inv;
+    fx[j] = 0ull;
   }
 }
 

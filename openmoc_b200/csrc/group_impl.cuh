@@ -65,7 +65,7 @@ static int grp_reduce(b200_solver* s) {
   b200_solver* c0 = g->shard[0];
   const size_t nphi = (size_t)c0->n_fsr * c0->G;
   std::vector<GrpTally> tallies;
-  if (c0->cfg.deterministic) tallies.push_back({'x', nphi}); else tallies.push_back({'p', nphi});
+  if (c0->cfg.deterministic) tallies.push_back({'x', (size_t)c0->n_fsr * c0->GP}); else tallies.push_back({'p', nphi});
   if (c0->linear) tallies.push_back({'m', 3 * nphi});
   if (c0->cmfd_on) tallies.push_back({'c', (size_t)c0->n_cmfd_slots * c0->ncg});
   size_t total = 0;
@@ -144,7 +144,7 @@ static int grp_sweep(b200_solver* s) {
   for (b200_solver* c : grp_shards(s))
     if (c->cfg.deterministic) {
       CU(cudaSetDevice(c->cfg.device));
-      fx_to_double_kernel<<<grid_for(c->n_fsr * c->G, 256), 256, 0, c->stream>>>(fsr_args(c), c->phi_fx.p);
+      fx_to_double_kernel<<<grid_for(c->n_fsr * c->G, 256), 256, 0, c->stream>>>(fsr_args(c), c->phi_fx.p, c->GP);
       CU(cudaGetLastError());
       c->n_launches++;
     }

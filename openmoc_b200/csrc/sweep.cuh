@@ -523,6 +523,46 @@ sweep_kernel(const SweepArgs a) {
 }
 
 
+/* ---- padded FSR rows ------------------------------------------------------------------
+ * With G = 7 a row of {q, sigma_t} pairs is 112 bytes and a tally row 56 bytes: laid end to end, 87 %
+ * of the gathers and 43 % of the tallies of a 7-lane item straddle two 128-byte lines, and every line a
+ * warp instruction touches is one more pass through the L1 data stage (the 3D sweep keeps that stage
+ * 81 % busy, profiles/r02_sweep3d.md).  The RED-bound sweeps (3D, linear source) therefore work on
+ * private copies whose rows are padded to GP = 8 groups (128-byte / 64-byte aligned): pack_pad_kernel
+ * copies the sources in before the sweep, unpack_pad_kernel sums the tally replicas back into the
+ * solver's [r*G + e] arrays afterwards (and clears them for the next sweep). */
+__global__ void pack_pad_kernel(const double2* __restrict__ qst, double2* __restrict__ qst_pad,
+                                const double4* __restrict__ qxyz, double4* __restrict__ qxyz_pad,
+                                int64_t n_fsr, int G, int GP, const int* __restrict__ done) {
+  if (done != nullptr && *done) return;
+  const int64_t n = n_fsr * GP;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / GP;
+    const int e = (int)(i - r * GP);
+    if (e < G) {
+      qst_pad[i] = qst[r * G + e];
+      if (qxyz != nullptr) qxyz_pad[i] = qxyz[r * G + e];
+    }
+  }
+}
+/* dst[plane][r*G + e] = sum over replicas of pad[rep][plane][r*GP + e]; the padded copies are cleared */
+__global__ void unpack_pad_kernel(double* __restrict__ pad, double* __restrict__ dst, int64_t n_fsr, int G, int GP,
+                                  int n_planes, int n_rep, const int* __restrict__ done) {
+  if (done != nullptr && *done) return;
+  const int64_t nphi = n_fsr * G, nphi_pad = n_fsr * GP, n = nphi * n_planes;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i / nphi, k = i - c * nphi, r = k / G;
+    const int e = (int)(k - r * G);
+    const int64_t j = c * nphi_pad + r * GP + e;
+    double sum = 0.0;
+    for (int rep = 0; rep < n_rep; rep++) {
+      sum += pad[(int64_t)rep * n_planes * nphi_pad + j];
+      pad[(int64_t)rep * n_planes * nphi_pad + j] = 0.0;
+    }
+    dst[i] = sum;
+  }
+}
+
 /* builds the padded SegRec stream from the uploaded SoA arrays (once per upload) */
 __global__ void build_segrec_kernel(SegRec* __restrict__ out, const double* __restrict__ len,
                                     const int32_t* __restrict__ fsr, int64_t n_seg, int G) {

@@ -320,4 +320,149 @@ sweep_kernel_staged(const SweepArgs a) {
   }
 }
 
+
+/* Round 2: the ring variant brought up to date (tally replicas, peer hand-offs) and tried on the 3D C5G7
+ * deck (1.06e9 segments, one polar angle per track), where 46 % of the stall samples of sweep_kernel sit on
+ * the long-scoreboard wait for the {q, sigma_t} gather: 47.9 ms (sweep_kernel) against 56.9 / 72.5 / 134 ms
+ * with 4 / 5 / 6 resident CTAs per SM (72 / 56 / 40 registers, 24 / 80 / 168 bytes of spills).  Rejected. */
+/* ------------------------------------------------------------------------------------
+ * Deep-pipeline variant for the latency-bound sweeps (3D tracks: one polar angle per track, so a
+ * segment is ~110 instructions of one warp and the {q, sigma_t} gather issued one segment ahead by
+ * sweep_kernel is not back in time: 46 % of the stall samples of the 3D C5G7 sweep sit on that
+ * long-scoreboard wait, profiles/r02_sweep3d.md).  Here the records travel three segments ahead and
+ * the gathers two, through a 4-slot register ring whose rotation is unrolled away; MINB trades
+ * registers for resident warps.  Plain double tally only (no fixed-point tally, no CMFD currents).
+ * ------------------------------------------------------------------------------------ */
+template <typename T, int NP, int GPL, int MINB>
+__global__ void __launch_bounds__(224, MINB)
+sweep_kernel_deep(const SweepArgs a) {
+  if (a.done != nullptr && *a.done) return;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t item = gtid / a.lpi;
+  const int sub = (int)(gtid - item * a.lpi);
+  if (item >= a.n_items) return;
+
+  const int G = a.G;
+  const int64_t t = a.order[item >> 1];
+  const int dir = (int)(item & 1);
+  const int64_t s0 = a.trk_off[t], s1 = a.trk_off[t + 1];
+  const int n = (int)(s1 - s0);
+  const int cls = a.trk_class[t];
+
+  uint32_t e[GPL];
+  bool valid[GPL];
+#pragma unroll
+  for (int j = 0; j < GPL; j++) {
+    int ej = sub + j * a.lpi;
+    valid[j] = a.exact || ej < G;
+    e[j] = (uint32_t)(valid[j] ? ej : G - 1);
+  }
+  T w[NP], inv_sin[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    w[p] = (T)a.cls_w[cls * NP + p];
+    inv_sin[p] = (T)a.cls_inv_sin[cls * NP + p];
+  }
+  const int F = G * NP;
+  const int64_t slot_in = (t * 2 + dir) * (int64_t)F;
+  float psi[NP][GPL];
+#pragma unroll
+  for (int p = 0; p < NP; p++)
+#pragma unroll
+    for (int j = 0; j < GPL; j++) psi[p][j] = a.psi_in[slot_in + p * G + e[j]];
+  if (a.carry[t * 2 + dir]) {
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+      for (int j = 0; j < GPL; j++)
+        if (valid[j]) a.psi_out[slot_in + p * G + e[j]] = psi[p][j];
+  }
+  double acc[GPL];
+#pragma unroll
+  for (int j = 0; j < GPL; j++) acc[j] = 0.0;
+
+  const int step = dir ? -1 : 1;
+  const SegRec* __restrict__ ps = a.seg + (dir ? s1 - 1 : s0);   /* record of step 0 */
+  const double2* __restrict__ const qst = a.qst;
+  double* __restrict__ const phi = a.phi;
+  const uint32_t rep_idx = (uint32_t)(blockIdx.x & a.rep_mask) * (uint32_t)a.rep_stride;
+  uint32_t et[GPL];
+#pragma unroll
+  for (int j = 0; j < GPL; j++) et[j] = e[j] + rep_idx;
+
+  /* ring slots: records of steps k..k+3, gathers of steps k..k+2 */
+  int4 R0, R1, R2, R3;
+  double2 Q0[GPL], Q1[GPL], Q2[GPL], Q3[GPL];
+  R0 = ld_rec(ps);
+  R1 = ld_rec(ps + step);
+  R2 = ld_rec(ps + 2 * step);
+#pragma unroll
+  for (int j = 0; j < GPL; j++) {
+    Q0[j] = ld_qs(&qst[(uint32_t)R0.z + e[j]]);
+    Q1[j] = ld_qs(&qst[(uint32_t)R1.z + e[j]]);
+  }
+  ps += 3 * step;                                               /* next record to load */
+
+#define B200_DEEP_STEP(RC, QC, RN, RN2, QN2, RN3, LAST)                                        \
+  {                                                                                            \
+    RN3 = ld_rec(ps);                                                                          \
+    ps += step;                                                                                \
+    _Pragma("unroll") for (int j = 0; j < GPL; j++) QN2[j] = ld_qs(&qst[(uint32_t)RN2.z + e[j]]); \
+    const T len = (T)__hiloint2double(RC.y, RC.x);                                             \
+    const uint32_t bc = (uint32_t)RC.z;                                                        \
+    const bool flush = ((uint32_t)RN.z != bc) || (LAST);                                       \
+    _Pragma("unroll") for (int j = 0; j < GPL; j++) {                                          \
+      const T tau = (T)QC[j].y * len;                                                          \
+      const T lq = len * (T)QC[j].x;                                                           \
+      T x[NP], f1[NP];                                                                         \
+      _Pragma("unroll") for (int p = 0; p < NP; p++) x[p] = tau * inv_sin[p];                  \
+      expF1_batch<T, NP>(x, f1, a.cf);                                                         \
+      _Pragma("unroll") for (int p = 0; p < NP; p++) {                                         \
+        const T ex = inv_sin[p] * f1[p];                                                       \
+        const T dpsi = (tau * (T)psi[p][j] - lq) * ex;                                         \
+        psi[p][j] = (float)((T)psi[p][j] - dpsi);                                              \
+        if constexpr (sizeof(T) == 8) acc[j] = fma((double)w[p], (double)dpsi, acc[j]);        \
+        else acc[j] += (double)(w[p] * dpsi);                                                  \
+      }                                                                                        \
+      red_add_if(&phi[bc + et[j]], acc[j], flush && valid[j]);                                 \
+      acc[j] = flush ? 0.0 : acc[j];                                                           \
+    }                                                                                          \
+  }
+
+  int i = 0;
+  for (; i + 4 < n; i += 4) {          /* strictly less: the last segment goes through the tail */
+    B200_DEEP_STEP(R0, Q0, R1, R2, Q2, R3, false)
+    B200_DEEP_STEP(R1, Q1, R2, R3, Q3, R0, false)
+    B200_DEEP_STEP(R2, Q2, R3, R0, Q0, R1, false)
+    B200_DEEP_STEP(R3, Q3, R0, R1, Q1, R2, false)
+  }
+  /* tail: 1..4 segments left (n > 0), the very last one always flushes */
+  const int rem = n - i;
+  if (rem > 0) { B200_DEEP_STEP(R0, Q0, R1, R2, Q2, R3, rem == 1) }
+  if (rem > 1) { B200_DEEP_STEP(R1, Q1, R2, R3, Q3, R0, rem == 2) }
+  if (rem > 2) { B200_DEEP_STEP(R2, Q2, R3, R0, Q0, R1, rem == 3) }
+  if (rem > 3) { B200_DEEP_STEP(R3, Q3, R0, R1, Q1, R2, true) }
+#undef B200_DEEP_STEP
+
+  const int64_t out = a.out_slot[t * 2 + dir];
+  if (out >= 0) {
+    const int peer = (int)(out >> PEER_SHIFT);
+    float* __restrict__ dst = peer ? a.peer_out.p[peer - 1] : a.psi_out;
+    const int64_t base = (out & PEER_SLOT_MASK) * (int64_t)F;
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+      for (int j = 0; j < GPL; j++)
+        if (valid[j]) dst[base + p * G + e[j]] = psi[p][j];
+  } else if (a.leakage != nullptr) {
+    double lk = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+      for (int j = 0; j < GPL; j++)
+        if (valid[j]) lk += (double)psi[p][j];
+    atomicAdd(&a.leakage[t], (float)((double)a.cls_w[cls * NP] * lk));
+  }
+}
+
 }  // namespace b200
