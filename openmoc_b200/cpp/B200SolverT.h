@@ -192,7 +192,15 @@ void B200SolverT<Base>::ensureDevice() {
   if (_h != NULL) { b200_destroy(_h); _h = NULL; }
   _flattened_key = key;
 
-  b200_flatten(_track_generator, &_flat, isLinearSource());
+  /* On-the-fly 3D formations go to the device tracer (no 3D segment is made on the host) unless a
+   * per-segment datum only the host traversal produces is needed: CMFD surfaces, linear-source starting
+   * points.  B200_HOST_OTF=1 forces the host expansion. */
+  bool device_otf = b200_can_trace_on_device(_track_generator) && !isLinearSource() && getenv("B200_HOST_OTF") == NULL;
+  {
+    Cmfd* cmfd = _geometry->getCmfd();
+    if (cmfd != NULL && cmfd->isFluxUpdateOn()) device_otf = false;
+  }
+  b200_flatten(_track_generator, &_flat, isLinearSource(), device_otf);
   b200_config cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.num_groups = _flat.num_groups;
@@ -209,6 +217,16 @@ void B200SolverT<Base>::ensureDevice() {
   check(b200_create(&cfg, &_h), "b200_create");
   if (_devices.size() > 1 || (_devices.size() == 1 && _devices[0] != _device))
     check(b200_set_devices(_h, (int)_devices.size(), _devices.data()), "b200_set_devices");
+  if (_flat.device_otf) {
+    check(b200_upload_otf_geometry(_h, _flat.n_tracks_2d, (int64_t)_flat.seg2d_length.size(), _flat.seg2d_length.data(),
+                                   _flat.seg2d_ext.data(), _flat.trk2d_seg_offset.data(), _flat.n_extruded,
+                                   _flat.ext_offset.data(), _flat.ext_mesh.data(), _flat.ext_fsr.data(), 0,
+                                   _flat.otf_theta.data()), "b200_upload_otf_geometry");
+    check(b200_upload_tracks_otf(_h, _flat.trk_2d.data(), _flat.trk_l0.data(), _flat.trk_z0.data(), _flat.trk_azim.data(),
+                                 _flat.trk_polar.data(), _flat.trk_next_fwd.data(), _flat.trk_next_bwd.data(),
+                                 _flat.trk_flags.data(), _flat.trk_bc_fwd.data(), _flat.trk_bc_bwd.data(), NULL),
+          "b200_upload_tracks_otf");
+  } else
   check(b200_upload_tracks(_h, _flat.seg_length.data(), _flat.seg_fsr.data(), _flat.trk_seg_offset.data(),
                            _flat.trk_azim.data(), _flat.trk_polar.data(), _flat.trk_next_fwd.data(),
                            _flat.trk_next_bwd.data(), _flat.trk_flags.data(), _flat.trk_bc_fwd.data(),

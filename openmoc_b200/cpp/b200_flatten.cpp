@@ -122,7 +122,107 @@ class FlattenPass : public TraverseSegments {
 }  // namespace
 
 
-void b200_flatten(TrackGenerator* tg, B200FlatTracks* ft, bool with_ls_data) {
+bool b200_can_trace_on_device(TrackGenerator* tg) {
+  TrackGenerator3D* tg3 = dynamic_cast<TrackGenerator3D*>(tg);
+  if (tg3 == NULL) return false;
+  segmentationType f = tg3->getSegmentFormation();
+  return f == OTF_TRACKS || f == OTF_STACKS;
+}
+
+namespace {
+
+/* The z-stacks handed to the device tracer: no 3D segment is ever made on the host.  Replaces the
+ * host-side expansion through TraverseSegments::loopOverTracksByTrackOTF / ByStackOTF
+ * (src/TraverseSegments.cpp:151-260), whose 56-byte struct segment per 3D segment is what stops
+ * production-size 3D decks long before the GPU's memory does. */
+void flatten_for_device_tracer(TrackGenerator3D* tg3, B200FlatTracks* ft) {
+  Geometry* geometry = tg3->getGeometry();
+  Quadrature* quad = tg3->getQuadrature();
+  const int A2 = ft->num_azim / 2, P = ft->num_polar;
+  ft->device_otf = true;
+
+  /* 2D tracks and their segments (segment::_region_id is the extruded FSR id in the OTF formations) */
+  Track** t2d = tg3->get2DTracksArray();
+  const long n2 = tg3->getNum2DTracks();
+  ft->n_tracks_2d = n2;
+  ft->trk2d_seg_offset.assign(n2 + 1, 0);
+  for (long t = 0; t < n2; t++) ft->trk2d_seg_offset[t + 1] = ft->trk2d_seg_offset[t] + t2d[t]->getNumSegments();
+  const int64_t ns2 = ft->trk2d_seg_offset[n2];
+  ft->seg2d_length.resize(ns2); ft->seg2d_ext.resize(ns2);
+  for (long t = 0; t < n2; t++) {
+    segment* segs = t2d[t]->getSegments();
+    int64_t o = ft->trk2d_seg_offset[t];
+    for (int s = 0; s < t2d[t]->getNumSegments(); s++, o++) {
+      ft->seg2d_length[o] = segs[s]._length;
+      ft->seg2d_ext[o] = segs[s]._region_id;
+    }
+  }
+
+  /* extruded FSRs: axial mesh (their own, or the global one) and 3D FSR ids, bottom-up */
+  double* global_mesh = NULL;
+  int global_n = 0;
+  tg3->retrieveGlobalZMesh(global_mesh, global_n);
+  const long n_ext = (long)geometry->getExtrudedFSRLookup().size();
+  ft->n_extruded = n_ext;
+  ft->ext_offset.assign(n_ext + 1, 0);
+  for (long e = 0; e < n_ext; e++)
+    ft->ext_offset[e + 1] = ft->ext_offset[e] + (global_mesh != NULL ? (long)global_n : (long)geometry->getExtrudedFSR(e)->_num_fsrs);
+  ft->ext_fsr.resize(ft->ext_offset[n_ext]);
+  ft->ext_mesh.resize(ft->ext_offset[n_ext] + n_ext);
+  for (long e = 0; e < n_ext; e++) {
+    ExtrudedFSR* ef = geometry->getExtrudedFSR(e);
+    const long n = ft->ext_offset[e + 1] - ft->ext_offset[e];
+    const double* mesh = global_mesh != NULL ? global_mesh : ef->_mesh;
+    for (long k = 0; k < n; k++) ft->ext_fsr[ft->ext_offset[e] + k] = (int32_t)ef->_fsr_ids[k];
+    for (long k = 0; k <= n; k++) ft->ext_mesh[ft->ext_offset[e] + e + k] = mesh[k];
+  }
+
+  /* corrected polar angles */
+  ft->otf_theta.resize((size_t)A2 * P);
+  for (int a = 0; a < A2; a++)
+    for (int p = 0; p < P; p++) ft->otf_theta[a * P + p] = quad->getTheta(a, p);
+
+  /* 3D tracks: TrackGenerator3D::getTrackOTF (src/TrackGenerator3D.cpp:1697-1745) once per track */
+  const size_t nt = ft->n_tracks;
+  ft->trk_2d.assign(nt, 0); ft->trk_l0.assign(nt, 0.); ft->trk_z0.assign(nt, 0.);
+  int*** tps = tg3->getTracksPerStack();
+  Track** rows = tg3->get2DTracks();
+  std::vector<char> seen(nt, 0);
+  for (int a = 0; a < A2; a++) {
+    const int nxy = tg3->getNumX(a) + tg3->getNumY(a);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int i = 0; i < nxy; i++) {
+      Track* flat2d = &rows[a][i];
+      const double cos_phi = cos(flat2d->getPhi());
+      for (int p = 0; p < P; p++)
+        for (int z = 0; z < tps[a][i][p]; z++) {
+          TrackStackIndexes tsi;
+          tsi._azim = a; tsi._xy = i; tsi._polar = p; tsi._z = z;
+          Track3D t;
+          tg3->getTrackOTF(&t, &tsi);
+          const long id = t.getUid();
+          if (id < 0 || id >= (long)nt) log_printf(ERROR, "b200_flatten: 3D track uid %ld out of range", id);
+          seen[id] = 1;
+          ft->trk_azim[id] = a; ft->trk_xy[id] = i; ft->trk_polar[id] = p;
+          ft->trk_phi[id] = t.getPhi(); ft->trk_theta[id] = t.getTheta();
+          ft->trk_next_fwd[id] = t.getTrackNextFwd(); ft->trk_next_bwd[id] = t.getTrackNextBwd();
+          ft->trk_flags[id] = (t.getNextFwdFwd() ? 1 : 0) | (t.getNextBwdFwd() ? 2 : 0);
+          ft->trk_bc_fwd[id] = (uint8_t)t.getBCFwd(); ft->trk_bc_bwd[id] = (uint8_t)t.getBCBwd();
+          ft->trk_2d[id] = (int32_t)flat2d->getUid();
+          ft->trk_l0[id] = (t.getStart()->getX() - flat2d->getStart()->getX()) / cos_phi;
+          ft->trk_z0[id] = t.getStart()->getZ();
+        }
+    }
+  }
+  for (size_t t = 0; t < nt; t++)
+    if (!seen[t]) log_printf(ERROR, "b200_flatten: 3D track %ld was never visited", (long)t);
+  ft->trk_seg_offset.assign(nt + 1, 0);
+  ft->n_segments = 0;
+}
+
+}  // namespace
+
+void b200_flatten(TrackGenerator* tg, B200FlatTracks* ft, bool with_ls_data, bool device_otf) {
 
   Geometry* geometry = tg->getGeometry();
   Quadrature* quad = tg->getQuadrature();
@@ -215,6 +315,11 @@ void b200_flatten(TrackGenerator* tg, B200FlatTracks* ft, bool with_ls_data) {
   ft->trk_flags.assign(nt, 0); ft->trk_bc_fwd.assign(nt, 0); ft->trk_bc_bwd.assign(nt, 0);
   ft->trk_phi.assign(nt, 0.); ft->trk_theta.assign(nt, 0.);
 
+  ft->device_otf = false;
+  if (device_otf && b200_can_trace_on_device(tg)) {
+    flatten_for_device_tracer(tg3, ft);
+    return;
+  }
   FlattenPass pass(tg, &mat_index, ft);
   pass.execute();
 

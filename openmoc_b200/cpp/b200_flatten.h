@@ -66,6 +66,18 @@ struct B200FlatTracks {
   std::vector<double> mat_sigma_s;      /* [dest*G+orig]  (Material.cpp:728-731) */
   std::vector<double> mat_fiss_matrix;  /* [G_dest*G+g_orig] (Material.cpp:975-978) */
   std::vector<uint8_t> mat_fissionable;
+
+  /* Axial on-the-fly tracks for the device tracer (b200_upload_otf_geometry / b200_upload_tracks_otf):
+   * filled by b200_flatten(..., device_otf = true) INSTEAD of the 3D segment stream.  2D segments of
+   * the radial tracks, the axial mesh and 3D FSR ids of every ExtrudedFSR (src/Geometry.h:84-107), the
+   * corrected polar angles, and per 3D track its 2D track, the distance of its start point from the
+   * start of that 2D track and its start height (what TraverseSegments::traceSegmentsOTF starts from,
+   * src/TraverseSegments.cpp:304-340). */
+  bool device_otf = false;
+  int64_t n_tracks_2d = 0, n_extruded = 0;
+  std::vector<double> seg2d_length, ext_mesh, otf_theta, trk_l0, trk_z0;
+  std::vector<int32_t> seg2d_ext, ext_fsr, trk_2d;
+  std::vector<int64_t> trk2d_seg_offset, ext_offset;
 };
 
 /**
@@ -74,7 +86,12 @@ struct B200FlatTracks {
  * (centroid re-centring and tau>max splitting mutate segments).
  */
 void b200_flatten(TrackGenerator* track_generator, B200FlatTracks* out,
-                  bool with_ls_data = true);
+                  bool with_ls_data = true, bool device_otf = false);
+
+/** True when the tracks can go to the device tracer: an on-the-fly 3D formation (OTF_TRACKS or
+ *  OTF_STACKS).  The caller still falls back to the host expansion when it needs per-segment data
+ *  the tracer does not produce (CMFD surfaces, linear-source starting points). */
+bool b200_can_trace_on_device(TrackGenerator* track_generator);
 
 /** Write / read the chunked binary track file (see openmoc_b200/trackfile.py). */
 void b200_write_trackfile(const B200FlatTracks& ft, const std::string& path);

@@ -161,3 +161,20 @@ def test_multi_device_b200solver_matches_cpusolver_in_process(args, devices):
     assert r["dk_pcm"] < 1.0 and r["max_rel_flux_err"] < 1e-4          # north_star
     tight = (1e-2, 2e-5) if "--cmfd" in args else (1e-3, 1e-7)
     assert r["dk_pcm"] < tight[0] and r["max_rel_flux_err"] < tight[1]
+
+
+# ---------------------------------------------------------------- OTF decks through the device tracer
+@pytest.mark.parametrize("formation", ["otf-stacks", "otf-tracks"])
+def test_otf_formations_are_traced_on_the_device(formation, monkeypatch):
+    """OTF_TRACKS / OTF_STACKS decks: the plug-in hands the 2D segments, the ExtrudedFSR axial meshes and
+    the start point of every 3D track to the device tracer (b200_upload_tracks_otf) - no 3D segment is made
+    on the host.  Same answer as CPUSolver, and as the host expansion of round 1 (B200_HOST_OTF=1)."""
+    args = ["--model", "c5g7-2d", "--dims", "3", "--azim", "4", "--polar", "4", "--spacing", "0.8", "--zspacing", "6",
+            "--axial", "3", "--quad", "equal-angle", "--formation", formation, "--max-iters", "15", "--threads", "4",
+            "--solver", "both"]
+    dev = run(args)
+    assert dev["b200_iters"] == dev["cpu_iters"] == 15
+    assert dev["dk_pcm"] < 1e-3 and dev["max_rel_flux_err"] < 1e-7
+    monkeypatch.setenv("B200_HOST_OTF", "1")
+    host = run(args)
+    assert abs(host["b200_keff"] - dev["b200_keff"]) < 1e-10
