@@ -265,7 +265,7 @@ def measure(name, args, env, primary):
     ft, azim, spacing = build_tracks(name, args, ncpu, world)
     t_gen = time.perf_counter() - t0
     F, G = ft.fluxes_per_track, ft.num_groups
-    precision = capi.PRECISION_MIXED if args.precision == "mixed" else capi.PRECISION_DOUBLE
+    precision = {"mixed": capi.PRECISION_MIXED, "table": capi.PRECISION_TABLE}.get(args.precision, capi.PRECISION_DOUBLE)
     partition = args.partition if wl["dims"] == 2 else args.partition_3d
 
     t0 = time.perf_counter()
@@ -509,7 +509,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "refgpu"])
     ap.add_argument("--workload", default="c5g7-2d", choices=sorted(WORKLOADS))
     ap.add_argument("--also", default="c5g7-3d", help="comma-separated secondary workloads, or 'none'")
-    ap.add_argument("--precision", default="double", choices=["double", "mixed"])
+    ap.add_argument("--precision", default="double", choices=["double", "mixed", "table"])
     ap.add_argument("--azim", type=int, default=None)
     ap.add_argument("--spacing", type=float, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -573,7 +573,8 @@ def main():
             "metric": "segment-group integrations/s", "value": main_res["value"], "unit": "integrations/s",
             "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if precision == "double" else "f32 segment math, f64 tally",
+            "dtype": {"double": "f64", "mixed": "f32 segment math, f64 tally",
+                      "table": "f64, exponential from an fp32 shared-memory table"}[precision],
             "data": "synthetic",
             "ns_per_integration": main_res["ns_per_integration"],
             "config": main_res["config"],

@@ -53,7 +53,10 @@ enum { B200_STAB_DIAGONAL = 0, B200_STAB_YAMAMOTO = 1, B200_STAB_GLOBAL = 2 };
 enum { B200_BC_VACUUM = 0, B200_BC_REFLECTIVE = 1, B200_BC_PERIODIC = 2, B200_BC_INTERFACE = 3 };
 /* arithmetic of the per-segment attenuation */
 enum { B200_PRECISION_DOUBLE = 0,   /* FP_PRECISION=double build of the reference: default */
-       B200_PRECISION_MIXED = 1 };  /* fp32 exponential + fp32 delta-psi, fp64 tally */
+       B200_PRECISION_MIXED = 1,    /* fp32 exponential + fp32 delta-psi, fp64 tally */
+       B200_PRECISION_TABLE = 2 };  /* double arithmetic, F1 from a shared-memory quadratic interpolation table
+                                     * (the role of ExpEvaluator's table, src/ExpEvaluator.cpp:190-330); held to the
+                                     * north-star tolerance only: k_eff within 1 pcm, fluxes within 1e-4 */
 
 typedef struct b200_config {
   int32_t num_groups;      /* G */

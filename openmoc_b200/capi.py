@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libb200moc.so")
 
 SCALAR_FLUX, FISSION_SOURCE, TOTAL_SOURCE = 0, 1, 2
 DIAGONAL, YAMAMOTO, GLOBAL = 0, 1, 2
-PRECISION_DOUBLE, PRECISION_MIXED = 0, 1
+PRECISION_DOUBLE, PRECISION_MIXED, PRECISION_TABLE = 0, 1, 2
 
 
 class B200Error(RuntimeError):

@@ -167,6 +167,7 @@ struct b200_solver {
   DevBuf<double4> qxyz_pad;
   DevBuf<double> tally_pad, tallym_pad;
   DevBuf<float> psi_a, psi_b;
+  DevBuf<float4> f1tab;               /* B200_PRECISION_TABLE: {a, b, c, 0} per interval (sweep.cuh) */
   float* psi_start = nullptr;  /* what the next sweep reads (= reference _start_flux) */
   float* psi_other = nullptr;
   DevBuf<double> scal, partials, hist_k, hist_res;
@@ -353,7 +354,7 @@ extern "C" int b200_create(const b200_config* cfg, b200_solver** out) {
   if (cfg->num_polar < 2 || cfg->num_polar % 2) return fail("b200_create: num_polar=%d must be even", cfg->num_polar);
   if (cfg->n_tracks < 0 || cfg->n_segments < 0 || cfg->n_fsrs < 1 || cfg->n_materials < 1)
     return fail("b200_create: negative or empty problem size");
-  if (cfg->precision != B200_PRECISION_DOUBLE && cfg->precision != B200_PRECISION_MIXED)
+  if (cfg->precision != B200_PRECISION_DOUBLE && cfg->precision != B200_PRECISION_MIXED && cfg->precision != B200_PRECISION_TABLE)
     return fail("b200_create: unknown precision %d", cfg->precision);
   if (cfg->deterministic && cfg->precision != B200_PRECISION_DOUBLE)
     return fail("b200_create: the deterministic tally needs B200_PRECISION_DOUBLE");
@@ -425,7 +426,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   s->otf_seg2d_len.release(); s->otf_mesh.release(); s->otf_l0.release(); s->otf_z0.release(); s->otf_cos.release();
   s->otf_sin.release(); s->otf_volw.release(); s->otf_seg2d_ext.release(); s->otf_ext_fsr.release(); s->otf_trk2d.release();
   s->otf_cls.release(); s->otf_count.release(); s->otf_trk2d_off.release(); s->otf_ext_off.release();
-  s->qst_pad.release(); s->qxyz_pad.release(); s->tally_pad.release(); s->tallym_pad.release();
+  s->f1tab.release(); s->qst_pad.release(); s->qxyz_pad.release(); s->tally_pad.release(); s->tallym_pad.release();
   s->phi_old.release(); s->fixed.release(); s->stab.release(); s->scratch.release();
   s->qst.release(); s->psi_a.release(); s->psi_b.release(); s->scal.release();
   s->partials.release(); s->hist_k.release(); s->hist_res.release(); s->iscal.release();
@@ -1179,6 +1180,36 @@ extern "C" int b200_finalize(b200_solver* s) {
   }
   const int64_t n_items = 2 * nt;
   s->sweep_blocks = (n_items + s->ipc - 1) / s->ipc;
+  if (s->cfg.precision == B200_PRECISION_TABLE) {
+    if (s->gpl != 1 || s->NP > 3)
+      return fail("B200_PRECISION_TABLE supports one group per thread and at most 3 polar angles per track (G = %d, NP = %d)", s->G, s->NP);
+    /* quadratic Taylor expansion of F1(x) = (1 - exp(-x)) / x about the midpoint of every interval */
+    std::vector<float4> tab(F1TAB_N);
+    const double h = 1.0 / (double)F1TAB_INV_H;
+    for (int i = 0; i < F1TAB_N; i++) {
+      const double x = (i + 0.5) * h;
+      double f0, f1, f2;          /* F1, F1', F1''/2 */
+      if (x < 0.5) {
+        f0 = f1 = f2 = 0.;
+        double fact = 1.0;
+        for (int k = 0; k < 30; k++) {
+          fact *= (k + 1);
+          const double ck = (k % 2 ? -1.0 : 1.0) / fact;        /* (-1)^k / (k+1)! */
+          f0 += ck * std::pow(x, k);
+          if (k >= 1) f1 += ck * k * std::pow(x, k - 1);
+          if (k >= 2) f2 += ck * k * (k - 1) * std::pow(x, k - 2) * 0.5;
+        }
+      } else {
+        const double ex = std::exp(-x);
+        f0 = (1.0 - ex) / x;
+        f1 = (ex * (x + 1.0) - 1.0) / (x * x);
+        f2 = 0.5 * (2.0 - ex * (x * x + 2.0 * x + 2.0)) / (x * x * x);
+      }
+      tab[i] = make_float4((float)f0, (float)f1, (float)f2, 0.f);
+    }
+    CU(s->f1tab.upload(tab.data(), F1TAB_N, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+  }
 
   s->smem_attr_set = false;
 
@@ -1368,7 +1399,18 @@ static int launch_sweep(b200_solver* s) {
         s->n_launches++;
       }
     } else {
-    sweep_fn fn;
+    sweep_fn fn = nullptr;
+    if (s->cfg.precision == B200_PRECISION_TABLE) {
+      if (s->cmfd_on || s->cfg.deterministic)
+        return fail("B200_PRECISION_TABLE: no CMFD current tally and no fixed-point tally in this build");
+      switch (s->NP) {
+        case 1: sweep_kernel_tab<1><<<(unsigned)nblk, nthr, 0, s->stream>>>(a, s->f1tab.p); break;
+        case 2: sweep_kernel_tab<2><<<(unsigned)nblk, nthr, 0, s->stream>>>(a, s->f1tab.p); break;
+        case 3: sweep_kernel_tab<3><<<(unsigned)nblk, nthr, 0, s->stream>>>(a, s->f1tab.p); break;
+      }
+      CU(cudaGetLastError());
+      s->n_launches++;
+    } else {
     if (s->cmfd_on) {
       if (mixed || s->cfg.deterministic)
         return fail("CMFD current tallies need B200_PRECISION_DOUBLE with the atomic tally in this build");
@@ -1382,6 +1424,7 @@ static int launch_sweep(b200_solver* s) {
     fn<<<(unsigned)nblk, nthr, 0, s->stream>>>(a);
     CU(cudaGetLastError());
     s->n_launches++;
+    }
     }
     if (pad_tally) {
       unpack_pad_kernel<<<grid_for(nphi, 256), 256, 0, s->stream>>>(s->tally_pad.p, s->phi.p, s->n_fsr, s->G, s->GP, 1, s->n_rep,

@@ -523,6 +523,117 @@ sweep_kernel(const SweepArgs a) {
 }
 
 
+/* ------------------------------------------------------------------------------------
+ * B200_PRECISION_TABLE: the exponential from a shared-memory interpolation table.
+ *
+ * The reference's ExpEvaluator was built around a table of F1 with linear interpolation
+ * (src/ExpEvaluator.cpp:190-330, now dead code behind the rational); the flat 2D sweep here is bound
+ * by FP64 issue - 15 of its 22 FP64 instructions per integration are the rational and its quotient.
+ * This optional mode trades them for one LDS.128 and two FFMA: F1 is a quadratic Taylor expansion
+ * about the midpoint of intervals of width 0.02 over [0, 40) (fp32 {a, b, c}, 2 000 entries, 32 KB of
+ * shared memory per CTA; truncation error < 4e-8, fp32 rounding 6e-8) and 1/x beyond.  Everything
+ * else - tau, the source term, the update of psi and the tally - stays in double.  Held to the
+ * north-star tolerance only (k_eff within 1 pcm, fluxes within 1e-4); the default stays bit-faithful.
+ * ------------------------------------------------------------------------------------ */
+constexpr int F1TAB_N = 2000;
+constexpr float F1TAB_INV_H = 50.0f;           /* 1 / 0.02 */
+constexpr float F1TAB_MAX = 40.0f;
+
+template <int NP>
+__global__ void __launch_bounds__(B200_LB_THREADS, B200_LB_BLOCKS)
+sweep_kernel_tab(const SweepArgs a, const float4* __restrict__ f1tab) {
+  __shared__ float4 tab[F1TAB_N];
+  for (int i = threadIdx.x; i < F1TAB_N; i += blockDim.x) tab[i] = f1tab[i];
+  __syncthreads();
+  if (a.done != nullptr && *a.done) return;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t item = gtid / a.lpi;
+  const int sub = (int)(gtid - item * a.lpi);
+  if (item >= a.n_items) return;
+
+  const int G = a.G;
+  const int64_t t = a.order[item >> 1];
+  const int dir = (int)(item & 1);
+  const int64_t s0 = a.trk_off[t], s1 = a.trk_off[t + 1];
+  const int n = (int)(s1 - s0);
+  const int cls = a.trk_class[t];
+  const uint32_t e = (uint32_t)sub;              /* one group per thread: lpi == G */
+
+  double w[NP];
+  float inv_sin[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    w[p] = a.cls_w[cls * NP + p];
+    inv_sin[p] = (float)a.cls_inv_sin[cls * NP + p];
+  }
+  const int F = G * NP;
+  const int64_t slot_in = (t * 2 + dir) * (int64_t)F;
+  float psi[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) psi[p] = a.psi_in[slot_in + p * G + e];
+  if (a.carry[t * 2 + dir]) {
+#pragma unroll
+    for (int p = 0; p < NP; p++) a.psi_out[slot_in + p * G + e] = psi[p];
+  }
+  double acc = 0.0;
+
+  const int step = dir ? -1 : 1;
+  const SegRec* __restrict__ ps = a.seg + (dir ? s1 - 1 : s0);
+  const int4 r0 = ld_rec(ps);
+  const int4 r1 = ld_rec(ps + step);
+  double L0 = __hiloint2double(r0.y, r0.x), L1 = __hiloint2double(r1.y, r1.x);
+  uint32_t b0 = (uint32_t)r0.z, b1 = (uint32_t)r1.z;
+  double2 qs0 = ld_qs(&a.qst[b0 + e]), qs1;
+  ps += 2 * step;
+  const uint32_t et = e + (uint32_t)(blockIdx.x & a.rep_mask) * (uint32_t)a.rep_stride;
+  double* __restrict__ const phi = a.phi;
+
+  for (int i = 0; i < n; i++) {
+    const int4 r2 = ld_rec(ps);
+    qs1 = ld_qs(&a.qst[b1 + e]);
+    const double tau = qs0.y * L0;
+    const double lq = L0 * qs0.x;
+    const float tau32 = (float)tau;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      /* ExpEvaluator::computeExponential (src/ExpEvaluator.h:170-183): inv_sin * F1(tau * inv_sin) */
+      const float x = tau32 * inv_sin[p];
+      const float xi = fminf(x, F1TAB_MAX - 0.001f) * F1TAB_INV_H;
+      const int k = (int)xi;
+      const float4 c = tab[k];
+      const float d = (xi - (float)k - 0.5f) * (1.0f / F1TAB_INV_H);       /* distance from the interval's midpoint */
+      float f1 = fmaf(fmaf(c.z, d, c.y), d, c.x);
+      f1 = x >= F1TAB_MAX ? __frcp_rn(x) : f1;
+      const double ex = (double)(inv_sin[p] * f1);
+      const double dpsi = (tau * (double)psi[p] - lq) * ex;
+      psi[p] = (float)((double)psi[p] - dpsi);
+      acc = fma(w[p], dpsi, acc);
+    }
+    const bool flush = b1 != b0;
+    red_add_if(&phi[b0 + et], acc, flush);
+    acc = flush ? 0.0 : acc;
+    L0 = L1; b0 = b1;
+    L1 = __hiloint2double(r2.y, r2.x); b1 = (uint32_t)r2.z;
+    qs0 = qs1;
+    ps += step;
+  }
+  if (n > 0 && acc != 0.0) atomicAdd(&phi[a.seg[dir ? s0 : s1 - 1].base + et], acc);
+
+  const int64_t out = a.out_slot[t * 2 + dir];
+  if (out >= 0) {
+    const int peer = (int)(out >> PEER_SHIFT);
+    float* __restrict__ dst = peer ? a.peer_out.p[peer - 1] : a.psi_out;
+    const int64_t base = (out & PEER_SLOT_MASK) * (int64_t)F;
+#pragma unroll
+    for (int p = 0; p < NP; p++) dst[base + p * G + e] = psi[p];
+  } else if (a.leakage != nullptr) {
+    double lk = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; p++) lk += (double)psi[p];
+    atomicAdd(&a.leakage[t], (float)(a.cls_w[cls * NP] * lk));
+  }
+}
+
 /* ---- padded FSR rows ------------------------------------------------------------------
  * With G = 7 a row of {q, sigma_t} pairs is 112 bytes and a tally row 56 bytes: laid end to end, 87 %
  * of the gathers and 43 % of the tallies of a 7-lane item straddle two 128-byte lines, and every line a

@@ -23,7 +23,7 @@ import numpy as np
 
 from . import capi
 from .capi import (B200Error, Config, FISSION_SOURCE, SCALAR_FLUX, TOTAL_SOURCE, DIAGONAL,
-                   PRECISION_DOUBLE, PRECISION_MIXED, check)
+                   PRECISION_DOUBLE, PRECISION_MIXED, PRECISION_TABLE, check)
 from .trackfile import FlatTracks
 
 

@@ -346,3 +346,23 @@ def test_cuda_graph_replay_equals_plain_launches(monkeypatch, max_iters):
     assert abs(a[1] - b[1]) < 1e-12
     np.testing.assert_allclose(b[2], a[2], rtol=1e-11)
     np.testing.assert_allclose(b[3], a[3], rtol=1e-5, atol=1e-12)     # boundary fluxes: buffer parity is right
+
+
+# ------------------------------------------------------- table-interpolated exponential (optional mode)
+@pytest.mark.parametrize("name", ["pin_cell", "simple_lattice", "c5g7_2d_coarse", "lattice3d_7g"])
+def test_precision_table_within_north_star_tolerance(name):
+    """B200_PRECISION_TABLE: F1 from the shared-memory quadratic table (fp32), the rest in double.
+    Held to the north-star tolerance: k_eff within 1 pcm, fluxes within 1e-4, same iteration count."""
+    from openmoc_b200.solver import B200Solver
+    from openmoc_b200.capi import PRECISION_TABLE
+    ft, ref = load_case(name)
+    gpu, cpu = B200Solver(ft, precision=PRECISION_TABLE), OracleSolver(ft)
+    iters = 40 if name.startswith("c5g7") else 500
+    gpu.setConvergenceThreshold(1e-5)
+    gpu.computeEigenvalue(iters, FISSION_SOURCE)
+    n = cpu.computeEigenvalue(iters, 1e-5, FISSION_SOURCE)
+    dk = abs(gpu.getKeff() - cpu.getKeff()) * 1e5
+    err = rel_err(gpu.getFluxes(), cpu.getFluxes())
+    print(name, "table mode: dk = %.3e pcm, max rel flux err = %.3e" % (dk, err))
+    assert dk < K_TOL_PCM and err < PHI_RTOL
+    assert abs(gpu.getNumIterations() - n) <= 1

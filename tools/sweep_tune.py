@@ -21,7 +21,7 @@ ap.add_argument("--ls", action="store_true", help="linear source (2D synthetic d
 args = ap.parse_args()
 ft = make_tracks(args.model, num_azim=args.azim, spacing=args.spacing, groups70=args.groups70, as_3d=args.as3d,
                  linear_source=args.ls)
-s = B200Solver(ft, precision=capi.PRECISION_MIXED if args.precision == "mixed" else capi.PRECISION_DOUBLE,
+s = B200Solver(ft, precision={"mixed": capi.PRECISION_MIXED, "table": capi.PRECISION_TABLE}.get(args.precision, capi.PRECISION_DOUBLE),
                deterministic=args.deterministic, linear_source=args.ls)
 s.zeroTrackFluxes(); s.flattenFSRFluxes(1.0); s.normalizeFluxes(); s.storeFSRFluxes()
 s.computeFSRSources(0)
