@@ -207,6 +207,10 @@ int b200_set_fluxes(b200_solver* s, const double* in_fluxes, int64_t num_fluxes)
 /* getFluxes and getKeff behind one host synchronisation */
 int b200_get_fluxes_keff(b200_solver* s, double* out_fluxes, int64_t num_fluxes, double* k_eff);
 int b200_set_fixed_source_by_fsr(b200_solver* s, int64_t fsr_id, int32_t group /*1-based*/, double source);
+/* CPULSSolver::setFixedSourceMomentByFSR (src/CPULSSolver.cpp:154-205): volume-averaged x, y, z moments
+ * of the fixed source in one FSR and group (1-based), linear-source solvers only */
+int b200_set_fixed_source_moments_by_fsr(b200_solver* s, int64_t fsr_id, int32_t group, double src_x,
+                                         double src_y, double src_z);
 int b200_reset_fixed_sources(b200_solver* s);
 int b200_compute_fsr_fission_rates(b200_solver* s, double* fission_rates, int64_t num_fsrs, int32_t nu);
 int b200_stabilize_transport(b200_solver* s, double factor, int32_t stabilization_type);

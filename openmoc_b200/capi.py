@@ -75,6 +75,7 @@ SIGNATURES = {
     "b200_set_fluxes": [_vp, _i64],
     "b200_get_fluxes_keff": [_vp, _i64, C.POINTER(_dbl)],
     "b200_set_fixed_source_by_fsr": [_i64, _i32, _dbl],
+    "b200_set_fixed_source_moments_by_fsr": [_i64, _i32, _dbl, _dbl, _dbl],
     "b200_reset_fixed_sources": [],
     "b200_compute_fsr_fission_rates": [_vp, _i64, _i32],
     "b200_stabilize_transport": [_dbl, _i32],

@@ -28,8 +28,6 @@ void B200LSSolver::uploadExtras() {
     dir[3 * t + 1] = sin(phi) * sin_theta;
     dir[3 * t + 2] = cos_theta;
   }
-  if (_fixed_source_moments_on)
-    log_printf(ERROR, "Fixed linear source moments are not supported by the B200LSSolver in this build");
   check(b200_upload_linear_source(_h, _flat.seg_start.data(), dir.data(), _FSR_lin_exp_matrix,
                                   _FSR_source_constants), "b200_upload_linear_source");
 }
@@ -47,4 +45,16 @@ void B200LSSolver::pushExtraHostFlux() {
 
 void B200LSSolver::getFluxMoments(FP_PRECISION* out, long n) {
   check(b200_get_flux_moments(_h, out, n), "getFluxMoments");
+}
+
+/* fixed source moments (CPULSSolver::initializeFixedSources, src/CPULSSolver.cpp:154-205) follow the flat
+ * fixed sources to the device */
+void B200LSSolver::pushExtraFixedSources() {
+  if (!_fixed_source_moments_on || _fixed_sources_xyz.empty()) return;
+  for (long r = 0; r < _num_FSRs; r++)
+    for (int g = 0; g < _num_groups; g++) {
+      const std::vector<double>& v = _fixed_sources_xyz[r * _num_groups + g];
+      if (v.size() == 3 && (v[0] != 0. || v[1] != 0. || v[2] != 0.))
+        check(b200_set_fixed_source_moments_by_fsr(_h, r, g + 1, v[0], v[1], v[2]), "b200_set_fixed_source_moments_by_fsr");
+    }
 }

@@ -19,6 +19,7 @@ protected:
   void uploadExtras();
   void syncExtraMirrors();
   void pushExtraHostFlux();
+  void pushExtraFixedSources();
   void allocateHostFluxMirrors();
   void allocateHostSourceMirrors();
 public:

@@ -58,6 +58,7 @@ protected:
   virtual void uploadExtras() {}
   virtual void syncExtraMirrors() {}
   virtual void pushExtraHostFlux() {}
+  virtual void pushExtraFixedSources() {}
   virtual void allocateHostFluxMirrors() {
     long size = _num_FSRs * _num_groups;
     if (_scalar_flux != NULL && !_user_fluxes) delete [] _scalar_flux;
@@ -298,6 +299,7 @@ void B200SolverT<Base>::pushFixedSourcesIfDirty() {
     for (it = _fix_src_FSR_map.begin(); it != _fix_src_FSR_map.end(); ++it)
       check(b200_set_fixed_source_by_fsr(_h, it->first.first, it->first.second, it->second),
             "b200_set_fixed_source_by_fsr");
+    pushExtraFixedSources();
   }
   _fixed_dirty = false;
 }

@@ -157,7 +157,8 @@ struct b200_solver {
   /* linear source */
   bool linear = false, have_ls = false;
   int nc = 3;
-  DevBuf<double> ls_seg_start, ls_trk_dir, ls_lin_exp, ls_src_const, phi_m, mom_stage;
+  DevBuf<double> ls_seg_start, ls_trk_dir, ls_lin_exp, ls_src_const, phi_m, mom_stage, fixed_m;
+  bool fixed_m_on = false;
   DevBuf<double4> seg_pos, qxyz;
   DevBuf<double2> qst;
   /* padded private copies of the sweep (sweep.cuh: pack_pad_kernel) */
@@ -300,6 +301,7 @@ static LsArgs ls_args(b200_solver* s) {
   l.src_const = s->ls_src_const.p;
   l.phi_m = s->phi_m.p;
   l.qxyz = s->qxyz.p;
+  l.fixed_m = s->fixed_m_on ? s->fixed_m.p : nullptr;
   return l;
 }
 
@@ -421,7 +423,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   s->chi.release(); s->max_ratio.release(); s->sigma_a.release(); s->part3.release(); s->leakage.release(); s->fissionable.release(); s->phi.release();
   s->phi_fx.release(); s->fx_bits.release();
   s->ls_seg_start.release(); s->ls_trk_dir.release(); s->ls_lin_exp.release(); s->ls_src_const.release();
-  s->phi_m.release(); s->mom_stage.release(); s->seg_pos.release(); s->qxyz.release();
+  s->phi_m.release(); s->mom_stage.release(); s->fixed_m.release(); s->seg_pos.release(); s->qxyz.release();
   s->cmfd_fwd.release(); s->cmfd_bwd.release(); s->cmfd_group.release(); s->seg_cmfd.release(); s->currents.release();
   s->otf_seg2d_len.release(); s->otf_mesh.release(); s->otf_l0.release(); s->otf_z0.release(); s->otf_cos.release();
   s->otf_sin.release(); s->otf_volw.release(); s->otf_seg2d_ext.release(); s->otf_ext_fsr.release(); s->otf_trk2d.release();
@@ -1575,7 +1577,6 @@ static int launch_sources(b200_solver* s, int iteration, int mode) {
   CU(cudaGetLastError());
   s->n_launches++;
   if (s->linear && mode == 0) {
-    if (s->fixed_on && false) return fail("fixed linear source moments are not supported");
     sources_ls_kernel<<<grid_for(n, 256, 1 << 30), 256, 0, s->stream>>>(a, ls_args(s), iteration, s->neg_allowed ? 1 : 0);
     CU(cudaGetLastError());
     s->n_launches++;
@@ -1767,10 +1768,35 @@ extern "C" int b200_set_fixed_source_by_fsr(b200_solver* s, int64_t fsr_id, int3
   s->fixed_on = true;
   return 0;
 }
+/* CPULSSolver::setFixedSourceMomentByFSR (src/CPULSSolver.cpp:154-205): x, y, z moments of the fixed source */
+extern "C" int b200_set_fixed_source_moments_by_fsr(b200_solver* s, int64_t fsr_id, int32_t group, double src_x,
+                                                    double src_y, double src_z) {
+  NEED_FINAL(s);
+  GRP_ALL(s, b200_set_fixed_source_moments_by_fsr(c, fsr_id, group, src_x, src_y, src_z));
+  if (!s->linear) return fail("Fixed source moments need the linear-source solver");
+  if (group <= 0 || group > s->G)
+    return fail("Unable to use fixed source moments for group %d in a %d energy group problem", group, s->G);
+  if (fsr_id < 0 || fsr_id >= s->n_fsr)
+    return fail("Unable to use fixed source moments for FSR %lld with only %lld FSRs in the geometry",
+                (long long)fsr_id, (long long)s->n_fsr);
+  const size_t nphi = (size_t)s->n_fsr * s->G;
+  if (s->fixed_m.n != 3 * nphi) {
+    CU(s->fixed_m.alloc(3 * nphi));
+    CU(cudaMemsetAsync(s->fixed_m.p, 0, 3 * nphi * 8, s->stream));
+  }
+  const double v[3] = {src_x, src_y, src_z};
+  for (int cidx = 0; cidx < 3; cidx++)
+    CU(cudaMemcpyAsync(s->fixed_m.p + cidx * nphi + fsr_id * s->G + (group - 1), &v[cidx], 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->fixed_m_on = true;
+  return 0;
+}
 extern "C" int b200_reset_fixed_sources(b200_solver* s) {
   NEED_FINAL(s);
   GRP_ALL(s, b200_reset_fixed_sources(c));
   CU(cudaMemsetAsync(s->fixed.p, 0, (size_t)s->n_fsr * s->G * 8, s->stream));
+  if (s->fixed_m.n) CU(cudaMemsetAsync(s->fixed_m.p, 0, s->fixed_m.n * 8, s->stream));
+  s->fixed_m_on = false;
   s->fixed_on = false;
   return 0;
 }

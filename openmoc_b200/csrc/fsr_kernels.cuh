@@ -519,6 +519,7 @@ struct LsArgs {
   double* __restrict__ phi_m;               /* [c*N_FSR*G + r*G+e] flux moments, one plane per component:
                                              * the sweep's moment REDs are then as coalesced as the phi RED */
   double4* __restrict__ qxyz;               /* {q_x, q_y, q_z, 0} per (r, e) */
+  const double* __restrict__ fixed_m;       /* fixed source moments, planes like phi_m; NULL: none (CPULSSolver.cpp:475-479) */
 };
 
 /* CPULSSolver::computeFSRSources, moment part (src/CPULSSolver.cpp:386-524): per (FSR, group)
@@ -545,7 +546,11 @@ sources_ls_kernel(const FsrArgs a, const LsArgs l, int iteration, int neg_allowe
     if (fissionable) { fx = fma(fm[gp], mx, fx); fy = fma(fm[gp], my, fy); fz = fma(fm[gp], mz, fz); }
   }
   const double k = a.scal[SC_KEFF];
-  const double src_x = sx + fx / k, src_y = sy + fy / k, src_z = sz + fz / k;
+  double src_x = sx + fx / k, src_y = sy + fy / k, src_z = sz + fz / k;
+  if (l.fixed_m != nullptr) {
+    const int64_t np = a.n_fsr * G;
+    src_x += l.fixed_m[idx]; src_y += l.fixed_m[np + idx]; src_z += l.fixed_m[2 * np + idx];
+  }
   double4 q = make_double4(0., 0., 0., 0.);
   const double* __restrict__ M = l.lin_exp + r * l.nc;
   const double c = ONE_OVER_FOUR_PI / 2;

@@ -317,6 +317,11 @@ class B200Solver:
     def setFixedSourceByFSR(self, fsr_id: int, group: int, source: float) -> None:
         check(self._lib.b200_set_fixed_source_by_fsr(self._h, int(fsr_id), int(group), float(source)))
 
+    def setFixedSourceMomentsByFSR(self, fsr_id: int, group: int, src_x: float, src_y: float, src_z: float) -> None:
+        """CPULSSolver::setFixedSourceMomentByFSR: x, y, z moments of the fixed source (1-based group)."""
+        check(self._lib.b200_set_fixed_source_moments_by_fsr(self._h, int(fsr_id), int(group), float(src_x),
+                                                             float(src_y), float(src_z)))
+
     def resetFixedSources(self) -> None:
         check(self._lib.b200_reset_fixed_sources(self._h))
 

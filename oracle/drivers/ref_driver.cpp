@@ -224,6 +224,22 @@ int main(int argc, char** argv) {
     }
   }
 
+  /* --fixed-moments g:x:y:z[,...] on the source cell (CPULSSolver::setFixedSourceMomentsByCell) */
+  std::string fmom = arg(argc, argv, "--fixed-moments", "");
+  if (!fmom.empty()) {
+    CPULSSolver* ls_solver = dynamic_cast<CPULSSolver*>(solver);
+    if (md.source_cell == NULL || ls_solver == NULL) { fprintf(stderr, "ref_driver: --fixed-moments needs a source cell and a linear-source solver\n"); return 2; }
+    size_t pos = 0;
+    while (pos < fmom.size()) {
+      int g = 0; double x = 0., y = 0., z = 0.; int used = 0;
+      if (sscanf(fmom.c_str() + pos, "%d:%lf:%lf:%lf%n", &g, &x, &y, &z, &used) != 4) break;
+      ls_solver->setFixedSourceMomentsByCell(md.source_cell, g, x, y, z);
+      pos += used;
+      if (pos < fmom.size() && fmom[pos] == ',') pos++;
+    }
+  }
+  if (flag(argc, argv, "--allow-negative")) solver->allowNegativeFluxes(true);
+
   if (mode == "eigen") {
     if (solver_name == "b200-fused") b200_solver->computeEigenvalueFused(max_iters, rt);
     else solver->computeEigenvalue(max_iters, rt);

@@ -40,6 +40,8 @@ struct moc_oracle {
   float* psi_start; float* psi_bound;
   double k_eff;
   int fixed_on, stabilize, stab_type, threads, balance;
+  int neg_allowed;            /* Solver::allowNegativeFluxes (src/Solver.cpp) */
+  double* fixed_m;            /* fixed source moments [r][3][G] (CPULSSolver.cpp:154-205), NULL until set */
   float* leakage; double* sigma_a;
   double stab_factor;
   double sweep_seconds;
@@ -176,7 +178,7 @@ void moc_oracle_destroy(moc_oracle* o) {
   free(o->weight); free(o->sin_theta); free(o->vol); free(o->fsr_mat);
   free(o->sigma_t); free(o->sigma_s); free(o->fiss); free(o->nu_sigma_f); free(o->sigma_f);
   free(o->chi); free(o->fissionable);
-  free(o->phi); free(o->phi_old); free(o->q); free(o->fixed); free(o->stab);
+  free(o->phi); free(o->phi_old); free(o->q); free(o->fixed); free(o->stab); free(o->fixed_m);
   free(o->psi_start); free(o->psi_bound); free(o->scratch); free(o->leakage); free(o->sigma_a);
   free(o->seg_start); free(o->seg_start0); free(o->trk_phi); free(o->trk_theta); free(o->phi_m); free(o->q_m);
   free(o->lin_exp); free(o->src_const);
@@ -256,7 +258,7 @@ void moc_oracle_compute_fsr_sources(moc_oracle* o, int iteration) {
         q += scatter_source;
         if (o->fixed_on) q += o->fixed[r * G + Gd];
         q *= ONE_OVER_FOUR_PI;
-        if (q < 0.0 && iteration < 30) q = FLUX_EPSILON;
+        if (q < 0.0 && iteration < 30 && !o->neg_allowed) q = FLUX_EPSILON;     /* CPUSolver.cpp:1981 */
         o->q[r * G + Gd] = q;
       }
     }
@@ -594,10 +596,15 @@ static void ls_sources(moc_oracle* o, int iteration) {
         for (int gp = 0; gp < G; gp++) buf[gp] = sigma_s[g * G + gp] * pm[c * G + gp];
         sca[c] = pairwise_sum(buf, G);
       }
-      const double src_x = sca[0] + fis[0], src_y = sca[1] + fis[1], src_z = sca[2] + fis[2];
+      double src_x = sca[0] + fis[0], src_y = sca[1] + fis[1], src_z = sca[2] + fis[2];
+      if (o->fixed_m != NULL) {          /* _fixed_source_moments_on, CPULSSolver.cpp:475-479 */
+        src_x += o->fixed_m[r * 3 * G + g];
+        src_y += o->fixed_m[r * 3 * G + G + g];
+        src_z += o->fixed_m[r * 3 * G + 2 * G + g];
+      }
       double* qm = o->q_m + r * 3 * G;
       const double* M = o->lin_exp + r * nc;
-      if (o->q[r * G + g] > 10 * FLUX_EPSILON || iteration > 29) {
+      if (o->neg_allowed || o->q[r * G + g] > 10 * FLUX_EPSILON || iteration > 29) {
         if (o->solve_3d) {
           qm[g] = ONE_OVER_FOUR_PI / 2 * (M[0] * src_x + M[2] * src_y + M[3] * src_z);
           qm[G + g] = ONE_OVER_FOUR_PI / 2 * (M[2] * src_x + M[1] * src_y + M[4] * src_z);
@@ -770,7 +777,7 @@ static void ls_closure(moc_oracle* o) {
       pm[e] /= sigma_t[e];
       pm[G + e] /= sigma_t[e];
       if (o->solve_3d) pm[2 * G + e] /= sigma_t[e];
-      if (o->phi[r * G + e] < 0.0) {
+      if (o->phi[r * G + e] < 0.0 && !o->neg_allowed) {
         o->phi[r * G + e] = o->phi_old[r * G + e] > FLUX_EPSILON ? o->phi_old[r * G + e] : FLUX_EPSILON;
         pm[e] = pm[G + e] = pm[2 * G + e] = 0;
       }
@@ -818,7 +825,7 @@ void moc_oracle_add_source_to_scalar_flux(moc_oracle* o) {
     for (int e = 0; e < G; e++) {
       o->phi[r * G + e] /= (sigma_t[e] * volume);
       o->phi[r * G + e] += FOUR_PI * o->q[r * G + e] / sigma_t[e];
-      if (o->phi[r * G + e] < 0.0) o->phi[r * G + e] = FLUX_EPSILON;
+      if (o->phi[r * G + e] < 0.0 && !o->neg_allowed) o->phi[r * G + e] = FLUX_EPSILON;   /* CPUSolver.cpp:2630 */
     }
   }
 }
@@ -1057,6 +1064,15 @@ void moc_oracle_get_start_fluxes(moc_oracle* o, float* out) { memcpy(out, o->psi
 void moc_oracle_set_start_fluxes(moc_oracle* o, const float* in) { memcpy(o->psi_start, in, (size_t)o->n_trk * 2 * o->F * 4); }
 
 /* src/Solver.cpp:479-497 + src/CPUSolver.cpp:425-456 (group0 is 0-based here) */
+/* CPULSSolver::setFixedSourceMomentByFSR (src/CPULSSolver.cpp): volume-averaged x, y, z moments */
+void moc_oracle_set_fixed_source_moments(moc_oracle* o, int64_t fsr, int group0, double sx, double sy, double sz) {
+  if (o->fixed_m == NULL) o->fixed_m = calloc((size_t)o->n_fsr * 3 * o->G, 8);
+  o->fixed_m[fsr * 3 * o->G + group0] = sx;
+  o->fixed_m[fsr * 3 * o->G + o->G + group0] = sy;
+  o->fixed_m[fsr * 3 * o->G + 2 * o->G + group0] = sz;
+}
+void moc_oracle_allow_negative_fluxes(moc_oracle* o, int allowed) { o->neg_allowed = allowed != 0; }
+
 void moc_oracle_set_fixed_source(moc_oracle* o, int64_t fsr, int group0, double value) {
   o->fixed_on = 1;
   o->fixed[fsr * o->G + group0] = value;

@@ -81,6 +81,8 @@ void   moc_oracle_set_sources(moc_oracle* o, const double* in);
 void   moc_oracle_get_start_fluxes(moc_oracle* o, float* out);   /* [n_tracks*2*F] */
 void   moc_oracle_set_start_fluxes(moc_oracle* o, const float* in);
 void   moc_oracle_set_fixed_source(moc_oracle* o, int64_t fsr, int group0, double value);
+void   moc_oracle_set_fixed_source_moments(moc_oracle* o, int64_t fsr, int group0, double sx, double sy, double sz);
+void   moc_oracle_allow_negative_fluxes(moc_oracle* o, int allowed);
 void   moc_oracle_stabilize_transport(moc_oracle* o, double factor, int type);
 void   moc_oracle_compute_fission_rates(moc_oracle* o, double* out, int nu);
 void   moc_oracle_set_num_threads(moc_oracle* o, int n);

@@ -63,6 +63,10 @@ def lib():
             f = getattr(L, "moc_oracle_" + name); f.restype = None; f.argtypes = [vp, vp]
         L.moc_oracle_set_fixed_source.restype = None
         L.moc_oracle_set_fixed_source.argtypes = [vp, i64, i32, dbl]
+        L.moc_oracle_set_fixed_source_moments.restype = None
+        L.moc_oracle_set_fixed_source_moments.argtypes = [vp, i64, i32, dbl, dbl, dbl]
+        L.moc_oracle_allow_negative_fluxes.restype = None
+        L.moc_oracle_allow_negative_fluxes.argtypes = [vp, i32]
         L.moc_oracle_stabilize_transport.restype = None
         L.moc_oracle_stabilize_transport.argtypes = [vp, dbl, i32]
         L.moc_oracle_compute_fission_rates.restype = None
@@ -191,6 +195,13 @@ class OracleSolver:
     def setFixedSourceByFSR(self, fsr_id, group, source):
         """group is 1-based like the reference (src/Solver.cpp:479-497)."""
         lib().moc_oracle_set_fixed_source(self.h, fsr_id, group - 1, float(source))
+
+    def setFixedSourceMomentsByFSR(self, fsr_id, group, src_x, src_y, src_z):
+        """CPULSSolver::setFixedSourceMomentByFSR, 1-based group."""
+        lib().moc_oracle_set_fixed_source_moments(self.h, fsr_id, group - 1, float(src_x), float(src_y), float(src_z))
+
+    def allowNegativeFluxes(self, allowed):
+        lib().moc_oracle_allow_negative_fluxes(self.h, int(bool(allowed)))
 
     def stabilizeTransport(self, factor, stab_type=0):
         lib().moc_oracle_stabilize_transport(self.h, float(factor), stab_type)

@@ -44,6 +44,12 @@ CASES = {
     "lattice3d_ls_70g": ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2",
                          "--spacing", "0.6", "--zspacing", "2.8", "--groups70", "--tol", "5e-3",
                          "--solver", "cpuls"],                                  # test_forward_3D_lattice_linear_70g
+    # tests/test_fixed_linear_source: the water box with a flat fixed source and its x, y, z moments, negative
+    # fluxes allowed, CPULSSolver::computeFlux
+    "water_box_ls": ["--model", "water-box", "--azim", "4", "--spacing", "0.1", "--solver", "cpuls", "--mode", "flux",
+                     "--res", "flux", "--allow-negative",
+                     "--fixed-source", "1:1.0,2:0.5,3:0.25,4:1.0,5:0.5,6:0.25,7:1.0",
+                     "--fixed-moments", "1:0.01:0.1:0.2,2:-0.1:0:-0.04,3:0.02:0:0"],
     "lattice3d_ls_7g": ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2",
                         "--spacing", "0.24", "--zspacing", "0.9", "--solver", "cpuls"],  # test_forward_3D_lattice_linear
 }
@@ -64,7 +70,7 @@ def main():
     for t in ("test_forward_pin_cell", "test_forward_simple_lattice", "test_forward_3D_lattice_70g",
               "test_forward_3D_lattice", "test_forward_hom_inf_medium",
               "test_forward_3D_lattice_linear", "test_forward_3D_lattice_linear_70g",
-              "test_compute_flux", "test_compute_source",
+              "test_compute_flux", "test_compute_source", "test_fixed_linear_source",
               "test_forward_pin_cell_70g", "test_1d_gradient", "test_2d_gradient", "test_adjoint_pin_cell", "test_adjoint_simple_lattice", "test_adjoint_hom_inf_medium"):
         gold[t] = open(os.path.join(REF, "tests", t, "results_true.dat")).read()
     json.dump(gold, open(os.path.join(HERE, "ref_goldens.json"), "w"), indent=1)

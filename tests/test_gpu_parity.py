@@ -366,3 +366,26 @@ def test_precision_table_within_north_star_tolerance(name):
     print(name, "table mode: dk = %.3e pcm, max rel flux err = %.3e" % (dk, err))
     assert dk < K_TOL_PCM and err < PHI_RTOL
     assert abs(gpu.getNumIterations() - n) <= 1
+
+
+# ------------------------------------------------------- fixed linear source (moments of the fixed source)
+def test_fixed_linear_source_golden_from_gpu():
+    """tests/test_fixed_linear_source/results_true.dat byte for byte from the GPU: flat fixed source in seven
+    groups, x / y / z moments in three (CPULSSolver::setFixedSourceMomentsByCell), negative fluxes allowed."""
+    from openmoc_b200.solver import B200Solver
+    from oracle.oracle_py import format_flux_results
+    ft, ref = load_case("water_box_ls")
+    flat = ((1, 1.0), (2, 0.5), (3, 0.25), (4, 1.0), (5, 0.5), (6, 0.25), (7, 1.0))
+    moments = ((1, 0.01, 0.1, 0.2), (2, -0.1, 0.0, -0.04), (3, 0.02, 0.0, 0.0))
+    for devices in (None, [0, 0]):
+        gpu = B200Solver(ft, linear_source=True, devices=devices)
+        gpu.allowNegativeFluxes(True)
+        for fsr in ref["source_fsrs"]:
+            for group, value in flat:
+                gpu.setFixedSourceByFSR(fsr, group, value)
+            for group, sx, sy, sz in moments:
+                gpu.setFixedSourceMomentsByFSR(fsr, group, sx, sy, sz)
+        gpu.setConvergenceThreshold(1e-5)
+        gpu.computeFlux(500, only_fixed_source=True)
+        assert format_flux_results(gpu.getNumIterations(), gpu.getFluxes()) == GOLDENS["test_fixed_linear_source"]
+        assert rel_err(gpu.getFluxes(), np.array(ref["fluxes"])) < TIGHT

@@ -178,3 +178,17 @@ def test_otf_formations_are_traced_on_the_device(formation, monkeypatch):
     monkeypatch.setenv("B200_HOST_OTF", "1")
     host = run(args)
     assert abs(host["b200_keff"] - dev["b200_keff"]) < 1e-10
+
+
+def test_fixed_linear_source_golden_through_the_plugin(tmp_path):
+    """B200LSSolver inside the reference's process: setFixedSourceByCell + setFixedSourceMomentsByCell +
+    allowNegativeFluxes + computeFlux reproduce tests/test_fixed_linear_source/results_true.dat"""
+    if not os.path.exists(DRIVER):
+        pytest.skip("ref_driver not built")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([DRIVER, "--model", "water-box", "--azim", "4", "--spacing", "0.1", "--solver", "b200ls", "--mode", "flux",
+                    "--res", "flux", "--allow-negative", "--fixed-source", "1:1.0,2:0.5,3:0.25,4:1.0,5:0.5,6:0.25,7:1.0",
+                    "--fixed-moments", "1:0.01:0.1:0.2,2:-0.1:0:-0.04,3:0.02:0:0", "--quiet", "--results", res],
+                   check=True, capture_output=True)
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_goldens.json")))["test_fixed_linear_source"]
+    assert open(res).read() == golden

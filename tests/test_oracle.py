@@ -169,6 +169,26 @@ def test_compute_flux_golden_bytes():
     np.testing.assert_allclose(s.getFluxes(), ref["fluxes"], rtol=1e-12)
 
 
+FIXED_FLAT = ((1, 1.0), (2, 0.5), (3, 0.25), (4, 1.0), (5, 0.5), (6, 0.25), (7, 1.0))
+FIXED_MOMENTS = ((1, 0.01, 0.1, 0.2), (2, -0.1, 0.0, -0.04), (3, 0.02, 0.0, 0.0))
+
+
+def test_fixed_linear_source_golden_bytes():
+    # tests/test_fixed_linear_source: the water box, CPULSSolver::computeFlux, a flat fixed source in all seven
+    # groups plus x, y, z moments in the first three, negative fluxes allowed (16th reference golden)
+    ft, ref = load_case("water_box_ls")
+    s = OracleSolver(ft, linear_source=True)
+    s.allowNegativeFluxes(True)
+    for fsr in ref["source_fsrs"]:
+        for group, value in FIXED_FLAT:
+            s.setFixedSourceByFSR(fsr, group, value)
+        for group, sx, sy, sz in FIXED_MOMENTS:
+            s.setFixedSourceMomentsByFSR(fsr, group, sx, sy, sz)
+    n = s.computeFlux(500, 1e-5, True)
+    assert format_flux_results(n, s.getFluxes()) == GOLDENS["test_fixed_linear_source"]
+    np.testing.assert_allclose(s.getFluxes(), ref["fluxes"], rtol=1e-12)
+
+
 def test_compute_source_golden_bytes():
     # tests/test_compute_source: same deck, source 1.0 in group 1, computeSource with TOTAL_SOURCE residual
     ft, ref = load_case("water_box")
