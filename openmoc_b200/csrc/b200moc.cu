@@ -157,7 +157,7 @@ struct b200_solver {
   /* linear source */
   bool linear = false, have_ls = false;
   int nc = 3;
-  DevBuf<double> ls_seg_start, ls_trk_dir, ls_lin_exp, ls_src_const, phi_m, mom_stage, fixed_m;
+  DevBuf<double> ls_seg_start, ls_trk_dir, ls_lin_exp, ls_src_const, phi_m, mom_stage, fixed_m, stab_m;
   bool fixed_m_on = false;
   DevBuf<double4> seg_pos, qxyz;
   DevBuf<double2> qst;
@@ -423,7 +423,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   s->chi.release(); s->max_ratio.release(); s->sigma_a.release(); s->part3.release(); s->leakage.release(); s->fissionable.release(); s->phi.release();
   s->phi_fx.release(); s->fx_bits.release();
   s->ls_seg_start.release(); s->ls_trk_dir.release(); s->ls_lin_exp.release(); s->ls_src_const.release();
-  s->phi_m.release(); s->mom_stage.release(); s->fixed_m.release(); s->seg_pos.release(); s->qxyz.release();
+  s->phi_m.release(); s->mom_stage.release(); s->fixed_m.release(); s->stab_m.release(); s->seg_pos.release(); s->qxyz.release();
   s->cmfd_fwd.release(); s->cmfd_bwd.release(); s->cmfd_group.release(); s->seg_cmfd.release(); s->currents.release();
   s->otf_seg2d_len.release(); s->otf_mesh.release(); s->otf_l0.release(); s->otf_z0.release(); s->otf_cos.release();
   s->otf_sin.release(); s->otf_volw.release(); s->otf_seg2d_ext.release(); s->otf_ext_fsr.release(); s->otf_trk2d.release();
@@ -1695,6 +1695,17 @@ static int launch_stabilizing_flux(b200_solver* s) {
       fsr_args(s), s->stab_type, s->stab_factor, s->max_ratio.p);
   CU(cudaGetLastError());
   s->n_launches++;
+  if (s->linear) {            /* _stabilize_moments, the reference's default (CPULSSolver.cpp:19) */
+    const size_t n3 = (size_t)s->n_fsr * s->G * 3;
+    if (s->stab_m.n != n3) {
+      CU(s->stab_m.alloc(n3));
+      CU(cudaMemsetAsync(s->stab_m.p, 0, n3 * 8, s->stream));
+    }
+    stabilizing_moments_kernel<<<grid_for((int64_t)n3, 256), 256, 0, s->stream>>>(fsr_args(s), s->phi_m.p, s->stab_m.p,
+                                                                                s->stab_type, s->stab_factor);
+    CU(cudaGetLastError());
+    s->n_launches++;
+  }
   return 0;
 }
 static int launch_stabilize_flux(b200_solver* s) {
@@ -1702,6 +1713,12 @@ static int launch_stabilize_flux(b200_solver* s) {
       fsr_args(s), s->stab_type, s->stab_factor, s->max_ratio.p);
   CU(cudaGetLastError());
   s->n_launches++;
+  if (s->linear && s->stab_m.n == (size_t)s->n_fsr * s->G * 3) {
+    stabilize_moments_kernel<<<grid_for((int64_t)s->stab_m.n, 256), 256, 0, s->stream>>>(fsr_args(s), s->phi_m.p, s->stab_m.p,
+                                                                                        s->stab_type, s->stab_factor);
+    CU(cudaGetLastError());
+    s->n_launches++;
+  }
   return 0;
 }
 
@@ -1813,7 +1830,6 @@ extern "C" int b200_compute_fsr_fission_rates(b200_solver* s, double* out, int64
 }
 extern "C" int b200_stabilize_transport(b200_solver* s, double factor, int32_t type) {
   NEED(s);
-  if (s->linear) return fail("transport stabilisation of the flux moments is not supported with the linear source in this build");
   if (type < 0 || type > 2) return fail("b200_stabilize_transport: unknown stabilization type %d", type);
   s->stabilize = true;
   s->stab_factor = factor;

@@ -400,6 +400,48 @@ __global__ void stabilizing_flux_kernel(const FsrArgs a, int type, double factor
     }
   }
 }
+/* The same two steps for the three flux-moment planes of the linear source
+ * (CPULSSolver::computeStabilizingFlux / stabilizeFlux, src/CPULSSolver.cpp:888-1052).  YAMAMOTO: the
+ * reference's search for the largest scattering ratio never updates its maximum (`ratio = max_ratio`,
+ * :943, :1028), so its moment stabilisation adds nothing and divides by one: reproduced as a no-op. */
+__global__ void stabilizing_moments_kernel(const FsrArgs a, const double* __restrict__ phi_m, double* __restrict__ stab_m,
+                                           int type, double factor) {
+  if (a.iscal[SI_DONE]) return;
+  const int G = a.G;
+  const int64_t n = a.n_fsr * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t idx = i % n, r = idx / G;
+    const int e = (int)(idx - r * G);
+    const int m = a.fsr_mat[r];
+    if (type == 0) {
+      const double ss = a.sigma_s[((int64_t)m * G + e) * G + e];
+      if (ss < 0.0) stab_m[i] = -phi_m[i] * factor * ss / a.sigma_t[(int64_t)m * G + e];
+    } else if (type == 1) {
+      stab_m[i] = phi_m[i] * 0.0;
+    } else {
+      stab_m[i] = phi_m[i] * (1.0 / factor - 1.0);
+    }
+  }
+}
+__global__ void stabilize_moments_kernel(const FsrArgs a, double* __restrict__ phi_m, const double* __restrict__ stab_m,
+                                         int type, double factor) {
+  if (a.iscal[SI_DONE]) return;
+  const int G = a.G;
+  const int64_t n = a.n_fsr * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t idx = i % n, r = idx / G;
+    const int e = (int)(idx - r * G);
+    const int m = a.fsr_mat[r];
+    if (type == 0) {
+      const double ss = a.sigma_s[((int64_t)m * G + e) * G + e];
+      if (ss < 0.0) phi_m[i] = (phi_m[i] + stab_m[i]) / (1.0 - factor * ss / a.sigma_t[(int64_t)m * G + e]);
+    } else if (type == 1) {
+      phi_m[i] = (phi_m[i] + stab_m[i]) / (1 + 0.0);
+    } else {
+      phi_m[i] = (phi_m[i] + stab_m[i]) * factor;
+    }
+  }
+}
 __global__ void stabilize_flux_kernel(const FsrArgs a, int type, double factor,
                                       const double* __restrict__ max_ratio) {
   if (a.iscal[SI_DONE]) return;

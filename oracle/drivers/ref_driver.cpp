@@ -68,6 +68,12 @@ int main(int argc, char** argv) {
   if (flag(argc, argv, "--quiet")) set_log_level("WARNING");
   else set_log_level("NORMAL");
 
+  /* --stabilize FACTOR:TYPE (0 DIAGONAL, 1 YAMAMOTO, 2 GLOBAL): Solver::stabilizeTransport */
+  double stab_factor = 0.; int stab_type = -1;
+  {
+    std::string st = arg(argc, argv, "--stabilize", "");
+    if (!st.empty()) sscanf(st.c_str(), "%lf:%d", &stab_factor, &stab_type);
+  }
   set_axial_layers(atoi(arg(argc, argv, "--axial", "1")));
   Model md = build_model(model_name, dims);
   if (flag(argc, argv, "--groups70")) set_70_group_xs(md);
@@ -137,6 +143,7 @@ int main(int argc, char** argv) {
     cpu.setConvergenceThreshold(tol);
     if (flag(argc, argv, "--verbose")) cpu.setVerboseIterationReport();
     if (flag(argc, argv, "--balance")) cpu.setKeffFromNeutronBalance();
+    if (stab_type >= 0) cpu.stabilizeTransport(stab_factor, (stabilizationType)stab_type);
     cpu.computeEigenvalue(max_iters, rt);
     Timer timer;
     double cpu_sweep = timer.getSplit("Transport Sweep");
@@ -164,6 +171,7 @@ int main(int argc, char** argv) {
     gpu.setConvergenceThreshold(tol);
     if (flag(argc, argv, "--verbose")) gpu.setVerboseIterationReport();
     if (flag(argc, argv, "--balance")) gpu.setKeffFromNeutronBalance();
+    if (stab_type >= 0) gpu.stabilizeTransport(stab_factor, (stabilizationType)stab_type);
     gpu.computeEigenvalue(max_iters, rt);
     double gpu_sweep = timer.getSplit("Transport Sweep");
     gpu.getFluxes(phi_gpu.data(), n_fsr * G);
@@ -239,6 +247,7 @@ int main(int argc, char** argv) {
     }
   }
   if (flag(argc, argv, "--allow-negative")) solver->allowNegativeFluxes(true);
+  if (stab_type >= 0) solver->stabilizeTransport(stab_factor, (stabilizationType)stab_type);
 
   if (mode == "eigen") {
     if (solver_name == "b200-fused") b200_solver->computeEigenvalueFused(max_iters, rt);

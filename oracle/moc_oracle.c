@@ -41,6 +41,7 @@ struct moc_oracle {
   double k_eff;
   int fixed_on, stabilize, stab_type, threads, balance;
   int neg_allowed;            /* Solver::allowNegativeFluxes (src/Solver.cpp) */
+  double* stab_m;             /* stabilising flux moments [r][3][G] (CPULSSolver.cpp:888-970) */
   double* fixed_m;            /* fixed source moments [r][3][G] (CPULSSolver.cpp:154-205), NULL until set */
   float* leakage; double* sigma_a;
   double stab_factor;
@@ -178,7 +179,7 @@ void moc_oracle_destroy(moc_oracle* o) {
   free(o->weight); free(o->sin_theta); free(o->vol); free(o->fsr_mat);
   free(o->sigma_t); free(o->sigma_s); free(o->fiss); free(o->nu_sigma_f); free(o->sigma_f);
   free(o->chi); free(o->fissionable);
-  free(o->phi); free(o->phi_old); free(o->q); free(o->fixed); free(o->stab); free(o->fixed_m);
+  free(o->phi); free(o->phi_old); free(o->q); free(o->fixed); free(o->stab); free(o->fixed_m); free(o->stab_m);
   free(o->psi_start); free(o->psi_bound); free(o->scratch); free(o->leakage); free(o->sigma_a);
   free(o->seg_start); free(o->seg_start0); free(o->trk_phi); free(o->trk_theta); free(o->phi_m); free(o->q_m);
   free(o->lin_exp); free(o->src_const);
@@ -947,6 +948,24 @@ void moc_oracle_compute_stabilizing_flux(moc_oracle* o) {
     double mult = 1.0 / o->stab_factor - 1.0;
     for (int64_t i = 0; i < o->n_fsr * G; i++) o->stab[i] = mult * o->phi[i];
   }
+  if (!o->ls) return;
+  /* CPULSSolver::computeStabilizingFlux, moment part (src/CPULSSolver.cpp:894-970; _stabilize_moments = true) */
+  if (o->stab_m == NULL) o->stab_m = calloc((size_t)o->n_fsr * 3 * G, 8);
+  for (int64_t r = 0; r < o->n_fsr; r++) {
+    int m = o->fsr_mat[r];
+    for (int e = 0; e < G; e++)
+      for (int c = 0; c < 3; c++) {
+        const size_t k = (size_t)r * 3 * G + c * G + e;
+        if (o->stab_type == STAB_DIAGONAL) {
+          double sigma_s = o->sigma_s[(size_t)m * G * G + e * G + e];
+          if (sigma_s < 0.0) o->stab_m[k] = -o->phi_m[k] * o->stab_factor * sigma_s / o->sigma_t[(size_t)m * G + e];
+        } else if (o->stab_type == STAB_YAMAMOTO) {
+          o->stab_m[k] = o->phi_m[k] * 0.0;      /* max_ratio stays 0 in the reference: `ratio = max_ratio` (:943) */
+        } else {
+          o->stab_m[k] = o->phi_m[k] * (1.0 / o->stab_factor - 1.0);
+        }
+      }
+  }
 }
 
 /* src/CPUSolver.cpp:2736-2805 */
@@ -982,6 +1001,28 @@ void moc_oracle_stabilize_flux(moc_oracle* o) {
       o->phi[i] += o->stab[i];
       o->phi[i] *= o->stab_factor;
     }
+  }
+  if (!o->ls || o->stab_m == NULL) return;
+  /* CPULSSolver::stabilizeFlux, moment part (src/CPULSSolver.cpp:978-1052) */
+  for (int64_t r = 0; r < o->n_fsr; r++) {
+    int m = o->fsr_mat[r];
+    for (int e = 0; e < G; e++)
+      for (int c = 0; c < 3; c++) {
+        const size_t k = (size_t)r * 3 * G + c * G + e;
+        if (o->stab_type == STAB_DIAGONAL) {
+          double sigma_s = o->sigma_s[(size_t)m * G * G + e * G + e];
+          if (sigma_s < 0.0) {
+            o->phi_m[k] += o->stab_m[k];
+            o->phi_m[k] /= (1.0 - o->stab_factor * sigma_s / o->sigma_t[(size_t)m * G + e]);
+          }
+        } else if (o->stab_type == STAB_YAMAMOTO) {
+          o->phi_m[k] += o->stab_m[k];
+          o->phi_m[k] /= (1 + 0.0);
+        } else {
+          o->phi_m[k] += o->stab_m[k];
+          o->phi_m[k] *= o->stab_factor;
+        }
+      }
   }
 }
 

@@ -391,3 +391,23 @@ def test_fixed_linear_source_golden_from_gpu():
         gpu.computeFlux(500, only_fixed_source=True)
         assert format_flux_results(gpu.getNumIterations(), gpu.getFluxes()) == GOLDENS["test_fixed_linear_source"]
         assert rel_err(gpu.getFluxes(), np.array(ref["fluxes"])) < TIGHT
+
+
+def test_linear_source_stabilisation_matches_oracle_and_reference():
+    """transport stabilisation with the linear source: scalar flux and the three moment planes
+    (CPULSSolver::computeStabilizingFlux / stabilizeFlux); GLOBAL against the reference's own run"""
+    from openmoc_b200.solver import B200Solver
+    ft, _ = load_case("simple_lattice_ls")
+    ref = json.load(open(os.path.join(GOLDEN, "simple_lattice_ls_stab.json")))
+    for stab_type in (0, 1, 2):
+        gpu, cpu = B200Solver(ft, linear_source=True), OracleSolver(ft, linear_source=True)
+        gpu.stabilizeTransport(0.5, stab_type); cpu.stabilizeTransport(0.5, stab_type)
+        gpu.setConvergenceThreshold(1e-5)
+        gpu.computeEigenvalue(1000, FISSION_SOURCE)
+        n = cpu.computeEigenvalue(1000, 1e-5, FISSION_SOURCE)
+        assert gpu.getNumIterations() == n, stab_type
+        assert abs(gpu.getKeff() - cpu.getKeff()) * 1e5 < 1e-3
+        assert rel_err(gpu.getFluxes(), cpu.getFluxes()) < 1e-8
+        if stab_type == 2:
+            assert n == ref["iterations"] and abs(gpu.getKeff() - ref["keff"]) * 1e5 < 1e-3
+            assert rel_err(gpu.getFluxes(), np.array(ref["fluxes"])) < 1e-8

@@ -192,3 +192,12 @@ def test_fixed_linear_source_golden_through_the_plugin(tmp_path):
                    check=True, capture_output=True)
     golden = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_goldens.json")))["test_fixed_linear_source"]
     assert open(res).read() == golden
+
+
+@pytest.mark.parametrize("stab", ["0.5:2", "0.7:0"])
+def test_stabilised_linear_source_through_the_plugin(stab):
+    """B200LSSolver::stabilizeTransport next to CPULSSolver in one process (moments stabilised too)"""
+    r = run(["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12", "--solver", "both", "--ls",
+             "--stabilize", stab, "--max-iters", "1000"])
+    assert r["b200_iters"] == r["cpu_iters"]
+    assert r["dk_pcm"] < 1e-3 and r["max_rel_flux_err"] < 1e-7

@@ -242,3 +242,16 @@ def test_vacuum_gradient_goldens(fixture, test, iters):
     s, n, _ = solve(fixture)
     assert n == iters
     assert format_harness_results(n, s.getKeff(), s.getFluxes()) == GOLDENS[test]
+
+
+def test_linear_source_global_stabilisation_matches_reference():
+    """CPULSSolver with stabilizeTransport(0.5, GLOBAL): the flux moments are damped like the scalar flux
+    (src/CPULSSolver.cpp:888-1052); full-precision run of the unmodified reference on the same tracks"""
+    ft, _ = load_case("simple_lattice_ls")
+    ref = json.load(open(os.path.join(GOLDEN, "simple_lattice_ls_stab.json")))
+    s = OracleSolver(ft, linear_source=True)
+    s.stabilizeTransport(0.5, 2)
+    n = s.computeEigenvalue(1000, 1e-5, FISSION_SOURCE)
+    assert n == ref["iterations"] == 234
+    assert abs(s.getKeff() - ref["keff"]) * 1e5 < 1e-6
+    np.testing.assert_allclose(s.getFluxes(), ref["fluxes"], rtol=1e-12)
