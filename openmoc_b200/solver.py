@@ -333,6 +333,7 @@ class B200Solver:
 
     def stabilizeTransport(self, stabilization_factor: float, stabilization_type: int = DIAGONAL) -> None:
         check(self._lib.b200_stabilize_transport(self._h, float(stabilization_factor), int(stabilization_type)))
+        self._stabilize = True
 
     def setKeffFromNeutronBalance(self) -> None:
         """Solver::setKeffFromNeutronBalance: k = fission / (absorption + leakage)."""
@@ -560,11 +561,16 @@ class B200Solver:
         self.normalizeFluxes()
         self.storeFSRFluxes()
         k_prev, iters = 1.0, 0
+        stabilize = getattr(self, "_stabilize", False)
         for i in range(max_iters):
+            if stabilize and i > 0:                 # Solver.cpp:1618-1619
+                self.computeStabilizingFlux()
             self.computeFSRSources(i)
             self.transportSweep()
             self.addSourceToScalarFlux()
             k = self.computeKeff()
+            if stabilize and i > 0:                 # Solver.cpp:1633-1634
+                self.stabilizeFlux()
             self.normalizeFluxes()
             residual = self.computeResidual(res_type)
             dk = int(1e5 * (k - k_prev))
