@@ -169,6 +169,10 @@ int b200_upload_tracks_otf(b200_solver* s, const int32_t* trk_2d, const double* 
                            const int64_t* trk_next_fwd, const int64_t* trk_next_bwd,
                            const uint8_t* trk_flags, const uint8_t* trk_bc_fwd, const uint8_t* trk_bc_bwd,
                            int64_t* n_segments);
+/* Solver::setMaxOpticalLength (src/Solver.cpp:550) / TrackGenerator::retrieveMaxOpticalLength: segments the
+ * device traces are cut at this optical length exactly like the reference's on-the-fly kernels cut them
+ * (src/MOCKernel.cpp:216-268, 353-410); default 100 (MAX_OPTICAL_LENGTH).  Takes effect at b200_finalize. */
+int b200_set_max_optical_length(b200_solver* s, double max_tau);
 int b200_get_num_segments(b200_solver* s, int64_t* n_segments);
 /* number of 3D segments of arbitrary tracks over the uploaded geometry: the work estimate a host
  * needs to balance a partition of on-the-fly tracks */

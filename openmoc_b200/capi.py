@@ -50,6 +50,7 @@ SIGNATURES = {
     "b200_upload_otf_geometry": [_i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp],
     "b200_otf_compute_volumes": [_i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "b200_upload_tracks_otf": [_vp] * 10 + [C.POINTER(_i64)],
+    "b200_set_max_optical_length": [_dbl],
     "b200_get_num_segments": [C.POINTER(_i64)],
     "b200_get_segments": [_vp, _vp, _i64, _vp],
     "b200_get_volumes": [_vp, _i64],

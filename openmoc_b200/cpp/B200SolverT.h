@@ -237,6 +237,8 @@ void B200SolverT<Base>::ensureDevice() {
   check(b200_upload_materials(_h, _flat.mat_sigma_t.data(), _flat.mat_sigma_s.data(), _flat.mat_fiss_matrix.data(),
                               _flat.mat_nu_sigma_f.data(), _flat.mat_sigma_f.data(), _flat.mat_chi.data(),
                               _flat.mat_fissionable.data()), "b200_upload_materials");
+  if (_flat.device_otf)
+    check(b200_set_max_optical_length(_h, _track_generator->retrieveMaxOpticalLength()), "b200_set_max_optical_length");
   uploadExtras();
   {
     Cmfd* cmfd = _geometry->getCmfd();

@@ -130,6 +130,9 @@ struct b200_solver {
   DevBuf<int32_t> otf_seg2d_ext, otf_ext_fsr, otf_trk2d, otf_cls, otf_count;
   DevBuf<int64_t> otf_trk2d_off, otf_ext_off;
   int otf_n_axial = 0;
+  double max_tau = 100.;              /* MAX_OPTICAL_LENGTH, src/constants.h:53 */
+  DevBuf<double> otf_max_sigt;
+  bool otf_split = false;             /* the stream was traced with the optical-length cuts */
   int64_t otf_n_trk2d = 0, otf_n_seg2d = 0, otf_n_ext = 0;
   int n_rep = 1;                      /* tally replicas */
   bool capturing = false;             /* inside cudaStreamBeginCapture: no events, no host syncs */
@@ -427,7 +430,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   s->cmfd_fwd.release(); s->cmfd_bwd.release(); s->cmfd_group.release(); s->seg_cmfd.release(); s->currents.release();
   s->otf_seg2d_len.release(); s->otf_mesh.release(); s->otf_l0.release(); s->otf_z0.release(); s->otf_cos.release();
   s->otf_sin.release(); s->otf_volw.release(); s->otf_seg2d_ext.release(); s->otf_ext_fsr.release(); s->otf_trk2d.release();
-  s->otf_cls.release(); s->otf_count.release(); s->otf_trk2d_off.release(); s->otf_ext_off.release();
+  s->otf_max_sigt.release(); s->otf_cls.release(); s->otf_count.release(); s->otf_trk2d_off.release(); s->otf_ext_off.release();
   s->f1tab.release(); s->qst_pad.release(); s->qxyz_pad.release(); s->tally_pad.release(); s->tallym_pad.release();
   s->phi_old.release(); s->fixed.release(); s->stab.release(); s->scratch.release();
   s->qst.release(); s->psi_a.release(); s->psi_b.release(); s->scal.release();
@@ -697,6 +700,7 @@ static OtfGeom otf_geom(b200_solver* s) {
   g.trk_2d = s->otf_trk2d.p; g.trk_l0 = s->otf_l0.p; g.trk_z0 = s->otf_z0.p; g.trk_class = s->otf_cls.p;
   g.cls_cos_theta = s->otf_cos.p; g.cls_sin_theta = s->otf_sin.p;
   g.n_trk = s->n_trk;
+  g.fsr_max_sigma_t = nullptr; g.max_tau = s->max_tau;
   return g;
 }
 
@@ -872,6 +876,54 @@ extern "C" int b200_otf_count_segments(b200_solver* s, int64_t n, const int32_t*
   return 0;
 }
 
+/* count + fill of the solver's own tracks.  with_cuts: cut pieces longer than the maximum optical length
+ * (needs the FSR materials, so b200_finalize repeats the expansion when the cuts change the count) */
+static int otf_expand(b200_solver* s, bool with_cuts) {
+  const int64_t nt = s->n_trk;
+  CU(s->otf_count.alloc(std::max<int64_t>(nt, 1)));
+  OtfGeom g = otf_geom(s);
+  if (with_cuts) g.fsr_max_sigma_t = s->otf_max_sigt.p;
+  std::vector<int32_t> cnt(nt);
+  if (nt > 0) {
+    otf_count_kernel<<<grid_for(nt, 128, 1 << 20), 128, 0, s->stream>>>(g, s->otf_count.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cnt.data(), s->otf_count.p, nt * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  int64_t ns = 0;
+  for (int64_t t = 0; t < nt; t++) ns += cnt[t];
+  if (with_cuts && ns == s->n_seg && s->seg_rec_ready) return 0;      /* nothing to cut: the stream stands */
+  s->h_off.assign(nt + 1, 0);
+  for (int64_t t = 0; t < nt; t++) s->h_off[t + 1] = s->h_off[t] + cnt[t];
+  s->n_seg = ns;
+  s->cfg.n_segments = ns;
+  CU(s->trk_off.upload(s->h_off.data(), nt + 1, s->stream));
+  /* pass 2: the device segment stream, written in place */
+  s->seg_len.release(); s->seg_fsr.release();
+  CU(s->seg_rec.alloc((size_t)ns + 2 * SEG_PAD));
+  otf_pad_kernel<<<1, 2 * SEG_PAD, 0, s->stream>>>(s->seg_rec.p, ns);
+  CU(cudaGetLastError());
+  if (nt > 0) {
+    otf_fill_kernel<<<grid_for(nt, 128, 1 << 20), 128, 0, s->stream>>>(g, s->trk_off.p, s->seg_rec.p + SEG_PAD, s->GP, nullptr, nullptr);
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  s->otf_split = with_cuts;
+  return 0;
+}
+
+/* Solver::setMaxOpticalLength / TrackGenerator::retrieveMaxOpticalLength: segments traced on the device
+ * are cut at this optical length like the reference's on-the-fly kernels cut them */
+extern "C" int b200_set_max_optical_length(b200_solver* s, double max_tau) {
+  NEED(s);
+  if (!(max_tau > 0.)) return fail("b200_set_max_optical_length: the maximum optical length must be positive");
+  s->max_tau = max_tau;
+  if (s->grp != nullptr && s->finalized)
+    for (b200_solver* c : grp_shards(s)) c->max_tau = max_tau;
+  s->finalized = false;
+  return 0;
+}
+
 extern "C" int b200_upload_tracks_otf(b200_solver* s, const int32_t* trk_2d, const double* trk_l0, const double* trk_z0,
                                       const int32_t* trk_azim, const int32_t* trk_polar,
                                       const int64_t* trk_next_fwd, const int64_t* trk_next_bwd,
@@ -908,31 +960,8 @@ extern "C" int b200_upload_tracks_otf(b200_solver* s, const int32_t* trk_2d, con
     }
   }
   if (otf_upload_track_starts(s, nt, trk_2d, trk_l0, trk_z0, trk_azim, trk_polar, s->otf_trk2d, s->otf_l0, s->otf_z0, s->otf_cls)) return 1;
-  /* pass 1: count, prefix sum on the host (one int per track) */
-  CU(s->otf_count.alloc(std::max<int64_t>(nt, 1)));
-  OtfGeom g = otf_geom(s);
-  std::vector<int32_t> cnt(nt);
-  if (nt > 0) {
-    otf_count_kernel<<<grid_for(nt, 128, 1 << 20), 128, 0, s->stream>>>(g, s->otf_count.p);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(cnt.data(), s->otf_count.p, nt * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
-  }
-  CU(cudaStreamSynchronize(s->stream));
-  s->h_off.assign(nt + 1, 0);
-  for (int64_t t = 0; t < nt; t++) s->h_off[t + 1] = s->h_off[t] + cnt[t];
-  const int64_t ns = s->h_off[nt];
-  s->n_seg = ns;
-  s->cfg.n_segments = ns;
-  CU(s->trk_off.upload(s->h_off.data(), nt + 1, s->stream));
-  /* pass 2: the device segment stream, written in place */
-  s->seg_len.release(); s->seg_fsr.release();
-  CU(s->seg_rec.alloc((size_t)ns + 2 * SEG_PAD));
-  otf_pad_kernel<<<1, 2 * SEG_PAD, 0, s->stream>>>(s->seg_rec.p, ns);
-  CU(cudaGetLastError());
-  if (nt > 0) {
-    otf_fill_kernel<<<grid_for(nt, 128, 1 << 20), 128, 0, s->stream>>>(g, s->trk_off.p, s->seg_rec.p + SEG_PAD, s->GP, nullptr, nullptr);
-    CU(cudaGetLastError());
-  }
+  if (otf_expand(s, false)) return 1;
+  const int64_t ns = s->n_seg;
   s->h_azim.assign(trk_azim, trk_azim + nt);
   s->h_polar.assign(trk_polar, trk_polar + nt);
   s->h_next_fwd.assign(trk_next_fwd, trk_next_fwd + nt);
@@ -1019,6 +1048,18 @@ extern "C" int b200_finalize(b200_solver* s) {
     return fail("b200_finalize: tracks, quadrature, FSRs and materials must all be uploaded first");
   const int64_t nt = s->n_trk;
   const int NP = s->NP, P = s->cfg.num_polar, A = s->cfg.num_azim;
+
+  if (s->otf) {
+    /* segments longer than the maximum optical length are cut (MOCKernel.cpp:216-268): now that the FSR
+     * materials are known, recount with the cuts and retrace if they change anything */
+    std::vector<double> mmax(s->n_mat, 0.), fmax(s->n_fsr);
+    for (int m = 0; m < s->n_mat; m++)
+      for (int e = 0; e < s->G; e++) mmax[m] = std::max(mmax[m], s->h_sigma_t[(size_t)m * s->G + e]);
+    for (int64_t r = 0; r < s->n_fsr; r++) fmax[r] = mmax[s->h_fsr_mat[r]];
+    CU(s->otf_max_sigt.upload(fmax.data(), s->n_fsr, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (otf_expand(s, true)) return 1;
+  }
 
   /* angle classes: 2D -> azim; 3D -> (azim, polar).  2D inverse sines follow the
    * ExpEvaluator sharing rule (src/Solver.cpp:763-779): azim a >= A/4 uses A/2-1-a. */

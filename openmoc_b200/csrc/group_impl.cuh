@@ -317,6 +317,7 @@ static int grp_finalize(b200_solver* s) {
     b200_solver* sc = nullptr;
     if (b200_create(&cc, &sc)) return 1;
     g->shard[c] = sc;
+    sc->max_tau = s->max_tau;
     if (g->have_explicit) {
       std::vector<double> len(cc.n_segments);
       std::vector<int32_t> fsr(cc.n_segments);

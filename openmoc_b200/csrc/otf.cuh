@@ -46,6 +46,10 @@ struct OtfGeom {
   const double* __restrict__ cls_cos_theta;    /* signed: negative for downward tracks */
   const double* __restrict__ cls_sin_theta;
   int64_t n_trk;
+  /* maximum optical length of a segment (MOCKernel::_max_tau): longer pieces are cut the way
+   * SegmentationKernel / TransportKernel cut them (src/MOCKernel.cpp:216-268, 353-410); NULL: no cuts */
+  const double* __restrict__ fsr_max_sigma_t;
+  double max_tau;
 };
 
 /* TraverseSegments::findMeshIndex (src/TraverseSegments.cpp:926-956) */
@@ -111,7 +115,19 @@ __device__ __forceinline__ void otf_trace(const OtfGeom& g, int64_t t, Emit emit
       else { d2 = remaining; d3 = seg_dist; zmove = 0; }
       if (d3 > OTF_TINY_MOVE) {
         const int32_t fsr = global ? (int32_t)((int64_t)e * nf + zi) : g.ext_fsr[fsr0 + zi];
-        emit(d3, fsr);
+        double len = d3;
+        if (g.fsr_max_sigma_t != nullptr) {
+          /* num_cuts = length * max_sigma_t * sin(theta) / max_tau + 1 pieces, all but the last of length
+           * max_tau / (max_sigma_t * sin(theta)) (the reference's rule, sin(theta) included) */
+          const double ms = __dmul_rn(g.fsr_max_sigma_t[fsr], sin_theta);
+          const double t = __dmul_rn(len, ms);
+          if (t > g.max_tau) {
+            const int cuts = (int)__ddiv_rn(t, g.max_tau) + 1;
+            const double piece = __ddiv_rn(g.max_tau, ms);
+            for (int c = 0; c < cuts - 1; c++) { emit(piece, fsr); len = __dsub_rn(len, piece); }
+          }
+        }
+        emit(len, fsr);
       }
       z = __dadd_rn(z, __dmul_rn(d3, cos_theta));
       remaining = __dsub_rn(remaining, d2);

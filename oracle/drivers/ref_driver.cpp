@@ -74,6 +74,8 @@ int main(int argc, char** argv) {
     std::string st = arg(argc, argv, "--stabilize", "");
     if (!st.empty()) sscanf(st.c_str(), "%lf:%d", &stab_factor, &stab_type);
   }
+  /* --max-tau X: Solver::setMaxOpticalLength (segments are cut at this optical length) */
+  const double max_tau_arg = atof(arg(argc, argv, "--max-tau", "0"));
   set_axial_layers(atoi(arg(argc, argv, "--axial", "1")));
   Model md = build_model(model_name, dims);
   if (flag(argc, argv, "--groups70")) set_70_group_xs(md);
@@ -144,6 +146,7 @@ int main(int argc, char** argv) {
     if (flag(argc, argv, "--verbose")) cpu.setVerboseIterationReport();
     if (flag(argc, argv, "--balance")) cpu.setKeffFromNeutronBalance();
     if (stab_type >= 0) cpu.stabilizeTransport(stab_factor, (stabilizationType)stab_type);
+    if (max_tau_arg > 0.) cpu.setMaxOpticalLength(max_tau_arg);
     cpu.computeEigenvalue(max_iters, rt);
     Timer timer;
     double cpu_sweep = timer.getSplit("Transport Sweep");
@@ -172,6 +175,7 @@ int main(int argc, char** argv) {
     if (flag(argc, argv, "--verbose")) gpu.setVerboseIterationReport();
     if (flag(argc, argv, "--balance")) gpu.setKeffFromNeutronBalance();
     if (stab_type >= 0) gpu.stabilizeTransport(stab_factor, (stabilizationType)stab_type);
+    if (max_tau_arg > 0.) gpu.setMaxOpticalLength(max_tau_arg);
     gpu.computeEigenvalue(max_iters, rt);
     double gpu_sweep = timer.getSplit("Transport Sweep");
     gpu.getFluxes(phi_gpu.data(), n_fsr * G);

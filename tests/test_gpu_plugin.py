@@ -201,3 +201,13 @@ def test_stabilised_linear_source_through_the_plugin(stab):
              "--stabilize", stab, "--max-iters", "1000"])
     assert r["b200_iters"] == r["cpu_iters"]
     assert r["dk_pcm"] < 1e-3 and r["max_rel_flux_err"] < 1e-7
+
+
+@pytest.mark.parametrize("formation", ["otf-stacks", "otf-tracks", "explicit"])
+def test_maximum_optical_length_cuts(formation):
+    """Solver::setMaxOpticalLength(0.5): the reference's on-the-fly kernels cut every 3D segment longer than
+    that (MOCKernel.cpp:216-268, 353-410); the device tracer cuts the same pieces (b200_set_max_optical_length)."""
+    r = run(["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
+             "--zspacing", "0.9", "--formation", formation, "--max-tau", "0.5", "--solver", "both"])
+    assert r["b200_iters"] == r["cpu_iters"]
+    assert r["dk_pcm"] < 1e-3 and r["max_rel_flux_err"] < 1e-7
