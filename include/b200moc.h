@@ -125,6 +125,20 @@ int b200_upload_materials(b200_solver* s, const double* sigma_t, const double* s
  *   lin_exp_matrix[n_fsrs][nc], source_constants[n_fsrs][nc][G]   (nc = 3 in 2D, 6 in 3D) */
 int b200_upload_linear_source(b200_solver* s, const double* seg_start, const double* trk_direction,
                               const double* lin_exp_matrix, const double* source_constants);
+/* The linear-source pre-pass itself on the device: LinearExpansionGenerator (src/TrackTraversingAlgorithms.cpp:
+ * 470-831) from flattened tracks to the two tables b200_upload_linear_source takes.  Stand-alone (no solver
+ * handle): host arrays in, host arrays out.  azim_spacing / azim_weight are [A/2], polar_spacing / polar_weight /
+ * sin_theta [A/2][P] (Quadrature.cpp:674-750); n_flat_fsrs counts the FSRs whose moment matrix is singular and
+ * which therefore keep a flat source.  The plug-in may keep using the reference's own host pre-pass instead. */
+int b200_ls_prepass(int32_t device, int32_t num_groups, int32_t num_azim, int32_t num_polar, int32_t solve_3d,
+                    int64_t n_tracks, int64_t n_segments, int64_t n_fsrs, int32_t n_materials,
+                    const double* seg_length, const int32_t* seg_fsr, const double* seg_start,
+                    const int64_t* trk_seg_offset, const int32_t* trk_azim, const int32_t* trk_polar,
+                    const double* trk_phi, const double* trk_theta,
+                    const double* azim_spacing, const double* azim_weight, const double* polar_spacing,
+                    const double* polar_weight, const double* sin_theta,
+                    const double* volume, const int32_t* fsr_material, const double* sigma_t,
+                    double* lin_exp_matrix, double* source_constants, int32_t* n_flat_fsrs);
 /* CMFD surface-current tally inside the sweep (Cmfd::tallyCurrent, src/Cmfd.h:572-670; the
  * reference calls it per segment from TransportSweep::onTrack).  seg_cmfd_fwd/bwd are
  * segment::_cmfd_surface_fwd/_bwd (src/Track.h:42-46: cell*26 + surface, or -1).  The tally

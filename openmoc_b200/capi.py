@@ -107,7 +107,7 @@ SIGNATURES = {
 }
 #: every symbol include/b200moc.h declares (checked by tests/test_abi.py)
 EXPORTS = sorted(list(SIGNATURES) + ["b200_last_error", "b200_version", "b200_device_count", "b200_create",
-                                      "b200_eval_expF1", "b200_measure_ceilings"])
+                                      "b200_eval_expF1", "b200_measure_ceilings", "b200_ls_prepass"])
 
 
 def load():
@@ -129,6 +129,8 @@ def load():
     L.b200_create.argtypes = [C.POINTER(Config), C.POINTER(_vp)]
     L.b200_eval_expF1.restype = C.c_int
     L.b200_eval_expF1.argtypes = [_i32, _i32, _vp, _i64, _vp]
+    L.b200_ls_prepass.restype = C.c_int
+    L.b200_ls_prepass.argtypes = [_i32, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i32] + [_vp] * 16 + [_vp, _vp, C.POINTER(_i32)]
     L.b200_measure_ceilings.restype = C.c_int
     L.b200_measure_ceilings.argtypes = [_i32, _i64, C.POINTER(_dbl), C.POINTER(_dbl)]
     for name, args in SIGNATURES.items():

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -26,6 +27,7 @@
 #include "otf.cuh"
 #include "microbench.cuh"
 #include "group.cuh"
+#include "ls_prepass.cuh"
 
 using namespace b200;
 
@@ -2306,6 +2308,72 @@ extern "C" int b200_eval_expF1(int32_t device, int32_t precision, const double* 
   eval_expf1_kernel<<<grid_for(n, 256), 256>>>(dx.p, dout.p, n, precision);
   CU(cudaGetLastError());
   CU(cudaMemcpy(out, dout.p, n * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* linear-source pre-pass on the device (ls_prepass.cuh)                        */
+/* ------------------------------------------------------------------------- */
+extern "C" int b200_ls_prepass(int32_t device, int32_t num_groups, int32_t num_azim, int32_t num_polar, int32_t solve_3d,
+                               int64_t n_tracks, int64_t n_segments, int64_t n_fsrs, int32_t n_materials,
+                               const double* seg_length, const int32_t* seg_fsr, const double* seg_start,
+                               const int64_t* trk_seg_offset, const int32_t* trk_azim, const int32_t* trk_polar,
+                               const double* trk_phi, const double* trk_theta,
+                               const double* azim_spacing, const double* azim_weight, const double* polar_spacing,
+                               const double* polar_weight, const double* sin_theta,
+                               const double* volume, const int32_t* fsr_material, const double* sigma_t,
+                               double* lin_exp_matrix, double* source_constants, int32_t* n_flat_fsrs) {
+  if (!seg_length || !seg_fsr || !seg_start || !trk_seg_offset || !trk_azim || !trk_polar || !trk_phi || !trk_theta ||
+      !azim_spacing || !azim_weight || !polar_spacing || !polar_weight || !sin_theta || !volume || !fsr_material ||
+      !sigma_t || !lin_exp_matrix || !source_constants)
+    return fail("b200_ls_prepass: null argument");
+  if (num_groups < 1 || n_tracks < 0 || n_segments < 0 || n_fsrs < 1 || n_materials < 1) return fail("b200_ls_prepass: bad size");
+  CU(cudaSetDevice(device));
+  const int nc = solve_3d ? 6 : 3, A2 = num_azim / 2;
+  DevBuf<double> d_len, d_start, d_phi, d_theta, d_as, d_aw, d_ps, d_pw, d_st, d_vol, d_sig, d_lem, d_ilem, d_sc;
+  DevBuf<int32_t> d_fsr, d_azim, d_polar, d_mat;
+  DevBuf<int64_t> d_off;
+  DevBuf<int> d_flat;
+  struct Guard {
+    std::vector<std::function<void()>> f;
+    ~Guard() { for (auto& g : f) g(); }
+  } guard;
+  auto own = [&](auto& b) { guard.f.push_back([&b]() { b.release(); }); };
+  own(d_len); own(d_start); own(d_phi); own(d_theta); own(d_as); own(d_aw); own(d_ps); own(d_pw); own(d_st); own(d_vol);
+  own(d_sig); own(d_lem); own(d_ilem); own(d_sc); own(d_fsr); own(d_azim); own(d_polar); own(d_mat); own(d_off); own(d_flat);
+  cudaStream_t st = nullptr;
+  CU(d_len.upload(seg_length, n_segments, st)); CU(d_fsr.upload(seg_fsr, n_segments, st));
+  CU(d_start.upload(seg_start, (size_t)n_segments * 3, st));
+  CU(d_off.upload(trk_seg_offset, n_tracks + 1, st)); CU(d_azim.upload(trk_azim, n_tracks, st));
+  CU(d_polar.upload(trk_polar, n_tracks, st)); CU(d_phi.upload(trk_phi, n_tracks, st)); CU(d_theta.upload(trk_theta, n_tracks, st));
+  CU(d_as.upload(azim_spacing, A2, st)); CU(d_aw.upload(azim_weight, A2, st));
+  CU(d_ps.upload(polar_spacing, (size_t)A2 * num_polar, st)); CU(d_pw.upload(polar_weight, (size_t)A2 * num_polar, st));
+  CU(d_st.upload(sin_theta, (size_t)A2 * num_polar, st));
+  CU(d_vol.upload(volume, n_fsrs, st)); CU(d_mat.upload(fsr_material, n_fsrs, st));
+  CU(d_sig.upload(sigma_t, (size_t)n_materials * num_groups, st));
+  CU(d_lem.alloc((size_t)n_fsrs * nc)); CU(d_ilem.alloc((size_t)n_fsrs * nc)); CU(d_sc.alloc((size_t)n_fsrs * nc * num_groups));
+  CU(d_flat.alloc(1));
+  CU(cudaMemset(d_lem.p, 0, (size_t)n_fsrs * nc * 8));
+  CU(cudaMemset(d_sc.p, 0, (size_t)n_fsrs * nc * num_groups * 8));
+  CU(cudaMemset(d_flat.p, 0, sizeof(int)));
+  LsPrepassArgs a;
+  a.G = num_groups; a.P = num_polar; a.solve_3d = solve_3d; a.nc = nc;
+  a.n_trk = n_tracks; a.n_seg = n_segments; a.n_fsr = n_fsrs;
+  a.seg_len = d_len.p; a.seg_fsr = d_fsr.p; a.seg_start = d_start.p; a.trk_off = d_off.p; a.trk_azim = d_azim.p;
+  a.trk_polar = d_polar.p; a.trk_phi = d_phi.p; a.trk_theta = d_theta.p; a.azim_spacing = d_as.p; a.azim_weight = d_aw.p;
+  a.polar_spacing = d_ps.p; a.polar_weight = d_pw.p; a.sin_theta = d_st.p; a.volume = d_vol.p; a.fsr_mat = d_mat.p;
+  a.sigma_t = d_sig.p; a.lem = d_lem.p; a.src_const = d_sc.p;
+  if (n_tracks > 0) {
+    ls_prepass_kernel<<<grid_for(n_tracks, 128, 1 << 20), 128>>>(a);
+    CU(cudaGetLastError());
+  }
+  ls_invert_kernel<<<grid_for(n_fsrs, 256), 256>>>(d_lem.p, d_vol.p, d_ilem.p, n_fsrs, solve_3d, d_flat.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(lin_exp_matrix, d_ilem.p, (size_t)n_fsrs * nc * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(source_constants, d_sc.p, (size_t)n_fsrs * nc * num_groups * 8, cudaMemcpyDeviceToHost));
+  int nf = 0;
+  CU(cudaMemcpy(&nf, d_flat.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (n_flat_fsrs) *n_flat_fsrs = nf;
   return 0;
 }
 

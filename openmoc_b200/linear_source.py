@@ -1,5 +1,7 @@
-"""Host-side pre-pass of the linear-source solver: the per-FSR linear expansion matrices and
-source constants the device kernels read (`b200_upload_linear_source`).
+"""Pre-pass of the linear-source solver: the per-FSR linear expansion matrices and source constants the
+sweep and closure kernels read (`b200_upload_linear_source`).  `linear_expansion_tables_device` runs it on
+the GPU (csrc/ls_prepass.cuh) and is what the solver uses; `linear_expansion_tables` is the numpy
+restatement the CPU tests check against the oracle and the GPU tests check the device version against.
 
 Restates `LinearExpansionGenerator::onTrack` / `execute`
 (src/TrackTraversingAlgorithms.cpp:536-831) on flattened tracks, vectorised over segments with
@@ -45,6 +47,28 @@ def track_directions(ft: FlatTracks) -> np.ndarray:
     else:
         st, ct = np.ones_like(phi), np.zeros_like(phi)
     return np.stack([np.cos(phi) * st, np.sin(phi) * st, ct], axis=1)
+
+
+def linear_expansion_tables_device(ft: FlatTracks, device: int = 0):
+    """The same tables from the device kernels (csrc/ls_prepass.cuh through b200_ls_prepass): what
+    B200Solver(linear_source=True) uses.  Returns (lin_exp, src_const, n_flat) like linear_expansion_tables."""
+    import ctypes as C
+    from . import capi
+    a = ft.arrays
+    G, P = ft.num_groups, ft.num_polar
+    nc = 6 if ft.solve_3d else 3
+    c = lambda k, dt: np.ascontiguousarray(a[k], dtype=dt)
+    ins = [c("seg_length", "f8"), c("seg_fsr", "i4"), c("seg_start", "f8"), c("trk_seg_offset", "i8"), c("trk_azim", "i4"),
+           c("trk_polar", "i4"), c("trk_phi", "f8"), c("trk_theta", "f8"), c("quad_azim_spacing", "f8"),
+           c("quad_azim_weight", "f8"), c("quad_polar_spacing", "f8"), c("quad_polar_weight", "f8"),
+           c("quad_sin_theta", "f8"), c("fsr_volume", "f8"), c("fsr_mat", "i4"), c("mat_sigma_t", "f8")]
+    lin_exp = np.zeros(ft.n_fsrs * nc)
+    src_const = np.zeros(ft.n_fsrs * nc * G)
+    n_flat = C.c_int32()
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    capi.check(capi.load().b200_ls_prepass(device, G, ft.num_azim, P, int(ft.solve_3d), ft.n_tracks, ft.n_segments, ft.n_fsrs,
+                                           ft.n_materials, *[p(x) for x in ins], p(lin_exp), p(src_const), C.byref(n_flat)))
+    return lin_exp, src_const, int(n_flat.value)
 
 
 def linear_expansion_tables(ft: FlatTracks):

@@ -94,12 +94,12 @@ class B200Solver:
         if self._linear:
             if deterministic:
                 raise B200Error("the deterministic tally is not available with the linear source")
-            from .linear_source import linear_expansion_tables, track_directions
+            from .linear_source import linear_expansion_tables_device, track_directions
             if tracks.arrays.get("seg_start", np.zeros(0)).size != 3 * tracks.n_segments:
                 raise B200Error("linear source needs the segment starting points (seg_start) in the track file")
             # the pre-pass tables are sums over ALL tracks (replicated); starting points and directions
             # follow this rank's shard below
-            lin_exp, src_const, self.num_flat_fsrs = linear_expansion_tables(global_tracks or tracks)
+            lin_exp, src_const, self.num_flat_fsrs = linear_expansion_tables_device(global_tracks or tracks, device)
         if self._world > 1:
             from .partition import partition_by_azim_pair, partition_by_chain, partition_by_track
             if partition == "chain":

@@ -411,3 +411,16 @@ def test_linear_source_stabilisation_matches_oracle_and_reference():
         if stab_type == 2:
             assert n == ref["iterations"] and abs(gpu.getKeff() - ref["keff"]) * 1e5 < 1e-3
             assert rel_err(gpu.getFluxes(), np.array(ref["fluxes"])) < 1e-8
+
+
+@pytest.mark.parametrize("name", ["simple_lattice_ls", "lattice3d_ls_7g", "lattice3d_ls_70g"])
+def test_linear_source_prepass_on_device(name):
+    """LinearExpansionGenerator on the device (b200_ls_prepass) against its numpy restatement, which
+    tests/test_host_logic.py pins to the oracle's (and thereby the reference's) tables"""
+    from openmoc_b200.linear_source import linear_expansion_tables, linear_expansion_tables_device
+    ft, _ = load_case(name)
+    a, b = linear_expansion_tables_device(ft), linear_expansion_tables(ft)
+    assert a[2] == b[2]                                   # FSRs that fall back to a flat source
+    scale = max(np.abs(b[0]).max(), 1e-300)
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-9, atol=1e-11 * scale)
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-10, atol=1e-14 * np.abs(b[1]).max())
