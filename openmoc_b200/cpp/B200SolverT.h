@@ -51,6 +51,8 @@ protected:
   void pushFixedSourcesIfDirty();
   void pushKeff();
   void handCurrentsToCmfd();
+  void tallyStartingCurrents();
+  std::vector<float> _start_flux_host;
   void pushHostFluxIfNewer();
 
   /* customisation points of the linear-source subclass */
@@ -346,8 +348,8 @@ void B200SolverT<Base>::initializeCmfd() {
     check(b200_set_cmfd_groups(_h, NULL, 0, 0), "b200_set_cmfd_groups");
     return;
   }
-  if (_cmfd->isSigmaTRebalanceOn())
-    log_printf(ERROR, "CMFD sigma-t rebalance (tallyStartingCurrents) is not supported by the B200 solvers");
+  if (_cmfd->isSigmaTRebalanceOn() && dynamic_cast<TrackGenerator3D*>(_track_generator) == NULL)
+    log_printf(ERROR, "Starting currents not implemented yet for 2D MOC");     /* CPUSolver.cpp:532, the reference's own limit */
   std::vector<int32_t> map(_num_groups);
   for (int e = 0; e < _num_groups; e++) map[e] = _cmfd->getCmfdGroup(e);
   check(b200_set_cmfd_groups(_h, map.data(), _cmfd->getNumCmfdGroups(), _cmfd->getNumCells()),
@@ -529,12 +531,40 @@ template <class Base>
 void B200SolverT<Base>::transportSweep() {
   pushHostFluxIfNewer();
   if (_cmfd_active) _cmfd->zeroCurrents();       /* CPUSolver.cpp:2343-2344 */
+  if (_cmfd_active && _cmfd->isSigmaTRebalanceOn()) tallyStartingCurrents();   /* CPUSolver.cpp:2356-2357 */
   _timer->startTimer();
   check(b200_transport_sweep(_h), "transportSweep");
   check(b200_synchronize(_h), "transportSweep");
   _timer->stopTimer();
   _timer->recordSplit("Transport Sweep");
   _mirror_stale = true;
+}
+
+/* CMFD sigma-t rebalance: the currents the starting angular fluxes carry into the boundary CMFD cells
+ * (CPUSolver::tallyStartingCurrents, src/CPUSolver.cpp:498-537).  The start fluxes come back from the
+ * device once per sweep (n_tracks * 2 * G floats); Cmfd::tallyStartingCurrent (src/Cmfd.cpp:5412) locates the
+ * cell and tallies, exactly as for the reference's own solver. */
+template <class Base>
+void B200SolverT<Base>::tallyStartingCurrents() {
+  TrackGenerator3D* tg3 = dynamic_cast<TrackGenerator3D*>(_track_generator);
+  if (tg3 == NULL) log_printf(ERROR, "Starting currents not implemented yet for 2D MOC");
+  const long nt = _flat.n_tracks;
+  const int F = _num_groups;
+  _start_flux_host.resize((size_t)nt * 2 * F);
+  check(b200_get_start_fluxes(_h, _start_flux_host.data(), (long)_start_flux_host.size()), "b200_get_start_fluxes");
+  Quadrature* quad = _track_generator->getQuadrature();
+#pragma omp parallel for schedule(static)
+  for (long t = 0; t < nt; t++) {
+    TrackStackIndexes tsi;
+    Track3D track;
+    tg3->getTSIByIndex(t, &tsi);
+    tg3->getTrackOTF(&track, &tsi);
+    const double azim = track.getPhi(), polar = track.getTheta();
+    const double dx = cos(azim) * sin(polar) * TINY_MOVE, dy = sin(azim) * sin(polar) * TINY_MOVE, dz = cos(polar) * TINY_MOVE;
+    const double weight = quad->getWeightInline(track.getAzimIndex(), track.getPolarIndex());
+    _cmfd->tallyStartingCurrent(track.getStart(), dx, dy, dz, &_start_flux_host[(size_t)(t * 2) * F], weight);
+    _cmfd->tallyStartingCurrent(track.getEnd(), -dx, -dy, -dz, &_start_flux_host[(size_t)(t * 2 + 1) * F], weight);
+  }
 }
 
 /* ------------------------------ public API ------------------------------- */

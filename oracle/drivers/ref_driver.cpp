@@ -97,6 +97,7 @@ int main(int argc, char** argv) {
     }
     if (!flag(argc, argv, "--no-knearest")) cmfd->setKNearest(3);
     if (flag(argc, argv, "--no-flux-limiting")) cmfd->useFluxLimiting(false);   /* diagnostics */
+    if (flag(argc, argv, "--rebalance")) cmfd->rebalanceSigmaT(true);          /* starting currents tallied every sweep */
     geometry->setCmfd(cmfd);
   }
   geometry->initializeFlatSourceRegions();

@@ -211,3 +211,17 @@ def test_maximum_optical_length_cuts(formation):
              "--zspacing", "0.9", "--formation", formation, "--max-tau", "0.5", "--solver", "both"])
     assert r["b200_iters"] == r["cpu_iters"]
     assert r["dk_pcm"] < 1e-3 and r["max_rel_flux_err"] < 1e-7
+
+
+@pytest.mark.parametrize("devices", [None, "0,0"])
+def test_cmfd_sigma_t_rebalance_starting_currents(devices):
+    """Cmfd::rebalanceSigmaT(true): every sweep starts by tallying the currents the starting angular fluxes
+    carry into the boundary CMFD cells (CPUSolver::tallyStartingCurrents, src/CPUSolver.cpp:498-537); the
+    plug-in feeds Cmfd::tallyStartingCurrent from the device's start fluxes."""
+    args = ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
+            "--zspacing", "0.9", "--cmfd", "2x2x2", "--rebalance", "--solver", "both"]
+    if devices:
+        args += ["--devices", devices]
+    r = run(args)
+    assert r["b200_iters"] == r["cpu_iters"]
+    assert r["dk_pcm"] < 1e-2 and r["max_rel_flux_err"] < 2e-5
