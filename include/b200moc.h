@@ -147,6 +147,61 @@ int b200_upload_cmfd_surfaces(b200_solver* s, const int32_t* seg_cmfd_fwd, const
 int b200_set_cmfd_groups(b200_solver* s, const int32_t* moc_to_cmfd_group, int32_t num_cmfd_groups,
                          int64_t num_cmfd_cells);   /* num_cmfd_groups <= 0 switches the tally off */
 int b200_get_cmfd_currents(b200_solver* s, double* out, int64_t n);
+
+/* ---- CMFD acceleration on the device ----
+ * Replaces what Cmfd::computeKeff (src/Cmfd.cpp:1192-1295) does between two sweeps: splitVertexCurrents /
+ * splitEdgeCurrents (:2126-2331), collapseXS (:720-1007), constructMatrices (:1353-1500, with
+ * getSurfaceDiffusionCoefficient :1048-1177 and computeLarsensEDCFactor :1625), eigenvalueSolve + linearSolve
+ * (src/linalg.cpp:25-163, 179-395), rescaleFlux (:1304) and updateMOCFlux (:1509-1580, getUpdateRatio /
+ * getFluxRatio :3178-3290) - on the scalar flux and the surface currents the sweep left in HBM.  The Cmfd object
+ * of the host keeps its role as the description of the mesh: the plug-in reads the lattice, the group structure,
+ * the FSR lists of the cells and the k-nearest stencils from it and hands them over once.
+ * Not reproduced (the plug-in then keeps the host Cmfd): domain decomposition, the sigma-t rebalance, the
+ * neutron-balance check, the few-group backup solver (a diverged solve keeps the last CMFD k_eff and skips the
+ * flux update, like the reference when the backup fails too). */
+typedef struct b200_cmfd_config {
+  int32_t num_x, num_y, num_z;          /* Cmfd::setLatticeStructure; num_z = 1 in 2D (Cmfd.cpp:3860-3869) */
+  int32_t num_cmfd_groups;              /* must equal b200_set_cmfd_groups' */
+  int32_t boundaries[6];                /* B200_BC_* per face SURFACE_X_MIN .. SURFACE_Z_MAX (src/constants.h:120-125) */
+  int32_t linear_source;                /* Cmfd::setFluxMoments was called: no Larsen factor, moments are scaled too */
+  int32_t flux_limiting;                /* Cmfd::useFluxLimiting, default on */
+  int32_t centroid_update;              /* Cmfd::setCentroidUpdateOn + setKNearest: needs b200_cmfd_set_stencils */
+  int32_t axial_interpolation;          /* Cmfd::useAxialInterpolation 0 / 1 / 2: needs b200_cmfd_set_axial_interpolants */
+  int32_t num_unbounded_iterations;     /* Cmfd::setNumUnboundedIterations */
+  int32_t num_azim_2, num_polar_2;      /* quadrature of the Larsen factor */
+  double sor_factor;                    /* Cmfd::setSORRelaxationFactor */
+  double relaxation_factor;             /* Cmfd::setCMFDRelaxationFactor, default 0.7 */
+  double linalg_tolerance;              /* MIN_LINALG_TOLERANCE = LINALG_TOL of the build (src/constants.h:77) */
+} b200_cmfd_config;
+/* widths_{x,y,z}: cell widths (Cmfd::_cell_widths_*); group_indices[ncg+1]: first MOC group of every CMFD group
+ * (Cmfd::_group_indices); cell_fsr_offset[n_cells+1] / cell_fsrs: Cmfd::getCellFSRs in its own order;
+ * azim_weight[num_azim_2], sin_theta / polar_weight[num_azim_2*num_polar_2]: Quadrature::getAzimWeight /
+ * getSinTheta / getPolarWeight.  Call after b200_set_cmfd_groups. */
+int b200_cmfd_configure(b200_solver* s, const b200_cmfd_config* cfg, const double* widths_x, const double* widths_y,
+                        const double* widths_z, const int32_t* group_indices, const int64_t* cell_fsr_offset,
+                        const int32_t* cell_fsrs, const double* azim_weight, const double* sin_theta,
+                        const double* polar_weight);
+/* k-nearest stencils (Cmfd::generateKNearestStencils, Cmfd.cpp:2887-2960) as getUpdateRatio reads them: for FSR r
+ * the entries [offset[r], offset[r+1]) are the stencil cells other than the FSR's own (already resolved with
+ * getCellByStencil) with their weights; own_weight[r] is the weight of the first entry of the stencil and
+ * stencil_size[r] its length (Cmfd.cpp:3178-3210). */
+int b200_cmfd_set_stencils(b200_solver* s, const int64_t* offset, const int32_t* cell, const double* weight,
+                           const double* own_weight, const int32_t* stencil_size);
+int b200_cmfd_set_axial_interpolants(b200_solver* s, const double* interpolants /* [n_fsrs*3] */);
+int b200_cmfd_set_keff(b200_solver* s, double k_eff);       /* Cmfd::setKeff */
+typedef struct b200_cmfd_stats {      /* struct ConvergenceData, src/linalg.h:31-68 */
+  double pf, cmfd_res_1, cmfd_res_end, linear_res_1, linear_res_end;
+  int32_t cmfd_iters, linear_iters_1, linear_iters_end, linear_iters_total, failed, bad_tallies;
+} b200_cmfd_stats;
+/* One CMFD solve + prolongation (Cmfd::computeKeff(moc_iteration)); k_eff of the solver becomes the CMFD one
+ * (Solver.cpp:1628).  source_threshold: Cmfd::setSourceConvergenceThreshold's value; < 0: the value the device
+ * keeps (0.01 x the last residual, Solver.cpp:1671-1675).  k_eff / stats may be NULL (no host synchronisation). */
+int b200_cmfd_solve(b200_solver* s, int32_t moc_iteration, double source_threshold, double* k_eff,
+                    b200_cmfd_stats* stats);
+/* Cmfd::getVertexSplitSurfaces / getEdgeSplitSurfaces (Cmfd.cpp:2348-2480) as this library restates them: the
+ * (cell*26 + surface) slots an edge or vertex current of `cell` is split onto.  Host-only; used by the tests. */
+int b200_cmfd_split_targets(int32_t num_x, int32_t num_y, int32_t num_z, const int32_t* boundaries, int32_t cell,
+                            int32_t surface, int32_t* targets /* [6] */, int32_t* num_targets);
 /* flux moments in the reference layout [r*3G + c*G + e] (src/CPULSSolver.h:22) */
 int b200_get_flux_moments(b200_solver* s, double* out, int64_t n);
 int b200_set_flux_moments(b200_solver* s, const double* in, int64_t n);

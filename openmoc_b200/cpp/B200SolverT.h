@@ -17,6 +17,7 @@
 #include "TrackGenerator3D.h"
 #include "Cmfd.h"
 #include "b200_flatten.h"
+#include "b200_cmfd_view.h"
 #include "../../include/b200moc.h"
 
 template <class Base>
@@ -40,6 +41,10 @@ protected:
   double _flattened_key;           /* fingerprint of the tracks the device image was built from */
   bool _materials_dirty, _fixed_dirty, _mirror_stale;
   bool _cmfd_active, _host_flux_newer;
+  bool _cmfd_on_device;            /* user switch (setCmfdOnDevice); B200_HOST_CMFD=1 forces the host Cmfd */
+  bool _cmfd_device_active;        /* this solve: collapse, diffusion solve and prolongation run on the device */
+  double _cmfd_device_keff;        /* the CMFD k_eff the device holds */
+  Cmfd* _cmfd_suspended;           /* Cmfd whose flux update is switched off while the device does its work */
   std::vector<double> _cmfd_currents;
   int _device, _precision;
   std::vector<int> _devices;       /* more than one entry: one handle drives them all (b200_set_devices) */
@@ -51,6 +56,8 @@ protected:
   void pushFixedSourcesIfDirty();
   void pushKeff();
   void handCurrentsToCmfd();
+  void configureDeviceCmfd();
+  void restoreCmfdFluxUpdate();
   void tallyStartingCurrents();
   std::vector<float> _start_flux_host;
   void pushHostFluxIfNewer();
@@ -134,6 +141,16 @@ public:
     _devices = devices;
     if (_h != NULL) { b200_destroy(_h); _h = NULL; }      /* the device image is rebuilt on the next solve */
   }
+  /** CMFD collapse / diffusion eigenvalue solve / prolongation on the device (default) or by the reference's
+   *  host Cmfd fed with the device's fluxes and currents.  The host path also serves what the device path does
+   *  not reproduce: the sigma-t rebalance and the neutron-balance check. */
+  void setCmfdOnDevice(bool on) { _cmfd_on_device = on; }
+  bool isCmfdOnDevice() { return _cmfd_device_active; }
+  /** Solver::computeEigenvalue is not virtual; this overload only restores Cmfd::isFluxUpdateOn afterwards. */
+  void computeEigenvalue(int max_iters = 1000, residualType res_type = FISSION_SOURCE) {
+    Base::computeEigenvalue(max_iters, res_type);
+    restoreCmfdFluxUpdate();
+  }
   /** Copy phi, old phi and q from the device into the base-class host arrays. */
   void syncHostMirrors();
   /** Fused device-side source iteration (b200_compute_eigenvalue): same results as
@@ -154,6 +171,10 @@ B200SolverT<Base>::B200SolverT(TrackGenerator* track_generator, int device, int 
   _fixed_dirty = false;
   _mirror_stale = false;
   _cmfd_active = false;
+  _cmfd_on_device = true;
+  _cmfd_device_active = false;
+  _cmfd_suspended = NULL;
+  _cmfd_device_keff = 1.;
   _host_flux_newer = false;
   _device = device;
   _precision = precision;
@@ -163,6 +184,7 @@ B200SolverT<Base>::B200SolverT(TrackGenerator* track_generator, int device, int 
 
 template <class Base>
 B200SolverT<Base>::~B200SolverT() {
+  restoreCmfdFluxUpdate();
   if (_h != NULL) b200_destroy(_h);
 }
 
@@ -342,8 +364,10 @@ void B200SolverT<Base>::initializeCmfd() {
    * _reduced_sources, volumes, materials): the CMFD solve stays the reference's host code,
    * fed every iteration with the device's fluxes and surface currents (addSourceToScalarFlux)
    * and read back before the next device step (pushHostFluxIfNewer). */
+  restoreCmfdFluxUpdate();
   Base::initializeCmfd();
   _cmfd_active = (_cmfd != NULL && _cmfd->isFluxUpdateOn());
+  _cmfd_device_active = false;
   if (!_cmfd_active) {
     check(b200_set_cmfd_groups(_h, NULL, 0, 0), "b200_set_cmfd_groups");
     return;
@@ -355,6 +379,63 @@ void B200SolverT<Base>::initializeCmfd() {
   check(b200_set_cmfd_groups(_h, map.data(), _cmfd->getNumCmfdGroups(), _cmfd->getNumCells()),
         "b200_set_cmfd_groups");
   _cmfd_currents.assign((size_t)_cmfd->getNumCells() * NUM_SURFACES * _cmfd->getNumCmfdGroups(), 0.);
+  configureDeviceCmfd();
+}
+
+/* Hands the mesh, the group structure, the FSR lists, the options and the k-nearest stencils of the Cmfd object
+ * to the device (b200_cmfd_configure) and takes the per-iteration work away from it: with the flux update
+ * switched off the base-class loop calls the virtual computeKeff() instead of Cmfd::computeKeff
+ * (Solver.cpp:1627-1630), which is where the device solve runs. */
+template <class Base>
+void B200SolverT<Base>::configureDeviceCmfd() {
+  const char* env = getenv("B200_HOST_CMFD");
+  if (!_cmfd_on_device || (env != NULL && atoi(env) != 0)) return;
+  B200CmfdView v;
+  b200_read_cmfd(_cmfd, _num_FSRs, &v);
+  if (v.balance_sigma_t || v.check_neutron_balance || _geometry->isDomainDecomposed()) return;   /* host Cmfd */
+  b200_cmfd_config c;
+  memset(&c, 0, sizeof c);
+  c.num_x = v.num_x; c.num_y = v.num_y; c.num_z = v.num_z;
+  c.num_cmfd_groups = v.num_cmfd_groups;
+  for (int s = 0; s < NUM_FACES; s++) c.boundaries[s] = v.boundaries[s];
+  c.linear_source = v.linear_source;
+  c.flux_limiting = v.flux_limiting;
+  c.centroid_update = v.centroid_update;
+  c.axial_interpolation = v.num_z >= 3 ? v.use_axial_interpolation : 0;
+  c.num_unbounded_iterations = v.num_unbounded_iterations;
+  c.sor_factor = v.sor_factor;
+  c.relaxation_factor = v.relaxation_factor;
+  c.linalg_tolerance = MIN_LINALG_TOLERANCE;
+  Quadrature* quad = _track_generator->getQuadrature();
+  c.num_azim_2 = quad->getNumAzimAngles() / 2;
+  c.num_polar_2 = quad->getNumPolarAngles() / 2;
+  std::vector<double> wa(c.num_azim_2), st((size_t)c.num_azim_2 * c.num_polar_2), wp(st.size());
+  for (int a = 0; a < c.num_azim_2; a++) {
+    wa[a] = quad->getAzimWeight(a);
+    for (int p = 0; p < c.num_polar_2; p++) {
+      st[a * c.num_polar_2 + p] = quad->getSinTheta(a, p);
+      wp[a * c.num_polar_2 + p] = quad->getPolarWeight(a, p);
+    }
+  }
+  check(b200_cmfd_configure(_h, &c, v.widths_x.data(), v.widths_y.data(), v.widths_z.data(), v.group_indices.data(),
+                            v.cell_fsr_offset.data(), v.cell_fsrs.data(), wa.data(), st.data(), wp.data()),
+        "b200_cmfd_configure");
+  if (v.centroid_update)
+    check(b200_cmfd_set_stencils(_h, v.st_offset.data(), v.st_cell.data(), v.st_weight.data(), v.st_own.data(),
+                                 v.st_size.data()), "b200_cmfd_set_stencils");
+  if (c.axial_interpolation)
+    check(b200_cmfd_set_axial_interpolants(_h, v.axial_interpolants.data()), "b200_cmfd_set_axial_interpolants");
+  check(b200_cmfd_set_keff(_h, v.k_eff), "b200_cmfd_set_keff");
+  _cmfd_device_keff = v.k_eff;
+  _cmfd->setFluxUpdateOn(false);
+  _cmfd_suspended = _cmfd;
+  _cmfd_device_active = true;
+}
+
+template <class Base>
+void B200SolverT<Base>::restoreCmfdFluxUpdate() {
+  if (_cmfd_suspended != NULL) _cmfd_suspended->setFluxUpdateOn(true);
+  _cmfd_suspended = NULL;
 }
 
 /* Device tallies -> Cmfd.  Faces go straight into the public current Vector
@@ -508,6 +589,30 @@ double B200SolverT<Base>::computeResidual(residualType res_type) {
 
 template <class Base>
 void B200SolverT<Base>::computeKeff() {
+  if (_cmfd_device_active) {
+    /* Cmfd::computeKeff(_num_iterations) on the device; the threshold is the one the base-class loop keeps
+     * setting on the Cmfd object (Solver.cpp:1159, 1674) */
+    b200_cmfd_stats st;
+    const double host_k = b200_cmfd_keff(_cmfd);          /* Cmfd::setKeff since the last solve (Solver.cpp:1249) */
+    if (host_k != _cmfd_device_keff) check(b200_cmfd_set_keff(_h, host_k), "b200_cmfd_set_keff");
+    check(b200_cmfd_solve(_h, _num_iterations, b200_cmfd_source_threshold(_cmfd), &_k_eff, &st), "b200_cmfd_solve");
+    if (st.failed)
+      log_printf(WARNING, "The CMFD solve on the device did not converge in MOC iteration %d: k_eff and fluxes "
+                 "are left as they are", _num_iterations);
+    if (st.bad_tallies > 0)
+      log_printf(WARNING_ONCE, "Negative or zero reaction tally calculated in %d CMFD cell-groups", st.bad_tallies);
+    ConvergenceData* cd = b200_cmfd_convergence_data(_cmfd);
+    if (cd != NULL) {
+      cd->pf = st.pf; cd->cmfd_res_1 = st.cmfd_res_1; cd->cmfd_res_end = st.cmfd_res_end;
+      cd->linear_res_1 = st.linear_res_1; cd->linear_res_end = st.linear_res_end;
+      cd->cmfd_iters = st.cmfd_iters; cd->linear_iters_1 = st.linear_iters_1; cd->linear_iters_end = st.linear_iters_end;
+    }
+    _cmfd->setKeff(_k_eff);
+    _cmfd_device_keff = _k_eff;
+    _device_keff = _k_eff;
+    _mirror_stale = true;
+    return;
+  }
   pushKeff();
   check(b200_compute_keff(_h, &_k_eff), "computeKeff");
   _device_keff = _k_eff;
@@ -517,7 +622,7 @@ template <class Base>
 void B200SolverT<Base>::addSourceToScalarFlux() {
   check(b200_add_source_to_scalar_flux(_h), "addSourceToScalarFlux");
   _mirror_stale = true;
-  if (_cmfd_active) {
+  if (_cmfd_active && !_cmfd_device_active) {
     /* the base-class loop calls _cmfd->computeKeff() right after this step (Solver.cpp:1628-1629) */
     syncHostMirrors();
     handCurrentsToCmfd();
@@ -530,8 +635,8 @@ void B200SolverT<Base>::addSourceToScalarFlux() {
 template <class Base>
 void B200SolverT<Base>::transportSweep() {
   pushHostFluxIfNewer();
-  if (_cmfd_active) _cmfd->zeroCurrents();       /* CPUSolver.cpp:2343-2344 */
-  if (_cmfd_active && _cmfd->isSigmaTRebalanceOn()) tallyStartingCurrents();   /* CPUSolver.cpp:2356-2357 */
+  if (_cmfd_active && !_cmfd_device_active) _cmfd->zeroCurrents();       /* CPUSolver.cpp:2343-2344 */
+  if (_cmfd_active && !_cmfd_device_active && _cmfd->isSigmaTRebalanceOn()) tallyStartingCurrents();   /* CPUSolver.cpp:2356-2357 */
   _timer->startTimer();
   check(b200_transport_sweep(_h), "transportSweep");
   check(b200_synchronize(_h), "transportSweep");

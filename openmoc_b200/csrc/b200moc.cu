@@ -28,6 +28,7 @@
 #include "microbench.cuh"
 #include "group.cuh"
 #include "ls_prepass.cuh"
+#include "cmfd.cuh"
 
 using namespace b200;
 
@@ -159,6 +160,7 @@ struct b200_solver {
   DevBuf<int32_t> cmfd_fwd, cmfd_bwd, cmfd_group;
   DevBuf<int2> seg_cmfd;
   DevBuf<double> currents;
+  struct b200_cmfd* cmfd = nullptr;   /* CMFD solve on the device (cmfd_impl.cuh) */
   /* linear source */
   bool linear = false, have_ls = false;
   int nc = 3;
@@ -253,6 +255,7 @@ static int grp_sweep(b200_solver* s);
 static int grp_iteration(b200_solver* s, int i, int res_type, int loop_kind);
 static int grp_sync(b200_solver* s);
 static void grp_destroy(b200_solver* s);
+static void cmfd_destroy(b200_solver* s);
 static int grp_get_start_fluxes(b200_solver* s, float* out, int64_t n);
 static int grp_set_start_fluxes(b200_solver* s, const float* in, int64_t n);
 static int grp_compute_eigenvalue(b200_solver* s, int max_iters, double tol, int res_type, int32_t* num_iterations);
@@ -419,6 +422,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   cudaSetDevice(s->cfg.device);
   cudaStreamSynchronize(s->stream);
   if (s->iter_graph != nullptr) cudaGraphExecDestroy(s->iter_graph);
+  cmfd_destroy(s);
   for (auto& p : s->ev_pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto& p : s->ev_free) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   s->seg_len.release(); s->seg_fsr.release(); s->seg_rec.release(); s->trk_off.release(); s->out_slot.release();
@@ -2525,3 +2529,4 @@ extern "C" int b200_set_stream(b200_solver* s, void* cuda_stream) {
 }
 
 #include "group_impl.cuh"
+#include "cmfd_impl.cuh"

@@ -15,13 +15,16 @@
  *                   [--max-iters N] [--threads N] [--res fission|flux|total]
  *                   [--axial N (c5g7-2d, dims 3: axial layers of the root lattice)]
  *                   [--devices 0,1,.. (--solver both: GPUs behind the one B200Solver; a device may repeat)]
- *                   [--cmfd NXxNY[xNZ]] [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
+ *                   [--cmfd NXxNY[xNZ]] [--host-cmfd (B200 solvers: the reference's host Cmfd instead of the device CMFD)]
+ *                   [--check-cmfd-split (compare the library's current-splitting tables with Cmfd's, no GPU needed)]
+ *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
  */
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
+#include <vector>
 
 #include "CPUSolver.h"
 #include "CPULSSolver.h"
@@ -33,6 +36,45 @@
 #include "../../openmoc_b200/cpp/b200_flatten.h"
 #include "../../openmoc_b200/cpp/B200Solver.h"
 #include "../../openmoc_b200/cpp/B200LSSolver.h"
+
+/* the reference's private current-splitting rules (Cmfd::getVertexSplitSurfaces / getEdgeSplitSurfaces,
+ * src/Cmfd.cpp:2348-2480), reached through an explicit instantiation: the checker of
+ * b200_cmfd_split_targets */
+namespace {
+typedef void (Cmfd::*SplitFn)(int, int, std::vector<int>*);
+template <typename Tag, typename Tag::type Member>
+struct Rob { friend typename Tag::type get(Tag) { return Member; } };
+struct TVertex { typedef SplitFn type; friend type get(TVertex); };
+struct TEdge { typedef SplitFn type; friend type get(TEdge); };
+template struct Rob<TVertex, &Cmfd::getVertexSplitSurfaces>;
+template struct Rob<TEdge, &Cmfd::getEdgeSplitSurfaces>;
+
+/* --check-cmfd-split NXxNYxNZ:b0b1b2b3b4b5 (boundaryType digit per face X_MIN..Z_MAX) */
+int check_cmfd_split(const char* spec) {
+  int nx = 1, ny = 1, nz = 1;
+  char bcs[16] = "111111";
+  sscanf(spec, "%dx%dx%d:%6s", &nx, &ny, &nz, bcs);
+  Cmfd cmfd;
+  cmfd.setNumX(nx); cmfd.setNumY(ny); cmfd.setNumZ(nz);
+  int32_t bc[6];
+  for (int s = 0; s < 6; s++) { bc[s] = bcs[s] - '0'; cmfd.setBoundary(s, (boundaryType)bc[s]); }
+  long checked = 0, mismatches = 0;
+  std::vector<int> ref;
+  for (int cell = 0; cell < nx * ny * nz; cell++)
+    for (int surf = NUM_FACES; surf < NUM_SURFACES; surf++) {
+      if (surf < NUM_FACES + NUM_EDGES) (cmfd.*get(TEdge()))(cell, surf, &ref);
+      else (cmfd.*get(TVertex()))(cell, surf, &ref);
+      int32_t mine[6], n = 0;
+      if (b200_cmfd_split_targets(nx, ny, nz, bc, cell, surf, mine, &n)) { fprintf(stderr, "%s\n", b200_last_error()); return 2; }
+      bool same = (n == (int)ref.size());
+      for (int j = 0; same && j < n; j++) same = (mine[j] == ref[j]);
+      checked++;
+      if (!same) mismatches++;
+    }
+  printf("{\"mesh\": \"%s\", \"checked\": %ld, \"mismatches\": %ld}\n", spec, checked, mismatches);
+  return mismatches == 0 ? 0 : 1;
+}
+}  // namespace
 
 static const char* arg(int argc, char** argv, const char* key, const char* dflt) {
   for (int i = 1; i < argc - 1; i++)
@@ -46,6 +88,7 @@ static bool flag(int argc, char** argv, const char* key) {
 }
 
 int main(int argc, char** argv) {
+  if (strlen(arg(argc, argv, "--check-cmfd-split", "")) > 0) return check_cmfd_split(arg(argc, argv, "--check-cmfd-split", ""));
   std::string model_name = arg(argc, argv, "--model", "pin-cell");
   int dims = atoi(arg(argc, argv, "--dims", "2"));
   int num_azim = atoi(arg(argc, argv, "--azim", "4"));
@@ -151,6 +194,7 @@ int main(int argc, char** argv) {
     cpu.computeEigenvalue(max_iters, rt);
     Timer timer;
     double cpu_sweep = timer.getSplit("Transport Sweep");
+    double cpu_total = timer.getSplit("Total time");
     std::vector<FP_PRECISION> phi_cpu(n_fsr * G), phi_gpu(n_fsr * G);
     cpu.getFluxes(phi_cpu.data(), n_fsr * G);
     double k_cpu = cpu.getKeff();
@@ -160,6 +204,7 @@ int main(int argc, char** argv) {
     B200LSSolver* gpu_ls = ls ? new B200LSSolver(tg) : NULL;
     Solver& gpu = ls ? *(Solver*)gpu_ls : *(Solver*)gpu_flat;
     if (ls) gpu_ls->setNumThreads(threads); else gpu_flat->setNumThreads(threads);
+    if (flag(argc, argv, "--host-cmfd")) { if (ls) gpu_ls->setCmfdOnDevice(false); else gpu_flat->setCmfdOnDevice(false); }
     {
       /* --devices 0,1,...: several GPUs (or several shards on one GPU) behind the one B200Solver */
       std::string dl = arg(argc, argv, "--devices", "");
@@ -179,6 +224,7 @@ int main(int argc, char** argv) {
     if (max_tau_arg > 0.) gpu.setMaxOpticalLength(max_tau_arg);
     gpu.computeEigenvalue(max_iters, rt);
     double gpu_sweep = timer.getSplit("Transport Sweep");
+    double gpu_total = timer.getSplit("Total time");
     gpu.getFluxes(phi_gpu.data(), n_fsr * G);
     double err = 0.;
     for (long i = 0; i < n_fsr * G; i++) {
@@ -192,10 +238,12 @@ int main(int argc, char** argv) {
     printf("{\"model\": \"%s\", \"n_segments\": %ld, \"n_fsrs\": %ld, \"cpu_threads\": %d, "
            "\"cpu_keff\": %.12f, \"b200_keff\": %.12f, \"dk_pcm\": %.3e, \"max_rel_flux_err\": %.3e, "
            "\"cpu_iters\": %d, \"b200_iters\": %d, \"cpu_sweep_s\": %.6g, \"b200_sweep_s\": %.6g, "
-           "\"b200_sweep_kernel_s\": %.6g, \"cpu_integrations_per_s\": %.4e, \"b200_integrations_per_s\": %.4e}\n",
+           "\"b200_sweep_kernel_s\": %.6g, \"cpu_integrations_per_s\": %.4e, \"b200_integrations_per_s\": %.4e, "
+           "\"cpu_total_s\": %.6g, \"b200_total_s\": %.6g, \"cmfd_on_device\": %s}\n",
            model_name.c_str(), n_seg, n_fsr, threads, k_cpu, gpu.getKeff(), fabs(gpu.getKeff() - k_cpu) * 1e5, err,
            it_cpu, gpu.getNumIterations(), cpu_sweep, gpu_sweep, dev_ms * 1e-3,
-           2.0 * F * n_seg * it_cpu / cpu_sweep, 2.0 * F * n_seg * gpu.getNumIterations() / gpu_sweep);
+           2.0 * F * n_seg * it_cpu / cpu_sweep, 2.0 * F * n_seg * gpu.getNumIterations() / gpu_sweep,
+           cpu_total, gpu_total, (ls ? gpu_ls->isCmfdOnDevice() : gpu_flat->isCmfdOnDevice()) ? "true" : "false");
     return 0;
   }
 
@@ -215,11 +263,17 @@ int main(int argc, char** argv) {
     solver = make(tg, atoi(arg(argc, argv, "--gpu-blocks", "0")), atoi(arg(argc, argv, "--gpu-threads", "0")));
   }
   else if (solver_name == "b200" || solver_name == "b200-fused") solver = b200_solver = new B200Solver(tg);
-  else if (solver_name == "b200ls") { B200LSSolver* ls = new B200LSSolver(tg); ls->setNumThreads(threads); solver = ls; }
+  else if (solver_name == "b200ls") {
+    B200LSSolver* ls = new B200LSSolver(tg);
+    ls->setNumThreads(threads);
+    if (flag(argc, argv, "--host-cmfd")) ls->setCmfdOnDevice(false);
+    solver = ls;
+  }
   else if (solver_name == "cpuls") solver = cpu_solver = new CPULSSolver(tg);
   else solver = cpu_solver = new CPUSolver(tg);
   if (cpu_solver != NULL) cpu_solver->setNumThreads(threads);
   if (b200_solver != NULL) b200_solver->setNumThreads(threads);   /* host side: flatten, Cmfd */
+  if (b200_solver != NULL && flag(argc, argv, "--host-cmfd")) b200_solver->setCmfdOnDevice(false);
   solver->setConvergenceThreshold(tol);
   if (flag(argc, argv, "--balance")) solver->setKeffFromNeutronBalance();   /* Solver.cpp:2047 */
 
