@@ -192,12 +192,17 @@ int b200_cmfd_set_keff(b200_solver* s, double k_eff);       /* Cmfd::setKeff */
 typedef struct b200_cmfd_stats {      /* struct ConvergenceData, src/linalg.h:31-68 */
   double pf, cmfd_res_1, cmfd_res_end, linear_res_1, linear_res_end;
   int32_t cmfd_iters, linear_iters_1, linear_iters_end, linear_iters_total, failed, bad_tallies;
+  double device_ms;                   /* CUDA-event time of the seven kernels of this solve */
 } b200_cmfd_stats;
 /* One CMFD solve + prolongation (Cmfd::computeKeff(moc_iteration)); k_eff of the solver becomes the CMFD one
  * (Solver.cpp:1628).  source_threshold: Cmfd::setSourceConvergenceThreshold's value; < 0: the value the device
  * keeps (0.01 x the last residual, Solver.cpp:1671-1675).  k_eff / stats may be NULL (no host synchronisation). */
 int b200_cmfd_solve(b200_solver* s, int32_t moc_iteration, double source_threshold, double* k_eff,
                     b200_cmfd_stats* stats);
+/* The fused loops (b200_compute_eigenvalue, b200_iterate, b200_iteration_end) run the CMFD solve after the closure of
+ * every iteration once b200_cmfd_configure has been called - the whole CMFD-accelerated source iteration then
+ * runs without a host round trip per step; on = 0 takes it out again (the host then calls b200_cmfd_solve). */
+int b200_cmfd_set_in_loop(b200_solver* s, int32_t on);
 /* Cmfd::getVertexSplitSurfaces / getEdgeSplitSurfaces (Cmfd.cpp:2348-2480) as this library restates them: the
  * (cell*26 + surface) slots an edge or vertex current of `cell` is split onto.  Host-only; used by the tests. */
 int b200_cmfd_split_targets(int32_t num_x, int32_t num_y, int32_t num_z, const int32_t* boundaries, int32_t cell,

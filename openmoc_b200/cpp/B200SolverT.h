@@ -43,6 +43,7 @@ protected:
   bool _cmfd_active, _host_flux_newer;
   bool _cmfd_on_device;            /* user switch (setCmfdOnDevice); B200_HOST_CMFD=1 forces the host Cmfd */
   bool _cmfd_device_active;        /* this solve: collapse, diffusion solve and prolongation run on the device */
+  double _cmfd_device_ms; long _cmfd_linear_iters;   /* accumulated over the solve */
   double _cmfd_device_keff;        /* the CMFD k_eff the device holds */
   Cmfd* _cmfd_suspended;           /* Cmfd whose flux update is switched off while the device does its work */
   std::vector<double> _cmfd_currents;
@@ -146,6 +147,8 @@ public:
    *  not reproduce: the sigma-t rebalance and the neutron-balance check. */
   void setCmfdOnDevice(bool on) { _cmfd_on_device = on; }
   bool isCmfdOnDevice() { return _cmfd_device_active; }
+  /** Device time (ms) of the CMFD solves of the last compute*() and their SOR iterations. */
+  void getCmfdStats(double* ms, long* linear_iterations) { *ms = _cmfd_device_ms; *linear_iterations = _cmfd_linear_iters; }
   /** Solver::computeEigenvalue is not virtual; this overload only restores Cmfd::isFluxUpdateOn afterwards. */
   void computeEigenvalue(int max_iters = 1000, residualType res_type = FISSION_SOURCE) {
     Base::computeEigenvalue(max_iters, res_type);
@@ -175,6 +178,7 @@ B200SolverT<Base>::B200SolverT(TrackGenerator* track_generator, int device, int 
   _cmfd_device_active = false;
   _cmfd_suspended = NULL;
   _cmfd_device_keff = 1.;
+  _cmfd_device_ms = 0.; _cmfd_linear_iters = 0;
   _host_flux_newer = false;
   _device = device;
   _precision = precision;
@@ -427,6 +431,7 @@ void B200SolverT<Base>::configureDeviceCmfd() {
     check(b200_cmfd_set_axial_interpolants(_h, v.axial_interpolants.data()), "b200_cmfd_set_axial_interpolants");
   check(b200_cmfd_set_keff(_h, v.k_eff), "b200_cmfd_set_keff");
   _cmfd_device_keff = v.k_eff;
+  _cmfd_device_ms = 0.; _cmfd_linear_iters = 0;
   _cmfd->setFluxUpdateOn(false);
   _cmfd_suspended = _cmfd;
   _cmfd_device_active = true;
@@ -595,7 +600,12 @@ void B200SolverT<Base>::computeKeff() {
     b200_cmfd_stats st;
     const double host_k = b200_cmfd_keff(_cmfd);          /* Cmfd::setKeff since the last solve (Solver.cpp:1249) */
     if (host_k != _cmfd_device_keff) check(b200_cmfd_set_keff(_h, host_k), "b200_cmfd_set_keff");
+    _timer->startTimer();
     check(b200_cmfd_solve(_h, _num_iterations, b200_cmfd_source_threshold(_cmfd), &_k_eff, &st), "b200_cmfd_solve");
+    _timer->stopTimer();
+    _timer->recordSplit("Total CMFD time");           /* the split Cmfd::computeKeff records (Cmfd.cpp:1286) */
+    _cmfd_device_ms += st.device_ms;
+    _cmfd_linear_iters += st.linear_iters_total;
     if (st.failed)
       log_printf(WARNING, "The CMFD solve on the device did not converge in MOC iteration %d: k_eff and fluxes "
                  "are left as they are", _num_iterations);
@@ -754,13 +764,14 @@ void B200SolverT<Base>::computeEigenvalueFused(int max_iters, residualType res_t
   initializeFluxArrays();
   initializeSourceArrays();
   initializeCmfd();
-  if (_cmfd_active)
+  if (_cmfd_active && !_cmfd_device_active)
     log_printf(ERROR, "computeEigenvalueFused runs the whole source iteration on the device and cannot "
-               "hand currents to the host Cmfd every iteration: use computeEigenvalue() with CMFD");
+               "hand currents to the host Cmfd every iteration: use computeEigenvalue() with this Cmfd");
   pushFixedSourcesIfDirty();
   int iters = 0;
   check(b200_compute_eigenvalue(_h, max_iters, _converge_thresh, (int)res_type, &iters), "computeEigenvalueFused");
   _num_iterations = iters;
+  restoreCmfdFluxUpdate();
   check(b200_get_keff(_h, &_k_eff), "computeEigenvalueFused");
   _device_keff = _k_eff;
   syncHostMirrors();

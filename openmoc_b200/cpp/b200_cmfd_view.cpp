@@ -95,13 +95,18 @@ void b200_read_cmfd(Cmfd* cmfd, long num_fsrs, B200CmfdView* out) {
   v.st_offset.clear(); v.st_cell.clear(); v.st_weight.clear(); v.st_own.clear(); v.st_size.clear();
   if (v.centroid_update) {
     StencilMap& st = cmfd->*get(TStencils());
+    /* FSR -> cell from the lists above (Cmfd::convertFSRIdToCmfdCell searches them linearly) */
+    std::vector<int32_t> fsr_cell(num_fsrs, -1);
+    for (size_t i = 0; i + 1 < v.cell_fsr_offset.size(); i++)
+      for (int64_t j = v.cell_fsr_offset[i]; j < v.cell_fsr_offset[i + 1]; j++)
+        if (v.cell_fsrs[j] >= 0 && v.cell_fsrs[j] < num_fsrs) fsr_cell[v.cell_fsrs[j]] = (int32_t)i;
     v.st_offset.assign(num_fsrs + 1, 0);
     v.st_own.assign(num_fsrs, 1.0);
     v.st_size.assign(num_fsrs, 1);
     for (long r = 0; r < num_fsrs; r++) {
       StencilMap::iterator it = st.find(r);
       if (it != st.end() && !it->second.empty()) {
-        const int cell = cmfd->convertFSRIdToCmfdCell(r);
+        const int cell = fsr_cell[r];
         const std::vector<std::pair<int, double> >& entries = it->second;
         v.st_size[r] = (int32_t)entries.size();
         v.st_own[r] = entries[0].second;

@@ -256,6 +256,10 @@ static int grp_iteration(b200_solver* s, int i, int res_type, int loop_kind);
 static int grp_sync(b200_solver* s);
 static void grp_destroy(b200_solver* s);
 static void cmfd_destroy(b200_solver* s);
+static bool cmfd_in_loop(const b200_solver* s);
+static int enqueue_cmfd(b200_solver* s, int moc_iteration, double source_threshold);
+static int enqueue_cmfd_threshold(b200_solver* s);
+static int cmfd_loop_init(b200_solver* s, double tol);
 static int grp_get_start_fluxes(b200_solver* s, float* out, int64_t n);
 static int grp_set_start_fluxes(b200_solver* s, const float* in, int64_t n);
 static int grp_compute_eigenvalue(b200_solver* s, int max_iters, double tol, int res_type, int32_t* num_iterations);
@@ -1988,7 +1992,15 @@ static int enqueue_iteration_begin(b200_solver* s, int i) {
 
 static int enqueue_iteration_end(b200_solver* s, int i, int res_type, int loop_kind) {
   FsrArgs a = fsr_args(s);
-  if (s->balance) {
+  if (cmfd_in_loop(s)) {
+    /* Solver.cpp:1624-1640 with CMFD: closure, Cmfd::computeKeff (k_eff and the prolongation), stabilisation,
+     * normalisation from the updated flux */
+    if (s->balance) return fail("k_eff from the neutron balance cannot be combined with CMFD (Solver.cpp:1627-1630)");
+    if (launch_closure(s, 0, nullptr)) return 1;
+    if (enqueue_cmfd(s, i, -1.0)) return 1;
+    if (i != 0 && s->stabilize) { if (launch_stabilize_flux(s)) return 1; }
+    if (launch_rate(s, 2)) return 1;
+  } else if (s->balance) {
     if (launch_closure(s, 0, nullptr)) return 1;
     if (launch_balance_keff(s)) return 1;
     if (i != 0 && s->stabilize) { if (launch_stabilize_flux(s)) return 1; }
@@ -2016,6 +2028,7 @@ static int enqueue_iteration_end(b200_solver* s, int i, int res_type, int loop_k
     s->n_launches++;
   }
   if (launch_residual(s, res_type, 1, 1, loop_kind, i)) return 1;
+  if (cmfd_in_loop(s)) return enqueue_cmfd_threshold(s);     /* Solver.cpp:1671-1675 */
   return 0;
 }
 
@@ -2037,6 +2050,7 @@ static int prepare_history(b200_solver* s, int max_iters) {
  * than 1e8 integrations per sweep use it. */
 static bool want_graph(const b200_solver* s) {
   if (!s->own_stream) return false;      /* a borrowed stream may be the legacy default stream: no capture */
+  if (cmfd_in_loop(s)) return false;     /* the CMFD solve may be a cooperative launch */
   if (const char* e = getenv("B200_GRAPH")) return atoi(e) != 0;
   return 2.0 * s->F * (double)s->n_seg < 1e8;
 }
@@ -2080,6 +2094,7 @@ extern "C" int b200_compute_eigenvalue(b200_solver* s, int32_t max_iters, double
   double init[SC_COUNT_D] = {0};
   init[SC_KEFF] = 1.0; init[SC_KPREV] = 1.0; init[SC_TOL] = tol;
   CU(cudaMemcpyAsync(s->scal.p, init, sizeof init, cudaMemcpyHostToDevice, s->stream));
+  if (cmfd_loop_init(s, tol)) return 1;
   if (clear_done(s)) return 1;
   if (b200_zero_track_fluxes(s)) return 1;
   CU(cudaMemsetAsync(s->phi_old.p, 0, (size_t)s->n_fsr * s->G * 8, s->stream));
@@ -2132,6 +2147,7 @@ extern "C" int b200_eigen_loop_init(b200_solver* s, int32_t max_iters, double to
   init[SC_KEFF] = 1.0; init[SC_KPREV] = 1.0; init[SC_TOL] = tol;
   CU(cudaMemcpyAsync(s->scal.p, init, sizeof init, cudaMemcpyHostToDevice, s->stream));
   CU(cudaStreamSynchronize(s->stream));
+  if (cmfd_loop_init(s, tol)) return 1;
   if (clear_done(s)) return 1;
   if (b200_zero_track_fluxes(s)) return 1;
   CU(cudaMemsetAsync(s->phi_old.p, 0, (size_t)s->n_fsr * s->G * 8, s->stream));

@@ -31,7 +31,7 @@ namespace cg = cooperative_groups;
 constexpr int CMFD_NS = 26;                 /* NUM_SURFACES, src/constants.h:119 */
 constexpr int CMFD_NF = 6;                  /* NUM_FACES */
 constexpr int CMFD_NFE = 18;                /* faces + edges */
-constexpr int CMFD_BLOCK_THREADS = 1024;    /* one-CTA solve */
+constexpr int CMFD_BLOCK_THREADS = 512;     /* one-CTA solve: 128 registers per thread */
 constexpr int CMFD_GRID_THREADS = 256;      /* cooperative solve */
 constexpr double CMFD_EPS = 1.0e-12;        /* FLT_EPSILON of src/constants.h:12 (NOT the C one) */
 constexpr double CMFD_FLUX_EPS = 1.0e-25;   /* FLUX_EPSILON, src/constants.h:15 */
@@ -370,13 +370,109 @@ __device__ __forceinline__ double cmfd_cell_source(const CmfdArgs& a, const doub
   return tot;
 }
 
-template <int MODE>
+/* One red/black SOR update of a cell (linalg.cpp:281-320) followed by its new source (M X) and, when `need`, its
+ * term of the residual.  The row is walked in the column order of the reference's CSR matrix: the lower
+ * neighbours (z-, y-, x-), the groups of the cell itself (Gauss-Seidel inside the cell, the source at the
+ * diagonal's position), the upper neighbours.  NCG > 0: group count known at compile time - the six neighbour
+ * fluxes of every group are requested before any arithmetic, so a phase costs one L2 round trip. */
+template <int MODE, int NCG>
+__device__ __forceinline__ void cmfd_sor_cell(const CmfdArgs& a, double* X, int64_t cell, double omega, bool need,
+                                              const double* old_src, double& part) {
+  const int32_t* nbp = a.nbr + cell * CMFD_NF;
+  if constexpr (NCG > 0) {
+    int nbi[CMFD_NF];
+#pragma unroll
+    for (int s = 0; s < CMFD_NF; s++) nbi[s] = __ldg(nbp + s);
+    /* everything this thread wrote itself (B, SO) and every flux is requested before the first store: the
+     * compiler cannot move a plain load above a store through another double*, and a load issued right before
+     * its use costs a full L2 round trip */
+    double xn[CMFD_NF][NCG], xo[NCG], bv[NCG];
+    double sold = 0.;
+#pragma unroll
+    for (int s = 0; s < CMFD_NF; s++)
+#pragma unroll
+      for (int g = 0; g < NCG; g++) xn[s][g] = nbi[s] >= 0 ? cmfd_ldx<MODE>(X, (int64_t)nbi[s] * NCG + g) : 0.;
+#pragma unroll
+    for (int g = 0; g < NCG; g++) { xo[g] = cmfd_ldx<MODE>(X, cell * NCG + g); bv[g] = a.B[cell * NCG + g]; }
+    if (need) {
+#pragma unroll
+      for (int e = 0; e < NCG; e++) sold += old_src[cell * NCG + e];
+    }
+#pragma unroll
+    for (int g = 0; g < NCG; g++) {
+      const int64_t row = cell * NCG + g;
+      const double d = __ldg(a.diag + row);
+      const double* of = a.off + row * CMFD_NF;
+      double v = (1.0 - omega) * xo[g] * (d / omega);
+      v -= __ldg(of + 2) * xn[2][g];
+      v -= __ldg(of + 1) * xn[1][g];
+      v -= __ldg(of + 0) * xn[0][g];
+#pragma unroll
+      for (int g2 = 0; g2 < NCG; g2++) {
+        if (g2 == g) v += bv[g];
+        else v -= __ldg(a.ain + row * NCG + g2) * xo[g2];
+      }
+      v -= __ldg(of + 3) * xn[3][g];
+      v -= __ldg(of + 4) * xn[4][g];
+      v -= __ldg(of + 5) * xn[5][g];
+      xo[g] = v * (omega / d);
+    }
+    double snew = 0., sn[NCG];
+#pragma unroll
+    for (int e = 0; e < NCG; e++) {
+      const int64_t row = cell * NCG + e;
+      double sv = 0.;
+#pragma unroll
+      for (int g = 0; g < NCG; g++) sv += __ldg(a.mm + row * NCG + g) * xo[g];
+      sn[e] = sv;
+      snew += sv;
+    }
+#pragma unroll
+    for (int g = 0; g < NCG; g++) { X[cell * NCG + g] = xo[g]; a.SN[cell * NCG + g] = sn[g]; }
+    if (need && fabs(sold) > CMFD_FLUX_EPS) { const double q = (snew - sold) / sold; part += q * q; }
+  } else {
+    const int ncg = a.ncg;
+    int nbi[CMFD_NF];
+    for (int s = 0; s < CMFD_NF; s++) nbi[s] = __ldg(nbp + s);
+    double sold = 0.;
+    if (need)
+      for (int e = 0; e < ncg; e++) sold += old_src[cell * ncg + e];
+    for (int g = 0; g < ncg; g++) {
+      const int64_t row = cell * ncg + g;
+      const double d = __ldg(a.diag + row);
+      const double* of = a.off + row * CMFD_NF;
+      double v = (1.0 - omega) * cmfd_ldx<MODE>(X, row) * (d / omega);
+      if (nbi[2] >= 0) v -= __ldg(of + 2) * cmfd_ldx<MODE>(X, (int64_t)nbi[2] * ncg + g);
+      if (nbi[1] >= 0) v -= __ldg(of + 1) * cmfd_ldx<MODE>(X, (int64_t)nbi[1] * ncg + g);
+      if (nbi[0] >= 0) v -= __ldg(of + 0) * cmfd_ldx<MODE>(X, (int64_t)nbi[0] * ncg + g);
+      for (int g2 = 0; g2 < ncg; g2++) {
+        if (g2 == g) v += a.B[row];
+        else v -= __ldg(a.ain + row * ncg + g2) * cmfd_ldx<MODE>(X, cell * ncg + g2);
+      }
+      if (nbi[3] >= 0) v -= __ldg(of + 3) * cmfd_ldx<MODE>(X, (int64_t)nbi[3] * ncg + g);
+      if (nbi[4] >= 0) v -= __ldg(of + 4) * cmfd_ldx<MODE>(X, (int64_t)nbi[4] * ncg + g);
+      if (nbi[5] >= 0) v -= __ldg(of + 5) * cmfd_ldx<MODE>(X, (int64_t)nbi[5] * ncg + g);
+      X[row] = v * (omega / d);
+    }
+    double snew = 0.;
+    for (int e = 0; e < ncg; e++) {
+      const int64_t row = cell * ncg + e;
+      double sv = 0.;
+      for (int g = 0; g < ncg; g++) sv += __ldg(a.mm + row * ncg + g) * cmfd_ldx<MODE>(X, cell * ncg + g);
+      a.SN[row] = sv;
+      snew += sv;
+    }
+    if (need && fabs(sold) > CMFD_FLUX_EPS) { const double q = (snew - sold) / sold; part += q * q; }
+  }
+}
+
+template <int MODE, int NCG>
 __global__ void __launch_bounds__(MODE == 0 ? CMFD_BLOCK_THREADS : CMFD_GRID_THREADS)
 cmfd_eigen_kernel(CmfdArgs a, double source_thresh) {
   extern __shared__ double cmfd_smem[];
   __shared__ double sh[34];
   if (a.iscal[SI_DONE]) return;
-  const int ncg = a.ncg;
+  const int ncg = NCG > 0 ? NCG : a.ncg;
   const int64_t T = (int64_t)gridDim.x * blockDim.x, gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int hx = (a.nx + 1) / 2;
   const int64_t n_slots = (int64_t)a.nz * a.ny * hx;
@@ -429,35 +525,16 @@ cmfd_eigen_kernel(CmfdArgs a, double source_thresh) {
     int liter = 0;
     while (liter < 10000) {
       const bool need = liter == 0 || liter + 1 > 25;
+      /* the source this sweep is compared with: the one before the solve until the 25th sweep, the previous
+       * sweep's afterwards (linalg.cpp:383-386 copies new to old from then on; here the previous source is simply
+       * read before it is overwritten) */
+      const double* old_src = liter >= 25 ? a.SN : a.SO;
       double part = 0.;
       for (int colour = 0; colour < 2; colour++) {
         for (int64_t idx = gt; idx < n_slots; idx += T) {
           const int64_t cell = cmfd_slot_cell(a, idx, colour, hx);
           if (cell < 0) continue;
-          const int32_t* nb = a.nbr + cell * CMFD_NF;
-          for (int g = 0; g < ncg; g++) {
-            const int64_t row = cell * ncg + g;
-            const double d = a.diag[row];
-            const double* of = a.off + row * CMFD_NF;
-            double v = (1.0 - omega) * X[row] * (d / omega);
-            if (nb[2] >= 0) v -= of[2] * cmfd_ldx<MODE>(X, (int64_t)nb[2] * ncg + g);
-            if (nb[1] >= 0) v -= of[1] * cmfd_ldx<MODE>(X, (int64_t)nb[1] * ncg + g);
-            if (nb[0] >= 0) v -= of[0] * cmfd_ldx<MODE>(X, (int64_t)nb[0] * ncg + g);
-            for (int g2 = 0; g2 < ncg; g2++) {
-              if (g2 == g) v += a.B[row];
-              else v -= a.ain[row * ncg + g2] * X[cell * ncg + g2];
-            }
-            if (nb[3] >= 0) v -= of[3] * cmfd_ldx<MODE>(X, (int64_t)nb[3] * ncg + g);
-            if (nb[4] >= 0) v -= of[4] * cmfd_ldx<MODE>(X, (int64_t)nb[4] * ncg + g);
-            if (nb[5] >= 0) v -= of[5] * cmfd_ldx<MODE>(X, (int64_t)nb[5] * ncg + g);
-            X[row] = v * (omega / d);
-          }
-          const double snew = cmfd_cell_source<MODE>(a, X, cell, a.SN);
-          if (need) {
-            double sold = 0.;
-            for (int e = 0; e < ncg; e++) sold += a.SO[cell * ncg + e];
-            if (fabs(sold) > CMFD_FLUX_EPS) { const double q = (snew - sold) / sold; part += q * q; }
-          }
+          cmfd_sor_cell<MODE, NCG>(a, X, cell, omega, need, old_src, part);
         }
         if (colour == 1 && need) cmfd_reduce_put<MODE>(part, sh, a.partials, slot);
         cmfd_barrier<MODE>();
@@ -476,13 +553,6 @@ cmfd_eigen_kernel(CmfdArgs a, double source_thresh) {
         if ((lres > 1e3 * min_res && min_res > 1e-10) || !(lres == lres)) { ok = false; break; }
         if (lres / linit < 0.1 || lres < lin_tol) break;
       }
-      if (liter > 24 && liter < 10000)
-        for (int c2 = 0; c2 < 2; c2++)
-          for (int64_t idx = gt; idx < n_slots; idx += T) {
-            const int64_t cell = cmfd_slot_cell(a, idx, c2, hx);
-            if (cell < 0) continue;
-            for (int e = 0; e < ncg; e++) a.SO[cell * ncg + e] = a.SN[cell * ncg + e];
-          }
     }
     lin_total += liter;
     lin_iters = liter;

@@ -10,6 +10,7 @@ struct b200_cmfd {
   b200_cmfd_config cfg;
   int64_t n_cells = 0;
   bool configured = false, have_stencils = false, have_interp = false;
+  bool in_loop = true;               /* the fused source iteration runs the CMFD solve (b200_cmfd_set_in_loop) */
   std::vector<double> h_wx, h_wy, h_wz;
   DevBuf<double> wx, wy, wz, azim_w, sin_theta, polar_w;
   DevBuf<int32_t> group_idx, cell_fsrs, fsr_cell, nbr, sv_src, se_src, st_cell, st_n;
@@ -20,7 +21,9 @@ struct b200_cmfd {
   DevBuf<int> ci;
   int eigen_mode = 0, eigen_blocks = 1;
   size_t eigen_smem = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   void release() {
+    if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); ev0 = ev1 = nullptr; }
     wx.release(); wy.release(); wz.release(); azim_w.release(); sin_theta.release(); polar_w.release();
     group_idx.release(); cell_fsrs.release(); fsr_cell.release(); nbr.release(); sv_src.release(); se_src.release();
     st_cell.release(); st_n.release(); cell_fsr_off.release(); sv_off.release(); se_off.release(); st_off.release();
@@ -31,6 +34,19 @@ struct b200_cmfd {
     partials.release(); cs.release(); ci.release();
   }
 };
+
+/* the eigenvalue kernel is compiled for the usual CMFD group counts (registers instead of loops), 0 = any */
+typedef void (*cmfd_eigen_fn)(CmfdArgs, double);
+template <int MODE>
+static cmfd_eigen_fn cmfd_pick_eigen(int ncg) {
+  switch (ncg) {
+    case 1: return cmfd_eigen_kernel<MODE, 1>;
+    case 2: return cmfd_eigen_kernel<MODE, 2>;
+    case 4: return cmfd_eigen_kernel<MODE, 4>;
+    case 7: return cmfd_eigen_kernel<MODE, 7>;
+    default: return cmfd_eigen_kernel<MODE, 0>;
+  }
+}
 
 static void cmfd_destroy(b200_solver* s) {
   if (s->cmfd == nullptr) return;
@@ -259,7 +275,7 @@ extern "C" int b200_cmfd_configure(b200_solver* s, const b200_cmfd_config* cfg, 
   /* launch shape of the eigenvalue solve: one CTA while a colour fits its threads a few times over, a cooperative
    * grid otherwise */
   const int64_t n_slots = (int64_t)cfg->num_z * cfg->num_y * ((cfg->num_x + 1) / 2);
-  int mode = n_slots <= 4 * CMFD_BLOCK_THREADS ? 0 : 1;
+  int mode = n_slots <= CMFD_BLOCK_THREADS ? 0 : 1;        /* one cell per thread and colour, or spread over SMs */
   if (const char* e = getenv("B200_CMFD_MODE")) mode = atoi(e) != 0;
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, s->cfg.device));
@@ -271,11 +287,11 @@ extern "C" int b200_cmfd_configure(b200_solver* s, const b200_cmfd_config* cfg, 
     const size_t need = nr * sizeof(double);
     if (need <= (size_t)prop.sharedMemPerBlockOptin - 1024) {
       c->eigen_smem = need;
-      CU(cudaFuncSetAttribute(cmfd_eigen_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+      CU(cudaFuncSetAttribute((const void*)cmfd_pick_eigen<0>(ncg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     }
   } else {
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmfd_eigen_kernel<1>, CMFD_GRID_THREADS, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmfd_pick_eigen<1>(ncg), CMFD_GRID_THREADS, 0));
     if (per_sm < 1) return fail("b200_cmfd_configure: the cooperative CMFD kernel does not fit an SM");
     int64_t blocks = (n_slots + CMFD_GRID_THREADS - 1) / CMFD_GRID_THREADS;
     const int64_t cap = (int64_t)per_sm * prop.multiProcessorCount;
@@ -328,6 +344,27 @@ extern "C" int b200_cmfd_set_keff(b200_solver* s, double k_eff) {
   GRP_ALL(s, b200_cmfd_set_keff(c, k_eff));
   if (s->cmfd == nullptr || !s->cmfd->configured) return fail("b200_cmfd_set_keff: call b200_cmfd_configure first");
   CU(cudaMemcpyAsync(s->cmfd->cs.p + CS_KEFF, &k_eff, 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+static bool cmfd_in_loop(const b200_solver* s) {
+  return s->cmfd != nullptr && s->cmfd->configured && s->cmfd->in_loop && s->cmfd_on;
+}
+
+extern "C" int b200_cmfd_set_in_loop(b200_solver* s, int32_t on) {
+  NEED_FINAL(s);
+  GRP_ALL(s, b200_cmfd_set_in_loop(c, on));
+  if (s->cmfd == nullptr || !s->cmfd->configured) return fail("b200_cmfd_set_in_loop: call b200_cmfd_configure first");
+  s->cmfd->in_loop = on != 0;
+  return 0;
+}
+
+/* start of a fused eigenvalue loop: Solver::initializeCmfd's threshold (Solver.cpp:1159) */
+static int cmfd_loop_init(b200_solver* s, double tol) {
+  if (!cmfd_in_loop(s)) return 0;
+  const double t = tol * 1.e-1;
+  CU(cudaMemcpyAsync(s->cmfd->cs.p + CS_THRESH, &t, 8, cudaMemcpyHostToDevice, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   return 0;
 }
@@ -386,14 +423,12 @@ static int enqueue_cmfd(b200_solver* s, int moc_iteration, double source_thresho
   CU(cudaGetLastError());
   cmfd_matrix_kernel<<<grid_for(c->n_cells * ncg, 256), 256, 0, st>>>(a, moc_iteration);
   CU(cudaGetLastError());
-  if (c->eigen_mode == 0) {
-    cmfd_eigen_kernel<0><<<1, CMFD_BLOCK_THREADS, c->eigen_smem, st>>>(a, source_threshold);
-    CU(cudaGetLastError());
-  } else {
-    void* params[] = {(void*)&a, (void*)&source_threshold};
-    CU(cudaLaunchCooperativeKernel((const void*)cmfd_eigen_kernel<1>, dim3(c->eigen_blocks), dim3(CMFD_GRID_THREADS),
+  void* params[] = {(void*)&a, (void*)&source_threshold};
+  if (c->eigen_mode == 0)
+    CU(cudaLaunchKernel((const void*)cmfd_pick_eigen<0>(ncg), dim3(1), dim3(CMFD_BLOCK_THREADS), params, c->eigen_smem, st));
+  else
+    CU(cudaLaunchCooperativeKernel((const void*)cmfd_pick_eigen<1>(ncg), dim3(c->eigen_blocks), dim3(CMFD_GRID_THREADS),
                                    params, 0, st));
-  }
   cmfd_update_kernel<<<grid_for(s->n_fsr, 256), 256, 0, st>>>(a, moc_iteration);
   CU(cudaGetLastError());
   s->n_launches += 6;
@@ -419,7 +454,13 @@ extern "C" int b200_cmfd_solve(b200_solver* s, int32_t moc_iteration, double sou
     return 0;
   }
   if (clear_done(s)) return 1;
+  const bool timed = stats != nullptr && !s->capturing;
+  if (timed) {
+    if (s->cmfd != nullptr && s->cmfd->ev0 == nullptr) { CU(cudaEventCreate(&s->cmfd->ev0)); CU(cudaEventCreate(&s->cmfd->ev1)); }
+    if (s->cmfd != nullptr) CU(cudaEventRecord(s->cmfd->ev0, s->stream));
+  }
   if (enqueue_cmfd(s, moc_iteration, source_threshold)) return 1;
+  if (timed) CU(cudaEventRecord(s->cmfd->ev1, s->stream));
   if (k_eff == nullptr && stats == nullptr) return 0;
   double cs[CS_COUNT];
   int ci[CI_COUNT];
@@ -440,6 +481,8 @@ extern "C" int b200_cmfd_solve(b200_solver* s, int32_t moc_iteration, double sou
     stats->cmfd_iters = ci[CI_POWER_ITERS]; stats->linear_iters_1 = ci[CI_LIN_ITERS_1];
     stats->linear_iters_end = ci[CI_LIN_ITERS_END]; stats->linear_iters_total = ci[CI_LIN_TOTAL];
     stats->failed = ci[CI_FAIL]; stats->bad_tallies = ci[CI_BAD_TALLY];
+    stats->device_ms = 0.;
+    if (timed) { float ms = 0.f; CU(cudaEventElapsedTime(&ms, s->cmfd->ev0, s->cmfd->ev1)); stats->device_ms = ms; }
   }
   return 0;
 }

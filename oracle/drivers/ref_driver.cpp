@@ -195,6 +195,7 @@ int main(int argc, char** argv) {
     Timer timer;
     double cpu_sweep = timer.getSplit("Transport Sweep");
     double cpu_total = timer.getSplit("Total time");
+    double cpu_cmfd = timer.getSplit("Total CMFD time");
     std::vector<FP_PRECISION> phi_cpu(n_fsr * G), phi_gpu(n_fsr * G);
     cpu.getFluxes(phi_cpu.data(), n_fsr * G);
     double k_cpu = cpu.getKeff();
@@ -225,6 +226,9 @@ int main(int argc, char** argv) {
     gpu.computeEigenvalue(max_iters, rt);
     double gpu_sweep = timer.getSplit("Transport Sweep");
     double gpu_total = timer.getSplit("Total time");
+    double gpu_cmfd = timer.getSplit("Total CMFD time");
+    double cmfd_dev_ms = 0.; long cmfd_lin = 0;
+    if (ls) gpu_ls->getCmfdStats(&cmfd_dev_ms, &cmfd_lin); else gpu_flat->getCmfdStats(&cmfd_dev_ms, &cmfd_lin);
     gpu.getFluxes(phi_gpu.data(), n_fsr * G);
     double err = 0.;
     for (long i = 0; i < n_fsr * G; i++) {
@@ -239,11 +243,13 @@ int main(int argc, char** argv) {
            "\"cpu_keff\": %.12f, \"b200_keff\": %.12f, \"dk_pcm\": %.3e, \"max_rel_flux_err\": %.3e, "
            "\"cpu_iters\": %d, \"b200_iters\": %d, \"cpu_sweep_s\": %.6g, \"b200_sweep_s\": %.6g, "
            "\"b200_sweep_kernel_s\": %.6g, \"cpu_integrations_per_s\": %.4e, \"b200_integrations_per_s\": %.4e, "
-           "\"cpu_total_s\": %.6g, \"b200_total_s\": %.6g, \"cmfd_on_device\": %s}\n",
+           "\"cpu_total_s\": %.6g, \"b200_total_s\": %.6g, \"cmfd_on_device\": %s, \"cpu_cmfd_s\": %.6g, "
+           "\"b200_cmfd_s\": %.6g, \"b200_cmfd_kernels_s\": %.6g, \"b200_cmfd_sor_iterations\": %ld}\n",
            model_name.c_str(), n_seg, n_fsr, threads, k_cpu, gpu.getKeff(), fabs(gpu.getKeff() - k_cpu) * 1e5, err,
            it_cpu, gpu.getNumIterations(), cpu_sweep, gpu_sweep, dev_ms * 1e-3,
            2.0 * F * n_seg * it_cpu / cpu_sweep, 2.0 * F * n_seg * gpu.getNumIterations() / gpu_sweep,
-           cpu_total, gpu_total, (ls ? gpu_ls->isCmfdOnDevice() : gpu_flat->isCmfdOnDevice()) ? "true" : "false");
+           cpu_total, gpu_total, (ls ? gpu_ls->isCmfdOnDevice() : gpu_flat->isCmfdOnDevice()) ? "true" : "false",
+           cpu_cmfd, gpu_cmfd, cmfd_dev_ms * 1e-3, cmfd_lin);
     return 0;
   }
 

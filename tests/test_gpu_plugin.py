@@ -88,7 +88,7 @@ def test_linear_source_reference_golden_from_gpu(tmp_path):
 
 
 # ---------------------------------------------------------------- CMFD acceleration
-@pytest.mark.parametrize("args", [
+CMFD_CASES = [
     ["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12", "--cmfd", "2x2"],
     ["--model", "simple-lattice", "--azim", "8", "--spacing", "0.05", "--cmfd", "4x4"],
     ["--model", "c5g7-2d", "--azim", "8", "--spacing", "0.2", "--cmfd", "51x51", "--threads", "1", "--max-iters", "60"],
@@ -96,17 +96,83 @@ def test_linear_source_reference_golden_from_gpu(tmp_path):
      "--zspacing", "0.9", "--cmfd", "2x2x2"],
     ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
      "--zspacing", "0.9", "--cmfd", "2x2x2", "--ls", "--formation", "otf-stacks"],
-])
-def test_cmfd_accelerated_solve_matches_reference(args):
-    """Surface currents tallied in the sweep kernel feed the reference's own host Cmfd
-    (collapse, diffusion solve, prolongation) every iteration: k_eff, fluxes and the
-    iteration count must match CPUSolver/CPULSSolver + Cmfd on the same tracks."""
+]
+
+
+@pytest.mark.parametrize("where", ["device", "host"])
+@pytest.mark.parametrize("args", CMFD_CASES)
+def test_cmfd_accelerated_solve_matches_reference(args, where, monkeypatch):
+    """CMFD-accelerated eigenvalue solves against CPUSolver/CPULSSolver + Cmfd on the same tracks: k_eff, fluxes
+    and the iteration count must match.  `device`: the sweep tallies the surface currents and the library runs the
+    whole Cmfd::computeKeff (current splitting, collapse, diffusion eigenvalue solve, prolongation:
+    b200_cmfd_solve).  `host`: the reference's own Cmfd object, fed with the device's fluxes and currents
+    (B200_HOST_CMFD=1 / B200Solver::setCmfdOnDevice(false))."""
+    if where == "host":
+        monkeypatch.setenv("B200_HOST_CMFD", "1")
     r = run(args + ["--solver", "both"])
+    assert r["cmfd_on_device"] == (where == "device")
     assert r["b200_iters"] == r["cpu_iters"]
     assert r["dk_pcm"] < 1.0 and r["max_rel_flux_err"] < 1e-4          # north_star
     # CMFD prolongation amplifies summation-order noise (the reference itself moves by ~5e-6 between
     # 1 and 8 OpenMP threads); still far inside the tolerance
     assert r["dk_pcm"] < 1e-2 and r["max_rel_flux_err"] < 2e-5
+
+
+@pytest.mark.parametrize("args", [
+    # every MOC group its own CMFD group (no condensation): 7-group kernel, k-nearest off / on
+    ["--model", "pin-cell", "--azim", "8", "--spacing", "0.05", "--cmfd", "3x3", "--no-knearest"],
+    ["--model", "hom-inf", "--azim", "4", "--spacing", "0.1", "--cmfd", "2x2"],
+    # VACUUM sides: the boundary branch of the surface diffusion coefficients
+    ["--model", "gradient-1d", "--azim", "4", "--spacing", "0.1", "--cmfd", "5x1"],
+    ["--model", "gradient-2d", "--azim", "4", "--spacing", "0.1", "--cmfd", "3x3"],
+    # 70 CMFD groups: the generic (run-time group count) kernel, cooperative grid forced below
+    ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "2.1",
+     "--zspacing", "2.8", "--groups70", "--tol", "5e-3", "--cmfd", "2x2x2"],
+    # flux limiting off
+    ["--model", "simple-lattice", "--azim", "8", "--spacing", "0.05", "--cmfd", "4x4", "--no-flux-limiting"],
+    # 3D C5G7 (configs[4] shape, coarse tracks): 51x51x9 cells, cooperative-grid solve, vertex and edge currents
+    ["--model", "c5g7-2d", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "1.0", "--zspacing", "5",
+     "--axial", "9", "--formation", "otf-stacks", "--cmfd", "51x51x9", "--max-iters", "12", "--threads", "8"],
+])
+def test_device_cmfd_options_and_boundaries(args):
+    r = run(args + ["--solver", "both"])
+    assert r["cmfd_on_device"]
+    assert r["b200_iters"] == r["cpu_iters"]
+    assert r["dk_pcm"] < 1e-2 and r["max_rel_flux_err"] < 2e-5
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_device_cmfd_one_cta_and_cooperative_grid_agree(mode, monkeypatch):
+    """The eigenvalue kernel as one CTA (flux in shared memory, __syncthreads) and as a cooperative grid (flux in
+    L2, grid barrier): both against the reference."""
+    monkeypatch.setenv("B200_CMFD_MODE", mode)
+    r = run(["--model", "simple-lattice", "--azim", "8", "--spacing", "0.05", "--cmfd", "4x4", "--solver", "both"])
+    assert r["cmfd_on_device"] and r["b200_iters"] == r["cpu_iters"]
+    assert r["dk_pcm"] < 1e-4 and r["max_rel_flux_err"] < 1e-9
+
+
+@pytest.mark.parametrize("args", [
+    ["--model", "simple-lattice", "--azim", "8", "--spacing", "0.05", "--cmfd", "4x4"],
+    ["--model", "c5g7-2d", "--azim", "8", "--spacing", "0.2", "--cmfd", "51x51", "--max-iters", "60"],
+])
+def test_fused_cmfd_loop_matches_cpusolver(args, tmp_path):
+    """computeEigenvalueFused with CMFD: the whole CMFD-accelerated source iteration (sweep with current tally,
+    closure, CMFD solve, prolongation, normalisation, residual, stopping rule) runs on the device without a host
+    round trip per step; compared with CPUSolver + Cmfd run in a separate process."""
+    import numpy as np
+    if not os.path.exists(DRIVER):
+        pytest.skip("ref_driver not built")
+    res = {}
+    for solver in ("cpu", "b200-fused"):
+        js = os.path.join(tmp_path, solver + ".json")
+        subprocess.run([DRIVER] + args + ["--solver", solver, "--threads", "1", "--quiet", "--json", js],
+                       check=True, capture_output=True)
+        res[solver] = json.load(open(js))
+    a, b = res["cpu"], res["b200-fused"]
+    assert a["iterations"] == b["iterations"]
+    fa, fb = np.array(a["fluxes"]), np.array(b["fluxes"])
+    assert abs(a["keff"] - b["keff"]) * 1e5 < 1e-2
+    assert np.max(np.abs(fa - fb) / np.abs(fa)) < 2e-5
 
 
 def test_3d_c5g7_linear_source_cmfd_in_separate_processes(tmp_path):
@@ -154,8 +220,8 @@ def _devices():
 ])
 def test_multi_device_b200solver_matches_cpusolver_in_process(args, devices):
     """B200Solver::setDevices: ONE solver object inside the reference's process drives several shards
-    (b200_set_devices); flat and linear source, with the reference's host Cmfd fed by the summed
-    currents.  Same tolerances as the single-device cases above."""
+    (b200_set_devices); flat and linear source; with CMFD the summed currents feed the device CMFD, which runs
+    replicated on every shard (same bits on each).  Same tolerances as the single-device cases above."""
     r = run(args + ["--solver", "both", "--devices", devices])
     assert r["b200_iters"] == r["cpu_iters"]
     assert r["dk_pcm"] < 1.0 and r["max_rel_flux_err"] < 1e-4          # north_star

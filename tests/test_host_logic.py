@@ -1,10 +1,11 @@
 """Host-side logic that needs no GPU: track files and the angular partition."""
+import json
 import os
 
 import numpy as np
 import pytest
 
-from conftest import load_case
+from conftest import ROOT, load_case
 from openmoc_b200.partition import assign_pairs, partition_by_azim_pair, partition_by_chain, track_components
 from openmoc_b200.trackfile import FlatTracks, read_trackfile, write_trackfile, REFLECTIVE, PERIODIC
 from oracle.oracle_py import OracleSolver
@@ -241,3 +242,47 @@ def test_linear_expansion_tables_match_the_oracle(name):
     np.testing.assert_allclose(src_const, ref_src, rtol=1e-10, atol=1e-13 * np.abs(ref_src).max())
     d = track_directions(ft)
     np.testing.assert_allclose(np.linalg.norm(d, axis=1), 1.0, rtol=1e-14)
+
+
+# ---------------------------------------------------------------- CMFD current splitting (host tables of the device CMFD)
+def _split_targets(lib, nx, ny, nz, bc, cell, surface):
+    import ctypes
+    out = (ctypes.c_int32 * 6)()
+    n = ctypes.c_int32(0)
+    bcs = (ctypes.c_int32 * 6)(*bc)
+    assert lib.b200_cmfd_split_targets(nx, ny, nz, bcs, cell, surface, out, ctypes.byref(n)) == 0
+    return [out[i] for i in range(n.value)]
+
+
+def test_cmfd_split_rules_conserve_the_current():
+    """b200_cmfd_split_targets (Cmfd::getVertexSplitSurfaces / getEdgeSplitSurfaces restated): an edge current goes
+    in halves onto two faces of the cell and onto two faces of neighbours (or back onto the cell at a reflective
+    side, nowhere at a vacuum side); a vertex current in thirds onto three faces and three edges."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "openmoc_b200", "libb200moc.so"))
+    nx, ny, nz = 3, 4, 2
+    for bc in ([1] * 6, [0] * 6, [2] * 6, [0, 1, 2, 1, 0, 2]):
+        for cell in range(nx * ny * nz):
+            for surf in range(6, 26):
+                t = _split_targets(lib, nx, ny, nz, bc, cell, surf)
+                n_dir = 2 if surf < 18 else 3
+                own = [v for v in t if v // 26 == cell and v % 26 < 6]
+                assert len(own) >= n_dir                      # the faces of the cell itself, always (more at a reflective side)
+                assert len(t) <= 2 * n_dir
+                for v in t:
+                    assert 0 <= v // 26 < nx * ny * nz
+                    assert v % 26 < (6 if surf < 18 else 18)  # edges split onto faces, vertices onto faces and edges
+                if all(b != 0 for b in bc):
+                    assert len(t) == 2 * n_dir                # nothing is lost without a vacuum side
+
+
+def test_cmfd_split_rules_match_the_reference():
+    """Same tables from the reference's private Cmfd methods (ref_driver --check-cmfd-split), where it was built."""
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    for spec in ("3x3x3:111111", "4x3x2:000000", "3x2x4:222222", "5x4x1:101101", "2x2x2:012210", "1x1x1:111111"):
+        out = subprocess.run([driver, "--check-cmfd-split", spec], check=True, capture_output=True, text=True).stdout
+        r = json.loads(out.strip().splitlines()[-1])
+        assert r["mismatches"] == 0 and r["checked"] > 0
