@@ -31,6 +31,23 @@ class Config(C.Structure):
                 ("linear_source", C.c_int32), ("reserved", C.c_int32)]
 
 
+class CmfdConfig(C.Structure):
+    """b200_cmfd_config (include/b200moc.h): the options of a reference Cmfd object."""
+    _fields_ = [("num_x", C.c_int32), ("num_y", C.c_int32), ("num_z", C.c_int32), ("num_cmfd_groups", C.c_int32),
+                ("boundaries", C.c_int32 * 6), ("linear_source", C.c_int32), ("flux_limiting", C.c_int32),
+                ("centroid_update", C.c_int32), ("axial_interpolation", C.c_int32),
+                ("num_unbounded_iterations", C.c_int32), ("num_azim_2", C.c_int32), ("num_polar_2", C.c_int32),
+                ("sor_factor", C.c_double), ("relaxation_factor", C.c_double), ("linalg_tolerance", C.c_double)]
+
+
+class CmfdStats(C.Structure):
+    """b200_cmfd_stats: struct ConvergenceData of the reference (src/linalg.h:31-68) + device time."""
+    _fields_ = [("pf", C.c_double), ("cmfd_res_1", C.c_double), ("cmfd_res_end", C.c_double),
+                ("linear_res_1", C.c_double), ("linear_res_end", C.c_double), ("cmfd_iters", C.c_int32),
+                ("linear_iters_1", C.c_int32), ("linear_iters_end", C.c_int32), ("linear_iters_total", C.c_int32),
+                ("failed", C.c_int32), ("bad_tallies", C.c_int32), ("device_ms", C.c_double)]
+
+
 _lib = None
 
 # name -> argument ctypes (after the solver handle); all return int status
@@ -45,6 +62,12 @@ SIGNATURES = {
     "b200_upload_cmfd_surfaces": [_vp, _vp],
     "b200_set_cmfd_groups": [_vp, _i32, _i64],
     "b200_get_cmfd_currents": [_vp, _i64],
+    "b200_cmfd_configure": [C.POINTER(CmfdConfig)] + [_vp] * 9,
+    "b200_cmfd_set_stencils": [_vp] * 5,
+    "b200_cmfd_set_axial_interpolants": [_vp],
+    "b200_cmfd_set_keff": [_dbl],
+    "b200_cmfd_solve": [_i32, _dbl, C.POINTER(_dbl), C.POINTER(CmfdStats)],
+    "b200_cmfd_set_in_loop": [_i32],
     "b200_get_flux_moments": [_vp, _i64],
     "b200_set_flux_moments": [_vp, _i64],
     "b200_upload_otf_geometry": [_i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp],
@@ -107,7 +130,8 @@ SIGNATURES = {
 }
 #: every symbol include/b200moc.h declares (checked by tests/test_abi.py)
 EXPORTS = sorted(list(SIGNATURES) + ["b200_last_error", "b200_version", "b200_device_count", "b200_create",
-                                      "b200_eval_expF1", "b200_measure_ceilings", "b200_ls_prepass"])
+                                      "b200_eval_expF1", "b200_measure_ceilings", "b200_ls_prepass",
+                                      "b200_cmfd_split_targets"])
 
 
 def load():
@@ -131,6 +155,8 @@ def load():
     L.b200_eval_expF1.argtypes = [_i32, _i32, _vp, _i64, _vp]
     L.b200_ls_prepass.restype = C.c_int
     L.b200_ls_prepass.argtypes = [_i32, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i32] + [_vp] * 16 + [_vp, _vp, C.POINTER(_i32)]
+    L.b200_cmfd_split_targets.restype = C.c_int
+    L.b200_cmfd_split_targets.argtypes = [_i32, _i32, _i32, _vp, _i32, _i32, _vp, C.POINTER(_i32)]
     L.b200_measure_ceilings.restype = C.c_int
     L.b200_measure_ceilings.argtypes = [_i32, _i64, C.POINTER(_dbl), C.POINTER(_dbl)]
     for name, args in SIGNATURES.items():
