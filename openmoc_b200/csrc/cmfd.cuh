@@ -70,6 +70,8 @@ struct CmfdArgs {
   /* CMFD state */
   double *rxn, *volc, *dift, *xs_t, *xs_nf, *xs_chi, *xs_s, *old_flux, *new_flux, *dcoef, *old_corr;
   double *diag, *off, *ain, *mm, *B, *SO, *SN, *partials;
+  double *dq, *qd;                          /* diag / omega and omega / diag of every row (linalg.cpp:288, 318) */
+  const int32_t* __restrict__ slot_cell;    /* [2][n_slots]: cell of every red / black slot, -1 for a hole */
   double* cs; int* ci;
   int x_in_smem;
   /* prolongation */
@@ -275,6 +277,8 @@ cmfd_matrix_kernel(CmfdArgs a, int moc_iteration) {
       a.off[row * CMFD_NF + s] = next >= 0 ? -(ds + dc) * delta_if : 0.;
     }
     a.diag[row] = diag;
+    a.dq[row] = diag / a.sor;
+    a.qd[row] = a.sor / diag;
     for (int g = 0; g < ncg; g++) {
       const double value = a.xs_chi[row] * a.xs_nf[i * ncg + g] * volume;
       a.mm[row * ncg + g] = fabs(value) > CMFD_EPS ? value : 0.;
@@ -401,9 +405,8 @@ __device__ __forceinline__ void cmfd_sor_cell(const CmfdArgs& a, double* X, int6
 #pragma unroll
     for (int g = 0; g < NCG; g++) {
       const int64_t row = cell * NCG + g;
-      const double d = __ldg(a.diag + row);
       const double* of = a.off + row * CMFD_NF;
-      double v = (1.0 - omega) * xo[g] * (d / omega);
+      double v = (1.0 - omega) * xo[g] * __ldg(a.dq + row);
       v -= __ldg(of + 2) * xn[2][g];
       v -= __ldg(of + 1) * xn[1][g];
       v -= __ldg(of + 0) * xn[0][g];
@@ -415,7 +418,7 @@ __device__ __forceinline__ void cmfd_sor_cell(const CmfdArgs& a, double* X, int6
       v -= __ldg(of + 3) * xn[3][g];
       v -= __ldg(of + 4) * xn[4][g];
       v -= __ldg(of + 5) * xn[5][g];
-      xo[g] = v * (omega / d);
+      xo[g] = v * __ldg(a.qd + row);
     }
     double snew = 0., sn[NCG];
 #pragma unroll
@@ -439,9 +442,8 @@ __device__ __forceinline__ void cmfd_sor_cell(const CmfdArgs& a, double* X, int6
       for (int e = 0; e < ncg; e++) sold += old_src[cell * ncg + e];
     for (int g = 0; g < ncg; g++) {
       const int64_t row = cell * ncg + g;
-      const double d = __ldg(a.diag + row);
       const double* of = a.off + row * CMFD_NF;
-      double v = (1.0 - omega) * cmfd_ldx<MODE>(X, row) * (d / omega);
+      double v = (1.0 - omega) * cmfd_ldx<MODE>(X, row) * __ldg(a.dq + row);
       if (nbi[2] >= 0) v -= __ldg(of + 2) * cmfd_ldx<MODE>(X, (int64_t)nbi[2] * ncg + g);
       if (nbi[1] >= 0) v -= __ldg(of + 1) * cmfd_ldx<MODE>(X, (int64_t)nbi[1] * ncg + g);
       if (nbi[0] >= 0) v -= __ldg(of + 0) * cmfd_ldx<MODE>(X, (int64_t)nbi[0] * ncg + g);
@@ -452,7 +454,7 @@ __device__ __forceinline__ void cmfd_sor_cell(const CmfdArgs& a, double* X, int6
       if (nbi[3] >= 0) v -= __ldg(of + 3) * cmfd_ldx<MODE>(X, (int64_t)nbi[3] * ncg + g);
       if (nbi[4] >= 0) v -= __ldg(of + 4) * cmfd_ldx<MODE>(X, (int64_t)nbi[4] * ncg + g);
       if (nbi[5] >= 0) v -= __ldg(of + 5) * cmfd_ldx<MODE>(X, (int64_t)nbi[5] * ncg + g);
-      X[row] = v * (omega / d);
+      X[row] = v * __ldg(a.qd + row);
     }
     double snew = 0.;
     for (int e = 0; e < ncg; e++) {
@@ -532,7 +534,7 @@ cmfd_eigen_kernel(CmfdArgs a, double source_thresh) {
       double part = 0.;
       for (int colour = 0; colour < 2; colour++) {
         for (int64_t idx = gt; idx < n_slots; idx += T) {
-          const int64_t cell = cmfd_slot_cell(a, idx, colour, hx);
+          const int64_t cell = __ldg(a.slot_cell + colour * n_slots + idx);
           if (cell < 0) continue;
           cmfd_sor_cell<MODE, NCG>(a, X, cell, omega, need, old_src, part);
         }
@@ -641,6 +643,291 @@ cmfd_eigen_kernel(CmfdArgs a, double source_thresh) {
     *reinterpret_cast<long long*>(&a.ci[CI_PF_MAX]) = 0;
     *reinterpret_cast<long long*>(&a.ci[CI_PF_MIN]) = 0;
   }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* The same solve on ONE thread-block cluster: the flux lives in the shared memory of the CTAs  */
+/* (CTA r owns the slots [r*S, (r+1)*S) of both colours), a neighbour's flux is a distributed-   */
+/* shared-memory load (ld.shared::cluster), the two colours are separated by the hardware        */
+/* cluster barrier, reductions go through per-CTA partials read over DSMEM in rank order.  With  */
+/* ALL_SMEM the three source vectors sit in shared memory too and a colour phase touches HBM/L2  */
+/* only for the (L1-resident, read-only) matrix coefficients.                                    */
+/* ------------------------------------------------------------------------------------------ */
+constexpr int CMFD_CLUSTER_THREADS = 512;
+
+struct CmfdClusterArgs {
+  int slots_per_cta;                       /* S */
+  int all_smem;                            /* B, SO, SN in shared memory as well */
+  const int32_t* __restrict__ nb_loc;      /* n_cells * 6: rank << 26 | (local slot * 2 + colour), -1 outside */
+};
+
+__device__ __forceinline__ int cmfd_slot_cell32(const CmfdArgs& a, int idx, int colour, int hx) {
+  const int rowi = idx / hx, k = idx - rowi * hx;
+  const int iy = rowi % a.ny, iz = rowi / a.ny;
+  const int ix = 2 * k + ((iy + iz + colour) & 1);
+  return ix >= a.nx ? -1 : rowi * a.nx + ix;
+}
+
+template <int NCG>
+__global__ void __launch_bounds__(CMFD_CLUSTER_THREADS)
+cmfd_eigen_cluster_kernel(CmfdArgs a, CmfdClusterArgs ca, double source_thresh) {
+  extern __shared__ double cmfd_smem[];
+  __shared__ double sh[40];                /* [0,32) warp sums, 32/33 result, 34..37 this CTA's partials (ping-pong x 2) */
+  if (a.iscal[SI_DONE]) return;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
+  const int S = ca.slots_per_cta, hx = (a.nx + 1) / 2;
+  const int n_slots = a.nz * a.ny * hx;
+  const int base = rank * S;
+  const int mine = max(0, min(S, n_slots - base));
+  const int64_t nr = a.n_cells * NCG;
+  double* Xs = cmfd_smem;                                     /* [S*2][NCG] */
+  double* Bv = ca.all_smem ? Xs + (size_t)S * 2 * NCG : a.B;
+  double* SOv = ca.all_smem ? Bv + (size_t)S * 2 * NCG : a.SO;
+  double* SNv = ca.all_smem ? SOv + (size_t)S * 2 * NCG : a.SN;
+  const bool sm = ca.all_smem != 0;
+  int slot = 0;
+  if (rank == 0 && threadIdx.x == 0) a.ci[CI_OLD_VALID] = 1;
+  if (source_thresh < 0.) source_thresh = a.cs[CS_THRESH];
+
+  /* cluster-wide sum with a fixed order: CTA partial -> own shared memory -> every CTA adds the C partials */
+  auto reduce_put = [&](double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.;
+      for (int j = 0; j < CMFD_CLUSTER_THREADS / 32; j++) t += sh[j];
+      sh[34 + slot] = t;
+    }
+  };
+  auto reduce_get = [&]() {
+    if (threadIdx.x == 0) {
+      double t = 0.;
+      for (int r = 0; r < C; r++) t += cluster.map_shared_rank(sh, r)[34 + slot];
+      sh[32] = t;
+    }
+    __syncthreads();
+    const double t = sh[32];
+    __syncthreads();
+    slot ^= 1;
+    return t;
+  };
+  auto reduce = [&](double v) { reduce_put(v); cluster.sync(); return reduce_get(); };
+
+#define CMFD_MY_CELLS(...)                                                         \
+  for (int ls = threadIdx.x; ls < mine; ls += CMFD_CLUSTER_THREADS)                \
+    for (int colour = 0; colour < 2; colour++) {                                   \
+      const int cell = cmfd_slot_cell32(a, base + ls, colour, hx);                 \
+      if (cell < 0) continue;                                                      \
+      const int li = ls * 2 + colour;                                              \
+      [[maybe_unused]] const int64_t iv = sm ? (int64_t)li : (int64_t)cell;        \
+      __VA_ARGS__                                                                  \
+    }
+
+  /* starting guess and initial source (Cmfd.cpp:1232, linalg.cpp:65-80) */
+  double local = 0.;
+  CMFD_MY_CELLS({
+    double x[NCG];
+#pragma unroll
+    for (int g = 0; g < NCG; g++) { x[g] = a.old_flux[(int64_t)cell * NCG + g]; }
+#pragma unroll
+    for (int e = 0; e < NCG; e++) {
+      double sv = 0.;
+#pragma unroll
+      for (int g = 0; g < NCG; g++) sv += __ldg(a.mm + ((int64_t)cell * NCG + e) * NCG + g) * x[g];
+      Bv[iv * NCG + e] = sv;
+      local += sv;
+    }
+#pragma unroll
+    for (int g = 0; g < NCG; g++) Xs[li * NCG + g] = x[g];
+  })
+  double sum = reduce(local);
+  double k = a.cs[CS_KEFF];
+  {
+    const double fb = (double)nr / sum, fx = (double)nr * k / sum;
+    CMFD_MY_CELLS({
+#pragma unroll
+      for (int e = 0; e < NCG; e++) { Bv[iv * NCG + e] *= fb; Xs[li * NCG + e] *= fx; }
+    })
+  }
+  cluster.sync();
+
+  const double lin_tol = fmax(a.linalg_tol, fmax(a.linalg_tol, source_thresh) * 1e-1);
+  const double inv_cells = 1.0 / (double)a.n_cells;
+  const double omega = a.sor;
+  double initial_residual = 0., residual = 0.;
+  int iter = 0, lin_total = 0, lin_iters = 0, lin_iters_1 = 0;
+  double lin_res_first = 0., lin_res_1 = 0., res_1 = 0.;
+  bool ok = true, converged = false;
+
+  for (iter = 0; iter < 25000; iter++) {
+    CMFD_MY_CELLS({
+#pragma unroll
+      for (int e = 0; e < NCG; e++) {
+        double sv = 0.;
+#pragma unroll
+        for (int g = 0; g < NCG; g++) sv += __ldg(a.mm + ((int64_t)cell * NCG + e) * NCG + g) * Xs[li * NCG + g];
+        SOv[iv * NCG + e] = sv;
+      }
+    })
+    double lres = 0., linit = 0., min_res = 1e6;
+    int liter = 0;
+    while (liter < 10000) {
+      const bool need = liter == 0 || liter + 1 > 25;
+      const double* old_src = liter >= 25 ? SNv : SOv;
+      double part = 0.;
+      for (int colour = 0; colour < 2; colour++) {
+        for (int ls = threadIdx.x; ls < mine; ls += CMFD_CLUSTER_THREADS) {
+          const int cell = __ldg(a.slot_cell + (int64_t)colour * n_slots + base + ls);
+          if (cell < 0) continue;
+          const int li = ls * 2 + colour;
+          const int64_t iv = sm ? (int64_t)li : (int64_t)cell;
+          int nb[CMFD_NF];
+#pragma unroll
+          for (int s = 0; s < CMFD_NF; s++) nb[s] = __ldg(ca.nb_loc + (int64_t)cell * CMFD_NF + s);
+          double xn[CMFD_NF][NCG], xo[NCG], bv[NCG];
+          double sold = 0.;
+#pragma unroll
+          for (int s = 0; s < CMFD_NF; s++) {
+            if (nb[s] >= 0) {
+              const double* rx = cluster.map_shared_rank(Xs, nb[s] >> 26) + (size_t)(nb[s] & 0x3ffffff) * NCG;
+#pragma unroll
+              for (int g = 0; g < NCG; g++) xn[s][g] = rx[g];
+            } else {
+#pragma unroll
+              for (int g = 0; g < NCG; g++) xn[s][g] = 0.;
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < NCG; g++) { xo[g] = Xs[li * NCG + g]; bv[g] = Bv[iv * NCG + g]; }
+          if (need) {
+#pragma unroll
+            for (int e = 0; e < NCG; e++) sold += old_src[iv * NCG + e];
+          }
+#pragma unroll
+          for (int g = 0; g < NCG; g++) {
+            const int64_t row = (int64_t)cell * NCG + g;
+            const double* of = a.off + row * CMFD_NF;
+            double v = (1.0 - omega) * xo[g] * __ldg(a.dq + row);
+            v -= __ldg(of + 2) * xn[2][g];
+            v -= __ldg(of + 1) * xn[1][g];
+            v -= __ldg(of + 0) * xn[0][g];
+#pragma unroll
+            for (int g2 = 0; g2 < NCG; g2++) {
+              if (g2 == g) v += bv[g];
+              else v -= __ldg(a.ain + row * NCG + g2) * xo[g2];
+            }
+            v -= __ldg(of + 3) * xn[3][g];
+            v -= __ldg(of + 4) * xn[4][g];
+            v -= __ldg(of + 5) * xn[5][g];
+            xo[g] = v * __ldg(a.qd + row);
+          }
+          double snew = 0., sn[NCG];
+#pragma unroll
+          for (int e = 0; e < NCG; e++) {
+            double sv = 0.;
+#pragma unroll
+            for (int g = 0; g < NCG; g++) sv += __ldg(a.mm + ((int64_t)cell * NCG + e) * NCG + g) * xo[g];
+            sn[e] = sv;
+            snew += sv;
+          }
+#pragma unroll
+          for (int g = 0; g < NCG; g++) { Xs[li * NCG + g] = xo[g]; SNv[iv * NCG + g] = sn[g]; }
+          if (need && fabs(sold) > CMFD_FLUX_EPS) { const double q = (snew - sold) / sold; part += q * q; }
+        }
+        if (colour == 1 && need) reduce_put(part);
+        cluster.sync();
+      }
+      double r = 0.;
+      if (need) r = sqrt(fmax(reduce_get(), 0.) * inv_cells);
+      if (liter == 0) { lres = r; linit = r; lin_res_first = r; }
+      liter++;
+      if (liter > 25) {
+        lres = r;
+        if (lres < min_res) min_res = lres;
+        if ((lres > 1e3 * min_res && min_res > 1e-10) || !(lres == lres)) { ok = false; break; }
+        if (lres / linit < 0.1 || lres < lin_tol) break;
+      }
+    }
+    lin_total += liter;
+    lin_iters = liter;
+    if (liter >= 10000) ok = false;
+    if (!ok) break;
+
+    local = 0.;
+    CMFD_MY_CELLS({
+#pragma unroll
+      for (int e = 0; e < NCG; e++) local += SNv[iv * NCG + e];
+    })
+    sum = reduce(local);
+    k = sum / (double)nr;
+    const double inv_k = 1.0 / k;
+    local = 0.;
+    CMFD_MY_CELLS({
+      double snew = 0., sold = 0.;
+#pragma unroll
+      for (int e = 0; e < NCG; e++) {
+        const double v = SNv[iv * NCG + e] * inv_k;
+        snew += v;
+        sold += Bv[iv * NCG + e];
+        Bv[iv * NCG + e] = v;
+      }
+      if (fabs(sold) > CMFD_FLUX_EPS) { const double q = (snew - sold) / sold; local += q * q; }
+    })
+    residual = sqrt(fmax(reduce(local), 0.) * inv_cells);
+    if (iter == 0) {
+      initial_residual = residual;
+      if (initial_residual < 1e-14) initial_residual = 1e-10;
+      res_1 = residual; lin_iters_1 = lin_iters; lin_res_1 = lin_res_first;
+    }
+    if ((residual / initial_residual < 0.03 || residual < a.linalg_tol) && iter > 25) { converged = true; break; }
+  }
+  if (!converged) ok = false;
+
+  if (ok) {
+    double ln = 0., lo = 0.;
+    CMFD_MY_CELLS({
+#pragma unroll
+      for (int e = 0; e < NCG; e++) {
+        double sn = 0., so = 0.;
+#pragma unroll
+        for (int g = 0; g < NCG; g++) {
+          const double m = __ldg(a.mm + ((int64_t)cell * NCG + e) * NCG + g);
+          sn += m * Xs[li * NCG + g];
+          so += m * a.old_flux[(int64_t)cell * NCG + g];
+        }
+        ln += sn; lo += so;
+      }
+    })
+    const double sum_new = reduce(ln);
+    const double sum_old = reduce(lo);
+    const double fn = 1.0 / sum_new, fo = 1.0 / sum_old;
+    CMFD_MY_CELLS({
+#pragma unroll
+      for (int e = 0; e < NCG; e++) {
+        a.new_flux[(int64_t)cell * NCG + e] = Xs[li * NCG + e] * fn;
+        a.old_flux[(int64_t)cell * NCG + e] *= fo;
+      }
+    })
+  }
+#undef CMFD_MY_CELLS
+  if (rank == 0 && threadIdx.x == 0) {
+    a.ci[CI_FAIL] = ok ? 0 : 1;
+    a.ci[CI_POWER_ITERS] = iter;
+    a.ci[CI_LIN_ITERS_1] = lin_iters_1;
+    a.ci[CI_LIN_ITERS_END] = lin_iters;
+    a.ci[CI_LIN_TOTAL] = lin_total;
+    a.ci[CI_SOLVES] += 1;
+    a.cs[CS_RES_1] = res_1; a.cs[CS_RES_END] = residual;
+    a.cs[CS_LIN_RES_1] = lin_res_1; a.cs[CS_LIN_RES_END] = lin_res_first;
+    if (ok) a.cs[CS_KEFF] = k;
+    a.scal[SC_KPREV] = a.scal[SC_KEFF];
+    a.scal[SC_KEFF] = a.cs[CS_KEFF];
+    *reinterpret_cast<long long*>(&a.ci[CI_PF_MAX]) = 0;
+    *reinterpret_cast<long long*>(&a.ci[CI_PF_MIN]) = 0;
+  }
+  cluster.sync();       /* no CTA leaves while another may still read its shared memory */
 }
 
 /* ------------------------------------------------------------------------------------------ */

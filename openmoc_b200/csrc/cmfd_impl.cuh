@@ -17,10 +17,14 @@ struct b200_cmfd {
   DevBuf<int64_t> cell_fsr_off, sv_off, se_off, st_off;
   DevBuf<double> st_w, st_own, ax_interp;
   DevBuf<double> rxn, volc, dift, xs_t, xs_nf, xs_chi, xs_s, old_flux, new_flux, dcoef, old_corr;
-  DevBuf<double> diag, off, ain, mm, B, SO, SN, partials, cs;
+  DevBuf<double> diag, off, ain, mm, B, SO, SN, partials, cs, dq, qd;
+  DevBuf<int32_t> slot_cell;
+  int grid_threads = CMFD_GRID_THREADS;
   DevBuf<int> ci;
-  int eigen_mode = 0, eigen_blocks = 1;
+  int eigen_mode = 0, eigen_blocks = 1;     /* 0 one CTA, 1 cooperative grid, 2 one thread-block cluster */
   size_t eigen_smem = 0;
+  int cluster_slots = 0, cluster_all_smem = 0;
+  DevBuf<int32_t> nb_loc;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   void release() {
     if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); ev0 = ev1 = nullptr; }
@@ -31,7 +35,7 @@ struct b200_cmfd {
     rxn.release(); volc.release(); dift.release(); xs_t.release(); xs_nf.release(); xs_chi.release(); xs_s.release();
     old_flux.release(); new_flux.release(); dcoef.release(); old_corr.release();
     diag.release(); off.release(); ain.release(); mm.release(); B.release(); SO.release(); SN.release();
-    partials.release(); cs.release(); ci.release();
+    partials.release(); cs.release(); ci.release(); nb_loc.release(); dq.release(); qd.release(); slot_cell.release();
   }
 };
 
@@ -45,6 +49,17 @@ static cmfd_eigen_fn cmfd_pick_eigen(int ncg) {
     case 4: return cmfd_eigen_kernel<MODE, 4>;
     case 7: return cmfd_eigen_kernel<MODE, 7>;
     default: return cmfd_eigen_kernel<MODE, 0>;
+  }
+}
+
+typedef void (*cmfd_cluster_fn)(CmfdArgs, CmfdClusterArgs, double);
+static cmfd_cluster_fn cmfd_pick_cluster(int ncg) {
+  switch (ncg) {
+    case 1: return cmfd_eigen_cluster_kernel<1>;
+    case 2: return cmfd_eigen_cluster_kernel<2>;
+    case 4: return cmfd_eigen_cluster_kernel<4>;
+    case 7: return cmfd_eigen_cluster_kernel<7>;
+    default: return nullptr;
   }
 }
 
@@ -264,7 +279,7 @@ extern "C" int b200_cmfd_configure(b200_solver* s, const b200_cmfd_config* cfg, 
   CU(c->xs_chi.alloc(nr)); CU(c->xs_s.alloc(nr * ncg)); CU(c->old_flux.alloc(nr)); CU(c->new_flux.alloc(nr));
   CU(c->dcoef.alloc(nr * 3)); CU(c->old_corr.alloc(nr * CMFD_NF)); CU(c->diag.alloc(nr)); CU(c->off.alloc(nr * CMFD_NF));
   CU(c->ain.alloc(nr * ncg)); CU(c->mm.alloc(nr * ncg)); CU(c->B.alloc(nr)); CU(c->SO.alloc(nr)); CU(c->SN.alloc(nr));
-  CU(c->cs.alloc(CS_COUNT)); CU(c->ci.alloc(CI_COUNT));
+  CU(c->cs.alloc(CS_COUNT)); CU(c->ci.alloc(CI_COUNT)); CU(c->dq.alloc(nr)); CU(c->qd.alloc(nr));
   CU(cudaMemsetAsync(c->old_corr.p, 0, nr * CMFD_NF * 8, st));
   CU(cudaMemsetAsync(c->ci.p, 0, CI_COUNT * sizeof(int), st));
   double cs0[CS_COUNT] = {0};
@@ -272,28 +287,98 @@ extern "C" int b200_cmfd_configure(b200_solver* s, const b200_cmfd_config* cfg, 
   cs0[CS_THRESH] = 1e-5;               /* Cmfd.cpp:23 */
   CU(cudaMemcpyAsync(c->cs.p, cs0, sizeof cs0, cudaMemcpyHostToDevice, st));
 
-  /* launch shape of the eigenvalue solve: one CTA while a colour fits its threads a few times over, a cooperative
-   * grid otherwise */
+  /* launch shape of the eigenvalue solve.  One thread-block cluster with the flux in distributed shared memory
+   * while a thread has at most a few cells per colour (mode 2); a cooperative grid with the flux in L2 for larger
+   * meshes or unusual group counts (mode 1); one CTA for tiny meshes (mode 0).  B200_CMFD_MODE overrides. */
   const int64_t n_slots = (int64_t)cfg->num_z * cfg->num_y * ((cfg->num_x + 1) / 2);
-  int mode = n_slots <= CMFD_BLOCK_THREADS ? 0 : 1;        /* one cell per thread and colour, or spread over SMs */
-  if (const char* e = getenv("B200_CMFD_MODE")) mode = atoi(e) != 0;
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, s->cfg.device));
-  if (mode == 1 && !prop.cooperativeLaunch) mode = 0;
-  c->eigen_mode = mode;
+  {
+    /* cell of every slot of the two colours (linalg.cpp:276-279: ix runs over (iy + iz + colour) % 2, +2, ...) */
+    const int hx = (cfg->num_x + 1) / 2;
+    std::vector<int32_t> slot_cell(2 * n_slots, -1);
+    for (int colour = 0; colour < 2; colour++)
+      for (int64_t idx = 0; idx < n_slots; idx++) {
+        const int64_t rowi = idx / hx;
+        const int k = (int)(idx - rowi * hx), iy = (int)(rowi % cfg->num_y), iz = (int)(rowi / cfg->num_y);
+        const int ix = 2 * k + ((iy + iz + colour) & 1);
+        if (ix < cfg->num_x) slot_cell[colour * n_slots + idx] = (int32_t)(rowi * cfg->num_x + ix);
+      }
+    CU(c->slot_cell.upload(slot_cell.data(), slot_cell.size(), st));
+    CU(cudaStreamSynchronize(st));
+  }
+  /* measured on a B200 (tools/cmfd_tune.sh, profiles/r02_cmfd.md): a colour phase costs ~1.4 us + 0.01 us per cell
+   * of the busiest SM on a cluster and ~3.9 us on a cooperative grid with one 128-thread CTA per SM */
+  int mode = n_slots <= 64 ? 0 : (n_slots <= 4096 ? 2 : 1);
+  if (const char* e = getenv("B200_CMFD_MODE")) mode = atoi(e);
+  if (mode < 0 || mode > 2) return fail("B200_CMFD_MODE must be 0, 1 or 2");
+  if (mode == 2 && cmfd_pick_cluster(ncg) == nullptr) mode = 1;
   c->eigen_smem = 0;
   c->eigen_blocks = 1;
+  if (mode == 2) {
+    /* the update of a cell is a chain of dependent FP64 operations: spread the cells over as many SMs as a
+     * cluster spans rather than filling the threads of few CTAs */
+    int C = (int)std::min<int64_t>(16, (n_slots + 31) / 32);
+    if (const char* e = getenv("B200_CMFD_CLUSTER")) C = std::max(1, std::min(16, atoi(e)));
+    const void* fn = (const void*)cmfd_pick_cluster(ncg);
+    const size_t limit = (size_t)prop.sharedMemPerBlockOptin - 2048;
+    bool placed = false;
+    for (; C >= 1 && !placed; C = (C > 8 ? 8 : C / 2)) {
+      const int S = (int)((n_slots + C - 1) / C);
+      const size_t xb = (size_t)S * 2 * ncg * sizeof(double);
+      if (xb > limit) { if (C == 1) break; continue; }
+      const int all = 4 * xb <= limit;
+      const size_t smem = all ? 4 * xb : xb;
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); if (C == 1) break; continue; }
+      if (C > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(C); lc.blockDim = dim3(CMFD_CLUSTER_THREADS); lc.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      lc.attrs = at; lc.numAttrs = 1;
+      int n_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, fn, &lc) != cudaSuccess || n_clusters < 1) { cudaGetLastError(); if (C == 1) break; continue; }
+      c->eigen_blocks = C; c->eigen_smem = smem; c->cluster_slots = S; c->cluster_all_smem = all;
+      placed = true;
+      break;
+    }
+    if (!placed) mode = 1;
+  }
+  if (mode == 2) {
+    /* where the flux of every neighbour lives: owning CTA and offset in its shared memory */
+    const int hx = (cfg->num_x + 1) / 2, S = c->cluster_slots;
+    std::vector<int32_t> loc(n_cells * CMFD_NF, -1);
+    for (int64_t i = 0; i < n_cells; i++)
+      for (int f = 0; f < CMFD_NF; f++) {
+        const int64_t nbc = nbr[i * CMFD_NF + f];
+        if (nbc < 0) continue;
+        const int ix = (int)(nbc % cfg->num_x), iy = (int)((nbc / cfg->num_x) % cfg->num_y), iz = (int)(nbc / ((int64_t)cfg->num_x * cfg->num_y));
+        const int colour = (ix + iy + iz) & 1;
+        const int64_t idx = ((int64_t)iz * cfg->num_y + iy) * hx + ix / 2;
+        const int r = (int)(idx / S);
+        loc[i * CMFD_NF + f] = (int32_t)((r << 26) | (int)((idx - (int64_t)r * S) * 2 + colour));
+      }
+    CU(c->nb_loc.upload(loc.data(), loc.size(), st));
+    CU(cudaStreamSynchronize(st));
+  }
+  if (mode == 1 && !prop.cooperativeLaunch) mode = 0;
+  c->eigen_mode = mode;
   if (mode == 0) {
     const size_t need = nr * sizeof(double);
     if (need <= (size_t)prop.sharedMemPerBlockOptin - 1024) {
       c->eigen_smem = need;
       CU(cudaFuncSetAttribute((const void*)cmfd_pick_eigen<0>(ncg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     }
-  } else {
+  } else if (mode == 1) {
+    /* few warps per SM on as many SMs as the mesh can use (see above) */
+    int threads = n_slots <= (int64_t)prop.multiProcessorCount * 128 ? 128 : CMFD_GRID_THREADS;
+    if (const char* e = getenv("B200_CMFD_THREADS")) threads = std::max(32, std::min(CMFD_GRID_THREADS, atoi(e) / 32 * 32));
+    c->grid_threads = threads;
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmfd_pick_eigen<1>(ncg), CMFD_GRID_THREADS, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmfd_pick_eigen<1>(ncg), threads, 0));
     if (per_sm < 1) return fail("b200_cmfd_configure: the cooperative CMFD kernel does not fit an SM");
-    int64_t blocks = (n_slots + CMFD_GRID_THREADS - 1) / CMFD_GRID_THREADS;
+    int64_t blocks = (n_slots + threads - 1) / threads;
     const int64_t cap = (int64_t)per_sm * prop.multiProcessorCount;
     if (blocks > cap) blocks = cap;
     if (const char* e = getenv("B200_CMFD_BLOCKS")) blocks = std::max<int64_t>(1, std::min<int64_t>(cap, atoll(e)));
@@ -392,6 +477,7 @@ static CmfdArgs cmfd_args(b200_solver* s) {
   a.dcoef = c->dcoef.p; a.old_corr = c->old_corr.p; a.diag = c->diag.p; a.off = c->off.p; a.ain = c->ain.p;
   a.mm = c->mm.p; a.B = c->B.p; a.SO = c->SO.p; a.SN = c->SN.p; a.partials = c->partials.p;
   a.cs = c->cs.p; a.ci = c->ci.p; a.x_in_smem = c->eigen_smem > 0;
+  a.dq = c->dq.p; a.qd = c->qd.p; a.slot_cell = c->slot_cell.p;
   a.st_off = c->st_off.p; a.st_cell = c->st_cell.p; a.st_w = c->st_w.p; a.st_own = c->st_own.p; a.st_n = c->st_n.p;
   a.ax_interp = c->ax_interp.p;
   return a;
@@ -424,10 +510,22 @@ static int enqueue_cmfd(b200_solver* s, int moc_iteration, double source_thresho
   cmfd_matrix_kernel<<<grid_for(c->n_cells * ncg, 256), 256, 0, st>>>(a, moc_iteration);
   CU(cudaGetLastError());
   void* params[] = {(void*)&a, (void*)&source_threshold};
-  if (c->eigen_mode == 0)
+  if (c->eigen_mode == 2) {
+    CmfdClusterArgs ca;
+    ca.slots_per_cta = c->cluster_slots; ca.all_smem = c->cluster_all_smem; ca.nb_loc = c->nb_loc.p;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(c->eigen_blocks); lc.blockDim = dim3(CMFD_CLUSTER_THREADS); lc.dynamicSmemBytes = c->eigen_smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = c->eigen_blocks; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    void* cparams[] = {(void*)&a, (void*)&ca, (void*)&source_threshold};
+    CU(cudaLaunchKernelExC(&lc, (const void*)cmfd_pick_cluster(ncg), cparams));
+  } else if (c->eigen_mode == 0)
     CU(cudaLaunchKernel((const void*)cmfd_pick_eigen<0>(ncg), dim3(1), dim3(CMFD_BLOCK_THREADS), params, c->eigen_smem, st));
   else
-    CU(cudaLaunchCooperativeKernel((const void*)cmfd_pick_eigen<1>(ncg), dim3(c->eigen_blocks), dim3(CMFD_GRID_THREADS),
+    CU(cudaLaunchCooperativeKernel((const void*)cmfd_pick_eigen<1>(ncg), dim3(c->eigen_blocks), dim3(c->grid_threads),
                                    params, 0, st));
   cmfd_update_kernel<<<grid_for(s->n_fsr, 256), 256, 0, st>>>(a, moc_iteration);
   CU(cudaGetLastError());

@@ -376,6 +376,15 @@ int main(int argc, char** argv) {
           }
         fprintf(f, "],\n");
       }
+      {
+        double cmfd_ms = 0.; long cmfd_lin = 0;
+        B200LSSolver* lsp = dynamic_cast<B200LSSolver*>(solver);
+        if (b200_solver != NULL) b200_solver->getCmfdStats(&cmfd_ms, &cmfd_lin);
+        else if (lsp != NULL) lsp->getCmfdStats(&cmfd_ms, &cmfd_lin);
+        Timer timer2;
+        fprintf(f, " \"cmfd_time_s\": %.9g, \"cmfd_kernels_s\": %.9g, \"cmfd_sor_iterations\": %ld,\n",
+                timer2.getSplit("Total CMFD time"), cmfd_ms * 1e-3, cmfd_lin);
+      }
       fprintf(f, " \"iterations\": %d, \"keff\": %.17g, \"sweep_time_s\": %.9g, "
                  "\"total_time_s\": %.9g, \"integrations\": %.17g,\n",
               it, solver->getKeff(), sweep_time, total_time, 2.0 * F * (double)n_seg * it);

@@ -141,12 +141,20 @@ def test_device_cmfd_options_and_boundaries(args):
     assert r["dk_pcm"] < 1e-2 and r["max_rel_flux_err"] < 2e-5
 
 
-@pytest.mark.parametrize("mode", ["0", "1"])
-def test_device_cmfd_one_cta_and_cooperative_grid_agree(mode, monkeypatch):
-    """The eigenvalue kernel as one CTA (flux in shared memory, __syncthreads) and as a cooperative grid (flux in
-    L2, grid barrier): both against the reference."""
+@pytest.mark.parametrize("mode,cluster", [("0", None), ("1", None), ("2", None), ("2", "3"), ("2", "16")])
+@pytest.mark.parametrize("args", [
+    ["--model", "simple-lattice", "--azim", "8", "--spacing", "0.05", "--cmfd", "4x4"],
+    ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
+     "--zspacing", "0.9", "--cmfd", "5x4x3", "--no-knearest"],
+])
+def test_device_cmfd_launch_shapes_agree(args, mode, cluster, monkeypatch):
+    """The eigenvalue kernel as one CTA (flux in shared memory, __syncthreads), as a cooperative grid (flux in L2,
+    grid barrier) and as one thread-block cluster (flux in distributed shared memory, cluster barrier; also with
+    more CTAs than the mesh needs): all against the reference."""
     monkeypatch.setenv("B200_CMFD_MODE", mode)
-    r = run(["--model", "simple-lattice", "--azim", "8", "--spacing", "0.05", "--cmfd", "4x4", "--solver", "both"])
+    if cluster is not None:
+        monkeypatch.setenv("B200_CMFD_CLUSTER", cluster)
+    r = run(args + ["--solver", "both"])
     assert r["cmfd_on_device"] and r["b200_iters"] == r["cpu_iters"]
     assert r["dk_pcm"] < 1e-4 and r["max_rel_flux_err"] < 1e-9
 

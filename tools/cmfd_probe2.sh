@@ -6,10 +6,12 @@ A="--model c5g7-2d --azim 32 --spacing 0.1 --cmfd 51x51 --threads 16"
 run $A
 B200_HOST_CMFD=1 run $A
 B200_CMFD_MODE=1 run $A
+B200_CMFD_MODE=2 B200_CMFD_CLUSTER=8 run $A
 B="--model c5g7-2d --dims 3 --azim 4 --polar 2 --spacing 1.0 --zspacing 5 --axial 9 --formation otf-stacks --cmfd 51x51x9 --max-iters 20 --threads 16"
 run $B
 B200_HOST_CMFD=1 run $B
-B200_CMFD_MODE=0 run $B
+B200_CMFD_MODE=1 run $B
+B200_CMFD_MODE=2 B200_CMFD_CLUSTER=8 run $B
 echo "== fused"
 for m in "--model simple-lattice --azim 8 --spacing 0.05 --cmfd 4x4" "--model c5g7-2d --azim 8 --spacing 0.2 --cmfd 51x51 --max-iters 60"; do
   $D $m --solver cpu --threads 4 --quiet --json /tmp/cpu.json > /dev/null 2>&1
