@@ -148,6 +148,16 @@ int b200_set_cmfd_groups(b200_solver* s, const int32_t* moc_to_cmfd_group, int32
                          int64_t num_cmfd_cells);   /* num_cmfd_groups <= 0 switches the tally off */
 int b200_get_cmfd_currents(b200_solver* s, double* out, int64_t n);
 
+/* CMFD on axially traced tracks (call between b200_upload_otf_geometry and b200_finalize): the device tracer then
+ * also produces segment::_cmfd_surface_fwd/_bwd of every 3D segment, the way traceSegmentsOTF / traceStackOTF do
+ * (src/TraverseSegments.cpp:429-457, 689-765; Cmfd::findCmfdSurfaceOTF -> Lattice::getLatticeSurfaceOTF,
+ * src/Universe.cpp:2241-2326): seg2d_surface_fwd/bwd[n_segments_2d] = surface (0..9: x / y faces and z-parallel edges,
+ * src/constants.h:120-129) the radial segment crosses at its forward / backward end, or -1;
+ * fsr_cmfd_cell[n_fsrs] = Geometry::getCmfdCell; z_planes[num_z+1] = the z planes of the CMFD mesh. */
+int b200_upload_otf_cmfd(b200_solver* s, const int8_t* seg2d_surface_fwd, const int8_t* seg2d_surface_bwd,
+                         const int32_t* fsr_cmfd_cell, int32_t num_x, int32_t num_y, int32_t num_z,
+                         const double* z_planes);
+
 /* ---- CMFD acceleration on the device ----
  * Replaces what Cmfd::computeKeff (src/Cmfd.cpp:1192-1295) does between two sweeps: splitVertexCurrents /
  * splitEdgeCurrents (:2126-2331), collapseXS (:720-1007), constructMatrices (:1353-1500, with

@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200_upload_cmfd_surfaces": [_vp, _vp],
     "b200_set_cmfd_groups": [_vp, _i32, _i64],
     "b200_get_cmfd_currents": [_vp, _i64],
+    "b200_upload_otf_cmfd": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "b200_cmfd_configure": [C.POINTER(CmfdConfig)] + [_vp] * 9,
     "b200_cmfd_set_stencils": [_vp] * 5,
     "b200_cmfd_set_axial_interpolants": [_vp],

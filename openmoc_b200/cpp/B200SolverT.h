@@ -221,14 +221,10 @@ void B200SolverT<Base>::ensureDevice() {
   if (_h != NULL) { b200_destroy(_h); _h = NULL; }
   _flattened_key = key;
 
-  /* On-the-fly 3D formations go to the device tracer (no 3D segment is made on the host) unless a
-   * per-segment datum only the host traversal produces is needed: CMFD surfaces, linear-source starting
+  /* On-the-fly 3D formations go to the device tracer (no 3D segment is made on the host), CMFD surfaces
+   * included, unless a per-segment datum only the host traversal produces is needed: linear-source starting
    * points.  B200_HOST_OTF=1 forces the host expansion. */
   bool device_otf = b200_can_trace_on_device(_track_generator) && !isLinearSource() && getenv("B200_HOST_OTF") == NULL;
-  {
-    Cmfd* cmfd = _geometry->getCmfd();
-    if (cmfd != NULL && cmfd->isFluxUpdateOn()) device_otf = false;
-  }
   b200_flatten(_track_generator, &_flat, isLinearSource(), device_otf);
   b200_config cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -251,6 +247,10 @@ void B200SolverT<Base>::ensureDevice() {
                                    _flat.seg2d_ext.data(), _flat.trk2d_seg_offset.data(), _flat.n_extruded,
                                    _flat.ext_offset.data(), _flat.ext_mesh.data(), _flat.ext_fsr.data(), 0,
                                    _flat.otf_theta.data()), "b200_upload_otf_geometry");
+    if (_flat.otf_cmfd)
+      check(b200_upload_otf_cmfd(_h, _flat.seg2d_surf_fwd.data(), _flat.seg2d_surf_bwd.data(), _flat.fsr_cmfd_cell.data(),
+                                 _flat.cmfd_nx, _flat.cmfd_ny, _flat.cmfd_nz, _flat.cmfd_z_planes.data()),
+            "b200_upload_otf_cmfd");
     check(b200_upload_tracks_otf(_h, _flat.trk_2d.data(), _flat.trk_l0.data(), _flat.trk_z0.data(), _flat.trk_azim.data(),
                                  _flat.trk_polar.data(), _flat.trk_next_fwd.data(), _flat.trk_next_bwd.data(),
                                  _flat.trk_flags.data(), _flat.trk_bc_fwd.data(), _flat.trk_bc_bwd.data(), NULL),
@@ -270,7 +270,7 @@ void B200SolverT<Base>::ensureDevice() {
   uploadExtras();
   {
     Cmfd* cmfd = _geometry->getCmfd();
-    if (cmfd != NULL && cmfd->isFluxUpdateOn())
+    if (cmfd != NULL && cmfd->isFluxUpdateOn() && !_flat.device_otf)
       check(b200_upload_cmfd_surfaces(_h, _flat.seg_cmfd_fwd.data(), _flat.seg_cmfd_bwd.data()),
             "b200_upload_cmfd_surfaces");
   }

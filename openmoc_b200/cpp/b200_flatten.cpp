@@ -5,6 +5,7 @@
  * Compiled against the reference's headers; see b200_flatten.h.
  */
 #include "b200_flatten.h"
+#include "Cmfd.h"
 
 #include <cstdio>
 #include <cstring>
@@ -149,13 +150,30 @@ void flatten_for_device_tracer(TrackGenerator3D* tg3, B200FlatTracks* ft) {
   for (long t = 0; t < n2; t++) ft->trk2d_seg_offset[t + 1] = ft->trk2d_seg_offset[t] + t2d[t]->getNumSegments();
   const int64_t ns2 = ft->trk2d_seg_offset[n2];
   ft->seg2d_length.resize(ns2); ft->seg2d_ext.resize(ns2);
+  Cmfd* cmfd = geometry->getCmfd();
+  ft->otf_cmfd = (cmfd != NULL && cmfd->isFluxUpdateOn());
+  if (ft->otf_cmfd) { ft->seg2d_surf_fwd.assign(ns2, -1); ft->seg2d_surf_bwd.assign(ns2, -1); }
   for (long t = 0; t < n2; t++) {
     segment* segs = t2d[t]->getSegments();
     int64_t o = ft->trk2d_seg_offset[t];
     for (int s = 0; s < t2d[t]->getNumSegments(); s++, o++) {
       ft->seg2d_length[o] = segs[s]._length;
       ft->seg2d_ext[o] = segs[s]._region_id;
+      if (ft->otf_cmfd) {
+        /* only the surface part matters: the 3D cell comes from the 3D FSR (TraverseSegments.cpp:447-456) */
+        if (segs[s]._cmfd_surface_fwd != -1) ft->seg2d_surf_fwd[o] = (int8_t)(segs[s]._cmfd_surface_fwd % NUM_SURFACES);
+        if (segs[s]._cmfd_surface_bwd != -1) ft->seg2d_surf_bwd[o] = (int8_t)(segs[s]._cmfd_surface_bwd % NUM_SURFACES);
+      }
     }
+  }
+  if (ft->otf_cmfd) {
+    ft->fsr_cmfd_cell.resize(ft->n_fsrs);
+    for (int64_t r = 0; r < ft->n_fsrs; r++) ft->fsr_cmfd_cell[r] = geometry->getCmfdCell(r);
+    Lattice* lat = cmfd->getLattice();
+    ft->cmfd_nx = cmfd->getNumX(); ft->cmfd_ny = cmfd->getNumY(); ft->cmfd_nz = cmfd->getNumZ();
+    const std::vector<double>& acc = lat->getAccumulateZ();
+    ft->cmfd_z_planes.resize(ft->cmfd_nz + 1);
+    for (int k = 0; k <= ft->cmfd_nz; k++) ft->cmfd_z_planes[k] = acc[k] + lat->getMinZ();
   }
 
   /* extruded FSRs: axial mesh (their own, or the global one) and 3D FSR ids, bottom-up */

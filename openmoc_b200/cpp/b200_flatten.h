@@ -78,6 +78,14 @@ struct B200FlatTracks {
   std::vector<double> seg2d_length, ext_mesh, otf_theta, trk_l0, trk_z0;
   std::vector<int32_t> seg2d_ext, ext_fsr, trk_2d;
   std::vector<int64_t> trk2d_seg_offset, ext_offset;
+  /* CMFD with the device tracer (b200_upload_otf_cmfd): the surface the 2D segments cross at their ends
+   * (segment::_cmfd_surface_fwd/_bwd % NUM_SURFACES of the radial tracks, or -1), Geometry::getCmfdCell of every
+   * 3D FSR and the z planes of the CMFD lattice; filled when the Geometry has a Cmfd */
+  bool otf_cmfd = false;
+  std::vector<int8_t> seg2d_surf_fwd, seg2d_surf_bwd;
+  std::vector<int32_t> fsr_cmfd_cell;
+  std::vector<double> cmfd_z_planes;
+  int cmfd_nx = 0, cmfd_ny = 0, cmfd_nz = 0;
 };
 
 /**
@@ -90,7 +98,7 @@ void b200_flatten(TrackGenerator* track_generator, B200FlatTracks* out,
 
 /** True when the tracks can go to the device tracer: an on-the-fly 3D formation (OTF_TRACKS or
  *  OTF_STACKS).  The caller still falls back to the host expansion when it needs per-segment data
- *  the tracer does not produce (CMFD surfaces, linear-source starting points). */
+ *  the tracer does not produce (linear-source starting points). */
 bool b200_can_trace_on_device(TrackGenerator* track_generator);
 
 /** Write / read the chunked binary track file (see openmoc_b200/trackfile.py). */

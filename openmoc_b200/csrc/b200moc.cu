@@ -137,6 +137,12 @@ struct b200_solver {
   DevBuf<double> otf_max_sigt;
   bool otf_split = false;             /* the stream was traced with the optical-length cuts */
   int64_t otf_n_trk2d = 0, otf_n_seg2d = 0, otf_n_ext = 0;
+  /* CMFD surfaces from the device tracer (b200_upload_otf_cmfd) */
+  bool otf_cmfd = false, otf_cmfd_filled = false;
+  DevBuf<int8_t> otf_surf_fwd, otf_surf_bwd;
+  DevBuf<int32_t> otf_fsr_cell;
+  DevBuf<double> otf_cmfd_z;
+  int otf_cmfd_nxy = 0;
   int n_rep = 1;                      /* tally replicas */
   bool capturing = false;             /* inside cudaStreamBeginCapture: no events, no host syncs */
   cudaGraphExec_t iter_graph = nullptr;   /* two fused source iterations (one per psi buffer parity) */
@@ -226,6 +232,11 @@ struct b200_group {
   std::vector<double> seg2d_len, ext_mesh, theta, trk_l0, trk_z0;
   std::vector<int32_t> seg2d_ext, ext_fsr, trk_2d;
   std::vector<int64_t> trk2d_off, ext_off;
+  bool have_otf_cmfd = false;
+  std::vector<int8_t> otf_surf_fwd, otf_surf_bwd;
+  std::vector<int32_t> otf_fsr_cell;
+  std::vector<double> otf_cmfd_z;
+  int otf_cmfd_nx = 0, otf_cmfd_ny = 0, otf_cmfd_nz = 0;
   /* volume tracks of b200_otf_compute_volumes */
   bool have_voltrk = false;
   std::vector<int32_t> v_2d, v_azim, v_polar;
@@ -440,6 +451,7 @@ extern "C" int b200_destroy(b200_solver* s) {
   s->cmfd_fwd.release(); s->cmfd_bwd.release(); s->cmfd_group.release(); s->seg_cmfd.release(); s->currents.release();
   s->otf_seg2d_len.release(); s->otf_mesh.release(); s->otf_l0.release(); s->otf_z0.release(); s->otf_cos.release();
   s->otf_sin.release(); s->otf_volw.release(); s->otf_seg2d_ext.release(); s->otf_ext_fsr.release(); s->otf_trk2d.release();
+  s->otf_surf_fwd.release(); s->otf_surf_bwd.release(); s->otf_fsr_cell.release(); s->otf_cmfd_z.release();
   s->otf_max_sigt.release(); s->otf_cls.release(); s->otf_count.release(); s->otf_trk2d_off.release(); s->otf_ext_off.release();
   s->f1tab.release(); s->qst_pad.release(); s->qxyz_pad.release(); s->tally_pad.release(); s->tallym_pad.release();
   s->phi_old.release(); s->fixed.release(); s->stab.release(); s->scratch.release();
@@ -709,6 +721,8 @@ static OtfGeom otf_geom(b200_solver* s) {
   g.ext_mesh = s->otf_mesh.p; g.ext_fsr = s->otf_ext_fsr.p; g.n_axial = s->otf_n_axial;
   g.trk_2d = s->otf_trk2d.p; g.trk_l0 = s->otf_l0.p; g.trk_z0 = s->otf_z0.p; g.trk_class = s->otf_cls.p;
   g.cls_cos_theta = s->otf_cos.p; g.cls_sin_theta = s->otf_sin.p;
+  g.seg2d_surf_fwd = s->otf_cmfd ? s->otf_surf_fwd.p : nullptr; g.seg2d_surf_bwd = s->otf_surf_bwd.p;
+  g.fsr_cmfd_cell = s->otf_fsr_cell.p; g.cmfd_z = s->otf_cmfd_z.p; g.cmfd_nxy = s->otf_cmfd_nxy;
   g.n_trk = s->n_trk;
   g.fsr_max_sigma_t = nullptr; g.max_tau = s->max_tau;
   return g;
@@ -851,7 +865,7 @@ extern "C" int b200_otf_compute_volumes(b200_solver* s, int64_t n, const int32_t
   g.trk_2d = tmp.trk2d.p; g.trk_l0 = tmp.l0.p; g.trk_z0 = tmp.z0.p; g.trk_class = tmp.cls.p;
   g.n_trk = n;
   if (n > 0) {
-    otf_fill_kernel<<<grid_for(n, 128, 1 << 20), 128, 0, s->stream>>>(g, nullptr, nullptr, s->G, s->otf_volw.p, s->vol.p);
+    otf_fill_kernel<<<grid_for(n, 128, 1 << 20), 128, 0, s->stream>>>(g, nullptr, nullptr, s->G, s->otf_volw.p, s->vol.p, nullptr);
     CU(cudaGetLastError());
   }
   CU(cudaStreamSynchronize(s->stream));
@@ -902,7 +916,8 @@ static int otf_expand(b200_solver* s, bool with_cuts) {
   CU(cudaStreamSynchronize(s->stream));
   int64_t ns = 0;
   for (int64_t t = 0; t < nt; t++) ns += cnt[t];
-  if (with_cuts && ns == s->n_seg && s->seg_rec_ready) return 0;      /* nothing to cut: the stream stands */
+  if (with_cuts && ns == s->n_seg && s->seg_rec_ready && (!s->otf_cmfd || s->otf_cmfd_filled))
+    return 0;                                                         /* nothing to cut: the stream stands */
   s->h_off.assign(nt + 1, 0);
   for (int64_t t = 0; t < nt; t++) s->h_off[t + 1] = s->h_off[t] + cnt[t];
   s->n_seg = ns;
@@ -913,12 +928,63 @@ static int otf_expand(b200_solver* s, bool with_cuts) {
   CU(s->seg_rec.alloc((size_t)ns + 2 * SEG_PAD));
   otf_pad_kernel<<<1, 2 * SEG_PAD, 0, s->stream>>>(s->seg_rec.p, ns);
   CU(cudaGetLastError());
+  if (s->otf_cmfd) {
+    /* the {forward, backward} CMFD surface stream of the sweep's current tally, padded like the records */
+    CU(s->seg_cmfd.alloc((size_t)ns + 2 * SEG_PAD));
+    CU(cudaMemsetAsync(s->seg_cmfd.p, 0xff, ((size_t)ns + 2 * SEG_PAD) * sizeof(int2), s->stream));
+  }
   if (nt > 0) {
-    otf_fill_kernel<<<grid_for(nt, 128, 1 << 20), 128, 0, s->stream>>>(g, s->trk_off.p, s->seg_rec.p + SEG_PAD, s->GP, nullptr, nullptr);
+    otf_fill_kernel<<<grid_for(nt, 128, 1 << 20), 128, 0, s->stream>>>(g, s->trk_off.p, s->seg_rec.p + SEG_PAD, s->GP, nullptr, nullptr,
+                                                                       s->otf_cmfd ? s->seg_cmfd.p + SEG_PAD : nullptr);
     CU(cudaGetLastError());
   }
   CU(cudaStreamSynchronize(s->stream));
+  if (s->otf_cmfd) { s->otf_cmfd_filled = true; s->have_cmfd_surf = true; }
   s->otf_split = with_cuts;
+  return 0;
+}
+
+/* CMFD with axially traced tracks: the tracer also produces segment::_cmfd_surface_fwd/_bwd of every 3D segment */
+extern "C" int b200_upload_otf_cmfd(b200_solver* s, const int8_t* seg2d_surface_fwd, const int8_t* seg2d_surface_bwd,
+                                    const int32_t* fsr_cmfd_cell, int32_t num_x, int32_t num_y, int32_t num_z,
+                                    const double* z_planes) {
+  NEED(s);
+  if (s->otf_n_seg2d == 0 && (s->grp == nullptr || !s->grp->have_geo))
+    return fail("b200_upload_otf_cmfd: b200_upload_otf_geometry has not been called");
+  if (!seg2d_surface_fwd || !seg2d_surface_bwd || !fsr_cmfd_cell || !z_planes) return fail("b200_upload_otf_cmfd: null argument");
+  if (num_x < 1 || num_y < 1 || num_z < 1) return fail("b200_upload_otf_cmfd: empty CMFD mesh");
+  const int64_t ns2 = s->grp != nullptr ? s->grp->n_seg2d : s->otf_n_seg2d;
+  const int64_t n_cells = (int64_t)num_x * num_y * num_z;
+  for (int64_t i = 0; i < ns2; i++)
+    if (seg2d_surface_fwd[i] < -1 || seg2d_surface_fwd[i] > 9 || seg2d_surface_bwd[i] < -1 || seg2d_surface_bwd[i] > 9)
+      return fail("b200_upload_otf_cmfd: 2D segment %lld crosses surface %d / %d; a radial segment can only cross x / y faces and edges (0..9)",
+                  (long long)i, seg2d_surface_fwd[i], seg2d_surface_bwd[i]);
+  for (int64_t r = 0; r < s->n_fsr; r++)
+    if (fsr_cmfd_cell[r] < 0 || fsr_cmfd_cell[r] >= n_cells)
+      return fail("b200_upload_otf_cmfd: FSR %lld lies in CMFD cell %d outside [0,%lld)", (long long)r, fsr_cmfd_cell[r], (long long)n_cells);
+  for (int k = 0; k < num_z; k++)
+    if (!(z_planes[k + 1] > z_planes[k])) return fail("b200_upload_otf_cmfd: the z planes of the CMFD mesh must increase");
+  if (s->grp != nullptr) {
+    b200_group* g = s->grp;
+    g->otf_surf_fwd.assign(seg2d_surface_fwd, seg2d_surface_fwd + ns2);
+    g->otf_surf_bwd.assign(seg2d_surface_bwd, seg2d_surface_bwd + ns2);
+    g->otf_fsr_cell.assign(fsr_cmfd_cell, fsr_cmfd_cell + s->n_fsr);
+    g->otf_cmfd_z.assign(z_planes, z_planes + num_z + 1);
+    g->otf_cmfd_nx = num_x; g->otf_cmfd_ny = num_y; g->otf_cmfd_nz = num_z;
+    g->have_otf_cmfd = true;
+    s->have_cmfd_surf = true;
+    s->finalized = false;
+    return 0;
+  }
+  CU(s->otf_surf_fwd.upload(seg2d_surface_fwd, ns2, s->stream));
+  CU(s->otf_surf_bwd.upload(seg2d_surface_bwd, ns2, s->stream));
+  CU(s->otf_fsr_cell.upload(fsr_cmfd_cell, s->n_fsr, s->stream));
+  CU(s->otf_cmfd_z.upload(z_planes, num_z + 1, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->otf_cmfd_nxy = num_x * num_y;
+  s->otf_cmfd = true;
+  s->otf_cmfd_filled = false;       /* the next expansion (b200_upload_tracks_otf / b200_finalize) writes the surface stream */
+  s->finalized = false;
   return 0;
 }
 

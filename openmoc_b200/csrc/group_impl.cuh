@@ -350,6 +350,9 @@ static int grp_finalize(b200_solver* s) {
       if (b200_upload_otf_geometry(sc, g->n_trk2d, g->n_seg2d, g->seg2d_len.data(), g->seg2d_ext.data(), g->trk2d_off.data(),
                                    g->n_ext, g->n_ext > 0 ? g->ext_off.data() : nullptr, g->ext_mesh.data(),
                                    g->n_ext > 0 ? g->ext_fsr.data() : nullptr, g->n_axial, g->theta.data())) return 1;
+      if (g->have_otf_cmfd &&
+          b200_upload_otf_cmfd(sc, g->otf_surf_fwd.data(), g->otf_surf_bwd.data(), g->otf_fsr_cell.data(), g->otf_cmfd_nx,
+                               g->otf_cmfd_ny, g->otf_cmfd_nz, g->otf_cmfd_z.data())) return 1;
       std::vector<int32_t> t2(n);
       std::vector<double> l0(n), z0(n);
       for (int64_t k = 0; k < n; k++) { t2[k] = g->trk_2d[ids[k]]; l0[k] = g->trk_l0[ids[k]]; z0[k] = g->trk_z0[ids[k]]; }

@@ -50,7 +50,37 @@ struct OtfGeom {
    * SegmentationKernel / TransportKernel cut them (src/MOCKernel.cpp:216-268, 353-410); NULL: no cuts */
   const double* __restrict__ fsr_max_sigma_t;
   double max_tau;
+  /* CMFD surfaces of the 3D segments (TraverseSegments.cpp:429-457 + Lattice::getLatticeSurfaceOTF,
+   * src/Universe.cpp:2241-2326): the surface (0..9, or -1) the 2D segment crosses at either end, the CMFD cell of
+   * every 3D FSR (Geometry::getCmfdCell) and the z planes of the CMFD mesh; seg2d_surf_fwd == NULL: no CMFD */
+  const int8_t* __restrict__ seg2d_surf_fwd;
+  const int8_t* __restrict__ seg2d_surf_bwd;
+  const int32_t* __restrict__ fsr_cmfd_cell;
+  const double* __restrict__ cmfd_z;
+  int cmfd_nxy;
 };
+
+/* Lattice::getLatticeSurfaceOTF: combines the 2D surface with a crossing of the cell's bottom / top plane */
+__device__ __forceinline__ int otf_cmfd_surface(const OtfGeom& g, int cell, double z, int surface_2d) {
+  const int lat_z = cell / g.cmfd_nxy;
+  int at = -1;
+  if (fabs(g.cmfd_z[lat_z] - z) < OTF_TINY_MOVE) at = 0;
+  else if (fabs(g.cmfd_z[lat_z + 1] - z) < OTF_TINY_MOVE) at = 1;
+  if (at < 0) return surface_2d < 0 ? -1 : cell * 26 + surface_2d;
+  int surface;
+  switch (surface_2d) {                         /* src/constants.h:120-145 */
+    case 0: surface = 10 + 2 * at; break;      /* X_MIN -> X_MIN_Z_MIN / X_MIN_Z_MAX */
+    case 3: surface = 11 + 2 * at; break;      /* X_MAX */
+    case 1: surface = 14 + 2 * at; break;      /* Y_MIN */
+    case 4: surface = 15 + 2 * at; break;      /* Y_MAX */
+    case 6: surface = 18 + at; break;          /* X_MIN_Y_MIN */
+    case 8: surface = 20 + at; break;          /* X_MIN_Y_MAX */
+    case 7: surface = 22 + at; break;          /* X_MAX_Y_MIN */
+    case 9: surface = 24 + at; break;          /* X_MAX_Y_MAX */
+    default: surface = 2 + 3 * at;             /* Z_MIN / Z_MAX */
+  }
+  return cell * 26 + surface;
+}
 
 /* TraverseSegments::findMeshIndex (src/TraverseSegments.cpp:926-956) */
 __device__ __forceinline__ int otf_mesh_index(const double* __restrict__ v, int size, double val, int sign) {
@@ -65,7 +95,8 @@ __device__ __forceinline__ int otf_mesh_index(const double* __restrict__ v, int 
   return imin;
 }
 
-/* Walks 3D track t forward and calls emit(length_3d, fsr_3d) for every 3D segment. */
+/* Walks 3D track t forward and calls emit(length_3d, fsr_3d, cmfd_surface_fwd, cmfd_surface_bwd) for every 3D
+ * segment (the surfaces are -1 without CMFD data). */
 template <typename Emit>
 __device__ __forceinline__ void otf_trace(const OtfGeom& g, int64_t t, Emit emit) {
   const int32_t t2 = g.trk_2d[t];
@@ -115,6 +146,16 @@ __device__ __forceinline__ void otf_trace(const OtfGeom& g, int64_t t, Emit emit
       else { d2 = remaining; d3 = seg_dist; zmove = 0; }
       if (d3 > OTF_TINY_MOVE) {
         const int32_t fsr = global ? (int32_t)((int64_t)e * nf + zi) : g.ext_fsr[fsr0 + zi];
+        int cf = -1, cb = -1;
+        if (g.seg2d_surf_fwd != nullptr) {
+          int s2b = -1, s2f = -1;
+          if (__dsub_rn(g.seg2d_len[s], remaining) <= OTF_TINY_MOVE) s2b = g.seg2d_surf_bwd[s];
+          const double next_dist = __ddiv_rn(__dsub_rn(remaining, d2), sin_theta);
+          if (zmove == 0 || next_dist <= OTF_TINY_MOVE) s2f = g.seg2d_surf_fwd[s];
+          const int cell = g.fsr_cmfd_cell[fsr];
+          cb = otf_cmfd_surface(g, cell, z, s2b);
+          cf = otf_cmfd_surface(g, cell, __dadd_rn(z, __dmul_rn(d3, cos_theta)), s2f);
+        }
         double len = d3;
         if (g.fsr_max_sigma_t != nullptr) {
           /* num_cuts = length * max_sigma_t * sin(theta) / max_tau + 1 pieces, all but the last of length
@@ -124,10 +165,13 @@ __device__ __forceinline__ void otf_trace(const OtfGeom& g, int64_t t, Emit emit
           if (t > g.max_tau) {
             const int cuts = (int)__ddiv_rn(t, g.max_tau) + 1;
             const double piece = __ddiv_rn(g.max_tau, ms);
-            for (int c = 0; c < cuts - 1; c++) { emit(piece, fsr); len = __dsub_rn(len, piece); }
+            /* SegmentationKernel::execute (MOCKernel.cpp:237-266): the backward surface stays with the first
+             * piece, the forward surface with the last */
+            for (int c = 0; c < cuts - 1; c++) { emit(piece, fsr, -1, c == 0 ? cb : -1); len = __dsub_rn(len, piece); }
+            if (cuts > 1) cb = -1;
           }
         }
-        emit(len, fsr);
+        emit(len, fsr, cf, cb);
       }
       z = __dadd_rn(z, __dmul_rn(d3, cos_theta));
       remaining = __dsub_rn(remaining, d2);
@@ -142,7 +186,7 @@ __device__ __forceinline__ void otf_trace(const OtfGeom& g, int64_t t, Emit emit
 __global__ void otf_count_kernel(const OtfGeom g, int32_t* __restrict__ count) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < g.n_trk; t += (int64_t)gridDim.x * blockDim.x) {
     int32_t n = 0;
-    otf_trace(g, t, [&](double, int32_t) { n++; });
+    otf_trace(g, t, [&](double, int32_t, int, int) { n++; });
     count[t] = n;
   }
 }
@@ -151,16 +195,19 @@ __global__ void otf_count_kernel(const OtfGeom g, int32_t* __restrict__ count) {
  * seg already skips the front padding) and, when cls_vol_weight is given, tallies the FSR volumes
  * (VolumeKernel, src/MOCKernel.cpp:80-162: azimuthal x polar spacing and weight times length) */
 __global__ void otf_fill_kernel(const OtfGeom g, const int64_t* __restrict__ trk_off, SegRec* __restrict__ seg,
-                                int G, const double* __restrict__ cls_vol_weight, double* __restrict__ volume) {
+                                int G, const double* __restrict__ cls_vol_weight, double* __restrict__ volume,
+                                int2* __restrict__ seg_cmfd) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < g.n_trk; t += (int64_t)gridDim.x * blockDim.x) {
     SegRec* out = seg != nullptr ? seg + trk_off[t] : nullptr;
+    int2* outc = (seg != nullptr && seg_cmfd != nullptr) ? seg_cmfd + trk_off[t] : nullptr;
     const double w = cls_vol_weight != nullptr ? cls_vol_weight[g.trk_class[t]] : 0.0;
-    otf_trace(g, t, [&](double len, int32_t fsr) {
+    otf_trace(g, t, [&](double len, int32_t fsr, int cf, int cb) {
       if (out != nullptr) {
         SegRec r;
         r.len = len; r.base = (uint32_t)fsr * (uint32_t)G; r.spare = 0u;
         *out++ = r;
       }
+      if (outc != nullptr) *outc++ = make_int2(cf, cb);
       if (volume != nullptr) atomicAdd(&volume[fsr], w * len);
     });
   }

@@ -254,6 +254,29 @@ def test_otf_formations_are_traced_on_the_device(formation, monkeypatch):
     assert abs(host["b200_keff"] - dev["b200_keff"]) < 1e-10
 
 
+@pytest.mark.parametrize("args", [
+    ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24", "--zspacing", "0.9",
+     "--cmfd", "2x2x2", "--formation", "otf-stacks"],
+    ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24", "--zspacing", "0.9",
+     "--cmfd", "4x4x3", "--formation", "otf-tracks", "--max-tau", "0.5"],
+    ["--model", "c5g7-2d", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "1.0", "--zspacing", "5", "--axial", "9",
+     "--formation", "otf-stacks", "--cmfd", "51x51x9", "--max-iters", "12", "--threads", "8"],
+    ["--model", "c5g7-2d", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "1.0", "--zspacing", "5", "--axial", "9",
+     "--formation", "otf-stacks", "--cmfd", "51x51x9", "--max-iters", "12", "--threads", "8", "--devices", "0,0"],
+])
+def test_otf_decks_with_cmfd_are_traced_on_the_device(args, monkeypatch):
+    """OTF decks WITH CMFD: the device tracer also produces the CMFD surface of every 3D segment
+    (b200_upload_otf_cmfd: TraverseSegments.cpp:429-457 + Lattice::getLatticeSurfaceOTF restated in otf.cuh), so
+    the current tally needs no host expansion either.  Against CPUSolver + Cmfd, and against the host expansion
+    through the reference's own traversal (B200_HOST_OTF=1)."""
+    dev = run(args + ["--solver", "both"])
+    assert dev["cmfd_on_device"] and dev["b200_iters"] == dev["cpu_iters"]
+    assert dev["dk_pcm"] < 1e-2 and dev["max_rel_flux_err"] < 2e-5
+    monkeypatch.setenv("B200_HOST_OTF", "1")
+    host = run(args + ["--solver", "both"])
+    assert abs(host["b200_keff"] - dev["b200_keff"]) < 5e-10
+
+
 def test_fixed_linear_source_golden_through_the_plugin(tmp_path):
     """B200LSSolver inside the reference's process: setFixedSourceByCell + setFixedSourceMomentsByCell +
     allowNegativeFluxes + computeFlux reproduce tests/test_fixed_linear_source/results_true.dat"""
