@@ -59,6 +59,9 @@ struct Gen {
   /* outputs */
   std::vector<double> seg_length;
   std::vector<int32_t> seg_fsr, seg_mat;
+  /* CMFD mesh = the pin lattice: surface codes of the segment ends, segment::_cmfd_surface_fwd/_bwd, FSR -> cell */
+  std::vector<int8_t> seg_surf_fwd, seg_surf_bwd;
+  std::vector<int32_t> seg_cmfd_fwd, seg_cmfd_bwd, fsr_cell;
   std::vector<int64_t> trk_seg_offset, trk_next_fwd, trk_next_bwd;
   std::vector<int32_t> trk_azim, trk_polar, trk_xy;
   std::vector<uint8_t> trk_flags, trk_bc_fwd, trk_bc_bwd;
@@ -112,7 +115,21 @@ inline int region_of(const TypeInfo& ti, double x, double y, double w, double h,
   return ti.n_fuel_regions + sector_of(x, y, std::max(t.n_sectors_mod, 1));
 }
 
-struct Piece { double len; int32_t fsr, mat; };
+/* cf / cb: surface of the lattice cell (= CMFD cell of a CMFD mesh laid over the pin lattice) the piece ends on in
+ * the forward / backward direction, 0..9 as in src/constants.h:120-129, or -1 (Lattice::getLatticeSurface,
+ * src/Universe.cpp:2100-2230, restricted to x / y) */
+struct Piece { double len; int32_t fsr, mat; int32_t cell; int8_t cf, cb; };
+
+inline int8_t lattice_surface_2d(double x, double y, double px, double py) {
+  const double tol = 1e-10;
+  const bool min_x = fabs(x + 0.5 * px) < tol, max_x = fabs(x - 0.5 * px) < tol;
+  const bool min_y = fabs(y + 0.5 * py) < tol, max_y = fabs(y - 0.5 * py) < tol;
+  if (min_x) return min_y ? 6 : (max_y ? 8 : 0);
+  if (max_x) return min_y ? 7 : (max_y ? 9 : 3);
+  if (min_y) return 1;
+  if (max_y) return 4;
+  return -1;
+}
 
 /* Trace one track from (x0, y0) along (dx, dy) for total length L. */
 void trace(const Gen& g, double x0, double y0, double dx, double dy, double L,
@@ -189,6 +206,7 @@ void trace(const Gen& g, double x0, double y0, double dx, double dy, double L,
     }
     std::sort(cuts.begin(), cuts.end());
     const int64_t base = g.fsr_base[cell];
+    const size_t first_piece = out.size();
     for (size_t c = 0; c + 1 < cuts.size(); c++) {
       const double sa = cuts[c], sb = cuts[c + 1];
       if (sb - sa <= tiny) continue;
@@ -199,8 +217,12 @@ void trace(const Gen& g, double x0, double y0, double dx, double dy, double L,
       if (!out.empty() && out.back().fsr == fsr && ti.t.kind == KIND_PIN && c > 0) {
         out.back().len += sb - sa;       /* a candidate cut that was no region boundary */
       } else {
-        out.push_back({sb - sa, fsr, mat});
+        out.push_back({sb - sa, fsr, mat, (int32_t)cell, -1, -1});
       }
+    }
+    if (out.size() > first_piece) {
+      out[first_piece].cb = lattice_surface_2d(ox + ta * dx, oy + ta * dy, g.px, g.py);
+      out.back().cf = lattice_surface_2d(ox + tb * dx, oy + tb * dy, g.px, g.py);
     }
   }
 }
@@ -393,11 +415,16 @@ int build(Gen& g, int polar_quad) {
   for (int64_t t = 0; t < nt; t++) g.trk_seg_offset[t + 1] = g.trk_seg_offset[t] + (int64_t)per_track[t].size();
   const int64_t ns = g.trk_seg_offset[nt];
   g.seg_length.resize(ns); g.seg_fsr.resize(ns); g.seg_mat.resize(ns);
+  g.seg_surf_fwd.resize(ns); g.seg_surf_bwd.resize(ns); g.seg_cmfd_fwd.resize(ns); g.seg_cmfd_bwd.resize(ns);
 #pragma omp parallel for schedule(dynamic, 256)
   for (int64_t t = 0; t < nt; t++) {
     int64_t o = g.trk_seg_offset[t];
     for (const Piece& p : per_track[t]) {
-      g.seg_length[o] = p.len; g.seg_fsr[o] = p.fsr; g.seg_mat[o] = p.mat; o++;
+      g.seg_length[o] = p.len; g.seg_fsr[o] = p.fsr; g.seg_mat[o] = p.mat;
+      g.seg_surf_fwd[o] = p.cf; g.seg_surf_bwd[o] = p.cb;
+      g.seg_cmfd_fwd[o] = p.cf < 0 ? -1 : p.cell * 26 + p.cf;      /* segment::_cmfd_surface_fwd, src/Track.h:42-46 */
+      g.seg_cmfd_bwd[o] = p.cb < 0 ? -1 : p.cell * 26 + p.cb;
+      o++;
     }
     std::vector<Piece>().swap(per_track[t]);
   }
@@ -405,6 +432,9 @@ int build(Gen& g, int polar_quad) {
   /* ---- FSR volumes (VolumeKernel, src/MOCKernel.cpp:145-162: w_a * spacing_a * L) and materials ---- */
   g.fsr_volume.assign(g.n_fsrs, 0.);
   g.fsr_mat.assign(g.n_fsrs, -1);
+  g.fsr_cell.resize(g.n_fsrs);
+  for (int64_t c = 0; c < n_cells; c++)
+    for (int64_t f = g.fsr_base[c]; f < g.fsr_base[c + 1]; f++) g.fsr_cell[f] = (int32_t)c;
   for (int64_t t = 0; t < nt; t++) {
     const int a = g.trk_azim[t];
     const double w = azim_weight[a] * azim_spacing[a];
@@ -1057,6 +1087,7 @@ int64_t b200_trackgen_get(b200_trackgen* h, const char* name, void* dst) {
   OUT(trk_azim) OUT(trk_polar) OUT(trk_xy) OUT(trk_flags) OUT(trk_bc_fwd) OUT(trk_bc_bwd) OUT(trk_phi)
   OUT(trk_theta) OUT(trk_start) OUT(trk_end) OUT(quad_weight) OUT(quad_sin_theta) OUT(fsr_volume) OUT(fsr_mat)
   OUT(quad_azim_spacing) OUT(quad_azim_weight) OUT(quad_polar_spacing) OUT(quad_polar_weight)
+  OUT(seg_surf_fwd) OUT(seg_surf_bwd) OUT(seg_cmfd_fwd) OUT(seg_cmfd_bwd) OUT(fsr_cell)
 #undef OUT
   return -1;
 }

@@ -39,6 +39,43 @@ class _DeviceArray:
                                          "version": 3, "strides": None}
 
 
+class CmfdMesh:
+    """What `Cmfd` describes in the reference (src/Cmfd.h:430-500), for hosts without OpenMOC objects: the lattice
+    (`setLatticeStructure` / `setWidths`), the boundaries, the group structure (`setGroupStructure`: lists of
+    1-based MOC groups, None = one CMFD group per MOC group), the options with the reference's defaults, and the
+    CMFD cell of every FSR (`Geometry::getCmfdCell`).  The tracks must carry the CMFD surfaces of their segments
+    (`seg_cmfd_fwd/bwd`, segment::_cmfd_surface_fwd/_bwd; on-the-fly 3D tracks: `seg2d_surf_fwd/bwd` + z_planes).
+    Centroid (k-nearest) updating needs stencils only a Geometry can make: not available here."""
+
+    def __init__(self, num_x, num_y, num_z, widths_x, widths_y, widths_z, boundaries, fsr_cell, group_structure=None,
+                 z_planes=None, sor_factor=1.5, relaxation_factor=0.7, flux_limiting=True, num_unbounded_iterations=0,
+                 linalg_tolerance=1e-15):
+        self.num_x, self.num_y, self.num_z = int(num_x), int(num_y), int(num_z)
+        self.widths_x, self.widths_y, self.widths_z = (np.ascontiguousarray(w, dtype="f8") for w in (widths_x, widths_y, widths_z))
+        self.boundaries = tuple(int(b) for b in boundaries)
+        self.fsr_cell = np.ascontiguousarray(fsr_cell, dtype="i4")
+        self.group_structure = group_structure
+        self.z_planes = None if z_planes is None else np.ascontiguousarray(z_planes, dtype="f8")
+        self.sor_factor, self.relaxation_factor = float(sor_factor), float(relaxation_factor)
+        self.flux_limiting, self.num_unbounded_iterations = bool(flux_limiting), int(num_unbounded_iterations)
+        self.linalg_tolerance = float(linalg_tolerance)
+
+    @property
+    def num_cells(self):
+        return self.num_x * self.num_y * self.num_z
+
+    def group_indices(self, num_groups):
+        """Cmfd::_group_indices (Cmfd.cpp:1943-1990): first MOC group (0-based) of every CMFD group, and the MOC -> CMFD map"""
+        gs = self.group_structure or [[g + 1] for g in range(num_groups)]
+        flat = [g for grp in gs for g in grp]
+        if flat != list(range(1, num_groups + 1)):
+            raise B200Error("the CMFD group structure must list the MOC groups 1..%d in order" % num_groups)
+        idx = np.zeros(len(gs) + 1, dtype="i4")
+        idx[1:] = np.cumsum([len(grp) for grp in gs])
+        moc_to_cmfd = np.repeat(np.arange(len(gs), dtype="i4"), [len(grp) for grp in gs])
+        return idx, moc_to_cmfd
+
+
 class B200Solver:
     """B200 implementation of the OpenMOC source-iteration solver (flat source).
 
@@ -61,6 +98,10 @@ class B200Solver:
                                the library shards the tracks by chain and sums the tallies with its own
                                peer-memory all-reduce.  A device may repeat (several shards on one GPU).
     global_tracks : optional   the whole problem's tracks when `tracks` already is one rank's shard
+    cmfd : optional            CmfdMesh: CMFD acceleration on the device (b200_cmfd_*): the sweep tallies the surface
+                               currents, every source iteration of computeEigenvalue / iterate ends with
+                               Cmfd::computeKeff's work (collapse, diffusion eigenvalue solve, prolongation).  One
+                               process (one GPU, or devices=[...]).
     linear_source : bool       CPULSSolver physics (src/CPULSSolver.cpp): needs a track file dumped
                                after a linear-source initialisation (centroid-relative segment
                                starting points, quadrature factors); the pre-pass tables come from
@@ -70,8 +111,9 @@ class B200Solver:
     def __init__(self, tracks: FlatTracks, device: int = 0, precision: int = PRECISION_DOUBLE,
                  process_group=None, use_distributed: Optional[bool] = None, deterministic: bool = False,
                  partition: str = "pair", linear_source: bool = False,
-                 global_tracks: Optional[FlatTracks] = None, devices=None):
+                 global_tracks: Optional[FlatTracks] = None, devices=None, cmfd: Optional[CmfdMesh] = None):
         self._lib = capi.load()
+        self._cmfd = cmfd
         self._h = C.c_void_p()
         # global_tracks: the full track set when `tracks` already is one rank's shard (the FSR volumes of
         # on-the-fly 3D tracks and the linear-source pre-pass are sums over ALL tracks)
@@ -100,6 +142,9 @@ class B200Solver:
             # the pre-pass tables are sums over ALL tracks (replicated); starting points and directions
             # follow this rank's shard below
             lin_exp, src_const, self.num_flat_fsrs = linear_expansion_tables_device(global_tracks or tracks, device)
+        if self._cmfd is not None and self._world > 1:
+            raise B200Error("CMFD with one process per GPU is not available in this build: use devices=[...] "
+                            "(one process driving all GPUs; the CMFD solve then runs replicated on every GPU)")
         if self._world > 1:
             from .partition import partition_by_azim_pair, partition_by_chain, partition_by_track
             if partition == "chain":
@@ -173,10 +218,50 @@ class B200Solver:
         check(L.b200_upload_materials(h, *[_ptr(x) for x in mats]))
         if self._ls_tables is not None:
             check(L.b200_upload_linear_source(h, *[_ptr(x) for x in self._ls_tables]))
+        if self._cmfd is not None and not self._otf:
+            if a.get("seg_cmfd_fwd", np.zeros(0)).size != ft.n_segments:
+                raise B200Error("CMFD needs the CMFD surfaces of the segments (seg_cmfd_fwd / seg_cmfd_bwd) in the tracks")
+            cf, cb = c("seg_cmfd_fwd", "i4"), c("seg_cmfd_bwd", "i4")
+            check(L.b200_upload_cmfd_surfaces(h, _ptr(cf), _ptr(cb)))
         check(L.b200_finalize(h))
         ns = C.c_int64()
         check(L.b200_get_num_segments(h, C.byref(ns)))
         self.num_segments = int(ns.value)
+        if self._cmfd is not None:
+            self._configure_cmfd(ft)
+
+    def _configure_cmfd(self, ft: FlatTracks) -> None:
+        """Solver::initializeCmfd + Cmfd::initialize for the device CMFD (b200_set_cmfd_groups, b200_cmfd_configure)"""
+        from .capi import CmfdConfig
+        m, L, h = self._cmfd, self._lib, self._h
+        if m.fsr_cell.size != ft.n_fsrs:
+            raise B200Error("CmfdMesh.fsr_cell has %d entries for %d FSRs" % (m.fsr_cell.size, ft.n_fsrs))
+        idx, moc_to_cmfd = m.group_indices(ft.num_groups)
+        check(L.b200_set_cmfd_groups(h, _ptr(moc_to_cmfd), idx.size - 1, m.num_cells))
+        order = np.argsort(m.fsr_cell, kind="stable").astype("i4")          # FSRs of every cell, ascending ids
+        off = np.zeros(m.num_cells + 1, dtype="i8")
+        off[1:] = np.cumsum(np.bincount(m.fsr_cell, minlength=m.num_cells))
+        A2, P = ft.num_azim // 2, ft.num_polar
+        g = self._global_tracks.arrays
+        cfg = CmfdConfig(num_x=m.num_x, num_y=m.num_y, num_z=m.num_z, num_cmfd_groups=idx.size - 1,
+                         boundaries=(C.c_int32 * 6)(*m.boundaries), linear_source=int(self._linear),
+                         flux_limiting=int(m.flux_limiting), centroid_update=0, axial_interpolation=0,
+                         num_unbounded_iterations=m.num_unbounded_iterations, num_azim_2=A2, num_polar_2=P // 2,
+                         sor_factor=m.sor_factor, relaxation_factor=m.relaxation_factor,
+                         linalg_tolerance=m.linalg_tolerance)
+        # Quadrature::getAzimWeight / getSinTheta / getPolarWeight over the first half of the polar angles
+        wa = np.ascontiguousarray(g["quad_azim_weight"], dtype="f8")
+        st = np.ascontiguousarray(np.asarray(g["quad_sin_theta"]).reshape(A2, P)[:, :P // 2], dtype="f8")
+        wp = np.ascontiguousarray(np.asarray(g["quad_polar_weight"]).reshape(A2, P)[:, :P // 2], dtype="f8")
+        keep = [m.widths_x, m.widths_y, m.widths_z, idx, off, order, wa, st, wp]
+        check(L.b200_cmfd_configure(h, C.byref(cfg), *[_ptr(x) for x in keep]))
+
+    def cmfdSolve(self, moc_iteration: int, source_threshold: float = -1.0):
+        """One Cmfd::computeKeff on the device (for hosts driving the iteration step by step); returns (k_eff, stats)"""
+        from .capi import CmfdStats
+        k, st = C.c_double(), CmfdStats()
+        check(self._lib.b200_cmfd_solve(self._h, int(moc_iteration), float(source_threshold), C.byref(k), C.byref(st)))
+        return k.value, st
 
     def _upload_otf(self, ft: FlatTracks) -> None:
         """Axial on-the-fly track set (synth.make_tracks_3d(expand=False), or what b200_flatten
@@ -204,6 +289,12 @@ class B200Solver:
         mine = [c(a, "trk_2d", "i4"), c(a, "trk_l0", "f8"), z0(a), c(a, "trk_azim", "i4"), c(a, "trk_polar", "i4"),
                 c(a, "trk_next_fwd", "i8"), c(a, "trk_next_bwd", "i8"), c(a, "trk_flags", "u1"),
                 c(a, "trk_bc_fwd", "u1"), c(a, "trk_bc_bwd", "u1")]
+        if self._cmfd is not None:
+            m = self._cmfd
+            if m.z_planes is None or "seg2d_surf_fwd" not in g:
+                raise B200Error("CMFD on axially traced tracks needs seg2d_surf_fwd / seg2d_surf_bwd and CmfdMesh.z_planes")
+            sf, sb = c(g, "seg2d_surf_fwd", "i1"), c(g, "seg2d_surf_bwd", "i1")
+            check(L.b200_upload_otf_cmfd(h, _ptr(sf), _ptr(sb), _ptr(m.fsr_cell), m.num_x, m.num_y, m.num_z, _ptr(m.z_planes)))
         ns = C.c_int64()
         check(L.b200_upload_tracks_otf(h, *[_ptr(x) for x in mine], C.byref(ns)))
         self.num_segments = int(ns.value)        # 0 on a multi-device handle until b200_finalize

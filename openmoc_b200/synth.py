@@ -162,6 +162,8 @@ def _renumber_by_discovery(arrays: Dict[str, np.ndarray]) -> None:
     arrays["seg_fsr"] = new_id[seg].astype("i4")
     arrays["fsr_volume"] = arrays["fsr_volume"][uniq[order]]
     arrays["fsr_mat"] = arrays["fsr_mat"][uniq[order]]
+    if "fsr_cell" in arrays:
+        arrays["fsr_cell"] = arrays["fsr_cell"][uniq[order]]
 
 
 def materials_70g(names: List[str]) -> Dict[str, np.ndarray]:
@@ -221,7 +223,7 @@ def make_tracks(model: str, num_azim: int = 4, spacing: float = 0.1, num_polar: 
                   "trk_phi": "f8", "trk_theta": "f8", "trk_start": "f8", "quad_weight": "f8",
                   "quad_sin_theta": "f8", "fsr_volume": "f8", "fsr_mat": "i4",
                   "quad_azim_spacing": "f8", "quad_azim_weight": "f8", "quad_polar_spacing": "f8",
-                  "quad_polar_weight": "f8"}
+                  "quad_polar_weight": "f8", "seg_cmfd_fwd": "i4", "seg_cmfd_bwd": "i4", "fsr_cell": "i4"}
         arrays = {}
         for k, dt in dtypes.items():
             n = L.b200_trackgen_get(h, k.encode(), None)
@@ -291,7 +293,8 @@ _DT3 = {"seg_length": "f8", "seg_fsr": "i4", "seg_mat": "i4", "trk_seg_offset": 
         "quad_weight": "f8", "quad_sin_theta": "f8", "fsr_volume": "f8", "fsr_mat": "i4",
         "quad_azim_spacing": "f8", "quad_azim_weight": "f8", "quad_polar_spacing": "f8", "quad_polar_weight": "f8",
         "seg2d_length": "f8", "seg2d_fsr": "i4", "seg2d_mat": "i4", "trk2d_seg_offset": "i8",
-        "trk2d_start": "f8", "trk2d_phi": "f8", "fsr2d_mat": "i4"}
+        "trk2d_start": "f8", "trk2d_phi": "f8", "fsr2d_mat": "i4",
+        "seg2d_surf_fwd": "i1", "seg2d_surf_bwd": "i1", "fsr2d_cell": "i4"}
 
 
 def make_tracks_3d(model: str, num_azim: int = 4, spacing: float = 0.1, num_polar: int = 2,
@@ -342,3 +345,36 @@ def make_tracks_3d(model: str, num_azim: int = 4, spacing: float = 0.1, num_pola
                     n_fsrs=int(arrays["fsr_volume"].size), n_materials=len(names), arrays=arrays)
     ft.n_axial = int(n_axial)
     return ft
+
+
+# ----------------------------------------------------------------------- CMFD mesh of a synthetic deck
+def cmfd_mesh(ft: FlatTracks, model: str, num_z: int = 1, group_structure=None, **options):
+    """A CMFD mesh laid over the pin lattice of the named deck (51 x 51 for C5G7, what
+    sample-input/benchmarks/c5g7/c5g7-2d.py:51-56 and profile/models/c5g7/c5g7-3d-cmfd.cpp:537-556 use), `num_z`
+    equal cells axially for the 3D decks (must divide the number of axial layers).  The generator has marked the
+    surface of the lattice cell every segment ends on (`seg_cmfd_fwd/bwd`, `seg2d_surf_fwd/bwd`) and the cell of every
+    FSR.  Returns the openmoc_b200.solver.CmfdMesh to hand to B200Solver(tracks, cmfd=...)."""
+    from .solver import CmfdMesh
+    nx, ny, px, py, xmin, ymin, _, _, bcs, _ = _model(model)
+    a = ft.arrays
+    if ft.solve_3d and "fsr2d_cell" in a:
+        zmin, zmax, bc_zmin, bc_zmax = AXIAL[model]
+        n_axial = int(getattr(ft, "n_axial", 1))
+        if n_axial % num_z:
+            raise ValueError("num_z must divide the number of axial layers")
+        cell2d = a["fsr2d_cell"].astype(np.int64)
+        layer = np.arange(n_axial, dtype=np.int64)
+        # 3D FSR id = 2D FSR id * n_axial + layer (trackgen.cpp); CMFD cell = (z cell * ny + y) * nx + x
+        fsr_cell = (cell2d[:, None] + (layer[None, :] * num_z // n_axial) * (nx * ny)).ravel()
+        wz = np.full(num_z, (zmax - zmin) / num_z)
+        z_planes = zmin + np.arange(num_z + 1) * (zmax - zmin) / num_z
+        bz = (bc_zmin, bc_zmax)
+    else:
+        if num_z != 1:
+            raise ValueError("a 2D deck has one axial CMFD cell")
+        fsr_cell, wz, z_planes, bz = a["fsr_cell"], np.ones(1), None, (REFLECTIVE, REFLECTIVE)   # Cmfd.cpp:3860-3869
+    # boundaries in face order X_MIN, Y_MIN, Z_MIN, X_MAX, Y_MAX, Z_MAX (src/constants.h:120-125); bcs = (xmin, xmax, ymin, ymax)
+    boundaries = (bcs[0], bcs[2], bz[0], bcs[1], bcs[3], bz[1])
+    return CmfdMesh(num_x=nx, num_y=ny, num_z=num_z, widths_x=np.full(nx, px), widths_y=np.full(ny, py), widths_z=wz,
+                    boundaries=boundaries, fsr_cell=np.ascontiguousarray(fsr_cell, dtype="i4"),
+                    group_structure=group_structure, z_planes=z_planes, **options)
