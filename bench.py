@@ -37,7 +37,9 @@ WORKLOADS = {
     # 2D decks: TY polar quadrature (what the reference's decks really run)
     "c5g7-2d": dict(dims=2, model="c5g7-2d", azim=128, spacing=0.01, polar=6,
                     desc="configs[2]: 2D C5G7 quarter core, 128 azim, 0.01 cm",
-                    cpu_sample=dict(azim=128, spacing=0.05)),
+                    cpu_sample=dict(azim=128, spacing=0.05),
+                    # CMFD as in sample-input/benchmarks/c5g7/c5g7-2d.py:51-56 (51 x 51, two groups, SOR 1.5)
+                    cmfd=dict(num_z=1, sample=dict(azim=32, spacing=0.1))),
     "simple-lattice": dict(dims=2, model="simple-lattice", azim=128, spacing=0.01, polar=6,
                            desc="configs[1]: simple-lattice 2D, 128 azim, 0.01 cm",
                            cpu_sample=dict(azim=128, spacing=0.01)),
@@ -49,8 +51,11 @@ WORKLOADS = {
                     quad="equal-angle",
                     desc="configs[4]: 3D C5G7 extruded core, 16 azim, 0.1 cm, 8 polar (equal angle), 1.0 cm axial "
                          "spacing, 135 axial layers, on-the-fly axial ray tracing on the device",
-                    cpu_sample=dict(azim=4, spacing=0.5, polar=4, zspacing=4.0, n_axial=9)),
+                    cpu_sample=dict(azim=4, spacing=0.5, polar=4, zspacing=4.0, n_axial=9),
+                    # CMFD as in profile/models/c5g7/c5g7-3d-cmfd.cpp:537-556 (51 x 51 x 9*axial_refines = 135)
+                    cmfd=dict(num_z=135, sample=dict(azim=4, spacing=0.8, polar=4, zspacing=6.0, n_axial=9, num_z=9))),
 }
+CMFD_GROUPS = [[1, 2, 3], [4, 5, 6, 7]]
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md
 # FP64-pipe instructions per integration in the flat sweep kernels (cuobjdump of libb200moc.so,
 # profiles/r02_sass.md): 11 Horner DFMA + 4 for the quotient + tau, L*q, delta-psi, psi update,
@@ -412,9 +417,98 @@ def measure(name, args, env, primary):
     solver.close()
     del solver
     torch.cuda.empty_cache()
+    if world == 1 and not args.no_cmfd:
+        res["cmfd"] = measure_cmfd(name, ft, args, local_rank, precision)
     if world > 1 and not args.no_group:
         res["group"] = measure_group(name, ft, args, env, steps, warmup, W_sweep, precision)
     return res
+
+
+def measure_cmfd(name, ft, args, device, precision, devices=None, max_iters=100):
+    """Time to solution of the CMFD-accelerated eigenvalue solve of the workload's deck (tolerance 1e-5, the
+    reference's default): the whole source iteration - sweep with current tally, closure, CMFD collapse / diffusion
+    eigenvalue solve / prolongation (b200_cmfd_*), normalisation, residual, stopping rule - runs on the device."""
+    import torch
+    from openmoc_b200.solver import B200Solver
+    from openmoc_b200.synth import cmfd_mesh
+    wl = WORKLOADS[name]
+    if "cmfd" not in wl:
+        return None
+    try:
+        mesh = cmfd_mesh(ft, wl["model"], num_z=wl["cmfd"]["num_z"], group_structure=CMFD_GROUPS)
+        t0 = time.perf_counter()
+        s = B200Solver(ft, device=device, precision=precision, devices=devices, cmfd=mesh)
+        t_setup = time.perf_counter() - t0
+        s.setConvergenceThreshold(1e-5)
+        s.resetSweepStats()
+        t0 = time.perf_counter()
+        s.computeEigenvalue(max_iters)
+        s.synchronize()
+        dt = time.perf_counter() - t0
+        iters = s.getNumIterations()
+        sweep_ms, n_sweeps, _ = s.getSweepStats()
+        W = 2.0 * ft.fluxes_per_track * s.num_segments
+        out = {"mesh": "%d x %d x %d CMFD cells, %d groups, SOR %.1f" % (mesh.num_x, mesh.num_y, mesh.num_z, len(CMFD_GROUPS), mesh.sor_factor),
+               "iterations_to_1e-5": iters, "converged": iters < max_iters, "k_eff": s.getKeff(),
+               "time_to_solution_s": dt, "ms_per_iteration": 1e3 * dt / max(iters, 1),
+               "sweep_ms_per_iteration": sweep_ms / max(n_sweeps, 1),
+               "cmfd_and_fsr_ms_per_iteration": 1e3 * dt / max(iters, 1) - sweep_ms / max(n_sweeps, 1),
+               "integrations_per_s_with_cmfd": W * iters / dt, "setup_s": round(t_setup, 2),
+               "timed": "host clock around b200_compute_eigenvalue (fused device loop, polled every 8 iterations)"}
+        s.close()
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:                     # the CMFD block must not lose the main measurement
+        return {"error": repr(e)}
+
+
+def cmfd_parity(workload, env, threads):
+    """CMFD-accelerated solve of a bounded sample of the deck: the CUDA path against the reference's CPUSolver + Cmfd
+    (oracle/_ref/ref_driver --cmfd, k-nearest updating off: its stencils need a Geometry), both to convergence."""
+    import numpy as np
+    from openmoc_b200.solver import B200Solver
+    from openmoc_b200.synth import make_tracks, make_tracks_3d, cmfd_mesh
+    wl = WORKLOADS[workload]
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if "cmfd" not in wl or not os.path.exists(driver):
+        return None
+    sm = wl["cmfd"]["sample"]
+    nz = sm.get("num_z", 1)
+    max_iters = 60 if wl["dims"] == 2 else 20
+    with tempfile.TemporaryDirectory() as td:
+        js = os.path.join(td, "ref.json")
+        cmd = [driver] + _driver_args(wl, sm) + ["--cmfd", "51x51" + ("x%d" % nz if wl["dims"] == 3 else ""), "--no-knearest",
+                                                 "--max-iters", str(max_iters), "--threads", str(threads), "--quiet",
+                                                 "--json", js, "--solver", "cpu"]
+        if wl["dims"] == 3:
+            cmd.append("--no-fluxes")
+        t0 = time.perf_counter()
+        subprocess.run(cmd, check=True, env=dict(os.environ, OMP_NUM_THREADS=str(threads)), stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, cwd=td)
+        wall = time.perf_counter() - t0
+        ref = json.load(open(js))
+    if wl["dims"] == 2:
+        ft = make_tracks(wl["model"], num_azim=sm["azim"], spacing=sm["spacing"], num_polar=wl["polar"])
+    else:
+        ft = make_tracks_3d(wl["model"], num_azim=sm["azim"], spacing=sm["spacing"], num_polar=sm["polar"],
+                            z_spacing=sm["zspacing"], n_axial=sm["n_axial"], polar_quad=_quad(wl), expand=False)
+    s = B200Solver(ft, device=env.local_rank, cmfd=cmfd_mesh(ft, wl["model"], num_z=nz, group_structure=CMFD_GROUPS))
+    if wl["dims"] == 3:
+        s.setConvergenceThreshold(1e-30)
+    t0 = time.perf_counter()
+    s.computeEigenvalue(max_iters)
+    s.synchronize()
+    dt = time.perf_counter() - t0
+    out = {"deck": sample_text(wl, sm) + ", CMFD 51 x 51" + (" x %d" % nz if wl["dims"] == 3 else "") + ", 2 groups",
+           "iterations_b200": s.getNumIterations(), "iterations_reference": ref["iterations"],
+           "k_eff_b200": s.getKeff(), "k_eff_reference": ref["keff"], "dk_pcm": abs(s.getKeff() - ref["keff"]) * 1e5,
+           "solve_s_b200": dt, "solve_s_reference": ref["total_time_s"], "reference_cores": threads,
+           "reference_wall_incl_ray_tracing_s": round(wall, 1), "tolerance": "north star: 1 pcm, 1e-4"}
+    if wl["dims"] == 2 and ref.get("fluxes") and len(ref["fluxes"]) == ft.n_fsrs * ft.num_groups:
+        phi, rp = s.getFluxes(), np.asarray(ref["fluxes"])
+        out["max_rel_phi_err"] = float(np.max(np.abs(phi - rp) / np.maximum(np.abs(rp), 1e-300)))
+    s.close()
+    return out
 
 
 def measure_group(name, ft, args, env, steps, warmup, W_sweep, precision):
@@ -457,6 +551,9 @@ def measure_group(name, ft, args, env, steps, warmup, W_sweep, precision):
                    "k_eff_after_timed_steps": s.getKeff(), "setup_s": round(t_setup, 2),
                    "collective": "library's own two-shot all-reduce over peer memory (csrc/group.cuh)"}
             s.close()
+            torch.cuda.empty_cache()
+            if not args.no_cmfd:
+                out["cmfd"] = measure_cmfd(name, ft, args, 0, precision, devices=list(range(world)))
         except Exception as e:
             out = {"error": repr(e)}
         torch.cuda.empty_cache()
@@ -517,6 +614,7 @@ def main():
     ap.add_argument("--partition-3d", default="block", choices=["chain", "track", "block"])
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--no-group", action="store_true", help="skip the one-process all-GPU measurement at N > 1")
+    ap.add_argument("--no-cmfd", action="store_true", help="skip the CMFD-accelerated time-to-solution blocks")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -564,6 +662,11 @@ def main():
                     block["parity"] = parity_check(w, cb, env)
                 except Exception as e:                     # a failed check must not lose the measurement
                     block["parity"] = {"error": repr(e)}
+                if not args.no_cmfd:
+                    try:
+                        block["parity_cmfd"] = cmfd_parity(w, env, ncpu)
+                    except Exception as e:
+                        block["parity_cmfd"] = {"error": repr(e)}
                 if w == args.workload:
                     cpu_baseline = block
                 else:
@@ -584,6 +687,7 @@ def main():
             "gpu_launches": main_res["gpu_launches"],
             "clocks": clocks,
             "group": main_res.get("group"),
+            "cmfd": main_res.get("cmfd"),
             "workloads": others,
         }
         print(json.dumps(line))
