@@ -33,6 +33,9 @@ constexpr int CMFD_NF = 6;                  /* NUM_FACES */
 constexpr int CMFD_NFE = 18;                /* faces + edges */
 constexpr int CMFD_BLOCK_THREADS = 512;     /* one-CTA solve: 128 registers per thread */
 constexpr int CMFD_GRID_THREADS = 256;      /* cooperative solve */
+#ifndef CMFD_GRID_MIN_BLOCKS
+#define CMFD_GRID_MIN_BLOCKS 2              /* resident CTAs per SM the cooperative kernel is compiled for (register cap) */
+#endif
 constexpr double CMFD_EPS = 1.0e-12;        /* FLT_EPSILON of src/constants.h:12 (NOT the C one) */
 constexpr double CMFD_FLUX_EPS = 1.0e-25;   /* FLUX_EPSILON, src/constants.h:15 */
 constexpr double CMFD_ZERO_SIGMA_T = 1.0e-6;
@@ -469,7 +472,7 @@ __device__ __forceinline__ void cmfd_sor_cell(const CmfdArgs& a, double* X, int6
 }
 
 template <int MODE, int NCG>
-__global__ void __launch_bounds__(MODE == 0 ? CMFD_BLOCK_THREADS : CMFD_GRID_THREADS)
+__global__ void __launch_bounds__(MODE == 0 ? CMFD_BLOCK_THREADS : CMFD_GRID_THREADS, MODE == 0 ? 1 : CMFD_GRID_MIN_BLOCKS)
 cmfd_eigen_kernel(CmfdArgs a, double source_thresh) {
   extern __shared__ double cmfd_smem[];
   __shared__ double sh[34];
