@@ -700,7 +700,7 @@ cmfd_eigen_cluster_kernel(CmfdArgs a, CmfdClusterArgs ca, double source_thresh) 
     __syncthreads();
     if (threadIdx.x == 0) {
       double t = 0.;
-      for (int j = 0; j < CMFD_CLUSTER_THREADS / 32; j++) t += sh[j];
+      for (int j = 0; j < (int)(blockDim.x >> 5); j++) t += sh[j];
       sh[34 + slot] = t;
     }
   };
@@ -719,7 +719,7 @@ cmfd_eigen_cluster_kernel(CmfdArgs a, CmfdClusterArgs ca, double source_thresh) 
   auto reduce = [&](double v) { reduce_put(v); cluster.sync(); return reduce_get(); };
 
 #define CMFD_MY_CELLS(...)                                                         \
-  for (int ls = threadIdx.x; ls < mine; ls += CMFD_CLUSTER_THREADS)                \
+  for (int ls = threadIdx.x; ls < mine; ls += (int)blockDim.x)                \
     for (int colour = 0; colour < 2; colour++) {                                   \
       const int cell = cmfd_slot_cell32(a, base + ls, colour, hx);                 \
       if (cell < 0) continue;                                                      \
@@ -781,7 +781,7 @@ cmfd_eigen_cluster_kernel(CmfdArgs a, CmfdClusterArgs ca, double source_thresh) 
       const double* old_src = liter >= 25 ? SNv : SOv;
       double part = 0.;
       for (int colour = 0; colour < 2; colour++) {
-        for (int ls = threadIdx.x; ls < mine; ls += CMFD_CLUSTER_THREADS) {
+        for (int ls = threadIdx.x; ls < mine; ls += (int)blockDim.x) {
           const int cell = __ldg(a.slot_cell + (int64_t)colour * n_slots + base + ls);
           if (cell < 0) continue;
           const int li = ls * 2 + colour;

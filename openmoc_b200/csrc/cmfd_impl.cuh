@@ -23,7 +23,7 @@ struct b200_cmfd {
   DevBuf<int> ci;
   int eigen_mode = 0, eigen_blocks = 1;     /* 0 one CTA, 1 cooperative grid, 2 one thread-block cluster */
   size_t eigen_smem = 0;
-  int cluster_slots = 0, cluster_all_smem = 0;
+  int cluster_slots = 0, cluster_all_smem = 0, cluster_threads = CMFD_CLUSTER_THREADS;
   DevBuf<int32_t> nb_loc;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   void release() {
@@ -340,6 +340,9 @@ extern "C" int b200_cmfd_configure(b200_solver* s, const b200_cmfd_config* cfg, 
       int n_clusters = 0;
       if (cudaOccupancyMaxActiveClusters(&n_clusters, fn, &lc) != cudaSuccess || n_clusters < 1) { cudaGetLastError(); if (C == 1) break; continue; }
       c->eigen_blocks = C; c->eigen_smem = smem; c->cluster_slots = S; c->cluster_all_smem = all;
+      /* no more warps than cells of a colour: idle warps only lengthen the barriers */
+      c->cluster_threads = std::max(64, std::min(CMFD_CLUSTER_THREADS, (S + 31) / 32 * 32));
+      if (const char* e = getenv("B200_CMFD_CLUSTER_THREADS")) c->cluster_threads = std::max(32, std::min(CMFD_CLUSTER_THREADS, atoi(e) / 32 * 32));
       placed = true;
       break;
     }
@@ -514,7 +517,7 @@ static int enqueue_cmfd(b200_solver* s, int moc_iteration, double source_thresho
     CmfdClusterArgs ca;
     ca.slots_per_cta = c->cluster_slots; ca.all_smem = c->cluster_all_smem; ca.nb_loc = c->nb_loc.p;
     cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(c->eigen_blocks); lc.blockDim = dim3(CMFD_CLUSTER_THREADS); lc.dynamicSmemBytes = c->eigen_smem;
+    lc.gridDim = dim3(c->eigen_blocks); lc.blockDim = dim3(c->cluster_threads); lc.dynamicSmemBytes = c->eigen_smem;
     lc.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
