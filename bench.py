@@ -552,7 +552,7 @@ def measure_group(name, ft, args, env, steps, warmup, W_sweep, precision):
                    "collective": "library's own two-shot all-reduce over peer memory (csrc/group.cuh)"}
             s.close()
             torch.cuda.empty_cache()
-            if not args.no_cmfd:
+            if args.group_cmfd and not args.no_cmfd:
                 out["cmfd"] = measure_cmfd(name, ft, args, 0, precision, devices=list(range(world)))
         except Exception as e:
             out = {"error": repr(e)}
@@ -615,6 +615,9 @@ def main():
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--no-group", action="store_true", help="skip the one-process all-GPU measurement at N > 1")
     ap.add_argument("--no-cmfd", action="store_true", help="skip the CMFD-accelerated time-to-solution blocks")
+    ap.add_argument("--group-cmfd", action="store_true",
+                    help="N > 1: also time the CMFD-accelerated solve on the one-process all-GPU group (the CMFD solve "
+                         "runs replicated on every GPU)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -150,6 +150,7 @@ def _gpu_worker(rank, world, port, out_dir, partition="pair"):
 
 
 @pytest.mark.gpu
+@pytest.mark.timeout(240)
 @pytest.mark.parametrize("partition", ["pair", "chain", "track"])
 def test_nccl_world2_matches_single_gpu(tmp_path, partition):
     if torch.cuda.device_count() < 2:
