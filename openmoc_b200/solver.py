@@ -85,7 +85,8 @@ class B200Solver:
     device : int               CUDA device ordinal
     precision : int            capi.PRECISION_DOUBLE (reference double build) or PRECISION_MIXED
     process_group : optional   torch.distributed group; when its world size > 1 the
-                               tracks are sharded by azimuthal pair across the ranks
+                               tracks are sharded by azimuthal pair across the ranks.  close() the solver before
+                               destroy_process_group(): its CUDA graphs hold captured NCCL kernels
     partition : str            "pair": whole azimuthal reflective pairs per rank (north-star
                                partition); "chain": whole track chains, balanced by segments;
                                "track": single tracks dealt by length, any number of ranks, the
@@ -314,6 +315,15 @@ class B200Solver:
         return out
 
     def close(self) -> None:
+        # CUDA graphs of the multi-GPU loop hold captured NCCL kernels: they must go before the process group does
+        # (torch.distributed.destroy_process_group() waits forever on a communicator a live graph still refers to)
+        for g in getattr(self, "_graphs", {}).values():
+            try:
+                g.reset()
+            except Exception:
+                pass
+        self._graphs = {}
+        self._phi_tensor = self._mom_tensor = None
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.b200_destroy(self._h)
             self._h = C.c_void_p()

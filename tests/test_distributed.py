@@ -146,6 +146,7 @@ def _gpu_worker(rank, world, port, out_dir, partition="pair"):
     s.computeEigenvalue(400, FISSION_SOURCE)
     np.save(os.path.join(out_dir, f"phi{rank}.npy"), s.getFluxes())
     np.save(os.path.join(out_dir, f"k{rank}.npy"), np.array([s.getKeff(), s.getNumIterations()]))
+    s.close()          # the solver's CUDA graphs hold captured NCCL kernels: release them before the communicator
     dist.destroy_process_group()
 
 
