@@ -286,3 +286,54 @@ def test_cmfd_split_rules_match_the_reference():
         out = subprocess.run([driver, "--check-cmfd-split", spec], check=True, capture_output=True, text=True).stdout
         r = json.loads(out.strip().splitlines()[-1])
         assert r["mismatches"] == 0 and r["checked"] > 0
+
+
+# ---------------------------------------------------------------- CMFD data of the synthetic decks (host side)
+def test_synthetic_tracks_carry_consistent_cmfd_surfaces():
+    """synth.make_tracks marks, for a CMFD mesh laid over the pin lattice, the surface every segment ends on
+    (segment::_cmfd_surface_fwd/_bwd = cell*26 + surface): every track starts and ends on a boundary face of the
+    mesh, a forward crossing is followed by the opposite backward surface of the neighbouring cell, and the cell of a
+    marked segment is the CMFD cell of its FSR."""
+    from openmoc_b200.synth import make_tracks, cmfd_mesh
+    ft = make_tracks("simple-lattice", 8, 0.1)
+    a = ft.arrays
+    mesh = cmfd_mesh(ft, "simple-lattice", group_structure=[[1, 2, 3], [4, 5, 6, 7]])
+    assert mesh.num_cells == 16 and mesh.fsr_cell.size == ft.n_fsrs
+    fwd, bwd, off, fsr = a["seg_cmfd_fwd"], a["seg_cmfd_bwd"], a["trk_seg_offset"], a["seg_fsr"]
+    opposite = {0: 3, 3: 0, 1: 4, 4: 1, 6: 9, 9: 6, 7: 8, 8: 7}       # X_MIN <-> X_MAX, ..., corners
+    nx = mesh.num_x
+    step = {0: -1, 3: 1, 1: -nx, 4: nx, 6: -nx - 1, 9: nx + 1, 7: -nx + 1, 8: nx - 1}
+    for t in range(ft.n_tracks):
+        s0, s1 = off[t], off[t + 1]
+        assert bwd[s0] >= 0 and fwd[s1 - 1] >= 0                     # both ends lie on the boundary of the mesh
+        for s in range(s0, s1):
+            for code in (fwd[s], bwd[s]):
+                if code >= 0:
+                    assert code // 26 == mesh.fsr_cell[fsr[s]] and code % 26 < 10
+            if fwd[s] >= 0 and s + 1 < s1:                           # crossing into the next cell
+                assert bwd[s + 1] >= 0
+                assert bwd[s + 1] % 26 == opposite[fwd[s] % 26]
+                assert bwd[s + 1] // 26 == fwd[s] // 26 + step[fwd[s] % 26]
+            elif s + 1 < s1:
+                assert bwd[s + 1] < 0
+
+
+def test_cmfd_mesh_group_structure_and_3d_cells():
+    from openmoc_b200.capi import B200Error
+    from openmoc_b200.synth import make_tracks_3d, cmfd_mesh
+    ft = make_tracks_3d("simple-lattice", 4, 0.5, 2, 2.0, 4, expand=False)
+    mesh = cmfd_mesh(ft, "simple-lattice", num_z=2, group_structure=[[1, 2, 3], [4, 5, 6, 7]])
+    idx, m2c = mesh.group_indices(7)
+    assert list(idx) == [0, 3, 7] and list(m2c) == [0, 0, 0, 1, 1, 1, 1]
+    assert list(cmfd_mesh(ft, "simple-lattice", num_z=2).group_indices(7)[0]) == list(range(8))   # no condensation
+    # 3D FSR = 2D FSR * n_axial + layer: layers 0, 1 lie in the lower CMFD cell, 2, 3 in the upper one
+    cell = mesh.fsr_cell.reshape(-1, 4)
+    assert np.all(cell[:, 0] == cell[:, 1]) and np.all(cell[:, 2] == cell[:, 3])
+    assert np.all(cell[:, 2] - cell[:, 0] == mesh.num_x * mesh.num_y)
+    assert np.allclose(mesh.z_planes, [-5.0, 0.0, 5.0]) and mesh.boundaries[2] == REFLECTIVE
+    assert set(np.unique(ft.arrays["seg2d_surf_fwd"])) <= set(range(-1, 10))
+    with pytest.raises(B200Error):
+        mesh.group_structure = [[1, 2], [4, 5, 6, 7]]
+        mesh.group_indices(7)
+    with pytest.raises(ValueError):
+        cmfd_mesh(ft, "simple-lattice", num_z=3)
