@@ -15,6 +15,7 @@
  *                   [--max-iters N] [--threads N] [--res fission|flux|total]
  *                   [--axial N (c5g7-2d, dims 3: axial layers of the root lattice)]
  *                   [--devices 0,1,.. (--solver both: GPUs behind the one B200Solver; a device may repeat)]
+ *                   [--cmfd-relax F (Cmfd::setCMFDRelaxationFactor)] [--cmfd-sor F] [--results-fsrs ("# FSRs:" line in --results)]
  *                   [--cmfd NXxNY[xNZ]] [--host-cmfd (B200 solvers: the reference's host Cmfd instead of the device CMFD)]
  *                   [--check-cmfd-split (compare the library's current-splitting tables with Cmfd's, no GPU needed)]
  *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
@@ -139,6 +140,8 @@ int main(int argc, char** argv) {
       cmfd->setGroupStructure(groups);
     }
     if (!flag(argc, argv, "--no-knearest")) cmfd->setKNearest(3);
+    if (strlen(arg(argc, argv, "--cmfd-relax", "")) > 0) cmfd->setCMFDRelaxationFactor(atof(arg(argc, argv, "--cmfd-relax", "0.7")));
+    if (strlen(arg(argc, argv, "--cmfd-sor", "")) > 0) cmfd->setSORRelaxationFactor(atof(arg(argc, argv, "--cmfd-sor", "1.5")));
     if (flag(argc, argv, "--no-flux-limiting")) cmfd->useFluxLimiting(false);   /* diagnostics */
     if (flag(argc, argv, "--rebalance")) cmfd->rebalanceSigmaT(true);          /* starting currents tallied every sweep */
     geometry->setCmfd(cmfd);
@@ -339,6 +342,7 @@ int main(int argc, char** argv) {
     FILE* f = fopen(results.c_str(), "w");
     fprintf(f, "# Iterations: %d\n", solver->getNumIterations());
     if (mode == "eigen") fprintf(f, "keff: %12.5E\n", solver->getKeff());
+    if (flag(argc, argv, "--results-fsrs")) fprintf(f, "# FSRs: %ld\n", n_fsr);      /* tests/testing_harness.py: num_fsrs=True */
     if (fluxes_in_results) {
       fprintf(f, "fluxes:\n");
       std::vector<FP_PRECISION> phi(n_fsr * G);

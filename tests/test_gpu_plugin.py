@@ -183,6 +183,27 @@ def test_fused_cmfd_loop_matches_cpusolver(args, tmp_path):
     assert np.max(np.abs(fa - fb) / np.abs(fa)) < 2e-5
 
 
+CMFD_GOLDEN_ARGS = ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "4", "--spacing", "0.12",
+                    "--zspacing", "0.5", "--formation", "otf-stacks", "--cmfd", "4x4x4", "--cmfd-relax", "1.0", "--tol", "1e-4",
+                    "--quiet", "--no-fluxes", "--results-fsrs"]
+
+
+@pytest.mark.parametrize("where", ["device", "host"])
+def test_cmfd_reference_golden_from_gpu(where, tmp_path, monkeypatch):
+    """tests/test_forward_3D_lattice_CMFD/results_true.dat (CPULSSolver, OTF_STACKS, CMFD 4 x 4 x 4, two groups,
+    k-nearest 3, relaxation 1.0: 24 iterations, keff 8.37390E-01, 2048 FSRs) byte for byte from B200LSSolver, with
+    the CMFD on the device and with the reference's host Cmfd fed by the device."""
+    if not os.path.exists(DRIVER):
+        pytest.skip("ref_driver not built")
+    if where == "host":
+        monkeypatch.setenv("B200_HOST_CMFD", "1")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([DRIVER] + CMFD_GOLDEN_ARGS + ["--solver", "b200ls", "--threads", "4", "--results", res],
+                   check=True, capture_output=True)
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_goldens.json")))["test_forward_3D_lattice_CMFD"]
+    assert open(res).read() == golden
+
+
 def test_3d_c5g7_linear_source_cmfd_in_separate_processes(tmp_path):
     """configs[4] shape at coarse tracks: extruded 3D C5G7, OTF_STACKS, CPULSSolver, CMFD 51x51x3.
     Run in two fresh processes: `--solver both` shares one Cmfd object between the two solves and

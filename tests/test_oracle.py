@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, load_case
+from conftest import GOLDEN, ROOT, load_case
 from oracle.oracle_py import (OracleSolver, format_harness_results, lib,
                               FISSION_SOURCE, SCALAR_FLUX, TOTAL_SOURCE)
 
@@ -255,3 +255,19 @@ def test_linear_source_global_stabilisation_matches_reference():
     assert n == ref["iterations"] == 234
     assert abs(s.getKeff() - ref["keff"]) * 1e5 < 1e-6
     np.testing.assert_allclose(s.getFluxes(), ref["fluxes"], rtol=1e-12)
+
+
+def test_ref_driver_reproduces_the_cmfd_golden(tmp_path):
+    """The checker of the CMFD path is the unmodified reference driven by oracle/_ref/ref_driver: its restatement of
+    tests/test_forward_3D_lattice_CMFD (SimpleLatticeInput 3D, OTF_STACKS, CPULSSolver, CMFD 4 x 4 x 4) must give the
+    reference's committed golden byte for byte."""
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([driver, "--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "4", "--spacing", "0.12",
+                    "--zspacing", "0.5", "--formation", "otf-stacks", "--cmfd", "4x4x4", "--cmfd-relax", "1.0", "--tol", "1e-4",
+                    "--solver", "cpuls", "--threads", "4", "--quiet", "--no-fluxes", "--results-fsrs", "--results", res],
+                   check=True, capture_output=True)
+    assert open(res).read() == GOLDENS["test_forward_3D_lattice_CMFD"]
