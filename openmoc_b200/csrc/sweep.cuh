@@ -310,7 +310,10 @@ template <typename T, int NP, int GPL, bool DET, bool CMFD>
 #ifndef B200_LB_BLOCKS_3D
 #define B200_LB_BLOCKS_3D B200_LB_BLOCKS     /* NP == 1 (3D tracks): experiments with more resident CTAs */
 #endif
-__global__ void __launch_bounds__(B200_LB_THREADS, (GPL == 1 && NP <= 3 && !CMFD) ? (NP == 1 ? B200_LB_BLOCKS_3D : B200_LB_BLOCKS) : 1)
+#ifndef B200_LB_BLOCKS_CMFD
+#define B200_LB_BLOCKS_CMFD 4                /* resident CTAs the current-tally variants are compiled for: 72 registers, no spill (was 106 at 2 CTAs: 7.98 -> 6.86 ms on C3) */
+#endif
+__global__ void __launch_bounds__(B200_LB_THREADS, (GPL == 1 && NP <= 3) ? (CMFD ? B200_LB_BLOCKS_CMFD : (NP == 1 ? B200_LB_BLOCKS_3D : B200_LB_BLOCKS)) : 1)
 sweep_kernel(const SweepArgs a) {
   if (a.done != nullptr && *a.done) return;
   /* flat mapping: LPI consecutive threads own one item; an item may straddle two
