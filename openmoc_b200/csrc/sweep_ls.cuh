@@ -65,7 +65,13 @@ __device__ __forceinline__ void ld_src(const double2* __restrict__ qst, const do
 }
 
 template <int NP, int GPL, bool IS3D>
-__global__ void __launch_bounds__(224)
+/* resident CTAs the kernel is compiled for (register cap).  Measured on a B200 (2D C5G7 64 azim / 0.02 cm; 3D 70-group
+ * lattice): one group per thread in 2D gains 5 % at three CTAs (80 registers, 32 B of spills: 2.66e11 -> 2.80e11 /s) and
+ * loses 15 % at four; the three-groups-per-thread 3D variants lose 43 % at three CTAs (208 B of spills) */
+#ifndef B200_LS_BLOCKS
+#define B200_LS_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(224, (GPL == 1 && !IS3D) ? B200_LS_BLOCKS : 1)
 sweep_ls_kernel(const SweepLSArgs la) {
   const SweepArgs& a = la.f;
   if (a.done != nullptr && *a.done) return;
