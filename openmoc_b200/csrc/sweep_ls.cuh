@@ -71,7 +71,7 @@ template <int NP, int GPL, bool IS3D>
 #ifndef B200_LS_BLOCKS
 #define B200_LS_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(224, (GPL == 1 && !IS3D) ? B200_LS_BLOCKS : 1)
+__global__ void __launch_bounds__(224, (GPL == 1 && !IS3D) ? B200_LS_BLOCKS : 0)   /* 0: no occupancy constraint, as before */
 sweep_ls_kernel(const SweepLSArgs la) {
   const SweepArgs& a = la.f;
   if (a.done != nullptr && *a.done) return;
