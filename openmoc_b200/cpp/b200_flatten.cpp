@@ -28,12 +28,17 @@ class FlattenPass : public TraverseSegments {
  public:
   struct Seg { double len; int32_t fsr, mat, cf, cb; double x, y, z; };
 
+  /* Explicit formations keep their segments in the Track objects, so their number is known before the
+   * traversal: with `offsets` given (trk_seg_offset, n_tracks + 1) the segments are written straight into the
+   * flat arrays of `out` and no per-track copy (56 bytes per segment) is ever made.  On-the-fly formations
+   * are traced as they go: their segments are collected per track first. */
   FlattenPass(TrackGenerator* tg, std::map<Material*, int>* mat_index,
-              B200FlatTracks* out)
-      : TraverseSegments(tg), _mat_index(mat_index), _out(out) {
-    _per_track.resize(out->n_tracks);
+              B200FlatTracks* out, const std::vector<int64_t>* offsets = NULL, bool with_ls_data = true)
+      : TraverseSegments(tg), _mat_index(mat_index), _out(out), _offsets(offsets), _with_ls(with_ls_data) {
+    if (_offsets == NULL) _per_track.resize(out->n_tracks);
     _seen.assign(out->n_tracks, 0);
   }
+  bool explicitFormation() { return _segment_formation == EXPLICIT_2D || _segment_formation == EXPLICIT_3D; }
 
   void execute() {
     if (_segment_formation != EXPLICIT_2D && _segment_formation != EXPLICIT_3D) {
@@ -90,6 +95,31 @@ class FlattenPass : public TraverseSegments {
     int n = track->getNumSegments();
     Material* last_mat = NULL;
     int last_idx = -1;
+    if (_offsets != NULL) {
+      /* explicit tracks: one track per call, straight into the flat arrays */
+      size_t o = (size_t)(*_offsets)[uid];
+      if ((int64_t)n != (*_offsets)[uid + 1] - (*_offsets)[uid])
+        log_printf(ERROR, "b200_flatten: track %ld changed its segment count during the traversal", uid);
+      for (int s = 0; s < n; s++, o++) {
+        const segment& sg = segments[s];
+        if (sg._material != last_mat) {
+          std::map<Material*, int>::iterator it = _mat_index->find(sg._material);
+          last_mat = sg._material;
+          last_idx = (it == _mat_index->end()) ? -1 : it->second;
+        }
+        _out->seg_length[o] = sg._length;
+        _out->seg_fsr[o] = sg._region_id;
+        _out->seg_mat[o] = last_idx;
+        _out->seg_cmfd_fwd[o] = sg._cmfd_surface_fwd;
+        _out->seg_cmfd_bwd[o] = sg._cmfd_surface_bwd;
+        if (_with_ls) {
+          _out->seg_start[3 * o] = sg._starting_position[0];
+          _out->seg_start[3 * o + 1] = sg._starting_position[1];
+          _out->seg_start[3 * o + 2] = sg._starting_position[2];
+        }
+      }
+      return;
+    }
     if (n_in_stack == 1) _per_track[uid].reserve(n);
     for (int s = 0; s < n; s++) {
       const segment& sg = segments[s];
@@ -118,6 +148,21 @@ class FlattenPass : public TraverseSegments {
  private:
   std::map<Material*, int>* _mat_index;
   B200FlatTracks* _out;
+  const std::vector<int64_t>* _offsets;
+  bool _with_ls;
+};
+
+/** Segment count of every explicit track (Track::getNumSegments), by uid. */
+class CountPass : public TraverseSegments {
+ public:
+  CountPass(TrackGenerator* tg, std::vector<int64_t>* counts) : TraverseSegments(tg), _counts(counts) {}
+  void execute() {
+#pragma omp parallel
+    loopOverTracks(NULL);
+  }
+  void onTrack(Track* track, segment* segments) { (*_counts)[track->getUid()] = track->getNumSegments(); }
+ private:
+  std::vector<int64_t>* _counts;
 };
 
 }  // namespace
@@ -337,6 +382,27 @@ void b200_flatten(TrackGenerator* tg, B200FlatTracks* ft, bool with_ls_data, boo
   if (device_otf && b200_can_trace_on_device(tg)) {
     flatten_for_device_tracer(tg3, ft);
     return;
+  }
+  {
+    FlattenPass probe(tg, &mat_index, ft);
+    if (probe.explicitFormation()) {
+      /* two traversals, no per-track copies: count, then write in place */
+      std::vector<int64_t> counts(nt, 0);
+      CountPass count(tg, &counts);
+      count.execute();
+      ft->trk_seg_offset.assign(nt + 1, 0);
+      for (size_t t = 0; t < nt; t++) ft->trk_seg_offset[t + 1] = ft->trk_seg_offset[t] + counts[t];
+      ft->n_segments = ft->trk_seg_offset[nt];
+      const size_t ns = ft->n_segments;
+      ft->seg_length.resize(ns); ft->seg_fsr.resize(ns); ft->seg_mat.resize(ns);
+      ft->seg_cmfd_fwd.resize(ns); ft->seg_cmfd_bwd.resize(ns);
+      if (with_ls_data) ft->seg_start.resize(3 * ns);
+      FlattenPass fill(tg, &mat_index, ft, &ft->trk_seg_offset, with_ls_data);
+      fill.execute();
+      for (size_t t = 0; t < nt; t++)
+        if (!fill._seen[t]) log_printf(ERROR, "b200_flatten: track %ld was never visited", (long)t);
+      return;
+    }
   }
   FlattenPass pass(tg, &mat_index, ft);
   pass.execute();
