@@ -5,8 +5,8 @@
  *        quadratures, TrackGenerator / TrackGenerator3D, CPUSolver / CPULSSolver), so that
  *        `B200Solver(track_generator)` is what it is in C++ - the role of the reference's SWIG modules
  *        (openmoc/swig/openmoc.i:167-169, openmoc/cuda/openmoc_cuda.i:52-56; `swig` is not in this image).
- *        Links the unmodified reference core (oracle/_ref/libopenmoc_ref.so) and libb200moc.so; built by
- *        oracle/Makefile because it needs the reference headers.  Python-side conveniences (log, options,
+ *        Links the unmodified reference core (libopenmoc_ref.so, built from the reference sources by the same recipe
+ *        that builds the checker: INTEGRATION.md) and libb200moc.so; it needs the reference headers.  Python-side conveniences (log, options,
  *        materials from the C5G7 cross-section file) live in openmoc_b200/openmoc.py.
  *
  * Ownership follows openmoc/swig/thisown.i: OpenMOC objects keep raw pointers to each other, so nothing created
