@@ -154,6 +154,16 @@ public:
     Base::computeEigenvalue(max_iters, res_type);
     restoreCmfdFluxUpdate();
   }
+  /** The summary of the base class with the Cmfd's flux update shown as the user set it (it is only switched
+   *  off on the host object because the device does that work). */
+  void printInputParamsSummary() {
+    if (_cmfd_suspended != NULL) _cmfd_suspended->setFluxUpdateOn(true);
+    Base::printInputParamsSummary();
+    if (_cmfd_suspended != NULL) {
+      _cmfd_suspended->setFluxUpdateOn(false);
+      log_printf(NORMAL, "CMFD collapse, diffusion solve and prolongation: on the B200 device");
+    }
+  }
   /** Copy phi, old phi and q from the device into the base-class host arrays. */
   void syncHostMirrors();
   /** Fused device-side source iteration (b200_compute_eigenvalue): same results as
