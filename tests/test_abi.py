@@ -51,3 +51,31 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "moc_oracle" not in src and "oracle_py" not in src and "oracle/" not in src, f
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """capi.Config / CmfdConfig / CmfdStats mirror b200_config / b200_cmfd_config / b200_cmfd_stats field for field:
+    sizes and offsets from a C compiler against ctypes."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    fields = {"b200_config": (capi.Config, None), "b200_cmfd_config": (capi.CmfdConfig, None), "b200_cmfd_stats": (capi.CmfdStats, None)}
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "b200moc.h"', "int main(void) {"]
+    for cname, (cls, _) in fields.items():
+        src.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            src.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src.append("return 0; }")
+    c = os.path.join(tmp_path, "layout.c")
+    open(c, "w").write("\n".join(src))
+    exe = os.path.join(tmp_path, "layout")
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, c], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split("\n")
+    for line in filter(None, out):
+        cname, what, value = line.split()
+        cls = fields[cname][0]
+        if what == "size":
+            assert C.sizeof(cls) == int(value), cname
+        else:
+            assert getattr(cls, what).offset == int(value), (cname, what)
