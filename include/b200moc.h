@@ -33,6 +33,10 @@
  *   B200_GRAPH=0|1            CUDA-graph replay of the fused iteration off / on; default: on
  *                             for decks with fewer than 1e8 integrations per sweep
  *   B200_GPL, B200_IPC, B200_CTA   lane map / CTA size of the sweep kernel (experiments)
+ *   B200_CMFD_MODE=0|1|2      launch shape of the CMFD eigenvalue solve: one CTA / cooperative grid / one thread-block
+ *                             cluster; default by mesh size (profiles/r02_cmfd.md).  B200_CMFD_CLUSTER (CTAs),
+ *                             B200_CMFD_CLUSTER_THREADS, B200_CMFD_THREADS, B200_CMFD_BLOCKS refine it (experiments)
+ *   (plug-in) B200_HOST_CMFD=1 keeps the reference's host Cmfd, B200_HOST_OTF=1 the host expansion of OTF tracks
  */
 #ifndef B200MOC_H_
 #define B200MOC_H_
