@@ -5,6 +5,7 @@
  * Compiled against the reference's headers; see b200_flatten.h.
  */
 #include "b200_flatten.h"
+#include "b200_cmfd_view.h"
 #include "Cmfd.h"
 
 #include <cstdio>
@@ -465,7 +466,7 @@ struct ChunkWriter {
 };
 }  // namespace
 
-void b200_write_trackfile(const B200FlatTracks& ft, const std::string& path) {
+void b200_write_trackfile(const B200FlatTracks& ft, const std::string& path, const B200CmfdView* cmfd) {
   FILE* f = fopen(path.c_str(), "wb");
   if (f == NULL) log_printf(ERROR, "b200_write_trackfile: cannot open %s", path.c_str());
   fwrite("B2TRK001", 1, 8, f);
@@ -497,6 +498,18 @@ void b200_write_trackfile(const B200FlatTracks& ft, const std::string& path) {
   w.v("mat_sigma_f", ft.mat_sigma_f); w.v("mat_nu_sigma_f", ft.mat_nu_sigma_f);
   w.v("mat_chi", ft.mat_chi); w.v("mat_sigma_s", ft.mat_sigma_s);
   w.v("mat_fiss_matrix", ft.mat_fiss_matrix); w.v("mat_fissionable", ft.mat_fissionable);
+  if (cmfd != NULL) {
+    std::vector<int32_t> dims = {cmfd->num_x, cmfd->num_y, cmfd->num_z, cmfd->num_cmfd_groups};
+    std::vector<int32_t> bcs(cmfd->boundaries, cmfd->boundaries + 6);
+    std::vector<double> options = {cmfd->sor_factor, cmfd->relaxation_factor, cmfd->flux_limiting ? 1. : 0.};
+    std::vector<int32_t> fsr_cell(ft.n_fsrs, -1);
+    for (size_t i = 0; i + 1 < cmfd->cell_fsr_offset.size(); i++)
+      for (int64_t j = cmfd->cell_fsr_offset[i]; j < cmfd->cell_fsr_offset[i + 1]; j++)
+        if (cmfd->cell_fsrs[j] >= 0 && cmfd->cell_fsrs[j] < ft.n_fsrs) fsr_cell[cmfd->cell_fsrs[j]] = (int32_t)i;
+    w.v("cmfd_dims", dims); w.v("cmfd_boundaries", bcs); w.v("cmfd_options", options);
+    w.v("cmfd_widths_x", cmfd->widths_x); w.v("cmfd_widths_y", cmfd->widths_y); w.v("cmfd_widths_z", cmfd->widths_z);
+    w.v("cmfd_group_indices", cmfd->group_indices); w.v("fsr_cmfd_cell", fsr_cell);
+  }
   fseek(f, 8, SEEK_SET);
   fwrite(&w.n, 8, 1, f);
   fclose(f);

@@ -102,6 +102,11 @@ void b200_flatten(TrackGenerator* track_generator, B200FlatTracks* out,
 bool b200_can_trace_on_device(TrackGenerator* track_generator);
 
 /** Write / read the chunked binary track file (see openmoc_b200/trackfile.py). */
-void b200_write_trackfile(const B200FlatTracks& ft, const std::string& path);
+struct B200CmfdView;
+/** cmfd != NULL (b200_read_cmfd of the Geometry's initialised Cmfd): the file also carries the CMFD mesh - chunks
+ *  cmfd_dims (num_x, num_y, num_z, num_cmfd_groups), cmfd_widths_x/y/z, cmfd_boundaries, cmfd_group_indices,
+ *  cmfd_options (SOR factor, relaxation factor, flux limiting) and fsr_cmfd_cell - next to the surfaces the
+ *  segments cross (seg_cmfd_fwd / seg_cmfd_bwd): openmoc_b200.solver.CmfdMesh.from_tracks rebuilds the mesh. */
+void b200_write_trackfile(const B200FlatTracks& ft, const std::string& path, const B200CmfdView* cmfd = NULL);
 
 #endif /* B200_FLATTEN_H_ */

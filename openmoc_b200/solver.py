@@ -64,6 +64,24 @@ class CmfdMesh:
     def num_cells(self):
         return self.num_x * self.num_y * self.num_z
 
+    @classmethod
+    def from_tracks(cls, ft, **options):
+        """The CMFD mesh a B2TRK track file carries when it was dumped from a Geometry with a Cmfd
+        (b200_write_trackfile: cmfd_dims, cmfd_widths_*, cmfd_boundaries, cmfd_group_indices, cmfd_options,
+        fsr_cmfd_cell; the segments' surfaces are seg_cmfd_fwd / seg_cmfd_bwd).  Centroid (k-nearest) updating is
+        not carried over: the mesh runs with the plain flux-ratio update (Cmfd::setCentroidUpdateOn(False))."""
+        a = ft.arrays
+        if "cmfd_dims" not in a:
+            raise B200Error("the track file carries no CMFD mesh (dump it from a Geometry with a Cmfd, after the solve)")
+        nx, ny, nz, ncg = (int(v) for v in a["cmfd_dims"])
+        idx = a["cmfd_group_indices"]
+        groups = [[g + 1 for g in range(int(idx[e]), int(idx[e + 1]))] for e in range(ncg)]
+        sor, relax, limiting = (float(v) for v in a["cmfd_options"])
+        kw = dict(sor_factor=sor, relaxation_factor=relax, flux_limiting=bool(limiting))
+        kw.update(options)
+        return cls(nx, ny, nz, a["cmfd_widths_x"], a["cmfd_widths_y"], a["cmfd_widths_z"], a["cmfd_boundaries"],
+                   a["fsr_cmfd_cell"], group_structure=groups, **kw)
+
     def group_indices(self, num_groups):
         """Cmfd::_group_indices (Cmfd.cpp:1943-1990): first MOC group (0-based) of every CMFD group, and the MOC -> CMFD map"""
         gs = self.group_structure or [[g + 1] for g in range(num_groups)]

@@ -35,6 +35,7 @@
 
 #include "models.h"
 #include "../../openmoc_b200/cpp/b200_flatten.h"
+#include "../../openmoc_b200/cpp/b200_cmfd_view.h"
 #include "../../openmoc_b200/cpp/B200Solver.h"
 #include "../../openmoc_b200/cpp/B200LSSolver.h"
 
@@ -406,7 +407,10 @@ int main(int argc, char** argv) {
   if (!dump_tracks.empty()) {
     B200FlatTracks ft;
     b200_flatten(tg, &ft);
-    b200_write_trackfile(ft, dump_tracks);
+    B200CmfdView view;
+    Cmfd* dumped_cmfd = solved ? geometry->getCmfd() : NULL;      /* the mesh is known once the solver initialised it */
+    if (dumped_cmfd != NULL) b200_read_cmfd(dumped_cmfd, n_fsr, &view);
+    b200_write_trackfile(ft, dump_tracks, dumped_cmfd != NULL ? &view : NULL);
     printf("[ref_driver] wrote %s: %ld tracks, %ld segments, %ld FSRs, G=%d F=%d\n",
            dump_tracks.c_str(), (long)ft.n_tracks, (long)ft.n_segments, (long)ft.n_fsrs,
            ft.num_groups, ft.fluxes_per_track);

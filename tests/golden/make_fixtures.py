@@ -54,6 +54,8 @@ CASES = {
     # stabilizeFlux, src/CPULSSolver.cpp:888-1052); same tracks as simple_lattice_ls: only the results are kept
     "simple_lattice_ls_stab": ["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12", "--solver", "cpuls",
                                "--stabilize", "0.5:2"],
+    # CMFD from a track file: the dump carries the mesh (cmfd_* chunks, fsr_cmfd_cell) next to the surfaces of the segments
+    "simple_lattice_cmfd": ["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12", "--cmfd", "4x4", "--no-knearest"],
     "lattice3d_ls_7g": ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2",
                         "--spacing", "0.24", "--zspacing", "0.9", "--solver", "cpuls"],  # test_forward_3D_lattice_linear
 }

@@ -81,3 +81,19 @@ def test_python_cmfd_on_a_device_group_equals_one_device():
         assert it == res[0][0]
         assert abs(k - res[0][1]) * 1e5 < 1e-3
         assert np.max(np.abs(phi - res[0][2]) / res[0][2]) < 1e-6
+
+
+def test_cmfd_from_a_reference_track_file():
+    """Tracks, CMFD surfaces and CMFD mesh dumped by the reference's own ray tracer (tests/golden/
+    simple_lattice_cmfd.b2trk, ref_driver --cmfd 4x4 --dump-tracks): the device solve reproduces the CPUSolver + Cmfd
+    run the dump came from (27 iterations) - same tracks, so to rounding."""
+    from openmoc_b200.solver import B200Solver, CmfdMesh
+    from openmoc_b200.trackfile import read_trackfile
+    golden = os.path.join(ROOT, "tests", "golden")
+    ft = read_trackfile(os.path.join(golden, "simple_lattice_cmfd.b2trk"))
+    ref = json.load(open(os.path.join(golden, "simple_lattice_cmfd.json")))
+    s = B200Solver(ft, cmfd=CmfdMesh.from_tracks(ft))
+    s.computeEigenvalue(500)
+    assert s.getNumIterations() == ref["iterations"] == 27
+    assert abs(s.getKeff() - ref["keff"]) * 1e5 < 1e-4
+    assert np.max(np.abs(s.getFluxes() - np.array(ref["fluxes"])) / np.array(ref["fluxes"])) < 1e-8

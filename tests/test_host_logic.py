@@ -337,3 +337,21 @@ def test_cmfd_mesh_group_structure_and_3d_cells():
         mesh.group_indices(7)
     with pytest.raises(ValueError):
         cmfd_mesh(ft, "simple-lattice", num_z=3)
+
+
+def test_trackfile_carries_the_cmfd_mesh():
+    """A B2TRK file dumped from a Geometry with a Cmfd (ref_driver --cmfd --dump-tracks) carries the mesh:
+    CmfdMesh.from_tracks rebuilds it, and the surfaces of the segments name the CMFD cell of their FSR."""
+    from openmoc_b200.solver import CmfdMesh
+    ft = read_trackfile(os.path.join(ROOT, "tests", "golden", "simple_lattice_cmfd.b2trk"))
+    m = CmfdMesh.from_tracks(ft)
+    assert (m.num_x, m.num_y, m.num_z) == (4, 4, 1) and m.group_structure == [[1, 2, 3], [4, 5, 6, 7]]
+    assert m.boundaries == (REFLECTIVE,) * 6 and np.allclose(m.widths_x, 1.0) and m.sor_factor == 1.5
+    assert m.fsr_cell.size == ft.n_fsrs and m.fsr_cell.min() == 0 and m.fsr_cell.max() == 15
+    a = ft.arrays
+    for key in ("seg_cmfd_fwd", "seg_cmfd_bwd"):
+        marked = a[key] >= 0
+        assert marked.any()
+        assert np.all(a[key][marked] // 26 == m.fsr_cell[a["seg_fsr"][marked]])
+        assert np.all(a[key][marked] % 26 < 10)                  # a 2D track crosses x / y faces and z-parallel edges only
+    assert CmfdMesh.from_tracks(ft, sor_factor=1.0).sor_factor == 1.0
