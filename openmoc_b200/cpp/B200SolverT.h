@@ -392,8 +392,10 @@ void B200SolverT<Base>::initializeCmfd() {
   for (int e = 0; e < _num_groups; e++) map[e] = _cmfd->getCmfdGroup(e);
   check(b200_set_cmfd_groups(_h, map.data(), _cmfd->getNumCmfdGroups(), _cmfd->getNumCells()),
         "b200_set_cmfd_groups");
-  _cmfd_currents.assign((size_t)_cmfd->getNumCells() * NUM_SURFACES * _cmfd->getNumCmfdGroups(), 0.);
   configureDeviceCmfd();
+  /* the host copy of the currents is only needed when the reference's host Cmfd does the work */
+  if (_cmfd_device_active) std::vector<double>().swap(_cmfd_currents);
+  else _cmfd_currents.assign((size_t)_cmfd->getNumCells() * NUM_SURFACES * _cmfd->getNumCmfdGroups(), 0.);
 }
 
 /* Hands the mesh, the group structure, the FSR lists, the options and the k-nearest stencils of the Cmfd object
