@@ -355,3 +355,57 @@ def test_trackfile_carries_the_cmfd_mesh():
         assert np.all(a[key][marked] // 26 == m.fsr_cell[a["seg_fsr"][marked]])
         assert np.all(a[key][marked] % 26 < 10)                  # a 2D track crosses x / y faces and z-parallel edges only
     assert CmfdMesh.from_tracks(ft, sor_factor=1.0).sor_factor == 1.0
+
+
+def test_multi_gpu_graph_bookkeeping_with_a_fake_library(monkeypatch):
+    """Host logic of the multi-GPU loop without a GPU: the CUDA graph of two split iterations is captured once,
+    the benchmark hook numbers its captured iterations 1000 (like b200_iterate: past the negative-source clipping
+    of the first 30 iterations, so k_eff after K steps is the same for every number of GPUs) while the converging
+    loop passes -1 (device-side counter), and the library's kernels inside every replay are counted."""
+    import contextlib
+    import ctypes as C
+    import torch
+    from openmoc_b200 import solver as S
+
+    class FakeLib:
+        def __init__(self):
+            self.launches, self.calls = 0, []
+        def b200_get_sweep_stats(self, h, ms, ns, nl):
+            nl._obj.value = self.launches
+            return 0
+        def b200_reset_sweep_stats(self, h):
+            self.launches = 0
+            return 0
+        def b200_set_capturing(self, h, v):
+            self.calls.append(("capturing", v)); return 0
+        def b200_iteration_begin(self, h, it):
+            self.calls.append(("begin", it)); self.launches += 3; return 0
+        def b200_iteration_end(self, h, it, res, chk):
+            self.calls.append(("end", it, chk)); self.launches += 5; return 0
+
+    class FakeGraph:
+        replays = 0
+        def replay(self):
+            FakeGraph.replays += 1
+
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph", lambda g, stream=None: contextlib.nullcontext())
+    s = S.B200Solver.__new__(S.B200Solver)
+    s._lib, s._h, s._cs = FakeLib(), None, None
+    s._graphs, s._graph_launches, s._replayed_launches = {}, {}, 0
+    s._tally_views = lambda: None
+    s._allreduce_scalar_flux = lambda: None
+    s.resetSweepStats()
+    s._split_iteration_graph(1, 0)
+    assert [c for c in s._lib.calls if c[0] == "begin"] == [("begin", 1000)] * 2
+    assert s._graph_launches[(1, 0)] == 16
+    assert s.getSweepStats()[2] == 0                       # capturing runs nothing
+    for _ in range(10):
+        s._replay((1, 0))
+    assert FakeGraph.replays == 10 and s.getSweepStats()[2] == 160
+    s.resetSweepStats()
+    assert s.getSweepStats()[2] == 0
+    s._lib.calls.clear()
+    s._split_iteration_graph(1, 1)
+    assert [c for c in s._lib.calls if c[0] != "capturing"] == [("begin", -1), ("end", -1, 1)] * 2
+    assert s._split_iteration_graph(1, 1) is s._graphs[(1, 1)] and len(s._lib.calls) == 6   # captured once
