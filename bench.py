@@ -377,6 +377,11 @@ def measure(name, args, env, primary):
             traffic = json.load(open(prof)).get(name, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    if traffic is not None:
+        if azim != wl["azim"] or spacing != wl["spacing"]:
+            traffic = None                      # the ncu capture is of the workload's own shape
+        elif world > 1:
+            traffic *= local_W / W_sweep        # one rank's launch streams its share of the captured deck
     rate_local = local_W / (sweep_avg_ms * 1e-3)                    # integrations/s of this rank's sweep kernel
     fp64_ceiling = env.fp64_rate / FP64_PER_INTEGRATION[wl["dims"]]
     # flat 2D tracks merge the tally over the NP polar angles and over runs of segments in one FSR;
