@@ -369,6 +369,9 @@ class B200Solver:
         self._k_eff = k.value
         return k.value
 
+    def setKeff(self, k_eff: float) -> None:
+        check(self._lib.b200_set_keff(self._h, float(k_eff)))
+
     def setConvergenceThreshold(self, threshold: float) -> None:
         if threshold <= 0.0:   # Solver.cpp setConvergenceThreshold
             raise B200Error("Unable to set the convergence threshold to %f since it is not a positive number"
@@ -718,9 +721,13 @@ class B200Solver:
 
     def computeFlux(self, max_iters: int = 1000, only_fixed_source: bool = True) -> None:
         """Solver::computeFlux (src/Solver.cpp:1352-1420)."""
-        if self._world > 1:
-            raise B200Error("computeFlux is single-GPU in this build")
         t0 = time.perf_counter()
+        if self._world > 1:
+            # one process per GPU: the same loop step by step, the sweep's collectives inside transportSweep
+            from .loops import flux_loop
+            self._num_iterations = flux_loop(self, max_iters, self._converge_thresh, only_fixed_source)
+            self._total_time = time.perf_counter() - t0
+            return
         n = C.c_int32()
         check(self._lib.b200_compute_flux(self._h, int(max_iters), self._converge_thresh,
                                           int(bool(only_fixed_source)), C.byref(n)))
@@ -729,9 +736,17 @@ class B200Solver:
 
     def computeSource(self, max_iters: int = 1000, k_eff: float = 1.0, res_type: int = TOTAL_SOURCE) -> None:
         """Solver::computeSource (src/Solver.cpp:1459-1516)."""
-        if self._world > 1:
-            raise B200Error("computeSource is single-GPU in this build")
         t0 = time.perf_counter()
+        if self._world > 1:
+            from .loops import source_loop
+            if k_eff <= 0.0:
+                raise B200Error("The Solver is unable to compute the source with keff = %f since it is not a "
+                                "positive value" % k_eff)
+            if res_type not in (SCALAR_FLUX, FISSION_SOURCE, TOTAL_SOURCE):
+                raise B200Error("computeSource: unknown residual type %r" % (res_type,))
+            self._num_iterations = source_loop(self, max_iters, float(k_eff), self._converge_thresh, int(res_type))
+            self._total_time = time.perf_counter() - t0
+            return
         n = C.c_int32()
         check(self._lib.b200_compute_source(self._h, int(max_iters), float(k_eff), self._converge_thresh,
                                             int(res_type), C.byref(n)))

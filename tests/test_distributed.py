@@ -132,6 +132,67 @@ def test_gloo_track_partition_with_flux_exchange(tmp_path, world):
         np.testing.assert_allclose(phi, ref.getFluxes(), rtol=1e-8)
 
 
+class _ShardStepper:
+    """The step methods of Solver over one rank's shard: the oracle sweeps the shard, the ranks sum their FSR
+    tallies - what B200Solver.transportSweep does over NCCL.  Drives openmoc_b200.loops on the CPU."""
+    def __init__(self, part, reduce_phi):
+        from oracle.oracle_py import OracleSolver
+        self.o, self.reduce_phi = OracleSolver(part), reduce_phi
+
+    def __getattr__(self, name):
+        return getattr(self.o, name)
+
+    def transportSweep(self):
+        self.o.transportSweep()
+        self.o.setFluxes(self.reduce_phi(self.o.getFluxes()))
+
+
+def _cpu_worker_fixed_source(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    from openmoc_b200.loops import flux_loop, source_loop
+    from openmoc_b200.partition import partition_by_azim_pair
+    from oracle.oracle_py import TOTAL_SOURCE
+
+    def reduce_phi(x):
+        t = torch.from_numpy(x.copy())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.numpy()
+    part = partition_by_azim_pair(_tracks(), world)[rank]
+    s = _ShardStepper(part, reduce_phi)
+    s.setFixedSourceByFSR(3, 1, 1.0); s.setFixedSourceByFSR(100, 2, 0.5)
+    n_flux = flux_loop(s, 300, 1e-6)
+    phi_flux = s.getFluxes().copy()
+    s = _ShardStepper(part, reduce_phi)
+    s.setFixedSourceByFSR(3, 1, 1.0)
+    n_src = source_loop(s, 600, 3.0, 1e-4, TOTAL_SOURCE)
+    np.savez(os.path.join(out_dir, f"fixed{rank}.npz"), n_flux=n_flux, phi_flux=phi_flux, n_src=n_src,
+             phi_src=s.getFluxes())
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_fixed_source_loops(tmp_path):
+    """computeFlux / computeSource with one process per rank (openmoc_b200.loops, the loops B200Solver runs at
+    world > 1) against the oracle's own single-process drivers: same iteration counts, same fluxes."""
+    from oracle.oracle_py import OracleSolver, TOTAL_SOURCE
+    port = _free_port()
+    mp.spawn(_cpu_worker_fixed_source, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ref = OracleSolver(_tracks())
+    ref.setFixedSourceByFSR(3, 1, 1.0); ref.setFixedSourceByFSR(100, 2, 0.5)
+    n_flux = ref.computeFlux(300, 1e-6)
+    phi_flux = ref.getFluxes().copy()
+    ref = OracleSolver(_tracks())
+    ref.setFixedSourceByFSR(3, 1, 1.0)
+    n_src = ref.computeSource(600, 3.0, 1e-4, TOTAL_SOURCE)
+    assert 2 < n_flux < 300 and 2 < n_src < 600
+    for r in range(2):
+        d = np.load(os.path.join(tmp_path, f"fixed{r}.npz"))
+        assert int(d["n_flux"]) == n_flux and int(d["n_src"]) == n_src
+        np.testing.assert_allclose(d["phi_flux"], phi_flux, rtol=1e-9, atol=1e-14)
+        np.testing.assert_allclose(d["phi_src"], ref.getFluxes(), rtol=1e-9, atol=1e-14)
+
+
 # ------------------------------------------------------------------ nccl / GPU
 def _gpu_worker(rank, world, port, out_dir, partition="pair"):
     import sys
