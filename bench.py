@@ -397,7 +397,7 @@ def measure(name, args, env, primary):
                    "n_fsrs": ft.n_fsrs, "groups": G, "fluxes_per_track": F,
                    "integrations_per_sweep": W_sweep,
                    "parallelism": "1 GPU" if world == 1 else f"{partition} partition x{world} + NCCL all-reduce of the FSR tally"
-                                  + (" + NCCL send/recv of cross-rank boundary fluxes" if partition in ("track", "block") else ""),
+                                  + (" + NCCL send/recv of cross-rank boundary fluxes" if partition in ("track", "block", "domain") else ""),
                    "deterministic_tally": bool(args.deterministic),
                    "l2": "segment stream (%.2f GB) is larger than the 126 MB L2; no flush" % (16.0 * n_seg / world / 1e9)
                          if 16.0 * n_seg / world > 2.5e8 else "inputs fit in L2; not flushed (launch-bound shape)",
@@ -615,7 +615,7 @@ def main():
     ap.add_argument("--azim", type=int, default=None)
     ap.add_argument("--spacing", type=float, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--partition", default="pair", choices=["pair", "chain", "track"])
+    ap.add_argument("--partition", default="pair", choices=["pair", "chain", "track", "domain"])
     ap.add_argument("--partition-3d", default="block", choices=["chain", "track", "block"])
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--no-group", action="store_true", help="skip the one-process all-GPU measurement at N > 1")

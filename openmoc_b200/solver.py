@@ -110,7 +110,11 @@ class B200Solver:
                                "track": single tracks dealt by length, any number of ranks, the
                                boundary fluxes that cross ranks are exchanged after every sweep
                                (NCCL send/recv); "block": the same exchange with contiguous blocks
-                               of the Track uid order per rank (3D decks: L2 locality of the FSR rows)
+                               of the Track uid order per rank (3D decks: L2 locality of the FSR rows);
+                               "domain": the reference's spatial decomposition (Geometry::setDomainDecomposition):
+                               `domains` = (nx, ny) boxes, one per rank, every track cut at the box faces, interface
+                               fluxes handed to the neighbouring box after every sweep and used one sweep later
+                               (openmoc_b200/domain.py; explicit 2D tracks)
     deterministic : bool       accumulate the FSR tally in 64-bit fixed point: results are
                                bitwise reproducible run to run (and across GPU counts)
     devices : optional         list of CUDA device ordinals: ONE solver handle drives them all (b200_set_devices);
@@ -130,7 +134,8 @@ class B200Solver:
     def __init__(self, tracks: FlatTracks, device: int = 0, precision: int = PRECISION_DOUBLE,
                  process_group=None, use_distributed: Optional[bool] = None, deterministic: bool = False,
                  partition: str = "pair", linear_source: bool = False,
-                 global_tracks: Optional[FlatTracks] = None, devices=None, cmfd: Optional[CmfdMesh] = None):
+                 global_tracks: Optional[FlatTracks] = None, devices=None, cmfd: Optional[CmfdMesh] = None,
+                 domains=None):
         self._lib = capi.load()
         self._cmfd = cmfd
         self._h = C.c_void_p()
@@ -176,8 +181,15 @@ class B200Solver:
                 from .partition import assign_blocks
                 tracks, self._plan = partition_by_track(tracks, self._world, owner=assign_blocks(tracks, self._world),
                                                         only=self._rank)[self._rank]
+            elif partition == "domain":
+                from .domain import partition_by_domain
+                try:
+                    tracks, self._plan = partition_by_domain(tracks, self._world, domains=domains,
+                                                             only=self._rank)[self._rank]
+                except ValueError as e:
+                    raise B200Error(str(e)) from None
             else:
-                raise B200Error("unknown partition %r (pair, chain, track, block)" % partition)
+                raise B200Error("unknown partition %r (pair, chain, track, block, domain)" % partition)
         if self._linear:
             self._ls_tables = (np.ascontiguousarray(tracks.arrays["seg_start"], dtype="f8"),
                                np.ascontiguousarray(track_directions(tracks).ravel(), dtype="f8"),
