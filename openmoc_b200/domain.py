@@ -16,7 +16,9 @@ directly).  As in the reference the flux crosses one box per sweep: the converge
 problem, the number of iterations grows slightly with the number of boxes.  FSR, material and quadrature data stay
 replicated (the FSR tally is summed over the ranks like in every other partition of `partition.py`).
 
-Explicit 2D track sets with `trk_start` / `trk_phi` (what `openmoc_b200.synth.make_tracks` and the track files carry).
+Explicit 2D and 3D track sets with `trk_start` / `trk_phi` (/ `trk_theta`): what `openmoc_b200.synth.make_tracks`,
+`make_tracks_3d(expand=True)` and the track files carry; 3D boxes are nx x ny x nz.  Axially traced 3D track sets
+(no explicit segments on the host) cannot be cut here: the device tracer walks a 3D track to the end of the geometry.
 """
 from __future__ import annotations
 
@@ -29,47 +31,60 @@ from .trackfile import FlatTracks, REFLECTIVE, PERIODIC
 PER_TRACK = ("trk_azim", "trk_polar", "trk_xy", "trk_phi", "trk_theta")
 
 
-def track_geometry_2d(ft: FlatTracks):
-    """start points [nt, 2], unit directions [nt, 2] and lengths [nt] of explicit 2D tracks"""
+def track_geometry(ft: FlatTracks):
+    """start points [nt, dim], unit directions [nt, dim] and lengths [nt] of explicit tracks (dim = 2 or 3)"""
     a = ft.arrays
     nt = ft.n_tracks
-    if ft.solve_3d or "trk_start" not in a or a["trk_start"].size != 2 * nt or "trk_phi" not in a:
-        raise ValueError("the domain decomposition needs explicit 2D tracks with trk_start and trk_phi")
+    dim = 3 if ft.solve_3d else 2
+    explicit = "trk_seg_offset" in a and a["trk_seg_offset"].size == nt + 1 and ft.n_segments > 0
+    if not explicit or "trk_start" not in a or a["trk_start"].size != dim * nt or "trk_phi" not in a \
+            or (dim == 3 and "trk_theta" not in a):
+        raise ValueError("the domain decomposition needs explicit tracks with trk_start and trk_phi (3D: trk_theta; "
+                         "axially traced track sets have no explicit segments to cut)")
     off = a["trk_seg_offset"].astype(np.int64)
     cum = np.concatenate(([0.0], np.cumsum(a["seg_length"].astype(np.longdouble))))
     length = (cum[off[1:]] - cum[off[:-1]]).astype(np.float64)
     phi = a["trk_phi"].astype(np.float64)
-    return a["trk_start"].reshape(nt, 2).astype(np.float64), np.stack([np.cos(phi), np.sin(phi)], axis=1), length
+    if dim == 2:
+        direction = np.stack([np.cos(phi), np.sin(phi)], axis=1)
+    else:
+        theta = a["trk_theta"].astype(np.float64)
+        direction = np.stack([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)], axis=1)
+    return a["trk_start"].reshape(nt, dim).astype(np.float64), direction, length
 
 
-def bounding_box(ft: FlatTracks) -> Tuple[float, float, float, float]:
-    """(xmin, xmax, ymin, ymax) of the geometry: every track starts and ends on its boundary"""
-    start, direction, length = track_geometry_2d(ft)
-    end = start + direction * length[:, None]
-    pts = np.concatenate([start, end])
-    return float(pts[:, 0].min()), float(pts[:, 0].max()), float(pts[:, 1].min()), float(pts[:, 1].max())
+track_geometry_2d = track_geometry
+
+
+def bounding_box(ft: FlatTracks):
+    """(xmin, xmax, ymin, ymax[, zmin, zmax]) of the geometry: every track starts and ends on its boundary"""
+    start, direction, length = track_geometry(ft)
+    pts = np.concatenate([start, start + direction * length[:, None]])
+    return tuple(float(f(pts[:, i])) for i in range(pts.shape[1]) for f in (np.min, np.max))
 
 
 def domain_planes(ft: FlatTracks, domains: Sequence[int]):
-    """interior cut planes of nx x ny equal boxes (Geometry::setDomainDecomposition makes equal boxes too)"""
-    nx, ny = int(domains[0]), int(domains[1])
-    if nx < 1 or ny < 1:
-        raise ValueError("the number of domains must be positive in every direction")
-    xmin, xmax, ymin, ymax = bounding_box(ft)
-    xs = xmin + (xmax - xmin) * np.arange(1, nx) / nx
-    ys = ymin + (ymax - ymin) * np.arange(1, ny) / ny
-    return xs, ys, (xmin, xmax, ymin, ymax)
+    """interior cut planes of nx x ny (x nz) equal boxes (Geometry::setDomainDecomposition makes equal boxes too):
+    one array per axis, and the bounding box"""
+    dim = 3 if ft.solve_3d else 2
+    n = [int(x) for x in domains] + [1] * (dim - len(domains))
+    if len(n) != dim or min(n) < 1:
+        raise ValueError("the number of domains must be positive in each of the %d directions" % dim)
+    box = bounding_box(ft)
+    planes = tuple(box[2 * i] + (box[2 * i + 1] - box[2 * i]) * np.arange(1, n[i]) / n[i] for i in range(dim))
+    return planes + (box,) if dim == 3 else (planes[0], planes[1], box)
 
 
-def split_tracks_2d(ft: FlatTracks, x_planes, y_planes, eps: float = None) -> FlatTracks:
-    """Cut every track at the planes x = X and y = Y.  Returns a track set with one track per piece, in the order
+def split_tracks(ft: FlatTracks, x_planes, y_planes, z_planes=(), eps: float = None) -> FlatTracks:
+    """Cut every track at the planes x = X, y = Y (and, 3D tracks, z = Z).  Returns a track set with one track per piece, in the order
     of the original tracks and along them; `piece_of` (original track of every piece) and `piece_d0` / `piece_d1`
     (distances from the original track's start) are added to its arrays.  A cut that falls on a segment boundary
     (the usual case: box faces are lattice-cell faces) splits no segment; otherwise the segment is split in two
     with the same FSR, like the reference does when it ray-traces every box on its own."""
     a = ft.arrays
     nt, ns = ft.n_tracks, ft.n_segments
-    start, direction, tlen = track_geometry_2d(ft)
+    start, direction, tlen = track_geometry(ft)
+    dim = start.shape[1]
     off = a["trk_seg_offset"].astype(np.int64)
     seg_len = a["seg_length"].astype(np.float64)
     if eps is None:
@@ -77,7 +92,11 @@ def split_tracks_2d(ft: FlatTracks, x_planes, y_planes, eps: float = None) -> Fl
 
     # ---- cuts: (track, distance from its start), sorted along the tracks, one per crossing point
     cut_t, cut_d = [np.zeros(0, np.int64)], [np.zeros(0)]
-    for axis, planes in ((0, x_planes), (1, y_planes)):
+    for axis, planes in ((0, x_planes), (1, y_planes), (2, z_planes)):
+        if axis >= dim:
+            if np.size(planes):
+                raise ValueError("z planes need 3D tracks")
+            continue
         for plane in np.asarray(planes, dtype=np.float64).ravel():
             with np.errstate(divide="ignore", invalid="ignore"):
                 d = (plane - start[:, axis]) / direction[:, axis]
@@ -138,7 +157,7 @@ def split_tracks_2d(ft: FlatTracks, x_planes, y_planes, eps: float = None) -> Fl
     if "seg_start" in a and a["seg_start"].size == 3 * ns:
         s0 = a["seg_start"].reshape(ns, 3)[orig].astype(np.float64)
         trk_of_seg = np.repeat(np.arange(nt, dtype=np.int64), np.diff(off))[orig]
-        s0[:, :2] += direction[trk_of_seg] * lo[:, None]
+        s0[:, :dim] += direction[trk_of_seg] * lo[:, None]
         b["seg_start"] = s0.ravel()
 
     # ---- new tracks: piece j of track t has the id t + (cuts in earlier tracks) + j
@@ -166,6 +185,13 @@ def split_tracks_2d(ft: FlatTracks, x_planes, y_planes, eps: float = None) -> Fl
         if key in a and a[key].size == nt:
             b[key] = a[key][piece_of]
     b["trk_start"] = (start[piece_of] + direction[piece_of] * d0[:, None]).ravel()
+    if dim == 3:
+        b["trk_end"] = (start[piece_of] + direction[piece_of] * d1[:, None]).ravel()
+        for key in ("trk_2d", "trk_lz"):
+            if key in a and a[key].size == nt:
+                b[key] = a[key][piece_of]
+        if "trk_l0" in a and a["trk_l0"].size == nt:        # distance of the start point along the 2D track
+            b["trk_l0"] = a["trk_l0"][piece_of] + d0 * np.hypot(direction[piece_of, 0], direction[piece_of, 1])
 
     # ---- links: inside a track piece to piece, at its two ends the original hand-offs, to the piece that holds the
     # entered end of the target track
@@ -185,26 +211,32 @@ def split_tracks_2d(ft: FlatTracks, x_planes, y_planes, eps: float = None) -> Fl
         flags = np.where(at_end_of_track, flags, (flags & ~bit) | inner_bit).astype(np.uint8)
     b["trk_flags"] = flags
     for key, v in a.items():
-        if key.startswith(("quad_", "fsr_", "mat_")):
+        if key.startswith(("quad_", "fsr_", "mat_")) or key == "z_mesh":
             b[key] = v
     return out
 
 
 def assign_domains(split: FlatTracks, box, domains: Sequence[int]) -> np.ndarray:
-    """Box of every piece (by its midpoint), numbered x fastest: the owner rank of `partition_by_track`"""
-    nx, ny = int(domains[0]), int(domains[1])
-    xmin, xmax, ymin, ymax = box
+    """Box of every piece (by its midpoint), numbered x fastest, then y, then z: the owner rank of
+    `partition_by_track`"""
+    start, direction, _ = track_geometry(split)
+    dim = start.shape[1]
+    n = [int(x) for x in domains] + [1] * (dim - len(domains))
     a = split.arrays
-    phi = a["trk_phi"].astype(np.float64)
-    half = 0.5 * (a["piece_d1"] - a["piece_d0"])
-    mid = a["trk_start"].reshape(-1, 2) + np.stack([np.cos(phi), np.sin(phi)], axis=1) * half[:, None]
-    ix = np.clip(np.floor((mid[:, 0] - xmin) / (xmax - xmin) * nx), 0, nx - 1).astype(np.int64)
-    iy = np.clip(np.floor((mid[:, 1] - ymin) / (ymax - ymin) * ny), 0, ny - 1).astype(np.int64)
-    return ix + nx * iy
+    mid = start + direction * (0.5 * (a["piece_d1"] - a["piece_d0"]))[:, None]
+    owner, stride = np.zeros(split.n_tracks, dtype=np.int64), 1
+    for i in range(dim):
+        lo, hi = box[2 * i], box[2 * i + 1]
+        owner += stride * np.clip(np.floor((mid[:, i] - lo) / (hi - lo) * n[i]), 0, n[i] - 1).astype(np.int64)
+        stride *= n[i]
+    return owner
 
 
-def default_domains(world: int) -> Tuple[int, int]:
-    """nx x ny = world, as square as it gets (8 -> 4 x 2)"""
+def default_domains(world: int, dim: int = 2) -> Tuple[int, ...]:
+    """nx x ny (x nz) = world, as square / cubic as it gets (2D: 8 -> 4 x 2; 3D: 8 -> 2 x 2 x 2)"""
+    if dim == 3:
+        nz = max(d for d in range(1, int(np.floor(world ** (1.0 / 3.0) + 1e-9)) + 1) if world % d == 0)
+        return default_domains(world // nz, 2) + (nz,)
     ny = int(np.floor(np.sqrt(world)))
     while world % ny:
         ny -= 1
@@ -213,12 +245,16 @@ def default_domains(world: int) -> Tuple[int, int]:
 
 def partition_by_domain(ft: FlatTracks, world: int, domains: Sequence[int] = None, only: int = None):
     """[(FlatTracks, ExchangePlan)] per rank: rank r sweeps the pieces of the tracks inside box r.  `domains`
-    (nx, ny) defaults to the squarest factorisation of `world`."""
+    (nx, ny) / (nx, ny, nz) defaults to the squarest / most cubic factorisation of `world`."""
     from .partition import partition_by_track
-    domains = default_domains(world) if domains is None else tuple(int(x) for x in domains)
-    if domains[0] * domains[1] != world:
-        raise ValueError("%d x %d domains for %d ranks" % (domains[0], domains[1], world))
-    xs, ys, box = domain_planes(ft, domains)
-    split = split_tracks_2d(ft, xs, ys)
+    dim = 3 if ft.solve_3d else 2
+    domains = default_domains(world, dim) if domains is None else tuple(int(x) for x in domains)
+    if len(domains) > dim or int(np.prod(domains)) != world:
+        raise ValueError("%s domains for %d ranks of a %dD problem" % (" x ".join(map(str, domains)), world, dim))
+    *planes, box = domain_planes(ft, domains)
+    split = split_tracks(ft, *planes)
     owner = assign_domains(split, box, domains)
     return partition_by_track(split, world, owner=owner, only=only)
+
+
+split_tracks_2d = split_tracks

@@ -112,9 +112,9 @@ class B200Solver:
                                (NCCL send/recv); "block": the same exchange with contiguous blocks
                                of the Track uid order per rank (3D decks: L2 locality of the FSR rows);
                                "domain": the reference's spatial decomposition (Geometry::setDomainDecomposition):
-                               `domains` = (nx, ny) boxes, one per rank, every track cut at the box faces, interface
-                               fluxes handed to the neighbouring box after every sweep and used one sweep later
-                               (openmoc_b200/domain.py; explicit 2D tracks)
+                               `domains` = (nx, ny[, nz]) boxes, one per rank, every track cut at the box faces,
+                               interface fluxes handed to the neighbouring box after every sweep and used one sweep
+                               later (openmoc_b200/domain.py; explicit 2D / 3D tracks)
     deterministic : bool       accumulate the FSR tally in 64-bit fixed point: results are
                                bitwise reproducible run to run (and across GPU counts)
     devices : optional         list of CUDA device ordinals: ONE solver handle drives them all (b200_set_devices);

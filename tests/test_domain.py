@@ -218,6 +218,50 @@ def test_boxes_on_ranks_equal_the_cut_tracks_in_one_process():
     assert sum(sub.n_segments for sub, _ in parts) == split_tracks_2d(ft, xs, ys).n_segments
 
 
+# ------------------------------------------------------------------ 3D: nx x ny x nz boxes of explicit 3D tracks
+def lattice3d():
+    from openmoc_b200.synth import make_tracks_3d
+    return make_tracks_3d("simple-lattice", num_azim=4, spacing=0.24, num_polar=2, z_spacing=0.9, n_axial=2, expand=True)
+
+
+def test_3d_tracks_are_cut_into_2x2x2_boxes():
+    from openmoc_b200.domain import split_tracks
+    ft = lattice3d()
+    xs, ys, zs, box = domain_planes(ft, (2, 2, 2))
+    assert len(box) == 6 and xs.size == ys.size == zs.size == 1
+    sp = split_tracks(ft, xs, ys, zs)
+    sp.validate()
+    np.testing.assert_allclose(fsr_track_length(sp), fsr_track_length(ft), rtol=1e-12)
+    owner = assign_domains(sp, box, (2, 2, 2))
+    assert set(np.unique(owner)) == set(range(8))
+    start, direction, length = track_geometry_2d(sp)
+    end = start + direction * length[:, None]
+    np.testing.assert_allclose(end.ravel(), sp.arrays["trk_end"], atol=1e-9)
+    idx = np.stack([owner % 2, owner // 2 % 2, owner // 4], axis=1)
+    for i in range(3):
+        lo, w = box[2 * i], (box[2 * i + 1] - box[2 * i]) / 2
+        for pts in (start, end):
+            assert np.all(pts[:, i] >= lo + idx[:, i] * w - 1e-8) and np.all(pts[:, i] <= lo + (idx[:, i] + 1) * w + 1e-8)
+    assert default_domains(8, 3) == (2, 2, 2) and default_domains(4, 3) == (2, 2, 1) and default_domains(2, 3) == (2, 1, 1)
+    with pytest.raises(ValueError):
+        split_tracks(lattice(), [], [], [0.0])               # z planes need 3D tracks
+    from openmoc_b200.synth import make_tracks_3d
+    with pytest.raises(ValueError):                          # axially traced set: nothing to cut on the host
+        partition_by_domain(make_tracks_3d("simple-lattice", num_azim=4, spacing=0.24, num_polar=2, z_spacing=0.9,
+                                           n_axial=2, expand=False), 2)
+
+
+def test_3d_decomposed_solve_converges_to_the_undivided_solution():
+    from oracle.oracle_py import OracleSolver, FISSION_SOURCE
+    ft = lattice3d()
+    ref = OracleSolver(ft)
+    n_ref = ref.computeEigenvalue(2000, 1e-9, FISSION_SOURCE)
+    k, phi, iters, parts = simulate(ft, 8, None, 2000, 1e-9)
+    assert n_ref <= iters <= 1.3 * n_ref
+    assert abs(k - ref.getKeff()) * 1e5 < 0.05
+    assert np.max(np.abs(phi - ref.getFluxes()) / ref.getFluxes()) < 2e-6
+
+
 # ------------------------------------------------------------------ the same over gloo, one process per box
 def _free_port():
     s = socket.socket()

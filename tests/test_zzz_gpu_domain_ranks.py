@@ -56,3 +56,19 @@ def test_boxes_on_the_gpu_follow_the_oracle(model, azim, spacing, world, domains
     k_cpu, phi_cpu = run_boxes(OracleSolver, parts, F, 10)
     assert abs(k_gpu - k_cpu) * 1e5 < 1e-3                      # pcm
     np.testing.assert_allclose(phi_gpu, phi_cpu, rtol=1e-6, atol=1e-12)
+
+
+def test_3d_boxes_on_the_gpu_follow_the_oracle():
+    """2 x 2 x 2 boxes of an explicit 3D track set (the decomposition of configs[4], profile/models/c5g7/
+    c5g7-3d-cmfd.cpp:557 `geometry.setDomainDecomposition(nx, ny, nz, ...)`, on the simple lattice)"""
+    from openmoc_b200.domain import partition_by_domain
+    from openmoc_b200.solver import B200Solver
+    from openmoc_b200.synth import make_tracks_3d
+    from oracle.oracle_py import OracleSolver
+    ft = make_tracks_3d("simple-lattice", num_azim=4, spacing=0.24, num_polar=2, z_spacing=0.9, n_axial=2, expand=True)
+    parts = partition_by_domain(ft, 8)
+    F = ft.fluxes_per_track
+    k_gpu, phi_gpu = run_boxes(lambda sub: B200Solver(sub, global_tracks=ft), parts, F, 10)
+    k_cpu, phi_cpu = run_boxes(OracleSolver, parts, F, 10)
+    assert abs(k_gpu - k_cpu) * 1e5 < 1e-3
+    np.testing.assert_allclose(phi_gpu, phi_cpu, rtol=1e-6, atol=1e-12)
