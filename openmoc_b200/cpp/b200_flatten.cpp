@@ -86,6 +86,13 @@ class FlattenPass : public TraverseSegments {
       _out->trk_polar[id] = tt3 ? tt3->getPolarIndex() : 0;
       _out->trk_phi[id] = t->getPhi();
       _out->trk_theta[id] = tt3 ? tt3->getTheta() : M_PI_2;
+      {
+        const size_t dim = _out->solve_3d ? 3 : 2;
+        Point* p0 = t->getStart();
+        _out->trk_start[dim * id] = p0->getX();
+        _out->trk_start[dim * id + 1] = p0->getY();
+        if (dim == 3) _out->trk_start[dim * id + 2] = p0->getZ();
+      }
       _out->trk_next_fwd[id] = t->getTrackNextFwd();
       _out->trk_next_bwd[id] = t->getTrackNextBwd();
       _out->trk_flags[id] = (t->getNextFwdFwd() ? 1 : 0) | (t->getNextBwdFwd() ? 2 : 0);
@@ -275,6 +282,9 @@ void flatten_for_device_tracer(TrackGenerator3D* tg3, B200FlatTracks* ft) {
           ft->trk_2d[id] = (int32_t)flat2d->getUid();
           ft->trk_l0[id] = (t.getStart()->getX() - flat2d->getStart()->getX()) / cos_phi;
           ft->trk_z0[id] = t.getStart()->getZ();
+          ft->trk_start[3 * id] = t.getStart()->getX();
+          ft->trk_start[3 * id + 1] = t.getStart()->getY();
+          ft->trk_start[3 * id + 2] = t.getStart()->getZ();
         }
     }
   }
@@ -378,6 +388,7 @@ void b200_flatten(TrackGenerator* tg, B200FlatTracks* ft, bool with_ls_data, boo
   ft->trk_next_fwd.assign(nt, -1); ft->trk_next_bwd.assign(nt, -1);
   ft->trk_flags.assign(nt, 0); ft->trk_bc_fwd.assign(nt, 0); ft->trk_bc_bwd.assign(nt, 0);
   ft->trk_phi.assign(nt, 0.); ft->trk_theta.assign(nt, 0.);
+  ft->trk_start.assign(nt * (ft->solve_3d ? 3 : 2), 0.);
 
   ft->device_otf = false;
   if (device_otf && b200_can_trace_on_device(tg)) {
@@ -489,7 +500,7 @@ void b200_write_trackfile(const B200FlatTracks& ft, const std::string& path, con
   w.v("trk_azim", ft.trk_azim); w.v("trk_polar", ft.trk_polar); w.v("trk_xy", ft.trk_xy);
   w.v("trk_next_fwd", ft.trk_next_fwd); w.v("trk_next_bwd", ft.trk_next_bwd);
   w.v("trk_flags", ft.trk_flags); w.v("trk_bc_fwd", ft.trk_bc_fwd); w.v("trk_bc_bwd", ft.trk_bc_bwd);
-  w.v("trk_phi", ft.trk_phi); w.v("trk_theta", ft.trk_theta);
+  w.v("trk_phi", ft.trk_phi); w.v("trk_theta", ft.trk_theta); w.v("trk_start", ft.trk_start);
   w.v("quad_weight", ft.quad_weight); w.v("quad_sin_theta", ft.quad_sin_theta);
   w.v("quad_azim_spacing", ft.quad_azim_spacing); w.v("quad_azim_weight", ft.quad_azim_weight);
   w.v("quad_polar_spacing", ft.quad_polar_spacing); w.v("quad_polar_weight", ft.quad_polar_weight);

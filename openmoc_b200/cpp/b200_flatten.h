@@ -48,6 +48,8 @@ struct B200FlatTracks {
   std::vector<uint8_t> trk_flags;   /* bit0 next_fwd_is_fwd, bit1 next_bwd_is_fwd */
   std::vector<uint8_t> trk_bc_fwd, trk_bc_bwd;  /* boundaryType enum values */
   std::vector<double> trk_phi, trk_theta;
+  std::vector<double> trk_start;   /* start point of every track, xy (2D) or xyz (3D): what a spatial domain
+                                    * decomposition cuts the tracks with (openmoc_b200/domain.py) */
 
   /* quadrature: [A/2][P] total weights, [A/2][P] sin(theta) */
   std::vector<double> quad_weight, quad_sin_theta;

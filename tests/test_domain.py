@@ -262,6 +262,50 @@ def test_3d_decomposed_solve_converges_to_the_undivided_solution():
     assert np.max(np.abs(phi - ref.getFluxes()) / ref.getFluxes()) < 2e-6
 
 
+# ------------------------------------------------------------------ tracks of the reference's own ray tracer
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+
+def reference_tracks(tmp_path, name, args):
+    import subprocess
+    from openmoc_b200.trackfile import read_trackfile
+    if not os.path.exists(DRIVER):
+        pytest.skip("oracle/_ref/ref_driver not built")
+    trk = os.path.join(tmp_path, name + ".b2trk")
+    subprocess.run([DRIVER] + args + ["--quiet", "--max-iters", "1", "--dump-tracks", trk,
+                                      "--json", os.path.join(tmp_path, name + ".json")],
+                   check=True, capture_output=True, cwd=tmp_path)
+    return read_trackfile(trk)
+
+
+def test_reference_track_dumps_are_cut_into_boxes(tmp_path):
+    """Track files dumped from the reference's TrackGenerator / TrackGenerator3D carry the start point of every track
+    (trk_start, b200_flatten.cpp): the decomposition applies to real OpenMOC geometries, 2D and 3D."""
+    from oracle.oracle_py import OracleSolver, FISSION_SOURCE
+    ft = reference_tracks(tmp_path, "sl", ["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12"])
+    assert ft.arrays["trk_start"].size == 2 * ft.n_tracks
+    ref = OracleSolver(ft)
+    n_ref = ref.computeEigenvalue(3000, 1e-9, FISSION_SOURCE)
+    k, phi, iters, _ = simulate(ft, 4, None, 3000, 1e-9)
+    assert n_ref <= iters <= 1.3 * n_ref and abs(k - ref.getKeff()) * 1e5 < 0.05
+    assert np.max(np.abs(phi - ref.getFluxes()) / ref.getFluxes()) < 2e-6
+
+    ft = reference_tracks(tmp_path, "l3", ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2",
+                                           "--spacing", "0.24", "--zspacing", "0.9"])
+    assert ft.solve_3d and ft.arrays["trk_start"].size == 3 * ft.n_tracks
+    from openmoc_b200.domain import split_tracks
+    *planes, box = domain_planes(ft, (2, 2, 2))
+    np.testing.assert_allclose(box, (-2, 2, -2, 2, -5, 5), atol=1e-9)
+    sp = split_tracks(ft, *planes)
+    sp.validate()
+    np.testing.assert_allclose(fsr_track_length(sp), fsr_track_length(ft), rtol=1e-12)
+    one = OracleSolver(sp)
+    one.computeEigenvalue(6, 1e-30, FISSION_SOURCE)
+    k, phi, iters, parts = simulate(ft, 8, (2, 2, 2), 6, 1e-30)
+    assert abs(k - one.getKeff()) < 1e-12
+    np.testing.assert_allclose(phi, one.getFluxes(), rtol=1e-10, atol=1e-14)
+
+
 # ------------------------------------------------------------------ the same over gloo, one process per box
 def _free_port():
     s = socket.socket()
