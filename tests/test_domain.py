@@ -218,6 +218,31 @@ def test_boxes_on_ranks_equal_the_cut_tracks_in_one_process():
     assert sum(sub.n_segments for sub, _ in parts) == split_tracks_2d(ft, xs, ys).n_segments
 
 
+def test_linear_source_on_cut_tracks():
+    """CPULSSolver physics on the cut tracks (one process): box faces on lattice-cell faces split no segment - same
+    pre-pass tables, same converged solution; a face inside FSRs splits segments, which refines the linear-source
+    discretisation exactly like the reference's own per-box ray tracing (and its optical-length cuts) does: the
+    geometric table is unchanged, the per-segment source constants and the solution move within the north-star
+    tolerance (1 pcm, 1e-4)."""
+    from oracle.oracle_py import OracleSolver, FISSION_SOURCE
+    ft = lattice(linear_source=True)
+    ref = OracleSolver(ft, linear_source=True)
+    ref.computeEigenvalue(3000, 1e-9, FISSION_SOURCE)
+    xs, ys, box = domain_planes(ft, (2, 2))
+    inside = ([box[0] + 0.37 * (box[1] - box[0])], [box[2] + 0.61 * (box[3] - box[2])])
+    for planes, aligned in (((xs, ys), True), (inside, False)):
+        sp = split_tracks_2d(ft, *planes)
+        assert (sp.n_segments == ft.n_segments) == aligned
+        s = OracleSolver(sp, linear_source=True)
+        s.computeEigenvalue(3000, 1e-9, FISSION_SOURCE)
+        (lin_a, con_a), (lin_b, con_b) = ref.getLinearSourceTables(), s.getLinearSourceTables()
+        np.testing.assert_allclose(lin_b, lin_a, rtol=0, atol=1e-9)
+        if aligned:
+            assert np.array_equal(con_a, con_b)
+        assert abs(s.getKeff() - ref.getKeff()) * 1e5 < (0.05 if aligned else 1.0)
+        assert np.max(np.abs(s.getFluxes() - ref.getFluxes()) / ref.getFluxes()) < (2e-6 if aligned else 1e-4)
+
+
 # ------------------------------------------------------------------ 3D: nx x ny x nz boxes of explicit 3D tracks
 def lattice3d():
     from openmoc_b200.synth import make_tracks_3d
