@@ -276,7 +276,8 @@ def measure(name, args, env, primary):
     t0 = time.perf_counter()
     solver = B200Solver(ft, device=local_rank, precision=precision,
                         process_group=(dist.group.WORLD if world > 1 else None),
-                        partition=partition, deterministic=args.deterministic)
+                        partition=partition, deterministic=args.deterministic,
+                        balance_domains=args.balance_domains)
     solver.useTorchStream()
     t_setup = time.perf_counter() - t0
     local_seg = solver.num_segments
@@ -618,6 +619,8 @@ def main():
     ap.add_argument("--partition", default="pair", choices=["pair", "chain", "track", "domain"])
     ap.add_argument("--partition-3d", default="block", choices=["chain", "track", "block"])
     ap.add_argument("--deterministic", action="store_true")
+    ap.add_argument("--balance-domains", action="store_true",
+                    help="--partition domain: box faces at the quantiles of the segment count instead of equal boxes")
     ap.add_argument("--no-group", action="store_true", help="skip the one-process all-GPU measurement at N > 1")
     ap.add_argument("--no-cmfd", action="store_true", help="skip the CMFD-accelerated time-to-solution blocks")
     ap.add_argument("--group-cmfd", action="store_true",

@@ -63,16 +63,39 @@ def bounding_box(ft: FlatTracks):
     return tuple(float(f(pts[:, i])) for i in range(pts.shape[1]) for f in (np.min, np.max))
 
 
-def domain_planes(ft: FlatTracks, domains: Sequence[int]):
-    """interior cut planes of nx x ny (x nz) equal boxes (Geometry::setDomainDecomposition makes equal boxes too):
-    one array per axis, and the bounding box"""
+def domain_planes(ft: FlatTracks, domains: Sequence[int], balance: bool = False):
+    """Interior cut planes of nx x ny (x nz) boxes, one array per axis, and the bounding box.  Equal boxes, as
+    Geometry::setDomainDecomposition makes them; `balance`: planes at the quantiles of the segment count along
+    every axis instead, so that the boxes of a core with a reflector hold about the same number of segments (the
+    2D C5G7 quarter core in 4 x 2 equal boxes: 0.59 - 1.36 of the mean)."""
     dim = 3 if ft.solve_3d else 2
     n = [int(x) for x in domains] + [1] * (dim - len(domains))
     if len(n) != dim or min(n) < 1:
         raise ValueError("the number of domains must be positive in each of the %d directions" % dim)
     box = bounding_box(ft)
-    planes = tuple(box[2 * i] + (box[2 * i + 1] - box[2 * i]) * np.arange(1, n[i]) / n[i] for i in range(dim))
-    return planes + (box,) if dim == 3 else (planes[0], planes[1], box)
+    if balance:
+        mid = segment_midpoints(ft)
+        planes = []
+        for i in range(dim):
+            hist, edges = np.histogram(mid[:, i], bins=4096, range=(box[2 * i], box[2 * i + 1]))
+            cdf = np.concatenate(([0.0], np.cumsum(hist))) / max(hist.sum(), 1)
+            planes.append(np.interp(np.arange(1, n[i]) / n[i], cdf, edges))
+        planes = tuple(planes)
+    else:
+        planes = tuple(box[2 * i] + (box[2 * i + 1] - box[2 * i]) * np.arange(1, n[i]) / n[i] for i in range(dim))
+    return planes + (box,)
+
+
+def segment_midpoints(ft: FlatTracks) -> np.ndarray:
+    """[n_segments, dim] midpoint of every segment"""
+    start, direction, _ = track_geometry(ft)
+    a = ft.arrays
+    off = a["trk_seg_offset"].astype(np.int64)
+    seg_len = a["seg_length"].astype(np.float64)
+    cum0 = np.concatenate(([np.longdouble(0)], np.cumsum(seg_len.astype(np.longdouble))))
+    trk = np.repeat(np.arange(ft.n_tracks, dtype=np.int64), np.diff(off))
+    along = (cum0[:-1] - cum0[off[trk]]).astype(np.float64) + 0.5 * seg_len
+    return start[trk] + direction[trk] * along[:, None]
 
 
 def split_tracks(ft: FlatTracks, x_planes, y_planes, z_planes=(), eps: float = None) -> FlatTracks:
@@ -216,19 +239,17 @@ def split_tracks(ft: FlatTracks, x_planes, y_planes, z_planes=(), eps: float = N
     return out
 
 
-def assign_domains(split: FlatTracks, box, domains: Sequence[int]) -> np.ndarray:
-    """Box of every piece (by its midpoint), numbered x fastest, then y, then z: the owner rank of
-    `partition_by_track`"""
+def assign_domains(split: FlatTracks, planes) -> np.ndarray:
+    """Box of every piece (by its midpoint; `planes`: the cut planes per axis), numbered x fastest, then y, then z:
+    the owner rank of `partition_by_track`"""
     start, direction, _ = track_geometry(split)
-    dim = start.shape[1]
-    n = [int(x) for x in domains] + [1] * (dim - len(domains))
     a = split.arrays
     mid = start + direction * (0.5 * (a["piece_d1"] - a["piece_d0"]))[:, None]
     owner, stride = np.zeros(split.n_tracks, dtype=np.int64), 1
-    for i in range(dim):
-        lo, hi = box[2 * i], box[2 * i + 1]
-        owner += stride * np.clip(np.floor((mid[:, i] - lo) / (hi - lo) * n[i]), 0, n[i] - 1).astype(np.int64)
-        stride *= n[i]
+    for i, cuts in enumerate(planes):
+        cuts = np.asarray(cuts, dtype=np.float64)
+        owner += stride * np.searchsorted(cuts, mid[:, i], side="right")
+        stride *= cuts.size + 1
     return owner
 
 
@@ -243,18 +264,19 @@ def default_domains(world: int, dim: int = 2) -> Tuple[int, ...]:
     return world // ny, ny
 
 
-def partition_by_domain(ft: FlatTracks, world: int, domains: Sequence[int] = None, only: int = None):
+def partition_by_domain(ft: FlatTracks, world: int, domains: Sequence[int] = None, only: int = None,
+                        balance: bool = False):
     """[(FlatTracks, ExchangePlan)] per rank: rank r sweeps the pieces of the tracks inside box r.  `domains`
-    (nx, ny) / (nx, ny, nz) defaults to the squarest / most cubic factorisation of `world`."""
+    (nx, ny) / (nx, ny, nz) defaults to the squarest / most cubic factorisation of `world`; `balance`: see
+    `domain_planes`."""
     from .partition import partition_by_track
     dim = 3 if ft.solve_3d else 2
     domains = default_domains(world, dim) if domains is None else tuple(int(x) for x in domains)
     if len(domains) > dim or int(np.prod(domains)) != world:
         raise ValueError("%s domains for %d ranks of a %dD problem" % (" x ".join(map(str, domains)), world, dim))
-    *planes, box = domain_planes(ft, domains)
+    *planes, _ = domain_planes(ft, domains, balance)
     split = split_tracks(ft, *planes)
-    owner = assign_domains(split, box, domains)
-    return partition_by_track(split, world, owner=owner, only=only)
+    return partition_by_track(split, world, owner=assign_domains(split, planes), only=only)
 
 
 split_tracks_2d = split_tracks

@@ -114,7 +114,8 @@ class B200Solver:
                                "domain": the reference's spatial decomposition (Geometry::setDomainDecomposition):
                                `domains` = (nx, ny[, nz]) boxes, one per rank, every track cut at the box faces,
                                interface fluxes handed to the neighbouring box after every sweep and used one sweep
-                               later (openmoc_b200/domain.py; explicit 2D / 3D tracks)
+                               later (openmoc_b200/domain.py; explicit 2D / 3D tracks); `balance_domains`: box faces
+                               at the quantiles of the segment count instead of equal boxes
     deterministic : bool       accumulate the FSR tally in 64-bit fixed point: results are
                                bitwise reproducible run to run (and across GPU counts)
     devices : optional         list of CUDA device ordinals: ONE solver handle drives them all (b200_set_devices);
@@ -135,7 +136,7 @@ class B200Solver:
                  process_group=None, use_distributed: Optional[bool] = None, deterministic: bool = False,
                  partition: str = "pair", linear_source: bool = False,
                  global_tracks: Optional[FlatTracks] = None, devices=None, cmfd: Optional[CmfdMesh] = None,
-                 domains=None):
+                 domains=None, balance_domains: bool = False):
         self._lib = capi.load()
         self._cmfd = cmfd
         self._h = C.c_void_p()
@@ -184,8 +185,8 @@ class B200Solver:
             elif partition == "domain":
                 from .domain import partition_by_domain
                 try:
-                    tracks, self._plan = partition_by_domain(tracks, self._world, domains=domains,
-                                                             only=self._rank)[self._rank]
+                    tracks, self._plan = partition_by_domain(tracks, self._world, domains=domains, only=self._rank,
+                                                             balance=balance_domains)[self._rank]
                 except ValueError as e:
                     raise B200Error(str(e)) from None
             else:

@@ -70,7 +70,7 @@ def test_split_keeps_every_track_and_cuts_it_at_the_planes(deck, domains):
         # the ends of the track keep their boundary conditions
         assert b["trk_bc_bwd"][first[t]] == a["trk_bc_bwd"][t] and b["trk_bc_fwd"][p] == a["trk_bc_fwd"][t]
     # every piece lies inside one box
-    owner = assign_domains(sp, box, domains)
+    owner = assign_domains(sp, (xs, ys))
     assert set(np.unique(owner)) == set(range(domains[0] * domains[1]))
     start, direction, length = track_geometry_2d(sp)
     end = start + direction * length[:, None]
@@ -141,11 +141,11 @@ def test_a_plane_inside_segments_splits_them():
 
 
 # ------------------------------------------------------------------ physics: the oracle on the decomposed tracks
-def simulate(ft, world, domains, max_iters, tol):
+def simulate(ft, world, domains, max_iters, tol, balance=False):
     """All ranks of partition_by_domain in one process: sweep per box, sum of the FSR tallies, interface fluxes moved
     by hand with the plan's index lists (what exchange_boundary_fluxes does over NCCL)."""
     from oracle.oracle_py import OracleSolver, FISSION_SOURCE
-    parts = partition_by_domain(ft, world, domains)
+    parts = partition_by_domain(ft, world, domains, balance=balance)
     F = ft.fluxes_per_track
     solvers = [OracleSolver(sub) for sub, _ in parts]
     plans = [p for _, p in parts]
@@ -218,6 +218,27 @@ def test_boxes_on_ranks_equal_the_cut_tracks_in_one_process():
     assert sum(sub.n_segments for sub, _ in parts) == split_tracks_2d(ft, xs, ys).n_segments
 
 
+def test_balanced_boxes_hold_about_the_same_number_of_segments():
+    """C5G7 quarter core (dense fuel block, sparse reflector): equal boxes are unbalanced, planes at the quantiles of
+    the segment count are not; the decomposed iteration is the same whatever the planes"""
+    from oracle.oracle_py import OracleSolver, FISSION_SOURCE
+    ft = c5g7()
+
+    def spread(balance):
+        parts = partition_by_domain(ft, 8, (4, 2), balance=balance)
+        n = np.array([sub.n_segments for sub, _ in parts], dtype=float)
+        return n.max() / n.mean(), parts
+    equal, _ = spread(False)
+    balanced, parts = spread(True)
+    assert equal > 1.25 and balanced < 1.12
+    *planes, _ = domain_planes(ft, (4, 2), balance=True)
+    one = OracleSolver(split_tracks_2d(ft, *planes))
+    one.computeEigenvalue(5, 1e-30, FISSION_SOURCE)
+    k, phi, iters, _ = simulate(ft, 8, (4, 2), 5, 1e-30, balance=True)
+    assert abs(k - one.getKeff()) < 1e-12
+    np.testing.assert_allclose(phi, one.getFluxes(), rtol=1e-10, atol=1e-14)
+
+
 def test_linear_source_on_cut_tracks():
     """CPULSSolver physics on the cut tracks (one process): box faces on lattice-cell faces split no segment - same
     pre-pass tables, same converged solution; a face inside FSRs splits segments, which refines the linear-source
@@ -257,7 +278,7 @@ def test_3d_tracks_are_cut_into_2x2x2_boxes():
     sp = split_tracks(ft, xs, ys, zs)
     sp.validate()
     np.testing.assert_allclose(fsr_track_length(sp), fsr_track_length(ft), rtol=1e-12)
-    owner = assign_domains(sp, box, (2, 2, 2))
+    owner = assign_domains(sp, (xs, ys, zs))
     assert set(np.unique(owner)) == set(range(8))
     start, direction, length = track_geometry_2d(sp)
     end = start + direction * length[:, None]
