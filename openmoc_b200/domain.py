@@ -99,9 +99,9 @@ def segment_midpoints(ft: FlatTracks) -> np.ndarray:
 
 
 def split_tracks(ft: FlatTracks, x_planes, y_planes, z_planes=(), eps: float = None) -> FlatTracks:
-    """Cut every track at the planes x = X, y = Y (and, 3D tracks, z = Z).  Returns a track set with one track per piece, in the order
-    of the original tracks and along them; `piece_of` (original track of every piece) and `piece_d0` / `piece_d1`
-    (distances from the original track's start) are added to its arrays.  A cut that falls on a segment boundary
+    """Cut every track at the planes x = X, y = Y (and, 3D tracks, z = Z).  Returns a track set with one track per
+    piece, in the order of the original tracks and along them; `piece_of` (original track of every piece) and
+    `piece_d0` / `piece_d1` (distances from the original track's start) are added to its arrays.  A cut that falls on a segment boundary
     (the usual case: box faces are lattice-cell faces) splits no segment; otherwise the segment is split in two
     with the same FSR, like the reference does when it ray-traces every box on its own."""
     a = ft.arrays
