@@ -129,7 +129,7 @@ class B200Solver:
     linear_source : bool       CPULSSolver physics (src/CPULSSolver.cpp): needs a track file dumped
                                after a linear-source initialisation (centroid-relative segment
                                starting points, quadrature factors); the pre-pass tables come from
-                               openmoc_b200.linear_source.  One GPU only in this build.
+                               openmoc_b200.linear_source.  With several ranks the moment tallies are summed like the scalar flux.
     """
 
     def __init__(self, tracks: FlatTracks, device: int = 0, precision: int = PRECISION_DOUBLE,
