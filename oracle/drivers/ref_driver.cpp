@@ -19,6 +19,8 @@
  *                   [--cmfd NXxNY[xNZ]] [--host-cmfd (B200 solvers: the reference's host Cmfd instead of the device CMFD)]
  *                   [--check-cmfd-split (compare the library's current-splitting tables with Cmfd's, no GPU needed)]
  *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
+ *                   [--cmfd-all-groups (no Cmfd::setGroupStructure)]
+ *                   [--max-tau T (Solver::setMaxOpticalLength)] [--no-keff] [--results-tracks] [--results-segments]
  */
 #include <cstdio>
 #include <cstdlib>
@@ -134,7 +136,8 @@ int main(int argc, char** argv) {
     cmfd->setSORRelaxationFactor(1.5);
     if (dims == 3) cmfd->setLatticeStructure(nx, ny, nz);
     else cmfd->setLatticeStructure(nx, ny);
-    if (geometry->getNumEnergyGroups() == 7 && !flag(argc, argv, "--groups70")) {
+    /* --cmfd-all-groups: no setGroupStructure, one CMFD group per MOC group (tests/test_split_segments_cmfd) */
+    if (geometry->getNumEnergyGroups() == 7 && !flag(argc, argv, "--groups70") && !flag(argc, argv, "--cmfd-all-groups")) {
       std::vector<std::vector<int> > groups(2);
       for (int g = 1; g <= 3; g++) groups[0].push_back(g);
       for (int g = 4; g <= 7; g++) groups[1].push_back(g);
@@ -317,6 +320,7 @@ int main(int argc, char** argv) {
   }
   if (flag(argc, argv, "--allow-negative")) solver->allowNegativeFluxes(true);
   if (stab_type >= 0) solver->stabilizeTransport(stab_factor, (stabilizationType)stab_type);
+  if (max_tau_arg > 0.) solver->setMaxOpticalLength(max_tau_arg);     /* tests/test_split_segments */
 
   if (mode == "eigen") {
     if (solver_name == "b200-fused") b200_solver->computeEigenvalueFused(max_iters, rt);
@@ -342,14 +346,17 @@ int main(int argc, char** argv) {
   if (solved && !results.empty()) {
     FILE* f = fopen(results.c_str(), "w");
     fprintf(f, "# Iterations: %d\n", solver->getNumIterations());
-    if (mode == "eigen") fprintf(f, "keff: %12.5E\n", solver->getKeff());
-    if (flag(argc, argv, "--results-fsrs")) fprintf(f, "# FSRs: %ld\n", n_fsr);      /* tests/testing_harness.py: num_fsrs=True */
+    if (mode == "eigen" && !flag(argc, argv, "--no-keff")) fprintf(f, "keff: %12.5E\n", solver->getKeff());
     if (fluxes_in_results) {
       fprintf(f, "fluxes:\n");
       std::vector<FP_PRECISION> phi(n_fsr * G);
       solver->getFluxes(phi.data(), n_fsr * G);
       for (long i = 0; i < n_fsr * G; i++) fprintf(f, "%12.6E\n", phi[i]);
     }
+    /* tests/testing_harness.py:190-203: num_fsrs / num_tracks / num_segments, in this order, after the fluxes */
+    if (flag(argc, argv, "--results-fsrs")) fprintf(f, "# FSRs: %ld\n", n_fsr);
+    if (flag(argc, argv, "--results-tracks")) fprintf(f, "# tracks: %ld\n", n_trk);
+    if (flag(argc, argv, "--results-segments")) fprintf(f, "# segments: %ld\n", n_seg);
     fclose(f);
   }
 

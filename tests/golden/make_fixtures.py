@@ -56,13 +56,21 @@ CASES = {
                                "--stabilize", "0.5:2"],
     # CMFD from a track file: the dump carries the mesh (cmfd_* chunks, fsr_cmfd_cell) next to the surfaces of the segments
     "simple_lattice_cmfd": ["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12", "--cmfd", "4x4", "--no-knearest"],
+    # tests/test_2d_gradient_linear_source: vacuum on xmin / ymax with the linear source
+    "gradient_2d_ls": ["--model", "gradient-2d", "--azim", "4", "--spacing", "0.1", "--solver", "cpuls"],
+    # tests/test_split_segments: Solver::setMaxOpticalLength(0.5) splits the segments of the pin cell (196 -> 1560);
+    # the dump is taken after the split, so the oracle sweeps what CPUSolver swept
+    "pin_cell_split": ["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--max-tau", "0.5", "--no-fluxes"],
     "lattice3d_ls_7g": ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2",
                         "--spacing", "0.24", "--zspacing", "0.9", "--solver", "cpuls"],  # test_forward_3D_lattice_linear
 }
 
 def main():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    only = sys.argv[1:]                      # optional: regenerate the named fixtures only
     for name, args in CASES.items():
+        if only and name not in only:
+            continue
         trk = os.path.join(HERE, name + ".b2trk")
         js = os.path.join(HERE, name + ".json")
         subprocess.check_call([DRIVER] + args + ["--quiet", "--dump-tracks", trk, "--json", js])
@@ -80,7 +88,8 @@ def main():
               "test_forward_3D_lattice_linear", "test_forward_3D_lattice_linear_70g",
               "test_compute_flux", "test_compute_source", "test_fixed_linear_source",
               "test_forward_pin_cell_70g", "test_1d_gradient", "test_2d_gradient", "test_adjoint_pin_cell", "test_adjoint_simple_lattice", "test_adjoint_hom_inf_medium",
-              "test_forward_3D_lattice_CMFD"):
+              "test_forward_3D_lattice_CMFD", "test_2d_gradient_linear_source", "test_split_segments",
+              "test_split_segments_cmfd"):
         gold[t] = open(os.path.join(REF, "tests", t, "results_true.dat")).read()
     json.dump(gold, open(os.path.join(HERE, "ref_goldens.json"), "w"), indent=1)
 

@@ -271,3 +271,37 @@ def test_ref_driver_reproduces_the_cmfd_golden(tmp_path):
                     "--solver", "cpuls", "--threads", "4", "--quiet", "--no-fluxes", "--results-fsrs", "--results", res],
                    check=True, capture_output=True)
     assert open(res).read() == GOLDENS["test_forward_3D_lattice_CMFD"]
+
+
+def test_gradient_2d_linear_source_golden_bytes():
+    # tests/test_2d_gradient_linear_source/results_true.dat: CPULSSolver, VACUUM on xmin / ymax, 52 iterations
+    s, n, ref = solve_ls("gradient_2d_ls")
+    assert n == ref["iterations"] == 52
+    assert format_harness_results(n, s.getKeff(), s.getFluxes()) == GOLDENS["test_2d_gradient_linear_source"]
+
+
+def test_split_segments_golden_bytes():
+    # tests/test_split_segments/results_true.dat: Solver::setMaxOpticalLength(0.5) on the pin cell, 196 -> 1560 segments;
+    # the fixture was dumped after the split, so the oracle sweeps the segments CPUSolver swept: 262 iterations, not 261
+    s, n, ref = solve("pin_cell_split")
+    assert s.ft.n_segments == 1560
+    assert "# Iterations: {0}\n# segments: {1}\n".format(n, s.ft.n_segments) == GOLDENS["test_split_segments"]
+    assert n == ref["iterations"] and abs(s.getKeff() - ref["keff"]) < 1e-11
+
+
+SPLIT_ARGS = ["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--max-tau", "0.5", "--quiet", "--no-fluxes",
+              "--no-keff", "--results-segments"]
+SPLIT_CMFD_ARGS = SPLIT_ARGS + ["--cmfd", "2x2", "--cmfd-all-groups", "--no-knearest"]
+
+
+@pytest.mark.parametrize("args,test", [(SPLIT_ARGS, "test_split_segments"), (SPLIT_CMFD_ARGS, "test_split_segments_cmfd")])
+def test_ref_driver_reproduces_the_split_segment_goldens(args, test, tmp_path):
+    """tests/test_split_segments and tests/test_split_segments_cmfd (a 2 x 2 Cmfd with its default options over the
+    pin cell: 11 iterations, 1616 segments) from the unmodified reference through ref_driver"""
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([driver] + args + ["--solver", "cpu", "--results", res], check=True, capture_output=True)
+    assert open(res).read() == GOLDENS[test]

@@ -1,0 +1,81 @@
+"""Three more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
+in tests/test_oracle.py): tests/test_2d_gradient_linear_source, tests/test_split_segments,
+tests/test_split_segments_cmfd.  Added when the round's GPU budget was spent: their CPU halves are verified, the
+GPU halves run for the first time on the driver's box (hence the late file name: the rest of the suite runs first)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, load_case
+
+pytestmark = pytest.mark.gpu
+
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+GOLDENS = json.load(open(os.path.join(GOLDEN, "ref_goldens.json")))
+SPLIT_ARGS = ["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--max-tau", "0.5", "--quiet", "--no-fluxes",
+              "--no-keff", "--results-segments"]
+
+
+def drive(args, tmp_path, env=None):
+    if not os.path.exists(DRIVER):
+        pytest.skip("ref_driver not built")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([DRIVER] + args + ["--results", res], check=True, capture_output=True,
+                   env=dict(os.environ, **(env or {})))
+    return open(res).read()
+
+
+def same_to_printed_precision(out, golden):
+    """iterations and k_eff lines byte for byte; fluxes equal to the 7 printed digits (one unit of the last digit
+    tolerated: a sum that differs in its last bits may round the other way)"""
+    a, b = out.split("fluxes:\n"), golden.split("fluxes:\n")
+    assert a[0] == b[0]
+    fa, fb = np.array(a[1].split(), dtype=float), np.array(b[1].split(), dtype=float)
+    assert fa.shape == fb.shape
+    np.testing.assert_allclose(fa, fb, rtol=1.1e-6)
+    return out == golden
+
+
+def test_gradient_2d_linear_source_golden_from_the_plug_in(tmp_path):
+    """B200LSSolver : CPULSSolver on the 2-group cube with VACUUM on xmin / ymax"""
+    out = drive(["--model", "gradient-2d", "--azim", "4", "--spacing", "0.1", "--solver", "b200ls", "--quiet"], tmp_path)
+    print("byte for byte:", same_to_printed_precision(out, GOLDENS["test_2d_gradient_linear_source"]))
+
+
+def test_gradient_2d_linear_source_golden_from_python():
+    """the same golden through the Python mirror on the dumped tracks (pre-pass on the device)"""
+    from openmoc_b200.capi import FISSION_SOURCE
+    from openmoc_b200.solver import B200Solver
+    from oracle.oracle_py import OracleSolver, format_harness_results
+    ft, ref = load_case("gradient_2d_ls")
+    gpu, cpu = B200Solver(ft, linear_source=True), OracleSolver(ft, linear_source=True)
+    gpu.setConvergenceThreshold(1e-5)
+    gpu.computeEigenvalue(500, FISSION_SOURCE)
+    n = cpu.computeEigenvalue(500, 1e-5, FISSION_SOURCE)
+    assert gpu.getNumIterations() == n == ref["iterations"] == 52
+    assert abs(gpu.getKeff() - cpu.getKeff()) * 1e5 < 1e-4
+    np.testing.assert_allclose(gpu.getFluxes(), cpu.getFluxes(), rtol=1e-8)
+    out = format_harness_results(gpu.getNumIterations(), gpu.getKeff(), gpu.getFluxes())
+    print("byte for byte:", same_to_printed_precision(out, GOLDENS["test_2d_gradient_linear_source"]))
+
+
+def test_split_segments_golden_from_the_gpu(tmp_path):
+    """Solver::setMaxOpticalLength(0.5): the plug-in flattens after the split (1560 segments), same 262 iterations"""
+    assert drive(SPLIT_ARGS + ["--solver", "b200"], tmp_path) == GOLDENS["test_split_segments"]
+    from openmoc_b200.capi import FISSION_SOURCE
+    from openmoc_b200.solver import B200Solver
+    ft, ref = load_case("pin_cell_split")
+    s = B200Solver(ft)
+    s.computeEigenvalue(500, FISSION_SOURCE)
+    assert s.getNumIterations() == ref["iterations"] == 262 and abs(s.getKeff() - ref["keff"]) * 1e5 < 1e-4
+
+
+@pytest.mark.parametrize("where", ["device", "host"])
+def test_split_segments_cmfd_golden_from_the_gpu(where, tmp_path):
+    """a 2 x 2 Cmfd with its default options (one CMFD group per MOC group) over the split pin cell: 11 iterations"""
+    out = drive(SPLIT_ARGS + ["--cmfd", "2x2", "--cmfd-all-groups", "--no-knearest", "--solver", "b200"], tmp_path,
+                env={"B200_HOST_CMFD": "1"} if where == "host" else None)
+    assert out == GOLDENS["test_split_segments_cmfd"]
