@@ -19,7 +19,7 @@
  *                   [--cmfd NXxNY[xNZ]] [--host-cmfd (B200 solvers: the reference's host Cmfd instead of the device CMFD)]
  *                   [--check-cmfd-split (compare the library's current-splitting tables with Cmfd's, no GPU needed)]
  *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
- *                   [--cmfd-all-groups (no Cmfd::setGroupStructure)]
+ *                   [--cmfd-all-groups (no Cmfd::setGroupStructure)] [--symmetry (Geometry::useSymmetry(true, true, true))]
  *                   [--max-tau T (Solver::setMaxOpticalLength)] [--no-keff] [--results-tracks] [--results-segments]
  */
 #include <cstdio>
@@ -127,6 +127,8 @@ int main(int argc, char** argv) {
   Model md = build_model(model_name, dims);
   if (flag(argc, argv, "--groups70")) set_70_group_xs(md);
   Geometry* geometry = md.geometry;
+  /* tests/test_forward_3D_lattice_symmetry: Geometry::useSymmetry on the three axes */
+  if (flag(argc, argv, "--symmetry")) geometry->useSymmetry(true, true, true);
   /* CMFD as in tests/test_cmfd_pwr_assembly / sample-input/benchmarks/c5g7/c5g7-2d.py:51-56 */
   std::string cmfd_arg = arg(argc, argv, "--cmfd", "");
   if (!cmfd_arg.empty()) {

@@ -305,3 +305,20 @@ def test_ref_driver_reproduces_the_split_segment_goldens(args, test, tmp_path):
     res = os.path.join(tmp_path, "res.dat")
     subprocess.run([driver] + args + ["--solver", "cpu", "--results", res], check=True, capture_output=True)
     assert open(res).read() == GOLDENS[test]
+
+
+SYMMETRY_ARGS = ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "4", "--spacing", "0.12",
+                 "--zspacing", "0.14", "--formation", "otf-stacks", "--symmetry", "--cmfd", "2x2x2", "--tol", "1e-4",
+                 "--threads", "4", "--quiet", "--no-fluxes", "--results-fsrs"]
+
+
+def test_ref_driver_reproduces_the_symmetry_golden(tmp_path):
+    """tests/test_forward_3D_lattice_symmetry: Geometry::useSymmetry(True, True, True) (one octant: 256 FSRs), CPULSSolver,
+    OTF_STACKS, CMFD 2 x 2 x 2 with k-nearest 3: 44 iterations, keff 4.03117E-01"""
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([driver] + SYMMETRY_ARGS + ["--solver", "cpuls", "--results", res], check=True, capture_output=True)
+    assert open(res).read() == GOLDENS["test_forward_3D_lattice_symmetry"]

@@ -1,6 +1,6 @@
-"""Three more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
+"""Four more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
 in tests/test_oracle.py): tests/test_2d_gradient_linear_source, tests/test_split_segments,
-tests/test_split_segments_cmfd.  Added when the round's GPU budget was spent: their CPU halves are verified, the
+tests/test_split_segments_cmfd, tests/test_forward_3D_lattice_symmetry.  Added when the round's GPU budget was spent: their CPU halves are verified, the
 GPU halves run for the first time on the driver's box (hence the late file name: the rest of the suite runs first)."""
 import json
 import os
@@ -79,3 +79,16 @@ def test_split_segments_cmfd_golden_from_the_gpu(where, tmp_path):
     out = drive(SPLIT_ARGS + ["--cmfd", "2x2", "--cmfd-all-groups", "--no-knearest", "--solver", "b200"], tmp_path,
                 env={"B200_HOST_CMFD": "1"} if where == "host" else None)
     assert out == GOLDENS["test_split_segments_cmfd"]
+
+
+SYMMETRY_ARGS = ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "4", "--spacing", "0.12",
+                 "--zspacing", "0.14", "--formation", "otf-stacks", "--symmetry", "--cmfd", "2x2x2", "--tol", "1e-4",
+                 "--threads", "4", "--quiet", "--no-fluxes", "--results-fsrs"]
+
+
+@pytest.mark.parametrize("where", ["device", "host"])
+def test_symmetry_golden_from_the_gpu(where, tmp_path):
+    """Geometry::useSymmetry(True, True, True): one octant of the 3D lattice, B200LSSolver, OTF_STACKS, CMFD 2 x 2 x 2
+    with k-nearest 3: 44 iterations, keff 4.03117E-01, 256 FSRs"""
+    out = drive(SYMMETRY_ARGS + ["--solver", "b200ls"], tmp_path, env={"B200_HOST_CMFD": "1"} if where == "host" else None)
+    assert out == GOLDENS["test_forward_3D_lattice_symmetry"]
