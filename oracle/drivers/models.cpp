@@ -33,6 +33,7 @@ std::map<std::string, Material*> make_c5g7_materials() {
 }
 
 int g_axial_layers = 1;
+int g_vacuum_mask = 0, g_periodic_mask = 0;
 
 void fill_lattice(Lattice* lat, int ny, int nx, const std::vector<Universe*>& rows_top_down) {
   /* rows_top_down is row-major starting at the upper-left corner, exactly the
@@ -125,6 +126,83 @@ Model simple_lattice(int dims) {
   fill_lattice(core, 2, 2, {assembly, assembly, assembly, assembly});
   root_cell->setFill(core);
 
+  md.geometry = new Geometry();
+  md.geometry->setRootUniverse(root);
+  return md;
+}
+
+/* ---------------- tests/input_set.py:420-559 (PwrAssemblyInput) ---------------- */
+/* A 17 x 17 mixed-enrichment MOX assembly, every pin with 3 rings and 8 sectors in the fuel AND in the moderator (one
+ * moderator Cell shared by the five pin universes, like the Python deck).  vacuum_mask / periodic_mask: bit 0 xmin,
+ * 1 xmax, 2 ymin, 3 ymax (tests/test_cmfd_vacuum_boundary, tests/test_cmfd_periodic_boundaries). */
+Model pwr_assembly(int, int vacuum_mask = 0, int periodic_mask = 0) {
+  Model md;
+  md.materials = make_c5g7_materials();
+  {
+    /* the Python decks read sample-input/c5g7-mgxs.h5, whose MOX-4.3% total cross section of group 7 is 0.682852;
+     * the C++ decks under profile/models/c5g7 (what c5g7_xs.h restates) carry 0.68285 */
+    Material* mox43 = md.materials["MOX-4.3%"];
+    std::vector<double> st(mox43->getSigmaT(), mox43->getSigmaT() + c5g7::G);
+    st[6] = 0.682852;
+    mox43->setSigmaT(st.data(), c5g7::G);
+  }
+  ZCylinder* fuel_radius = new ZCylinder(0.0, 0.0, 0.54);
+  XPlane* xmin = new XPlane(-10.71); XPlane* xmax = new XPlane(10.71);
+  YPlane* ymin = new YPlane(-10.71); YPlane* ymax = new YPlane(10.71);
+  Surface* sides[4] = {xmin, xmax, ymin, ymax};
+  for (int i = 0; i < 4; i++)
+    sides[i]->setBoundaryType((vacuum_mask >> i) & 1 ? VACUUM : (periodic_mask >> i) & 1 ? PERIODIC : REFLECTIVE);
+
+  const char* fills[5] = {"MOX-4.3%", "MOX-7%", "MOX-8.7%", "Guide Tube", "Fission Chamber"};   /* template ids 1..5 */
+  Cell* moderator = new Cell();
+  moderator->setFill(md.materials["Water"]);
+  moderator->addSurface(+1, fuel_radius);
+  moderator->setNumRings(3);
+  moderator->setNumSectors(8);
+  Universe* pins[5];
+  for (int i = 0; i < 5; i++) {
+    Cell* fuel = new Cell();
+    fuel->setFill(md.materials[fills[i]]);
+    fuel->setNumRings(3);
+    fuel->setNumSectors(8);
+    fuel->addSurface(-1, fuel_radius);
+    pins[i] = new Universe();
+    pins[i]->addCell(fuel);
+  }
+  /* the Python deck creates the five fuel cells and universes first and adds the moderator afterwards */
+  for (int i = 0; i < 5; i++) pins[i]->addCell(moderator);
+
+  static const int tmpl[17][17] = {
+    {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1},
+    {1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1},
+    {1, 2, 2, 2, 2, 4, 2, 2, 4, 2, 2, 4, 2, 2, 2, 2, 1},
+    {1, 2, 2, 4, 2, 3, 3, 3, 3, 3, 3, 3, 2, 4, 2, 2, 1},
+    {1, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 2, 1},
+    {1, 2, 4, 3, 3, 4, 3, 3, 4, 3, 3, 4, 3, 3, 4, 2, 1},
+    {1, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 1},
+    {1, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 1},
+    {1, 2, 4, 3, 3, 4, 3, 3, 5, 3, 3, 4, 3, 3, 4, 2, 1},
+    {1, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 1},
+    {1, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 1},
+    {1, 2, 4, 3, 3, 4, 3, 3, 4, 3, 3, 4, 3, 3, 4, 2, 1},
+    {1, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 2, 1},
+    {1, 2, 2, 4, 2, 3, 3, 3, 3, 3, 3, 3, 2, 4, 2, 2, 1},
+    {1, 2, 2, 2, 2, 4, 2, 2, 4, 2, 2, 4, 2, 2, 2, 2, 1},
+    {1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1},
+    {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}};
+  std::vector<Universe*> rows;
+  for (int i = 0; i < 17; i++)
+    for (int j = 0; j < 17; j++) rows.push_back(pins[tmpl[i][j] - 1]);
+  Lattice* assembly = new Lattice();
+  assembly->setWidth(1.26, 1.26);
+  fill_lattice(assembly, 17, 17, rows);
+
+  Cell* root_cell = new Cell();
+  root_cell->setFill(assembly);
+  root_cell->addSurface(+1, xmin); root_cell->addSurface(-1, xmax);
+  root_cell->addSurface(+1, ymin); root_cell->addSurface(-1, ymax);
+  Universe* root = new Universe();
+  root->addCell(root_cell);
   md.geometry = new Geometry();
   md.geometry->setRootUniverse(root);
   return md;
@@ -352,6 +430,7 @@ std::vector<double> linspace(double a, double b, int n) {
 
 
 void set_axial_layers(int n) { g_axial_layers = n < 1 ? 1 : n; }
+void set_boundary_masks(int vacuum_mask, int periodic_mask) { g_vacuum_mask = vacuum_mask; g_periodic_mask = periodic_mask; }
 
 Model build_model(const std::string& name, int dims) {
   if (name == "pin-cell") return pin_cell(dims);
@@ -360,6 +439,7 @@ Model build_model(const std::string& name, int dims) {
   if (name == "gradient-1d") return hom_inf(dims, 1 | 2);     /* tests/test_1d_gradient: VACUUM in x */
   if (name == "gradient-2d") return hom_inf(dims, 1 | 8);     /* tests/test_2d_gradient: VACUUM on xmin, ymax */
   if (name == "water-box") return water_box(dims);
+  if (name == "pwr-assembly") return pwr_assembly(dims, g_vacuum_mask, g_periodic_mask);
   if (name == "c5g7-2d") return c5g7_2d(dims);
   log_printf(ERROR, "unknown model %s", name.c_str());
   return Model();

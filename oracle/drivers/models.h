@@ -35,6 +35,9 @@ Model build_model(const std::string& name, int dims);
 /** c5g7-2d with dims = 3: number of equal axial layers of the root lattice (3 x 3 x N, the structure of
  *  profile/models/c5g7/c5g7-3d-cmfd.cpp:520-535 with identical layers); default 1. */
 void set_axial_layers(int n);
+/** pwr-assembly: sides switched to VACUUM / PERIODIC (bit 0 xmin, 1 xmax, 2 ymin, 3 ymax), what
+ *  tests/test_cmfd_vacuum_boundary and tests/test_cmfd_periodic_boundaries do to PwrAssemblyInput. */
+void set_boundary_masks(int vacuum_mask, int periodic_mask);
 
 /** Replace the UO2/Water data by the synthetic 70-group set of
  *  tests/test_forward_3D_lattice_70g/test_forward_3D_lattice_70g.py:43-61. */

@@ -19,6 +19,7 @@
  *                   [--cmfd NXxNY[xNZ]] [--host-cmfd (B200 solvers: the reference's host Cmfd instead of the device CMFD)]
  *                   [--check-cmfd-split (compare the library's current-splitting tables with Cmfd's, no GPU needed)]
  *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
+ *                   [--vacuum-mask M] [--periodic-mask M] (pwr-assembly: bit 0 xmin, 1 xmax, 2 ymin, 3 ymax)
  *                   [--cmfd-all-groups (no Cmfd::setGroupStructure)] [--symmetry (Geometry::useSymmetry(true, true, true))]
  *                   [--max-tau T (Solver::setMaxOpticalLength)] [--no-keff] [--results-tracks] [--results-segments]
  */
@@ -124,6 +125,7 @@ int main(int argc, char** argv) {
   /* --max-tau X: Solver::setMaxOpticalLength (segments are cut at this optical length) */
   const double max_tau_arg = atof(arg(argc, argv, "--max-tau", "0"));
   set_axial_layers(atoi(arg(argc, argv, "--axial", "1")));
+  set_boundary_masks(atoi(arg(argc, argv, "--vacuum-mask", "0")), atoi(arg(argc, argv, "--periodic-mask", "0")));
   Model md = build_model(model_name, dims);
   if (flag(argc, argv, "--groups70")) set_70_group_xs(md);
   Geometry* geometry = md.geometry;
