@@ -417,7 +417,8 @@ int main(int argc, char** argv) {
   /* ---- flattened tracks (segments are final after the solve/initialize) ---- */
   if (!dump_tracks.empty()) {
     B200FlatTracks ft;
-    b200_flatten(tg, &ft);
+    /* --dump-device-otf: what the plug-in hands to the device tracer for an OTF deck (no 3D segment on the host) */
+    b200_flatten(tg, &ft, true, flag(argc, argv, "--dump-device-otf"));
     B200CmfdView view;
     Cmfd* dumped_cmfd = solved ? geometry->getCmfd() : NULL;      /* the mesh is known once the solver initialised it */
     if (dumped_cmfd != NULL) b200_read_cmfd(dumped_cmfd, n_fsr, &view);

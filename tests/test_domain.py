@@ -352,6 +352,19 @@ def test_reference_track_dumps_are_cut_into_boxes(tmp_path):
     np.testing.assert_allclose(phi, one.getFluxes(), rtol=1e-10, atol=1e-14)
 
 
+def test_device_tracer_hand_over_carries_the_same_track_data(tmp_path):
+    """b200_flatten(device_otf=true) - what the plug-in gives the device tracer for an OTF deck, no 3D segment on the
+    host - and the host expansion agree on every per-track array, start points included"""
+    args = ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
+            "--zspacing", "0.9", "--formation", "otf-stacks", "--mode", "none"]
+    host = reference_tracks(tmp_path, "host", args)
+    dev = reference_tracks(tmp_path, "dev", args + ["--dump-device-otf"])
+    assert dev.n_segments == 0 and host.n_segments > 0 and dev.n_tracks == host.n_tracks
+    for k in ("trk_start", "trk_phi", "trk_theta", "trk_azim", "trk_polar", "trk_next_fwd", "trk_next_bwd", "trk_flags",
+              "trk_bc_fwd", "trk_bc_bwd"):
+        assert np.array_equal(dev.arrays[k], host.arrays[k]), k
+
+
 # ------------------------------------------------------------------ the same over gloo, one process per box
 def _free_port():
     s = socket.socket()
