@@ -19,6 +19,7 @@
  *                   [--cmfd NXxNY[xNZ]] [--host-cmfd (B200 solvers: the reference's host Cmfd instead of the device CMFD)]
  *                   [--check-cmfd-split (compare the library's current-splitting tables with Cmfd's, no GPU needed)]
  *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
+ *                   [--stabilize F:T | --stabilize-sequence F:T,F:T,...] [--negative-water-scatter]
  *                   [--vacuum-mask M] [--periodic-mask M] (pwr-assembly: bit 0 xmin, 1 xmax, 2 ymin, 3 ymax)
  *                   [--cmfd-all-groups (no Cmfd::setGroupStructure)] [--symmetry (Geometry::useSymmetry(true, true, true))]
  *                   [--max-tau T (Solver::setMaxOpticalLength)] [--no-keff] [--results-tracks] [--results-segments]
@@ -122,12 +123,28 @@ int main(int argc, char** argv) {
     std::string st = arg(argc, argv, "--stabilize", "");
     if (!st.empty()) sscanf(st.c_str(), "%lf:%d", &stab_factor, &stab_type);
   }
+  /* --stabilize-sequence F:T,F:T,...: one eigenvalue solve per entry on the same solver, results of the last one
+   * (tests/test_transport_stabilization runs DIAGONAL, YAMAMOTO, GLOBAL in a row) */
+  std::vector<std::pair<double, int> > stab_sequence;
+  {
+    std::string st = arg(argc, argv, "--stabilize-sequence", "");
+    size_t pos = 0;
+    while (pos < st.size()) {
+      double f = 0.; int t = 0, used = 0;
+      if (sscanf(st.c_str() + pos, "%lf:%d%n", &f, &t, &used) != 2) break;
+      stab_sequence.push_back(std::make_pair(f, t));
+      pos += used;
+      if (pos < st.size() && st[pos] == ',') pos++;
+    }
+  }
   /* --max-tau X: Solver::setMaxOpticalLength (segments are cut at this optical length) */
   const double max_tau_arg = atof(arg(argc, argv, "--max-tau", "0"));
   set_axial_layers(atoi(arg(argc, argv, "--axial", "1")));
   set_boundary_masks(atoi(arg(argc, argv, "--vacuum-mask", "0")), atoi(arg(argc, argv, "--periodic-mask", "0")));
   Model md = build_model(model_name, dims);
   if (flag(argc, argv, "--groups70")) set_70_group_xs(md);
+  /* tests/test_transport_stabilization: a large negative in-scatter in the moderator */
+  if (flag(argc, argv, "--negative-water-scatter")) md.materials["Water"]->setSigmaSByGroup(-1., 4, 4);
   Geometry* geometry = md.geometry;
   /* tests/test_forward_3D_lattice_symmetry: Geometry::useSymmetry on the three axes */
   if (flag(argc, argv, "--symmetry")) geometry->useSymmetry(true, true, true);
@@ -326,7 +343,12 @@ int main(int argc, char** argv) {
   if (stab_type >= 0) solver->stabilizeTransport(stab_factor, (stabilizationType)stab_type);
   if (max_tau_arg > 0.) solver->setMaxOpticalLength(max_tau_arg);     /* tests/test_split_segments */
 
-  if (mode == "eigen") {
+  if (mode == "eigen" && !stab_sequence.empty()) {
+    for (size_t i = 0; i < stab_sequence.size(); i++) {
+      solver->stabilizeTransport(stab_sequence[i].first, (stabilizationType)stab_sequence[i].second);
+      solver->computeEigenvalue(max_iters, rt);
+    }
+  } else if (mode == "eigen") {
     if (solver_name == "b200-fused") b200_solver->computeEigenvalueFused(max_iters, rt);
     else solver->computeEigenvalue(max_iters, rt);
   } else if (mode == "flux") {

@@ -90,7 +90,7 @@ def main():
               "test_forward_pin_cell_70g", "test_1d_gradient", "test_2d_gradient", "test_adjoint_pin_cell", "test_adjoint_simple_lattice", "test_adjoint_hom_inf_medium",
               "test_forward_3D_lattice_CMFD", "test_2d_gradient_linear_source", "test_split_segments",
               "test_split_segments_cmfd", "test_forward_3D_lattice_symmetry", "test_cmfd_pwr_assembly",
-              "test_cmfd_vacuum_boundary", "test_cmfd_periodic_boundaries", "test_cmfd_linear_source"):
+              "test_cmfd_vacuum_boundary", "test_cmfd_periodic_boundaries", "test_cmfd_linear_source", "test_transport_stabilization"):
         gold[t] = open(os.path.join(REF, "tests", t, "results_true.dat")).read()
     json.dump(gold, open(os.path.join(HERE, "ref_goldens.json"), "w"), indent=1)
 

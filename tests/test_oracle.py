@@ -348,3 +348,22 @@ def test_ref_driver_reproduces_the_cmfd_assembly_goldens(test, tmp_path):
     res = os.path.join(tmp_path, "res.dat")
     subprocess.run([driver] + PWR_CASES[test] + ["--results", res], check=True, capture_output=True)
     assert hashlib.sha512(open(res).read().encode()).hexdigest() == GOLDENS[test].strip()
+
+
+STABILIZATION_ARGS = ["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12", "--cmfd", "17x17", "--cmfd-relax", "0.7",
+                      "--negative-water-scatter", "--stabilize-sequence", "0.4:0,0.4:1,0.4:2", "--quiet"]
+
+
+def test_ref_driver_reproduces_the_transport_stabilization_golden(tmp_path):
+    """tests/test_transport_stabilization: CPULSSolver + CMFD 17 x 17 on the simple lattice with a large negative
+    in-scatter in the moderator, DIAGONAL, YAMAMOTO and GLOBAL stabilisation (factor 0.4) solved one after the other
+    on the same solver; the golden is the SHA-512 of the last solve (43 iterations, keff 5.67687E-01, all fluxes)"""
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([driver] + STABILIZATION_ARGS + ["--solver", "cpuls", "--results", res], check=True, capture_output=True)
+    out = open(res).read()
+    assert out.startswith("# Iterations: 43\nkeff:  5.67687E-01\n")
+    assert hashlib.sha512(out.encode()).hexdigest() == GOLDENS["test_transport_stabilization"].strip()

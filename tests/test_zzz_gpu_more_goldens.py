@@ -1,7 +1,8 @@
-"""Eight more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
+"""Nine more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
 in tests/test_oracle.py): tests/test_2d_gradient_linear_source, tests/test_split_segments,
 tests/test_split_segments_cmfd, tests/test_forward_3D_lattice_symmetry, tests/test_cmfd_pwr_assembly,
-tests/test_cmfd_vacuum_boundary, tests/test_cmfd_periodic_boundaries, tests/test_cmfd_linear_source.  Added when the
+tests/test_cmfd_vacuum_boundary, tests/test_cmfd_periodic_boundaries, tests/test_cmfd_linear_source,
+tests/test_transport_stabilization.  Added when the
 round's GPU budget was spent: their CPU halves are verified, the GPU halves run for the first time on the driver's box
 (hence the late file name: the rest of the suite runs first)."""
 import hashlib
@@ -124,3 +125,18 @@ def test_cmfd_assembly_goldens_from_the_gpu(test, where, tmp_path):
     gpu = drive(args + ["--solver", gpu_solver], tmp_path, env={"B200_HOST_CMFD": "1"} if where == "host" else None)
     same = same_to_printed_precision(gpu, cpu)
     print("digest from the GPU equals the reference's:", same)
+
+
+STABILIZATION_ARGS = ["--model", "simple-lattice", "--azim", "4", "--spacing", "0.12", "--cmfd", "17x17", "--cmfd-relax", "0.7",
+                      "--negative-water-scatter", "--stabilize-sequence", "0.4:0,0.4:1,0.4:2", "--quiet"]
+
+
+@pytest.mark.parametrize("where", ["device", "host"])
+def test_transport_stabilization_golden_from_the_gpu(where, tmp_path):
+    """B200LSSolver + CMFD with DIAGONAL, YAMAMOTO and GLOBAL stabilisation solved in a row on one solver object (negative
+    in-scatter in the moderator): the reference run on this box gives the committed digest, the B200 run the same
+    iterations, printed k_eff and fluxes to the printed digits"""
+    cpu = drive(STABILIZATION_ARGS + ["--solver", "cpuls"], tmp_path)
+    assert hashlib.sha512(cpu.encode()).hexdigest() == GOLDENS["test_transport_stabilization"].strip()
+    gpu = drive(STABILIZATION_ARGS + ["--solver", "b200ls"], tmp_path, env={"B200_HOST_CMFD": "1"} if where == "host" else None)
+    print("digest from the GPU equals the reference's:", same_to_printed_precision(gpu, cpu))
