@@ -208,6 +208,83 @@ Model pwr_assembly(int, int vacuum_mask = 0, int periodic_mask = 0) {
   return md;
 }
 
+/* ---------------- tests/input_set.py:712-868 (AxialExtendedInput) ---------------- */
+/* A 4 x 4 x 20 NON-UNIFORM lattice (gap, pin, pin, gap in x and y; twenty 1 cm layers), two pins replaced by the gap
+ * material in one layer: extruded FSRs with different axial meshes.  The Clad material of sample-input/c5g7-mgxs.h5
+ * (not among the seven of the C++ decks) is restated here from the file's datasets 'total' and 'scatter matrix'. */
+Model axial_extended(int) {
+  Model md;
+  md.materials = make_c5g7_materials();
+  {
+    double total[7] = {0.13006, 0.30548, 0.32991, 0.2697, 0.27278, 0.27794, 0.29563};
+    double scatter[49] = {0.097249, 0.032548, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.30398, 0.00077285, 0.0, 0.0, 0.0, 0.0,
+                          0.0, 0.0, 0.32428, 0.00059405, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.2632, 0.0053135, 0.0, 0.0,
+                          0.0, 0.0, 0.0, 0.0021268, 0.25395, 0.013908, 0.0, 0.0, 0.0, 0.0, 0.0, 0.01485, 0.24185,
+                          0.016534, 0.0, 0.0, 0.0, 0.0, 0.0, 0.029899, 0.25716};
+    double zeros[7] = {0., 0., 0., 0., 0., 0., 0.};
+    Material* clad = new Material(100, "Clad");
+    clad->setNumEnergyGroups(7);
+    clad->setSigmaT(total, 7);
+    clad->setSigmaS(scatter, 49);
+    clad->setSigmaF(zeros, 7); clad->setNuSigmaF(zeros, 7); clad->setChi(zeros, 7);
+    md.materials["Clad"] = clad;
+  }
+  const int num_sectors = 8;
+  const double pin_pitch = 1.26, gap_size = 0.05;
+  ZCylinder* c_fuel = new ZCylinder(0., 0., 0.54);
+  ZCylinder* c_clad = new ZCylinder(0., 0., 0.57);
+  ZCylinder* c_large = new ZCylinder(0., 0., 0.60);
+  ZPlane* z_lo = new ZPlane(-1.0E10);
+  ZPlane* z_hi = new ZPlane(1.0E10);
+
+  Cell* fuel = new Cell(); Cell* clad = new Cell(); Cell* mod = new Cell(); Cell* gap = new Cell();
+  Cell* large_fuel = new Cell(); Cell* large_mod = new Cell();
+  fuel->addSurface(-1, c_fuel); fuel->addSurface(+1, z_lo); fuel->addSurface(-1, z_hi);
+  fuel->setFill(md.materials["UO2"]); fuel->setNumSectors(num_sectors); fuel->setNumRings(1);
+  clad->addSurface(+1, c_fuel); clad->addSurface(-1, c_clad); clad->addSurface(+1, z_lo); clad->addSurface(-1, z_hi);
+  clad->setFill(md.materials["Clad"]); clad->setNumSectors(num_sectors);
+  mod->addSurface(+1, c_clad); mod->addSurface(+1, z_lo); mod->addSurface(-1, z_hi);
+  mod->setFill(md.materials["Water"]); mod->setNumSectors(num_sectors); mod->setNumRings(1);
+  gap->addSurface(+1, z_lo); gap->addSurface(-1, z_hi);
+  gap->setFill(md.materials["Clad"]);
+  large_fuel->addSurface(-1, c_large); large_fuel->addSurface(+1, z_lo); large_fuel->addSurface(-1, z_hi);
+  large_fuel->setFill(md.materials["UO2"]); large_fuel->setNumSectors(num_sectors);
+  large_mod->addSurface(+1, c_large); large_mod->addSurface(+1, z_lo); large_mod->addSurface(-1, z_hi);
+  large_mod->setFill(md.materials["Water"]); large_mod->setNumSectors(num_sectors);
+
+  Universe* pin = new Universe(); pin->addCell(fuel); pin->addCell(clad); pin->addCell(mod);
+  Universe* ugap = new Universe(); ugap->addCell(gap);
+  Universe* large_pin = new Universe(); large_pin->addCell(large_fuel); large_pin->addCell(large_mod);   /* unused, as in the deck */
+
+  const int n_z = 20;
+  std::vector<double> wx = {gap_size, pin_pitch, pin_pitch, gap_size}, wy = wx, wz(n_z, 1.0);
+  const double sx = 2 * gap_size + 2 * pin_pitch, sz = n_z * 1.0;
+  Lattice* lattice = new Lattice();
+  lattice->setWidths(wx, wy, wz);
+  lattice->setOffset(sx / 2., sx / 2., sz / 2.);
+  Universe* layer[16] = {ugap, ugap, ugap, ugap,  ugap, pin, pin, ugap,  ugap, pin, pin, ugap,  ugap, ugap, ugap, ugap};
+  std::vector<Universe*> fill;
+  for (int k = 0; k < n_z; k++) fill.insert(fill.end(), layer, layer + 16);
+  fill[2 * 16 + 1 * 4 + 1] = ugap;                       /* fill_universes[2][1][1] = g: axially heterogeneous */
+  lattice->setUniverses(n_z, 4, 4, fill.data());
+
+  XPlane* xmin = new XPlane(0.); XPlane* xmax = new XPlane(sx);
+  YPlane* ymin = new YPlane(0.); YPlane* ymax = new YPlane(sx);
+  ZPlane* zmin = new ZPlane(0.); ZPlane* zmax = new ZPlane(sz);
+  Surface* sides[6] = {xmin, xmax, ymin, ymax, zmin, zmax};
+  for (int i = 0; i < 6; i++) sides[i]->setBoundaryType(REFLECTIVE);
+  Cell* root_cell = new Cell();
+  root_cell->setFill(lattice);
+  root_cell->addSurface(+1, xmin); root_cell->addSurface(-1, xmax);
+  root_cell->addSurface(+1, ymin); root_cell->addSurface(-1, ymax);
+  root_cell->addSurface(+1, zmin); root_cell->addSurface(-1, zmax);
+  Universe* root = new Universe();
+  root->addCell(root_cell);
+  md.geometry = new Geometry();
+  md.geometry->setRootUniverse(root);
+  return md;
+}
+
 /* ---------------- tests/input_set.py:32-92 ---------------- */
 Model hom_inf(int, int vacuum_mask = 0) {   /* bit 0 xmin, 1 xmax, 2 ymin, 3 ymax set to VACUUM */
   Model md;
@@ -439,6 +516,7 @@ Model build_model(const std::string& name, int dims) {
   if (name == "gradient-1d") return hom_inf(dims, 1 | 2);     /* tests/test_1d_gradient: VACUUM in x */
   if (name == "gradient-2d") return hom_inf(dims, 1 | 8);     /* tests/test_2d_gradient: VACUUM on xmin, ymax */
   if (name == "water-box") return water_box(dims);
+  if (name == "axial-extended") return axial_extended(dims);
   if (name == "pwr-assembly") return pwr_assembly(dims, g_vacuum_mask, g_periodic_mask);
   if (name == "c5g7-2d") return c5g7_2d(dims);
   log_printf(ERROR, "unknown model %s", name.c_str());

@@ -19,6 +19,8 @@
  *                   [--cmfd NXxNY[xNZ]] [--host-cmfd (B200 solvers: the reference's host Cmfd instead of the device CMFD)]
  *                   [--check-cmfd-split (compare the library's current-splitting tables with Cmfd's, no GPU needed)]
  *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
+ *                   [--seg-zones z0,z1,.. (TrackGenerator3D::setSegmentationZones)]
+ *                   [--cmfd-widths "x..;y..;z.." (Cmfd::setWidths; give --cmfd 1x1 as well)] [--cmfd-axial-interp 0|1|2]
  *                   [--stabilize F:T | --stabilize-sequence F:T,F:T,...] [--negative-water-scatter]
  *                   [--vacuum-mask M] [--periodic-mask M] (pwr-assembly: bit 0 xmin, 1 xmax, 2 ymin, 3 ymax)
  *                   [--cmfd-all-groups (no Cmfd::setGroupStructure)] [--symmetry (Geometry::useSymmetry(true, true, true))]
@@ -155,8 +157,22 @@ int main(int argc, char** argv) {
     sscanf(cmfd_arg.c_str(), "%dx%dx%d", &nx, &ny, &nz);
     Cmfd* cmfd = new Cmfd();
     cmfd->setSORRelaxationFactor(1.5);
-    if (dims == 3) cmfd->setLatticeStructure(nx, ny, nz);
+    /* --cmfd-widths "x0,x1,..;y0,..;z0,.." instead of a uniform lattice (Cmfd::setWidths, tests/test_cmfd_axial_interpolation_*) */
+    std::string cw = arg(argc, argv, "--cmfd-widths", "");
+    if (!cw.empty()) {
+      std::vector<std::vector<double> > widths(1);
+      for (size_t pos = 0; pos < cw.size();) {
+        if (cw[pos] == ';') { widths.push_back(std::vector<double>()); pos++; continue; }
+        if (cw[pos] == ',') { pos++; continue; }
+        char* end = NULL;
+        widths.back().push_back(strtod(cw.c_str() + pos, &end));
+        pos = end - cw.c_str();
+      }
+      cmfd->setWidths(widths);
+    }
+    else if (dims == 3) cmfd->setLatticeStructure(nx, ny, nz);
     else cmfd->setLatticeStructure(nx, ny);
+    if (strlen(arg(argc, argv, "--cmfd-axial-interp", "")) > 0) cmfd->useAxialInterpolation(atoi(arg(argc, argv, "--cmfd-axial-interp", "0")));
     /* --cmfd-all-groups: no setGroupStructure, one CMFD group per MOC group (tests/test_split_segments_cmfd) */
     if (geometry->getNumEnergyGroups() == 7 && !flag(argc, argv, "--groups70") && !flag(argc, argv, "--cmfd-all-groups")) {
       std::vector<std::vector<int> > groups(2);
@@ -192,6 +208,18 @@ int main(int argc, char** argv) {
     if (formation == "explicit") tg3->setSegmentFormation(EXPLICIT_3D);
     else if (formation == "otf-stacks") tg3->setSegmentFormation(OTF_STACKS);
     else tg3->setSegmentFormation(OTF_TRACKS);
+    /* --seg-zones z0,z1,...: TrackGenerator3D::setSegmentationZones (tests/test_axial_segmentation) */
+    std::string zones = arg(argc, argv, "--seg-zones", "");
+    if (!zones.empty()) {
+      std::vector<double> z;
+      for (size_t pos = 0; pos < zones.size();) {
+        if (zones[pos] == ',') { pos++; continue; }
+        char* end = NULL;
+        z.push_back(strtod(zones.c_str() + pos, &end));
+        pos = end - zones.c_str();
+      }
+      tg3->setSegmentationZones(z);
+    }
     tg = tg3;
   } else {
     tg = new TrackGenerator(geometry, num_azim, spacing);

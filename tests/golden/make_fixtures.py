@@ -61,6 +61,11 @@ CASES = {
     # tests/test_split_segments: Solver::setMaxOpticalLength(0.5) splits the segments of the pin cell (196 -> 1560);
     # the dump is taken after the split, so the oracle sweeps what CPUSolver swept
     "pin_cell_split": ["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--max-tau", "0.5", "--no-fluxes"],
+    # tests/test_axial_segmentation: AxialExtendedInput (non-uniform lattice, axially heterogeneous), OTF_TRACKS with
+    # segmentation zones, 30 iterations without convergence
+    "axial_extended": ["--model", "axial-extended", "--dims", "3", "--azim", "4", "--polar", "2", "--spacing", "0.24",
+                       "--zspacing", "0.9", "--formation", "otf-tracks", "--seg-zones", "0,1,2,3,4,5,6,7,8,9,10,20",
+                       "--max-iters", "30", "--no-fluxes"],
     "lattice3d_ls_7g": ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "2",
                         "--spacing", "0.24", "--zspacing", "0.9", "--solver", "cpuls"],  # test_forward_3D_lattice_linear
 }
@@ -75,7 +80,7 @@ def main():
         js = os.path.join(HERE, name + ".json")
         subprocess.check_call([DRIVER] + args + ["--quiet", "--dump-tracks", trk, "--json", js])
         d = json.load(open(js))
-        if name.startswith("c5g7") or name.startswith("lattice3d_70g") or name.startswith("lattice3d_ls"):
+        if name.startswith(("c5g7", "lattice3d_70g", "lattice3d_ls", "axial_extended")):
             d.pop("fluxes", None)    # keep the fixture small; phi is compared through the oracle
         d.pop("sweep_time_s", None); d.pop("total_time_s", None)
         if name.endswith("_stab"):
@@ -90,7 +95,8 @@ def main():
               "test_forward_pin_cell_70g", "test_1d_gradient", "test_2d_gradient", "test_adjoint_pin_cell", "test_adjoint_simple_lattice", "test_adjoint_hom_inf_medium",
               "test_forward_3D_lattice_CMFD", "test_2d_gradient_linear_source", "test_split_segments",
               "test_split_segments_cmfd", "test_forward_3D_lattice_symmetry", "test_cmfd_pwr_assembly",
-              "test_cmfd_vacuum_boundary", "test_cmfd_periodic_boundaries", "test_cmfd_linear_source", "test_transport_stabilization"):
+              "test_cmfd_vacuum_boundary", "test_cmfd_periodic_boundaries", "test_cmfd_linear_source", "test_transport_stabilization", "test_axial_segmentation",
+              "test_cmfd_axial_interpolation_average", "test_cmfd_axial_interpolation_centroid"):
         gold[t] = open(os.path.join(REF, "tests", t, "results_true.dat")).read()
     json.dump(gold, open(os.path.join(HERE, "ref_goldens.json"), "w"), indent=1)
 

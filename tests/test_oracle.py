@@ -367,3 +367,38 @@ def test_ref_driver_reproduces_the_transport_stabilization_golden(tmp_path):
     out = open(res).read()
     assert out.startswith("# Iterations: 43\nkeff:  5.67687E-01\n")
     assert hashlib.sha512(out.encode()).hexdigest() == GOLDENS["test_transport_stabilization"].strip()
+
+
+def test_axial_segmentation_golden_bytes():
+    # tests/test_axial_segmentation/results_true.dat: AxialExtendedInput (non-uniform 4 x 4 x 20 lattice, one layer
+    # with two pins taken out), OTF_TRACKS with segmentation zones, computeEigenvalue(max_iters=30): not converged
+    s, n, ref = solve("axial_extended", max_iters=30)
+    assert n == ref["iterations"] == 30 and abs(s.getKeff() - ref["keff"]) < 1e-11
+    assert format_harness_results(n, s.getKeff()) == GOLDENS["test_axial_segmentation"]
+
+
+AXIAL = ["--model", "axial-extended", "--dims", "3", "--azim", "4", "--quiet", "--no-fluxes"]
+AXIAL_SEGMENTATION_ARGS = AXIAL + ["--polar", "2", "--spacing", "0.24", "--zspacing", "0.9", "--formation", "otf-tracks",
+                                   "--seg-zones", "0,1,2,3,4,5,6,7,8,9,10,20", "--max-iters", "30"]
+AXIAL_INTERPOLATION_ARGS = AXIAL + ["--polar", "4", "--quad", "gl", "--spacing", "0.1", "--zspacing", "0.5", "--formation",
+                                    "otf-stacks", "--seg-zones", "0,17,18,20", "--cmfd", "1x1", "--cmfd-widths",
+                                    "0.05,1.26,1.26,0.05;0.05,1.26,1.26,0.05;1,2,3,4,1,2,3,4", "--cmfd-sor", "1.5",
+                                    "--cmfd-relax", "0.7", "--cmfd-all-groups", "--no-knearest", "--tol", "1e-4",
+                                    "--threads", "4", "--results-fsrs"]
+
+
+@pytest.mark.parametrize("args,solver,test", [
+    (AXIAL_SEGMENTATION_ARGS, "cpu", "test_axial_segmentation"),
+    (AXIAL_INTERPOLATION_ARGS + ["--cmfd-axial-interp", "1"], "cpuls", "test_cmfd_axial_interpolation_average"),
+    (AXIAL_INTERPOLATION_ARGS + ["--cmfd-axial-interp", "2"], "cpuls", "test_cmfd_axial_interpolation_centroid")])
+def test_ref_driver_reproduces_the_axial_goldens(args, solver, test, tmp_path):
+    """The restated AxialExtendedInput through ref_driver: OTF_TRACKS with segmentation zones; CPULSSolver on OTF_STACKS
+    with a non-uniform Cmfd (Cmfd::setWidths, one CMFD group per MOC group) and its axial interpolation of the
+    prolongation (FSR average / centroid): 15 iterations, keff 1.26899E+00, 2137 FSRs"""
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([driver] + args + ["--solver", solver, "--results", res], check=True, capture_output=True)
+    assert open(res).read() == GOLDENS[test]

@@ -1,8 +1,9 @@
-"""Nine more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
+"""Twelve more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
 in tests/test_oracle.py): tests/test_2d_gradient_linear_source, tests/test_split_segments,
 tests/test_split_segments_cmfd, tests/test_forward_3D_lattice_symmetry, tests/test_cmfd_pwr_assembly,
 tests/test_cmfd_vacuum_boundary, tests/test_cmfd_periodic_boundaries, tests/test_cmfd_linear_source,
-tests/test_transport_stabilization.  Added when the
+tests/test_transport_stabilization, tests/test_axial_segmentation, tests/test_cmfd_axial_interpolation_average,
+tests/test_cmfd_axial_interpolation_centroid.  Added when the
 round's GPU budget was spent: their CPU halves are verified, the GPU halves run for the first time on the driver's box
 (hence the late file name: the rest of the suite runs first)."""
 import hashlib
@@ -156,3 +157,47 @@ def test_transport_stabilization_golden_from_the_gpu(where, tmp_path):
     assert hashlib.sha512(cpu.encode()).hexdigest() == GOLDENS["test_transport_stabilization"].strip()
     gpu = drive(STABILIZATION_ARGS + ["--solver", "b200ls"], tmp_path, env={"B200_HOST_CMFD": "1"} if where == "host" else None)
     print("digest from the GPU equals the reference's:", same_to_printed_precision(gpu, cpu))
+
+
+# ------------------------------------------------------------------ AxialExtendedInput: extruded FSRs with different axial meshes
+AXIAL = ["--model", "axial-extended", "--dims", "3", "--azim", "4", "--quiet", "--no-fluxes"]
+AXIAL_SEGMENTATION_ARGS = AXIAL + ["--polar", "2", "--spacing", "0.24", "--zspacing", "0.9", "--formation", "otf-tracks",
+                                   "--seg-zones", "0,1,2,3,4,5,6,7,8,9,10,20", "--max-iters", "30"]
+AXIAL_INTERPOLATION_ARGS = AXIAL + ["--polar", "4", "--quad", "gl", "--spacing", "0.1", "--zspacing", "0.5", "--formation",
+                                    "otf-stacks", "--seg-zones", "0,17,18,20", "--cmfd", "1x1", "--cmfd-widths",
+                                    "0.05,1.26,1.26,0.05;0.05,1.26,1.26,0.05;1,2,3,4,1,2,3,4", "--cmfd-sor", "1.5",
+                                    "--cmfd-relax", "0.7", "--cmfd-all-groups", "--no-knearest", "--tol", "1e-4",
+                                    "--threads", "4", "--results-fsrs"]
+
+
+@pytest.mark.parametrize("tracer", ["device", "host"])
+def test_axial_segmentation_golden_from_the_gpu(tracer, tmp_path):
+    """OTF_TRACKS with segmentation zones on a non-uniform, axially heterogeneous lattice: the device tracer (and the
+    host expansion, B200_HOST_OTF=1) give the reference's 30 unconverged iterations and k_eff to the printed digits"""
+    out = drive(AXIAL_SEGMENTATION_ARGS + ["--solver", "b200"], tmp_path, env={"B200_HOST_OTF": "1"} if tracer == "host" else None)
+    assert out == GOLDENS["test_axial_segmentation"]
+
+
+def test_axial_segmentation_golden_from_python():
+    """the same golden through the Python mirror on the tracks dumped from the reference (explicit 3D segments)"""
+    r = in_child("""
+from oracle.oracle_py import format_harness_results
+ft, ref = load_case("axial_extended")
+s = B200Solver(ft)
+s.computeEigenvalue(30, FISSION_SOURCE)
+print("RESULT " + json.dumps({"iters": s.getNumIterations(), "dk_pcm": abs(s.getKeff() - ref["keff"]) * 1e5,
+                              "harness": format_harness_results(s.getNumIterations(), s.getKeff())}))
+""")
+    assert r["iters"] == 30 and r["dk_pcm"] < 1e-4
+    assert r["harness"] == GOLDENS["test_axial_segmentation"]
+
+
+@pytest.mark.parametrize("where", ["device", "host"])
+@pytest.mark.parametrize("interp,test", [("1", "test_cmfd_axial_interpolation_average"),
+                                         ("2", "test_cmfd_axial_interpolation_centroid")])
+def test_cmfd_axial_interpolation_goldens_from_the_gpu(interp, test, where, tmp_path):
+    """B200LSSolver on OTF_STACKS with a non-uniform Cmfd (Cmfd::setWidths) and the axial interpolation of its
+    prolongation: 15 iterations, keff 1.26899E+00, 2137 FSRs"""
+    out = drive(AXIAL_INTERPOLATION_ARGS + ["--cmfd-axial-interp", interp, "--solver", "b200ls"], tmp_path,
+                env={"B200_HOST_CMFD": "1"} if where == "host" else None)
+    assert out == GOLDENS[test]
