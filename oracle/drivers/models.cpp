@@ -80,8 +80,9 @@ Model simple_lattice(int dims) {
   md.materials = make_c5g7_materials();
   XPlane* xmin = new XPlane(-2.0); XPlane* xmax = new XPlane(2.0);
   YPlane* ymin = new YPlane(-2.0); YPlane* ymax = new YPlane(2.0);
-  xmin->setBoundaryType(REFLECTIVE); xmax->setBoundaryType(REFLECTIVE);
-  ymin->setBoundaryType(REFLECTIVE); ymax->setBoundaryType(REFLECTIVE);
+  /* --vacuum-mask: bit 0 xmin, 1 xmax, 2 ymin, 3 ymax, 4 zmin (tests/test_OTF_transport switches three sides) */
+  xmin->setBoundaryType((g_vacuum_mask & 1) ? VACUUM : REFLECTIVE); xmax->setBoundaryType((g_vacuum_mask & 2) ? VACUUM : REFLECTIVE);
+  ymin->setBoundaryType((g_vacuum_mask & 4) ? VACUUM : REFLECTIVE); ymax->setBoundaryType((g_vacuum_mask & 8) ? VACUUM : REFLECTIVE);
 
   const double radii[3] = {0.4, 0.3, 0.2};
   Universe* pins[3];
@@ -107,7 +108,7 @@ Model simple_lattice(int dims) {
   root_cell->addSurface(+1, ymin); root_cell->addSurface(-1, ymax);
   if (dims == 3) {
     ZPlane* zmin = new ZPlane(-5.0); ZPlane* zmax = new ZPlane(5.0);
-    zmin->setBoundaryType(REFLECTIVE);
+    zmin->setBoundaryType((g_vacuum_mask & 16) ? VACUUM : REFLECTIVE);
     zmax->setBoundaryType(VACUUM);
     root_cell->addSurface(+1, zmin); root_cell->addSurface(-1, zmax);
   }

@@ -334,6 +334,7 @@ int main(int argc, char** argv) {
   else if (solver_name == "cpuls") solver = cpu_solver = new CPULSSolver(tg);
   else solver = cpu_solver = new CPUSolver(tg);
   if (cpu_solver != NULL) cpu_solver->setNumThreads(threads);
+  if (flag(argc, argv, "--otf-transport")) solver->setOTFTransport();     /* tests/test_OTF_transport (CPU solvers trace while they sweep) */
   if (b200_solver != NULL) b200_solver->setNumThreads(threads);   /* host side: flatten, Cmfd */
   if (b200_solver != NULL && flag(argc, argv, "--host-cmfd")) b200_solver->setCmfdOnDevice(false);
   solver->setConvergenceThreshold(tol);

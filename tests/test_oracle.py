@@ -402,3 +402,21 @@ def test_ref_driver_reproduces_the_axial_goldens(args, solver, test, tmp_path):
     res = os.path.join(tmp_path, "res.dat")
     subprocess.run([driver] + args + ["--solver", solver, "--results", res], check=True, capture_output=True)
     assert open(res).read() == GOLDENS[test]
+
+
+OTF_TRANSPORT_ARGS = ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "4", "--spacing", "0.4",
+                      "--zspacing", "1.2", "--formation", "otf-stacks", "--vacuum-mask", "22", "--cmfd", "4x4x4",
+                      "--cmfd-relax", "1.0", "--cmfd-sor", "1.5", "--tol", "1e-3", "--threads", "4", "--quiet", "--no-fluxes"]
+
+
+def test_ref_driver_reproduces_the_otf_transport_golden(tmp_path):
+    """tests/test_OTF_transport: the 3D lattice with VACUUM on xmax, ymin and zmin (and zmax), OTF_STACKS, CMFD 4 x 4 x 4,
+    CPUSolver::setOTFTransport (segments traced while sweeping): 20 iterations, keff 5.84272E-02"""
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([driver] + OTF_TRANSPORT_ARGS + ["--otf-transport", "--solver", "cpu", "--results", res], check=True,
+                   capture_output=True)
+    assert open(res).read() == GOLDENS["test_OTF_transport"]

@@ -1,9 +1,9 @@
-"""Twelve more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
+"""Thirteen more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
 in tests/test_oracle.py): tests/test_2d_gradient_linear_source, tests/test_split_segments,
 tests/test_split_segments_cmfd, tests/test_forward_3D_lattice_symmetry, tests/test_cmfd_pwr_assembly,
 tests/test_cmfd_vacuum_boundary, tests/test_cmfd_periodic_boundaries, tests/test_cmfd_linear_source,
 tests/test_transport_stabilization, tests/test_axial_segmentation, tests/test_cmfd_axial_interpolation_average,
-tests/test_cmfd_axial_interpolation_centroid.  Added when the
+tests/test_cmfd_axial_interpolation_centroid, tests/test_OTF_transport.  Added when the
 round's GPU budget was spent: their CPU halves are verified, the GPU halves run for the first time on the driver's box
 (hence the late file name: the rest of the suite runs first)."""
 import hashlib
@@ -201,3 +201,17 @@ def test_cmfd_axial_interpolation_goldens_from_the_gpu(interp, test, where, tmp_
     out = drive(AXIAL_INTERPOLATION_ARGS + ["--cmfd-axial-interp", interp, "--solver", "b200ls"], tmp_path,
                 env={"B200_HOST_CMFD": "1"} if where == "host" else None)
     assert out == GOLDENS[test]
+
+
+OTF_TRANSPORT_ARGS = ["--model", "simple-lattice", "--dims", "3", "--azim", "4", "--polar", "4", "--spacing", "0.4",
+                      "--zspacing", "1.2", "--formation", "otf-stacks", "--vacuum-mask", "22", "--cmfd", "4x4x4",
+                      "--cmfd-relax", "1.0", "--cmfd-sor", "1.5", "--tol", "1e-3", "--threads", "4", "--quiet", "--no-fluxes"]
+
+
+@pytest.mark.parametrize("where", ["device", "host"])
+def test_otf_transport_golden_from_the_gpu(where, tmp_path):
+    """tests/test_OTF_transport (the reference traces its segments while sweeping): z-stacks traced on the device with
+    their CMFD surfaces, VACUUM on four of the six sides, CMFD 4 x 4 x 4 on the device / on the host: 20 iterations,
+    keff 5.84272E-02"""
+    out = drive(OTF_TRANSPORT_ARGS + ["--solver", "b200"], tmp_path, env={"B200_HOST_CMFD": "1"} if where == "host" else None)
+    assert out == GOLDENS["test_OTF_transport"]
