@@ -19,6 +19,7 @@
  *                   [--cmfd NXxNY[xNZ]] [--host-cmfd (B200 solvers: the reference's host Cmfd instead of the device CMFD)]
  *                   [--check-cmfd-split (compare the library's current-splitting tables with Cmfd's, no GPU needed)]
  *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
+ *                   [--restart (Solver::setRestartStatus(true) and a second computeEigenvalue)] [--otf-transport]
  *                   [--seg-zones z0,z1,.. (TrackGenerator3D::setSegmentationZones)]
  *                   [--cmfd-widths "x..;y..;z.." (Cmfd::setWidths; give --cmfd 1x1 as well)] [--cmfd-axial-interp 0|1|2]
  *                   [--stabilize F:T | --stabilize-sequence F:T,F:T,...] [--negative-water-scatter]
@@ -380,6 +381,10 @@ int main(int argc, char** argv) {
   } else if (mode == "eigen") {
     if (solver_name == "b200-fused") b200_solver->computeEigenvalueFused(max_iters, rt);
     else solver->computeEigenvalue(max_iters, rt);
+    if (flag(argc, argv, "--restart")) {          /* tests/test_cmfd_restart: a second solve that keeps the fluxes */
+      solver->setRestartStatus(true);
+      solver->computeEigenvalue(max_iters, rt);
+    }
   } else if (mode == "flux") {
     solver->computeFlux(max_iters);                       /* tests/testing_harness.py:151 */
   } else if (mode == "source") {

@@ -332,6 +332,9 @@ PWR_CASES = {
     "test_cmfd_vacuum_boundary": PWR + ["--cmfd-relax", "0.7", "--cmfd-sor", "1.0", "--vacuum-mask", "1", "--solver", "cpu"],
     "test_cmfd_periodic_boundaries": PWR + ["--cmfd-relax", "0.7", "--cmfd-sor", "1.0", "--periodic-mask", "3", "--solver", "cpu"],
     "test_cmfd_linear_source": PWR + ["--cmfd-relax", "0.7", "--cmfd-sor", "1.0", "--solver", "cpuls"],
+    # a Cmfd with its default group structure (7 groups) and k-nearest; Solver::setRestartStatus(True) and a second
+    # computeEigenvalue that starts from the converged fluxes (2 iterations)
+    "test_cmfd_restart": PWR + ["--cmfd-relax", "1.0", "--cmfd-all-groups", "--no-knearest", "--restart", "--solver", "cpu"],
 }
 
 

@@ -1,9 +1,9 @@
-"""Thirteen more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
+"""Fourteen more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
 in tests/test_oracle.py): tests/test_2d_gradient_linear_source, tests/test_split_segments,
 tests/test_split_segments_cmfd, tests/test_forward_3D_lattice_symmetry, tests/test_cmfd_pwr_assembly,
 tests/test_cmfd_vacuum_boundary, tests/test_cmfd_periodic_boundaries, tests/test_cmfd_linear_source,
 tests/test_transport_stabilization, tests/test_axial_segmentation, tests/test_cmfd_axial_interpolation_average,
-tests/test_cmfd_axial_interpolation_centroid, tests/test_OTF_transport.  Added when the
+tests/test_cmfd_axial_interpolation_centroid, tests/test_OTF_transport, tests/test_cmfd_restart.  Added when the
 round's GPU budget was spent: their CPU halves are verified, the GPU halves run for the first time on the driver's box
 (hence the late file name: the rest of the suite runs first)."""
 import hashlib
@@ -126,6 +126,7 @@ PWR_CASES = {
     "test_cmfd_vacuum_boundary": (PWR + ["--cmfd-relax", "0.7", "--cmfd-sor", "1.0", "--vacuum-mask", "1"], "cpu", "b200"),
     "test_cmfd_periodic_boundaries": (PWR + ["--cmfd-relax", "0.7", "--cmfd-sor", "1.0", "--periodic-mask", "3"], "cpu", "b200"),
     "test_cmfd_linear_source": (PWR + ["--cmfd-relax", "0.7", "--cmfd-sor", "1.0"], "cpuls", "b200ls"),
+    "test_cmfd_restart": (PWR + ["--cmfd-relax", "1.0", "--cmfd-all-groups", "--no-knearest", "--restart"], "cpu", "b200"),
 }
 
 
