@@ -19,6 +19,7 @@
  *                   [--cmfd NXxNY[xNZ]] [--host-cmfd (B200 solvers: the reference's host Cmfd instead of the device CMFD)]
  *                   [--check-cmfd-split (compare the library's current-splitting tables with Cmfd's, no GPU needed)]
  *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
+ *                   [--repeat N (the same eigenvalue solve N times on one solver; --results then holds one "Iters / keff" line per solve)]
  *                   [--restart (Solver::setRestartStatus(true) and a second computeEigenvalue)] [--otf-transport]
  *                   [--seg-zones z0,z1,.. (TrackGenerator3D::setSegmentationZones)]
  *                   [--cmfd-widths "x..;y..;z.." (Cmfd::setWidths; give --cmfd 1x1 as well)] [--cmfd-axial-interp 0|1|2]
@@ -373,10 +374,20 @@ int main(int argc, char** argv) {
   if (stab_type >= 0) solver->stabilizeTransport(stab_factor, (stabilizationType)stab_type);
   if (max_tau_arg > 0.) solver->setMaxOpticalLength(max_tau_arg);     /* tests/test_split_segments */
 
+  const int repeat = atoi(arg(argc, argv, "--repeat", "1"));
+  std::string multisim;
   if (mode == "eigen" && !stab_sequence.empty()) {
     for (size_t i = 0; i < stab_sequence.size(); i++) {
       solver->stabilizeTransport(stab_sequence[i].first, (stabilizationType)stab_sequence[i].second);
       solver->computeEigenvalue(max_iters, rt);
+    }
+  } else if (mode == "eigen" && repeat > 1) {
+    /* tests/testing_harness.py:398-425 (MultiSimTestHarness): the same solve several times on one solver object */
+    for (int i = 0; i < repeat; i++) {
+      solver->computeEigenvalue(max_iters, rt);
+      char line[96];
+      snprintf(line, sizeof line, "Iters: %d\tkeff: %12.5E\n", solver->getNumIterations(), solver->getKeff());
+      multisim += line;
     }
   } else if (mode == "eigen") {
     if (solver_name == "b200-fused") b200_solver->computeEigenvalueFused(max_iters, rt);
@@ -403,7 +414,11 @@ int main(int argc, char** argv) {
   if (solved && !flag(argc, argv, "--quiet")) solver->printTimerReport();
 
   /* ---- results in the harness format ---- */
-  if (solved && !results.empty()) {
+  if (solved && !results.empty() && !multisim.empty()) {
+    FILE* f = fopen(results.c_str(), "w");
+    fputs(multisim.c_str(), f);
+    fclose(f);
+  } else if (solved && !results.empty()) {
     FILE* f = fopen(results.c_str(), "w");
     fprintf(f, "# Iterations: %d\n", solver->getNumIterations());
     if (mode == "eigen" && !flag(argc, argv, "--no-keff")) fprintf(f, "keff: %12.5E\n", solver->getKeff());

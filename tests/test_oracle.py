@@ -423,3 +423,35 @@ def test_ref_driver_reproduces_the_otf_transport_golden(tmp_path):
     subprocess.run([driver] + OTF_TRANSPORT_ARGS + ["--otf-transport", "--solver", "cpu", "--results", res], check=True,
                    capture_output=True)
     assert open(res).read() == GOLDENS["test_OTF_transport"]
+
+
+MULTISIM_CASES = {
+    "test_multisim_simple": ["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--solver", "cpu"],
+    "test_multisim_linear_source": ["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--solver", "cpuls"],
+    "test_multisim_cmfd": ["--model", "pwr-assembly", "--azim", "4", "--spacing", "0.1", "--cmfd", "17x17", "--cmfd-relax", "1.0",
+                           "--cmfd-sor", "1.5", "--max-iters", "5", "--solver", "cpu"],
+}
+
+
+@pytest.mark.parametrize("test", sorted(MULTISIM_CASES))
+def test_ref_driver_reproduces_the_multi_simulation_goldens(test, tmp_path):
+    """MultiSimTestHarness (tests/testing_harness.py:398-425): the same eigenvalue solve three times on one solver
+    object gives the same iteration count and k_eff three times - flat, linear source, with CMFD"""
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([driver] + MULTISIM_CASES[test] + ["--repeat", "3", "--quiet", "--results", res], check=True,
+                   capture_output=True)
+    assert open(res).read() == GOLDENS[test]
+
+
+def test_oracle_repeated_solves_match_the_multi_simulation_golden():
+    """the oracle solved three times in a row on the pin cell: tests/test_multisim_simple/results_true.dat"""
+    ft, _ = load_case("pin_cell")
+    s, out = OracleSolver(ft), ""
+    for _ in range(3):
+        n = s.computeEigenvalue(500, 1e-5, FISSION_SOURCE)
+        out += "Iters: {0}\tkeff: {1:12.5E}\n".format(n, s.getKeff())
+    assert out == GOLDENS["test_multisim_simple"]

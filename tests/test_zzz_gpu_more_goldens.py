@@ -1,9 +1,10 @@
-"""Fourteen more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
+"""Seventeen more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
 in tests/test_oracle.py): tests/test_2d_gradient_linear_source, tests/test_split_segments,
 tests/test_split_segments_cmfd, tests/test_forward_3D_lattice_symmetry, tests/test_cmfd_pwr_assembly,
 tests/test_cmfd_vacuum_boundary, tests/test_cmfd_periodic_boundaries, tests/test_cmfd_linear_source,
 tests/test_transport_stabilization, tests/test_axial_segmentation, tests/test_cmfd_axial_interpolation_average,
-tests/test_cmfd_axial_interpolation_centroid, tests/test_OTF_transport, tests/test_cmfd_restart.  Added when the
+tests/test_cmfd_axial_interpolation_centroid, tests/test_OTF_transport, tests/test_cmfd_restart, tests/test_multisim_simple,
+tests/test_multisim_linear_source, tests/test_multisim_cmfd.  Added when the
 round's GPU budget was spent: their CPU halves are verified, the GPU halves run for the first time on the driver's box
 (hence the late file name: the rest of the suite runs first)."""
 import hashlib
@@ -216,3 +217,19 @@ def test_otf_transport_golden_from_the_gpu(where, tmp_path):
     keff 5.84272E-02"""
     out = drive(OTF_TRANSPORT_ARGS + ["--solver", "b200"], tmp_path, env={"B200_HOST_CMFD": "1"} if where == "host" else None)
     assert out == GOLDENS["test_OTF_transport"]
+
+
+MULTISIM_CASES = {
+    "test_multisim_simple": (["--model", "pin-cell", "--azim", "4", "--spacing", "0.1"], "b200"),
+    "test_multisim_linear_source": (["--model", "pin-cell", "--azim", "4", "--spacing", "0.1"], "b200ls"),
+    "test_multisim_cmfd": (["--model", "pwr-assembly", "--azim", "4", "--spacing", "0.1", "--cmfd", "17x17", "--cmfd-relax", "1.0",
+                            "--cmfd-sor", "1.5", "--max-iters", "5"], "b200"),
+}
+
+
+@pytest.mark.parametrize("test", sorted(MULTISIM_CASES))
+def test_multi_simulation_goldens_from_the_gpu(test, tmp_path):
+    """MultiSimTestHarness: three eigenvalue solves in a row on one B200 solver object (device image reused, materials
+    and fluxes re-initialised by the base class) print the reference's three identical lines"""
+    args, solver = MULTISIM_CASES[test]
+    assert drive(args + ["--repeat", "3", "--quiet", "--solver", solver], tmp_path) == GOLDENS[test]
