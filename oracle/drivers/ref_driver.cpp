@@ -19,6 +19,7 @@
  *                   [--cmfd NXxNY[xNZ]] [--host-cmfd (B200 solvers: the reference's host Cmfd instead of the device CMFD)]
  *                   [--check-cmfd-split (compare the library's current-splitting tables with Cmfd's, no GPU needed)]
  *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
+ *                   [--azim-sequence n1,n2,.. (tracks laid again with another azimuthal count before every solve)]
  *                   [--repeat N (the same eigenvalue solve N times on one solver; --results then holds one "Iters / keff" line per solve)]
  *                   [--restart (Solver::setRestartStatus(true) and a second computeEigenvalue)] [--otf-transport]
  *                   [--seg-zones z0,z1,.. (TrackGenerator3D::setSegmentationZones)]
@@ -375,12 +376,38 @@ int main(int argc, char** argv) {
   if (max_tau_arg > 0.) solver->setMaxOpticalLength(max_tau_arg);     /* tests/test_split_segments */
 
   const int repeat = atoi(arg(argc, argv, "--repeat", "1"));
+  std::vector<int> azim_sequence;
+  {
+    std::string st = arg(argc, argv, "--azim-sequence", "");
+    for (size_t pos = 0; pos < st.size();) {
+      if (st[pos] == ',') { pos++; continue; }
+      char* end = NULL;
+      azim_sequence.push_back((int)strtol(st.c_str() + pos, &end, 10));
+      pos = end - st.c_str();
+    }
+  }
   std::string multisim;
   if (mode == "eigen" && !stab_sequence.empty()) {
     for (size_t i = 0; i < stab_sequence.size(); i++) {
       solver->stabilizeTransport(stab_sequence[i].first, (stabilizationType)stab_sequence[i].second);
       solver->computeEigenvalue(max_iters, rt);
     }
+  } else if (mode == "eigen" && !azim_sequence.empty()) {
+    /* tests/test_multisim_num_azim: the tracks are laid again with another number of azimuthal angles between
+     * the solves, on the same TrackGenerator and the same solver */
+    std::string counts;
+    for (size_t i = 0; i < azim_sequence.size(); i++) {
+      tg->setNumAzim(azim_sequence[i]);
+      tg->generateTracks();
+      solver->setTrackGenerator(tg);
+      solver->computeEigenvalue(max_iters, rt);
+      char line[96];
+      snprintf(line, sizeof line, "# tracks: %ld\t# segments: %ld\n", (long)tg->getNumTracks(), (long)tg->getNumSegments());
+      counts += line;
+      snprintf(line, sizeof line, "Iters: %d\tkeff: %12.5E\n", solver->getNumIterations(), solver->getKeff());
+      multisim += line;
+    }
+    multisim = counts + multisim;
   } else if (mode == "eigen" && repeat > 1) {
     /* tests/testing_harness.py:398-425 (MultiSimTestHarness): the same solve several times on one solver object */
     for (int i = 0; i < repeat; i++) {

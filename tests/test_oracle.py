@@ -455,3 +455,16 @@ def test_oracle_repeated_solves_match_the_multi_simulation_golden():
         n = s.computeEigenvalue(500, 1e-5, FISSION_SOURCE)
         out += "Iters: {0}\tkeff: {1:12.5E}\n".format(n, s.getKeff())
     assert out == GOLDENS["test_multisim_simple"]
+
+
+def test_ref_driver_reproduces_the_num_azim_golden(tmp_path):
+    """tests/test_multisim_num_azim: 4, 8 and 16 azimuthal angles one after the other on the same TrackGenerator and
+    the same solver (tracks regenerated in between)"""
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([driver, "--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--azim-sequence", "4,8,16", "--quiet",
+                    "--solver", "cpu", "--results", res], check=True, capture_output=True)
+    assert open(res).read() == GOLDENS["test_multisim_num_azim"]

@@ -1,10 +1,10 @@
-"""Seventeen more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
+"""Eighteen more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
 in tests/test_oracle.py): tests/test_2d_gradient_linear_source, tests/test_split_segments,
 tests/test_split_segments_cmfd, tests/test_forward_3D_lattice_symmetry, tests/test_cmfd_pwr_assembly,
 tests/test_cmfd_vacuum_boundary, tests/test_cmfd_periodic_boundaries, tests/test_cmfd_linear_source,
 tests/test_transport_stabilization, tests/test_axial_segmentation, tests/test_cmfd_axial_interpolation_average,
 tests/test_cmfd_axial_interpolation_centroid, tests/test_OTF_transport, tests/test_cmfd_restart, tests/test_multisim_simple,
-tests/test_multisim_linear_source, tests/test_multisim_cmfd.  Added when the
+tests/test_multisim_linear_source, tests/test_multisim_cmfd, tests/test_multisim_num_azim.  Added when the
 round's GPU budget was spent: their CPU halves are verified, the GPU halves run for the first time on the driver's box
 (hence the late file name: the rest of the suite runs first)."""
 import hashlib
@@ -233,3 +233,11 @@ def test_multi_simulation_goldens_from_the_gpu(test, tmp_path):
     and fluxes re-initialised by the base class) print the reference's three identical lines"""
     args, solver = MULTISIM_CASES[test]
     assert drive(args + ["--repeat", "3", "--quiet", "--solver", solver], tmp_path) == GOLDENS[test]
+
+
+def test_num_azim_golden_from_the_gpu(tmp_path):
+    """tests/test_multisim_num_azim: the tracks are laid again with 4, 8 and 16 azimuthal angles between the solves of one
+    B200Solver - the device image must follow the TrackGenerator (B200SolverT::ensureDevice), never a stale one"""
+    out = drive(["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--azim-sequence", "4,8,16", "--quiet",
+                 "--solver", "b200"], tmp_path)
+    assert out == GOLDENS["test_multisim_num_azim"]
