@@ -222,6 +222,12 @@ void B200SolverT<Base>::ensureDevice() {
   double key = (double)n_seg * 1e-3 + (double)_track_generator->getNumTracks() + 7. * (double)_num_FSRs;
   if (_FSR_volumes != NULL)
     for (long r = 0; r < _num_FSRs; r++) key += (double)_FSR_volumes[r] * (1. + 1e-3 * (double)(r % 977));
+  /* ... and the identity of the FSR materials: the device's FSR -> material indices follow the order of
+   * Geometry::getAllMaterials() at flatten time, which changes when cells are refilled with other (e.g. cloned)
+   * Material objects between two solves (tests/test_multisim_materials) */
+  if (this->_FSR_materials != NULL)
+    for (long r = 0; r < _num_FSRs; r++)
+      if (this->_FSR_materials[r] != NULL) key += 1e-3 * (double)this->_FSR_materials[r]->getId() * (double)(1 + r % 31);
   {
     Quadrature* q = _track_generator->getQuadrature();
     for (int a = 0; a < q->getNumAzimAngles() / 2; a++)

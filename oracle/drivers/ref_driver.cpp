@@ -20,6 +20,7 @@
  *                   [--check-cmfd-split (compare the library's current-splitting tables with Cmfd's, no GPU needed)]
  *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
  *                   [--azim-sequence n1,n2,.. (tracks laid again with another azimuthal count before every solve)]
+ *                   [--clone-materials (with --repeat: cells refilled with clones of their Materials before every solve)]
  *                   [--repeat N (the same eigenvalue solve N times on one solver; --results then holds one "Iters / keff" line per solve)]
  *                   [--restart (Solver::setRestartStatus(true) and a second computeEigenvalue)] [--otf-transport]
  *                   [--seg-zones z0,z1,.. (TrackGenerator3D::setSegmentationZones)]
@@ -411,6 +412,12 @@ int main(int argc, char** argv) {
   } else if (mode == "eigen" && repeat > 1) {
     /* tests/testing_harness.py:398-425 (MultiSimTestHarness): the same solve several times on one solver object */
     for (int i = 0; i < repeat; i++) {
+      if (flag(argc, argv, "--clone-materials")) {
+        /* tests/test_multisim_materials: every material cell is refilled with a clone of its Material before each solve */
+        std::map<int, Cell*> cells = geometry->getAllMaterialCells();
+        for (std::map<int, Cell*>::iterator it = cells.begin(); it != cells.end(); ++it)
+          it->second->setFill(it->second->getFillMaterial()->clone());
+      }
       solver->computeEigenvalue(max_iters, rt);
       char line[96];
       snprintf(line, sizeof line, "Iters: %d\tkeff: %12.5E\n", solver->getNumIterations(), solver->getKeff());

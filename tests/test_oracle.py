@@ -428,6 +428,8 @@ def test_ref_driver_reproduces_the_otf_transport_golden(tmp_path):
 MULTISIM_CASES = {
     "test_multisim_simple": ["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--solver", "cpu"],
     "test_multisim_linear_source": ["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--solver", "cpuls"],
+    # every material cell refilled with a clone of its Material before each solve
+    "test_multisim_materials": ["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--clone-materials", "--solver", "cpu"],
     "test_multisim_cmfd": ["--model", "pwr-assembly", "--azim", "4", "--spacing", "0.1", "--cmfd", "17x17", "--cmfd-relax", "1.0",
                            "--cmfd-sor", "1.5", "--max-iters", "5", "--solver", "cpu"],
 }

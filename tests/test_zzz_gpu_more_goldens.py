@@ -1,10 +1,11 @@
-"""Eighteen more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
+"""Nineteen more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
 in tests/test_oracle.py): tests/test_2d_gradient_linear_source, tests/test_split_segments,
 tests/test_split_segments_cmfd, tests/test_forward_3D_lattice_symmetry, tests/test_cmfd_pwr_assembly,
 tests/test_cmfd_vacuum_boundary, tests/test_cmfd_periodic_boundaries, tests/test_cmfd_linear_source,
 tests/test_transport_stabilization, tests/test_axial_segmentation, tests/test_cmfd_axial_interpolation_average,
 tests/test_cmfd_axial_interpolation_centroid, tests/test_OTF_transport, tests/test_cmfd_restart, tests/test_multisim_simple,
-tests/test_multisim_linear_source, tests/test_multisim_cmfd, tests/test_multisim_num_azim.  Added when the
+tests/test_multisim_linear_source, tests/test_multisim_cmfd, tests/test_multisim_num_azim,
+tests/test_multisim_materials.  Added when the
 round's GPU budget was spent: their CPU halves are verified, the GPU halves run for the first time on the driver's box
 (hence the late file name: the rest of the suite runs first)."""
 import hashlib
@@ -222,6 +223,9 @@ def test_otf_transport_golden_from_the_gpu(where, tmp_path):
 MULTISIM_CASES = {
     "test_multisim_simple": (["--model", "pin-cell", "--azim", "4", "--spacing", "0.1"], "b200"),
     "test_multisim_linear_source": (["--model", "pin-cell", "--azim", "4", "--spacing", "0.1"], "b200ls"),
+    # cells refilled with clones before each solve: Geometry::getAllMaterials() changes its order (clone ids follow the
+    # cells), the device image is rebuilt (B200SolverT::ensureDevice keys on the FSR materials)
+    "test_multisim_materials": (["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--clone-materials"], "b200"),
     "test_multisim_cmfd": (["--model", "pwr-assembly", "--azim", "4", "--spacing", "0.1", "--cmfd", "17x17", "--cmfd-relax", "1.0",
                             "--cmfd-sor", "1.5", "--max-iters", "5"], "b200"),
 }
