@@ -219,7 +219,8 @@ void B200SolverT<Base>::ensureDevice() {
   /* The device image is reused only for the very same tracks: a re-traced geometry can keep its
    * segment count while volumes, quadrature or FSR numbering change, so the key also covers the
    * track counts, the FSR volumes and the quadrature weights. */
-  double key = (double)n_seg * 1e-3 + (double)_track_generator->getNumTracks() + 7. * (double)_num_FSRs;
+  double key = (double)n_seg * 1e-3 + (double)_track_generator->getNumTracks() + 7. * (double)_num_FSRs
+             + 1e6 * (double)_num_groups;     /* a Material given another group structure between two solves */
   if (_FSR_volumes != NULL)
     for (long r = 0; r < _num_FSRs; r++) key += (double)_FSR_volumes[r] * (1. + 1e-3 * (double)(r % 977));
   /* ... and the identity of the FSR materials: the device's FSR -> material indices follow the order of

@@ -21,6 +21,7 @@
  *                   [--dump-tracks FILE] [--results FILE] [--json FILE] [--quiet] [--balance]
  *                   [--azim-sequence n1,n2,.. (tracks laid again with another azimuthal count before every solve)]
  *                   [--clone-materials (with --repeat: cells refilled with clones of their Materials before every solve)]
+ *                   [--multisim-groups (hom-inf: 1-group, then 2-group data in the same Material, two solves)]
  *                   [--repeat N (the same eigenvalue solve N times on one solver; --results then holds one "Iters / keff" line per solve)]
  *                   [--restart (Solver::setRestartStatus(true) and a second computeEigenvalue)] [--otf-transport]
  *                   [--seg-zones z0,z1,.. (TrackGenerator3D::setSegmentationZones)]
@@ -409,6 +410,26 @@ int main(int argc, char** argv) {
       multisim += line;
     }
     multisim = counts + multisim;
+  } else if (mode == "eigen" && flag(argc, argv, "--multisim-groups")) {
+    /* tests/test_multisim_num_groups: the infinite medium solved with 1-group, then with 2-group data given to the
+     * same Material object, on the same tracks and the same solver */
+    Material* m = md.materials["infinite medium"];
+    if (m == NULL) { fprintf(stderr, "ref_driver: --multisim-groups needs --model hom-inf\n"); return 2; }
+    for (int pass = 0; pass < 2; pass++) {
+      if (pass == 0) {
+        double nsf[1] = {0.0994076580}, ss[1] = {0.383259177}, chi[1] = {1.0}, st[1] = {0.452648699};
+        m->setNumEnergyGroups(1);
+        m->setNuSigmaF(nsf, 1); m->setSigmaS(ss, 1); m->setChi(chi, 1); m->setSigmaT(st, 1);
+      } else {
+        double nsf[2] = {0.0015, 0.325}, ss[4] = {0.1, 0.117, 0., 1.42}, chi[2] = {1.0, 0.0}, st[2] = {0.2208, 1.604};
+        m->setNumEnergyGroups(2);
+        m->setNuSigmaF(nsf, 2); m->setSigmaS(ss, 4); m->setChi(chi, 2); m->setSigmaT(st, 2);
+      }
+      solver->computeEigenvalue(max_iters, rt);
+      char line[96];
+      snprintf(line, sizeof line, "Iters: %d\tkeff: %12.5E\n", solver->getNumIterations(), solver->getKeff());
+      multisim += line;
+    }
   } else if (mode == "eigen" && repeat > 1) {
     /* tests/testing_harness.py:398-425 (MultiSimTestHarness): the same solve several times on one solver object */
     for (int i = 0; i < repeat; i++) {

@@ -470,3 +470,16 @@ def test_ref_driver_reproduces_the_num_azim_golden(tmp_path):
     subprocess.run([driver, "--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--azim-sequence", "4,8,16", "--quiet",
                     "--solver", "cpu", "--results", res], check=True, capture_output=True)
     assert open(res).read() == GOLDENS["test_multisim_num_azim"]
+
+
+def test_ref_driver_reproduces_the_num_groups_golden(tmp_path):
+    """tests/test_multisim_num_groups: the infinite medium with 1-group and then 2-group data set on the same Material,
+    solved one after the other on the same tracks and solver"""
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([driver, "--model", "hom-inf", "--azim", "4", "--spacing", "0.1", "--multisim-groups", "--quiet",
+                    "--solver", "cpu", "--results", res], check=True, capture_output=True)
+    assert open(res).read() == GOLDENS["test_multisim_num_groups"]

@@ -1,11 +1,11 @@
-"""Nineteen more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
+"""Twenty more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
 in tests/test_oracle.py): tests/test_2d_gradient_linear_source, tests/test_split_segments,
 tests/test_split_segments_cmfd, tests/test_forward_3D_lattice_symmetry, tests/test_cmfd_pwr_assembly,
 tests/test_cmfd_vacuum_boundary, tests/test_cmfd_periodic_boundaries, tests/test_cmfd_linear_source,
 tests/test_transport_stabilization, tests/test_axial_segmentation, tests/test_cmfd_axial_interpolation_average,
 tests/test_cmfd_axial_interpolation_centroid, tests/test_OTF_transport, tests/test_cmfd_restart, tests/test_multisim_simple,
 tests/test_multisim_linear_source, tests/test_multisim_cmfd, tests/test_multisim_num_azim,
-tests/test_multisim_materials.  Added when the
+tests/test_multisim_materials, tests/test_multisim_num_groups.  Added when the
 round's GPU budget was spent: their CPU halves are verified, the GPU halves run for the first time on the driver's box
 (hence the late file name: the rest of the suite runs first)."""
 import hashlib
@@ -245,3 +245,11 @@ def test_num_azim_golden_from_the_gpu(tmp_path):
     out = drive(["--model", "pin-cell", "--azim", "4", "--spacing", "0.1", "--azim-sequence", "4,8,16", "--quiet",
                  "--solver", "b200"], tmp_path)
     assert out == GOLDENS["test_multisim_num_azim"]
+
+
+def test_num_groups_golden_from_the_gpu(tmp_path):
+    """tests/test_multisim_num_groups: one group, then two groups in the same Material between two solves of one
+    B200Solver on the same tracks - the device image keys on the number of groups"""
+    out = drive(["--model", "hom-inf", "--azim", "4", "--spacing", "0.1", "--multisim-groups", "--quiet", "--solver", "b200"],
+                tmp_path)
+    assert out == GOLDENS["test_multisim_num_groups"]
