@@ -451,6 +451,19 @@ int main(int argc, char** argv) {
       solver->setRestartStatus(true);
       solver->computeEigenvalue(max_iters, rt);
     }
+  } else if ((mode == "flux" || mode == "source") && repeat > 1) {
+    /* tests/test_multisim_fixed_source: the fixed-source solve several times on one solver, iterations and fluxes of each */
+    long nf = geometry->getNumFSRs() * geometry->getNumEnergyGroups();
+    std::vector<FP_PRECISION> phi(nf);
+    for (int i = 0; i < repeat; i++) {
+      if (mode == "flux") solver->computeFlux(max_iters);
+      else solver->computeSource(max_iters, 1.0, rt);
+      char line[64];
+      snprintf(line, sizeof line, "Iters: %d\nfluxes:\n", solver->getNumIterations());
+      multisim += line;
+      solver->getFluxes(phi.data(), nf);
+      for (long j = 0; j < nf; j++) { snprintf(line, sizeof line, "%12.6E\n", phi[j]); multisim += line; }
+    }
   } else if (mode == "flux") {
     solver->computeFlux(max_iters);                       /* tests/testing_harness.py:151 */
   } else if (mode == "source") {

@@ -97,7 +97,7 @@ def main():
               "test_split_segments_cmfd", "test_forward_3D_lattice_symmetry", "test_cmfd_pwr_assembly",
               "test_cmfd_vacuum_boundary", "test_cmfd_periodic_boundaries", "test_cmfd_linear_source", "test_transport_stabilization", "test_axial_segmentation",
               "test_cmfd_axial_interpolation_average", "test_cmfd_axial_interpolation_centroid", "test_OTF_transport", "test_cmfd_restart", "test_multisim_simple",
-              "test_multisim_linear_source", "test_multisim_cmfd", "test_multisim_num_azim", "test_multisim_materials", "test_multisim_num_groups"):
+              "test_multisim_linear_source", "test_multisim_cmfd", "test_multisim_num_azim", "test_multisim_materials", "test_multisim_num_groups", "test_multisim_fixed_source"):
         gold[t] = open(os.path.join(REF, "tests", t, "results_true.dat")).read()
     json.dump(gold, open(os.path.join(HERE, "ref_goldens.json"), "w"), indent=1)
 

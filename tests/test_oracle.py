@@ -483,3 +483,26 @@ def test_ref_driver_reproduces_the_num_groups_golden(tmp_path):
     subprocess.run([driver, "--model", "hom-inf", "--azim", "4", "--spacing", "0.1", "--multisim-groups", "--quiet",
                     "--solver", "cpu", "--results", res], check=True, capture_output=True)
     assert open(res).read() == GOLDENS["test_multisim_num_groups"]
+
+
+def test_multisim_fixed_source_golden_from_the_oracle_and_the_reference(tmp_path):
+    """tests/test_multisim_fixed_source: computeSource three times in a row on the water box (source 1.0 in group 1);
+    the golden is the SHA-512 of the three 'Iters / fluxes' blocks - from the oracle on the dumped tracks and from the
+    unmodified reference through ref_driver"""
+    ft, ref = load_case("water_box")
+    s, out = OracleSolver(ft), ""
+    for fsr in ref["source_fsrs"]:
+        s.setFixedSourceByFSR(fsr, 1, 1.0)
+    for _ in range(3):
+        n = s.computeSource(500, 1.0, 1e-5, TOTAL_SOURCE)
+        out += "Iters: {0}\nfluxes:\n".format(n) + "\n".join("{0:12.6E}".format(f) for f in s.getFluxes()) + "\n"
+    assert hashlib.sha512(out.encode()).hexdigest() == GOLDENS["test_multisim_fixed_source"].strip()
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    res = os.path.join(tmp_path, "res.dat")
+    subprocess.run([driver, "--model", "water-box", "--azim", "4", "--spacing", "0.1", "--mode", "source", "--res", "total",
+                    "--fixed-source", "1:1.0", "--repeat", "3", "--quiet", "--solver", "cpu", "--results", res], check=True,
+                   capture_output=True)
+    assert open(res).read() == out

@@ -1,11 +1,12 @@
-"""Twenty more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
+"""Twenty-one more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
 in tests/test_oracle.py): tests/test_2d_gradient_linear_source, tests/test_split_segments,
 tests/test_split_segments_cmfd, tests/test_forward_3D_lattice_symmetry, tests/test_cmfd_pwr_assembly,
 tests/test_cmfd_vacuum_boundary, tests/test_cmfd_periodic_boundaries, tests/test_cmfd_linear_source,
 tests/test_transport_stabilization, tests/test_axial_segmentation, tests/test_cmfd_axial_interpolation_average,
 tests/test_cmfd_axial_interpolation_centroid, tests/test_OTF_transport, tests/test_cmfd_restart, tests/test_multisim_simple,
 tests/test_multisim_linear_source, tests/test_multisim_cmfd, tests/test_multisim_num_azim,
-tests/test_multisim_materials, tests/test_multisim_num_groups.  Added when the
+tests/test_multisim_materials, tests/test_multisim_num_groups,
+tests/test_multisim_fixed_source.  Added when the
 round's GPU budget was spent: their CPU halves are verified, the GPU halves run for the first time on the driver's box
 (hence the late file name: the rest of the suite runs first)."""
 import hashlib
@@ -253,3 +254,19 @@ def test_num_groups_golden_from_the_gpu(tmp_path):
     out = drive(["--model", "hom-inf", "--azim", "4", "--spacing", "0.1", "--multisim-groups", "--quiet", "--solver", "b200"],
                 tmp_path)
     assert out == GOLDENS["test_multisim_num_groups"]
+
+
+def test_multisim_fixed_source_golden_from_the_gpu(tmp_path):
+    """tests/test_multisim_fixed_source: computeSource three times in a row on one B200Solver (water box, source in
+    group 1): the reference run on this box gives the committed digest, the B200 run the same iteration counts and the
+    same fluxes to the printed digits"""
+    args = ["--model", "water-box", "--azim", "4", "--spacing", "0.1", "--mode", "source", "--res", "total",
+            "--fixed-source", "1:1.0", "--repeat", "3", "--quiet"]
+    cpu = drive(args + ["--solver", "cpu"], tmp_path)
+    assert hashlib.sha512(cpu.encode()).hexdigest() == GOLDENS["test_multisim_fixed_source"].strip()
+    gpu = drive(args + ["--solver", "b200"], tmp_path)
+    words = lambda text: [l for l in text.splitlines() if not l[0].isdigit() and not l[0] == "-"]
+    values = lambda text: np.array([float(l) for l in text.splitlines() if l[0].isdigit() or l[0] == "-"])
+    assert words(gpu) == words(cpu)                                  # "Iters: 130" / "fluxes:" three times
+    np.testing.assert_allclose(values(gpu), values(cpu), rtol=1.1e-6)
+    print("digest from the GPU equals the reference's:", gpu == cpu)
