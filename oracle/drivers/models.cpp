@@ -49,8 +49,9 @@ Model pin_cell(int dims) {
   ZCylinder* zcyl = new ZCylinder(0.0, 0.0, 1.0);
   XPlane* xmin = new XPlane(-2.0); XPlane* xmax = new XPlane(2.0);
   YPlane* ymin = new YPlane(-2.0); YPlane* ymax = new YPlane(2.0);
-  xmin->setBoundaryType(REFLECTIVE); xmax->setBoundaryType(REFLECTIVE);
-  ymin->setBoundaryType(REFLECTIVE); ymax->setBoundaryType(REFLECTIVE);
+  /* --vacuum-mask 15: the deck of tests/test_krylov_forward (all four sides VACUUM) */
+  xmin->setBoundaryType((g_vacuum_mask & 1) ? VACUUM : REFLECTIVE); xmax->setBoundaryType((g_vacuum_mask & 2) ? VACUUM : REFLECTIVE);
+  ymin->setBoundaryType((g_vacuum_mask & 4) ? VACUUM : REFLECTIVE); ymax->setBoundaryType((g_vacuum_mask & 8) ? VACUUM : REFLECTIVE);
 
   Cell* fuel = new Cell();
   fuel->setFill(md.materials["UO2"]);
