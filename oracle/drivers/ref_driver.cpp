@@ -22,6 +22,7 @@
  *                   [--azim-sequence n1,n2,.. (tracks laid again with another azimuthal count before every solve)]
  *                   [--clone-materials (with --repeat: cells refilled with clones of their Materials before every solve)]
  *                   [--multisim-groups (hom-inf: 1-group, then 2-group data in the same Material, two solves)]
+ *                   [--fission-rates (--json also holds computeFSRFissionRates with nu = false and nu = true)]
  *                   [--repeat N (the same eigenvalue solve N times on one solver; --results then holds one "Iters / keff" line per solve)]
  *                   [--restart (Solver::setRestartStatus(true) and a second computeEigenvalue)] [--otf-transport]
  *                   [--seg-zones z0,z1,.. (TrackGenerator3D::setSegmentationZones)]
@@ -548,6 +549,16 @@ int main(int argc, char** argv) {
       fprintf(f, " \"fluxes\": [");
       for (long i = 0; i < n_fsr * G; i++) fprintf(f, "%s%.17g", i ? ", " : "", phi[i]);
       fprintf(f, "],\n");
+      if (flag(argc, argv, "--fission-rates")) {
+        /* Solver::computeFSRFissionRates with its default nu = false (sigma_f, not nu-sigma_f) and with nu = true */
+        std::vector<double> rates(n_fsr);
+        for (int nu = 0; nu < 2; nu++) {
+          solver->computeFSRFissionRates(rates.data(), n_fsr, nu != 0);
+          fprintf(f, " \"%s\": [", nu ? "nu_fission_rates" : "fission_rates");
+          for (long i = 0; i < n_fsr; i++) fprintf(f, "%s%.17g", i ? ", " : "", rates[i]);
+          fprintf(f, "],\n");
+        }
+      }
     }
     fprintf(f, " \"ok\": true}\n");
     fclose(f);

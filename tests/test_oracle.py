@@ -506,3 +506,24 @@ def test_multisim_fixed_source_golden_from_the_oracle_and_the_reference(tmp_path
                     "--fixed-source", "1:1.0", "--repeat", "3", "--quiet", "--solver", "cpu", "--results", res], check=True,
                    capture_output=True)
     assert open(res).read() == out
+
+
+def test_fission_rates_without_nu_match_the_reference(tmp_path):
+    """Solver::computeFSRFissionRates with its default nu = false after TWO solves on one solver (the second solve
+    re-initialises the materials): the oracle on the dumped tracks against the unmodified reference (only
+    nu = true was covered, and a second solve used to wipe sigma_f on the device)"""
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/ref_driver was not built (no /root/reference at build time)")
+    js = os.path.join(tmp_path, "ref.json")
+    subprocess.run([driver, "--model", "simple-lattice", "--azim", "4", "--spacing", "0.12", "--repeat", "2", "--fission-rates",
+                    "--quiet", "--solver", "cpu", "--json", js], check=True, capture_output=True)
+    ref = json.load(open(js))
+    s, n, _ = solve("simple_lattice")
+    s.computeEigenvalue(500, 1e-5, FISSION_SOURCE)                    # second solve
+    assert n == ref["iterations"] == 187
+    rates = np.array(ref["fission_rates"])
+    assert rates.max() > 0 and np.count_nonzero(rates) < rates.size    # fuel only
+    np.testing.assert_allclose(s.computeFSRFissionRates(nu=False), rates, rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(s.computeFSRFissionRates(nu=True), ref["nu_fission_rates"], rtol=1e-10, atol=1e-14)

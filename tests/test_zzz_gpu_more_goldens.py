@@ -270,3 +270,34 @@ def test_multisim_fixed_source_golden_from_the_gpu(tmp_path):
     assert words(gpu) == words(cpu)                                  # "Iters: 130" / "fluxes:" three times
     np.testing.assert_allclose(values(gpu), values(cpu), rtol=1.1e-6)
     print("digest from the GPU equals the reference's:", gpu == cpu)
+
+
+def test_fission_rates_without_nu_after_two_solves(tmp_path):
+    """the second solve of a B200Solver used to upload an all-zero sigma_f, after which
+    computeFSRFissionRates(nu = false) - the reference's default - returned zeros.  Two solves in a row through the
+    plug-in, rates with and without nu against CPUSolver; the same through the Python mirror against the oracle."""
+    if not os.path.exists(DRIVER):
+        pytest.skip("ref_driver not built")
+    out = {}
+    for solver in ("cpu", "b200"):
+        js = os.path.join(tmp_path, solver + ".json")
+        subprocess.run([DRIVER, "--model", "simple-lattice", "--azim", "4", "--spacing", "0.12", "--repeat", "2",
+                        "--fission-rates", "--quiet", "--solver", solver, "--json", js], check=True, capture_output=True,
+                       timeout=240)
+        out[solver] = json.load(open(js))
+    assert out["b200"]["iterations"] == out["cpu"]["iterations"] == 187
+    for key in ("fission_rates", "nu_fission_rates"):
+        ref = np.array(out["cpu"][key])
+        assert ref.max() > 0
+        np.testing.assert_allclose(out["b200"][key], ref, rtol=1e-8, atol=1e-14)
+    r = in_child("""
+from oracle.oracle_py import OracleSolver
+ft, ref = load_case("simple_lattice")
+gpu, cpu = B200Solver(ft), OracleSolver(ft)
+for _ in range(2):
+    gpu.computeEigenvalue(500, FISSION_SOURCE)
+    cpu.computeEigenvalue(500, 1e-5, FISSION_SOURCE)
+a, b = gpu.computeFSRFissionRates(nu=False), cpu.computeFSRFissionRates(nu=False)
+print("RESULT " + json.dumps({"max": float(b.max()), "err": float(np.max(np.abs(a - b)) / b.max())}))
+""")
+    assert r["max"] > 0 and r["err"] < 1e-8
