@@ -1,14 +1,16 @@
-"""Twenty-one more of the reference's committed goldens from the GPU (pinned for the oracle and for ref_driver on the CPU
-in tests/test_oracle.py): tests/test_2d_gradient_linear_source, tests/test_split_segments,
-tests/test_split_segments_cmfd, tests/test_forward_3D_lattice_symmetry, tests/test_cmfd_pwr_assembly,
-tests/test_cmfd_vacuum_boundary, tests/test_cmfd_periodic_boundaries, tests/test_cmfd_linear_source,
-tests/test_transport_stabilization, tests/test_axial_segmentation, tests/test_cmfd_axial_interpolation_average,
-tests/test_cmfd_axial_interpolation_centroid, tests/test_OTF_transport, tests/test_cmfd_restart, tests/test_multisim_simple,
-tests/test_multisim_linear_source, tests/test_multisim_cmfd, tests/test_multisim_num_azim,
-tests/test_multisim_materials, tests/test_multisim_num_groups,
-tests/test_multisim_fixed_source.  Added when the
-round's GPU budget was spent: their CPU halves are verified, the GPU halves run for the first time on the driver's box
-(hence the late file name: the rest of the suite runs first)."""
+"""GPU halves of the reference goldens pinned on the CPU at the end of round 2 (tests/test_oracle.py holds the CPU halves:
+the oracle and / or the unmodified reference behind ref_driver reproduce the committed results_true.dat of)
+
+  test_2d_gradient_linear_source, test_split_segments, test_split_segments_cmfd, test_forward_3D_lattice_symmetry,
+  test_cmfd_pwr_assembly, test_cmfd_vacuum_boundary, test_cmfd_periodic_boundaries, test_cmfd_linear_source,
+  test_cmfd_restart, test_transport_stabilization, test_axial_segmentation, test_cmfd_axial_interpolation_average,
+  test_cmfd_axial_interpolation_centroid, test_OTF_transport, test_multisim_simple, test_multisim_linear_source,
+  test_multisim_cmfd, test_multisim_num_azim, test_multisim_materials, test_multisim_num_groups,
+  test_multisim_fixed_source
+
+and the fission-rate test ADVICE r1 asked for.  Written when the round's GPU budget was spent: the CPU halves are
+verified, these run for the first time on the driver's box (hence the late file name: the rest of the suite runs
+first, and every GPU run here is a child process with a time limit)."""
 import hashlib
 import json
 import os
